@@ -1,0 +1,81 @@
+"""ctypes binding of the C-ABI library ``lib/libgnnfd_b200.so`` (declared in include/gnnfd_b200.h).
+
+There is deliberately no fallback: if the library is missing or an entry point is absent the import
+fails loudly, and every op raises ``RuntimeError`` on a non-zero status.  Build with
+``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C gnn_fluid_dynamics_b200/csrc``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgnnfd_b200.so")
+
+PREC_F32, PREC_BF16X3, PREC_BF16X1, PREC_FP16X2, PREC_FP16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"f32": PREC_F32, "bf16x3": PREC_BF16X3, "bf16x1": PREC_BF16X1,
+              "fp16x2": PREC_FP16X2, "fp16x3": PREC_FP16X3}
+ACT_SILU, ACT_TANH = 0, 1
+SEG_DIRECT, SEG_GATHER, SEG_SUM2, SEG_DIFF2, SEG_MEAN3 = 0, 1, 2, 3, 4
+
+EXPORTS = [
+    "gnnfd_abi_version", "gnnfd_last_error", "gnnfd_index_narrow", "gnnfd_csr_workspace_bytes",
+    "gnnfd_csr_build", "gnnfd_segment_sum", "gnnfd_mlp_forward", "gnnfd_pack_mlp_bytes",
+    "gnnfd_pack_mlp",
+]
+
+
+class Segment(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("idx", C.c_void_p * 3), ("ld", C.c_int32), ("col", C.c_int32),
+                ("width", C.c_int32), ("mode", C.c_int32)]
+
+
+class MlpArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("n_seg", C.c_int32), ("seg", Segment * 3),
+        ("k_in", C.c_int32), ("hidden", C.c_int32), ("n_out", C.c_int32),
+        ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("w3", C.c_void_p), ("b3", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+        ("has_ln", C.c_int32), ("ln_eps", C.c_float), ("act", C.c_int32),
+        ("mul", C.c_void_p), ("residual", C.c_void_p), ("out_raw", C.c_void_p),
+        ("out_sum", C.c_void_p), ("packed", C.c_void_p), ("precision", C.c_int32),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA library of gnn_fluid_dynamics_b200 is not built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+            "There is no CPU or PyTorch fallback for this path.")
+    lib = C.CDLL(LIB_PATH)
+    missing = [s for s in EXPORTS if not hasattr(lib, s)]
+    if missing:
+        raise ImportError(f"{LIB_PATH} does not export {missing}")
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.gnnfd_abi_version.restype = C.c_int
+    lib.gnnfd_last_error.restype = C.c_char_p
+    lib.gnnfd_index_narrow.argtypes = [vp, vp, i64, i64, vp, vp]
+    lib.gnnfd_csr_workspace_bytes.argtypes = [i64, i64]
+    lib.gnnfd_csr_workspace_bytes.restype = C.c_size_t
+    lib.gnnfd_csr_build.argtypes = [vp, i64, i64, vp, vp, vp, C.c_size_t, vp]
+    lib.gnnfd_segment_sum.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, i64, vp, vp, i64, vp, i32, vp]
+    lib.gnnfd_mlp_forward.argtypes = [C.POINTER(MlpArgs), vp]
+    lib.gnnfd_pack_mlp_bytes.argtypes = [i32, i32, i32, i32]
+    lib.gnnfd_pack_mlp_bytes.restype = C.c_size_t
+    lib.gnnfd_pack_mlp.argtypes = [C.POINTER(MlpArgs), vp, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("gnnfd_abi_version",):
+            pass
+    if lib.gnnfd_abi_version() != 1:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.gnnfd_abi_version()} != 1; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with status {rc}: {lib.gnnfd_last_error().decode()}")

@@ -1,0 +1,66 @@
+// Shared helpers for the gnnfd_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gnnfd_b200.h"
+
+namespace gnnfd {
+
+void set_error(const char *fmt, ...);
+
+#define GNNFD_CHECK_ARG(cond, msg)                 \
+  do {                                             \
+    if (!(cond)) {                                 \
+      gnnfd::set_error("%s: %s", __func__, msg);   \
+      return GNNFD_E_BADARG;                       \
+    }                                              \
+  } while (0)
+
+#define GNNFD_CUDA(call)                                                               \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      gnnfd::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e_));  \
+      return GNNFD_E_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+#define GNNFD_LAUNCH_CHECK()                                                           \
+  do {                                                                                 \
+    cudaError_t e_ = cudaGetLastError();                                               \
+    if (e_ != cudaSuccess) {                                                           \
+      gnnfd::set_error("%s: launch failed: %s", __func__, cudaGetErrorString(e_));     \
+      return GNNFD_E_CUDA;                                                             \
+    }                                                                                  \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// exact-path activations (IEEE expf / tanhf); the tensor-core path uses the fast variants
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+__device__ __forceinline__ float act_f(float v, int act) {
+  return act == GNNFD_ACT_SILU ? silu_f(v) : tanhf(v);
+}
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanh_fast(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float *p) {
+  return __ldg(reinterpret_cast<const float4 *>(p));
+}
+
+}  // namespace gnnfd

@@ -1,0 +1,69 @@
+// C-ABI entry points for the fused MLP block: argument validation + precision dispatch.
+#include "common.cuh"
+
+namespace gnnfd {
+int mlp_forward_f32(const gnnfd_mlp_args *args, cudaStream_t stream);
+int mlp_forward_tc(const gnnfd_mlp_args *args, cudaStream_t stream);
+size_t pack_mlp_bytes_tc(int k_in, int hidden, int n_out, int precision);
+int pack_mlp_tc(const gnnfd_mlp_args *args, void *packed_out, cudaStream_t stream);
+
+int validate_mlp_args(const gnnfd_mlp_args *a) {
+  GNNFD_CHECK_ARG(a != nullptr, "null args");
+  GNNFD_CHECK_ARG(a->rows >= 0, "negative rows");
+  GNNFD_CHECK_ARG(a->hidden == 128, "hidden width must be 128");
+  GNNFD_CHECK_ARG(a->n_seg >= 1 && a->n_seg <= 3, "n_seg must be 1..3");
+  GNNFD_CHECK_ARG(a->n_out >= 1 && a->n_out <= 128, "n_out out of range");
+  GNNFD_CHECK_ARG(a->act == GNNFD_ACT_SILU || a->act == GNNFD_ACT_TANH, "unknown activation");
+  int k = 0;
+  for (int s = 0; s < a->n_seg; ++s) {
+    const gnnfd_segment &sg = a->seg[s];
+    GNNFD_CHECK_ARG(sg.width > 0 && sg.ld >= sg.col + sg.width && sg.col >= 0, "bad segment geometry");
+    GNNFD_CHECK_ARG(sg.mode >= GNNFD_SEG_DIRECT && sg.mode <= GNNFD_SEG_MEAN3, "bad segment mode");
+    if (a->rows > 0) {
+      GNNFD_CHECK_ARG(sg.src != nullptr, "null segment source");
+      if (sg.mode >= GNNFD_SEG_GATHER) GNNFD_CHECK_ARG(sg.idx[0] != nullptr, "null gather index 0");
+      if (sg.mode >= GNNFD_SEG_SUM2) GNNFD_CHECK_ARG(sg.idx[1] != nullptr, "null gather index 1");
+      if (sg.mode == GNNFD_SEG_MEAN3) GNNFD_CHECK_ARG(sg.idx[2] != nullptr, "null gather index 2");
+    }
+    k += sg.width;
+  }
+  GNNFD_CHECK_ARG(k == a->k_in, "segment widths do not add up to k_in");
+  GNNFD_CHECK_ARG(a->w1 && a->w2 && a->w3, "null weight");
+  GNNFD_CHECK_ARG(!a->out_sum || a->residual, "out_sum requires residual");
+  GNNFD_CHECK_ARG(a->out_raw || a->out_sum || a->rows == 0, "no output requested");
+  return GNNFD_OK;
+}
+}  // namespace gnnfd
+
+using namespace gnnfd;
+
+extern "C" int gnnfd_mlp_forward(const gnnfd_mlp_args *args, void *stream) {
+  int rc = validate_mlp_args(args);
+  if (rc != GNNFD_OK) return rc;
+  if (args->rows == 0) return GNNFD_OK;
+  switch (args->precision) {
+    case GNNFD_PREC_F32:
+      return mlp_forward_f32(args, (cudaStream_t)stream);
+    case GNNFD_PREC_BF16X3:
+    case GNNFD_PREC_BF16X1:
+    case GNNFD_PREC_FP16X2:
+    case GNNFD_PREC_FP16X3:
+      return mlp_forward_tc(args, (cudaStream_t)stream);
+    default:
+      set_error("gnnfd_mlp_forward: unknown precision %d", args->precision);
+      return GNNFD_E_BADARG;
+  }
+}
+
+extern "C" size_t gnnfd_pack_mlp_bytes(int32_t k_in, int32_t hidden, int32_t n_out, int32_t precision) {
+  if (precision == GNNFD_PREC_F32) return 0;
+  return pack_mlp_bytes_tc(k_in, hidden, n_out, precision);
+}
+
+extern "C" int gnnfd_pack_mlp(const gnnfd_mlp_args *args, void *packed_out, void *stream) {
+  int rc = validate_mlp_args(args);
+  if (rc != GNNFD_OK) return rc;
+  if (args->precision == GNNFD_PREC_F32) return GNNFD_OK;
+  GNNFD_CHECK_ARG(packed_out != nullptr, "null pack buffer");
+  return pack_mlp_tc(args, packed_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,95 @@
+// Deterministic segment sum over receiver-sorted CSR rows (kernel (c) of BASELINE.json: north_star).
+//
+// Replaces torch_scatter.scatter_add's atomics: every output row is owned by one group of lanes that
+// walks the row's contributions in ascending source position - the same order the CPU scatter_add
+// uses - so results are reproducible and match the sequential CPU sum bit for bit.
+// HBM traffic: each contribution is one coalesced `width`-float read (float4 per lane), each output
+// row one coalesced write; the CSR costs 4 B per contribution + 4 B per row.
+#include "common.cuh"
+
+namespace gnnfd {
+
+template <int LPR>  // lanes per output row: width = 4 * LPR floats
+__global__ void __launch_bounds__(256) segment_sum_kernel(
+    const float *__restrict__ a, const float *__restrict__ b, int ld_a, int ld_b, int col_a, int col_b,
+    float sign_b, int64_t n_half, const int32_t *__restrict__ offsets, const int32_t *__restrict__ perm,
+    int64_t n_rows, float *__restrict__ out, int ld_out) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t row = warp * RPW + lane / LPR;
+  if (row >= n_rows) return;
+  const int beg = offsets[row], end = offsets[row + 1];
+  const float *pa = a + col_a + sub * 4;
+  const float *pb = b + col_b + sub * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = beg; p < end; p += 4) {
+    float4 v[4];
+    float s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s[j] = 0.f;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p + j < end) {
+        int64_t q = perm[p + j];
+        if (q < n_half) {
+          v[j] = ldg_f4(pa + q * ld_a);
+          s[j] = 1.0f;
+        } else {
+          v[j] = ldg_f4(pb + (q - n_half) * ld_b);
+          s[j] = sign_b;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (p + j < end) {  // sequential order; +-1 scaling is exact
+        acc.x += s[j] * v[j].x;
+        acc.y += s[j] * v[j].y;
+        acc.z += s[j] * v[j].z;
+        acc.w += s[j] * v[j].w;
+      }
+    }
+  }
+  *reinterpret_cast<float4 *>(out + row * (int64_t)ld_out + sub * 4) = acc;
+}
+
+}  // namespace gnnfd
+
+using namespace gnnfd;
+
+extern "C" int gnnfd_segment_sum(const float *a, const float *b, int32_t ld_a, int32_t ld_b,
+                                 int32_t col_a, int32_t col_b, int32_t width, float sign_b,
+                                 int64_t n_half, const int32_t *offsets, const int32_t *perm,
+                                 int64_t n_rows, float *out, int32_t ld_out, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNNFD_CHECK_ARG(n_rows >= 0 && n_half >= 0, "negative size");
+  if (n_rows == 0) return GNNFD_OK;
+  GNNFD_CHECK_ARG(a && b && offsets && out, "null pointer");
+  GNNFD_CHECK_ARG(perm || n_half == 0, "null perm");
+  GNNFD_CHECK_ARG((ld_a % 4) == 0 && (ld_b % 4) == 0 && (ld_out % 4) == 0 && (col_a % 4) == 0 &&
+                      (col_b % 4) == 0,
+                  "strides/columns must be multiples of 4 floats");
+  GNNFD_CHECK_ARG(sign_b == 1.0f || sign_b == -1.0f, "sign_b must be +-1");
+  const int lpr = width / 4;
+  GNNFD_CHECK_ARG(width > 0 && (width % 4) == 0 && lpr <= 32 && (32 % lpr) == 0,
+                  "width must be 4*2^k <= 128");
+  const int rpw = 32 / lpr;
+  int64_t warps = (n_rows + rpw - 1) / rpw;
+  int blocks = (int)((warps * 32 + 255) / 256);
+#define LAUNCH(L)                                                                                   \
+  segment_sum_kernel<L><<<blocks, 256, 0, stream>>>(a, b, ld_a, ld_b, col_a, col_b, sign_b, n_half, \
+                                                    offsets, perm, n_rows, out, ld_out)
+  switch (lpr) {
+    case 32: LAUNCH(32); break;
+    case 16: LAUNCH(16); break;
+    case 8: LAUNCH(8); break;
+    case 4: LAUNCH(4); break;
+    case 2: LAUNCH(2); break;
+    default: LAUNCH(1); break;
+  }
+#undef LAUNCH
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}

@@ -1,0 +1,110 @@
+"""Conservative family on the B200 kernels - drop-in for reference ``src/models/Conservative.py``
+(ConservativeA): symmetric + antisymmetric face encodings, sum-form face block, signed direct
+edge->cell aggregation (Conservative.py:191-262).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .. import processor as P
+from .._lib import ACT_TANH
+from ..topology import get_topology
+from .base import build_mlp, build_mlp_antisym, col, n_class_types
+from .Fvgn import FvgnA
+
+
+class ConservativeA(FvgnA):
+    family = "cons_a"
+    _registry_overrides = {
+        "face_velocity_diff_char": lambda graphs: torch.norm(graphs[1].x_asym[:, 0:2], dim=1)}
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.encoder = self.Encoder(config, self.input_sizes, self.hidden_size)
+        self.processer_list = nn.ModuleList(
+            [self.GN_Block(config, self.hidden_size) for _ in range(config.model.mp_num)])
+        self.decoder = self.Decoder(config, self.hidden_size, self.output_sizes)
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 3 + n_class_types(dataset), 0], [0, 5, 0])   # Conservative.py:62-64
+
+    @classmethod
+    def normalisation_tables(cls):   # Conservative.py:105-145
+        z = "z_score"
+        kinds = {k: z for k in ["cell_velocity_x", "cell_velocity_y", "cell_velocity_change_x",
+                                "cell_velocity_change_y", "face_area", "face_adjacent_distance",
+                                "face_velocity_x", "face_velocity_y", "face_pressure"]}
+        kinds["face_velocity_diff_char"] = "mean_scale"
+        inputs = [(0, "x", col(0), "cell_velocity_x"), (0, "x", col(1), "cell_velocity_y"),
+                  (1, "x_asym", col(0, 2), "face_velocity_diff_char"),
+                  (1, "x_symm", col(0), "face_area"), (1, "x_symm", col(2), "face_adjacent_distance"),
+                  (0, "y", col(0), "cell_velocity_change_x"), (0, "y", col(1), "cell_velocity_change_y"),
+                  (1, "y", col(0), "face_velocity_x"), (1, "y", col(1), "face_velocity_y"),
+                  (1, "y", col(2), "face_pressure")]
+        outputs = [(0, col(0), "cell_velocity_change_x"), (0, col(1), "cell_velocity_change_y"),
+                   (1, col(0), "face_velocity_x"), (1, col(1), "face_velocity_y"),
+                   (1, col(2), "face_pressure")]
+        return kinds, inputs, outputs
+
+    def encode_process_decode(self, c_x, f_x_symm, f_x_asym, topo, hook=None):
+        prec = self.prec
+        e = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
+        e_asym = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
+        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        # GN_Block returns a fresh Data without edge_attr_asym, so the asym multiply fires in block 0
+        # only (Conservative.py:220, 232-233); run_processor reproduces that.
+        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, e_asym=e_asym, hook=hook)
+        return x, e, P.mlp_rows(self.decoder.face_mlp, e, prec)
+
+    def forward(self, graphs, mode="rollout"):   # Conservative.py:164-189
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x_symm
+        c_graph.edge_attr_asym = f_graph.x_asym
+        topo = get_topology(graphs, need_cell_csr=True, two_hop=False)
+        _, _, edge_attr_out = self.encode_process_decode(c_graph.x, f_graph.x_symm, f_graph.x_asym, topo)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
+        output = [acc_pred, edge_attr_out, None]
+        if mode == "rollout":
+            output = self.normalizer.output(output, inverse=True)
+        return {"cell_velocity_change": output[0][:, 0:2], "face_velocity": output[1][:, :2],
+                "face_pressure": output[1][:, 2:3]}
+
+    def update_features(self, output, input_graphs):   # Conservative.py:147-162
+        c_graph, f_graph, v_graph = input_graphs
+        c_graph.x = output["cell_velocity"].detach()
+        u = c_graph.x[:, :2]
+        dv = u[c_graph.edge_index[0]] - u[c_graph.edge_index[1]]
+        mask = ((f_graph.type == 2) | (f_graph.type == 1)).squeeze(-1)
+        dv[mask] = f_graph.y[:, 0:2][mask]
+        f_graph.x_asym[:, 0:2] = dv
+        return [c_graph, f_graph, v_graph]
+
+    class Encoder(nn.Module):   # Conservative.py:191-202
+        def __init__(self, config, input_sizes, hidden_size):
+            super().__init__()
+            self.faceA_mlp = build_mlp_antisym(config, 4, hidden_size, hidden_size)
+            self.faceS_mlp = build_mlp(config, input_sizes[1], hidden_size, hidden_size)
+            self.cell_mlp = build_mlp(config, input_sizes[0], hidden_size, hidden_size)
+
+    class GN_Block(nn.Module):   # Conservative.py:204-254
+        family = "cons_a"
+
+        def __init__(self, config, hidden_size):
+            super().__init__()
+            self.face_block = self.Face_Block(config, hidden_size)
+            self.cell_block = self.Cell_Block(config, hidden_size)
+
+        class Face_Block(nn.Module):
+            def __init__(self, config, hidden_size):
+                super().__init__()
+                self.face_mlp = build_mlp(config, hidden_size * 2, hidden_size, hidden_size)
+
+        class Cell_Block(nn.Module):
+            def __init__(self, config, hidden_size, mp_times=2):
+                super().__init__()
+                self.cell_mlp = build_mlp(config, hidden_size * 2, hidden_size, hidden_size)
+                self.mp_times = mp_times

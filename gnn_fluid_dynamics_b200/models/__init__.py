@@ -1,0 +1,10 @@
+"""B200-native drop-ins for the reference's ``src/models`` modules (same module and class names, so
+``config.model.module = "gnn_fluid_dynamics_b200.models.Fvgn"``, ``config.model.name = "FvgnA"``)."""
+from .Fvgn import FvgnA  # noqa: F401
+from .Mgn import MgnA  # noqa: F401
+from .Flux import FluxA  # noqa: F401
+from .Conservative import ConservativeA  # noqa: F401
+from .VertPot import VertPotA  # noqa: F401
+
+MODEL_CLASSES = {"FvgnA": FvgnA, "MgnA": MgnA, "FluxA": FluxA, "ConservativeA": ConservativeA,
+                 "VertPotA": VertPotA}

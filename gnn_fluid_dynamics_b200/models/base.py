@@ -1,0 +1,176 @@
+"""Host-side mirror of the reference's model interface (``src/models/Model.py``).
+
+Same constructor ``Model(config, loss_func, dataset, stats)``, same ``forward(graphs, mode) -> dict``,
+``loss``, ``update_features``, classmethods ``get_feature_sizes`` / ``get_normalisation_map`` and - the
+hard constraint - the same ``state_dict`` keys and shapes, so the reference's checkpoints load and
+``config.model.module = "gnn_fluid_dynamics_b200.models.Fvgn"`` is the whole switch-over
+(``src/train.py:348-349``).  The parameters live in ordinary ``nn.Sequential`` / ``nn.LayerNorm``
+containers (``monitoring.py:18`` iterates ``decoder.face_mlp``); the arithmetic of
+encoder/processor/decoder is done by the CUDA kernels through ``processor.py``.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+
+import torch
+from torch import nn
+
+from .._lib import PRECISIONS
+
+# default GEMM arithmetic of the hot path; "f32" = exact CUDA-core path, others = tcgen05
+DEFAULT_PRECISION = "f32"
+
+
+def build_mlp(config, in_size, hidden_size, out_size, norm_layer=True):
+    """Parameter container with the reference's layout (Model.py:12-40): ``Sequential(Linear, SiLU,
+    Linear, SiLU, Linear)`` (indices 0,2,4), wrapped as ``Sequential(mlp, LayerNorm)`` when normalised.
+    Dropout (only inserted by the reference when ``dropout_rate > 0``; 0.0 in every shipped config)
+    is not supported on the fused path."""
+    rate = getattr(getattr(config, "training", None), "dropout_rate", 0.0) or 0.0
+    if rate > 0:
+        raise NotImplementedError("dropout_rate > 0 is not supported by the fused B200 path")
+    mlp = nn.Sequential(nn.Linear(in_size, hidden_size), nn.SiLU(),
+                        nn.Linear(hidden_size, hidden_size), nn.SiLU(),
+                        nn.Linear(hidden_size, out_size))
+    if norm_layer:
+        return nn.Sequential(mlp, nn.LayerNorm(normalized_shape=out_size))
+    return mlp
+
+
+def build_mlp_antisym(config, in_size, hidden_size, out_size):
+    """Bias-free Tanh MLP, no LayerNorm (Conservative.py:31-43; every call site passes
+    norm_layer=False)."""
+    return nn.Sequential(nn.Linear(in_size, hidden_size, bias=False), nn.Tanh(),
+                         nn.Linear(hidden_size, hidden_size, bias=False), nn.Tanh(),
+                         nn.Linear(hidden_size, out_size, bias=False))
+
+
+class Normalizer(nn.Module):
+    """Per-column affine (de)normalisation with the reference's buffer names ``{key}_{stat}``
+    (normalisation.py:207-278).  ``inputs`` rows are (graph index, attribute, column slice, stats
+    key); ``outputs`` rows are (output index, column slice, stats key); ``kinds`` maps a stats key to
+    z_score | mean_scale | std_scale | max_scale | min_max (normalisation.py:281-322).
+    """
+
+    def __init__(self, stats, kinds, inputs, outputs):
+        super().__init__()
+        self.kinds = dict(kinds)
+        self.inputs = list(inputs)
+        self.outputs = list(outputs)
+        for key, stat in stats.items():
+            for name, value in stat.items():
+                self.register_buffer(f"{key}_{name}", torch.tensor(value, dtype=torch.float))
+
+    def _apply_one(self, data, key, inverse):
+        kind = self.kinds[key]
+        g = lambda s: getattr(self, f"{key}_{s}")
+        if kind == "z_score":
+            scale = torch.clamp(g("std"), min=1e-8) + 1e-8
+            return data * scale + g("mean") if inverse else (data - g("mean")) / scale
+        if kind == "mean_scale":
+            scale = g("mean") + 1e-8
+            return data * scale if inverse else data / scale
+        if kind == "std_scale":
+            scale = g("std") + 1e-8
+            return data * scale if inverse else data / scale
+        if kind == "max_scale":
+            scale = g("max") + 1e-8
+            return data * scale if inverse else data / scale
+        if kind == "min_max":
+            rng = g("max") - g("min") + 1e-8
+            return data * rng + g("min") if inverse else (data - g("min")) / rng
+        raise ValueError(kind)
+
+    def input(self, graphs, inverse=False):
+        """In place on the passed graphs, like the reference (normalisation.py:255-264)."""
+        for gi, attr, cols, key in self.inputs:
+            t = getattr(graphs[gi], attr, None)
+            if t is None or t.dim() < 2 or t.shape[1] < cols.stop:
+                continue
+            t[:, cols] = self._apply_one(t[:, cols], key, inverse)
+        return graphs
+
+    def output(self, outputs, inverse=False):
+        for oi, cols, key in self.outputs:
+            t = outputs[oi]
+            if t is None or t.shape[1] < cols.stop:
+                continue
+            t[:, cols] = self._apply_one(t[:, cols], key, inverse)
+        return outputs
+
+
+def col(i, j=None):
+    return slice(i, i + 1 if j is None else j)
+
+
+class Model(nn.Module, ABC):
+    """Base class: configuration, feature sizes, normaliser, precision switch."""
+    cell_grad_weights_use = False
+    face_grad_weights_use = False
+    pushforward_use = False
+    family = None  # processor data-flow, see processor.py
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__()
+        self.config = config
+        self.loss_func = loss_func
+        self.hidden_size = config.model.hidden_width
+        if self.hidden_size != 128:
+            raise NotImplementedError("the B200 kernels are built for hidden_width = 128 "
+                                      "(every shipped reference config, config/train.json:27)")
+        self.input_sizes, self.output_sizes = self.get_feature_sizes(dataset)
+        kinds, inputs, outputs = self.normalisation_tables()
+        self.normalizer = Normalizer(stats, kinds, inputs, outputs)
+        self.precision = getattr(config.model, "precision", None) or DEFAULT_PRECISION
+
+    @property
+    def prec(self) -> int:
+        return PRECISIONS[self.precision]
+
+    def set_precision(self, name: str):
+        if name not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision = name
+        return self
+
+    @classmethod
+    @abstractmethod
+    def get_feature_sizes(cls, dataset):
+        ...
+
+    @classmethod
+    @abstractmethod
+    def normalisation_tables(cls):
+        """(kinds {stats key: kind}, inputs [(graph, attr, cols, key)], outputs [(out, cols, key)])."""
+        ...
+
+    @classmethod
+    def get_normalisation_map(cls):
+        """The reference's (registry, inputs, outputs) dict-of-lambdas form of the same tables
+        (consumed by its statistics accumulator, ``src/datasets/DataSet.py:318``)."""
+        kinds, inputs, outputs = cls.normalisation_tables()
+        registry = {}
+        for gi, attr, cols, key in inputs:
+            registry.setdefault(key, ((lambda g, gi=gi, attr=attr, cols=cols: getattr(g[gi], attr)[:, cols]),
+                                      kinds[key]))
+        for key, fn in getattr(cls, "_registry_overrides", {}).items():
+            registry[key] = (fn, kinds[key])
+        for key, kind in kinds.items():
+            registry.setdefault(key, ((lambda g: None), kind))
+        ins = {f"in{i}_{key}": ((lambda g, gi=gi, attr=attr, cols=cols: getattr(g[gi], attr)[:, cols]), key)
+               for i, (gi, attr, cols, key) in enumerate(inputs)}
+        outs = {f"out{i}_{key}": ((lambda o, oi=oi, cols=cols: o[oi][:, cols]), key)
+                for i, (oi, cols, key) in enumerate(outputs)}
+        return registry, ins, outs
+
+    @abstractmethod
+    def forward(self, graphs, mode="train"):
+        ...
+
+    def count_parameters(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+
+def n_class_types(dataset) -> int:
+    ct = getattr(dataset, "class_types", None)
+    return len(ct) if ct is not None else 5

@@ -1,0 +1,148 @@
+"""Encoder / GN_Block / decoder data-flows on the CUDA kernels (the product hot path).
+
+One function per reference sub-module; each issues only C-ABI kernel calls (``ops``).  Families and
+their block order follow SURVEY.md section 8a:
+
+  fvgn    : vertex segment-sum(e) -> node MLP(x, mean3) -> edge MLP(e, x'[row], x'[col])   Fvgn.py:274-325
+  mgn     : edge MLP(e, x[row], x[col]) -> vertex segment-sum(e') -> node MLP               Mgn.py:216-267
+  cons_a  : edge MLP(e, x[row]+x[col]) [* asym] -> signed cell segment-sum(e') -> node MLP  Conservative.py:210-254
+  vertpot : fvgn + full-width vertex sum of e'                                              VertPot.py:195-222
+
+The second sub-block consumes the first one's RAW output; both residuals are applied by the
+kernels' epilogues (out_sum = residual + out), so no clone / add pass exists.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import ACT_SILU, ACT_TANH, PREC_F32, SEG_DIRECT, SEG_GATHER, SEG_MEAN3, SEG_SUM2
+from .ops import MLPWeights, Seg
+from .topology import MeshTopology
+
+H = 128
+
+
+def _split_mlp(seq: torch.nn.Module):
+    """(inner Sequential of Linear/act/Linear/act/Linear, LayerNorm or None)."""
+    if isinstance(seq[0], torch.nn.Sequential):
+        return seq[0], seq[1]
+    return seq, None
+
+
+def weights_of(seq: torch.nn.Module, act: int = ACT_SILU) -> MLPWeights:
+    """MLPWeights view of a reference-layout MLP module, cached on the module and refreshed when a
+    parameter is replaced or modified in place (``_version``), e.g. by an optimizer step."""
+    inner, ln = _split_mlp(seq)
+    lin = [m for m in inner if isinstance(m, torch.nn.Linear)]
+    params = [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias]
+    if ln is not None:
+        params += [ln.weight, ln.bias]
+    key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+    cached = getattr(seq, "_gnnfd_w", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    d = lambda p: None if p is None else p.detach()
+    w = MLPWeights(w1=d(lin[0].weight), b1=d(lin[0].bias), w2=d(lin[1].weight), b2=d(lin[1].bias),
+                   w3=d(lin[2].weight), b3=d(lin[2].bias),
+                   ln_w=d(ln.weight) if ln is not None else None,
+                   ln_b=d(ln.bias) if ln is not None else None,
+                   has_ln=ln is not None, ln_eps=ln.eps if ln is not None else 1e-5, act=act)
+    object.__setattr__(seq, "_gnnfd_w", (key, w))
+    return w
+
+
+# --- sub-blocks -----------------------------------------------------------------------------------
+
+def vertex_half_sum(e: torch.Tensor, topo: MeshTopology) -> torch.Tensor:
+    """vsum[V, H/2]: half 0 of each face latent onto its first vertex, half 1 onto its second
+    (scatter_add of Fvgn.py:312-314) as a deterministic CSR segment sum."""
+    return ops.segment_sum(e, e, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm,
+                           topo.n_vertices)
+
+
+def node_mlp_two_hop(seq, x, vsum, topo, prec, want_raw, residual=True):
+    """x' = cell_mlp(cat[x, (vsum[vf0]+vsum[vf1]+vsum[vf2])/3])  (Fvgn.py:316-323)."""
+    segs = [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf)]
+    return ops.mlp_forward(segs, weights_of(seq), x.shape[0], prec, residual=x if residual else None,
+                           want_raw=want_raw, want_sum=residual)
+
+
+def edge_mlp_concat(seq, e, x_src, topo, prec, want_raw, residual=True):
+    """e' = face_mlp(cat[e, x[row], x[col]])  (Fvgn.py:292-296, Mgn.py:234-238)."""
+    segs = [Seg(e), Seg(x_src, SEG_GATHER, (topo.row,)), Seg(x_src, SEG_GATHER, (topo.col,))]
+    return ops.mlp_forward(segs, weights_of(seq), e.shape[0], prec, residual=e if residual else None,
+                           want_raw=want_raw, want_sum=residual)
+
+
+def edge_mlp_sum(seq, e, x_src, topo, prec, mul=None):
+    """e' = face_mlp(cat[e, x[row] + x[col]]) [* e_asym]  (Conservative.py:228-234)."""
+    segs = [Seg(e), Seg(x_src, SEG_SUM2, (topo.row, topo.col))]
+    return ops.mlp_forward(segs, weights_of(seq), e.shape[0], prec, mul=mul, residual=e,
+                           want_raw=True, want_sum=True)
+
+
+def cell_signed_sum(e_raw: torch.Tensor, topo: MeshTopology) -> torch.Tensor:
+    """agg[c] = sum_{col(k)=c} e_k - sum_{row(k)=c} e_k  (Conservative.py:244-249)."""
+    off, perm = topo.build_cell_csr()
+    return ops.segment_sum(e_raw, e_raw, 0, 0, H, -1.0, off, perm, topo.n_cells)
+
+
+def vertex_full_sum(e_raw: torch.Tensor, topo: MeshTopology, n_rows: int) -> torch.Tensor:
+    """Vertex_Block (VertPot.py:217-222): full-width sum with ``n_rows`` (= N cells) output rows."""
+    return ops.segment_sum(e_raw, e_raw, 0, 0, H, 1.0, topo.vertex_csr_rows(n_rows), topo.vtx_perm, n_rows)
+
+
+# --- encoder / block / decoder ------------------------------------------------------------------
+
+def mlp_rows(seq, src: torch.Tensor, prec: int, act: int = ACT_SILU) -> torch.Tensor:
+    """Plain per-row MLP (encoder / decoder heads)."""
+    src = src.contiguous()
+    out, _ = ops.mlp_forward([Seg(src)], weights_of(seq, act), src.shape[0], prec)
+    return out
+
+
+def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
+             e_asym: Optional[torch.Tensor] = None, want_vertex: bool = False):
+    """One GN_Block -> (x_new, e_new, vertex_x or None)."""
+    if family == "fvgn":
+        vsum = vertex_half_sum(e, topo)
+        x_raw, x_new = node_mlp_two_hop(block.cell_block.cell_mlp, x, vsum, topo, prec, want_raw=True)
+        _, e_new = edge_mlp_concat(block.face_block.face_mlp, e, x_raw, topo, prec, want_raw=False)
+        return x_new, e_new, None
+    if family == "mgn":
+        e_raw, e_new = edge_mlp_concat(block.face_block.face_mlp, e, x, topo, prec, want_raw=True)
+        vsum = vertex_half_sum(e_raw, topo)
+        _, x_new = node_mlp_two_hop(block.cell_block.cell_mlp, x, vsum, topo, prec, want_raw=False)
+        return x_new, e_new, None
+    if family == "cons_a":
+        e_raw, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec, mul=e_asym)
+        agg = cell_signed_sum(e_raw, topo)
+        _, x_new = ops.mlp_forward([Seg(x), Seg(agg)], weights_of(block.cell_block.cell_mlp),
+                                   x.shape[0], prec, residual=x, want_raw=False, want_sum=True)
+        return x_new, e_new, None
+    if family == "vertpot":
+        vsum = vertex_half_sum(e, topo)
+        x_raw, x_new = node_mlp_two_hop(block.node_block.cell_mlp, x, vsum, topo, prec, want_raw=True)
+        e_raw, e_new = edge_mlp_concat(block.edge_block.face_mlp, e, x_raw, topo, prec, want_raw=want_vertex)
+        vx = vertex_full_sum(e_raw, topo, x.shape[0]) if want_vertex else None
+        return x_new, e_new, vx
+    raise ValueError(f"unknown family {family!r}")
+
+
+def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=None, hook=None):
+    """All GN_Blocks.  VertPot's vertex sum is only live after the last block (VertPot.py:208: it is
+    overwritten every block and never fed back), so it is computed once."""
+    vx = None
+    n = len(blocks)
+    for i, blk in enumerate(blocks):
+        x, e, vx_i = gn_block(family, blk, x, e, topo, prec,
+                              e_asym=e_asym if (family == "cons_a" and i == 0) else None,
+                              want_vertex=(family == "vertpot" and i == n - 1))
+        if vx_i is not None:
+            vx = vx_i
+        if hook is not None:
+            hook(i, x, e)
+    return x, e, vx

@@ -1,0 +1,67 @@
+"""Deterministic parameters / statistics shared by the golden generator, the tests and the bench.
+
+Parameters are a pure function of their state_dict key (numpy RandomState seeded by crc32 of the
+key), so the reference model, the oracle and the CUDA modules get bit-identical weights without
+shipping an 8.8 MB checkpoint per model and without depending on module construction order.
+Distributions follow PyTorch's defaults: Linear weight and bias
+U(+-1/sqrt(fan_in)); LayerNorm affine is perturbed away from (1, 0) so that it is exercised.
+"""
+from __future__ import annotations
+
+import zlib
+
+import numpy as np
+import torch
+
+STAT_KEYS = [
+    "cell_velocity_x", "cell_velocity_y", "cell_velocity_change_x", "cell_velocity_change_y",
+    "cell_pressure", "face_velocity_difference_x", "face_velocity_difference_y",
+    "face_edge_vector_x", "face_edge_vector_y", "face_area", "face_velocity_x", "face_velocity_y",
+    "face_pressure", "face_flux", "face_adjacent_distance", "face_velocity_diff_char",
+    "cell_velocity_char",
+]
+
+
+def default_stats():
+    """Non-trivial per-key statistics (mean/std/min/max) so (de)normalisation is exercised."""
+    out = {}
+    for i, k in enumerate(STAT_KEYS):
+        out[k] = {"mean": 0.05 * (i % 5) + 0.1, "std": 1.0 + 0.1 * (i % 4), "min": -1.0, "max": 1.0}
+    return out
+
+
+def _rs(key: str, seed: int) -> np.random.RandomState:
+    return np.random.RandomState((zlib.crc32(key.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
+
+
+@torch.no_grad()
+def fill_state_dict_deterministic(module: torch.nn.Module, seed: int = 1) -> None:
+    """Overwrite every Linear / LayerNorm / BatchNorm tensor of ``module`` in place."""
+    sd = module.state_dict()
+    for key, t in sd.items():
+        if "normalizer." in key:
+            continue
+        rs = _rs(key, seed)
+        leaf = key.rsplit(".", 1)[-1]
+        base = key.rsplit(".", 1)[0]
+        if leaf == "weight" and t.dim() == 2:
+            bound = 1.0 / np.sqrt(t.shape[1])
+            t.copy_(torch.from_numpy(rs.uniform(-bound, bound, size=tuple(t.shape)).astype(np.float32)))
+        elif leaf == "bias" and (base + ".weight") in sd and sd[base + ".weight"].dim() == 2:
+            bound = 1.0 / np.sqrt(sd[base + ".weight"].shape[1])
+            t.copy_(torch.from_numpy(rs.uniform(-bound, bound, size=tuple(t.shape)).astype(np.float32)))
+        elif leaf == "weight":          # LayerNorm / BatchNorm scale
+            t.copy_(torch.from_numpy((1.0 + 0.1 * rs.uniform(-1, 1, size=tuple(t.shape))).astype(np.float32)))
+        elif leaf == "bias":
+            t.copy_(torch.from_numpy((0.1 * rs.uniform(-1, 1, size=tuple(t.shape))).astype(np.float32)))
+        elif leaf == "running_mean":
+            t.fill_(0.2)
+        elif leaf == "running_var":
+            t.fill_(1.5)
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    """||a - b||_2 / ||b||_2 (the parity metric of BASELINE.json: north_star)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))

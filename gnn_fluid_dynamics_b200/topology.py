@@ -1,0 +1,112 @@
+"""Device-resident mesh topology consumed by the kernels: int32 index tensors + receiver-sorted CSRs.
+
+Built once per mesh (or per training batch) from the reference's graph objects:
+``c_graph.edge_index`` (cells of each face), ``v_graph.edge_index`` (vertices of each face, same
+column order), ``v_graph.face`` (vertices of each cell) - SURVEY.md Appendix A/B.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+
+
+class MeshTopology:
+    """``__gnnfd_shared__`` makes ``Data.clone()/to()`` pass the object by reference, so a topology
+    attached to ``v_graph.topology`` survives the per-step ``g.clone()`` of the rollout loop
+    (reference ``src/rollout.py:313``) without being rebuilt or copied."""
+
+    __gnnfd_shared__ = True
+
+    def __init__(self, c_edge_index: torch.Tensor, v_edge_index: Optional[torch.Tensor],
+                 v_face: Optional[torch.Tensor], n_cells: int, n_vertices: Optional[int],
+                 need_cell_csr: bool = False):
+        dev = c_edge_index.device
+        if dev.type != "cuda":
+            raise RuntimeError("MeshTopology needs CUDA tensors (no CPU fallback on this path)")
+        self.device = dev
+        self.n_cells = int(n_cells)
+        self.n_faces = int(c_edge_index.shape[1])
+        self.n_vertices = None if n_vertices is None else int(n_vertices)
+        cei = ops.index_narrow(c_edge_index, self.n_cells)
+        self._flags = [cei._gnnfd_range_flag]
+        self.row, self.col = cei[0], cei[1]          # contiguous views of the [2,E] tensor
+        self.vtx_offsets = self.vtx_perm = None
+        self.v0 = self.v1 = None
+        self.vf = None
+        if v_edge_index is not None:
+            vei = ops.index_narrow(v_edge_index, self.n_vertices)
+            self._flags.append(vei._gnnfd_range_flag)
+            self.v0, self.v1 = vei[0], vei[1]
+            # index vector cat[v_ei[0]; v_ei[1]] == the [2,E] tensor flattened row-major
+            self.vtx_offsets, self.vtx_perm = ops.csr_build(vei.reshape(-1), self.n_vertices)
+        if v_face is not None:
+            vf = ops.index_narrow(v_face, self.n_vertices)
+            self._flags.append(vf._gnnfd_range_flag)
+            self.vf = (vf[0], vf[1], vf[2])
+        self.cell_offsets = self.cell_perm = None
+        self._cell_index = None
+        if need_cell_csr:
+            self.build_cell_csr()
+        self._vtx_n_offsets = None
+
+    def build_cell_csr(self):
+        """CSR of cat[col; row] over cells (Conservative.py:244-245)."""
+        if self.cell_offsets is None:
+            idx = torch.cat([self.col, self.row])
+            self.cell_offsets, self.cell_perm = ops.csr_build(idx, self.n_cells)
+        return self.cell_offsets, self.cell_perm
+
+    def vertex_csr_rows(self, n_rows: int):
+        """Vertex CSR padded to ``n_rows`` >= V rows (Vertex_Block writes N rows, VertPot.py:221)."""
+        if n_rows == self.n_vertices:
+            return self.vtx_offsets
+        if self._vtx_n_offsets is None or self._vtx_n_offsets.numel() != n_rows + 1:
+            if n_rows < self.n_vertices:
+                raise RuntimeError("vertex_csr_rows: n_rows < n_vertices")
+            pad = self.vtx_offsets[-1:].expand(n_rows - self.n_vertices)
+            self._vtx_n_offsets = torch.cat([self.vtx_offsets, pad]).contiguous()
+        return self._vtx_n_offsets
+
+    def validate(self):
+        """Synchronising range check of every narrowed index tensor."""
+        bad = sum(int(f.item()) for f in self._flags)
+        if bad:
+            raise RuntimeError("MeshTopology: an index is out of range for its node count")
+        return self
+
+    @classmethod
+    def from_graphs(cls, graphs, need_cell_csr: bool = False, two_hop: bool = True) -> "MeshTopology":
+        c, f, v = graphs
+        n_cells = c.x.shape[0]
+        if two_hop:
+            n_vertices = v.num_nodes
+            if n_vertices is None:
+                raise RuntimeError("v_graph.num_nodes unavailable (needs pos or x)")
+            return cls(c.edge_index, v.edge_index, v.face, n_cells, n_vertices, need_cell_csr)
+        return cls(c.edge_index, None, None, n_cells, None, need_cell_csr)
+
+
+def get_topology(graphs, need_cell_csr: bool = False, two_hop: bool = True) -> MeshTopology:
+    """Topology attached by ``attach_topology`` if it matches the graphs, else a fresh build."""
+    c, _, v = graphs
+    topo = getattr(v, "topology", None) if v is not None else None
+    if topo is None:
+        topo = getattr(c, "topology", None)
+    if isinstance(topo, MeshTopology) and topo.n_faces == c.edge_index.shape[1] \
+            and topo.n_cells == c.x.shape[0] and (not two_hop or topo.vtx_offsets is not None):
+        if need_cell_csr:
+            topo.build_cell_csr()
+        return topo
+    return MeshTopology.from_graphs(graphs, need_cell_csr, two_hop)
+
+
+def attach_topology(graphs, need_cell_csr: bool = False, two_hop: bool = True) -> MeshTopology:
+    """Build the topology once and hang it on the graphs (static meshes: rollout, validation)."""
+    topo = MeshTopology.from_graphs(graphs, need_cell_csr, two_hop).validate()
+    graphs[0].topology = topo
+    if graphs[2] is not None:
+        graphs[2].topology = topo
+    return topo

@@ -1,0 +1,146 @@
+/*
+ * gnnfd_b200.h - C ABI of the B200-native message-passing hot path.
+ *
+ * The reference (aj-dray/gnn-fluid-dynamics) is pure Python: its "operator interface" for this path
+ * is a set of library calls made from src/models/*.py.  Each entry point below replaces one group
+ * of those call sites (cited per function, paths relative to the reference root).  A maintainer of
+ * the reference binds them with ctypes; this repo's own host layer
+ * (gnn_fluid_dynamics_b200/_lib.py) does exactly that.
+ *
+ * Conventions
+ *  - extern "C", POD arguments only: device pointers, sizes, enums, a cudaStream_t passed as void*.
+ *  - Every function returns 0 on success or a negative GNNFD_E_* code; no C++ exception crosses
+ *    the ABI; gnnfd_last_error() returns a static message for the calling thread.
+ *  - No allocation inside: outputs and workspaces are caller-owned device memory, sized with the
+ *    matching *_workspace_bytes query.  Kernels are stream-ordered, never synchronise the host and
+ *    are CUDA-graph capturable.
+ *  - All floating-point tensors are fp32 row-major; all index tensors consumed by kernels are
+ *    int32 (gnnfd_index_narrow converts the reference's int64 tensors once per mesh).
+ */
+#ifndef GNNFD_B200_H
+#define GNNFD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNNFD_ABI_VERSION 1
+
+enum {
+  GNNFD_OK = 0,
+  GNNFD_E_BADARG = -1,      /* null pointer, negative size, unsupported width */
+  GNNFD_E_UNSUPPORTED = -2, /* combination not implemented by the selected precision */
+  GNNFD_E_WORKSPACE = -3,   /* workspace too small */
+  GNNFD_E_CUDA = -4,        /* a CUDA runtime call or launch failed */
+  GNNFD_E_RANGE = -5        /* an index is out of range (reported through the device flag) */
+};
+
+/* arithmetic used for the three GEMMs of an MLP (accumulation, bias, activation, LayerNorm and
+ * residual are fp32 in every mode) */
+enum {
+  GNNFD_PREC_F32 = 0,    /* CUDA-core FFMA, exact fp32 operands */
+  GNNFD_PREC_BF16X3 = 1, /* tcgen05 kind::f16, split-bf16 operands: hi*hi + lo*hi + hi*lo */
+  GNNFD_PREC_BF16X1 = 2, /* tcgen05 kind::f16, single bf16 pass (fails the 1e-3 parity bar) */
+  GNNFD_PREC_FP16X2 = 3, /* tcgen05 kind::f16, fp16 weights, split-fp16 activations */
+  GNNFD_PREC_FP16X3 = 4  /* tcgen05 kind::f16, split-fp16 both operands */
+};
+
+enum { GNNFD_ACT_SILU = 0, GNNFD_ACT_TANH = 1 };
+
+/* how one K-segment of an MLP's input row r is assembled */
+enum {
+  GNNFD_SEG_DIRECT = 0, /* src[r, col:col+width]                                             */
+  GNNFD_SEG_GATHER = 1, /* src[idx0[r], col:col+width]                 (x[row], x[col])       */
+  GNNFD_SEG_SUM2 = 2,   /* src[idx0[r]] + src[idx1[r]]                 (Conservative.py:230)  */
+  GNNFD_SEG_DIFF2 = 3,  /* src[idx0[r]] - src[idx1[r]]                 (Conservative.py:621)  */
+  GNNFD_SEG_MEAN3 = 4   /* ((src[idx0[r]] + src[idx1[r]]) + src[idx2[r]]) / 3.0  (Fvgn.py:317-321) */
+};
+
+typedef struct {
+  const float *src;      /* row-major source matrix */
+  const int32_t *idx[3]; /* per-output-row gather indices (NULL where unused) */
+  int32_t ld;            /* row stride of src, in floats */
+  int32_t col;           /* first source column */
+  int32_t width;         /* number of K columns contributed */
+  int32_t mode;          /* GNNFD_SEG_* */
+} gnnfd_segment;
+
+/*
+ * One fused "assemble input row -> Linear -> act -> Linear -> act -> Linear -> [LayerNorm] ->
+ * [* mul] -> [+ residual]" pass over `rows` rows.
+ *
+ * Replaces, per call: torch.cat + x[row]/x[col] gathers + nn.Sequential(Linear,SiLU,Linear,SiLU,
+ * Linear)+LayerNorm + residual add of
+ *   Face_Block.forward  src/models/Fvgn.py:292-296, src/models/Mgn.py:234-238,
+ *                       src/models/Conservative.py:228-234
+ *   Cell_Block.forward  src/models/Fvgn.py:316-323, src/models/Mgn.py:258-265 (MLP part),
+ *                       src/models/Conservative.py:251-252
+ *   Encoder / Decoder   src/models/Fvgn.py:263-266, 332-333; src/models/Mgn.py:205-208, 274-275
+ *   build_mlp           src/models/Model.py:12-40;  build_mlp_antisym src/models/Conservative.py:31-43
+ *   residuals           src/models/Fvgn.py:281-282, src/models/Mgn.py:223-224
+ */
+typedef struct {
+  int64_t rows;
+  int32_t n_seg;
+  gnnfd_segment seg[3];
+  int32_t k_in;   /* sum of segment widths == W1.shape[1] */
+  int32_t hidden; /* 128 */
+  int32_t n_out;  /* 128 (latent) or 1..16 (decoder head) */
+  /* fp32 parameters in PyTorch layout: w1[hidden,k_in] w2[hidden,hidden] w3[n_out,hidden];
+   * biases and LayerNorm affine may be NULL (bias-free antisym MLP; decoder without LN) */
+  const float *w1, *b1, *w2, *b2, *w3, *b3, *ln_w, *ln_b;
+  int32_t has_ln; /* LayerNorm(n_out) with eps ln_eps; affine iff ln_w != NULL */
+  float ln_eps;
+  int32_t act;    /* GNNFD_ACT_* */
+  const float *mul;      /* optional [rows,n_out]: out *= mul (Conservative.py:233) */
+  const float *residual; /* optional [rows,n_out] */
+  float *out_raw;        /* optional [rows,n_out]: MLP(+LN)(*mul) output */
+  float *out_sum;        /* optional [rows,n_out]: residual + output */
+  /* tensor-core precisions only: operand pack produced by gnnfd_pack_mlp (NULL for F32) */
+  const void *packed;
+  int32_t precision; /* GNNFD_PREC_* */
+} gnnfd_mlp_args;
+
+int gnnfd_abi_version(void);
+const char *gnnfd_last_error(void);
+
+/* int64 -> int32 index conversion with range check [0, limit); *err_flag (device int32, caller
+ * zeroes it) is set to 1 if any index is out of range.  Replaces nothing in the reference: it is
+ * the one-off narrowing of edge_index / face tensors (src/datasets/DataSet.py:212-213 uses long). */
+int gnnfd_index_narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t limit,
+                       int32_t *err_flag, void *stream);
+
+/* Receiver-sorted CSR of an index vector: perm = stable argsort(index), offsets[r] = #{index < r}.
+ * Integer-exact against torch.sort(index, stable=True) + bincount.
+ * It is what lets the deterministic segment sums replace torch_scatter.scatter_add's atomics
+ * (src/models/Fvgn.py:307-314, src/models/Mgn.py:249-256, src/models/Conservative.py:244-249). */
+size_t gnnfd_csr_workspace_bytes(int64_t n, int64_t n_rows);
+int gnnfd_csr_build(const int32_t *index, int64_t n, int64_t n_rows, int32_t *offsets /*n_rows+1*/,
+                    int32_t *perm /*n*/, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Deterministic segment sum over CSR rows, replacing scatter_add(cat[A;B], cat[i0;i1], dim_size):
+ *   out[r, :] = sum over p in perm[offsets[r]:offsets[r+1]] (ascending position p, i.e. the CPU
+ *   scatter_add order) of   p < n_half ?  a[p, col_a:col_a+width]
+ *                                      :  sign_b * b[p - n_half, col_b:col_b+width]
+ * two-hop halves (Fvgn.py:312-314): a=b=e, col_a=0, col_b=H/2, width=H/2, sign_b=+1
+ * signed edge->cell (Conservative.py:248-249): a=b=e, cols 0, width=H, sign_b=-1
+ * Vertex_Block (VertPot.py:219-221): a=b=e, cols 0, width=H, sign_b=+1 */
+int gnnfd_segment_sum(const float *a, const float *b, int32_t ld_a, int32_t ld_b, int32_t col_a,
+                      int32_t col_b, int32_t width, float sign_b, int64_t n_half,
+                      const int32_t *offsets, const int32_t *perm, int64_t n_rows, float *out,
+                      int32_t ld_out, void *stream);
+
+int gnnfd_mlp_forward(const gnnfd_mlp_args *args, void *stream);
+
+/* operand pack for the tensor-core precisions (bf16/fp16 hi+lo parts in the UMMA shared-memory
+ * layout, biases and LayerNorm affine appended) */
+size_t gnnfd_pack_mlp_bytes(int32_t k_in, int32_t hidden, int32_t n_out, int32_t precision);
+int gnnfd_pack_mlp(const gnnfd_mlp_args *args, void *packed_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNFD_B200_H */

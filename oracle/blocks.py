@@ -1,0 +1,155 @@
+"""Oracle: encoder / GN_Block / decoder data-flows of the reference's model families, CPU fp32.
+
+Every function takes a reference-layout ``state_dict`` (same keys the reference's modules produce)
+plus plain tensors, so the same parameters drive the reference (golden fixtures), this oracle and
+the CUDA path.
+
+Families:
+  'fvgn'   FvgnA / FluxA-D / FvgnB..K  : Cell_Block -> Face_Block      (Fvgn.py:268-325)
+  'mgn'    MgnA-C / StreamFuncA-D      : Face_Block -> Cell_Block      (Mgn.py:210-267)
+  'cons_a' ConservativeA / B           : sum-form face block, signed edge->cell sum
+                                                                       (Conservative.py:204-254)
+  'vertpot' VertPotA..                 : fvgn order + Vertex_Block     (VertPot.py:187-222)
+"""
+from __future__ import annotations
+
+import torch
+
+from .mlp import mlp_from_state
+from .scatter import scatter_add
+
+FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot")
+
+_FAMILY_OF = {
+    "FvgnA": "fvgn", "FluxA": "fvgn", "MgnA": "mgn", "StreamFuncA": "mgn",
+    "ConservativeA": "cons_a", "ConservativeB": "cons_a", "VertPotA": "vertpot",
+}
+
+
+def family_of(model_name: str) -> str:
+    return _FAMILY_OF[model_name]
+
+
+# --- sub-blocks -----------------------------------------------------------------------------
+
+def two_hop_aggregate(e, v_edge_index, v_face, n_vertices):
+    """Cell_Block aggregation (Fvgn.py:305-321 == Mgn.py:247-263).
+
+    The edge latent is split in halves; half 0 is summed onto the face's first vertex
+    (v_edge_index[0]), half 1 onto its second; each cell then takes (s[v0] + s[v1] + s[v2]) / 3.
+    """
+    idx = torch.cat([v_edge_index[0], v_edge_index[1]], dim=0)
+    fwd, rev = torch.chunk(e, 2, dim=-1)
+    vsum = scatter_add(torch.cat([fwd, rev], dim=0), idx, n_vertices)
+    agg = (vsum.index_select(0, v_face[0]) + vsum.index_select(0, v_face[1])
+           + vsum.index_select(0, v_face[2])) / 3.0
+    return agg, vsum
+
+
+def cell_block_two_hop(sd, prefix, x, e, v_edge_index, v_face, n_vertices):
+    agg, _ = two_hop_aggregate(e, v_edge_index, v_face, n_vertices)
+    return mlp_from_state(sd, prefix, torch.cat([x, agg], dim=-1))
+
+
+def face_block_concat(sd, prefix, x, e, c_edge_index):
+    """Face_Block, concat form (Fvgn.py:292-296 == Mgn.py:234-238): order is [e, x[row], x[col]]."""
+    row, col = c_edge_index[0], c_edge_index[1]
+    return mlp_from_state(sd, prefix, torch.cat([e, x[row], x[col]], dim=1))
+
+
+def face_block_sum(sd, prefix, x, e, c_edge_index, e_asym=None):
+    """Face_Block, sum form (Conservative.py:228-234); optional multiply by the asym encoding."""
+    row, col = c_edge_index[0], c_edge_index[1]
+    out = mlp_from_state(sd, prefix, torch.cat([e, x[row] + x[col]], dim=1))
+    if e_asym is not None:
+        out = out * e_asym
+    return out
+
+
+def cell_block_signed(sd, prefix, x, e, c_edge_index):
+    """Cell_Block, signed direct edge->cell sum (Conservative.py:243-254):
+    agg[c] = sum_{col(k)=c} e_k - sum_{row(k)=c} e_k."""
+    row, col = c_edge_index[0], c_edge_index[1]
+    idx = torch.cat([col, row], dim=0)
+    agg = scatter_add(torch.cat([e, -e], dim=0), idx, x.shape[0])
+    return mlp_from_state(sd, prefix, torch.cat([x, agg], dim=-1))
+
+
+def vertex_block(e, v_edge_index, n_rows):
+    """Vertex_Block (VertPot.py:217-222): full-width edge->vertex sum; the output has
+    ``cell_graph.x.size(0)`` rows (N, not V) - rows >= V stay zero."""
+    idx = torch.cat([v_edge_index[0], v_edge_index[1]], dim=0)
+    return scatter_add(e.repeat(2, 1), idx, n_rows)
+
+
+# --- encoder / block / decoder per family ---------------------------------------------------
+
+def encoder_fwd(family, sd, c_x, f_x, f_x_asym=None):
+    """Encoder.forward (Fvgn.py:257-266, Mgn.py:199-208, Conservative.py:191-202).
+    Returns (x0, e0, e0_asym-or-None)."""
+    if family == "cons_a":
+        e0 = mlp_from_state(sd, "encoder.faceS_mlp", f_x)
+        ea = mlp_from_state(sd, "encoder.faceA_mlp", f_x_asym, act="tanh")
+        x0 = mlp_from_state(sd, "encoder.cell_mlp", c_x)
+        return x0, e0, ea
+    e0 = mlp_from_state(sd, "encoder.face_mlp", f_x)
+    x0 = mlp_from_state(sd, "encoder.cell_mlp", c_x)
+    return x0, e0, None
+
+
+def gn_block_fwd(family, sd, i, x, e, topo, e_asym=None):
+    """One GN_Block.  ``topo`` has c_edge_index, v_edge_index, v_face, n_vertices.
+    The second sub-block consumes the first one's RAW output, the residuals are added after both
+    (Fvgn.py:274-284, Mgn.py:216-226, Conservative.py:210-220, VertPot.py:195-210).
+    Returns (x_new, e_new, vertex_x-or-None)."""
+    p = f"processer_list.{i}"
+    if family == "fvgn":
+        xr = cell_block_two_hop(sd, f"{p}.cell_block.cell_mlp", x, e, topo["v_edge_index"],
+                                topo["v_face"], topo["n_vertices"])
+        er = face_block_concat(sd, f"{p}.face_block.face_mlp", xr, e, topo["c_edge_index"])
+        return x + xr, e + er, None
+    if family == "mgn":
+        er = face_block_concat(sd, f"{p}.face_block.face_mlp", x, e, topo["c_edge_index"])
+        xr = cell_block_two_hop(sd, f"{p}.cell_block.cell_mlp", x, er, topo["v_edge_index"],
+                                topo["v_face"], topo["n_vertices"])
+        return x + xr, e + er, None
+    if family == "cons_a":
+        er = face_block_sum(sd, f"{p}.face_block.face_mlp", x, e, topo["c_edge_index"], e_asym)
+        xr = cell_block_signed(sd, f"{p}.cell_block.cell_mlp", x, er, topo["c_edge_index"])
+        return x + xr, e + er, None
+    if family == "vertpot":
+        xr = cell_block_two_hop(sd, f"{p}.node_block.cell_mlp", x, e, topo["v_edge_index"],
+                                topo["v_face"], topo["n_vertices"])
+        er = face_block_concat(sd, f"{p}.edge_block.face_mlp", xr, e, topo["c_edge_index"])
+        # Vertex_Block runs on the face block's RAW output (c_graph at that point carries e')
+        vx = vertex_block(er, topo["v_edge_index"], x.shape[0])
+        return x + xr, e + er, vx
+    raise ValueError(family)
+
+
+def decoder_fwd(family, sd, x, e, vx=None):
+    """Decoder.forward: edge head (Fvgn.py:327-333), node head (Mgn.py:269-275),
+    edge+vertex heads (VertPot.py:224-231)."""
+    if family == "mgn":
+        return mlp_from_state(sd, "decoder.face_mlp", x)
+    if family == "vertpot":
+        return (mlp_from_state(sd, "decoder.edge_mlp", e), mlp_from_state(sd, "decoder.vertex_mlp", vx))
+    return mlp_from_state(sd, "decoder.face_mlp", e)
+
+
+def processor_fwd(family, sd, c_x, f_x, topo, mp_num, f_x_asym=None, keep_blocks=False):
+    """encoder -> mp_num x GN_Block -> decoder on already-normalised inputs.
+
+    ConservativeA quirk reproduced: GN_Block returns a fresh Data without ``edge_attr_asym`` so
+    the asym multiply fires in block 0 only (Conservative.py:220, 232-233)."""
+    x, e, ea = encoder_fwd(family, sd, c_x, f_x, f_x_asym)
+    out = {"x0": x, "e0": e}
+    vx = None
+    per_block = []
+    for i in range(mp_num):
+        x, e, vx = gn_block_fwd(family, sd, i, x, e, topo, e_asym=ea if i == 0 else None)
+        if keep_blocks:
+            per_block.append((x, e))
+    out.update({"x": x, "e": e, "vx": vx, "blocks": per_block})
+    out["dec"] = decoder_fwd(family, sd, x, e, vx)
+    return out

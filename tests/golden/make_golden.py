@@ -1,0 +1,177 @@
+"""Generate the committed golden fixtures by running the REFERENCE's own code in this container.
+
+Run here only:  python tests/golden/make_golden.py
+(needs /root/reference, which does not exist on the GPU box; the .npz files it writes travel.)
+
+What is pinned
+  connectivity_{k}.npz : reference utils/geometry.compute_connectivity on three synthetic meshes
+  fwd_{Model}.npz      : reference model forward (MgnA, FvgnA, FluxA, ConservativeA, VertPotA),
+                         hidden 128, 15 blocks, deterministic parameters
+                         (gnn_fluid_dynamics_b200.testing.fill_state_dict_deterministic, seed 1),
+                         mesh make_mesh(160, kind, seed=3), features mesh_graphs(seed=5):
+                         encoder outputs, processor outputs after block 1 and block 15, decoder
+                         outputs, the forward() dict in 'train' and 'rollout' modes
+  train_FvgnA.npz      : reference FvgnA train-mode forward + model.loss + backward: loss values and
+                         gradients (norm of every parameter's grad + a few full tensors)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refstub  # noqa: E402
+
+refstub.install()
+
+from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs  # noqa: E402
+from gnn_fluid_dynamics_b200.testing import default_stats, fill_state_dict_deterministic  # noqa: E402
+from gnn_fluid_dynamics_b200.graph import Data  # noqa: E402
+
+from utils.config import Config  # noqa: E402  (reference)
+from utils.geometry import compute_connectivity  # noqa: E402
+from utils.loss import MSE_per_element_torch  # noqa: E402
+from datasets.OpenFoam import NodeType  # noqa: E402
+import importlib  # noqa: E402
+
+torch.set_num_threads(4)
+
+MODELS = {
+    "MgnA": ("models.Mgn", "cylinder", "fvgn"),
+    "FvgnA": ("models.Fvgn", "cylinder", "fvgn"),
+    "FluxA": ("models.Flux", "ellipse", "fvgn"),
+    "ConservativeA": ("models.Conservative", "cylinder", "conservative"),
+    "VertPotA": ("models.VertPot", "airfoil", "fvgn"),
+}
+LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
+          "face_flux": 1, "face_pressure": 1}
+
+
+class _Dataset:
+    class_types = NodeType
+    noise = False
+    mode = "valid"
+
+
+def ref_config():
+    return Config.from_dict({
+        "model": {"hidden_width": 128, "mp_num": 15, "cell_grad_weights_order": 1,
+                  "face_grad_weights_order": 1},
+        "training": {"dropout_rate": 0.0, "loss_weights": LOSS_W},
+    })
+
+
+def build_ref(name):
+    module, kind, flavour = MODELS[name]
+    cls = getattr(importlib.import_module(module), name)
+    model = cls(ref_config(), MSE_per_element_torch, _Dataset(), default_stats())
+    fill_state_dict_deterministic(model, seed=1)
+    return model, kind, flavour
+
+
+def graphs_for(name, kind, flavour, flip=False):
+    mesh = make_mesh(160, kind, seed=3)
+    g = mesh_graphs(mesh, seed=5, flavour=flavour, flip_edges=flip)
+    c, f, v = g
+    if name == "MgnA":
+        c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
+        f.y = f.y[:, :2].contiguous()
+    elif name in ("FvgnA", "ConservativeA", "VertPotA"):
+        f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
+    c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
+    f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
+    return mesh, g
+
+
+def to_np(d):
+    return {k: v.detach().cpu().numpy() for k, v in d.items() if torch.is_tensor(v)}
+
+
+def gen_connectivity():
+    for i, (n, kind, srt) in enumerate([(200, "cylinder", False), (700, "airfoil", True), (512, "none", False)]):
+        m = make_mesh(n, kind, seed=i, sort_cell_vertices=srt)
+        fi, cei, vei = compute_connectivity(m.cells, m.vertex_pos)
+        np.savez_compressed(os.path.join(HERE, f"connectivity_{i}.npz"), cells=m.cells,
+                            vertex_pos=m.vertex_pos, face_index=fi, cell_edge_index=cei,
+                            vertex_edge_index=vei)
+        print("connectivity", i, m.n_cells, m.n_faces, m.n_vertices)
+
+
+def gen_forward(name):
+    model, kind, flavour = build_ref(name)
+    model.eval()
+    mesh, graphs = graphs_for(name, kind, flavour)
+    cap = {}
+
+    def grab_enc(mod, inp, out):
+        cap["x0"], cap["e0"] = out.x.clone(), out.edge_attr.clone()
+        if hasattr(out, "edge_attr_asym"):
+            cap["e0_asym"] = out.edge_attr_asym.clone()
+
+    def grab_block(tag):
+        def hook(mod, inp, out):
+            cg = out[0] if isinstance(out, tuple) else out
+            cap[f"x{tag}"], cap[f"e{tag}"] = cg.x.clone(), cg.edge_attr.clone()
+            if isinstance(out, tuple):
+                cap[f"vx{tag}"] = out[1].x.clone()
+        return hook
+
+    def grab_dec(mod, inp, out):
+        if isinstance(out, tuple):
+            cap["dec"], cap["dec_vertex"] = out[0].clone(), out[1].clone()
+        else:
+            cap["dec"] = out.clone()
+
+    model.encoder.register_forward_hook(grab_enc)
+    model.processer_list[0].register_forward_hook(grab_block(1))
+    model.processer_list[-1].register_forward_hook(grab_block(15))
+    model.decoder.register_forward_hook(grab_dec)
+
+    out = {}
+    with torch.no_grad():
+        for mode in ("train", "rollout"):
+            res = model([g.clone() for g in graphs], mode=mode)
+            for k, v in res.items():
+                out[f"out_{mode}_{k}"] = v.clone()
+    out.update(cap)
+    np.savez_compressed(os.path.join(HERE, f"fwd_{name}.npz"), **to_np(out))
+    print(name, {k: tuple(v.shape) for k, v in out.items()})
+
+
+def gen_train():
+    name = "FvgnA"
+    model, kind, flavour = build_ref(name)
+    model.train()
+    mesh, graphs = graphs_for(name, kind, flavour, flip=True)
+    batch = [g.clone() for g in graphs]
+    output = model(batch, mode="train")
+    losses = model.loss(output, batch)
+    losses["total_log_loss"].backward()
+    out = {f"loss_{k}": v.detach().reshape(1) for k, v in losses.items()}
+    keep_full = ["processer_list.0.cell_block.cell_mlp.1.weight", "processer_list.14.face_block.face_mlp.1.bias",
+                 "decoder.face_mlp.4.weight", "encoder.cell_mlp.0.0.weight",
+                 "processer_list.7.face_block.face_mlp.0.0.bias"]
+    names, norms = [], []
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        names.append(k)
+        norms.append(float(p.grad.double().norm()))
+        if k in keep_full:
+            out["grad_" + k] = p.grad.clone()
+    out["grad_norms"] = torch.tensor(norms, dtype=torch.float64)
+    for k, v in output.items():
+        out["out_" + k] = v.detach()
+    d = to_np(out)
+    d["grad_names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, "train_FvgnA.npz"), **d)
+    print("train", {k: float(v) for k, v in losses.items()}, len(names), "param grads")
+
+
+if __name__ == "__main__":
+    gen_connectivity()
+    for n in MODELS:
+        gen_forward(n)
+    gen_train()

@@ -1,0 +1,57 @@
+"""Shared test helpers: configs, deterministic models, fixtures."""
+import os
+from types import SimpleNamespace as NS
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
+          "face_flux": 1, "face_pressure": 1}
+# (mesh kind, feature flavour) used by tests/golden/make_golden.py per model
+GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "FluxA": ("ellipse", "fvgn"),
+                "ConservativeA": ("cylinder", "conservative"), "VertPotA": ("airfoil", "fvgn")}
+
+
+def make_config(mp_num=15, precision=None):
+    return NS(model=NS(hidden_width=128, mp_num=mp_num, precision=precision),
+              training=NS(dropout_rate=0.0, loss_weights=dict(LOSS_W)))
+
+
+def mse(output, target, mask, batch=None):
+    if mask is not None:
+        output, target = output[mask], target[mask]
+    return torch.nn.functional.mse_loss(output, target)
+
+
+def build_model(name, mp_num=15, precision=None, seed=1, device="cpu"):
+    from gnn_fluid_dynamics_b200.models import MODEL_CLASSES
+    from gnn_fluid_dynamics_b200.testing import default_stats, fill_state_dict_deterministic
+    model = MODEL_CLASSES[name](make_config(mp_num, precision), mse, None, default_stats())
+    fill_state_dict_deterministic(model, seed=seed)
+    return model.to(device)
+
+
+def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
+    """Same construction as tests/golden/make_golden.py:graphs_for."""
+    from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs
+    kind, flavour = GOLDEN_SETUP[name]
+    mesh = make_mesh(n_cells, kind, seed=mesh_seed)
+    g = mesh_graphs(mesh, seed=feat_seed, flavour=flavour, flip_edges=flip)
+    c, f, v = g
+    if name == "MgnA":
+        c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
+        f.y = f.y[:, :2].contiguous()
+    elif name in ("FvgnA", "ConservativeA"):
+        f.y = f.y[:, :3].contiguous()
+    c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
+    f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
+    return mesh, g
+
+
+def load_golden(fname):
+    return {k: v for k, v in np.load(os.path.join(GOLDEN, fname), allow_pickle=False).items()}
+
+
+def graphs_to(graphs, device):
+    return [g.to(device) for g in graphs]

@@ -1,0 +1,114 @@
+"""The oracle (oracle/) against the fixtures produced by the reference itself (tests/golden/*.npz):
+this is what pins the oracle (SURVEY.md section 8c - the reference ships no golden vectors)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import model as omodel
+from gnn_fluid_dynamics_b200.mesh import connectivity
+from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
+from helpers import GOLDEN, LOSS_W, build_model, golden_graphs, load_golden
+
+MODELS = ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA"]
+TOL = 2e-5   # fp32 CPU restatement vs fp32 CPU reference: summation-order noise only
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_connectivity_matches_reference(i):
+    g = load_golden(f"connectivity_{i}.npz")
+    fi, cei, vei = connectivity(g["cells"], g["vertex_pos"])
+    assert np.array_equal(fi, g["face_index"])
+    assert np.array_equal(cei, g["cell_edge_index"])
+    assert np.array_equal(vei, g["vertex_edge_index"])
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_state_dict_keys_match_reference(name):
+    ref = json.load(open(os.path.join(GOLDEN, f"keys_{name}.json")))
+    mine = [[k, list(v.shape)] for k, v in build_model(name).state_dict().items()]
+    assert mine == ref
+
+
+def _processor_inputs(name, graphs, model):
+    graphs = model.normalizer.input(graphs)
+    c, f, v = graphs
+    topo = {"c_edge_index": c.edge_index, "v_edge_index": v.edge_index, "v_face": v.face,
+            "n_vertices": v.num_nodes}
+    if name == "ConservativeA":
+        return c.x, f.x_symm, f.x_asym, topo
+    return c.x, f.x, None, topo
+
+
+@pytest.mark.parametrize("name", MODELS)
+def test_oracle_processor_matches_reference(name):
+    gold = load_golden(f"fwd_{name}.npz")
+    model = build_model(name)
+    sd = model.state_dict()
+    _, graphs = golden_graphs(name)
+    c_x, f_x, f_xa, topo = _processor_inputs(name, [g.clone() for g in graphs], model)
+    fam = oracle.family_of(name)
+    with torch.no_grad():
+        out = oracle.processor_fwd(fam, sd, c_x, f_x, topo, 15, f_x_asym=f_xa, keep_blocks=True)
+    assert rel_l2(out["x0"], torch.from_numpy(gold["x0"])) < TOL
+    assert rel_l2(out["e0"], torch.from_numpy(gold["e0"])) < TOL
+    assert rel_l2(out["blocks"][0][0], torch.from_numpy(gold["x1"])) < TOL
+    assert rel_l2(out["blocks"][0][1], torch.from_numpy(gold["e1"])) < TOL
+    assert rel_l2(out["x"], torch.from_numpy(gold["x15"])) < TOL
+    assert rel_l2(out["e"], torch.from_numpy(gold["e15"])) < TOL
+    if name == "VertPotA":
+        assert rel_l2(out["vx"], torch.from_numpy(gold["vx15"])) < TOL
+        assert rel_l2(out["dec"][0], torch.from_numpy(gold["dec"])) < TOL
+        assert rel_l2(out["dec"][1], torch.from_numpy(gold["dec_vertex"])) < TOL
+    else:
+        assert rel_l2(out["dec"], torch.from_numpy(gold["dec"])) < TOL
+
+
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA"])
+@pytest.mark.parametrize("mode", ["train", "rollout"])
+def test_oracle_full_forward_matches_reference(name, mode):
+    gold = load_golden(f"fwd_{name}.npz")
+    sd = build_model(name).state_dict()
+    _, graphs = golden_graphs(name)
+    with torch.no_grad():
+        out, _ = omodel.model_forward(name, sd, default_stats(), [g.clone() for g in graphs], 15, mode=mode)
+    for k, v in out.items():
+        assert rel_l2(v, torch.from_numpy(gold[f"out_{mode}_{k}"])) < TOL, k
+
+
+def test_oracle_train_step_matches_reference():
+    gold = load_golden("train_FvgnA.npz")
+    model = build_model("FvgnA")
+    params = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    _, graphs = golden_graphs("FvgnA", flip=True)
+    out, _ = omodel.model_forward("FvgnA", params, default_stats(), [g.clone() for g in graphs], 15,
+                                  mode="train", training=True)
+    graphs_n = omodel.normalise_inputs("FvgnA", default_stats(), [g.clone() for g in graphs])
+    losses = omodel.fvgn_loss(params, out, graphs_n, LOSS_W, training=True)
+    for k, v in losses.items():
+        assert abs(float(v) - float(gold[f"loss_{k}"][0])) < 1e-4 * max(1.0, abs(float(gold[f"loss_{k}"][0]))), k
+    losses["total_log_loss"].backward()
+    names = [str(n) for n in gold["grad_names"]]
+    for n, ref_norm in zip(names, gold["grad_norms"]):
+        g = params[n].grad
+        assert g is not None, n
+        assert abs(float(g.double().norm()) - ref_norm) <= 2e-4 * max(ref_norm, 1e-6) + 1e-9, n
+    for k in gold:
+        if k.startswith("grad_processer") or k.startswith("grad_decoder") or k.startswith("grad_encoder"):
+            assert rel_l2(params[k[5:]].grad, torch.from_numpy(gold[k])) < 1e-4, k
+
+
+def test_scatter_add_matches_loop_and_csr_is_stable_sort():
+    rng = np.random.RandomState(0)
+    idx = rng.randint(0, 37, size=400)
+    src = rng.randn(400, 8).astype(np.float32)
+    a = oracle.scatter_add(torch.from_numpy(src), torch.from_numpy(idx), 40).numpy()
+    b = oracle.scatter_add_loop(src, idx, 40)
+    assert np.array_equal(a, b)       # same summation order -> bit-identical
+    off, perm = oracle.csr_build(idx, 40)
+    ref_perm = torch.sort(torch.from_numpy(idx), stable=True).indices.numpy()
+    assert np.array_equal(perm, ref_perm)
+    assert np.array_equal(np.diff(off), np.bincount(idx, minlength=40))
