@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py - processor edge-updates/sec of the message-passing hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+                  [--precision P]
+
+A step is one pass of the hot path (encoder -> 15 GN_Blocks -> decoder [-> loss -> backward for the
+training workload]) over one batch of synthetic meshes.  Default workload = BASELINE.json configs[1]:
+FvgnA, batch 8 x 20k-cell cylinder meshes, on each GPU (weak scaling, meshes are independent units,
+no data-path collective in the forward; gradient all-reduce in the training workload).
+Prints ONE JSON line (rank 0).  `--impl reference` times the oracle port of the reference's CPU
+implementation on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+MP_NUM = 15
+WORKLOADS = {
+    # name: (model, meshes per GPU, cells per mesh, obstacle, training step?)
+    "fvgn_fwd_8x20k": ("FvgnA", 8, 20000, "cylinder", False),
+    "fvgn_train_8x20k": ("FvgnA", 8, 20000, "cylinder", True),
+    "mgn_fwd_2k": ("MgnA", 1, 2048, "none", False),
+    "mgn_fwd_200k": ("MgnA", 1, 200000, "airfoil", False),
+}
+DEFAULT_WORKLOAD = "fvgn_fwd_8x20k"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def build_batch(model_name, n_meshes, n_cells, kind, seed0=0):
+    """Synthetic batch of independent meshes, PyG-style concatenation (training-time edge flips on)."""
+    from gnn_fluid_dynamics_b200.graph import collate_triplet
+    from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs
+    samples = []
+    for i in range(n_meshes):
+        g = mesh_graphs(make_mesh(n_cells, kind, seed=seed0 + i), seed=100 + seed0 + i, flip_edges=True)
+        if model_name == "MgnA":
+            g[0].y = torch.cat([g[0].y, torch.zeros(g[0].x.shape[0], 1)], 1)
+            g[1].y = g[1].y[:, :2].contiguous()
+        else:
+            g[1].y = g[1].y[:, :3].contiguous()
+        samples.append(g)
+    return collate_triplet(samples) if n_meshes > 1 else _with_batch(samples[0])
+
+
+def _with_batch(g):
+    g[0].batch = torch.zeros(g[0].x.shape[0], dtype=torch.long)
+    g[1].batch = torch.zeros(g[1].x.shape[0], dtype=torch.long)
+    return g
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as exc:  # noqa: BLE001
+            self.err = repr(exc)
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.ok:
+            self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok and self.t.is_alive():
+            self.t.join(timeout=1)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def algorithmic_bytes_edge_kernel(E, N):
+    """Fused edge block, FVGN order: read e (E rows) + gather x' (N unique rows) + write e+e' (E rows),
+    512 B per fp32 row, + row/col int32 indices."""
+    return 512 * (2 * E + N) + 8 * E
+
+
+def run_reference(args, world, rank):
+    """Reference arm: the oracle port of the reference's CPU path on the host cores (the Python
+    reference itself cannot travel to the GPU box)."""
+    if rank != 0:
+        return
+    import oracle
+    from oracle import model as omodel
+    from helpers import LOSS_W, build_model
+    from gnn_fluid_dynamics_b200.testing import default_stats
+    model_name, n_meshes, n_cells, kind, train = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    graphs = build_batch(model_name, 1, n_cells, kind)      # bounded sample: ONE mesh of the batch
+    model = build_model(model_name)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    E = graphs[0].edge_index.shape[1]
+    stats = default_stats()
+
+    def step():
+        g = [x.clone() for x in graphs]
+        if train:
+            params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+            out, _ = omodel.model_forward(model_name, params, stats, g, MP_NUM, mode="train", training=True)
+            loss = omodel.fvgn_loss(params, out, g, LOSS_W, training=True)["total_log_loss"]
+            loss.backward()
+        else:
+            with torch.no_grad():
+                omodel.model_forward(model_name, sd, stats, g, MP_NUM, mode="train")
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = E * MP_NUM / dt
+    sample = f"1 of {n_meshes} meshes ({n_cells}-cell {kind}), whole forward{'+loss+backward' if train else ''} per step"
+    line = {
+        "impl": "reference", "metric": "processor edge-updates/sec", "value": value, "unit": "edge-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": model_name, "mp_num": MP_NUM, "hidden": 128,
+                   "meshes_per_gpu": n_meshes, "cells_per_mesh": n_cells},
+        "cpu_baseline": {"value": value, "unit": "edge-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, world, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from helpers import build_model
+    from gnn_fluid_dynamics_b200 import ops
+    from gnn_fluid_dynamics_b200.precisions import available
+    from gnn_fluid_dynamics_b200.topology import get_topology
+
+    model_name, n_meshes, n_cells, kind, train = WORKLOADS[args.workload]
+    if train:
+        raise SystemExit("training workload needs the backward kernels (not in this build)")
+    prec = args.precision or available()[-1]
+    model = build_model(model_name, precision=prec).to(dev).eval()
+    host_graphs = [g.pin_memory() for g in build_batch(model_name, n_meshes, n_cells, kind, seed0=rank * n_meshes)]
+    N, E = host_graphs[0].x.shape[0], host_graphs[0].edge_index.shape[1]
+    V = host_graphs[2].pos.shape[0]
+
+    # ---- device-resident leg (`value`): inputs already normalised and in HBM ------------------------
+    gd = model.normalizer.input([g.to(dev) for g in host_graphs])
+    topo = get_topology(gd).validate()
+    working_set = 4 * 128 * (2 * E + 3 * N) + 4 * 64 * V
+    flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev) if working_set < 256e6 else None
+
+    def step_resident():
+        with torch.no_grad():
+            return model.encode_process_decode(gd[0].x, gd[1].x, topo)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ops.LAUNCHES = 0
+    for s, e in ev:
+        if flush is not None:
+            flush.zero_()                       # L2 flush between timed iterations (not timed)
+        s.record()
+        step_resident()
+        e.record()
+    barrier()
+    launches = ops.LAUNCHES
+    ms = sum(s.elapsed_time(e) for s, e in ev) / args.steps
+    clocks = sampler.stop()
+
+    # ---- end-to-end leg (`e2e`): host graphs -> model.forward -> host result ------------------------
+    def step_e2e():
+        with torch.no_grad():
+            g = [x.to(dev, non_blocking=True) for x in host_graphs]
+            out = model(g, mode="train")
+            return out["cell_velocity_change"].to("cpu", non_blocking=False)
+
+    h2d = sum(t.numel() * t.element_size() for g in host_graphs for t in g._store.values() if torch.is_tensor(t))
+    d2h = N * 2 * 4
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    # ---- dominant kernel (fused edge block) timed alone with CUDA events on its stream -------------
+    blk = model.processer_list[7]
+    from gnn_fluid_dynamics_b200 import processor as P
+    x_lat = torch.randn(N, 128, device=dev)
+    e_lat = torch.randn(E, 128, device=dev)
+    kev = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            if flush is not None:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            P.edge_mlp_concat(blk.face_block.face_mlp, e_lat, x_lat, topo, model.prec, want_raw=False)
+            b.record()
+            if i >= args.warmup:
+                kev.append((a, b))
+    torch.cuda.synchronize()
+    k_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+    hbm_peak, peak_kind = peaks()
+    alg = algorithmic_bytes_edge_kernel(E, N)
+    achieved = alg / (k_ms * 1e-3) / 1e9
+
+    # ---- max over ranks, aggregate -------------------------------------------------------------------
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    tot = torch.tensor([float(E)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    E_total = float(tot[0])
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = time_cpu_baseline(model_name, n_meshes, n_cells, kind)
+
+    if rank == 0:
+        line = {
+            "metric": "processor edge-updates/sec", "value": E_total * MP_NUM / (ms * 1e-3),
+            "unit": "edge-updates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"f32": "f32", "bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate)"}.get(prec, prec),
+            "data": "synthetic",
+            "config": {"workload": args.workload, "model": model_name, "mp_num": MP_NUM, "hidden": 128,
+                       "meshes_per_gpu": n_meshes, "cells_per_mesh": n_cells, "cells": N, "faces": E,
+                       "vertices": V, "precision": prec, "timed": "encoder + 15 GN_Blocks + decoder",
+                       "l2": "flushed between iterations" if flush is not None else "working set > L2"},
+            "e2e": {"value": E_total * MP_NUM / (ms_e2e * 1e-3), "unit": "edge-updates/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                    "api": "model.forward(graphs, mode='train') from pinned host graphs"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"kernel": "fused edge block (gather + 3-layer MLP + LayerNorm + residual)",
+                         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                         "kernel_ms": k_ms, "algorithmic_bytes": alg},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_cpu_baseline(model_name, n_meshes, n_cells, kind):
+    """Oracle port of the reference's CPU path on this box's host cores, bounded sample (1 mesh)."""
+    import oracle  # noqa: F401
+    from oracle import model as omodel
+    from helpers import build_model
+    from gnn_fluid_dynamics_b200.testing import default_stats
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    graphs = build_batch(model_name, 1, n_cells, kind)
+    sd = {k: v.clone() for k, v in build_model(model_name).state_dict().items()}
+    E = graphs[0].edge_index.shape[1]
+    best = None
+    with torch.no_grad():
+        for i in range(4):
+            t0 = time.perf_counter()
+            omodel.model_forward(model_name, sd, default_stats(), [g.clone() for g in graphs], MP_NUM, mode="train")
+            dt = time.perf_counter() - t0
+            if i > 0:
+                best = dt if best is None else min(best, dt)
+    return {"value": E * MP_NUM / best, "unit": "edge-updates/s", "cores": cores, "kind": "port",
+            "sample": f"1 of {n_meshes} meshes ({n_cells}-cell {kind}), whole forward, best of 3 after 1 warm-up"}
+
+
+if __name__ == "__main__":
+    main()

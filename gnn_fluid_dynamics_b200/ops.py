@@ -16,6 +16,14 @@ from ._lib import (ACT_SILU, ACT_TANH, PRECISIONS, SEG_DIFF2, SEG_DIRECT, SEG_GA
                    SEG_SUM2, MlpArgs, check, lib)
 
 
+LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -41,6 +49,7 @@ def index_narrow(index: torch.Tensor, limit: int) -> torch.Tensor:
     flag = torch.zeros(1, dtype=torch.int32, device=index.device)
     check(lib.gnnfd_index_narrow(index.data_ptr(), out.data_ptr(), index.numel(), int(limit),
                                  flag.data_ptr(), _stream()), "gnnfd_index_narrow")
+    _count(1)
     out._gnnfd_range_flag = flag  # checked lazily by MeshTopology.validate() (needs a sync)
     return out
 
@@ -56,6 +65,7 @@ def csr_build(index: torch.Tensor, n_rows: int) -> Tuple[torch.Tensor, torch.Ten
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     check(lib.gnnfd_csr_build(index.data_ptr(), n, n_rows, offsets.data_ptr(), perm.data_ptr(),
                               ws.data_ptr(), ws_bytes, _stream()), "gnnfd_csr_build")
+    _count(6)
     return offsets, perm
 
 
@@ -75,6 +85,7 @@ def segment_sum(a: torch.Tensor, b: torch.Tensor, col_a: int, col_b: int, width:
     check(lib.gnnfd_segment_sum(a.data_ptr(), b.data_ptr(), a.stride(0), b.stride(0), col_a, col_b,
                                 width, float(sign_b), a.shape[0], offsets.data_ptr(), perm.data_ptr(),
                                 n_rows, out.data_ptr(), out.stride(0), _stream()), "gnnfd_segment_sum")
+    _count(1)
     return out
 
 
@@ -177,5 +188,6 @@ def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = 
     args.out_raw = _ptr(out_raw) if want_raw else None
     args.out_sum = _ptr(out_sum) if want_sum else None
     check(lib.gnnfd_mlp_forward(C.byref(args), _stream()), "gnnfd_mlp_forward")
+    _count(1)
     del keep
     return (out_raw if want_raw else None), (out_sum if want_sum else None)

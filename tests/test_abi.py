@@ -1,0 +1,49 @@
+"""The C-ABI library loads and exports every symbol include/gnnfd_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "gnnfd_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gnnfd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    from gnn_fluid_dynamics_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 9
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/gnnfd_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == syms, "python binding list and header disagree"
+
+
+def test_abi_version_and_struct_layout():
+    from gnn_fluid_dynamics_b200 import _lib
+    assert _lib.lib.gnnfd_abi_version() == 1
+    # gnnfd_segment: ptr + 3 ptr + 4 int32 = 48 bytes; args struct must be 8-byte aligned
+    assert ctypes.sizeof(_lib.Segment) == 48
+    assert ctypes.sizeof(_lib.MlpArgs) % 8 == 0
+
+
+def test_bad_arguments_return_status_not_crash():
+    from gnn_fluid_dynamics_b200 import _lib
+    args = _lib.MlpArgs()
+    args.rows = -1
+    rc = _lib.lib.gnnfd_mlp_forward(ctypes.byref(args), None)
+    assert rc == -1
+    assert b"rows" in _lib.lib.gnnfd_last_error()
+    assert _lib.lib.gnnfd_csr_workspace_bytes(1000, 100) > 4 * 1100
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gnn_fluid_dynamics_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), fn

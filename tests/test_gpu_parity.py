@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle and the reference-made
+golden fixtures.  Tolerances: integer work bit-exact; fp32 path 2e-5 rel-L2 (summation order only);
+tensor-core precisions <= 1e-3 rel-L2 per processor output (BASELINE.json: north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import model as omodel
+from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
+from helpers import build_model, golden_graphs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"f32": 2e-5, "bf16x3": 1e-3, "fp16x2": 1e-3, "fp16x3": 1e-3}
+
+
+def precisions():
+    from gnn_fluid_dynamics_b200.precisions import available
+    return [p for p in available() if p in TOL]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+# ---------------------------------------------------------------------------------- CSR (integer)
+@pytest.mark.parametrize("n,rows", [(0, 5), (1, 1), (1000, 37), (4096, 4096), (100000, 3), (50000, 70001)])
+def test_csr_build_is_stable_argsort(n, rows):
+    from gnn_fluid_dynamics_b200 import ops
+    g = torch.Generator().manual_seed(n + rows)
+    idx = torch.randint(0, rows, (n,), generator=g, dtype=torch.int64)
+    off, perm = ops.csr_build(ops.index_narrow(idx.to(dev()), rows), rows)
+    ref_off, ref_perm = oracle.csr_build(idx.numpy(), rows)
+    assert np.array_equal(off.cpu().numpy(), ref_off)
+    assert np.array_equal(perm.cpu().numpy(), ref_perm)
+    if n:
+        assert torch.equal(perm.cpu().long(), torch.sort(idx, stable=True).indices)
+
+
+def test_csr_on_mesh_index_vectors_and_range_check():
+    from gnn_fluid_dynamics_b200.mesh import make_mesh
+    from gnn_fluid_dynamics_b200 import ops
+    m = make_mesh(20000, "cylinder", seed=1)
+    for vec, rows in [(np.concatenate([m.vertex_edge_index[0], m.vertex_edge_index[1]]), m.n_vertices),
+                      (np.concatenate([m.cell_edge_index[1], m.cell_edge_index[0]]), m.n_cells)]:
+        off, perm = ops.csr_build(ops.index_narrow(torch.from_numpy(vec).to(dev()), rows), rows)
+        ref_off, ref_perm = oracle.csr_build(vec, rows)
+        assert np.array_equal(off.cpu().numpy(), ref_off) and np.array_equal(perm.cpu().numpy(), ref_perm)
+    bad = ops.index_narrow(torch.tensor([0, 5, 9], device=dev()), 9)
+    assert int(bad._gnnfd_range_flag.item()) == 1
+
+
+# -------------------------------------------------------------------- segment sum (bit-exact order)
+@pytest.mark.parametrize("mode", ["halves", "signed", "full"])
+def test_segment_sum_matches_sequential_scatter_add(mode):
+    from gnn_fluid_dynamics_b200 import ops
+    from gnn_fluid_dynamics_b200.mesh import make_mesh
+    m = make_mesh(3000, "airfoil", seed=2)
+    E = m.n_faces
+    e = torch.randn(E, 128, generator=torch.Generator().manual_seed(0))
+    if mode == "signed":
+        idx = np.concatenate([m.cell_edge_index[1], m.cell_edge_index[0]]); rows = m.n_cells
+        src = np.concatenate([e.numpy(), -e.numpy()]); args = (0, 0, 128, -1.0)
+    elif mode == "halves":
+        idx = np.concatenate([m.vertex_edge_index[0], m.vertex_edge_index[1]]); rows = m.n_vertices
+        src = np.concatenate([e.numpy()[:, :64], e.numpy()[:, 64:]]); args = (0, 64, 64, 1.0)
+    else:
+        idx = np.concatenate([m.vertex_edge_index[0], m.vertex_edge_index[1]]); rows = m.n_cells
+        src = np.concatenate([e.numpy(), e.numpy()]); args = (0, 0, 128, 1.0)
+    ref = oracle.scatter_add_loop(src, idx, rows)
+    off, perm = ops.csr_build(ops.index_narrow(torch.from_numpy(idx).to(dev()), rows), rows)
+    ed = e.to(dev())
+    out = ops.segment_sum(ed, ed, args[0], args[1], args[2], args[3], off, perm, rows)
+    assert np.array_equal(out.cpu().numpy(), ref)      # same order of additions -> bit-identical
+
+
+# -------------------------------------------------------------------------------- fused MLP block
+def _rand_mlp(k_in, n_out, ln, bias=True, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    u = lambda *s, b: (torch.rand(*s, generator=g) * 2 - 1) * b
+    p = dict(w1=u(128, k_in, b=k_in ** -0.5), b1=u(128, b=k_in ** -0.5) if bias else None,
+             w2=u(128, 128, b=128 ** -0.5), b2=u(128, b=128 ** -0.5) if bias else None,
+             w3=u(n_out, 128, b=128 ** -0.5), b3=u(n_out, b=128 ** -0.5) if bias else None,
+             ln_w=1 + u(n_out, b=0.1) if ln else None, ln_b=u(n_out, b=0.1) if ln else None)
+    return p
+
+
+def _to_weights(p, act):
+    from gnn_fluid_dynamics_b200.ops import MLPWeights
+    d = lambda t: None if t is None else t.to(dev()).contiguous()
+    return MLPWeights(w1=d(p["w1"]), b1=d(p["b1"]), w2=d(p["w2"]), b2=d(p["b2"]), w3=d(p["w3"]),
+                      b3=d(p["b3"]), ln_w=d(p["ln_w"]), ln_b=d(p["ln_b"]), has_ln=p["ln_w"] is not None,
+                      act=act)
+
+
+@pytest.mark.parametrize("rows", [1, 63, 64, 65, 1000])
+@pytest.mark.parametrize("k_in,n_out,ln,act,bias", [
+    (128, 128, True, "silu", True), (10, 128, True, "silu", True), (2, 128, True, "silu", True),
+    (8, 128, True, "silu", True), (4, 128, False, "tanh", False), (128, 5, False, "silu", True),
+    (128, 3, False, "silu", True), (128, 1, False, "silu", True), (128, 6, False, "silu", True)])
+def test_mlp_rows_vs_oracle(rows, k_in, n_out, ln, act, bias):
+    from gnn_fluid_dynamics_b200 import ops, _lib
+    for prec in precisions():
+        p = _rand_mlp(k_in, n_out, ln, bias, seed=rows + k_in)
+        x = torch.randn(rows, k_in, generator=torch.Generator().manual_seed(1))
+        ref = oracle.mlp3(x, p["w1"], p["b1"], p["w2"], p["b2"], p["w3"], p["b3"], p["ln_w"], p["ln_b"], act=act)
+        w = _to_weights(p, _lib.ACT_SILU if act == "silu" else _lib.ACT_TANH)
+        out, _ = ops.mlp_forward([ops.Seg(x.to(dev()))], w, rows, _lib.PRECISIONS[prec])
+        assert rel_l2(out, ref) < TOL[prec], (prec, rel_l2(out, ref))
+
+
+def test_fused_edge_and_node_blocks_vs_oracle():
+    """gather/concat, sum2, mean3 input assembly + mul + residual epilogue, ragged row counts."""
+    from gnn_fluid_dynamics_b200 import ops, _lib
+    g = torch.Generator().manual_seed(3)
+    N, E, V = 333, 517, 190
+    x, e = torch.randn(N, 128, generator=g), torch.randn(E, 128, generator=g)
+    vs = torch.randn(V, 64, generator=g)
+    mul = torch.randn(E, 128, generator=g)
+    row, col = torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)
+    vf = [torch.randint(0, V, (N,), generator=g) for _ in range(3)]
+    i32 = lambda t: t.to(torch.int32).to(dev())
+    xd, ed, vsd = x.to(dev()), e.to(dev()), vs.to(dev())
+    for prec in precisions():
+        P_ = _lib.PRECISIONS[prec]
+        # edge block, concat form
+        p = _rand_mlp(384, 128, True, seed=5)
+        ref = oracle.mlp3(torch.cat([e, x[row], x[col]], 1), p["w1"], p["b1"], p["w2"], p["b2"], p["w3"], p["b3"], p["ln_w"], p["ln_b"])
+        raw, summed = ops.mlp_forward([ops.Seg(ed), ops.Seg(xd, _lib.SEG_GATHER, (i32(row),)),
+                                       ops.Seg(xd, _lib.SEG_GATHER, (i32(col),))], _to_weights(p, 0), E, P_,
+                                      residual=ed, want_raw=True, want_sum=True)
+        assert rel_l2(raw, ref) < TOL[prec] and rel_l2(summed, e + ref) < TOL[prec]
+        # edge block, sum form with asym multiply
+        p = _rand_mlp(256, 128, True, seed=6)
+        ref = oracle.mlp3(torch.cat([e, x[row] + x[col]], 1), p["w1"], p["b1"], p["w2"], p["b2"], p["w3"], p["b3"], p["ln_w"], p["ln_b"]) * mul
+        raw, summed = ops.mlp_forward([ops.Seg(ed), ops.Seg(xd, _lib.SEG_SUM2, (i32(row), i32(col)))],
+                                      _to_weights(p, 0), E, P_, mul=mul.to(dev()), residual=ed,
+                                      want_raw=True, want_sum=True)
+        assert rel_l2(raw, ref) < TOL[prec] and rel_l2(summed, e + ref) < TOL[prec]
+        # node block, mean3 form
+        p = _rand_mlp(192, 128, True, seed=7)
+        agg = (vs[vf[0]] + vs[vf[1]] + vs[vf[2]]) / 3.0
+        ref = oracle.mlp3(torch.cat([x, agg], 1), p["w1"], p["b1"], p["w2"], p["b2"], p["w3"], p["b3"], p["ln_w"], p["ln_b"])
+        raw, summed = ops.mlp_forward([ops.Seg(xd), ops.Seg(vsd, _lib.SEG_MEAN3, tuple(i32(t) for t in vf))],
+                                      _to_weights(p, 0), N, P_, residual=xd, want_raw=True, want_sum=True)
+        assert rel_l2(raw, ref) < TOL[prec] and rel_l2(summed, x + ref) < TOL[prec]
+
+
+# --------------------------------------------------------------------- processors vs golden + oracle
+def _run_processor(name, model, graphs_dev):
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    c, f, v = graphs_dev
+    grab = {}
+    hook = lambda i, x, e: grab.__setitem__(i, (x, e)) if i in (0, 14) else None
+    if name == "ConservativeA":
+        topo = get_topology(graphs_dev, need_cell_csr=True, two_hop=False).validate()
+        x, e, dec = model.encode_process_decode(c.x, f.x_symm, f.x_asym, topo, hook=hook)
+        return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
+    topo = get_topology(graphs_dev).validate()
+    if name == "VertPotA":
+        x, e, vx, dec, dec_v = model.encode_process_decode(c.x, f.x, topo, hook=hook)
+        return {"x": x, "e": e, "vx": vx, "dec": dec, "dec_vertex": dec_v, "b1": grab[0]}
+    x, e, dec = model.encode_process_decode(c.x, f.x, topo, hook=hook)
+    return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
+
+
+@pytest.mark.parametrize("name", ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA"])
+def test_processor_matches_reference_golden(name):
+    gold = load_golden(f"fwd_{name}.npz")
+    model = build_model(name).eval()
+    _, graphs = golden_graphs(name)
+    graphs = model.normalizer.input([g.clone() for g in graphs])
+    model.to(dev())
+    gd = [g.to(dev()) for g in graphs]
+    for prec in precisions():
+        model.set_precision(prec)
+        with torch.no_grad():
+            out = _run_processor(name, model, gd)
+        t = TOL[prec]
+        assert rel_l2(out["b1"][0], torch.from_numpy(gold["x1"])) < t
+        assert rel_l2(out["b1"][1], torch.from_numpy(gold["e1"])) < t
+        assert rel_l2(out["x"], torch.from_numpy(gold["x15"])) < t, (prec, rel_l2(out["x"], torch.from_numpy(gold["x15"])))
+        assert rel_l2(out["e"], torch.from_numpy(gold["e15"])) < t, (prec, rel_l2(out["e"], torch.from_numpy(gold["e15"])))
+        assert rel_l2(out["dec"], torch.from_numpy(gold["dec"])) < 2 * t
+        if name == "VertPotA":
+            assert rel_l2(out["vx"], torch.from_numpy(gold["vx15"])) < t
+            assert rel_l2(out["dec_vertex"], torch.from_numpy(gold["dec_vertex"])) < 2 * t
+
+
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA"])
+@pytest.mark.parametrize("mode", ["train", "rollout"])
+def test_full_forward_matches_reference_golden(name, mode):
+    gold = load_golden(f"fwd_{name}.npz")
+    model = build_model(name).to(dev()).eval()
+    _, graphs = golden_graphs(name)
+    for prec in precisions():
+        model.set_precision(prec)
+        with torch.no_grad():
+            out = model([g.clone().to(dev()) for g in graphs], mode=mode)
+        for k, v in out.items():
+            err = rel_l2(v, torch.from_numpy(gold[f"out_{mode}_{k}"]))
+            assert err < 3 * TOL[prec], (name, k, prec, err)
+
+
+@pytest.mark.parametrize("name,n_cells", [("FvgnA", 20000), ("MgnA", 2048)])
+def test_processor_vs_oracle_at_baseline_sizes(name, n_cells):
+    """BASELINE.json configs[0] (2k-cell MGN) and the per-mesh size of configs[1] (20k-cell FVGN)."""
+    model = build_model(name).eval()
+    _, graphs = golden_graphs(name, n_cells=n_cells, mesh_seed=7, feat_seed=8)
+    graphs = model.normalizer.input([g.clone() for g in graphs])
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    c, f, v = graphs
+    topo = {"c_edge_index": c.edge_index, "v_edge_index": v.edge_index, "v_face": v.face, "n_vertices": v.num_nodes}
+    with torch.no_grad():
+        ref = oracle.processor_fwd(oracle.family_of(name), sd, c.x, f.x, topo, 15)
+    model.to(dev())
+    gd = [g.to(dev()) for g in graphs]
+    for prec in precisions():
+        model.set_precision(prec)
+        with torch.no_grad():
+            out = _run_processor(name, model, gd)
+        assert rel_l2(out["x"], ref["x"]) < TOL[prec], (prec, rel_l2(out["x"], ref["x"]))
+        assert rel_l2(out["e"], ref["e"]) < TOL[prec], (prec, rel_l2(out["e"], ref["e"]))
+
+
+def test_batched_meshes_equal_individual_meshes():
+    """PyG-style concatenated batch == per-mesh results (independent units)."""
+    from gnn_fluid_dynamics_b200.graph import collate_triplet
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    model = build_model("FvgnA").to(dev()).eval()
+    samples = [golden_graphs("FvgnA", n_cells=n, mesh_seed=s)[1] for n, s in [(300, 1), (500, 2), (200, 3)]]
+    with torch.no_grad():
+        singles = []
+        for s in samples:
+            gd = [g.clone().to(dev()) for g in s]
+            singles.append(model.encode_process_decode(gd[0].x, gd[1].x, get_topology(gd).validate()))
+        batch = [g.to(dev()) for g in collate_triplet([[g.clone() for g in s] for s in samples])]
+        xb, eb, db = model.encode_process_decode(batch[0].x, batch[1].x, get_topology(batch).validate())
+    assert torch.equal(xb, torch.cat([s[0] for s in singles]))     # row-independent kernels: bitwise
+    assert torch.equal(eb, torch.cat([s[1] for s in singles]))
+    assert torch.equal(db, torch.cat([s[2] for s in singles]))
+
+
+def test_determinism_bitwise_repeatable():
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    model = build_model("MgnA").to(dev()).eval()
+    _, graphs = golden_graphs("MgnA", n_cells=5000)
+    gd = [g.to(dev()) for g in graphs]
+    topo = get_topology(gd).validate()
+    with torch.no_grad():
+        a = model.encode_process_decode(gd[0].x, gd[1].x, topo)
+        b = model.encode_process_decode(gd[0].x, gd[1].x, topo)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))
