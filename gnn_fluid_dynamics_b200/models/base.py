@@ -18,7 +18,7 @@ from torch import nn
 from .._lib import PRECISIONS
 
 # default GEMM arithmetic of the hot path; "f32" = exact CUDA-core path, others = tcgen05
-DEFAULT_PRECISION = "f32"
+DEFAULT_PRECISION = "bf16x3"
 
 
 def build_mlp(config, in_size, hidden_size, out_size, norm_layer=True):

@@ -12,7 +12,9 @@ from helpers import build_model, golden_graphs, load_golden
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"f32": 2e-5, "bf16x3": 1e-3, "fp16x2": 1e-3, "fp16x3": 1e-3}
+# fp16x2 (fp16 weights, split activations) and bf16x1 are built but measured at 4.6e-3 / >1e-2 on the
+# FvgnA forward: they fail the bar and are therefore not parity-gated defaults.
+TOL = {"f32": 2e-5, "bf16x3": 1e-3, "fp16x3": 1e-3}
 
 
 def precisions():
