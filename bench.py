@@ -202,7 +202,9 @@ def main():
     model_name, n_meshes, n_cells, kind, train = WORKLOADS[args.workload]
     if train:
         raise SystemExit("training workload needs the backward kernels (not in this build)")
-    prec = args.precision or available()[-1]
+    from gnn_fluid_dynamics_b200.models.base import DEFAULT_PRECISION
+    prec = args.precision or DEFAULT_PRECISION
+    assert prec in available(), prec
     model = build_model(model_name, precision=prec).to(dev).eval()
     host_graphs = [g.pin_memory() for g in build_batch(model_name, n_meshes, n_cells, kind, seed0=rank * n_meshes)]
     N, E = host_graphs[0].x.shape[0], host_graphs[0].edge_index.shape[1]

@@ -21,7 +21,7 @@ SEG_DIRECT, SEG_GATHER, SEG_SUM2, SEG_DIFF2, SEG_MEAN3 = 0, 1, 2, 3, 4
 EXPORTS = [
     "gnnfd_abi_version", "gnnfd_last_error", "gnnfd_index_narrow", "gnnfd_csr_workspace_bytes",
     "gnnfd_csr_build", "gnnfd_segment_sum", "gnnfd_mlp_forward", "gnnfd_pack_mlp_bytes",
-    "gnnfd_pack_mlp",
+    "gnnfd_pack_mlp", "gnnfd_tc_profile_read",
 ]
 
 
@@ -64,6 +64,7 @@ def _load():
     lib.gnnfd_pack_mlp_bytes.argtypes = [i32, i32, i32, i32]
     lib.gnnfd_pack_mlp_bytes.restype = C.c_size_t
     lib.gnnfd_pack_mlp.argtypes = [C.POINTER(MlpArgs), vp, vp]
+    lib.gnnfd_tc_profile_read.argtypes = [C.POINTER(C.c_uint64)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("gnnfd_abi_version",):

@@ -6,6 +6,7 @@ int mlp_forward_f32(const gnnfd_mlp_args *args, cudaStream_t stream);
 int mlp_forward_tc(const gnnfd_mlp_args *args, cudaStream_t stream);
 size_t pack_mlp_bytes_tc(int k_in, int hidden, int n_out, int precision);
 int pack_mlp_tc(const gnnfd_mlp_args *args, void *packed_out, cudaStream_t stream);
+int tc_profile_read(unsigned long long *out16);
 
 int validate_mlp_args(const gnnfd_mlp_args *a) {
   GNNFD_CHECK_ARG(a != nullptr, "null args");
@@ -66,4 +67,9 @@ extern "C" int gnnfd_pack_mlp(const gnnfd_mlp_args *args, void *packed_out, void
   if (args->precision == GNNFD_PREC_F32) return GNNFD_OK;
   GNNFD_CHECK_ARG(packed_out != nullptr, "null pack buffer");
   return pack_mlp_tc(args, packed_out, (cudaStream_t)stream);
+}
+
+extern "C" int gnnfd_tc_profile_read(uint64_t *out16) {
+  GNNFD_CHECK_ARG(out16 != nullptr, "null output");
+  return tc_profile_read((unsigned long long *)out16);
 }

@@ -140,6 +140,12 @@ int gnnfd_mlp_forward(const gnnfd_mlp_args *args, void *stream);
 size_t gnnfd_pack_mlp_bytes(int32_t k_in, int32_t hidden, int32_t n_out, int32_t precision);
 int gnnfd_pack_mlp(const gnnfd_mlp_args *args, void *packed_out, void *stream);
 
+/* Diagnostic: cycle counters recorded by CTA 0 of the last tensor-core MLP launch (synchronises).
+ * out16[0..6]  MMA issuer: total, w_empty wait, w_full wait, acc_free wait, a_full wait, act_ready
+ *              wait, tiles;  [8..10] epilogue: total, hidden acc_full wait, final acc_full wait;
+ *              [12..13] producer: total, a_empty wait. */
+int gnnfd_tc_profile_read(uint64_t *out16);
+
 #ifdef __cplusplus
 }
 #endif

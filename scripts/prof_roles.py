@@ -1,0 +1,40 @@
+"""Role wait-time breakdown of the tensor-core MLP kernel (CTA 0), edge/node block shapes."""
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import torch
+from helpers import build_model
+from gnn_fluid_dynamics_b200 import processor as P, _lib
+from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs
+from gnn_fluid_dynamics_b200.graph import collate_triplet
+from gnn_fluid_dynamics_b200.topology import get_topology
+
+dev = torch.device("cuda:0")
+prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+model = build_model("FvgnA", precision=prec).to(dev).eval()
+g = collate_triplet([mesh_graphs(make_mesh(20000, "cylinder", seed=i), seed=i) for i in range(8)])
+gd = [x.to(dev) for x in g]
+topo = get_topology(gd).validate()
+N, E = gd[0].x.shape[0], gd[0].edge_index.shape[1]
+x = torch.randn(N, 128, device=dev); e = torch.randn(E, 128, device=dev)
+blk = model.processer_list[3]
+vs = P.vertex_half_sum(e, topo)
+for which in ("edge", "node"):
+    def run():
+        if which == "edge":
+            P.edge_mlp_concat(blk.face_block.face_mlp, e, x, topo, model.prec, want_raw=False)
+        else:
+            P.node_mlp_two_hop(blk.cell_block.cell_mlp, x, vs, topo, model.prec, want_raw=True)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); run(); b.record(); torch.cuda.synchronize()
+    buf = (ctypes.c_uint64 * 16)()
+    _lib.check(_lib.lib.gnnfd_tc_profile_read(buf), "profile")
+    v = list(buf)
+    T = max(v[6], 1)
+    print(f"[{which} {prec}] kernel {a.elapsed_time(b)*1e3:.1f} us, tiles/CTA {T}")
+    print(f"  MMA issuer : total {v[0]/T:8.0f} cyc/tile | w_empty {v[1]/T:7.0f} w_full {v[2]/T:7.0f} acc_free {v[3]/T:7.0f} a_full {v[4]/T:7.0f} act_ready {v[5]/T:7.0f}")
+    print(f"  epilogue   : total {v[8]/T:8.0f} cyc/tile | wait hidden {v[9]/T:7.0f} wait final {v[10]/T:7.0f}")
+    print(f"  producer   : total {v[12]/T:8.0f} cyc/tile | wait a_empty {v[13]/T:7.0f}")
