@@ -1,18 +1,24 @@
 // Fused MLP block on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
 //
 //   assemble input rows (gather / concat / sum / mean3)            -> bf16|fp16 hi/lo parts, SMEM
-//   3 x [ tcgen05.mma kind::f16, M=128 N=128 K=16, fp32 accum in TMEM ]
-//   epilogues: tcgen05.ld -> +bias, SiLU/Tanh -> hi/lo split -> SMEM A operand of the next layer
+//   layer 1: tcgen05.mma kind::f16 SS (A, W from shared memory), M=128 N=128 K=16, fp32 accum in TMEM
+//   hidden epilogues: tcgen05.ld -> +bias, SiLU/Tanh -> hi/lo split -> tcgen05.st IN PLACE
+//   layers 2, 3: tcgen05.mma TS (A operand read straight from TMEM, W from shared memory)
 //   final epilogue: +bias -> LayerNorm -> *mul -> coalesced (+residual) stores
 //
-// One CTA (256 threads) owns a 128-row tile end to end; no intermediate touches HBM.  Operand
-// precision is a template: split operands (x = hi + lo, products hi*hi + lo*hi + hi*lo) restore
+// One persistent CTA per SM keeps TWO 128-row tiles in flight (TMEM slots 0/1, 256 columns each): the
+// MMA warp works on one tile's layer while an epilogue warpgroup turns the other tile's accumulator
+// into the next layer's operand.  No intermediate touches HBM or shared memory: a slot is two
+// 128-column regions X, Y;  L1: D=X | E1: X -> X (in place) | L2: A=X, D=Y | E2: Y -> Y | L3: A=Y, D=X.
+// In-place layout: the 32 fp32 columns of chunk c become 16 columns of packed hi pairs + 16 of lo pairs.
+//
+// Operand precision is a template: split operands (x = hi + lo, products hi*hi + lo*hi + hi*lo) restore
 // ~fp32 accuracy on the bf16/fp16 tensor pipe (single-pass bf16 fails the 1e-3 bar).
 //
 // Shared-memory operand layout: canonical UMMA K-major SWIZZLE_128B - a k-block is 64 elements
 // (128 B per row), rows in groups of 8 (1024 B atoms), 16-byte chunk c of row r stored at chunk
 // c ^ (r & 7).  Weights are pre-packed by gnnfd_pack_mlp into exactly this image per (layer,
-// k-block, part), so one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) lands a stage.
+// k-block, part), so one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) lands a unit.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -24,22 +30,27 @@ constexpr int TC_BM = 128;            // rows per tile == UMMA M
 constexpr int TC_H = 128;             // hidden width == UMMA N
 constexpr int TC_KB = 64;             // elements per k-block (128 B of 16-bit operands)
 constexpr int TC_IMG = TC_BM * 128;   // bytes of one [128 x 64] operand image = 16 KB
-// warp roles: 0-7 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = column half),
-//             8-15 producers (gather -> split -> swizzled A stage), 16 = TMA + MMA issuer
+// warp roles: 0-3 epilogue of even local tiles (TMEM slot 0), 4-7 epilogue of odd local tiles (slot 1)
+//             (warp & 3 = TMEM lane quarter, thread = row), 8-15 producers (gather -> split -> swizzled A
+//             stage), 16 = MMA issuer, 17 = weight loader (TMA bulk copies)
 constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 8;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32, TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
-constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;   // 544
-constexpr int TC_A_STAGES = 2;        // A ring: {A_hi, A_lo} images per stage
+constexpr int TC_WLD_WARP = TC_MMA_WARP + 1;
+constexpr int TC_THREADS = (TC_WLD_WARP + 1) * 32;   // 576
+constexpr int TC_A_STAGES = 3;        // A ring: {A_hi, A_lo} images per stage
 constexpr int TC_W_SLOTS = 4;         // W ring: one 16 KB image (hi or lo part of a k-block) per slot
-constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 64 KB
+constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 96 KB
 constexpr int TC_W_BYTES = TC_W_SLOTS * TC_IMG;        // 64 KB
-constexpr int TC_ACT = 4 * TC_IMG;    // hidden activation operand: 2 k-blocks x (hi, lo); also output staging
 constexpr int TC_STG_STRIDE = 36;     // floats per row of a warp's 32x32 output staging block
+constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * TC_STG_STRIDE * 4;   // 36 KB
+constexpr int TC_IDX_SLOTS = 4;
 constexpr int TC_IDX_SLOT = 9 * TC_BM;               // ints: [3 seg][3 idx][128 rows]
-constexpr int TC_SMEM = TC_A_BYTES + TC_W_BYTES + TC_ACT + 2 * TC_IDX_SLOT * 4 + 5 * TC_H * 4 +
-                        2 * TC_BM * 8 + 256 + 1024;
-constexpr int TC_TMEM_COLS = 256;     // two accumulators: tile j uses columns (j & 1) * 128
+constexpr int TC_NBAR = 24;
+constexpr int TC_SMEM = TC_A_BYTES + TC_W_BYTES + TC_STG_BYTES + TC_IDX_SLOTS * TC_IDX_SLOT * 4 +
+                        5 * TC_H * 4 + TC_NBAR * 8 + 64 + 1024;
+constexpr int TC_TMEM_COLS = 512;     // two slots x {X, Y} x 128 columns
+constexpr int TC_MAX_KB = 8;
 
 // ---------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -62,28 +73,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -94,13 +106,24 @@ __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T   (A: lane = row, 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
@@ -123,9 +146,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
+// Advancing K by 16 elements (32 B) inside the 128 B swizzle row adds 2 to the start field.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -164,6 +210,17 @@ __device__ __forceinline__ uint32_t sw128(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
+// how the producers assemble one 64-wide k-block of layer 1's input
+struct KbDesc {
+  const float *src;   // segment source matrix
+  int32_t ld;         // row stride (floats)
+  int32_t colk;       // first source column of this k-block
+  int32_t mode;       // GNNFD_SEG_*
+  int32_t kvalid;     // valid columns in this k-block (<= 64)
+  int32_t seg;        // segment number (index slot)
+  int32_t vec;        // 16-byte vector loads are legal
+};
+
 struct TcParams {
   gnnfd_mlp_args a;
   int kb1;       // k-blocks of layer 1
@@ -171,70 +228,118 @@ struct TcParams {
   int n3;        // UMMA N of layer 3: 128, or 16 for a narrow head
   uint32_t w_block_bytes;   // bytes of one packed 128-row k-block (all parts)
   uint32_t w3_block_bytes;  // bytes of one packed layer-3 k-block
+  int64_t direct_tile_bytes;   // bytes of one tile's rows of a contiguous DIRECT segment 0 (0: no L2 prefetch)
+  KbDesc kb[TC_MAX_KB];
 };
 
-// -------------------------------------------------------------------------------------- kernel
-// Weight units (one 16 KB image each: the hi or lo part of a 64-wide k-block) are consumed in the MMA
-// issue order   L1(0); for j: L2(j), L1(j+1), L3(j)   - L1 of the next tile is queued between L2 and L3
-// of the current one so the tensor pipe works on it while the epilogue warps turn L2's accumulator into
-// L3's operand.  WSeq enumerates that order for the loader cursor.
-// Diagnostic cycle counters of CTA 0 (role wait times), read back with gnnfd_tc_profile_read.
+// Diagnostic cycle counters of CTA 0 (role wait times), read back with gnnfd_tc_profile_read; only
+// recorded when the library is built with -DGNNFD_TC_PROF.
 __device__ unsigned long long g_tc_prof[16];
+#ifdef GNNFD_TC_PROF
+#define PROF_DECL unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long t_begin = clock64()
 #define PROF_WAIT(slot, stmt)                                  \
   do {                                                         \
     const long long t0_ = clock64();                           \
     stmt;                                                      \
     if (blockIdx.x == 0) prof[slot] += clock64() - t0_;        \
   } while (0)
+#else
+#define PROF_DECL do {} while (0)
+#define PROF_WAIT(slot, stmt) stmt
+#endif
 
-template <int NW>
-struct WSeq {
-  int T, j, step, kb, part, kb1;
-  bool valid;
-  __device__ void init(int tiles, int kb1_) {
-    T = tiles; kb1 = kb1_; j = -1; step = 1; kb = 0; part = 0; valid = tiles > 0;
+// ------------------------------------------------------------------------------------ producers
+__device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *ix, int64_t row0, int kb,
+                                              int rbase, int f4, float4 (&v)[8]) {
+  const KbDesc &d = p.kb[kb];
+  const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
+  const int32_t *ixs = ix + d.seg * 3 * TC_BM;
+  const bool active = f4 * 4 < ksteps * 16;
+  const int64_t rows = p.a.rows;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int r = rbase + 16 * jj;
+    const int64_t g = row0 + r;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (active && g < rows) {
+      const int64_t i0 = d.mode == GNNFD_SEG_DIRECT ? g : (int64_t)ixs[r];
+      const float *b0 = d.src + i0 * d.ld + d.colk + f4 * 4;
+      if (d.vec) {
+        if (f4 * 4 < d.kvalid) {
+          x = ldg_f4(b0);
+          if (d.mode >= GNNFD_SEG_SUM2) {
+            const float4 y = ldg_f4(d.src + (int64_t)ixs[TC_BM + r] * d.ld + d.colk + f4 * 4);
+            if (d.mode == GNNFD_SEG_DIFF2) { x.x -= y.x; x.y -= y.y; x.z -= y.z; x.w -= y.w; }
+            else { x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+            if (d.mode == GNNFD_SEG_MEAN3) {
+              const float4 z = ldg_f4(d.src + (int64_t)ixs[2 * TC_BM + r] * d.ld + d.colk + f4 * 4);
+              x.x = (x.x + z.x) / 3.0f; x.y = (x.y + z.y) / 3.0f;
+              x.z = (x.z + z.z) / 3.0f; x.w = (x.w + z.w) / 3.0f;
+            }
+          }
+        }
+      } else {
+        float t4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float t = 0.f;
+          if (f4 * 4 + q < d.kvalid) {
+            t = __ldg(b0 + q);
+            if (d.mode >= GNNFD_SEG_SUM2) {
+              const float y = __ldg(d.src + (int64_t)ixs[TC_BM + r] * d.ld + d.colk + f4 * 4 + q);
+              t = d.mode == GNNFD_SEG_DIFF2 ? t - y : t + y;
+              if (d.mode == GNNFD_SEG_MEAN3)
+                t = (t + __ldg(d.src + (int64_t)ixs[2 * TC_BM + r] * d.ld + d.colk + f4 * 4 + q)) / 3.0f;
+            }
+          }
+          t4[q] = t;
+        }
+        x = make_float4(t4[0], t4[1], t4[2], t4[3]);
+      }
+    }
+    v[jj] = x;
   }
-  __device__ int blocks() const { return step == 1 ? kb1 : 2; }
-  __device__ void advance() {
-    if (++part < NW) return;
-    part = 0;
-    if (++kb < blocks()) return;
-    kb = 0;
-    // next segment
-    if (j < 0) { j = 0; step = 0; return; }
-    ++step;
-    if (step == 1 && j + 1 >= T) ++step;
-    if (step == 3) { step = 0; ++j; if (j >= T) valid = false; }
-  }
-};
+}
 
+template <bool FP16, int NA>
+__device__ __forceinline__ void tc_store_block(uint8_t *sA, const float4 (&v)[8], int rbase, int f4, bool active) {
+  if (active) {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      const int r = rbase + 16 * jj;
+      uint32_t h0, l0, h1, l1;
+      split2<FP16>(v[jj].x, v[jj].y, h0, l0);
+      split2<FP16>(v[jj].z, v[jj].w, h1, l1);
+      const uint32_t off = sw128(r, f4 >> 1) + (f4 & 1) * 8;
+      *reinterpret_cast<uint2 *>(sA + off) = make_uint2(h0, h1);
+      if (NA == 2) *reinterpret_cast<uint2 *>(sA + TC_IMG + off) = make_uint2(l0, l1);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------- kernel
 template <bool FP16, int NA, int NW>
-__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const gnnfd_mlp_args &a = p.a;
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *s_a = smem;                                     // A ring: 2 x {hi, lo}
-  uint8_t *s_w = s_a + TC_A_BYTES;                         // W ring: 4 x 16 KB
-  uint8_t *s_act = s_w + TC_W_BYTES;                       // activations / output staging
-  int32_t *s_idx = (int32_t *)(s_act + TC_ACT);            // [2 tiles][3 seg][3][128]
-  float *s_vec = (float *)(s_idx + 2 * TC_IDX_SLOT);       // b1, b2, b3, ln_w, ln_b
-  float2 *s_stat = (float2 *)(s_vec + 5 * TC_H);           // [2 halves][128]
-  uint64_t *s_bar = (uint64_t *)(s_stat + 2 * TC_BM);
-  uint64_t *a_full = s_bar, *a_empty = s_bar + 2, *w_full = s_bar + 4, *w_empty = s_bar + 8;
-  uint64_t *acc_full = s_bar + 12, *acc_free = s_bar + 14, *act_ready = s_bar + 16;
-  uint32_t *s_tmem = (uint32_t *)(s_bar + 18);
+  uint8_t *s_a = smem;                                     // A ring
+  uint8_t *s_w = s_a + TC_A_BYTES;                         // W ring
+  float *s_stg = (float *)(s_w + TC_W_BYTES);              // output staging, one 32x36 block per epilogue warp
+  int32_t *s_idx = (int32_t *)((uint8_t *)s_stg + TC_STG_BYTES);   // [4 tiles][3 seg][3][128]
+  float *s_vec = (float *)(s_idx + TC_IDX_SLOTS * TC_IDX_SLOT);    // b1, b2, b3, ln_w, ln_b
+  uint64_t *s_bar = (uint64_t *)(s_vec + 5 * TC_H);
+  uint64_t *a_full = s_bar, *a_empty = s_bar + 3, *w_full = s_bar + 6, *w_empty = s_bar + 10;
+  uint64_t *acc_full = s_bar + 14, *acc_free = s_bar + 16, *hid_ready = s_bar + 18;   // hid_ready[slot*2 + half]
+  uint32_t *s_tmem = (uint32_t *)(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], TC_PROD_THREADS);
-      mbar_init(&a_empty[i], 1);
-      mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_free[i], TC_EPI_THREADS);
-    }
+    for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < TC_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    mbar_init(act_ready, TC_EPI_THREADS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 4); }
+    for (int i = 0; i < 4; ++i) mbar_init(&hid_ready[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
@@ -251,337 +356,295 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
 
   const int64_t n_tiles = (a.rows + TC_BM - 1) / TC_BM;
   const int T = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // tiles of this CTA
+  auto tile_row0 = [&](int j) { return ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * TC_BM; };
 
   if (warp >= TC_EPI_WARPS && warp < TC_MMA_WARP) {
     // =============================================================================== producers
     const int pt = tid - TC_EPI_THREADS;   // 0..255
     const int f4 = pt & 15;                // float4 column inside the 64-wide k-block
     const int rbase = pt >> 4;             // rows rbase + 16 j
+    const int NB = T * p.kb1;              // k-blocks this CTA produces, in MMA consumption order
 
-    auto stage_idx = [&](int j) {          // async copy of tile j's gather indices into slot j & 1
-      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * TC_BM;
-      int32_t *dst = s_idx + (j & 1) * TC_IDX_SLOT;
-      for (int s = 0; s < a.n_seg; ++s) {
-        const gnnfd_segment &sg = a.seg[s];
-        const int n_idx = sg.mode == GNNFD_SEG_DIRECT ? 0 : sg.mode == GNNFD_SEG_GATHER ? 1
-                          : sg.mode == GNNFD_SEG_MEAN3 ? 3 : 2;
-        for (int q = pt; q < n_idx * TC_BM; q += TC_PROD_THREADS) {
-          const int ji = q / TC_BM, r = q % TC_BM;
-          const int64_t g = row0 + r;
-          int32_t *d = dst + (s * 3 + ji) * TC_BM + r;
-          if (g < a.rows) cp_async4(d, sg.idx[ji] + g); else *d = 0;
+    auto stage_idx = [&](int j) {          // async copy of tile j's gather indices into slot j & 3
+      if (j < T) {
+        const int64_t row0 = tile_row0(j);
+        int32_t *dst = s_idx + (j & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT;
+        for (int s = 0; s < a.n_seg; ++s) {
+          const gnnfd_segment &sg = a.seg[s];
+          const int n_idx = sg.mode == GNNFD_SEG_DIRECT ? 0 : sg.mode == GNNFD_SEG_GATHER ? 1
+                            : sg.mode == GNNFD_SEG_MEAN3 ? 3 : 2;
+          for (int q = pt; q < n_idx * TC_BM; q += TC_PROD_THREADS) {
+            const int ji = q / TC_BM, r = q % TC_BM;
+            const int64_t g = row0 + r;
+            int32_t *d = dst + (s * 3 + ji) * TC_BM + r;
+            if (g < a.rows) cp_async4(d, sg.idx[ji] + g); else *d = 0;
+          }
+        }
+        if (pt == 0 && p.direct_tile_bytes > 0) {   // pull the tile's contiguous DIRECT rows into L2 early
+          const int64_t nrow = min((int64_t)TC_BM, a.rows - row0);
+          bulk_prefetch_l2(a.seg[0].src + row0 * a.seg[0].ld, (uint32_t)(nrow * a.seg[0].ld * 4));
         }
       }
+      cp_async_commit();
     };
-
-    float4 vn[8];
-    auto load_block = [&](int j, int kb) {   // issue the global loads of k-block kb of tile j into vn
-      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * TC_BM;
-      int seg = 0, seg_k0 = 0;
-      const int k0 = kb * TC_KB;
-      while (seg + 1 < a.n_seg && k0 >= seg_k0 + a.seg[seg].width) { seg_k0 += a.seg[seg].width; ++seg; }
-      const gnnfd_segment &sg = a.seg[seg];
-      const int kloc = k0 - seg_k0;
-      const int kvalid = min(TC_KB, sg.width - kloc);
+    auto issue = [&](int b, float4(&v)[8]) {
+      if (b < NB) {
+        const int j = b / p.kb1, kb = b - j * p.kb1;
+        tc_load_block(p, s_idx + (j & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT, tile_row0(j), kb, rbase, f4, v);
+      }
+    };
+    PROF_DECL;
+    auto step = [&](int b, float4(&v)[8]) {
+      const int j = b / p.kb1, kb = b - j * p.kb1;
+      if (kb == 0) {
+        // tile boundary: every index copy issued so far has landed (tiles <= j + 2) and every producer
+        // has issued its loads of tile j - 1, so that tile's index slot can be refilled with tile j + 3
+        if (j > 0) { cp_async_wait_all(); named_bar_sync(1, TC_PROD_THREADS); }
+        stage_idx(j + 3);
+      }
+      const int st = b % TC_A_STAGES;
+      if (b >= TC_A_STAGES) PROF_WAIT(0, mbar_wait(&a_empty[st], ((b / TC_A_STAGES) - 1) & 1));
       const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
-      const int32_t *ix = s_idx + (j & 1) * TC_IDX_SLOT + seg * 3 * TC_BM;
-      const bool vec = ((sg.ld & 3) == 0) && (((sg.col + kloc) & 3) == 0) && ((kvalid & 3) == 0) &&
-                       ((reinterpret_cast<uintptr_t>(sg.src) & 15) == 0);
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const int r = rbase + 16 * jj;
-        const int64_t g = row0 + r;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < a.rows && f4 * 4 < ksteps * 16) {
-          const int64_t i0 = sg.mode == GNNFD_SEG_DIRECT ? g : (int64_t)ix[r];
-          const float *b0 = sg.src + i0 * sg.ld + sg.col + kloc + f4 * 4;
-          if (vec) {
-            if (f4 * 4 < kvalid) {
-              x = ldg_f4(b0);
-              if (sg.mode >= GNNFD_SEG_SUM2) {
-                const float4 y = ldg_f4(sg.src + (int64_t)ix[TC_BM + r] * sg.ld + sg.col + kloc + f4 * 4);
-                if (sg.mode == GNNFD_SEG_DIFF2) { x.x -= y.x; x.y -= y.y; x.z -= y.z; x.w -= y.w; }
-                else { x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-                if (sg.mode == GNNFD_SEG_MEAN3) {
-                  const float4 z = ldg_f4(sg.src + (int64_t)ix[2 * TC_BM + r] * sg.ld + sg.col + kloc + f4 * 4);
-                  x.x = (x.x + z.x) / 3.0f; x.y = (x.y + z.y) / 3.0f;
-                  x.z = (x.z + z.z) / 3.0f; x.w = (x.w + z.w) / 3.0f;
-                }
-              }
-            }
-          } else {
-            float t4[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float t = 0.f;
-              if (f4 * 4 + q < kvalid) {
-                t = __ldg(b0 + q);
-                if (sg.mode >= GNNFD_SEG_SUM2) {
-                  const float y = __ldg(sg.src + (int64_t)ix[TC_BM + r] * sg.ld + sg.col + kloc + f4 * 4 + q);
-                  t = sg.mode == GNNFD_SEG_DIFF2 ? t - y : t + y;
-                  if (sg.mode == GNNFD_SEG_MEAN3)
-                    t = (t + __ldg(sg.src + (int64_t)ix[2 * TC_BM + r] * sg.ld + sg.col + kloc + f4 * 4 + q)) / 3.0f;
-                }
-              }
-              t4[q] = t;
-            }
-            x = make_float4(t4[0], t4[1], t4[2], t4[3]);
-          }
-        }
-        vn[jj] = x;
-      }
+      tc_store_block<FP16, NA>(s_a + st * 2 * TC_IMG, v, rbase, f4, f4 * 4 < ksteps * 16);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[st]);
+      issue(b + 2, v);
     };
 
-    if (T > 0) {
-      stage_idx(0);
-      cp_async_commit_wait_all();
-      named_bar_sync(1, TC_PROD_THREADS);
-      if (T > 1) stage_idx(1);
-      load_block(0, 0);
+    float4 v0[8], v1[8];
+    stage_idx(0); stage_idx(1); stage_idx(2);
+    cp_async_wait_all();
+    named_bar_sync(1, TC_PROD_THREADS);
+    issue(0, v0);
+    issue(1, v1);
+    for (int b = 0; b < NB; b += 2) {
+      step(b, v0);
+      if (b + 1 < NB) step(b + 1, v1);
     }
-    uint32_t pa = 0;
-    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long t_begin = clock64();
-    for (int j = 0; j < T; ++j) {
-      for (int kb = 0; kb < p.kb1; ++kb, ++pa) {
-        float4 vc[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) vc[jj] = vn[jj];
-        // issue the next block's loads before touching shared memory (keeps HBM requests in flight)
-        if (kb + 1 < p.kb1) {
-          load_block(j, kb + 1);
-        } else if (j + 1 < T) {
-          cp_async_commit_wait_all();                 // indices of tile j+1 have landed
-          named_bar_sync(1, TC_PROD_THREADS);         // ... for every producer thread; slot j&1 is free
-          if (j + 2 < T) stage_idx(j + 2);
-          load_block(j + 1, 0);
-        }
-        const int st = pa & 1;
-        if (pa >= 2) PROF_WAIT(0, mbar_wait(&a_empty[st], ((pa >> 1) - 1) & 1));
-        uint8_t *sA = s_a + st * 2 * TC_IMG;
-        const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
-        if (f4 * 4 < ksteps * 16) {
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const int r = rbase + 16 * jj;
-            uint32_t h0, l0, h1, l1;
-            split2<FP16>(vc[jj].x, vc[jj].y, h0, l0);
-            split2<FP16>(vc[jj].z, vc[jj].w, h1, l1);
-            const uint32_t off = sw128(r, f4 >> 1) + (f4 & 1) * 8;
-            *reinterpret_cast<uint2 *>(sA + off) = make_uint2(h0, h1);
-            if (NA == 2) *reinterpret_cast<uint2 *>(sA + TC_IMG + off) = make_uint2(l0, l1);
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(&a_full[st]);
-      }
-    }
-    if (blockIdx.x == 0 && pt == 0) {
-      g_tc_prof[12] = clock64() - t_begin;
-      g_tc_prof[13] = prof[0];
-    }
-  } else if (warp == TC_MMA_WARP) {
-    // ======================================================================= TMA + MMA issuer
+    cp_async_wait_all();
+#ifdef GNNFD_TC_PROF
+    if (blockIdx.x == 0 && pt == 0) { g_tc_prof[12] = clock64() - t_begin; g_tc_prof[13] = prof[0]; }
+#endif
+  } else if (warp == TC_WLD_WARP) {
+    // ============================================================================ weight loader
     if (lane == 0 && T > 0) {
-      constexpr uint32_t IDESC_H = make_idesc(FP16 ? 0 : 1, TC_H);
-      const uint32_t idesc3 = make_idesc(FP16 ? 0 : 1, p.n3);
       const uint8_t *w1p = (const uint8_t *)a.packed;
       const uint8_t *w2p = w1p + (size_t)p.kb1 * p.w_block_bytes;
       const uint8_t *w3p = w2p + (size_t)2 * p.w_block_bytes;
       const uint32_t w3_part = p.w3_block_bytes / NW;
-      WSeq<NW> seq;
-      seq.init(T, p.kb1);
-      uint32_t wl = 0, wc = 0, ca = 0;
-      unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const long long t_begin = clock64();
-
-      auto prefetch = [&](uint32_t upto) {      // issue weight units [wl, upto)
-        while (wl < upto && seq.valid) {
-          const int slot = wl & (TC_W_SLOTS - 1);
-          if (wl >= TC_W_SLOTS) PROF_WAIT(1, mbar_wait(&w_empty[slot], ((wl / TC_W_SLOTS) - 1) & 1));
-          const uint8_t *src;
-          uint32_t bytes;
-          if (seq.step == 1) { src = w1p + (size_t)seq.kb * p.w_block_bytes + seq.part * TC_IMG; bytes = TC_IMG; }
-          else if (seq.step == 0) { src = w2p + (size_t)seq.kb * p.w_block_bytes + seq.part * TC_IMG; bytes = TC_IMG; }
-          else { src = w3p + (size_t)seq.kb * p.w3_block_bytes + seq.part * w3_part; bytes = w3_part; }
-          mbar_expect_tx(&w_full[slot], bytes);
-          bulk_g2s(s_w + slot * TC_IMG, src, bytes, &w_full[slot]);
-          seq.advance();
-          ++wl;
-        }
+      uint32_t wl = 0;
+      auto load_unit = [&](const uint8_t *src, uint32_t bytes) {
+        const int slot = wl & (TC_W_SLOTS - 1);
+        if (wl >= TC_W_SLOTS) mbar_wait(&w_empty[slot], ((wl / TC_W_SLOTS) - 1) & 1);
+        mbar_expect_tx(&w_full[slot], bytes);
+        bulk_g2s(s_w + slot * TC_IMG, src, bytes, &w_full[slot]);
+        ++wl;
       };
-      // one k-block: A images at a_hi / a_lo, weight parts from the ring; `first` = start of a layer
-      auto mma_block = [&](uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int ksteps, uint32_t idesc, bool first) {
-        prefetch(wc + 3);
-        int slot = wc & (TC_W_SLOTS - 1);
+      // same order as the MMA issuer: per pair of tiles  L1 L1 | L2 L2 | L3 L3
+      for (int j0 = 0; j0 < T; j0 += 2) {
+        const int nt = min(2, T - j0);
+        for (int t = 0; t < nt; ++t)
+          for (int kb = 0; kb < p.kb1; ++kb)
+            for (int part = 0; part < NW; ++part) load_unit(w1p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
+        for (int t = 0; t < nt; ++t)
+          for (int kb = 0; kb < 2; ++kb)
+            for (int part = 0; part < NW; ++part) load_unit(w2p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
+        for (int t = 0; t < nt; ++t)
+          for (int kb = 0; kb < 2; ++kb)
+            for (int part = 0; part < NW; ++part) load_unit(w3p + (size_t)kb * p.w3_block_bytes + part * w3_part, w3_part);
+      }
+    }
+    __syncwarp();
+  } else if (warp == TC_MMA_WARP) {
+    // ================================================================================ MMA issuer
+    if (lane == 0 && T > 0) {
+      constexpr uint32_t IDESC_H = make_idesc(FP16 ? 0 : 1, TC_H);
+      const uint32_t idesc3 = make_idesc(FP16 ? 0 : 1, p.n3);
+      uint32_t wc = 0, ca = 0;
+      PROF_DECL;
+      // consume one weight unit: returns its descriptor; release with umma_commit(&w_empty[slot])
+      auto w_acquire = [&](int &slot) {
+        slot = wc & (TC_W_SLOTS - 1);
         PROF_WAIT(2, mbar_wait(&w_full[slot], (wc / TC_W_SLOTS) & 1));
         tc_fence_after();
-        uint32_t wb = smem_u32(s_w + slot * TC_IMG);
-        for (int k = 0; k < ksteps; ++k) {
-          umma_f16(d_tmem, make_desc(a_hi + k * 32), make_desc(wb + k * 32), idesc, !(first && k == 0));
-          if (NA == 2) umma_f16(d_tmem, make_desc(a_lo + k * 32), make_desc(wb + k * 32), idesc, 1);
-        }
-        umma_commit(&w_empty[slot]);
         ++wc;
-        if (NW == 2) {
-          prefetch(wc + 3);
-          slot = wc & (TC_W_SLOTS - 1);
-          PROF_WAIT(2, mbar_wait(&w_full[slot], (wc / TC_W_SLOTS) & 1));
-          tc_fence_after();
-          wb = smem_u32(s_w + slot * TC_IMG);
-          for (int k = 0; k < ksteps; ++k)
-            umma_f16(d_tmem, make_desc(a_hi + k * 32), make_desc(wb + k * 32), idesc, 1);
-          umma_commit(&w_empty[slot]);
-          ++wc;
-        }
+        return make_desc(smem_u32(s_w + slot * TC_IMG));
       };
       auto layer1 = [&](int j) {
-        const int b = j & 1;
-        if (j >= 2) { PROF_WAIT(3, mbar_wait(&acc_free[b], ((j >> 1) - 1) & 1)); tc_fence_after(); }
-        const uint32_t d = tmem_base + b * TC_H;
+        const int sl = j & 1, n = j >> 1;
+        if (n >= 1) { PROF_WAIT(3, mbar_wait(&acc_free[sl], (n - 1) & 1)); tc_fence_after(); }
+        const uint32_t d = tmem_base + sl * 256;
         for (int kb = 0; kb < p.kb1; ++kb, ++ca) {
-          const int st = ca & 1;
-          PROF_WAIT(4, mbar_wait(&a_full[st], (ca >> 1) & 1));
+          const int st = ca % TC_A_STAGES;
+          PROF_WAIT(4, mbar_wait(&a_full[st], (ca / TC_A_STAGES) & 1));
           tc_fence_after();
-          const uint32_t ah = smem_u32(s_a + st * 2 * TC_IMG);
-          mma_block(d, ah, ah + TC_IMG, (kb == p.kb1 - 1) ? p.ksteps1 : 4, IDESC_H, kb == 0);
+          const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
+          const uint64_t ah = make_desc(smem_u32(s_a + st * 2 * TC_IMG)), al = ah + (TC_IMG >> 4);
+          int slot;
+          uint64_t wb = w_acquire(slot);
+          for (int k = 0; k < ksteps; ++k) {
+            umma_ss(d, ah + 2 * k, wb + 2 * k, IDESC_H, (kb | k) != 0);
+            if (NA == 2) umma_ss(d, al + 2 * k, wb + 2 * k, IDESC_H, 1);
+          }
+          umma_commit(&w_empty[slot]);
+          if (NW == 2) {
+            wb = w_acquire(slot);
+            for (int k = 0; k < ksteps; ++k) umma_ss(d, ah + 2 * k, wb + 2 * k, IDESC_H, 1);
+            umma_commit(&w_empty[slot]);
+          }
           umma_commit(&a_empty[st]);
         }
-        umma_commit(&acc_full[b]);
+        umma_commit(&acc_full[sl]);
       };
+      // layers 2 and 3: A = the in-place converted accumulator region, 32-column chunk per 32 elements
       auto layer23 = [&](int j, int layer) {
-        const int b = j & 1;
-        PROF_WAIT(5, mbar_wait(act_ready, layer == 2 ? 0 : 1));
-        tc_fence_after();
-        const uint32_t d = tmem_base + b * TC_H;
+        const int sl = j & 1;
+        const uint32_t xr = tmem_base + sl * 256, yr = xr + 128;
+        const uint32_t a_reg = layer == 2 ? xr : yr, d = layer == 2 ? yr : xr;
+        const uint32_t idesc = layer == 2 ? IDESC_H : idesc3;
         for (int kb = 0; kb < 2; ++kb) {
-          const uint32_t ah = smem_u32(s_act) + kb * 2 * TC_IMG;
-          mma_block(d, ah, ah + TC_IMG, 4, layer == 2 ? IDESC_H : idesc3, kb == 0);
+          PROF_WAIT(5, mbar_wait(&hid_ready[sl * 2 + kb], layer == 2 ? 0 : 1));
+          tc_fence_after();
+          int slot;
+          uint64_t wb = w_acquire(slot);
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ta = a_reg + (kb * 2 + (k >> 1)) * 32 + (k & 1) * 8;
+            umma_ts(d, ta, wb + 2 * k, idesc, (kb | k) != 0);
+            if (NA == 2) umma_ts(d, ta + 16, wb + 2 * k, idesc, 1);
+          }
+          umma_commit(&w_empty[slot]);
+          if (NW == 2) {
+            wb = w_acquire(slot);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ta = a_reg + (kb * 2 + (k >> 1)) * 32 + (k & 1) * 8;
+              umma_ts(d, ta, wb + 2 * k, idesc, 1);
+            }
+            umma_commit(&w_empty[slot]);
+          }
         }
-        umma_commit(&acc_full[b]);
+        umma_commit(&acc_full[sl]);
       };
-
-      layer1(0);
-      for (int j = 0; j < T; ++j) {
-        layer23(j, 2);
-        if (j + 1 < T) layer1(j + 1);
-        layer23(j, 3);
+      for (int j0 = 0; j0 < T; j0 += 2) {
+        const int nt = min(2, T - j0);
+        for (int t = 0; t < nt; ++t) layer1(j0 + t);
+        for (int t = 0; t < nt; ++t) layer23(j0 + t, 2);
+        for (int t = 0; t < nt; ++t) layer23(j0 + t, 3);
       }
+#ifdef GNNFD_TC_PROF
       if (blockIdx.x == 0) {
         g_tc_prof[0] = clock64() - t_begin;
         for (int i = 1; i < 6; ++i) g_tc_prof[i] = prof[i];
         g_tc_prof[6] = (unsigned long long)T;
       }
+#endif
     }
     __syncwarp();
   } else {
     // ================================================================================ epilogue
-    const int q4 = warp & 3, ehalf = warp >> 2;
-    const int erow = q4 * 32 + lane;
-    float *stg = (float *)s_act + warp * (32 * TC_STG_STRIDE);   // this warp's 32x32 staging block
-    unsigned long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long t_begin = clock64();
-    for (int j = 0; j < T; ++j) {
-      const int b = j & 1;
-      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * TC_BM;
-      const uint32_t t_acc = tmem_base + b * TC_H + ((uint32_t)(q4 * 32) << 16) + ehalf * 64;
-      const uint32_t ph0 = 3u * (uint32_t)(j >> 1);
-      // ---- hidden layers: accumulator -> +bias, act -> hi/lo -> next layer's A operand in s_act
+    const int sl = warp >> 2, q4 = warp & 3;
+    const int erow = q4 * 32 + lane;                       // row of the tile owned by this thread
+    float *stg = s_stg + warp * (32 * TC_STG_STRIDE);      // this warp's 32x32 staging block
+    const uint32_t xr = tmem_base + sl * 256 + ((uint32_t)(q4 * 32) << 16), yr = xr + 128;
+    const int rr = lane >> 3, c4 = lane & 7;               // copy-out mapping: 4 rows x 128 B per instruction
+    PROF_DECL;
+    for (int j = sl; j < T; j += 2) {
+      const int n = j >> 1;
+      const int64_t row0 = tile_row0(j);
+      // ---- hidden layers: accumulator -> +bias, act -> hi/lo pairs, written back in place
       for (int layer = 0; layer < 2; ++layer) {
-        PROF_WAIT(0, mbar_wait(&acc_full[b], (ph0 + layer) & 1));
-        __syncwarp();
+        PROF_WAIT(0, mbar_wait(&acc_full[sl], (3 * n + layer) & 1));
         tc_fence_after();
+        const uint32_t reg = layer == 0 ? xr : yr;
         const float *bias = s_vec + layer * TC_H;
-#pragma unroll
-        for (int h32 = 0; h32 < 2; ++h32) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
           float acc[32];
-          tmem_ld32(t_acc + h32 * 32, acc);
+          tmem_ld32(reg + c * 32, acc);
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int col = ehalf * 64 + h32 * 32 + c * 8 + q * 2;
-              float x0 = acc[c * 8 + q * 2] + bias[col];
-              float x1 = acc[c * 8 + q * 2 + 1] + bias[col + 1];
-              if (a.act == GNNFD_ACT_SILU) { x0 = silu_fast(x0); x1 = silu_fast(x1); }
-              else { x0 = tanhf(x0); x1 = tanhf(x1); }
-              split2<FP16>(x0, x1, hi[q], lo[q]);
-            }
-            const uint32_t off = (uint32_t)ehalf * (2 * TC_IMG) + sw128(erow, h32 * 4 + c);
-            *reinterpret_cast<uint4 *>(s_act + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (NA == 2) *reinterpret_cast<uint4 *>(s_act + TC_IMG + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int i = 0; i < 16; ++i) {
+            const float2 b2 = *reinterpret_cast<const float2 *>(bias + c * 32 + 2 * i);
+            float x0 = acc[2 * i] + b2.x, x1 = acc[2 * i + 1] + b2.y;
+            if (a.act == GNNFD_ACT_SILU) { x0 = silu_fast(x0); x1 = silu_fast(x1); }
+            else { x0 = tanhf(x0); x1 = tanhf(x1); }
+            split2<FP16>(x0, x1, hi[i], lo[i]);
+          }
+          tmem_st16(reg + c * 32, hi);
+          if (NA == 2) tmem_st16(reg + c * 32 + 16, lo);
+          if (c & 1) {   // a 64-element k-block of the next layer's operand is complete
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hid_ready[sl * 2 + (c >> 1)]);
           }
         }
-        tc_fence_before();
-        fence_proxy_async();
-        mbar_arrive(act_ready);
       }
       // ---- final epilogue
-      PROF_WAIT(1, mbar_wait(&acc_full[b], (ph0 + 2) & 1));
-      __syncwarp();
+      PROF_WAIT(1, mbar_wait(&acc_full[sl], (3 * n + 2) & 1));
       tc_fence_after();
       if (a.n_out == TC_H) {
         float mean = 0.f, rstd = 1.f;
         if (a.has_ln) {
-          float s = 0.f;
-#pragma unroll
-          for (int h32 = 0; h32 < 2; ++h32) {
+          // shifted single pass: sums of (x - x0), (x - x0)^2
+          float shift = 0.f, s = 0.f, qv = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
             float acc[32];
-            tmem_ld32(t_acc + h32 * 32, acc);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) s += acc[i] + s_vec[2 * TC_H + ehalf * 64 + h32 * 32 + i];
-          }
-          s_stat[ehalf * TC_BM + erow].x = s;
-          named_bar_sync(2, TC_EPI_THREADS);
-          mean = (s_stat[erow].x + s_stat[TC_BM + erow].x) * (1.0f / TC_H);
-          float qv = 0.f;
-#pragma unroll
-          for (int h32 = 0; h32 < 2; ++h32) {
-            float acc[32];
-            tmem_ld32(t_acc + h32 * 32, acc);
+            tmem_ld32(xr + c * 32, acc);
+            if (c == 0) shift = acc[0] + s_vec[2 * TC_H];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float d = acc[i] + s_vec[2 * TC_H + ehalf * 64 + h32 * 32 + i] - mean;
-              qv += d * d;
+              const float d = acc[i] + s_vec[2 * TC_H + c * 32 + i] - shift;
+              s += d;
+              qv = fmaf(d, d, qv);
             }
           }
-          s_stat[ehalf * TC_BM + erow].y = qv;
-          named_bar_sync(2, TC_EPI_THREADS);
-          rstd = rsqrtf((s_stat[erow].y + s_stat[TC_BM + erow].y) * (1.0f / TC_H) + a.ln_eps);
+          const float md = s * (1.0f / TC_H);
+          mean = shift + md;
+          rstd = rsqrtf(fmaxf(qv * (1.0f / TC_H) - md * md, 0.f) + a.ln_eps);
         }
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          // residual rows of this chunk, coalesced mapping, requested before the TMEM read
+          float4 res[8];
+          if (a.out_sum) {
 #pragma unroll
-        for (int h32 = 0; h32 < 2; ++h32) {
-          float acc[32];
-          tmem_ld32(t_acc + h32 * 32, acc);
-          if (h32 == 1) {   // last TMEM read of this tile: the accumulator may be overwritten
-            tc_fence_before();
-            mbar_arrive(&acc_free[b]);
+            for (int jr = 0; jr < 8; ++jr) {
+              const int64_t g = row0 + q4 * 32 + jr * 4 + rr;
+              res[jr] = g < a.rows ? ldg_f4(a.residual + (size_t)g * TC_H + c * 32 + c4 * 4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
           }
-          const int cbase = ehalf * 64 + h32 * 32;
+          float acc[32];
+          tmem_ld32(xr + c * 32, acc);
+          if (c == 3) {   // last TMEM read of this tile: the slot may be overwritten by the next L1
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[sl]);
+          }
+          const float *b3 = s_vec + 2 * TC_H + c * 32, *gw = s_vec + 3 * TC_H + c * 32, *gb = s_vec + 4 * TC_H + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 o;
-            o.x = (acc[i] + s_vec[2 * TC_H + cbase + i] - mean) * rstd * s_vec[3 * TC_H + cbase + i] + s_vec[4 * TC_H + cbase + i];
-            o.y = (acc[i + 1] + s_vec[2 * TC_H + cbase + i + 1] - mean) * rstd * s_vec[3 * TC_H + cbase + i + 1] + s_vec[4 * TC_H + cbase + i + 1];
-            o.z = (acc[i + 2] + s_vec[2 * TC_H + cbase + i + 2] - mean) * rstd * s_vec[3 * TC_H + cbase + i + 2] + s_vec[4 * TC_H + cbase + i + 2];
-            o.w = (acc[i + 3] + s_vec[2 * TC_H + cbase + i + 3] - mean) * rstd * s_vec[3 * TC_H + cbase + i + 3] + s_vec[4 * TC_H + cbase + i + 3];
+            o.x = (acc[i] + b3[i] - mean) * rstd * gw[i] + gb[i];
+            o.y = (acc[i + 1] + b3[i + 1] - mean) * rstd * gw[i + 1] + gb[i + 1];
+            o.z = (acc[i + 2] + b3[i + 2] - mean) * rstd * gw[i + 2] + gb[i + 2];
+            o.w = (acc[i + 3] + b3[i + 3] - mean) * rstd * gw[i + 3] + gb[i + 3];
             *reinterpret_cast<float4 *>(stg + lane * TC_STG_STRIDE + i) = o;
           }
           __syncwarp();
-          // coalesced copy-out of the 32x32 block: each instruction covers 4 rows x 128 B
-          const int rr = lane >> 3, c4 = lane & 7;
 #pragma unroll
           for (int jr = 0; jr < 8; ++jr) {
             const int rl = jr * 4 + rr;
             const int64_t g = row0 + q4 * 32 + rl;
             if (g < a.rows) {
               float4 o = *reinterpret_cast<const float4 *>(stg + rl * TC_STG_STRIDE + c4 * 4);
-              const size_t off = (size_t)g * TC_H + cbase + c4 * 4;
+              const size_t off = (size_t)g * TC_H + c * 32 + c4 * 4;
               if (a.mul) { const float4 m = ldg_f4(a.mul + off); o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w; }
               if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + off) = o;
               if (a.out_sum) {
-                float4 r4 = ldg_f4(a.residual + off);
+                float4 r4 = res[jr];
                 r4.x += o.x; r4.y += o.y; r4.z += o.z; r4.w += o.w;
                 *reinterpret_cast<float4 *>(a.out_sum + off) = r4;
               }
@@ -589,44 +652,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const TcParams p)
           }
           __syncwarp();
         }
-        // staging aliases s_act: the next tile's hidden epilogue writes it only after every epilogue
-        // thread is done reading its staging block
-        named_bar_sync(2, TC_EPI_THREADS);
       } else {
-        if (ehalf == 0) {
-          uint32_t r16[16];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r16[0]), "=r"(r16[1]), "=r"(r16[2]), "=r"(r16[3]), "=r"(r16[4]), "=r"(r16[5]), "=r"(r16[6]),
-                "=r"(r16[7]), "=r"(r16[8]), "=r"(r16[9]), "=r"(r16[10]), "=r"(r16[11]), "=r"(r16[12]),
-                "=r"(r16[13]), "=r"(r16[14]), "=r"(r16[15])
-              : "r"(t_acc)
-              : "memory");
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int64_t g = row0 + erow;
-          if (g < a.rows) {
+        float acc[16];
+        tmem_ld16(xr, acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_free[sl]);
+        const int64_t g = row0 + erow;
+        if (g < a.rows) {
 #pragma unroll
-            for (int o = 0; o < 16; ++o) {
-              if (o < a.n_out) {
-                float vv = __uint_as_float(r16[o]) + s_vec[2 * TC_H + o];
-                const size_t off = (size_t)g * a.n_out + o;
-                if (a.mul) vv *= __ldg(a.mul + off);
-                if (a.out_raw) a.out_raw[off] = vv;
-                if (a.out_sum) a.out_sum[off] = __ldg(a.residual + off) + vv;
-              }
+          for (int o = 0; o < 16; ++o) {
+            if (o < a.n_out) {
+              float vv = acc[o] + s_vec[2 * TC_H + o];
+              const size_t off = (size_t)g * a.n_out + o;
+              if (a.mul) vv *= __ldg(a.mul + off);
+              if (a.out_raw) a.out_raw[off] = vv;
+              if (a.out_sum) a.out_sum[off] = __ldg(a.residual + off) + vv;
             }
           }
         }
-        tc_fence_before();
-        mbar_arrive(&acc_free[b]);
       }
     }
+#ifdef GNNFD_TC_PROF
     if (blockIdx.x == 0 && tid == 0) {
       g_tc_prof[8] = clock64() - t_begin;
       g_tc_prof[9] = prof[0];
       g_tc_prof[10] = prof[1];
     }
+#endif
   }
 
   tc_fence_before();
@@ -659,8 +712,13 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, int n_rows_w, i
 }
 
 int tc_profile_read(unsigned long long *out16) {
+#ifndef GNNFD_TC_PROF
+  set_error("gnnfd_tc_profile_read: library built without -DGNNFD_TC_PROF");
+  return GNNFD_E_UNSUPPORTED;
+#else
   GNNFD_CUDA(cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(unsigned long long) * 16));
   return GNNFD_OK;
+#endif
 }
 
 struct TcMode { bool fp16; int na, nw; };
@@ -719,7 +777,7 @@ int pack_mlp_tc(const gnnfd_mlp_args *a, void *packed_out, cudaStream_t stream) 
 int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   TcMode m;
   if (!tc_mode(a->precision, m)) { set_error("mlp_forward_tc: bad precision"); return GNNFD_E_BADARG; }
-  TcParams p;
+  TcParams p{};
   p.a = *a;
   if (tc_geometry(a, m, p) != GNNFD_OK) {
     set_error("mlp_forward_tc: unsupported shape (hidden=%d n_out=%d)", a->hidden, a->n_out);
@@ -732,6 +790,24 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
         set_error("mlp_forward_tc: with several segments every width must be a multiple of 64");
         return GNNFD_E_UNSUPPORTED;
       }
+  if (p.kb1 > TC_MAX_KB) { set_error("mlp_forward_tc: k_in too large"); return GNNFD_E_UNSUPPORTED; }
+  for (int kb = 0, seg = 0, seg_k0 = 0; kb < p.kb1; ++kb) {
+    const int k0 = kb * TC_KB;
+    while (seg + 1 < a->n_seg && k0 >= seg_k0 + a->seg[seg].width) { seg_k0 += a->seg[seg].width; ++seg; }
+    const gnnfd_segment &sg = a->seg[seg];
+    KbDesc &d = p.kb[kb];
+    const int kloc = k0 - seg_k0;
+    d.src = sg.src; d.ld = sg.ld; d.colk = sg.col + kloc; d.mode = sg.mode; d.seg = seg;
+    d.kvalid = sg.width - kloc < TC_KB ? sg.width - kloc : TC_KB;
+    d.vec = ((sg.ld & 3) == 0) && ((d.colk & 3) == 0) && ((d.kvalid & 3) == 0) &&
+            ((reinterpret_cast<uintptr_t>(sg.src) & 15) == 0);
+  }
+  {
+    const gnnfd_segment &s0 = a->seg[0];
+    const bool contig = s0.mode == GNNFD_SEG_DIRECT && s0.col == 0 && s0.width == s0.ld && (s0.ld & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(s0.src) & 15) == 0;
+    p.direct_tile_bytes = contig ? (int64_t)TC_BM * s0.ld * 4 : 0;
+  }
   const int64_t n_tiles = (a->rows + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
 #define LAUNCH(FP, NA_, NW_)                                                                              \
