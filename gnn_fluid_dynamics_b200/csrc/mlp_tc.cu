@@ -205,6 +205,33 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
   }
 }
 
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 16 activations at a time, written stage by stage so the MUFU latencies of independent elements overlap
+template <int ACT>
+__device__ __forceinline__ void act16(float (&v)[16]) {
+  if constexpr (ACT == GNNFD_ACT_SILU) {
+    float e[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = ex2_ftz(v[i] * -1.4426950408889634f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) e[i] = rcp_ftz(1.0f + e[i]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= e[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
+  }
+}
+
 // byte offset of 16-byte chunk `c` of row `r` inside a [rows x 64] SWIZZLE_128B image
 __device__ __forceinline__ uint32_t sw128(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
@@ -249,55 +276,97 @@ __device__ unsigned long long g_tc_prof[16];
 #endif
 
 // ------------------------------------------------------------------------------------ producers
-__device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *ix, int64_t row0, int kb,
-                                              int rbase, int f4, float4 (&v)[8]) {
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
+// generic (slow) path: partial k-blocks, unaligned sources
+__device__ __noinline__ void tc_load_block_generic(const TcParams &p, const int32_t *ix, int64_t row0, int kb,
+                                                   int rbase, int f4, float4 (&v)[8]) {
   const KbDesc &d = p.kb[kb];
   const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
   const int32_t *ixs = ix + d.seg * 3 * TC_BM;
   const bool active = f4 * 4 < ksteps * 16;
   const int64_t rows = p.a.rows;
-#pragma unroll
+#pragma unroll 1
   for (int jj = 0; jj < 8; ++jj) {
     const int r = rbase + 16 * jj;
     const int64_t g = row0 + r;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    float t4[4] = {0.f, 0.f, 0.f, 0.f};
     if (active && g < rows) {
       const int64_t i0 = d.mode == GNNFD_SEG_DIRECT ? g : (int64_t)ixs[r];
       const float *b0 = d.src + i0 * d.ld + d.colk + f4 * 4;
-      if (d.vec) {
-        if (f4 * 4 < d.kvalid) {
-          x = ldg_f4(b0);
-          if (d.mode >= GNNFD_SEG_SUM2) {
-            const float4 y = ldg_f4(d.src + (int64_t)ixs[TC_BM + r] * d.ld + d.colk + f4 * 4);
-            if (d.mode == GNNFD_SEG_DIFF2) { x.x -= y.x; x.y -= y.y; x.z -= y.z; x.w -= y.w; }
-            else { x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
-            if (d.mode == GNNFD_SEG_MEAN3) {
-              const float4 z = ldg_f4(d.src + (int64_t)ixs[2 * TC_BM + r] * d.ld + d.colk + f4 * 4);
-              x.x = (x.x + z.x) / 3.0f; x.y = (x.y + z.y) / 3.0f;
-              x.z = (x.z + z.z) / 3.0f; x.w = (x.w + z.w) / 3.0f;
-            }
-          }
-        }
-      } else {
-        float t4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float t = 0.f;
-          if (f4 * 4 + q < d.kvalid) {
-            t = __ldg(b0 + q);
-            if (d.mode >= GNNFD_SEG_SUM2) {
-              const float y = __ldg(d.src + (int64_t)ixs[TC_BM + r] * d.ld + d.colk + f4 * 4 + q);
-              t = d.mode == GNNFD_SEG_DIFF2 ? t - y : t + y;
-              if (d.mode == GNNFD_SEG_MEAN3)
-                t = (t + __ldg(d.src + (int64_t)ixs[2 * TC_BM + r] * d.ld + d.colk + f4 * 4 + q)) / 3.0f;
-            }
+      for (int q = 0; q < 4; ++q) {
+        float t = 0.f;
+        if (f4 * 4 + q < d.kvalid) {
+          t = __ldg(b0 + q);
+          if (d.mode >= GNNFD_SEG_SUM2) {
+            const float y = __ldg(d.src + (int64_t)ixs[TC_BM + r] * d.ld + d.colk + f4 * 4 + q);
+            t = d.mode == GNNFD_SEG_DIFF2 ? t - y : t + y;
+            if (d.mode == GNNFD_SEG_MEAN3)
+              t = (t + __ldg(d.src + (int64_t)ixs[2 * TC_BM + r] * d.ld + d.colk + f4 * 4 + q)) / 3.0f;
           }
-          t4[q] = t;
         }
-        x = make_float4(t4[0], t4[1], t4[2], t4[3]);
+        t4[q] = t;
       }
     }
-    v[jj] = x;
+    v[jj] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+  }
+}
+
+// Issue the global loads of k-block kb of the tile starting at row0 into v.  Rows past the end of the
+// matrix read a clamped (valid) row: their results are never stored.
+__device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *ix, int64_t row0, int kb,
+                                              int rbase, int f4, float4 (&v)[8]) {
+  const KbDesc &d = p.kb[kb];
+  if (!d.vec || d.kvalid != TC_KB) {
+    float4 t[8];   // only this temporary gets a stack home; v stays in registers
+    tc_load_block_generic(p, ix, row0, kb, rbase, f4, t);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) v[jj] = t[jj];
+    return;
+  }
+  const int32_t *ixs = ix + d.seg * 3 * TC_BM + rbase;
+  const float *base = d.src + d.colk + f4 * 4;
+  const int64_t ld = d.ld;
+  if (d.mode == GNNFD_SEG_DIRECT) {
+    const int64_t last = p.a.rows - 1;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + min(row0 + rbase + 16 * jj, last) * ld);
+  } else if (d.mode == GNNFD_SEG_GATHER) {
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + (int64_t)ixs[16 * jj] * ld);
+  } else if (d.mode == GNNFD_SEG_MEAN3) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float4 y[2], z[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int jj = h * 2 + u;
+        v[jj] = ldg_f4(base + (int64_t)ixs[16 * jj] * ld);
+        y[u] = ldg_f4(base + (int64_t)ixs[TC_BM + 16 * jj] * ld);
+        z[u] = ldg_f4(base + (int64_t)ixs[2 * TC_BM + 16 * jj] * ld);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float4 t = f4_add(f4_add(v[h * 2 + u], y[u]), z[u]);
+        v[h * 2 + u] = make_float4(t.x / 3.0f, t.y / 3.0f, t.z / 3.0f, t.w / 3.0f);
+      }
+    }
+  } else {
+    const bool diff = d.mode == GNNFD_SEG_DIFF2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int jj = h * 4 + u;
+        v[jj] = ldg_f4(base + (int64_t)ixs[16 * jj] * ld);
+        y[u] = ldg_f4(base + (int64_t)ixs[TC_BM + 16 * jj] * ld);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[h * 4 + u] = diff ? f4_sub(v[h * 4 + u], y[u]) : f4_add(v[h * 4 + u], y[u]);
+    }
   }
 }
 
@@ -387,40 +456,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       }
       cp_async_commit();
     };
-    auto issue = [&](int b, float4(&v)[8]) {
-      if (b < NB) {
-        const int j = b / p.kb1, kb = b - j * p.kb1;
-        tc_load_block(p, s_idx + (j & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT, tile_row0(j), kb, rbase, f4, v);
+    // blocks are issued two ahead of the one being converted; (ij, ikb) tracks the next block to issue
+    int ij = 0, ikb = 0;
+    auto issue = [&](float4(&v)[8]) {
+      if (ij < T) {
+        tc_load_block(p, s_idx + (ij & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT, tile_row0(ij), ikb, rbase, f4, v);
+        if (++ikb == p.kb1) { ikb = 0; ++ij; }
       }
     };
     PROF_DECL;
-    auto step = [&](int b, float4(&v)[8]) {
-      const int j = b / p.kb1, kb = b - j * p.kb1;
-      if (kb == 0) {
-        // tile boundary: every index copy issued so far has landed (tiles <= j + 2) and every producer
-        // has issued its loads of tile j - 1, so that tile's index slot can be refilled with tile j + 3
-        if (j > 0) { cp_async_wait_all(); named_bar_sync(1, TC_PROD_THREADS); }
-        stage_idx(j + 3);
+    int sj = 0, skb = 0, st = 0;
+    uint32_t sphase = 1;   // parity to wait on a_empty for: first pass over the ring needs no wait
+    auto step = [&](float4(&v)[8]) {
+      if (skb == 0) {
+        // tile boundary: every index copy issued so far has landed (tiles <= sj + 2) and every producer
+        // has issued its loads of tile sj - 1, so that tile's index slot can be refilled with tile sj + 3
+        if (sj > 0) { cp_async_wait_all(); named_bar_sync(1, TC_PROD_THREADS); }
+        stage_idx(sj + 3);
       }
-      const int st = b % TC_A_STAGES;
-      if (b >= TC_A_STAGES) PROF_WAIT(0, mbar_wait(&a_empty[st], ((b / TC_A_STAGES) - 1) & 1));
-      const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
+      PROF_WAIT(0, mbar_wait(&a_empty[st], sphase));
+      const int ksteps = (skb == p.kb1 - 1) ? p.ksteps1 : 4;
       tc_store_block<FP16, NA>(s_a + st * 2 * TC_IMG, v, rbase, f4, f4 * 4 < ksteps * 16);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[st]);
-      issue(b + 2, v);
+      if (++skb == p.kb1) { skb = 0; ++sj; }
+      if (++st == TC_A_STAGES) { st = 0; sphase ^= 1; }
+      issue(v);
     };
 
     float4 v0[8], v1[8];
     stage_idx(0); stage_idx(1); stage_idx(2);
     cp_async_wait_all();
     named_bar_sync(1, TC_PROD_THREADS);
-    issue(0, v0);
-    issue(1, v1);
+    issue(v0);
+    issue(v1);
     for (int b = 0; b < NB; b += 2) {
-      step(b, v0);
-      if (b + 1 < NB) step(b + 1, v1);
+      step(v0);
+      if (b + 1 < NB) step(v1);
     }
     cp_async_wait_all();
 #ifdef GNNFD_TC_PROF
@@ -563,12 +636,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           tmem_ld32(reg + c * 32, acc);
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 b2 = *reinterpret_cast<const float2 *>(bias + c * 32 + 2 * i);
-            float x0 = acc[2 * i] + b2.x, x1 = acc[2 * i + 1] + b2.y;
-            if (a.act == GNNFD_ACT_SILU) { x0 = silu_fast(x0); x1 = silu_fast(x1); }
-            else { x0 = tanhf(x0); x1 = tanhf(x1); }
-            split2<FP16>(x0, x1, hi[i], lo[i]);
+          for (int h = 0; h < 2; ++h) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4 *>(bias + c * 32 + h * 16 + i);
+              v[i] = acc[h * 16 + i] + b4.x; v[i + 1] = acc[h * 16 + i + 1] + b4.y;
+              v[i + 2] = acc[h * 16 + i + 2] + b4.z; v[i + 3] = acc[h * 16 + i + 3] + b4.w;
+            }
+            if (a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split2<FP16>(v[2 * i], v[2 * i + 1], hi[h * 8 + i], lo[h * 8 + i]);
           }
           tmem_st16(reg + c * 32, hi);
           if (NA == 2) tmem_st16(reg + c * 32 + 16, lo);
@@ -587,19 +665,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         float mean = 0.f, rstd = 1.f;
         if (a.has_ln) {
           // shifted single pass: sums of (x - x0), (x - x0)^2
-          float shift = 0.f, s = 0.f, qv = 0.f;
+          float shift = 0.f, s4[4] = {0.f, 0.f, 0.f, 0.f}, q4s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             float acc[32];
             tmem_ld32(xr + c * 32, acc);
             if (c == 0) shift = acc[0] + s_vec[2 * TC_H];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float d = acc[i] + s_vec[2 * TC_H + c * 32 + i] - shift;
-              s += d;
-              qv = fmaf(d, d, qv);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4 *>(s_vec + 2 * TC_H + c * 32 + i);
+              const float d0 = acc[i] + b4.x - shift, d1 = acc[i + 1] + b4.y - shift;
+              const float d2 = acc[i + 2] + b4.z - shift, d3 = acc[i + 3] + b4.w - shift;
+              s4[0] += d0; s4[1] += d1; s4[2] += d2; s4[3] += d3;
+              q4s[0] = fmaf(d0, d0, q4s[0]); q4s[1] = fmaf(d1, d1, q4s[1]);
+              q4s[2] = fmaf(d2, d2, q4s[2]); q4s[3] = fmaf(d3, d3, q4s[3]);
             }
           }
+          const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]), qv = (q4s[0] + q4s[1]) + (q4s[2] + q4s[3]);
           const float md = s * (1.0f / TC_H);
           mean = shift + md;
           rstd = rsqrtf(fmaxf(qv * (1.0f / TC_H) - md * md, 0.f) + a.ln_eps);
@@ -626,11 +708,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           const float *b3 = s_vec + 2 * TC_H + c * 32, *gw = s_vec + 3 * TC_H + c * 32, *gb = s_vec + 4 * TC_H + c * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4 *>(b3 + i);
+            const float4 w4 = *reinterpret_cast<const float4 *>(gw + i);
+            const float4 g4 = *reinterpret_cast<const float4 *>(gb + i);
             float4 o;
-            o.x = (acc[i] + b3[i] - mean) * rstd * gw[i] + gb[i];
-            o.y = (acc[i + 1] + b3[i + 1] - mean) * rstd * gw[i + 1] + gb[i + 1];
-            o.z = (acc[i + 2] + b3[i + 2] - mean) * rstd * gw[i + 2] + gb[i + 2];
-            o.w = (acc[i + 3] + b3[i + 3] - mean) * rstd * gw[i + 3] + gb[i + 3];
+            o.x = fmaf((acc[i] + b4.x - mean) * rstd, w4.x, g4.x);
+            o.y = fmaf((acc[i + 1] + b4.y - mean) * rstd, w4.y, g4.y);
+            o.z = fmaf((acc[i + 2] + b4.z - mean) * rstd, w4.z, g4.z);
+            o.w = fmaf((acc[i + 3] + b4.w - mean) * rstd, w4.w, g4.w);
             *reinterpret_cast<float4 *>(stg + lane * TC_STG_STRIDE + i) = o;
           }
           __syncwarp();
@@ -808,6 +893,7 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
                         (reinterpret_cast<uintptr_t>(s0.src) & 15) == 0;
     p.direct_tile_bytes = contig ? (int64_t)TC_BM * s0.ld * 4 : 0;
   }
+  if (a->rows == 0) return GNNFD_OK;
   const int64_t n_tiles = (a->rows + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
 #define LAUNCH(FP, NA_, NW_)                                                                              \
