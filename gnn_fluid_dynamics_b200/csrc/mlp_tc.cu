@@ -350,7 +350,8 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const float4 t = f4_add(f4_add(v[h * 2 + u], y[u]), z[u]);
-        v[h * 2 + u] = make_float4(t.x / 3.0f, t.y / 3.0f, t.z / 3.0f, t.w / 3.0f);
+        constexpr float third = 1.0f / 3.0f;   // operands are rounded to 2 x bf16 right after: 1 ulp is immaterial
+        v[h * 2 + u] = make_float4(t.x * third, t.y * third, t.z * third, t.w * third);
       }
     }
   } else {
@@ -471,18 +472,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       if (skb == 0) {
         // tile boundary: every index copy issued so far has landed (tiles <= sj + 2) and every producer
         // has issued its loads of tile sj - 1, so that tile's index slot can be refilled with tile sj + 3
-        if (sj > 0) { cp_async_wait_all(); named_bar_sync(1, TC_PROD_THREADS); }
+        if (sj > 0) { PROF_WAIT(4, cp_async_wait_all(); named_bar_sync(1, TC_PROD_THREADS)); }
         stage_idx(sj + 3);
       }
       PROF_WAIT(0, mbar_wait(&a_empty[st], sphase));
       const int ksteps = (skb == p.kb1 - 1) ? p.ksteps1 : 4;
-      tc_store_block<FP16, NA>(s_a + st * 2 * TC_IMG, v, rbase, f4, f4 * 4 < ksteps * 16);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[st]);
+      PROF_WAIT(1, (tc_store_block<FP16, NA>(s_a + st * 2 * TC_IMG, v, rbase, f4, f4 * 4 < ksteps * 16)));
+      PROF_WAIT(2, fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(&a_full[st]));
       if (++skb == p.kb1) { skb = 0; ++sj; }
       if (++st == TC_A_STAGES) { st = 0; sphase ^= 1; }
-      issue(v);
+      PROF_WAIT(3, issue(v));
     };
 
     float4 v0[8], v1[8];
@@ -497,7 +496,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     }
     cp_async_wait_all();
 #ifdef GNNFD_TC_PROF
-    if (blockIdx.x == 0 && pt == 0) { g_tc_prof[12] = clock64() - t_begin; g_tc_prof[13] = prof[0]; }
+    if (blockIdx.x == 0 && pt == 0) {
+      g_tc_prof[12] = clock64() - t_begin; g_tc_prof[13] = prof[0];
+      g_tc_prof[14] = prof[1]; g_tc_prof[15] = prof[2]; g_tc_prof[7] = prof[3]; g_tc_prof[11] = prof[4];
+    }
 #endif
   } else if (warp == TC_WLD_WARP) {
     // ============================================================================ weight loader
@@ -514,19 +516,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         bulk_g2s(s_w + slot * TC_IMG, src, bytes, &w_full[slot]);
         ++wl;
       };
-      // same order as the MMA issuer: per pair of tiles  L1 L1 | L2 L2 | L3 L3
-      for (int j0 = 0; j0 < T; j0 += 2) {
-        const int nt = min(2, T - j0);
-        for (int t = 0; t < nt; ++t)
-          for (int kb = 0; kb < p.kb1; ++kb)
-            for (int part = 0; part < NW; ++part) load_unit(w1p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
-        for (int t = 0; t < nt; ++t)
-          for (int kb = 0; kb < 2; ++kb)
-            for (int part = 0; part < NW; ++part) load_unit(w2p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
-        for (int t = 0; t < nt; ++t)
-          for (int kb = 0; kb < 2; ++kb)
-            for (int part = 0; part < NW; ++part) load_unit(w3p + (size_t)kb * p.w3_block_bytes + part * w3_part, w3_part);
-      }
+      // same order as the MMA issuer (see there)
+      auto l1 = [&](int kb0, int kb1) {
+        for (int kb = kb0; kb < kb1; ++kb)
+          for (int part = 0; part < NW; ++part) load_unit(w1p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
+      };
+      auto l2 = [&]() {
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < NW; ++part) load_unit(w2p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
+      };
+      auto l3 = [&]() {
+        for (int kb = 0; kb < 2; ++kb)
+          for (int part = 0; part < NW; ++part) load_unit(w3p + (size_t)kb * p.w3_block_bytes + part * w3_part, w3_part);
+      };
+      const int n1 = (p.kb1 + 2) / 3, n2 = (2 * p.kb1 + 2) / 3;
+      l1(0, p.kb1);
+      for (int j = 1; j < T; ++j) { l1(0, n1); l2(); l1(n1, n2); l3(); l1(n2, p.kb1); }
+      l2(); l3();
     }
     __syncwarp();
   } else if (warp == TC_MMA_WARP) {
@@ -544,11 +550,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         ++wc;
         return make_desc(smem_u32(s_w + slot * TC_IMG));
       };
-      auto layer1 = [&](int j) {
+      auto layer1 = [&](int j, int kb0, int kb1) {
         const int sl = j & 1, n = j >> 1;
-        if (n >= 1) { PROF_WAIT(3, mbar_wait(&acc_free[sl], (n - 1) & 1)); tc_fence_after(); }
+        if (kb0 == 0 && n >= 1) { PROF_WAIT(3, mbar_wait(&acc_free[sl], (n - 1) & 1)); tc_fence_after(); }
         const uint32_t d = tmem_base + sl * 256;
-        for (int kb = 0; kb < p.kb1; ++kb, ++ca) {
+        for (int kb = kb0; kb < kb1; ++kb, ++ca) {
           const int st = ca % TC_A_STAGES;
           PROF_WAIT(4, mbar_wait(&a_full[st], (ca / TC_A_STAGES) & 1));
           tc_fence_after();
@@ -568,7 +574,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           }
           umma_commit(&a_empty[st]);
         }
-        umma_commit(&acc_full[sl]);
+        if (kb0 < kb1 && kb1 == p.kb1) umma_commit(&acc_full[sl]);   // (empty ranges occur when kb1 < 3)
       };
       // layers 2 and 3: A = the in-place converted accumulator region, 32-column chunk per 32 elements
       auto layer23 = [&](int j, int layer) {
@@ -598,12 +604,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         }
         umma_commit(&acc_full[sl]);
       };
-      for (int j0 = 0; j0 < T; j0 += 2) {
-        const int nt = min(2, T - j0);
-        for (int t = 0; t < nt; ++t) layer1(j0 + t);
-        for (int t = 0; t < nt; ++t) layer23(j0 + t, 2);
-        for (int t = 0; t < nt; ++t) layer23(j0 + t, 3);
+      // Issue order: layer 1 of tile j is interleaved, a third at a time, with layers 2 and 3 of tile
+      // j - 1 (the other TMEM slot).  The A ring drains steadily, so the producers never idle behind a
+      // long L2/L3 phase, and each hidden/final epilogue of tile j - 1 has a third of a tile period.
+      const int n1 = (p.kb1 + 2) / 3, n2 = (2 * p.kb1 + 2) / 3;
+      layer1(0, 0, p.kb1);
+      for (int j = 1; j < T; ++j) {
+        layer1(j, 0, n1);
+        layer23(j - 1, 2);
+        layer1(j, n1, n2);
+        layer23(j - 1, 3);
+        layer1(j, n2, p.kb1);
       }
+      layer23(T - 1, 2);
+      layer23(T - 1, 3);
 #ifdef GNNFD_TC_PROF
       if (blockIdx.x == 0) {
         g_tc_prof[0] = clock64() - t_begin;
