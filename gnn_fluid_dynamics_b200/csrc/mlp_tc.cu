@@ -32,12 +32,15 @@ constexpr int TC_KB = 64;             // elements per k-block (128 B of 16-bit o
 constexpr int TC_IMG = TC_BM * 128;   // bytes of one [128 x 64] operand image = 16 KB
 // warp roles: 0-3 epilogue of even local tiles (TMEM slot 0), 4-7 epilogue of odd local tiles (slot 1)
 //             (warp & 3 = TMEM lane quarter, thread = row), 8-15 producers (gather -> split -> swizzled A
-//             stage), 16 = MMA issuer, 17 = weight loader (TMA bulk copies)
+//             stage), 16 = MMA issuer, 17 = weight loader (TMA bulk copies), 18-19 idle.
+// Registers: 5 warps per SM sub-partition cap the launch at 96 per thread; warpgroup 16-19 shrinks to 48
+// (setmaxnreg.dec) and the two producer warpgroups grow to 120 (setmaxnreg.inc; only registers released inside the CTA can be claimed) for their two in-flight
+// k-blocks of gathered rows.
 constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 8;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32, TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
 constexpr int TC_WLD_WARP = TC_MMA_WARP + 1;
-constexpr int TC_THREADS = (TC_WLD_WARP + 1) * 32;   // 576
+constexpr int TC_THREADS = (TC_WLD_WARP + 3) * 32;   // 640: warps 18, 19 only complete the register-donor warpgroup
 constexpr int TC_A_STAGES = 3;        // A ring: {A_hi, A_lo} images per stage
 constexpr int TC_W_SLOTS = 4;         // W ring: one 16 KB image (hi or lo part of a k-block) per slot
 constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 96 KB
@@ -48,7 +51,7 @@ constexpr int TC_IDX_SLOTS = 4;
 constexpr int TC_IDX_SLOT = 9 * TC_BM;               // ints: [3 seg][3 idx][128 rows]
 constexpr int TC_NBAR = 24;
 constexpr int TC_SMEM = TC_A_BYTES + TC_W_BYTES + TC_STG_BYTES + TC_IDX_SLOTS * TC_IDX_SLOT * 4 +
-                        5 * TC_H * 4 + TC_NBAR * 8 + 64 + 1024;
+                        5 * TC_H * 4 + 4 * TC_BM * 8 + TC_NBAR * 8 + 64 + 1024;
 constexpr int TC_TMEM_COLS = 512;     // two slots x {X, Y} x 128 columns
 constexpr int TC_MAX_KB = 8;
 
@@ -205,6 +208,22 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
   }
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts_f2(uint32_t saddr, float2 v) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ float ex2_ftz(float x) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -398,7 +417,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   float *s_stg = (float *)(s_w + TC_W_BYTES);              // output staging, one 32x36 block per epilogue warp
   int32_t *s_idx = (int32_t *)((uint8_t *)s_stg + TC_STG_BYTES);   // [4 tiles][3 seg][3][128]
   float *s_vec = (float *)(s_idx + TC_IDX_SLOTS * TC_IDX_SLOT);    // b1, b2, b3, ln_w, ln_b
-  uint64_t *s_bar = (uint64_t *)(s_vec + 5 * TC_H);
+  float2 *s_stat = (float2 *)(s_vec + 5 * TC_H);                   // LayerNorm partials [2 slots][2 halves][128 rows]
+  uint64_t *s_bar = (uint64_t *)(s_stat + 4 * TC_BM);
   uint64_t *a_full = s_bar, *a_empty = s_bar + 3, *w_full = s_bar + 6, *w_empty = s_bar + 10;
   uint64_t *acc_full = s_bar + 14, *acc_free = s_bar + 16, *hid_ready = s_bar + 18;   // hid_ready[slot*2 + half]
   uint32_t *s_tmem = (uint32_t *)(s_bar + TC_NBAR);
@@ -408,7 +428,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   if (tid == 0) {
     for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < TC_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_EPI_WARPS); }
     for (int i = 0; i < 4; ++i) mbar_init(&hid_ready[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -430,6 +450,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 
   if (warp >= TC_EPI_WARPS && warp < TC_MMA_WARP) {
     // =============================================================================== producers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     const int pt = tid - TC_EPI_THREADS;   // 0..255
     const int f4 = pt & 15;                // float4 column inside the 64-wide k-block
     const int rbase = pt >> 4;             // rows rbase + 16 j
@@ -501,8 +522,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       g_tc_prof[14] = prof[1]; g_tc_prof[15] = prof[2]; g_tc_prof[7] = prof[3]; g_tc_prof[11] = prof[4];
     }
 #endif
+  } else if (warp > TC_WLD_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
   } else if (warp == TC_WLD_WARP) {
     // ============================================================================ weight loader
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (lane == 0 && T > 0) {
       const uint8_t *w1p = (const uint8_t *)a.packed;
       const uint8_t *w2p = w1p + (size_t)p.kb1 * p.w_block_bytes;
@@ -537,6 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     __syncwarp();
   } else if (warp == TC_MMA_WARP) {
     // ================================================================================ MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (lane == 0 && T > 0) {
       constexpr uint32_t IDESC_H = make_idesc(FP16 ? 0 : 1, TC_H);
       const uint32_t idesc3 = make_idesc(FP16 ? 0 : 1, p.n3);
@@ -629,23 +654,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     __syncwarp();
   } else {
     // ================================================================================ epilogue
-    const int sl = warp >> 2, q4 = warp & 3;
+    // warp = (lane quarter q4, column half eh): thread = row, 64 of the 128 columns, for EVERY tile; half eh
+    // of a hidden layer's output is exactly k-block eh of the next layer's operand.
+    const int q4 = warp & 3, eh = warp >> 2;
     const int erow = q4 * 32 + lane;                       // row of the tile owned by this thread
-    float *stg = s_stg + warp * (32 * TC_STG_STRIDE);      // this warp's 32x32 staging block
-    const uint32_t xr = tmem_base + sl * 256 + ((uint32_t)(q4 * 32) << 16), yr = xr + 128;
+    const uint32_t stg = smem_u32(s_stg + warp * (32 * TC_STG_STRIDE));   // this warp's 32x32 staging block
+    const uint32_t vec = smem_u32(s_vec), stat = smem_u32(s_stat);
     const int rr = lane >> 3, c4 = lane & 7;               // copy-out mapping: 4 rows x 128 B per instruction
     PROF_DECL;
-    for (int j = sl; j < T; j += 2) {
-      const int n = j >> 1;
+    for (int j = 0; j < T; ++j) {
+      const int sl = j & 1, n = j >> 1;
       const int64_t row0 = tile_row0(j);
+      const uint32_t xr = tmem_base + sl * 256 + ((uint32_t)(q4 * 32) << 16) + eh * 64, yr = xr + 128;
       // ---- hidden layers: accumulator -> +bias, act -> hi/lo pairs, written back in place
       for (int layer = 0; layer < 2; ++layer) {
         PROF_WAIT(0, mbar_wait(&acc_full[sl], (3 * n + layer) & 1));
         tc_fence_after();
         const uint32_t reg = layer == 0 ? xr : yr;
-        const float *bias = s_vec + layer * TC_H;
+        const uint32_t bias = vec + (layer * TC_H + eh * 64) * 4;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           float acc[32];
           tmem_ld32(reg + c * 32, acc);
           uint32_t hi[16], lo[16];
@@ -654,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             float v[16];
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4 *>(bias + c * 32 + h * 16 + i);
+              const float4 b4 = lds_f4(bias + (c * 32 + h * 16 + i) * 4);
               v[i] = acc[h * 16 + i] + b4.x; v[i + 1] = acc[h * 16 + i + 1] + b4.y;
               v[i + 2] = acc[h * 16 + i + 2] + b4.z; v[i + 3] = acc[h * 16 + i + 3] + b4.w;
             }
@@ -664,13 +692,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           }
           tmem_st16(reg + c * 32, hi);
           if (NA == 2) tmem_st16(reg + c * 32 + 16, lo);
-          if (c & 1) {   // a 64-element k-block of the next layer's operand is complete
-            tmem_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hid_ready[sl * 2 + (c >> 1)]);
-          }
         }
+        // this half's 64 columns = one k-block of the next layer's operand
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&hid_ready[sl * 2 + eh]);
       }
       // ---- final epilogue
       PROF_WAIT(1, mbar_wait(&acc_full[sl], (3 * n + 2) & 1));
@@ -678,16 +705,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       if (a.n_out == TC_H) {
         float mean = 0.f, rstd = 1.f;
         if (a.has_ln) {
-          // shifted single pass: sums of (x - x0), (x - x0)^2
+          // this half: shifted single pass over 64 columns -> (mean_h, M2_h); halves merged with Chan's formula
           float shift = 0.f, s4[4] = {0.f, 0.f, 0.f, 0.f}, q4s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {
             float acc[32];
             tmem_ld32(xr + c * 32, acc);
-            if (c == 0) shift = acc[0] + s_vec[2 * TC_H];
+            const uint32_t b3 = vec + (2 * TC_H + eh * 64 + c * 32) * 4;
+            if (c == 0) shift = acc[0] + lds_f4(b3).x;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 b4 = *reinterpret_cast<const float4 *>(s_vec + 2 * TC_H + c * 32 + i);
+              const float4 b4 = lds_f4(b3 + i * 4);
               const float d0 = acc[i] + b4.x - shift, d1 = acc[i + 1] + b4.y - shift;
               const float d2 = acc[i + 2] + b4.z - shift, d3 = acc[i + 3] + b4.w - shift;
               s4[0] += d0; s4[1] += d1; s4[2] += d2; s4[3] += d3;
@@ -695,42 +723,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               q4s[2] = fmaf(d2, d2, q4s[2]); q4s[3] = fmaf(d3, d3, q4s[3]);
             }
           }
-          const float s = (s4[0] + s4[1]) + (s4[2] + s4[3]), qv = (q4s[0] + q4s[1]) + (q4s[2] + q4s[3]);
-          const float md = s * (1.0f / TC_H);
-          mean = shift + md;
-          rstd = rsqrtf(fmaxf(qv * (1.0f / TC_H) - md * md, 0.f) + a.ln_eps);
+          const float sh = (s4[0] + s4[1]) + (s4[2] + s4[3]), qh = (q4s[0] + q4s[1]) + (q4s[2] + q4s[3]);
+          const float md = sh * (1.0f / 64.0f);
+          const float mean_h = shift + md, m2_h = fmaxf(qh - sh * md, 0.f);
+          sts_f2(stat + ((sl * 2 + eh) * TC_BM + erow) * 8, make_float2(mean_h, m2_h));
+          named_bar_sync(2 + q4, 64);                   // the two warps that share these 32 rows
+          const float2 o = lds_f2(stat + ((sl * 2 + (eh ^ 1)) * TC_BM + erow) * 8);
+          const float dm = mean_h - o.x;
+          mean = 0.5f * (mean_h + o.x);
+          rstd = rsqrtf((m2_h + o.y + dm * dm * 32.0f) * (1.0f / TC_H) + a.ln_eps);
         }
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
+          const int col0 = eh * 64 + c * 32;
           // residual rows of this chunk, coalesced mapping, requested before the TMEM read
           float4 res[8];
           if (a.out_sum) {
 #pragma unroll
             for (int jr = 0; jr < 8; ++jr) {
-              const int64_t g = row0 + q4 * 32 + jr * 4 + rr;
-              res[jr] = g < a.rows ? ldg_f4(a.residual + (size_t)g * TC_H + c * 32 + c4 * 4)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+              const int64_t g = min(row0 + q4 * 32 + jr * 4 + rr, a.rows - 1);
+              res[jr] = ldg_f4(a.residual + (size_t)g * TC_H + col0 + c4 * 4);
             }
           }
           float acc[32];
           tmem_ld32(xr + c * 32, acc);
-          if (c == 3) {   // last TMEM read of this tile: the slot may be overwritten by the next L1
+          if (c == 1) {   // last TMEM read of this tile: the slot may be overwritten by the next L1
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[sl]);
           }
-          const float *b3 = s_vec + 2 * TC_H + c * 32, *gw = s_vec + 3 * TC_H + c * 32, *gb = s_vec + 4 * TC_H + c * 32;
+          const uint32_t b3 = vec + (2 * TC_H + col0) * 4, gw = vec + (3 * TC_H + col0) * 4, gb = vec + (4 * TC_H + col0) * 4;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4 *>(b3 + i);
-            const float4 w4 = *reinterpret_cast<const float4 *>(gw + i);
-            const float4 g4 = *reinterpret_cast<const float4 *>(gb + i);
+            const float4 b4 = lds_f4(b3 + i * 4), w4 = lds_f4(gw + i * 4), g4 = lds_f4(gb + i * 4);
             float4 o;
             o.x = fmaf((acc[i] + b4.x - mean) * rstd, w4.x, g4.x);
             o.y = fmaf((acc[i + 1] + b4.y - mean) * rstd, w4.y, g4.y);
             o.z = fmaf((acc[i + 2] + b4.z - mean) * rstd, w4.z, g4.z);
             o.w = fmaf((acc[i + 3] + b4.w - mean) * rstd, w4.w, g4.w);
-            *reinterpret_cast<float4 *>(stg + lane * TC_STG_STRIDE + i) = o;
+            sts_f4(stg + (lane * TC_STG_STRIDE + i) * 4, o);
           }
           __syncwarp();
 #pragma unroll
@@ -738,8 +769,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             const int rl = jr * 4 + rr;
             const int64_t g = row0 + q4 * 32 + rl;
             if (g < a.rows) {
-              float4 o = *reinterpret_cast<const float4 *>(stg + rl * TC_STG_STRIDE + c4 * 4);
-              const size_t off = (size_t)g * TC_H + c * 32 + c4 * 4;
+              float4 o = lds_f4(stg + (rl * TC_STG_STRIDE + c4 * 4) * 4);
+              const size_t off = (size_t)g * TC_H + col0 + c4 * 4;
               if (a.mul) { const float4 m = ldg_f4(a.mul + off); o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w; }
               if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + off) = o;
               if (a.out_sum) {
@@ -752,23 +783,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           __syncwarp();
         }
       } else {
-        float acc[16];
-        tmem_ld16(xr, acc);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_free[sl]);
-        const int64_t g = row0 + erow;
-        if (g < a.rows) {
+        if (eh == 0) {
+          float acc[16];
+          tmem_ld16(xr, acc);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_free[sl]);
+          const int64_t g = row0 + erow;
+          if (g < a.rows) {
 #pragma unroll
-          for (int o = 0; o < 16; ++o) {
-            if (o < a.n_out) {
-              float vv = acc[o] + s_vec[2 * TC_H + o];
-              const size_t off = (size_t)g * a.n_out + o;
-              if (a.mul) vv *= __ldg(a.mul + off);
-              if (a.out_raw) a.out_raw[off] = vv;
-              if (a.out_sum) a.out_sum[off] = __ldg(a.residual + off) + vv;
+            for (int o = 0; o < 16; ++o) {
+              if (o < a.n_out) {
+                float vv = acc[o] + s_vec[2 * TC_H + o];
+                const size_t off = (size_t)g * a.n_out + o;
+                if (a.mul) vv *= __ldg(a.mul + off);
+                if (a.out_raw) a.out_raw[off] = vv;
+                if (a.out_sum) a.out_sum[off] = __ldg(a.residual + off) + vv;
+              }
             }
           }
+        } else {
+          if (lane == 0) mbar_arrive(&acc_free[sl]);
         }
       }
     }
