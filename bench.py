@@ -113,6 +113,24 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused edge block, from the committed
+    `ncu --set full` capture of this same command (profiles/*_ncu_summary.json; scripts/summarize_ncu.py)."""
+    if workload != DEFAULT_WORKLOAD:
+        return None, None
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if name.endswith("_ncu_summary.json"):
+            try:
+                d = json.load(open(os.path.join(pdir, name)))
+                edge = max(d["launches"], key=lambda x: x.get("duration_us", 0))   # edge block = the longer launch
+                best = (int(edge["dram_traffic_bytes"]), name)
+            except Exception:  # noqa: BLE001
+                pass
+    return best if best else (None, None)
+
+
 def algorithmic_bytes_edge_kernel(E, N):
     """Fused edge block, FVGN order: read e (E rows) + gather x' (N unique rows) + write e+e' (E rows),
     512 B per fp32 row, + row/col int32 indices."""
@@ -281,6 +299,7 @@ def main():
     k_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
     hbm_peak, peak_kind = peaks()
     alg = algorithmic_bytes_edge_kernel(E, N)
+    traffic, traffic_src = ncu_traffic(args.workload)
     achieved = alg / (k_ms * 1e-3) / 1e9
 
     # ---- max over ranks, aggregate -------------------------------------------------------------------
@@ -314,7 +333,8 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "fused edge block (gather + 3-layer MLP + LayerNorm + residual)",
                          "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_kind": peak_kind,
                          "kernel_ms": k_ms, "algorithmic_bytes": alg},
             "cpu_baseline": cpu_baseline,
         }
