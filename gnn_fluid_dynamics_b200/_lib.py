@@ -22,7 +22,10 @@ EXPORTS = [
     "gnnfd_abi_version", "gnnfd_last_error", "gnnfd_index_narrow", "gnnfd_csr_workspace_bytes",
     "gnnfd_csr_build", "gnnfd_segment_sum", "gnnfd_mlp_forward", "gnnfd_pack_mlp_bytes",
     "gnnfd_pack_mlp", "gnnfd_tc_profile_read",
+    "gnnfd_ln_backward_workspace_bytes", "gnnfd_ln_backward", "gnnfd_wgrad_workspace_bytes", "gnnfd_wgrad",
+    "gnnfd_segment_sum3", "gnnfd_gather_pair_add", "gnnfd_struct_size",
 ]
+ABI_VERSION = 2
 
 
 class Segment(C.Structure):
@@ -39,6 +42,17 @@ class MlpArgs(C.Structure):
         ("has_ln", C.c_int32), ("ln_eps", C.c_float), ("act", C.c_int32),
         ("mul", C.c_void_p), ("residual", C.c_void_p), ("out_raw", C.c_void_p),
         ("out_sum", C.c_void_p), ("packed", C.c_void_p), ("precision", C.c_int32),
+        ("n_layers", C.c_int32), ("mul_mode", C.c_int32),
+        ("save_a1", C.c_void_p), ("save_a2", C.c_void_p), ("save_rstd", C.c_void_p), ("save_xhat", C.c_void_p),
+        ("w1_ld_n", C.c_int32), ("w1_ld_k", C.c_int32), ("w1_rows", C.c_int32),
+    ]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("a", Segment), ("a_act", C.c_int32), ("n_b", C.c_int32), ("b", Segment * 3),
+        ("b_act", C.c_int32), ("out", C.c_void_p), ("ld_out", C.c_int32), ("transpose_out", C.c_int32),
+        ("colsum", C.c_void_p), ("colsum_of_b", C.c_int32),
     ]
 
 
@@ -65,12 +79,23 @@ def _load():
     lib.gnnfd_pack_mlp_bytes.restype = C.c_size_t
     lib.gnnfd_pack_mlp.argtypes = [C.POINTER(MlpArgs), vp, vp]
     lib.gnnfd_tc_profile_read.argtypes = [C.POINTER(C.c_uint64)]
-    for name in EXPORTS:
-        fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("gnnfd_abi_version",):
-            pass
-    if lib.gnnfd_abi_version() != 1:
-        raise ImportError(f"{LIB_PATH}: ABI version {lib.gnnfd_abi_version()} != 1; rebuild")
+    lib.gnnfd_ln_backward_workspace_bytes.argtypes = [i64]
+    lib.gnnfd_ln_backward_workspace_bytes.restype = C.c_size_t
+    lib.gnnfd_ln_backward.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, C.c_size_t, vp]
+    lib.gnnfd_wgrad_workspace_bytes.argtypes = [i64, i32]
+    lib.gnnfd_wgrad_workspace_bytes.restype = C.c_size_t
+    lib.gnnfd_wgrad.argtypes = [C.POINTER(WgradArgs), vp, C.c_size_t, vp]
+    lib.gnnfd_segment_sum3.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, f32, i64, vp, vp, i64, f32, vp, i32,
+                                       vp, i32, vp]
+    lib.gnnfd_gather_pair_add.argtypes = [vp, vp, vp, i32, vp, vp, f32, i32, i64, vp]
+    lib.gnnfd_struct_size.argtypes = [i32]
+    lib.gnnfd_struct_size.restype = C.c_size_t
+    for which, mirror in ((0, MlpArgs), (1, WgradArgs), (2, Segment)):
+        if lib.gnnfd_struct_size(which) != C.sizeof(mirror):
+            raise ImportError(f"{LIB_PATH}: struct {mirror.__name__} is {lib.gnnfd_struct_size(which)} bytes in the "
+                              f"library but {C.sizeof(mirror)} in the binding; rebuild")
+    if lib.gnnfd_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.gnnfd_abi_version()} != {ABI_VERSION}; rebuild")
     return lib
 
 

@@ -29,7 +29,19 @@ int validate_mlp_args(const gnnfd_mlp_args *a) {
     k += sg.width;
   }
   GNNFD_CHECK_ARG(k == a->k_in, "segment widths do not add up to k_in");
-  GNNFD_CHECK_ARG(a->w1 && a->w2 && a->w3, "null weight");
+  GNNFD_CHECK_ARG(a->n_layers == 0 || a->n_layers == 1 || a->n_layers == 3, "n_layers must be 0, 1 or 3");
+  if (a->n_layers == 1) {
+    GNNFD_CHECK_ARG(a->w1 != nullptr, "null weight");
+    GNNFD_CHECK_ARG(a->precision != GNNFD_PREC_F32, "n_layers == 1 needs a tensor-core precision");
+    GNNFD_CHECK_ARG(a->n_out == 128 && !a->has_ln, "n_layers == 1 needs n_out == 128 and no LayerNorm");
+  } else {
+    GNNFD_CHECK_ARG(a->w1 && a->w2 && a->w3, "null weight");
+  }
+  GNNFD_CHECK_ARG(a->mul_mode >= 0 && a->mul_mode <= 2, "bad mul_mode");
+  if (a->precision == GNNFD_PREC_F32)
+    GNNFD_CHECK_ARG(!a->save_a1 && !a->save_a2 && !a->save_rstd && !a->save_xhat && a->mul_mode == 0,
+                    "training stashes need a tensor-core precision");
+  GNNFD_CHECK_ARG(!a->save_xhat || a->n_out == 128, "save_xhat needs n_out == 128");
   GNNFD_CHECK_ARG(!a->out_sum || a->residual, "out_sum requires residual");
   GNNFD_CHECK_ARG(a->out_raw || a->out_sum || a->rows == 0, "no output requested");
   return GNNFD_OK;
@@ -72,4 +84,13 @@ extern "C" int gnnfd_pack_mlp(const gnnfd_mlp_args *args, void *packed_out, void
 extern "C" int gnnfd_tc_profile_read(uint64_t *out16) {
   GNNFD_CHECK_ARG(out16 != nullptr, "null output");
   return tc_profile_read((unsigned long long *)out16);
+}
+
+extern "C" size_t gnnfd_struct_size(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(gnnfd_mlp_args);
+    case 1: return sizeof(gnnfd_wgrad_args);
+    case 2: return sizeof(gnnfd_segment);
+    default: return 0;
+  }
 }

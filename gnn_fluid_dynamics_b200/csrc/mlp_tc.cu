@@ -19,17 +19,10 @@
 // (128 B per row), rows in groups of 8 (1024 B atoms), 16-byte chunk c of row r stored at chunk
 // c ^ (r & 7).  Weights are pre-packed by gnnfd_pack_mlp into exactly this image per (layer,
 // k-block, part), so one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) lands a unit.
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gnnfd {
 
-constexpr int TC_BM = 128;            // rows per tile == UMMA M
-constexpr int TC_H = 128;             // hidden width == UMMA N
-constexpr int TC_KB = 64;             // elements per k-block (128 B of 16-bit operands)
-constexpr int TC_IMG = TC_BM * 128;   // bytes of one [128 x 64] operand image = 16 KB
 // warp roles: 0-3 epilogue of even local tiles (TMEM slot 0), 4-7 epilogue of odd local tiles (slot 1)
 //             (warp & 3 = TMEM lane quarter, thread = row), 8-15 producers (gather -> split -> swizzled A
 //             stage), 16 = MMA issuer, 17 = weight loader (TMA bulk copies), 18-19 idle.
@@ -55,207 +48,6 @@ constexpr int TC_SMEM = TC_A_BYTES + TC_W_BYTES + TC_STG_BYTES + TC_IDX_SLOTS * 
 constexpr int TC_TMEM_COLS = 512;     // two slots x {X, Y} x 128 columns
 constexpr int TC_MAX_KB = 8;
 
-// ---------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int n) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]^T   (A: lane = row, 32-bit column = two consecutive K elements)
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
-      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64)
-// Advancing K by 16 elements (32 B) inside the 128 B swizzle row adds 2 to the start field.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;            // LBO = 16 B (ignored for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;  // SBO = 1024 B between 8-row groups
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a/b format, K-major both, N>>3, M>>4
-__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int n) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(TC_BM >> 4) << 24);
-}
-
-// -------------------------------------------------------------------------- operand conversion
-template <bool FP16>
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-  if constexpr (FP16) {
-    __half2 h = __floats2half2_rn(a, b);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t *>(&h);
-    lo = *reinterpret_cast<uint32_t *>(&l);
-  } else {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    float2 hf = __bfloat1622float2(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t *>(&h);
-    lo = *reinterpret_cast<uint32_t *>(&l);
-  }
-}
-
-__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
-  float2 v;
-  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts_f2(uint32_t saddr, float2 v) {
-  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ float ex2_ftz(float x) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float rcp_ftz(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-// 16 activations at a time, written stage by stage so the MUFU latencies of independent elements overlap
-template <int ACT>
-__device__ __forceinline__ void act16(float (&v)[16]) {
-  if constexpr (ACT == GNNFD_ACT_SILU) {
-    float e[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) e[i] = ex2_ftz(v[i] * -1.4426950408889634f);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) e[i] = rcp_ftz(1.0f + e[i]);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= e[i];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);
-  }
-}
-
-// byte offset of 16-byte chunk `c` of row `r` inside a [rows x 64] SWIZZLE_128B image
-__device__ __forceinline__ uint32_t sw128(int r, int c) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
-}
-
 // how the producers assemble one 64-wide k-block of layer 1's input
 struct KbDesc {
   const float *src;   // segment source matrix
@@ -272,6 +64,7 @@ struct TcParams {
   int kb1;       // k-blocks of layer 1
   int ksteps1;   // K=16 steps in the LAST k-block of layer 1 (1..4)
   int n3;        // UMMA N of layer 3: 128, or 16 for a narrow head
+  int nl;        // layers: 3 (MLP) or 1 (single Linear)
   uint32_t w_block_bytes;   // bytes of one packed 128-row k-block (all parts)
   uint32_t w3_block_bytes;  // bytes of one packed layer-3 k-block
   int64_t direct_tile_bytes;   // bytes of one tile's rows of a contiguous DIRECT segment 0 (0: no L2 prefetch)
@@ -434,7 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   }
   for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
     const int v = i / TC_H, c = i % TC_H;
-    const float *src = v == 0 ? a.b1 : v == 1 ? a.b2 : v == 2 ? a.b3 : v == 3 ? a.ln_w : a.ln_b;
+    const float *src = v == 0 ? a.b1 : v == 1 ? a.b2 : v == 2 ? (p.nl == 1 ? a.b1 : a.b3) : v == 3 ? a.ln_w : a.ln_b;
     const int n = (v == 2 || v >= 3) ? a.n_out : TC_H;
     s_vec[i] = (src && c < n) ? __ldg(src + c) : (v == 3 ? 1.f : 0.f);
   }
@@ -554,9 +347,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           for (int part = 0; part < NW; ++part) load_unit(w3p + (size_t)kb * p.w3_block_bytes + part * w3_part, w3_part);
       };
       const int n1 = (p.kb1 + 2) / 3, n2 = (2 * p.kb1 + 2) / 3;
-      l1(0, p.kb1);
-      for (int j = 1; j < T; ++j) { l1(0, n1); l2(); l1(n1, n2); l3(); l1(n2, p.kb1); }
-      l2(); l3();
+      if (p.nl == 1) {
+        for (int j = 0; j < T; ++j) l1(0, p.kb1);
+      } else {
+        l1(0, p.kb1);
+        for (int j = 1; j < T; ++j) { l1(0, n1); l2(); l1(n1, n2); l3(); l1(n2, p.kb1); }
+        l2(); l3();
+      }
     }
     __syncwarp();
   } else if (warp == TC_MMA_WARP) {
@@ -633,16 +430,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       // j - 1 (the other TMEM slot).  The A ring drains steadily, so the producers never idle behind a
       // long L2/L3 phase, and each hidden/final epilogue of tile j - 1 has a third of a tile period.
       const int n1 = (p.kb1 + 2) / 3, n2 = (2 * p.kb1 + 2) / 3;
-      layer1(0, 0, p.kb1);
-      for (int j = 1; j < T; ++j) {
-        layer1(j, 0, n1);
-        layer23(j - 1, 2);
-        layer1(j, n1, n2);
-        layer23(j - 1, 3);
-        layer1(j, n2, p.kb1);
+      if (p.nl == 1) {
+        for (int j = 0; j < T; ++j) layer1(j, 0, p.kb1);
+      } else {
+        layer1(0, 0, p.kb1);
+        for (int j = 1; j < T; ++j) {
+          layer1(j, 0, n1);
+          layer23(j - 1, 2);
+          layer1(j, n1, n2);
+          layer23(j - 1, 3);
+          layer1(j, n2, p.kb1);
+        }
+        layer23(T - 1, 2);
+        layer23(T - 1, 3);
       }
-      layer23(T - 1, 2);
-      layer23(T - 1, 3);
 #ifdef GNNFD_TC_PROF
       if (blockIdx.x == 0) {
         g_tc_prof[0] = clock64() - t_begin;
@@ -667,11 +468,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       const int64_t row0 = tile_row0(j);
       const uint32_t xr = tmem_base + sl * 256 + ((uint32_t)(q4 * 32) << 16) + eh * 64, yr = xr + 128;
       // ---- hidden layers: accumulator -> +bias, act -> hi/lo pairs, written back in place
-      for (int layer = 0; layer < 2; ++layer) {
+      for (int layer = 0; layer < p.nl - 1; ++layer) {
         PROF_WAIT(0, mbar_wait(&acc_full[sl], (3 * n + layer) & 1));
         tc_fence_after();
         const uint32_t reg = layer == 0 ? xr : yr;
         const uint32_t bias = vec + (layer * TC_H + eh * 64) * 4;
+        float *save = layer == 0 ? a.save_a1 : a.save_a2;
+        if (save != nullptr) save = (row0 + erow < a.rows) ? save + (size_t)(row0 + erow) * TC_H + eh * 64 : nullptr;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           float acc[32];
@@ -685,6 +488,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               const float4 b4 = lds_f4(bias + (c * 32 + h * 16 + i) * 4);
               v[i] = acc[h * 16 + i] + b4.x; v[i + 1] = acc[h * 16 + i + 1] + b4.y;
               v[i + 2] = acc[h * 16 + i + 2] + b4.z; v[i + 3] = acc[h * 16 + i + 3] + b4.w;
+            }
+            if (save != nullptr) {   // training: stash the pre-activation (thread = row, 64 B per store group)
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4 *>(save + c * 32 + h * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
             if (a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
 #pragma unroll
@@ -700,7 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         if (lane == 0) mbar_arrive(&hid_ready[sl * 2 + eh]);
       }
       // ---- final epilogue
-      PROF_WAIT(1, mbar_wait(&acc_full[sl], (3 * n + 2) & 1));
+      PROF_WAIT(1, mbar_wait(&acc_full[sl], (p.nl * n + p.nl - 1) & 1));
       tc_fence_after();
       if (a.n_out == TC_H) {
         float mean = 0.f, rstd = 1.f;
@@ -732,6 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           const float dm = mean_h - o.x;
           mean = 0.5f * (mean_h + o.x);
           rstd = rsqrtf((m2_h + o.y + dm * dm * 32.0f) * (1.0f / TC_H) + a.ln_eps);
+          if (a.save_rstd != nullptr && eh == 0 && row0 + erow < a.rows) a.save_rstd[row0 + erow] = rstd;
         }
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -752,18 +561,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[sl]);
           }
-          const uint32_t b3 = vec + (2 * TC_H + col0) * 4, gw = vec + (3 * TC_H + col0) * 4, gb = vec + (4 * TC_H + col0) * 4;
+          // staged value = normalised row (x-hat); the LayerNorm affine is applied in the coalesced copy-out,
+          // where the training stash of x-hat is also written
+          const uint32_t b3 = vec + (2 * TC_H + col0) * 4;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = lds_f4(b3 + i * 4), w4 = lds_f4(gw + i * 4), g4 = lds_f4(gb + i * 4);
+            const float4 b4 = lds_f4(b3 + i * 4);
             float4 o;
-            o.x = fmaf((acc[i] + b4.x - mean) * rstd, w4.x, g4.x);
-            o.y = fmaf((acc[i + 1] + b4.y - mean) * rstd, w4.y, g4.y);
-            o.z = fmaf((acc[i + 2] + b4.z - mean) * rstd, w4.z, g4.z);
-            o.w = fmaf((acc[i + 3] + b4.w - mean) * rstd, w4.w, g4.w);
+            o.x = (acc[i] + b4.x - mean) * rstd;
+            o.y = (acc[i + 1] + b4.y - mean) * rstd;
+            o.z = (acc[i + 2] + b4.z - mean) * rstd;
+            o.w = (acc[i + 3] + b4.w - mean) * rstd;
             sts_f4(stg + (lane * TC_STG_STRIDE + i) * 4, o);
           }
           __syncwarp();
+          const float4 w4 = lds_f4(vec + (3 * TC_H + col0 + c4 * 4) * 4), g4 = lds_f4(vec + (4 * TC_H + col0 + c4 * 4) * 4);
 #pragma unroll
           for (int jr = 0; jr < 8; ++jr) {
             const int rl = jr * 4 + rr;
@@ -771,7 +583,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             if (g < a.rows) {
               float4 o = lds_f4(stg + (rl * TC_STG_STRIDE + c4 * 4) * 4);
               const size_t off = (size_t)g * TC_H + col0 + c4 * 4;
-              if (a.mul) { const float4 m = ldg_f4(a.mul + off); o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w; }
+              if (a.save_xhat) *reinterpret_cast<float4 *>(a.save_xhat + off) = o;
+              o.x = fmaf(o.x, w4.x, g4.x); o.y = fmaf(o.y, w4.y, g4.y);
+              o.z = fmaf(o.z, w4.z, g4.z); o.w = fmaf(o.w, w4.w, g4.w);
+              if (a.mul) {
+                float4 m = ldg_f4(a.mul + off);
+                if (a.mul_mode == 1) { m.x = dsilu(m.x); m.y = dsilu(m.y); m.z = dsilu(m.z); m.w = dsilu(m.w); }
+                else if (a.mul_mode == 2) { m.x = dtanh(m.x); m.y = dtanh(m.y); m.z = dtanh(m.z); m.w = dtanh(m.w); }
+                o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+              }
               if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + off) = o;
               if (a.out_sum) {
                 float4 r4 = res[jr];
@@ -824,8 +644,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 // ------------------------------------------------------------------------------ weight packing
 // image element (n, k) of one part: 16-bit value at sw128(n, (k % 64) / 8) + (k % 8) * 2
 template <bool FP16>
-__global__ void pack_weights_kernel(const float *__restrict__ w, int n_rows_w, int K, int n_img_rows,
-                                    int n_kblocks, int nw, uint8_t *__restrict__ out, uint32_t block_bytes) {
+__global__ void pack_weights_kernel(const float *__restrict__ w, int ld_n, int ld_k, int n_rows_w, int K,
+                                    int n_img_rows, int n_kblocks, int nw, uint8_t *__restrict__ out,
+                                    uint32_t block_bytes) {
   // one thread per (k-block, image row, 16-byte chunk)
   const int total = n_kblocks * n_img_rows * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -834,8 +655,8 @@ __global__ void pack_weights_kernel(const float *__restrict__ w, int n_rows_w, i
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int k = kb * TC_KB + c * 8 + q * 2;
-      const float x0 = (n < n_rows_w && k < K) ? w[(size_t)n * K + k] : 0.f;
-      const float x1 = (n < n_rows_w && k + 1 < K) ? w[(size_t)n * K + k + 1] : 0.f;
+      const float x0 = (n < n_rows_w && k < K) ? w[(size_t)n * ld_n + (size_t)k * ld_k] : 0.f;
+      const float x1 = (n < n_rows_w && k + 1 < K) ? w[(size_t)n * ld_n + (size_t)(k + 1) * ld_k] : 0.f;
       split2<FP16>(x0, x1, hi[q], lo[q]);
     }
     uint8_t *blk = out + (size_t)kb * block_bytes;
@@ -871,6 +692,9 @@ static int tc_geometry(const gnnfd_mlp_args *a, const TcMode &m, TcParams &p) {
   const int kpad = ((a->k_in + 15) / 16) * 16;
   p.kb1 = (kpad + TC_KB - 1) / TC_KB;
   p.ksteps1 = (kpad - (p.kb1 - 1) * TC_KB) / 16;
+  p.nl = a->n_layers == 1 ? 1 : 3;
+  if (a->n_layers != 0 && a->n_layers != 1 && a->n_layers != 3) return GNNFD_E_UNSUPPORTED;
+  if (p.nl == 1 && (a->n_out != TC_H || a->has_ln)) return GNNFD_E_UNSUPPORTED;
   p.n3 = a->n_out == TC_H ? TC_H : 16;
   if (a->n_out != TC_H && (a->n_out > 16 || a->has_ln)) return GNNFD_E_UNSUPPORTED;
   p.w_block_bytes = (uint32_t)(m.nw * TC_IMG);
@@ -896,11 +720,16 @@ int pack_mlp_tc(const gnnfd_mlp_args *a, void *packed_out, cudaStream_t stream) 
   uint8_t *out = (uint8_t *)packed_out;
   uint8_t *o2 = out + (size_t)p.kb1 * p.w_block_bytes;
   uint8_t *o3 = o2 + (size_t)2 * p.w_block_bytes;
+  const bool strided = p.nl == 1 && (a->w1_ld_n != 0 || a->w1_ld_k != 0);
+  const int ld_n1 = strided ? a->w1_ld_n : a->k_in, ld_k1 = strided ? a->w1_ld_k : 1;
+  const int rows1 = (p.nl == 1 && a->w1_rows > 0) ? a->w1_rows : TC_H;
 #define PACK(FP)                                                                                              \
   do {                                                                                                        \
-    pack_weights_kernel<FP><<<64, 256, 0, stream>>>(a->w1, TC_H, a->k_in, TC_H, p.kb1, m.nw, out, p.w_block_bytes); \
-    pack_weights_kernel<FP><<<32, 256, 0, stream>>>(a->w2, TC_H, TC_H, TC_H, 2, m.nw, o2, p.w_block_bytes);   \
-    pack_weights_kernel<FP><<<32, 256, 0, stream>>>(a->w3, a->n_out, TC_H, p.n3, 2, m.nw, o3, p.w3_block_bytes); \
+    pack_weights_kernel<FP><<<64, 256, 0, stream>>>(a->w1, ld_n1, ld_k1, rows1, a->k_in, TC_H, p.kb1, m.nw, out, p.w_block_bytes); \
+    if (p.nl == 3) {                                                                                          \
+      pack_weights_kernel<FP><<<32, 256, 0, stream>>>(a->w2, TC_H, 1, TC_H, TC_H, TC_H, 2, m.nw, o2, p.w_block_bytes); \
+      pack_weights_kernel<FP><<<32, 256, 0, stream>>>(a->w3, TC_H, 1, a->n_out, TC_H, p.n3, 2, m.nw, o3, p.w3_block_bytes); \
+    }                                                                                                         \
   } while (0)
   if (m.fp16) PACK(true); else PACK(false);
 #undef PACK

@@ -1,0 +1,383 @@
+// Weight-gradient GEMM of the fused MLP block on tcgen05 (kind::tf32, fp32 accumulation in TMEM), sm_100a.
+//
+//   D[128, n] = sum over rows r of  A[r, 0:128]^T  B[r, 0:n]          (dW = dA^T . H, reduction over E or N rows)
+//
+// Both operands are row-major [rows, cols] with the REDUCTION dimension as the row, i.e. "MN-major" UMMA
+// operands: a stage is a [32 rows x cols] fp32 slab whose shared-memory image is the canonical MN-major
+// layout for 32-bit operands, SWIZZLE_128B_BASE32B (the only one tcgen05 accepts for MN-major tf32):
+// 32-column (128 B) x 4-row atoms of 512 B, 32-byte chunk c of row r stored at chunk c ^ (r & 3), atoms
+// ordered [k-atom][mn-atom] (LBO = 512 B between MN atoms, SBO = n_atoms * 512 B between K atoms).
+// The image is written by the producer warps with conflict-free 16-byte stores in the same orientation as
+// global memory (no transposition anywhere); one tcgen05.mma M128 x N<=256 x K8 consumes two K atoms.
+//
+// Producers assemble B on the fly exactly like the forward kernel assembles its input rows (direct /
+// gather / sum2 / diff2 / mean3 segments) and can apply the activation to a saved pre-activation
+// (H = SiLU(a)), so neither the concatenated MLP input nor the hidden activations are ever materialised.
+// Column sums of one operand (the bias gradient) are accumulated by the producers in registers.
+//
+// Split-K over a persistent grid: CTA i reduces rows [i * rows_per_cta, ...) into partial[i][128][n_pad];
+// reduce_partials_kernel adds the partials in CTA order (deterministic, no atomics).
+#include "tc_common.cuh"
+
+namespace gnnfd {
+
+constexpr int WG_KR = 32;          // rows per stage = 4 K atoms
+constexpr int WG_PROD_WARPS = 8;
+constexpr int WG_THREADS = (WG_PROD_WARPS + 1) * 32;   // + MMA issuer warp
+constexpr int WG_MAX_STAGES = 6;
+constexpr int WG_MAX_SLOTS = 8;    // gather-index slots prefetched one stage ahead
+
+struct WgPiece {           // piece 0 = A (128 columns); pieces 1.. = consecutive column blocks of B
+  const float *src;
+  int32_t ld, col, width, mode, act, vec;
+  int32_t atom0;           // first MN atom of this piece inside its operand image
+  int32_t slot0;           // first gather-index slot
+};
+
+struct WgParams {
+  WgPiece pc[4];
+  const int32_t *slot[WG_MAX_SLOTS];
+  int n_pieces, n_slots;
+  int64_t rows;
+  int n_pad;               // B columns, multiple of 32
+  int stages;
+  int64_t rows_per_cta;    // multiple of WG_KR
+  float *partial;          // [grid][128][n_pad]
+  float *colsum;           // [grid][128] or nullptr
+  int colsum_piece;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(512 >> 4) << 16;         // LBO: stride between MN atoms
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;   // SBO: stride between K atoms (4 rows each)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                  // SWIZZLE_128B_BASE32B
+  return d;
+}
+// c = F32, a = b = TF32, both MN-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {   // round to nearest (the tensor core itself truncates)
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float wg_act(float v, int act) {
+  if (act == 1) return v * rcp_ftz(1.0f + ex2_ftz(v * -1.4426950408889634f));
+  if (act == 2) return tanhf(v);
+  return v;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nb_atoms = p.n_pad >> 5;
+  const uint32_t a_bytes = 8 * 4 * 512;                         // [8 k-atoms][4 mn-atoms] = 16 KB
+  const uint32_t b_bytes = 8 * (uint32_t)nb_atoms * 512;        // [8 k-atoms][nb mn-atoms]
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint8_t *s_tail = smem + (size_t)p.stages * stage_bytes;
+  float *s_cs = (float *)s_tail;                                // [8 warps][128] column-sum scratch
+  uint64_t *s_bar = (uint64_t *)(s_tail + WG_PROD_WARPS * 128 * 4);
+  uint64_t *full = s_bar, *empty = s_bar + WG_MAX_STAGES, *done = s_bar + 2 * WG_MAX_STAGES;
+  uint32_t *s_tmem = (uint32_t *)(s_bar + 2 * WG_MAX_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], WG_PROD_WARPS); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_PROD_WARPS) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+  const int64_t r_end = min(p.rows, r_begin + p.rows_per_cta);
+  const int n_stage_iters = (int)((r_end - r_begin + WG_KR - 1) / WG_KR);
+
+  if (warp < WG_PROD_WARPS) {
+    // =============================================================================== producers
+    // warp w owns rows {w, w + 8, w + 16, w + 24} of every stage; lane l owns float4 column l of each piece
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    // gather indices of the NEXT stage, one per lane: lane = slot * 4 + row slot
+    auto load_idx = [&](int it) -> int32_t {
+      const int j = lane & 3, q = lane >> 2;
+      const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 8 * j;
+      return (q < p.n_slots && it < n_stage_iters && g < r_end) ? __ldg(p.slot[q] + g) : 0;
+    };
+    int32_t idx_cur = load_idx(0);
+    for (int it = 0; it < n_stage_iters; ++it) {
+      const int st = it % p.stages;
+      uint8_t *sA = smem + (size_t)st * stage_bytes, *sB = sA + a_bytes;
+      float4 v[4][4];   // [piece][row slot]
+#pragma unroll
+      for (int pi = 0; pi < 4; ++pi) {
+        if (pi < p.n_pieces) {
+          const WgPiece &pc = p.pc[pi];
+          const int wpad = (pc.width + 31) & ~31;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 8 * j;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int32_t i0 = __shfl_sync(0xffffffffu, idx_cur, (pc.slot0 & 7) * 4 + j);
+            const int32_t i1 = __shfl_sync(0xffffffffu, idx_cur, ((pc.slot0 + 1) & 7) * 4 + j);
+            const int32_t i2 = __shfl_sync(0xffffffffu, idx_cur, ((pc.slot0 + 2) & 7) * 4 + j);
+            if (g < r_end && lane * 4 < wpad) {
+              const int64_t rr0 = pc.mode == GNNFD_SEG_DIRECT ? g : (int64_t)i0;
+              if (pc.vec) {
+                if (lane * 4 < pc.width) {
+                  const float *b = pc.src + pc.col + lane * 4;
+                  t = ldg_f4(b + rr0 * pc.ld);
+                  if (pc.mode >= GNNFD_SEG_SUM2) {
+                    const float4 y = ldg_f4(b + (int64_t)i1 * pc.ld);
+                    if (pc.mode == GNNFD_SEG_DIFF2) { t.x -= y.x; t.y -= y.y; t.z -= y.z; t.w -= y.w; }
+                    else { t.x += y.x; t.y += y.y; t.z += y.z; t.w += y.w; }
+                    if (pc.mode == GNNFD_SEG_MEAN3) {
+                      const float4 z = ldg_f4(b + (int64_t)i2 * pc.ld);
+                      constexpr float third = 1.0f / 3.0f;
+                      t.x = (t.x + z.x) * third; t.y = (t.y + z.y) * third;
+                      t.z = (t.z + z.z) * third; t.w = (t.w + z.w) * third;
+                    }
+                  }
+                }
+              } else {
+                float e4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int c = lane * 4 + q;
+                  if (c < pc.width) {
+                    float t0 = __ldg(pc.src + rr0 * pc.ld + pc.col + c);
+                    if (pc.mode >= GNNFD_SEG_SUM2) {
+                      const float y = __ldg(pc.src + (int64_t)i1 * pc.ld + pc.col + c);
+                      t0 = pc.mode == GNNFD_SEG_DIFF2 ? t0 - y : t0 + y;
+                      if (pc.mode == GNNFD_SEG_MEAN3)
+                        t0 = (t0 + __ldg(pc.src + (int64_t)i2 * pc.ld + pc.col + c)) * (1.0f / 3.0f);
+                    }
+                    e4[q] = t0;
+                  }
+                }
+                t = make_float4(e4[0], e4[1], e4[2], e4[3]);
+              }
+            }
+            v[pi][j] = t;
+          }
+        }
+      }
+      const int32_t idx_next = load_idx(it + 1);
+      if (it >= p.stages) mbar_wait(&empty[st], ((it / p.stages) - 1) & 1);
+#pragma unroll
+      for (int pi = 0; pi < 4; ++pi) {
+        if (pi < p.n_pieces) {
+          const WgPiece &pc = p.pc[pi];
+          const int wpad = (pc.width + 31) & ~31;
+          if (lane * 4 < wpad) {
+            uint8_t *img = pi == 0 ? sA : sB;
+            const int natoms = pi == 0 ? 4 : nb_atoms;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4 t = v[pi][j];
+              if (pi == p.colsum_piece) { cs.x += t.x; cs.y += t.y; cs.z += t.z; cs.w += t.w; }
+              if (pc.act) { t.x = wg_act(t.x, pc.act); t.y = wg_act(t.y, pc.act); t.z = wg_act(t.z, pc.act); t.w = wg_act(t.w, pc.act); }
+              t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
+              // stage row r = warp + 8 j: r & 3 == warp & 3, r >> 2 == 2 j + (warp >> 2)
+              const uint32_t off = (uint32_t)(((2 * j + (warp >> 2)) * natoms + pc.atom0 + (lane >> 3)) * 512 +
+                                              (warp & 3) * 128 + (((((lane & 7) >> 1) ^ (warp & 3))) << 5) +
+                                              ((lane & 1) << 4));
+              *reinterpret_cast<float4 *>(img + off) = t;
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+      idx_cur = idx_next;
+    }
+    if (p.colsum != nullptr) {   // column sums: warps reduced in fixed order
+      *reinterpret_cast<float4 *>(s_cs + warp * 128 + lane * 4) = cs;
+      named_bar_sync(1, WG_PROD_WARPS * 32);
+      if (tid < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < WG_PROD_WARPS; ++w) s += s_cs[w * 128 + tid];
+        p.colsum[(size_t)blockIdx.x * 128 + tid] = s;
+      }
+    }
+    // ================================================================================ epilogue
+    if (warp < 4) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      float *dst = p.partial + ((size_t)blockIdx.x * 128 + warp * 32 + lane) * p.n_pad;
+      for (int c = 0; c < nb_atoms; ++c) {
+        float acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, acc);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4 *>(dst + c * 32 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      }
+      tc_fence_before();
+    }
+  } else {
+    // ================================================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t sbo_a = 4 * 512, sbo_b = (uint32_t)nb_atoms * 512;
+      for (int it = 0; it < n_stage_iters; ++it) {
+        const int st = it % p.stages;
+        mbar_wait(&full[st], (it / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + (size_t)st * stage_bytes), sB = sA + a_bytes;
+#pragma unroll 1
+        for (int ka = 0; ka < WG_KR / 8; ++ka) {
+          const uint64_t ad = make_desc_mn(sA + 2 * ka * sbo_a, sbo_a);
+          const uint32_t acc = (it | ka) != 0;
+          for (int n0 = 0; n0 < p.n_pad; n0 += 256) {
+            const int n = min(256, p.n_pad - n0);
+            const uint64_t bd = make_desc_mn(sB + 2 * ka * sbo_b + (n0 >> 5) * 512, sbo_b);
+            umma_tf32_ss(tmem_base + n0, ad, bd, make_idesc_tf32_mn(n), acc);
+          }
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WG_PROD_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
+// out[m, j] = sum over parts (ascending) of part[c][m][n_pad + j]; optionally transposed store; plus colsum
+__global__ void reduce_partials_kernel(const float *__restrict__ part, int n_parts, int n_pad, int m_valid,
+                                       int n_valid, float *__restrict__ out, int ld_out, int transpose,
+                                       const float *__restrict__ cs_part, float *__restrict__ cs_out, int cs_valid) {
+  const int total = m_valid * n_valid;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) {
+    const int m = i / n_valid, j = i % n_valid;
+    const float *src = part + (size_t)m * n_pad + j;
+    float s = 0.f;
+    for (int c = 0; c < n_parts; ++c) s += src[(size_t)c * 128 * n_pad];
+    if (transpose) out[(size_t)j * ld_out + m] = s; else out[(size_t)m * ld_out + j] = s;
+  } else if (cs_out != nullptr && i - total < cs_valid) {
+    const int k = i - total;
+    float s = 0.f;
+    for (int c = 0; c < n_parts; ++c) s += cs_part[(size_t)c * 128 + k];
+    cs_out[k] = s;
+  }
+}
+
+static int64_t wg_rows_per_cta(int64_t rows, int &grid) {
+  const int sms = num_sms();
+  int64_t per = (rows + sms - 1) / sms;
+  per = ((per + WG_KR - 1) / WG_KR) * WG_KR;
+  if (per < 4 * WG_KR) per = 4 * WG_KR;                   // tiny inputs: fewer CTAs, fewer partials
+  grid = (int)((rows + per - 1) / per);
+  return per;
+}
+
+}  // namespace gnnfd
+
+using namespace gnnfd;
+
+static int wg_n_pad(const gnnfd_wgrad_args *a) {
+  int n = 0;
+  for (int s = 0; s < a->n_b; ++s) n += (a->b[s].width + 31) & ~31;
+  return n;
+}
+
+extern "C" size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded) {
+  if (rows <= 0) return 256;
+  int grid;
+  wg_rows_per_cta(rows, grid);
+  return (size_t)grid * 128 * (size_t)n_cols_padded * 4 + (size_t)grid * 128 * 4 + 256;
+}
+
+extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNNFD_CHECK_ARG(a != nullptr && a->out != nullptr, "null args/out");
+  GNNFD_CHECK_ARG(a->rows >= 0, "negative rows");
+  GNNFD_CHECK_ARG(a->n_b >= 1 && a->n_b <= 3, "n_b must be 1..3");
+  GNNFD_CHECK_ARG(a->a.mode == GNNFD_SEG_DIRECT && a->a.width > 0 && a->a.width <= 128, "A must be a DIRECT segment of <= 128 columns");
+  const int n_pad = wg_n_pad(a);
+  GNNFD_CHECK_ARG(n_pad <= 384, "B wider than 384 columns");
+  int n_valid = 0;
+  for (int s = 0; s < a->n_b; ++s) {
+    GNNFD_CHECK_ARG(a->b[s].width > 0 && a->b[s].width <= 128, "B segment width must be 1..128");
+    GNNFD_CHECK_ARG(s == a->n_b - 1 || (a->b[s].width & 31) == 0, "only the last B segment may be narrower than a multiple of 32");
+    n_valid += a->b[s].width;
+  }
+  const int cs_valid = a->colsum ? (a->colsum_of_b ? a->b[0].width : a->a.width) : 0;
+  if (a->rows == 0) {
+    const int m_valid = a->a.width;
+    if (a->transpose_out) { for (int j = 0; j < n_valid; ++j) GNNFD_CUDA(cudaMemsetAsync(a->out + (size_t)j * a->ld_out, 0, m_valid * 4, stream)); }
+    else { for (int m = 0; m < m_valid; ++m) GNNFD_CUDA(cudaMemsetAsync(a->out + (size_t)m * a->ld_out, 0, n_valid * 4, stream)); }
+    if (a->colsum) GNNFD_CUDA(cudaMemsetAsync(a->colsum, 0, cs_valid * 4, stream));
+    return GNNFD_OK;
+  }
+  WgParams p{};
+  int grid;
+  p.rows_per_cta = wg_rows_per_cta(a->rows, grid);
+  p.rows = a->rows;
+  p.n_pad = n_pad;
+  const size_t need = (size_t)grid * 128 * (size_t)n_pad * 4 + (size_t)grid * 128 * 4;
+  if (workspace == nullptr || workspace_bytes < need) { set_error("gnnfd_wgrad: workspace too small"); return GNNFD_E_WORKSPACE; }
+  p.partial = (float *)workspace;
+  float *cs_part = p.partial + (size_t)grid * 128 * n_pad;
+  p.colsum = a->colsum ? cs_part : nullptr;
+  p.colsum_piece = a->colsum ? (a->colsum_of_b ? 1 : 0) : -1;
+  p.n_pieces = 1 + a->n_b;
+  int atom = 0, slot = 0;
+  for (int pi = 0; pi < p.n_pieces; ++pi) {
+    const gnnfd_segment &sg = pi == 0 ? a->a : a->b[pi - 1];
+    WgPiece &pc = p.pc[pi];
+    GNNFD_CHECK_ARG(sg.src != nullptr, "null segment source");
+    GNNFD_CHECK_ARG(sg.mode >= GNNFD_SEG_DIRECT && sg.mode <= GNNFD_SEG_MEAN3, "bad segment mode");
+    pc.src = sg.src; pc.ld = sg.ld; pc.col = sg.col; pc.width = sg.width; pc.mode = sg.mode;
+    pc.act = pi == 0 ? a->a_act : a->b_act;
+    pc.vec = ((sg.ld & 3) == 0) && ((sg.col & 3) == 0) && ((sg.width & 3) == 0) &&
+             ((reinterpret_cast<uintptr_t>(sg.src) & 15) == 0);
+    pc.atom0 = pi == 0 ? 0 : atom;
+    if (pi > 0) atom += ((sg.width + 31) & ~31) >> 5;
+    const int n_idx = sg.mode == GNNFD_SEG_DIRECT ? 0 : sg.mode == GNNFD_SEG_GATHER ? 1 : sg.mode == GNNFD_SEG_MEAN3 ? 3 : 2;
+    pc.slot0 = slot;
+    for (int q = 0; q < n_idx; ++q) {
+      GNNFD_CHECK_ARG(sg.idx[q] != nullptr, "null gather index");
+      GNNFD_CHECK_ARG(slot < WG_MAX_SLOTS, "too many gather indices");
+      p.slot[slot++] = sg.idx[q];
+    }
+  }
+  p.n_slots = slot;
+  const uint32_t stage_bytes = 16 * 1024 + (uint32_t)n_pad * 128;
+  int stages = (int)((200u * 1024u) / stage_bytes);
+  p.stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
+  const int smem = p.stages * (int)stage_bytes + WG_PROD_WARPS * 128 * 4 + (2 * WG_MAX_STAGES + 1) * 8 + 64 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  wgrad_tc_kernel<<<grid, WG_THREADS, smem, stream>>>(p);
+  GNNFD_LAUNCH_CHECK();
+  const int m_valid = a->a.width;
+  const int total = m_valid * n_valid + cs_valid;
+  reduce_partials_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.partial, grid, n_pad, m_valid, n_valid, a->out,
+                                                                  a->ld_out, a->transpose_out, cs_part, a->colsum, cs_valid);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}

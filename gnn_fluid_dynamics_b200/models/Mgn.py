@@ -50,6 +50,9 @@ class MgnA(Model):
 
     def encode_process_decode(self, c_x, f_x, topo, hook=None):
         prec = self.prec
+        if self.wants_grad():   # training step: same kernels + stash, kernel-scheduled backward (training.py)
+            from ..training import encode_process_decode_train
+            return None, None, encode_process_decode_train(self.training_plan(), topo, prec, c_x, f_x)
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
         x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook)

@@ -133,6 +133,21 @@ class Model(nn.Module, ABC):
         self.precision = name
         return self
 
+    def wants_grad(self) -> bool:
+        """True when the hot path must record its backward (training step, reference src/train.py:253-256)."""
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.processer_list.parameters())
+
+    def training_plan(self):
+        """MLP sites of encoder / processor / decoder for the kernel-scheduled backward (training.py)."""
+        from ..training import Plan, Site
+        plan = getattr(self, "_gnnfd_plan", None)
+        if plan is None:
+            blocks = [(Site(b.cell_block.cell_mlp), Site(b.face_block.face_mlp)) for b in self.processer_list]
+            plan = Plan(self.family, Site(self.encoder.face_mlp), Site(self.encoder.cell_mlp), blocks,
+                        Site(self.decoder.face_mlp))
+            object.__setattr__(self, "_gnnfd_plan", plan)
+        return plan
+
     @classmethod
     @abstractmethod
     def get_feature_sizes(cls, dataset):

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_SILU, ACT_TANH, PRECISIONS, SEG_DIFF2, SEG_DIRECT, SEG_GATHER, SEG_MEAN3,  # noqa: F401
-                   SEG_SUM2, MlpArgs, check, lib)
+                   SEG_SUM2, MlpArgs, WgradArgs, check, lib)
 
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -115,6 +115,17 @@ class MLPWeights:
     act: int = ACT_SILU
     packed: Optional[torch.Tensor] = None
     packed_prec: int = -1
+    bwd_packs: Optional[dict] = None   # dgrad operand packs keyed by (which, col0, precision)
+
+
+@dataclass
+class MLPStash:
+    """What the backward needs from one fused-MLP forward (the autograd stash): pre-activations of the
+    two hidden layers, the normalised rows before the LayerNorm affine and 1/sqrt(var + eps)."""
+    a1: torch.Tensor
+    a2: torch.Tensor
+    xhat: Optional[torch.Tensor]
+    rstd: Optional[torch.Tensor]
 
 
 def _fill_args(args: MlpArgs, segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int):
@@ -166,8 +177,10 @@ def pack_mlp(w: MLPWeights, precision: int) -> None:
 def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = _lib.PREC_F32,
                 mul: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
                 want_raw: bool = True, want_sum: bool = False,
-                out_raw: Optional[torch.Tensor] = None, out_sum: Optional[torch.Tensor] = None):
-    """Run the fused block; returns (out_raw or None, out_sum or None)."""
+                out_raw: Optional[torch.Tensor] = None, out_sum: Optional[torch.Tensor] = None,
+                stash: bool = False):
+    """Run the fused block; returns (out_raw or None, out_sum or None) and, with ``stash=True``
+    (training), additionally the ``MLPStash`` the backward consumes."""
     args = MlpArgs()
     keep = _fill_args(args, segs, w, rows, precision)
     n_out = w.w3.shape[0]
@@ -187,7 +200,141 @@ def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = 
     args.residual = _ptr(_req(residual, torch.float32, "residual")) if residual is not None else None
     args.out_raw = _ptr(out_raw) if want_raw else None
     args.out_sum = _ptr(out_sum) if want_sum else None
+    st = None
+    if stash:
+        if precision == _lib.PREC_F32:
+            raise RuntimeError("training needs a tensor-core precision (the f32 kernel keeps no stash)")
+        hid = w.w2.shape[0]
+        st = MLPStash(a1=torch.empty(rows, hid, dtype=torch.float32, device=dev),
+                      a2=torch.empty(rows, hid, dtype=torch.float32, device=dev),
+                      xhat=torch.empty(rows, n_out, dtype=torch.float32, device=dev) if w.has_ln else None,
+                      rstd=torch.empty(rows, dtype=torch.float32, device=dev) if w.has_ln else None)
+        args.save_a1, args.save_a2 = st.a1.data_ptr(), st.a2.data_ptr()
+        args.save_xhat, args.save_rstd = _ptr(st.xhat), _ptr(st.rstd)
     check(lib.gnnfd_mlp_forward(C.byref(args), _stream()), "gnnfd_mlp_forward")
     _count(1)
     del keep
+    if stash:
+        return (out_raw if want_raw else None), (out_sum if want_sum else None), st
     return (out_raw if want_raw else None), (out_sum if want_sum else None)
+
+
+# ------------------------------------------------------------------------------------------ backward
+
+def _fill_segment(sg, s: Seg, name: str):
+    src = _req(s.src, torch.float32, f"{name}.src")
+    width = s.width if s.width is not None else src.shape[1] - s.col
+    sg.src = src.data_ptr()
+    for j in range(3):
+        sg.idx[j] = _req(s.idx[j], torch.int32, f"{name}.idx[{j}]").data_ptr() if j < len(s.idx) else None
+    sg.ld, sg.col, sg.width, sg.mode = src.stride(0), s.col, width, s.mode
+    return width
+
+
+def linear_tc(src: Seg, rows: int, w_t: torch.Tensor, ld_n: int, ld_k: int, w_rows: int, k_in: int,
+              pack_cache: dict, pack_key, precision: int, bias: Optional[torch.Tensor] = None,
+              mul: Optional[torch.Tensor] = None, mul_mode: int = 0, residual: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[rows,128] = (src . Wt^T (+ bias)) (* mul | act'(mul)) (+ residual), one tensor-core Linear
+    (gnnfd_mlp_forward with n_layers = 1).  ``w_t`` is addressed as element (n, k) = w_t.data_ptr()
+    [n * ld_n + k * ld_k] so a forward weight is used transposed in place (dgrad: dH = dA . W)."""
+    args = MlpArgs()
+    args.rows, args.n_seg = rows, 1
+    width = _fill_segment(args.seg[0], src, "src")
+    if width != k_in:
+        raise RuntimeError(f"linear_tc: source width {width} != k_in {k_in}")
+    args.k_in, args.hidden, args.n_out = k_in, 128, 128
+    args.w1 = w_t.data_ptr()
+    args.b1 = _ptr(bias)
+    args.has_ln, args.ln_eps, args.act = 0, 0.0, ACT_SILU
+    args.precision = precision
+    args.n_layers, args.mul_mode = 1, mul_mode
+    args.w1_ld_n, args.w1_ld_k, args.w1_rows = ld_n, ld_k, w_rows
+    if out is None:
+        out = torch.empty(rows, 128, dtype=torch.float32, device=w_t.device)
+    args.mul = _ptr(_req(mul, torch.float32, "mul")) if mul is not None else None
+    if residual is not None:
+        args.residual, args.out_sum = _req(residual, torch.float32, "residual").data_ptr(), out.data_ptr()
+    else:
+        args.out_raw = out.data_ptr()
+    key = (pack_key, precision)
+    packed = pack_cache.get(key)
+    if packed is None:
+        nbytes = lib.gnnfd_pack_mlp_bytes(k_in, 128, 128, precision)
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=w_t.device)
+        check(lib.gnnfd_pack_mlp(C.byref(args), packed.data_ptr(), _stream()), "gnnfd_pack_mlp")
+        _count(1)
+        pack_cache[key] = packed
+    args.packed = packed.data_ptr()
+    check(lib.gnnfd_mlp_forward(C.byref(args), _stream()), "gnnfd_mlp_forward")
+    _count(1)
+    return out
+
+
+def ln_backward(g: torch.Tensor, xhat: torch.Tensor, rstd: torch.Tensor, ln_w: Optional[torch.Tensor]):
+    """(dy[rows,128], sums[3,128]) - see gnnfd_ln_backward."""
+    g = _req(g, torch.float32, "g")
+    rows = g.shape[0]
+    dy = torch.empty_like(g)
+    sums = torch.empty(3, 128, dtype=torch.float32, device=g.device)
+    nb = lib.gnnfd_ln_backward_workspace_bytes(rows)
+    ws = torch.empty(nb, dtype=torch.uint8, device=g.device)
+    check(lib.gnnfd_ln_backward(g.data_ptr(), _req(xhat, torch.float32, "xhat").data_ptr(),
+                                _req(rstd, torch.float32, "rstd").data_ptr(), _ptr(ln_w), rows, dy.data_ptr(),
+                                sums.data_ptr(), ws.data_ptr(), nb, _stream()), "gnnfd_ln_backward")
+    _count(2)
+    return dy, sums
+
+
+def wgrad(a: Seg, b: Sequence[Seg], rows: int, out: torch.Tensor, a_act: int = 0, b_act: int = 0,
+          transpose_out: bool = False, colsum: Optional[torch.Tensor] = None, colsum_of_b: bool = False,
+          workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[m, n] = sum_r A[r, m] B[r, n] on the tensor cores (gnnfd_wgrad); activations: 0 none, 1 SiLU, 2 tanh."""
+    args = WgradArgs()
+    args.rows = rows
+    _fill_segment(args.a, a, "a")
+    args.a_act, args.b_act, args.n_b = a_act, b_act, len(b)
+    n_pad = 0
+    for i, s in enumerate(b):
+        n_pad += (_fill_segment(args.b[i], s, f"b[{i}]") + 31) // 32 * 32
+    _req(out, torch.float32, "out")
+    args.out, args.ld_out, args.transpose_out = out.data_ptr(), out.stride(0), int(transpose_out)
+    args.colsum, args.colsum_of_b = _ptr(colsum), int(colsum_of_b)
+    nb = lib.gnnfd_wgrad_workspace_bytes(rows, n_pad)
+    if workspace is None or workspace.numel() < nb:
+        workspace = torch.empty(nb, dtype=torch.uint8, device=out.device)
+    check(lib.gnnfd_wgrad(C.byref(args), workspace.data_ptr(), workspace.numel(), _stream()), "gnnfd_wgrad")
+    _count(2)
+    return out
+
+
+def segment_sum3(a, b, c, cols, width: int, sign_b: float, n_part: int, offsets, perm, n_rows: int,
+                 scale: float = 1.0, base: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """out[r] = base[r] + scale * sum over CSR row r of the three-part source (gnnfd_segment_sum3)."""
+    a = _req(a, torch.float32, "a")
+    ld = a.stride(0)
+    for t in (b, c):
+        if t is not None and _req(t, torch.float32, "part").stride(0) != ld:
+            raise RuntimeError("segment_sum3: parts must share a row stride")
+    if out is None:
+        out = torch.empty(n_rows, width, dtype=torch.float32, device=a.device)
+    check(lib.gnnfd_segment_sum3(a.data_ptr(), _ptr(b), _ptr(c), ld, cols[0], cols[1], cols[2], width, float(sign_b),
+                                 n_part, _req(offsets, torch.int32, "offsets").data_ptr(),
+                                 _req(perm, torch.int32, "perm").data_ptr(), n_rows, float(scale), _ptr(base),
+                                 base.stride(0) if base is not None else 0, out.data_ptr(), out.stride(0), _stream()),
+          "gnnfd_segment_sum3")
+    _count(1)
+    return out
+
+
+def gather_pair_add(src: torch.Tensor, i0: torch.Tensor, i1: torch.Tensor, sign: float, halves: bool, rows: int,
+                    base: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[rows,128] = base + gathered pair (gnnfd_gather_pair_add); ``out`` may be ``base`` (in place)."""
+    src = _req(src, torch.float32, "src")
+    if out is None:
+        out = torch.empty(rows, 128, dtype=torch.float32, device=src.device)
+    check(lib.gnnfd_gather_pair_add(out.data_ptr(), _ptr(base), src.data_ptr(), src.stride(0),
+                                    _req(i0, torch.int32, "i0").data_ptr(), _req(i1, torch.int32, "i1").data_ptr(),
+                                    float(sign), int(halves), rows, _stream()), "gnnfd_gather_pair_add")
+    _count(1)
+    return out

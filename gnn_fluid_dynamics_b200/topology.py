@@ -59,6 +59,19 @@ class MeshTopology:
             self.cell_offsets, self.cell_perm = ops.csr_build(idx, self.n_cells)
         return self.cell_offsets, self.cell_perm
 
+    def build_rowcol_csr(self):
+        """CSR of cat[row; col] over cells: the transpose of the Face_Block gathers x[row], x[col]
+        (Fvgn.py:294) - d x[n] = sum_{row(k)=n} dIn1[k] + sum_{col(k)=n} dIn2[k]."""
+        if getattr(self, "_rowcol", None) is None:
+            self._rowcol = ops.csr_build(torch.cat([self.row, self.col]), self.n_cells)
+        return self._rowcol
+
+    def build_vf_csr(self):
+        """CSR of cat[vf0; vf1; vf2] over vertices: the transpose of the 3-vertex mean (Fvgn.py:317-321)."""
+        if getattr(self, "_vfcsr", None) is None:
+            self._vfcsr = ops.csr_build(torch.cat(list(self.vf)), self.n_vertices)
+        return self._vfcsr
+
     def vertex_csr_rows(self, n_rows: int):
         """Vertex CSR padded to ``n_rows`` >= V rows (Vertex_Block writes N rows, VertPot.py:221)."""
         if n_rows == self.n_vertices:

@@ -1,0 +1,223 @@
+"""Training path of the hot path: encoder -> GN_Blocks -> decoder as ONE autograd node whose backward
+is a hand-scheduled chain of CUDA kernels (BASELINE.json north_star (e)).
+
+The reference trains through autograd over ~25 library kernels per block (``src/train.py:253-256``);
+here the forward is the same fused kernels as inference (with the backward stash switched on) and
+the backward of every sub-block is:
+
+  LayerNorm backward (streaming, + d ln_w / d ln_b / d b3 column sums)      ops.ln_backward
+  dgrad chain  dA2 = (dy W3) * act'(a2), dA1 = (dA2 W2) * act'(a1), dIn = dA1 W1[:, segment]
+               - tcgen05 single-Linear launches, activation derivative and gradient accumulation
+                 (out = residual + ...) fused in the epilogue                    ops.linear_tc
+  wgrad        dW = dA^T H on tcgen05 kind::tf32, H = act(a) / the gathered MLP input assembled on the
+               fly, bias gradients as column sums of dA                          ops.wgrad
+  transposed gathers: the Face_Block's x[row], x[col] gathers become a deterministic segment sum over
+               the CSR of cat[row; col]; the 3-vertex mean becomes a segment sum over cat[vf0; vf1; vf2];
+               the edge->vertex scatter_add becomes a gather                     ops.segment_sum3 / gather_pair_add
+
+Families: 'fvgn' (Fvgn/Flux) and 'mgn' (Mgn/StreamFunc).  No atomics anywhere: gradients are bitwise
+reproducible run to run.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import ops
+from ._lib import ACT_SILU, SEG_GATHER, SEG_MEAN3
+from .ops import MLPStash, MLPWeights, Seg
+from .processor import H, _split_mlp, vertex_half_sum, weights_of
+from .topology import MeshTopology
+
+PARAM_NAMES = ("w1", "b1", "w2", "b2", "w3", "b3", "ln_w", "ln_b")
+
+
+class Site:
+    """One MLP module of the stack and its parameters in PARAM_NAMES order (None where absent)."""
+
+    def __init__(self, seq: torch.nn.Module, act: int = ACT_SILU):
+        self.seq, self.act = seq, act
+        inner, ln = _split_mlp(seq)
+        lin = [m for m in inner if isinstance(m, torch.nn.Linear)]
+        self.params = [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias,
+                       ln.weight if ln is not None else None, ln.bias if ln is not None else None]
+
+    def weights(self) -> MLPWeights:
+        return weights_of(self.seq, self.act)
+
+
+def mlp_backward(w: MLPWeights, st: MLPStash, segs: Sequence[Seg], rows: int, g: torch.Tensor, prec: int,
+                 din: Sequence[Optional[dict]], workspace: Optional[torch.Tensor] = None):
+    """Backward of one fused MLP.  ``g`` = gradient w.r.t. the MLP(+LN) output.  ``din[i]`` is None (segment i
+    needs no gradient) or a dict with optional ``residual`` (added to the segment's input gradient) and
+    ``out`` (destination).  Returns (parameter gradients in PARAM_NAMES order, [dIn_i or None])."""
+    if w.bwd_packs is None:
+        w.bwd_packs = {}
+    packs = w.bwd_packs
+    code = w.act + 1                      # SiLU -> 1, tanh -> 2 (wgrad act / dgrad mul_mode)
+    dev = g.device
+    n_out, k_in = w.w3.shape[0], w.w1.shape[1]
+    grads = {}
+    g = g.contiguous()
+    if w.has_ln:
+        dy, sums = ops.ln_backward(g, st.xhat, st.rstd, w.ln_w)
+        if w.ln_w is not None:
+            grads["ln_w"], grads["ln_b"] = sums[0], sums[1]
+        db3_from_ln = sums[2]
+    else:
+        dy, db3_from_ln = g, None
+    new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+    # ---- layer 3
+    grads["w3"] = new(n_out, H)
+    want_b3 = w.b3 is not None and db3_from_ln is None
+    if want_b3:
+        grads["b3"] = new(n_out)
+    elif w.b3 is not None:
+        grads["b3"] = db3_from_ln
+    if n_out == H:
+        ops.wgrad(Seg(dy), [Seg(st.a2)], rows, grads["w3"], b_act=code,
+                  colsum=grads["b3"] if want_b3 else None, workspace=workspace)
+    else:   # narrow head: put the 128-wide activation on the M side, store transposed
+        ops.wgrad(Seg(st.a2), [Seg(dy)], rows, grads["w3"], a_act=code, transpose_out=True,
+                  colsum=grads["b3"] if want_b3 else None, colsum_of_b=True, workspace=workspace)
+    d_a2 = ops.linear_tc(Seg(dy), rows, w.w3, 1, H, H, n_out, packs, "w3t", prec, mul=st.a2, mul_mode=code)
+    # ---- layer 2
+    grads["w2"] = new(H, H)
+    if w.b2 is not None:
+        grads["b2"] = new(H)
+    ops.wgrad(Seg(d_a2), [Seg(st.a1)], rows, grads["w2"], b_act=code, colsum=grads.get("b2"), workspace=workspace)
+    d_a1 = ops.linear_tc(Seg(d_a2), rows, w.w2, 1, H, H, H, packs, "w2t", prec, mul=st.a1, mul_mode=code)
+    # ---- layer 1
+    grads["w1"] = new(H, k_in)
+    if w.b1 is not None:
+        grads["b1"] = new(H)
+    ops.wgrad(Seg(d_a1), list(segs), rows, grads["w1"], colsum=grads.get("b1"), workspace=workspace)
+    dins: List[Optional[torch.Tensor]] = []
+    col0 = 0
+    for i, s in enumerate(segs):
+        width = s.width if s.width is not None else s.src.shape[1] - s.col
+        spec = din[i] if i < len(din) else None
+        if spec is None:
+            dins.append(None)
+        else:
+            dins.append(ops.linear_tc(Seg(d_a1), rows, w.w1[:, col0:], 1, k_in, width, H, packs, ("w1t", col0), prec,
+                                      residual=spec.get("residual"), out=spec.get("out")))
+        col0 += width
+    return [grads.get(n) for n in PARAM_NAMES], dins
+
+
+class Plan:
+    """The MLP sites of one model in execution order + the data-flow family."""
+
+    def __init__(self, family: str, enc_edge: Site, enc_node: Site, blocks: Sequence[tuple], dec: Site):
+        if family not in ("fvgn", "mgn"):
+            raise NotImplementedError(f"training kernels cover the 'fvgn' and 'mgn' families, not {family!r}")
+        self.family, self.enc_edge, self.enc_node, self.blocks, self.dec = family, enc_edge, enc_node, list(blocks), dec
+        self.sites = [enc_edge, enc_node] + [s for b in self.blocks for s in b] + [dec]   # block = (node site, edge site)
+
+    def flat_params(self):
+        return [p for s in self.sites for p in s.params if p is not None]
+
+
+def _node_segs(x, vsum, topo):
+    return [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf)]
+
+
+def _edge_segs(e, xs, topo):
+    return [Seg(e), Seg(xs, SEG_GATHER, (topo.row,)), Seg(xs, SEG_GATHER, (topo.col,))]
+
+
+class EncodeProcessDecode(torch.autograd.Function):
+    """decoder(processor(encoder(c_x, f_x))) with a kernel-scheduled backward; differentiable w.r.t. every
+    MLP parameter (inputs are data: no gradient)."""
+
+    @staticmethod
+    def forward(ctx, plan: Plan, topo: MeshTopology, prec: int, c_x: torch.Tensor, f_x: torch.Tensor, *params):
+        fam = plan.family
+        c_x, f_x = c_x.contiguous(), f_x.contiguous()
+        N, E = c_x.shape[0], f_x.shape[0]
+        e, _, st_ee = ops.mlp_forward([Seg(f_x)], plan.enc_edge.weights(), E, prec, stash=True)
+        x, _, st_en = ops.mlp_forward([Seg(c_x)], plan.enc_node.weights(), N, prec, stash=True)
+        saved = []
+        for node_site, edge_site in plan.blocks:
+            wn, we = node_site.weights(), edge_site.weights()
+            if fam == "fvgn":
+                vsum = vertex_half_sum(e, topo)
+                x_raw, x_new, st_n = ops.mlp_forward(_node_segs(x, vsum, topo), wn, N, prec, residual=x,
+                                                     want_raw=True, want_sum=True, stash=True)
+                _, e_new, st_e = ops.mlp_forward(_edge_segs(e, x_raw, topo), we, E, prec, residual=e,
+                                                 want_raw=False, want_sum=True, stash=True)
+                saved.append((x, e, vsum, x_raw, st_n, st_e))
+            else:
+                e_raw, e_new, st_e = ops.mlp_forward(_edge_segs(e, x, topo), we, E, prec, residual=e,
+                                                     want_raw=True, want_sum=True, stash=True)
+                vsum = vertex_half_sum(e_raw, topo)
+                _, x_new, st_n = ops.mlp_forward(_node_segs(x, vsum, topo), wn, N, prec, residual=x,
+                                                 want_raw=False, want_sum=True, stash=True)
+                saved.append((x, e, vsum, None, st_n, st_e))
+            x, e = x_new, e_new
+        dec_in = e if fam == "fvgn" else x
+        out, _, st_d = ops.mlp_forward([Seg(dec_in)], plan.dec.weights(), dec_in.shape[0], prec, stash=True)
+        ctx.plan, ctx.topo, ctx.prec = plan, topo, prec
+        ctx.stash = (c_x, f_x, st_ee, st_en, saved, dec_in, st_d)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        plan, topo, prec = ctx.plan, ctx.topo, ctx.prec
+        c_x, f_x, st_ee, st_en, saved, dec_in, st_d = ctx.stash
+        fam = plan.family
+        N, E, V = c_x.shape[0], f_x.shape[0], topo.n_vertices
+        dev = g_out.device
+        ws = torch.empty(ops.lib.gnnfd_wgrad_workspace_bytes(max(N, E), 384), dtype=torch.uint8, device=dev)
+        rc_off, rc_perm = topo.build_rowcol_csr()
+        vf_off, vf_perm = topo.build_vf_csr()
+        site_grads = {}
+
+        gd, dins = mlp_backward(plan.dec.weights(), st_d, [Seg(dec_in)], dec_in.shape[0], g_out, prec, [{}], ws)
+        site_grads[id(plan.dec)] = gd
+        d_e, d_x = (dins[0], None) if fam == "fvgn" else (None, dins[0])
+
+        for (node_site, edge_site), (x_in, e_in, vsum, x_raw, st_n, st_e) in zip(reversed(plan.blocks), reversed(saved)):
+            wn, we = node_site.weights(), edge_site.weights()
+            if fam == "fvgn":
+                # e_new = e + edge(e, x_raw[row], x_raw[col]);  x_new = x + x_raw;  x_raw = node(x, mean3(S(e)))
+                ge, dins = mlp_backward(we, st_e, _edge_segs(e_in, x_raw, topo), E, d_e, prec,
+                                        [{"residual": d_e}, {}, {}], ws)
+                d_e_acc, t1, t2 = dins
+                d_x_raw = ops.segment_sum3(t1, t2, None, (0, 0, 0), H, 1.0, E, rc_off, rc_perm, N, base=d_x)
+                gn, dins = mlp_backward(wn, st_n, _node_segs(x_in, vsum, topo), N, d_x_raw, prec,
+                                        [{"residual": d_x} if d_x is not None else {}, {}], ws)
+                d_x, t3 = dins
+                d_vsum = ops.segment_sum3(t3, None, None, (0, 0, 0), H // 2, 1.0, N, vf_off, vf_perm, V, scale=1.0 / 3.0)
+                d_e = ops.gather_pair_add(d_vsum, topo.v0, topo.v1, 1.0, True, E, base=d_e_acc, out=d_e_acc)
+            else:
+                # e_raw = edge(e, x[row], x[col]); e_new = e + e_raw;  x_new = x + node(x, mean3(S(e_raw)))
+                gn, dins = mlp_backward(wn, st_n, _node_segs(x_in, vsum, topo), N, d_x, prec,
+                                        [{"residual": d_x}, {}], ws)
+                d_x_acc, t3 = dins
+                d_vsum = ops.segment_sum3(t3, None, None, (0, 0, 0), H // 2, 1.0, N, vf_off, vf_perm, V, scale=1.0 / 3.0)
+                d_e_raw = ops.gather_pair_add(d_vsum, topo.v0, topo.v1, 1.0, True, E, base=d_e)
+                ge, dins = mlp_backward(we, st_e, _edge_segs(e_in, x_in, topo), E, d_e_raw, prec,
+                                        [{"residual": d_e} if d_e is not None else {}, {}, {}], ws)
+                d_e, t1, t2 = dins
+                d_x = ops.segment_sum3(t1, t2, None, (0, 0, 0), H, 1.0, E, rc_off, rc_perm, N, base=d_x_acc)
+            site_grads[id(node_site)], site_grads[id(edge_site)] = gn, ge
+
+        if d_e is None:
+            d_e = torch.zeros(E, H, dtype=torch.float32, device=dev)
+        if d_x is None:
+            d_x = torch.zeros(N, H, dtype=torch.float32, device=dev)
+        site_grads[id(plan.enc_edge)], _ = mlp_backward(plan.enc_edge.weights(), st_ee, [Seg(f_x)], E, d_e, prec, [None], ws)
+        site_grads[id(plan.enc_node)], _ = mlp_backward(plan.enc_node.weights(), st_en, [Seg(c_x)], N, d_x, prec, [None], ws)
+        ctx.stash = None
+        flat = []
+        for s in plan.sites:
+            gs = site_grads[id(s)]
+            flat.extend(gr for gr, p in zip(gs, s.params) if p is not None)
+        return (None, None, None, None, None, *flat)
+
+
+def encode_process_decode_train(plan: Plan, topo: MeshTopology, prec: int, c_x, f_x):
+    return EncodeProcessDecode.apply(plan, topo, prec, c_x, f_x, *plan.flat_params())

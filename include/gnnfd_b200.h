@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 1
+#define GNNFD_ABI_VERSION 2
 
 enum {
   GNNFD_OK = 0,
@@ -102,6 +102,23 @@ typedef struct {
   /* tensor-core precisions only: operand pack produced by gnnfd_pack_mlp (NULL for F32) */
   const void *packed;
   int32_t precision; /* GNNFD_PREC_* */
+  /* --- training support (tensor-core precisions; all optional, zero = inference behaviour) --------
+   * n_layers 0|3: the 3-Linear MLP above.  n_layers 1: a single Linear out = In W1^T (+ b1), n_out ==
+   * hidden == 128 rows of w1, no activation / LayerNorm - the building block of the backward dgrad chain
+   * (dH = dA W, with w1 = W^T).
+   * mul_mode: how `mul` is applied: 0 out *= mul, 1 out *= silu'(mul), 2 out *= tanh'(mul)  (mul then
+   * holds the saved pre-activation, i.e. dA = dH . act'(A)).
+   * save_a1/save_a2 [rows, hidden]: pre-activations (bias included) of the two hidden layers;
+   * save_rstd [rows]: LayerNorm 1/sqrt(var + eps) - what the backward needs (autograd stash). */
+  int32_t n_layers;
+  int32_t mul_mode;
+  float *save_a1, *save_a2, *save_rstd;
+  float *save_xhat; /* [rows, n_out] normalised rows before the LayerNorm affine (n_out == 128 only) */
+  /* n_layers == 1 only: how w1 is addressed - element (output feature n, input feature k) is
+   * w1[n * w1_ld_n + k * w1_ld_k]; both 0 = the PyTorch layout [n_out, k_in] (ld_n = k_in, ld_k = 1).
+   * dgrad uses a forward weight W[out, in] transposed in place: w1 = W + col0, ld_n = 1, ld_k = in.
+   * w1_rows: valid output features (rows >= w1_rows of the 128 are zero); 0 = 128. */
+  int32_t w1_ld_n, w1_ld_k, w1_rows;
 } gnnfd_mlp_args;
 
 int gnnfd_abi_version(void);
@@ -139,6 +156,65 @@ int gnnfd_mlp_forward(const gnnfd_mlp_args *args, void *stream);
  * layout, biases and LayerNorm affine appended) */
 size_t gnnfd_pack_mlp_bytes(int32_t k_in, int32_t hidden, int32_t n_out, int32_t precision);
 int gnnfd_pack_mlp(const gnnfd_mlp_args *args, void *packed_out, void *stream);
+
+/* ------------------------------------------------------------------------------------ training
+ * Backward kernels (BASELINE.json north_star (e)).  The reference gets its backward from autograd over
+ * the same call sites (src/train.py:256 `losses["total_log_loss"].backward()`); these entry points are
+ * what a torch.autograd.Function around gnnfd_mlp_forward calls (gnn_fluid_dynamics_b200/training.py).
+ *
+ * dgrad of one Linear is gnnfd_mlp_forward with n_layers = 1 and the forward weight addressed
+ * transposed (w1_ld_n / w1_ld_k), its activation derivative fused through mul / mul_mode. */
+
+/* LayerNorm backward (nn.LayerNorm of Model.py:39):
+ *   dy = rstd * (g*w - mean(g*w) - xhat * mean(g*w*xhat))       rows x 128
+ *   sums[0,:] = sum_r g*xhat (d ln_w)   sums[1,:] = sum_r g (d ln_b)   sums[2,:] = sum_r dy (d bias of Linear 3)
+ * ln_w may be NULL (no affine).  Deterministic (fixed row ownership, ordered partial sums). */
+size_t gnnfd_ln_backward_workspace_bytes(int64_t rows);
+int gnnfd_ln_backward(const float *g, const float *xhat, const float *rstd, const float *ln_w, int64_t rows,
+                      float *dy, float *sums /*[3,128]*/, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Weight gradient of one Linear: out[m, n] = sum_r A[r, m] * B[r, n]  (tcgen05 kind::tf32, MN-major operands,
+ * split-K over the grid with an ordered reduction).  A is a DIRECT [rows, <=128] matrix, B is assembled from
+ * up to three segments exactly like the forward input (so dW1 of a Face_Block reads e, x[row], x[col] in
+ * place); a_act / b_act (0 none, 1 SiLU, 2 tanh) turn a saved pre-activation into the hidden activation on
+ * load.  colsum (optional) receives the column sums of A (or of B segment 0 when colsum_of_b) - the bias
+ * gradient.  transpose_out stores out[n * ld_out + m]. */
+typedef struct {
+  int64_t rows;
+  gnnfd_segment a;
+  int32_t a_act;
+  int32_t n_b;
+  gnnfd_segment b[3];
+  int32_t b_act;
+  float *out;
+  int32_t ld_out;
+  int32_t transpose_out;
+  float *colsum;
+  int32_t colsum_of_b;
+} gnnfd_wgrad_args;
+size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded /* sum of B widths rounded up to 32 */);
+int gnnfd_wgrad(const gnnfd_wgrad_args *args, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Transpose of a gather = deterministic segment sum with up to three source parts, a scale and a base:
+ *   out[r, :] = base[r, :] + scale * sum over p in perm[offsets[r]:offsets[r+1]] (ascending) of
+ *               p < n ? a[p, col_a:+width] : p < 2n ? sign_b * b[p-n, col_b:+width] : c[p-2n, col_c:+width]
+ * d x[row], d x[col] of a Face_Block (CSR of cat[row; col]); d vsum of the 3-vertex mean (CSR of
+ * cat[vf0; vf1; vf2], scale 1/3).  b, c NULL = a; base NULL = 0. */
+int gnnfd_segment_sum3(const float *a, const float *b, const float *c, int32_t ld, int32_t col_a, int32_t col_b,
+                       int32_t col_c, int32_t width, float sign_b, int64_t n_part, const int32_t *offsets,
+                       const int32_t *perm, int64_t n_rows, float scale, const float *base, int32_t ld_base,
+                       float *out, int32_t ld_out, void *stream);
+
+/* Transpose of the edge->vertex / edge->cell segment sums (a scatter_add backward is a gather) over
+ * dst[rows, 128], base NULL = 0, base may alias dst:
+ *   halves: dst[k, 0:64] = base[k, 0:64] + src[i0[k], 0:64], dst[k, 64:128] = base[k, 64:128] + sign * src[i1[k], 0:64]
+ *   else  : dst[k, :] = base[k, :] + src[i0[k], :] + sign * src[i1[k], :] */
+int gnnfd_gather_pair_add(float *dst, const float *base, const float *src, int32_t ld_src, const int32_t *i0,
+                          const int32_t *i1, float sign, int32_t halves, int64_t rows, void *stream);
+
+/* sizeof(gnnfd_mlp_args) (which = 0), sizeof(gnnfd_wgrad_args) (1), sizeof(gnnfd_segment) (2): lets a
+ * foreign-function binding verify its struct mirror against the library it loaded. */
+size_t gnnfd_struct_size(int32_t which);
 
 /* Diagnostic: cycle counters recorded by CTA 0 of the last tensor-core MLP launch (synchronises).
  * out16[0..6]  MMA issuer: total, w_empty wait, w_full wait, acc_free wait, a_full wait, act_ready

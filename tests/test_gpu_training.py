@@ -1,0 +1,222 @@
+"""GPU parity of the backward kernels (BASELINE.json north_star (e)): unit kernels against plain fp64/fp32
+torch restatements, the whole training step (loss + every parameter gradient) against the CPU oracle's
+autograd and against the reference-generated golden fixture tests/golden/train_FvgnA.npz.
+
+Tolerances: loss 1e-4 relative; gradients rel-L2 <= 1e-3 per parameter tensor (same bar north_star states
+for processor outputs: dgrad runs split-bf16 (~1e-5), wgrad runs single-pass TF32 with round-to-nearest
+operands (~3e-4), fp32 accumulation everywhere)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as omodel
+from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
+from helpers import LOSS_W, build_model, golden_graphs, load_golden
+
+pytestmark = pytest.mark.gpu
+GRAD_TOL = 1e-3
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def i32(t):
+    return t.to(torch.int32).to(dev())
+
+
+# ------------------------------------------------------------------------------------ unit kernels
+@pytest.mark.parametrize("rows", [1, 31, 32, 33, 1000, 40000])
+def test_wgrad_dense_vs_torch(rows):
+    from gnn_fluid_dynamics_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    a, b = torch.randn(rows, 128, generator=g), torch.randn(rows, 128, generator=g)
+    ref = a.double().t() @ torch.nn.functional.silu(b.double())
+    out = torch.empty(128, 128, device=dev())
+    cs = torch.empty(128, device=dev())
+    ops.wgrad(ops.Seg(a.to(dev())), [ops.Seg(b.to(dev()))], rows, out, b_act=1, colsum=cs)
+    assert rel_l2(out, ref.float()) < GRAD_TOL, rel_l2(out, ref.float())
+    assert rel_l2(cs, a.double().sum(0).float()) < 1e-5
+
+
+def test_wgrad_gathered_concat_and_narrow_vs_torch():
+    """dW1 of a Face_Block (B = [e | x[row] | x[col]], 384 columns), of a Cell_Block (B = [x | mean3(vsum)]),
+    of an encoder (B 10 columns) and dW3 of a decoder head (narrow side transposed)."""
+    from gnn_fluid_dynamics_b200 import ops, _lib
+    g = torch.Generator().manual_seed(11)
+    N, E, V = 700, 1111, 400
+    x, e, vs = torch.randn(N, 128, generator=g), torch.randn(E, 128, generator=g), torch.randn(V, 64, generator=g)
+    row, col = torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)
+    vf = [torch.randint(0, V, (N,), generator=g) for _ in range(3)]
+    da_e, da_n = torch.randn(E, 128, generator=g), torch.randn(N, 128, generator=g)
+    xd, ed, vsd = x.to(dev()), e.to(dev()), vs.to(dev())
+    # edge layer 1
+    ref = da_e.double().t() @ torch.cat([e, x[row], x[col]], 1).double()
+    out = torch.empty(128, 384, device=dev())
+    cs = torch.empty(128, device=dev())
+    ops.wgrad(ops.Seg(da_e.to(dev())), [ops.Seg(ed), ops.Seg(xd, _lib.SEG_GATHER, (i32(row),)),
+                                        ops.Seg(xd, _lib.SEG_GATHER, (i32(col),))], E, out, colsum=cs)
+    assert rel_l2(out, ref.float()) < GRAD_TOL, rel_l2(out, ref.float())
+    assert rel_l2(cs, da_e.double().sum(0).float()) < 1e-5
+    # node layer 1
+    agg = (vs[vf[0]] + vs[vf[1]] + vs[vf[2]]) / 3.0
+    ref = da_n.double().t() @ torch.cat([x, agg], 1).double()
+    out = torch.empty(128, 192, device=dev())
+    ops.wgrad(ops.Seg(da_n.to(dev())), [ops.Seg(xd), ops.Seg(vsd, _lib.SEG_MEAN3, tuple(i32(t) for t in vf))], N, out)
+    assert rel_l2(out, ref.float()) < GRAD_TOL, rel_l2(out, ref.float())
+    # encoder layer 1 (10 input columns) and decoder layer 3 (5 outputs, transposed store, colsum of B)
+    f = torch.randn(E, 10, generator=g)
+    out = torch.empty(128, 10, device=dev())
+    ops.wgrad(ops.Seg(da_e.to(dev())), [ops.Seg(f.to(dev()))], E, out)
+    assert rel_l2(out, (da_e.double().t() @ f.double()).float()) < GRAD_TOL
+    dy = torch.randn(E, 5, generator=g)
+    out = torch.empty(5, 128, device=dev())
+    cs = torch.empty(5, device=dev())
+    ops.wgrad(ops.Seg(ed), [ops.Seg(dy.to(dev()))], E, out, a_act=1, transpose_out=True, colsum=cs, colsum_of_b=True)
+    assert rel_l2(out, (dy.double().t() @ torch.nn.functional.silu(e.double())).float()) < GRAD_TOL
+    assert rel_l2(cs, dy.double().sum(0).float()) < 1e-5
+
+
+@pytest.mark.parametrize("rows", [1, 7, 4096, 33333])
+def test_ln_backward_vs_autograd(rows):
+    from gnn_fluid_dynamics_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    y = torch.randn(rows, 128, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (1 + 0.1 * torch.randn(128, generator=g, dtype=torch.float64)).requires_grad_()
+    b = torch.zeros(128, dtype=torch.float64, requires_grad=True)
+    go = torch.randn(rows, 128, generator=g, dtype=torch.float64)
+    out = torch.nn.functional.layer_norm(y, (128,), w, b, 1e-5)
+    out.backward(go)
+    mean, var = y.mean(1, keepdim=True), y.var(1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-5).rsqrt()
+    xhat = ((y - mean) * rstd).detach()
+    dy, sums = ops.ln_backward(go.float().to(dev()), xhat.float().to(dev()), rstd.detach().float().reshape(-1).to(dev()),
+                               w.detach().float().to(dev()))
+    assert rel_l2(dy, y.grad.float()) < 1e-5
+    assert rel_l2(sums[0], w.grad.float()) < 1e-5 and rel_l2(sums[1], b.grad.float()) < 1e-5
+    assert rel_l2(sums[2], y.grad.sum(0).float()) < 1e-4
+
+
+def test_linear_tc_dgrad_with_activation_derivative():
+    from gnn_fluid_dynamics_b200 import ops, _lib
+    g = torch.Generator().manual_seed(5)
+    R = 777
+    da, a_pre, res = torch.randn(R, 128, generator=g), torch.randn(R, 128, generator=g), torch.randn(R, 128, generator=g)
+    W = torch.randn(128, 384, generator=g) * 0.1          # forward weight [out=128, in=384]
+    ap = a_pre.double().requires_grad_()
+    torch.nn.functional.silu(ap).backward(torch.ones_like(ap))
+    Wd = W.to(dev())
+    packs = {}
+    # dIn segment 1 = dA . W[:, 128:256], accumulated onto a residual
+    out = ops.linear_tc(ops.Seg(da.to(dev())), R, Wd[:, 128:], 1, 384, 128, 128, packs, ("w1t", 128), _lib.PREC_BF16X3,
+                        residual=res.to(dev()))
+    assert rel_l2(out, (res.double() + da.double() @ W[:, 128:256].double()).float()) < 1e-4
+    # narrow block (64 valid output columns) with the activation derivative fused
+    out = ops.linear_tc(ops.Seg(da.to(dev())), R, Wd[:, 320:], 1, 384, 64, 128, packs, ("w1t", 320), _lib.PREC_BF16X3,
+                        mul=a_pre.to(dev()), mul_mode=1)
+    ref = (da.double() @ W[:, 320:384].double()) * ap.grad[:, :64]
+    assert rel_l2(out[:, :64], ref.float()) < 1e-4
+    assert float(out[:, 64:].abs().max()) == 0.0
+
+
+def test_transposed_gathers_vs_index_add():
+    from gnn_fluid_dynamics_b200 import ops
+    from gnn_fluid_dynamics_b200.mesh import make_mesh
+    m = make_mesh(3000, "cylinder", seed=4)
+    N, E, V = m.n_cells, m.n_faces, m.n_vertices
+    g = torch.Generator().manual_seed(2)
+    row, col = torch.from_numpy(m.cell_edge_index[0]), torch.from_numpy(m.cell_edge_index[1])
+    t1, t2, base = torch.randn(E, 128, generator=g), torch.randn(E, 128, generator=g), torch.randn(N, 128, generator=g)
+    off, perm = ops.csr_build(i32(torch.cat([row, col])), N)
+    out = ops.segment_sum3(t1.to(dev()), t2.to(dev()), None, (0, 0, 0), 128, 1.0, E, off, perm, N, base=base.to(dev()))
+    ref = base.double().index_add(0, row, t1.double()).index_add(0, col, t2.double())
+    assert rel_l2(out, ref.float()) < 1e-6
+    vf = [torch.from_numpy(m.cells[:, j].copy()).long() for j in range(3)] if hasattr(m, "cells") else None
+    if vf is None:
+        vf = [torch.randint(0, V, (N,), generator=g) for _ in range(3)]
+    t3 = torch.randn(N, 128, generator=g)
+    off, perm = ops.csr_build(i32(torch.cat(vf)), V)
+    out = ops.segment_sum3(t3.to(dev()), None, None, (0, 0, 0), 64, 1.0, N, off, perm, V, scale=1.0 / 3.0)
+    ref = torch.zeros(V, 64, dtype=torch.float64)
+    for j in range(3):
+        ref.index_add_(0, vf[j], t3[:, :64].double())
+    assert rel_l2(out, (ref / 3).float()) < 1e-6
+    v0, v1 = torch.from_numpy(m.vertex_edge_index[0]), torch.from_numpy(m.vertex_edge_index[1])
+    dv, de = torch.randn(V, 64, generator=g), torch.randn(E, 128, generator=g)
+    out = ops.gather_pair_add(dv.to(dev()), i32(v0), i32(v1), 1.0, True, E, base=de.to(dev()))
+    assert torch.equal(out.cpu(), de + torch.cat([dv[v0], dv[v1]], 1))
+    dn = torch.randn(N, 128, generator=g)
+    out = ops.gather_pair_add(dn.to(dev()), i32(col), i32(row), -1.0, False, E)
+    assert rel_l2(out, dn[col] - dn[row]) < 1e-6
+
+
+# ---------------------------------------------------------------------------------- whole training step
+def _oracle_step(name, model, graphs):
+    params = {k: v.detach().cpu().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    out, _ = omodel.model_forward(name, params, default_stats(), [g.clone() for g in graphs], 15, mode="train", training=True)
+    graphs_n = omodel.normalise_inputs(name, default_stats(), [g.clone() for g in graphs])
+    if name == "FvgnA":
+        loss = omodel.fvgn_loss(params, out, graphs_n, LOSS_W, training=True)["total_log_loss"]
+    else:
+        c = graphs_n[0]
+        mse = lambda a, b: torch.mean((a - b) ** 2)
+        total = LOSS_W["cell_velocity_change"] * mse(out["cell_velocity_change"], c.y[:, 0:2]) \
+            + LOSS_W["cell_pressure"] * mse(out["cell_pressure"], c.y[:, 2:3])
+        loss = torch.mean(torch.log(total))
+    loss.backward()
+    return float(loss), {k: p.grad for k, p in params.items() if p.grad is not None}
+
+
+@pytest.mark.parametrize("name,n_cells", [("FvgnA", 160), ("MgnA", 160), ("FvgnA", 3000)])
+def test_training_step_gradients_vs_oracle(name, n_cells):
+    model = build_model(name).train()
+    _, graphs = golden_graphs(name, flip=True, n_cells=n_cells)
+    ref_loss, ref_grads = _oracle_step(name, model, graphs)
+    model.to(dev())
+    out = model([g.clone().to(dev()) for g in graphs], mode="train")
+    gn = model.normalizer.input([g.clone().to(dev()) for g in graphs])
+    loss = model.loss(out, gn)["total_log_loss"]
+    loss.backward()
+    assert abs(float(loss) - ref_loss) < 1e-4 * max(1.0, abs(ref_loss)), (float(loss), ref_loss)
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        if k not in ref_grads:
+            continue
+        assert p.grad is not None, k
+        err = rel_l2(p.grad, ref_grads[k])
+        if err > worst[1]:
+            worst = (k, err)
+    assert worst[1] < GRAD_TOL, worst
+
+
+def test_training_step_matches_reference_golden():
+    """Loss values and gradients of the reference's own FvgnA training step (tests/golden/train_FvgnA.npz)."""
+    gold = load_golden("train_FvgnA.npz")
+    model = build_model("FvgnA").to(dev()).train()
+    _, graphs = golden_graphs("FvgnA", flip=True)
+    out = model([g.clone().to(dev()) for g in graphs], mode="train")
+    gn = model.normalizer.input([g.clone().to(dev()) for g in graphs])
+    losses = model.loss(out, gn)
+    for k, v in losses.items():
+        assert abs(float(v) - float(gold[f"loss_{k}"][0])) < 1e-4 * max(1.0, abs(float(gold[f"loss_{k}"][0]))), k
+    losses["total_log_loss"].backward()
+    grads = dict(model.named_parameters())
+    for n, ref_norm in zip([str(n) for n in gold["grad_names"]], gold["grad_norms"]):
+        if n in grads and grads[n].grad is not None:
+            assert abs(float(grads[n].grad.double().norm()) - ref_norm) <= 2e-3 * max(ref_norm, 1e-6) + 1e-9, n
+    for k in gold:
+        if k.startswith(("grad_processer", "grad_decoder", "grad_encoder")):
+            assert rel_l2(grads[k[5:]].grad, torch.from_numpy(gold[k])) < GRAD_TOL, k
+
+
+def test_training_gradients_are_bitwise_reproducible():
+    model = build_model("FvgnA").to(dev()).train()
+    _, graphs = golden_graphs("FvgnA", flip=True, n_cells=2000)
+    runs = []
+    for _ in range(2):
+        model.zero_grad(set_to_none=True)
+        out = model([g.clone().to(dev()) for g in graphs], mode="train")
+        gn = model.normalizer.input([g.clone().to(dev()) for g in graphs])
+        model.loss(out, gn)["total_log_loss"].backward()
+        runs.append([p.grad.clone() for p in model.parameters() if p.grad is not None])
+    assert all(torch.equal(a, b) for a, b in zip(*runs))
