@@ -32,7 +32,7 @@ WORKLOADS = {
     "mgn_fwd_2k": ("MgnA", 1, 2048, "none", False),
     "mgn_fwd_200k": ("MgnA", 1, 200000, "airfoil", False),
 }
-DEFAULT_WORKLOAD = "fvgn_fwd_8x20k"
+DEFAULT_WORKLOAD = "fvgn_train_8x20k"   # BASELINE.json configs[1]
 
 
 def peaks():
@@ -155,13 +155,17 @@ def run_reference(args, world, rank):
     E = graphs[0].edge_index.shape[1]
     stats = default_stats()
 
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-4) if train else None
+
     def step():
         g = [x.clone() for x in graphs]
         if train:
-            params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+            opt.zero_grad(set_to_none=True)
             out, _ = omodel.model_forward(model_name, params, stats, g, MP_NUM, mode="train", training=True)
             loss = omodel.fvgn_loss(params, out, g, LOSS_W, training=True)["total_log_loss"]
             loss.backward()
+            opt.step()
         else:
             with torch.no_grad():
                 omodel.model_forward(model_name, sd, stats, g, MP_NUM, mode="train")
@@ -173,7 +177,7 @@ def run_reference(args, world, rank):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     value = E * MP_NUM / dt
-    sample = f"1 of {n_meshes} meshes ({n_cells}-cell {kind}), whole forward{'+loss+backward' if train else ''} per step"
+    sample = f"1 of {n_meshes} meshes ({n_cells}-cell {kind}), whole forward{'+loss+backward+Adam step' if train else ''} per step"
     line = {
         "impl": "reference", "metric": "processor edge-updates/sec", "value": value, "unit": "edge-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -218,12 +222,12 @@ def main():
     from gnn_fluid_dynamics_b200.topology import get_topology
 
     model_name, n_meshes, n_cells, kind, train = WORKLOADS[args.workload]
-    if train:
-        raise SystemExit("training workload needs the backward kernels (not in this build)")
     from gnn_fluid_dynamics_b200.models.base import DEFAULT_PRECISION
     prec = args.precision or DEFAULT_PRECISION
     assert prec in available(), prec
-    model = build_model(model_name, precision=prec).to(dev).eval()
+    model = build_model(model_name, precision=prec).to(dev)
+    model.train() if train else model.eval()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4) if train else None      # reference src/train.py:83
     host_graphs = [g.pin_memory() for g in build_batch(model_name, n_meshes, n_cells, kind, seed0=rank * n_meshes)]
     N, E = host_graphs[0].x.shape[0], host_graphs[0].edge_index.shape[1]
     V = host_graphs[2].pos.shape[0]
@@ -231,10 +235,34 @@ def main():
     # ---- device-resident leg (`value`): inputs already normalised and in HBM ------------------------
     gd = model.normalizer.input([g.to(dev) for g in host_graphs])
     topo = get_topology(gd).validate()
+    if train:
+        topo.build_rowcol_csr(); topo.build_vf_csr()
+        gd[0].topology = gd[2].topology = topo
     working_set = 4 * 128 * (2 * E + 3 * N) + 4 * 64 * V
     flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev) if working_set < 256e6 else None
 
+    def train_step(graphs_norm):
+        """forward (encoder + 15 GN_Blocks + decoder, integrator) + loss + backward + clip + Adam step
+        (reference Trainer._train_step, src/train.py:245-272)."""
+        opt.zero_grad(set_to_none=True)
+        out = model.forward_normalised(graphs_norm, mode="train")
+        loss = model.loss(out, graphs_norm)["total_log_loss"]
+        loss.backward()
+        if world > 1:   # data-parallel: meshes are independent units, one gradient all-reduce per step
+            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+            dist.all_reduce(flat)
+            flat /= world
+            o = 0
+            for p in model.parameters():
+                if p.grad is not None:
+                    p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+
     def step_resident():
+        if train:
+            return train_step(gd)
         with torch.no_grad():
             return model.encode_process_decode(gd[0].x, gd[1].x, topo)
 
@@ -261,15 +289,33 @@ def main():
     ms = sum(s.elapsed_time(e) for s, e in ev) / args.steps
     clocks = sampler.stop()
 
-    # ---- end-to-end leg (`e2e`): host graphs -> model.forward -> host result ------------------------
-    def step_e2e():
+    # forward-only time of the same batch (reported next to the training number)
+    fwd_ms = None
+    if train:
+        model.eval()
         with torch.no_grad():
-            g = [x.to(dev, non_blocking=True) for x in host_graphs]
+            for _ in range(3):
+                model.encode_process_decode(gd[0].x, gd[1].x, topo)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                model.encode_process_decode(gd[0].x, gd[1].x, topo)
+            b.record()
+        torch.cuda.synchronize()
+        fwd_ms = a.elapsed_time(b) / 5
+        model.train()
+
+    # ---- end-to-end leg (`e2e`): host graphs -> public API -> host result ---------------------------
+    def step_e2e():
+        g = [x.to(dev, non_blocking=True) for x in host_graphs]
+        if train:
+            return float(train_step(model.normalizer.input(g)).item())      # D2H of the loss
+        with torch.no_grad():
             out = model(g, mode="train")
             return out["cell_velocity_change"].to("cpu", non_blocking=False)
 
     h2d = sum(t.numel() * t.element_size() for g in host_graphs for t in g._store.values() if torch.is_tensor(t))
-    d2h = N * 2 * 4
+    d2h = 4 if train else N * 2 * 4
     for _ in range(3):
         step_e2e()
     barrier()
@@ -280,6 +326,7 @@ def main():
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
 
     # ---- dominant kernel (fused edge block) timed alone with CUDA events on its stream -------------
+    model.eval()
     blk = model.processer_list[7]
     from gnn_fluid_dynamics_b200 import processor as P
     x_lat = torch.randn(N, 128, device=dev)
@@ -313,7 +360,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = time_cpu_baseline(model_name, n_meshes, n_cells, kind)
+        cpu_baseline = time_cpu_baseline(model_name, n_meshes, n_cells, kind, train)
 
     if rank == 0:
         line = {
@@ -324,11 +371,16 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "model": model_name, "mp_num": MP_NUM, "hidden": 128,
                        "meshes_per_gpu": n_meshes, "cells_per_mesh": n_cells, "cells": N, "faces": E,
-                       "vertices": V, "precision": prec, "timed": "encoder + 15 GN_Blocks + decoder",
+                       "vertices": V, "precision": prec,
+                       "timed": ("forward (encoder + 15 GN_Blocks + decoder + integrator) + loss + backward + grad clip + Adam step"
+                                 if train else "encoder + 15 GN_Blocks + decoder"),
+                       "forward_only_ms": fwd_ms,
+                       "backward_precision": "dgrad bf16x3, wgrad tf32 (rna operands), fp32 accumulate" if train else None,
                        "l2": "flushed between iterations" if flush is not None else "working set > L2"},
             "e2e": {"value": E_total * MP_NUM / (ms_e2e * 1e-3), "unit": "edge-updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                    "api": "model.forward(graphs, mode='train') from pinned host graphs"},
+                    "api": ("model.forward + model.loss + backward + Adam step from pinned host graphs, loss read back"
+                            if train else "model.forward(graphs, mode='train') from pinned host graphs")},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "fused edge block (gather + 3-layer MLP + LayerNorm + residual)",
@@ -343,27 +395,37 @@ def main():
         dist.destroy_process_group()
 
 
-def time_cpu_baseline(model_name, n_meshes, n_cells, kind):
+def time_cpu_baseline(model_name, n_meshes, n_cells, kind, train=False):
     """Oracle port of the reference's CPU path on this box's host cores, bounded sample (1 mesh)."""
     import oracle  # noqa: F401
     from oracle import model as omodel
-    from helpers import build_model
+    from helpers import LOSS_W, build_model
     from gnn_fluid_dynamics_b200.testing import default_stats
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     graphs = build_batch(model_name, 1, n_cells, kind)
     sd = {k: v.clone() for k, v in build_model(model_name).state_dict().items()}
     E = graphs[0].edge_index.shape[1]
+    params = {k: v.clone().requires_grad_(train and v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-4) if train else None
     best = None
-    with torch.no_grad():
-        for i in range(4):
-            t0 = time.perf_counter()
-            omodel.model_forward(model_name, sd, default_stats(), [g.clone() for g in graphs], MP_NUM, mode="train")
-            dt = time.perf_counter() - t0
-            if i > 0:
-                best = dt if best is None else min(best, dt)
+    for i in range(4):
+        t0 = time.perf_counter()
+        g = [x.clone() for x in graphs]
+        if train:
+            opt.zero_grad(set_to_none=True)
+            out, _ = omodel.model_forward(model_name, params, default_stats(), g, MP_NUM, mode="train", training=True)
+            omodel.fvgn_loss(params, out, g, LOSS_W, training=True)["total_log_loss"].backward()
+            opt.step()
+        else:
+            with torch.no_grad():
+                omodel.model_forward(model_name, sd, default_stats(), g, MP_NUM, mode="train")
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = dt if best is None else min(best, dt)
+    what = "forward + loss + backward + Adam step" if train else "whole forward"
     return {"value": E * MP_NUM / best, "unit": "edge-updates/s", "cores": cores, "kind": "port",
-            "sample": f"1 of {n_meshes} meshes ({n_cells}-cell {kind}), whole forward, best of 3 after 1 warm-up"}
+            "sample": f"1 of {n_meshes} meshes ({n_cells}-cell {kind}), {what}, best of 3 after 1 warm-up"}
 
 
 if __name__ == "__main__":

@@ -24,6 +24,8 @@ EXPORTS = [
     "gnnfd_pack_mlp", "gnnfd_tc_profile_read",
     "gnnfd_ln_backward_workspace_bytes", "gnnfd_ln_backward", "gnnfd_wgrad_workspace_bytes", "gnnfd_wgrad",
     "gnnfd_segment_sum3", "gnnfd_gather_pair_add", "gnnfd_struct_size",
+    "gnnfd_mlp_backward_workspace_bytes", "gnnfd_pack_mlp_backward_bytes", "gnnfd_pack_mlp_backward",
+    "gnnfd_mlp_backward",
 ]
 ABI_VERSION = 2
 
@@ -45,6 +47,9 @@ class MlpArgs(C.Structure):
         ("n_layers", C.c_int32), ("mul_mode", C.c_int32),
         ("save_a1", C.c_void_p), ("save_a2", C.c_void_p), ("save_rstd", C.c_void_p), ("save_xhat", C.c_void_p),
         ("w1_ld_n", C.c_int32), ("w1_ld_k", C.c_int32), ("w1_rows", C.c_int32),
+        ("bwd_chain", C.c_int32), ("hid_mul1", C.c_void_p), ("hid_mul2", C.c_void_p),
+        ("w2_ld_n", C.c_int32), ("w2_ld_k", C.c_int32), ("w3_ld_n", C.c_int32), ("w3_ld_k", C.c_int32),
+        ("w3_rows", C.c_int32),
     ]
 
 
@@ -53,6 +58,18 @@ class WgradArgs(C.Structure):
         ("rows", C.c_int64), ("a", Segment), ("a_act", C.c_int32), ("n_b", C.c_int32), ("b", Segment * 3),
         ("b_act", C.c_int32), ("out", C.c_void_p), ("ld_out", C.c_int32), ("transpose_out", C.c_int32),
         ("colsum", C.c_void_p), ("colsum_of_b", C.c_int32),
+    ]
+
+
+class MlpBackwardArgs(C.Structure):
+    _fields_ = [
+        ("fwd", MlpArgs), ("g", C.c_void_p),
+        ("a1", C.c_void_p), ("a2", C.c_void_p), ("xhat", C.c_void_p), ("rstd", C.c_void_p),
+        ("packed_bwd", C.c_void_p),
+        ("d_w1", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2", C.c_void_p), ("d_b2", C.c_void_p),
+        ("d_w3", C.c_void_p), ("d_b3", C.c_void_p), ("d_ln_w", C.c_void_p), ("d_ln_b", C.c_void_p),
+        ("din_out", C.c_void_p * 3), ("din_residual", C.c_void_p * 3),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -90,7 +107,13 @@ def _load():
     lib.gnnfd_gather_pair_add.argtypes = [vp, vp, vp, i32, vp, vp, f32, i32, i64, vp]
     lib.gnnfd_struct_size.argtypes = [i32]
     lib.gnnfd_struct_size.restype = C.c_size_t
-    for which, mirror in ((0, MlpArgs), (1, WgradArgs), (2, Segment)):
+    lib.gnnfd_mlp_backward_workspace_bytes.argtypes = [C.POINTER(MlpArgs)]
+    lib.gnnfd_mlp_backward_workspace_bytes.restype = C.c_size_t
+    lib.gnnfd_pack_mlp_backward_bytes.argtypes = [C.POINTER(MlpArgs)]
+    lib.gnnfd_pack_mlp_backward_bytes.restype = C.c_size_t
+    lib.gnnfd_pack_mlp_backward.argtypes = [C.POINTER(MlpArgs), vp, vp]
+    lib.gnnfd_mlp_backward.argtypes = [C.POINTER(MlpBackwardArgs), vp]
+    for which, mirror in ((0, MlpArgs), (1, WgradArgs), (2, Segment), (3, MlpBackwardArgs)):
         if lib.gnnfd_struct_size(which) != C.sizeof(mirror):
             raise ImportError(f"{LIB_PATH}: struct {mirror.__name__} is {lib.gnnfd_struct_size(which)} bytes in the "
                               f"library but {C.sizeof(mirror)} in the binding; rebuild")

@@ -63,8 +63,21 @@ __global__ void sum_partials_kernel(const float *__restrict__ partial, int n_par
 
 static int lnb_grid(int64_t rows) {
   const int64_t want = (rows + LNB_WARPS * 8 - 1) / (LNB_WARPS * 8);   // >= 8 rows per warp
-  const int64_t cap = (int64_t)num_sms() * 8;
+  const int64_t cap = (int64_t)num_sms() * 2;                          // few partials: the ordered sum stays short
   return (int)(want < 1 ? 1 : want > cap ? cap : want);
+}
+
+size_t ln_backward_ws(int64_t rows) { return (size_t)lnb_grid(rows) * 384 * 4 + 256; }
+
+int ln_backward_launch(const float *g, const float *xhat, const float *rstd, const float *ln_w, int64_t rows,
+                       float *dy, float *sums, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const int grid = lnb_grid(rows);
+  if (workspace == nullptr || workspace_bytes < (size_t)grid * 384 * 4) { set_error("ln_backward: workspace too small"); return GNNFD_E_WORKSPACE; }
+  ln_backward_kernel<<<grid, LNB_THREADS, 0, stream>>>(g, xhat, rstd, ln_w, rows, dy, (float *)workspace);
+  GNNFD_LAUNCH_CHECK();
+  sum_partials_kernel<<<12, 32, 0, stream>>>((const float *)workspace, grid, 384, sums);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
 }
 
 // Three-part segment sum with scale and base:  out[r] = base[r] + scale * sum_{p in row r} part(p)
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(256) gather_pair_add_kernel(float *dst, const 
 
 using namespace gnnfd;
 
-extern "C" size_t gnnfd_ln_backward_workspace_bytes(int64_t rows) { return (size_t)lnb_grid(rows) * 384 * 4 + 256; }
+extern "C" size_t gnnfd_ln_backward_workspace_bytes(int64_t rows) { return ln_backward_ws(rows); }
 
 extern "C" int gnnfd_ln_backward(const float *g, const float *xhat, const float *rstd, const float *ln_w,
                                  int64_t rows, float *dy, float *sums, void *workspace, size_t workspace_bytes,
@@ -149,13 +162,7 @@ extern "C" int gnnfd_ln_backward(const float *g, const float *xhat, const float 
   GNNFD_CHECK_ARG(sums != nullptr, "null sums");
   if (rows == 0) { GNNFD_CUDA(cudaMemsetAsync(sums, 0, 384 * 4, stream)); return GNNFD_OK; }
   GNNFD_CHECK_ARG(g && xhat && rstd && dy, "null pointer");
-  const int grid = lnb_grid(rows);
-  if (workspace == nullptr || workspace_bytes < (size_t)grid * 384 * 4) { set_error("gnnfd_ln_backward: workspace too small"); return GNNFD_E_WORKSPACE; }
-  ln_backward_kernel<<<grid, LNB_THREADS, 0, stream>>>(g, xhat, rstd, ln_w, rows, dy, (float *)workspace);
-  GNNFD_LAUNCH_CHECK();
-  sum_partials_kernel<<<3, 128, 0, stream>>>((const float *)workspace, grid, 384, sums);
-  GNNFD_LAUNCH_CHECK();
-  return GNNFD_OK;
+  return ln_backward_launch(g, xhat, rstd, ln_w, rows, dy, sums, workspace, workspace_bytes, stream);
 }
 
 extern "C" int gnnfd_segment_sum3(const float *a, const float *b, const float *c, int32_t ld, int32_t col_a,

@@ -38,6 +38,11 @@ int validate_mlp_args(const gnnfd_mlp_args *a) {
     GNNFD_CHECK_ARG(a->w1 && a->w2 && a->w3, "null weight");
   }
   GNNFD_CHECK_ARG(a->mul_mode >= 0 && a->mul_mode <= 2, "bad mul_mode");
+  if (a->bwd_chain) {
+    GNNFD_CHECK_ARG(a->n_layers != 1 && a->n_out == 128 && !a->has_ln && a->precision != GNNFD_PREC_F32,
+                    "bwd_chain needs the 3-layer tensor-core path, n_out == 128 and no LayerNorm");
+    GNNFD_CHECK_ARG(a->hid_mul1 && a->hid_mul2, "bwd_chain needs hid_mul1/hid_mul2");
+  }
   if (a->precision == GNNFD_PREC_F32)
     GNNFD_CHECK_ARG(!a->save_a1 && !a->save_a2 && !a->save_rstd && !a->save_xhat && a->mul_mode == 0,
                     "training stashes need a tensor-core precision");
@@ -91,6 +96,7 @@ extern "C" size_t gnnfd_struct_size(int32_t which) {
     case 0: return sizeof(gnnfd_mlp_args);
     case 1: return sizeof(gnnfd_wgrad_args);
     case 2: return sizeof(gnnfd_segment);
+    case 3: return sizeof(gnnfd_mlp_backward_args);
     default: return 0;
   }
 }

@@ -200,7 +200,7 @@ __device__ __forceinline__ void tc_store_block(uint8_t *sA, const float4 (&v)[8]
 }
 
 // -------------------------------------------------------------------------------------- kernel
-template <bool FP16, int NA, int NW>
+template <bool FP16, int NA, int NW, bool BWD>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const gnnfd_mlp_args &a = p.a;
@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
     const int v = i / TC_H, c = i % TC_H;
     const float *src = v == 0 ? a.b1 : v == 1 ? a.b2 : v == 2 ? (p.nl == 1 ? a.b1 : a.b3) : v == 3 ? a.ln_w : a.ln_b;
+    if (BWD && v < 3) src = nullptr;
     const int n = (v == 2 || v >= 3) ? a.n_out : TC_H;
     s_vec[i] = (src && c < n) ? __ldg(src + c) : (v == 3 ? 1.f : 0.f);
   }
@@ -267,6 +268,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         if (pt == 0 && p.direct_tile_bytes > 0) {   // pull the tile's contiguous DIRECT rows into L2 early
           const int64_t nrow = min((int64_t)TC_BM, a.rows - row0);
           bulk_prefetch_l2(a.seg[0].src + row0 * a.seg[0].ld, (uint32_t)(nrow * a.seg[0].ld * 4));
+        }
+        if (BWD && pt == 32) {   // saved pre-activations read by the hidden epilogues (thread = row)
+          const int64_t nrow = min((int64_t)TC_BM, a.rows - row0);
+          bulk_prefetch_l2(a.hid_mul1 + row0 * TC_H, (uint32_t)(nrow * TC_H * 4));
+          bulk_prefetch_l2(a.hid_mul2 + row0 * TC_H, (uint32_t)(nrow * TC_H * 4));
         }
       }
       cp_async_commit();
@@ -469,12 +475,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       const uint32_t xr = tmem_base + sl * 256 + ((uint32_t)(q4 * 32) << 16) + eh * 64, yr = xr + 128;
       // ---- hidden layers: accumulator -> +bias, act -> hi/lo pairs, written back in place
       for (int layer = 0; layer < p.nl - 1; ++layer) {
-        PROF_WAIT(0, mbar_wait(&acc_full[sl], (3 * n + layer) & 1));
-        tc_fence_after();
         const uint32_t reg = layer == 0 ? xr : yr;
         const uint32_t bias = vec + (layer * TC_H + eh * 64) * 4;
         float *save = layer == 0 ? a.save_a1 : a.save_a2;
         if (save != nullptr) save = (row0 + erow < a.rows) ? save + (size_t)(row0 + erow) * TC_H + eh * 64 : nullptr;
+        // backward chain: the saved pre-activation of this layer (rows past the end read row 0; never stored),
+        // fetched one 16-column group ahead of its use
+        const float *hm = nullptr;
+        float4 m4[2][4];
+        if (BWD) {
+          hm = (layer == 0 ? a.hid_mul1 : a.hid_mul2) + (size_t)((row0 + erow < a.rows) ? row0 + erow : 0) * TC_H + eh * 64;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) m4[0][i] = ldg_f4(hm + i * 4);
+        }
+        PROF_WAIT(0, mbar_wait(&acc_full[sl], (3 * n + layer) & 1));
+        tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           float acc[32];
@@ -483,18 +498,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float v[16];
+            if (BWD) {
+              if (h == 0 || c == 0) {   // next group: (c, 1) after (c, 0); (1, 0) after (0, 1)
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = lds_f4(bias + (c * 32 + h * 16 + i) * 4);
-              v[i] = acc[h * 16 + i] + b4.x; v[i + 1] = acc[h * 16 + i + 1] + b4.y;
-              v[i + 2] = acc[h * 16 + i + 2] + b4.z; v[i + 3] = acc[h * 16 + i + 3] + b4.w;
+                for (int i = 0; i < 4; ++i) m4[(h + 1) & 1][i] = ldg_f4(hm + (h == 0 ? c * 32 + 16 : 32) + i * 4);
+              }
+              const bool silu = a.act == GNNFD_ACT_SILU;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float4 m = m4[h & 1][i];
+                v[4 * i] = acc[h * 16 + 4 * i] * (silu ? dsilu(m.x) : dtanh(m.x));
+                v[4 * i + 1] = acc[h * 16 + 4 * i + 1] * (silu ? dsilu(m.y) : dtanh(m.y));
+                v[4 * i + 2] = acc[h * 16 + 4 * i + 2] * (silu ? dsilu(m.z) : dtanh(m.z));
+                v[4 * i + 3] = acc[h * 16 + 4 * i + 3] * (silu ? dsilu(m.w) : dtanh(m.w));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = lds_f4(bias + (c * 32 + h * 16 + i) * 4);
+                v[i] = acc[h * 16 + i] + b4.x; v[i + 1] = acc[h * 16 + i + 1] + b4.y;
+                v[i + 2] = acc[h * 16 + i + 2] + b4.z; v[i + 3] = acc[h * 16 + i + 3] + b4.w;
+              }
             }
-            if (save != nullptr) {   // training: stash the pre-activation (thread = row, 64 B per store group)
+            if (save != nullptr) {   // training: stash the pre-activation / dA (thread = row, 64 B per store group)
 #pragma unroll
               for (int i = 0; i < 16; i += 4)
                 *reinterpret_cast<float4 *>(save + c * 32 + h * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
             }
-            if (a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
+            if (BWD) { /* linear chain: no activation */ }
+            else if (a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) split2<FP16>(v[2 * i], v[2 * i + 1], hi[h * 8 + i], lo[h * 8 + i]);
           }
@@ -720,15 +752,18 @@ int pack_mlp_tc(const gnnfd_mlp_args *a, void *packed_out, cudaStream_t stream) 
   uint8_t *out = (uint8_t *)packed_out;
   uint8_t *o2 = out + (size_t)p.kb1 * p.w_block_bytes;
   uint8_t *o3 = o2 + (size_t)2 * p.w_block_bytes;
-  const bool strided = p.nl == 1 && (a->w1_ld_n != 0 || a->w1_ld_k != 0);
+  const bool strided = (p.nl == 1 || a->bwd_chain) && (a->w1_ld_n != 0 || a->w1_ld_k != 0);
   const int ld_n1 = strided ? a->w1_ld_n : a->k_in, ld_k1 = strided ? a->w1_ld_k : 1;
-  const int rows1 = (p.nl == 1 && a->w1_rows > 0) ? a->w1_rows : TC_H;
+  const int rows1 = ((p.nl == 1 || a->bwd_chain) && a->w1_rows > 0) ? a->w1_rows : TC_H;
+  const int ld_n2 = a->bwd_chain ? a->w2_ld_n : TC_H, ld_k2 = a->bwd_chain ? a->w2_ld_k : 1;
+  const int ld_n3 = a->bwd_chain ? a->w3_ld_n : TC_H, ld_k3 = a->bwd_chain ? a->w3_ld_k : 1;
+  const int rows3 = (a->bwd_chain && a->w3_rows > 0) ? a->w3_rows : a->n_out;
 #define PACK(FP)                                                                                              \
   do {                                                                                                        \
     pack_weights_kernel<FP><<<64, 256, 0, stream>>>(a->w1, ld_n1, ld_k1, rows1, a->k_in, TC_H, p.kb1, m.nw, out, p.w_block_bytes); \
     if (p.nl == 3) {                                                                                          \
-      pack_weights_kernel<FP><<<32, 256, 0, stream>>>(a->w2, TC_H, 1, TC_H, TC_H, TC_H, 2, m.nw, o2, p.w_block_bytes); \
-      pack_weights_kernel<FP><<<32, 256, 0, stream>>>(a->w3, TC_H, 1, a->n_out, TC_H, p.n3, 2, m.nw, o3, p.w3_block_bytes); \
+      pack_weights_kernel<FP><<<32, 256, 0, stream>>>(a->w2, ld_n2, ld_k2, TC_H, TC_H, TC_H, 2, m.nw, o2, p.w_block_bytes); \
+      pack_weights_kernel<FP><<<32, 256, 0, stream>>>(a->w3, ld_n3, ld_k3, rows3, TC_H, p.n3, 2, m.nw, o3, p.w3_block_bytes); \
     }                                                                                                         \
   } while (0)
   if (m.fp16) PACK(true); else PACK(false);
@@ -774,20 +809,25 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   if (a->rows == 0) return GNNFD_OK;
   const int64_t n_tiles = (a->rows + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-#define LAUNCH(FP, NA_, NW_)                                                                              \
+#define LAUNCH1(FP, NA_, NW_, BW)                                                                         \
   do {                                                                                                    \
     static bool attr = false;                                                                             \
     if (!attr) {                                                                                          \
-      GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); \
+      GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); \
       attr = true;                                                                                        \
     }                                                                                                     \
-    mlp_tc_kernel<FP, NA_, NW_><<<grid, TC_THREADS, TC_SMEM, stream>>>(p);                                \
+    mlp_tc_kernel<FP, NA_, NW_, BW><<<grid, TC_THREADS, TC_SMEM, stream>>>(p);                            \
+  } while (0)
+#define LAUNCH(FP, NA_, NW_)                                                                              \
+  do {                                                                                                    \
+    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true); else LAUNCH1(FP, NA_, NW_, false);                     \
   } while (0)
   if (!m.fp16 && m.na == 2 && m.nw == 2) LAUNCH(false, 2, 2);
   else if (!m.fp16 && m.na == 1) LAUNCH(false, 1, 1);
   else if (m.fp16 && m.nw == 1) LAUNCH(true, 2, 1);
   else LAUNCH(true, 2, 2);
 #undef LAUNCH
+#undef LAUNCH1
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

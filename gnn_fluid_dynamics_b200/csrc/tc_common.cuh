@@ -194,8 +194,8 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 }
 // derivatives of the activations at a saved pre-activation x (backward: dA = dH * act'(A))
 __device__ __forceinline__ float dsilu(float x) {
-  const float sg = 1.0f / (1.0f + __expf(-x));
-  return sg * (1.0f + x * (1.0f - sg));
+  const float sg = rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f));   // same fast sigmoid as the forward's SiLU
+  return sg * fmaf(x, 1.0f - sg, 1.0f);
 }
 __device__ __forceinline__ float dtanh(float x) {
   const float t = tanhf(x);

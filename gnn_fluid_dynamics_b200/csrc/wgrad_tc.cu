@@ -21,8 +21,8 @@
 
 namespace gnnfd {
 
-constexpr int WG_KR = 32;          // rows per stage = 4 K atoms
-constexpr int WG_PROD_WARPS = 8;
+constexpr int WG_KR = 32;          // rows per stage = 8 K atoms
+constexpr int WG_PROD_WARPS = 16;  // warp w owns stage rows {w, w + 16}
 constexpr int WG_THREADS = (WG_PROD_WARPS + 1) * 32;   // + MMA issuer warp
 constexpr int WG_MAX_STAGES = 6;
 constexpr int WG_MAX_SLOTS = 8;    // gather-index slots prefetched one stage ahead
@@ -77,10 +77,49 @@ __device__ __forceinline__ float to_tf32(float x) {   // round to nearest (the t
 }
 __device__ __forceinline__ float wg_act(float v, int act) {
   if (act == 1) return v * rcp_ftz(1.0f + ex2_ftz(v * -1.4426950408889634f));
-  if (act == 2) return tanhf(v);
-  return v;
+  return tanhf(v);
 }
 
+// one (row, piece) item: the lane's float4 of the assembled operand row (zero outside the matrix / the width)
+__device__ __forceinline__ float4 wg_load_item(const WgPiece &pc, int lane, bool row_ok, int64_t g, int32_t i0,
+                                               int32_t i1, int32_t i2) {
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!row_ok || lane * 4 >= pc.width) return t;
+  const int64_t r0 = pc.mode == GNNFD_SEG_DIRECT ? g : (int64_t)i0;
+  if (pc.vec) {
+    const float *b = pc.src + pc.col + lane * 4;
+    t = ldg_f4(b + r0 * pc.ld);
+    if (pc.mode >= GNNFD_SEG_SUM2) {
+      const float4 y = ldg_f4(b + (int64_t)i1 * pc.ld);
+      if (pc.mode == GNNFD_SEG_DIFF2) { t.x -= y.x; t.y -= y.y; t.z -= y.z; t.w -= y.w; }
+      else { t.x += y.x; t.y += y.y; t.z += y.z; t.w += y.w; }
+      if (pc.mode == GNNFD_SEG_MEAN3) {
+        const float4 z = ldg_f4(b + (int64_t)i2 * pc.ld);
+        constexpr float third = 1.0f / 3.0f;
+        t.x = (t.x + z.x) * third; t.y = (t.y + z.y) * third; t.z = (t.z + z.z) * third; t.w = (t.w + z.w) * third;
+      }
+    }
+  } else {   // narrow / unaligned sources (encoder inputs, decoder heads)
+    float e4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int c = lane * 4 + q;
+      if (c < pc.width) {
+        float t0 = __ldg(pc.src + r0 * pc.ld + pc.col + c);
+        if (pc.mode >= GNNFD_SEG_SUM2) {
+          const float y = __ldg(pc.src + (int64_t)i1 * pc.ld + pc.col + c);
+          t0 = pc.mode == GNNFD_SEG_DIFF2 ? t0 - y : t0 + y;
+          if (pc.mode == GNNFD_SEG_MEAN3) t0 = (t0 + __ldg(pc.src + (int64_t)i2 * pc.ld + pc.col + c)) * (1.0f / 3.0f);
+        }
+        e4[q] = t0;
+      }
+    }
+    t = make_float4(e4[0], e4[1], e4[2], e4[3]);
+  }
+  return t;
+}
+
+template <int NP>   // pieces: A + (NP - 1) column blocks of B
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -89,7 +128,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t b_bytes = 8 * (uint32_t)nb_atoms * 512;        // [8 k-atoms][nb mn-atoms]
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t *s_tail = smem + (size_t)p.stages * stage_bytes;
-  float *s_cs = (float *)s_tail;                                // [8 warps][128] column-sum scratch
+  float *s_cs = (float *)s_tail;                                // [16 warps][128] column-sum scratch
   uint64_t *s_bar = (uint64_t *)(s_tail + WG_PROD_WARPS * 128 * 4);
   uint64_t *full = s_bar, *empty = s_bar + WG_MAX_STAGES, *done = s_bar + 2 * WG_MAX_STAGES;
   uint32_t *s_tmem = (uint32_t *)(s_bar + 2 * WG_MAX_STAGES + 1);
@@ -112,101 +151,73 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 
   if (warp < WG_PROD_WARPS) {
     // =============================================================================== producers
-    // warp w owns rows {w, w + 8, w + 16, w + 24} of every stage; lane l owns float4 column l of each piece
+    // warp w owns rows {w, w + 16} of every stage; lane l owns float4 column l of each piece
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    // gather indices of the NEXT stage, one per lane: lane = slot * 4 + row slot
+    // gather indices of a stage, one per lane: lane = slot * 2 + row slot (fetched one stage before use)
     auto load_idx = [&](int it) -> int32_t {
-      const int j = lane & 3, q = lane >> 2;
-      const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 8 * j;
+      const int j = lane & 1, q = lane >> 1;
+      const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 16 * j;
       return (q < p.n_slots && it < n_stage_iters && g < r_end) ? __ldg(p.slot[q] + g) : 0;
     };
-    int32_t idx_cur = load_idx(0);
-    for (int it = 0; it < n_stage_iters; ++it) {
-      const int st = it % p.stages;
-      uint8_t *sA = smem + (size_t)st * stage_bytes, *sB = sA + a_bytes;
-      float4 v[4][4];   // [piece][row slot]
+    auto load_stage = [&](int it, int32_t idx, float4(&v)[NP][2]) {
 #pragma unroll
-      for (int pi = 0; pi < 4; ++pi) {
-        if (pi < p.n_pieces) {
-          const WgPiece &pc = p.pc[pi];
-          const int wpad = (pc.width + 31) & ~31;
+      for (int pi = 0; pi < NP; ++pi) {
+        const WgPiece &pc = p.pc[pi];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 8 * j;
-            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int32_t i0 = __shfl_sync(0xffffffffu, idx_cur, (pc.slot0 & 7) * 4 + j);
-            const int32_t i1 = __shfl_sync(0xffffffffu, idx_cur, ((pc.slot0 + 1) & 7) * 4 + j);
-            const int32_t i2 = __shfl_sync(0xffffffffu, idx_cur, ((pc.slot0 + 2) & 7) * 4 + j);
-            if (g < r_end && lane * 4 < wpad) {
-              const int64_t rr0 = pc.mode == GNNFD_SEG_DIRECT ? g : (int64_t)i0;
-              if (pc.vec) {
-                if (lane * 4 < pc.width) {
-                  const float *b = pc.src + pc.col + lane * 4;
-                  t = ldg_f4(b + rr0 * pc.ld);
-                  if (pc.mode >= GNNFD_SEG_SUM2) {
-                    const float4 y = ldg_f4(b + (int64_t)i1 * pc.ld);
-                    if (pc.mode == GNNFD_SEG_DIFF2) { t.x -= y.x; t.y -= y.y; t.z -= y.z; t.w -= y.w; }
-                    else { t.x += y.x; t.y += y.y; t.z += y.z; t.w += y.w; }
-                    if (pc.mode == GNNFD_SEG_MEAN3) {
-                      const float4 z = ldg_f4(b + (int64_t)i2 * pc.ld);
-                      constexpr float third = 1.0f / 3.0f;
-                      t.x = (t.x + z.x) * third; t.y = (t.y + z.y) * third;
-                      t.z = (t.z + z.z) * third; t.w = (t.w + z.w) * third;
-                    }
-                  }
-                }
-              } else {
-                float e4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int c = lane * 4 + q;
-                  if (c < pc.width) {
-                    float t0 = __ldg(pc.src + rr0 * pc.ld + pc.col + c);
-                    if (pc.mode >= GNNFD_SEG_SUM2) {
-                      const float y = __ldg(pc.src + (int64_t)i1 * pc.ld + pc.col + c);
-                      t0 = pc.mode == GNNFD_SEG_DIFF2 ? t0 - y : t0 + y;
-                      if (pc.mode == GNNFD_SEG_MEAN3)
-                        t0 = (t0 + __ldg(pc.src + (int64_t)i2 * pc.ld + pc.col + c)) * (1.0f / 3.0f);
-                    }
-                    e4[q] = t0;
-                  }
-                }
-                t = make_float4(e4[0], e4[1], e4[2], e4[3]);
-              }
-            }
-            v[pi][j] = t;
+        for (int j = 0; j < 2; ++j) {
+          const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 16 * j;
+          int32_t i0 = 0, i1 = 0, i2 = 0;
+          if (pc.mode != GNNFD_SEG_DIRECT) {     // uniform per piece
+            i0 = __shfl_sync(0xffffffffu, idx, (pc.slot0 & 15) * 2 + j);
+            if (pc.mode >= GNNFD_SEG_SUM2) i1 = __shfl_sync(0xffffffffu, idx, ((pc.slot0 + 1) & 15) * 2 + j);
+            if (pc.mode == GNNFD_SEG_MEAN3) i2 = __shfl_sync(0xffffffffu, idx, ((pc.slot0 + 2) & 15) * 2 + j);
           }
+          v[pi][j] = wg_load_item(pc, lane, it < n_stage_iters && g < r_end, g, i0, i1, i2);
         }
       }
-      const int32_t idx_next = load_idx(it + 1);
+    };
+    // activation / tf32 rounding / swizzled store of stage `it`, then hand the stage to the MMA issuer
+    auto store_stage = [&](int it, const float4(&v)[NP][2]) {
+      const int st = it % p.stages;
+      uint8_t *sA = smem + (size_t)st * stage_bytes, *sB = sA + a_bytes;
       if (it >= p.stages) mbar_wait(&empty[st], ((it / p.stages) - 1) & 1);
 #pragma unroll
-      for (int pi = 0; pi < 4; ++pi) {
-        if (pi < p.n_pieces) {
-          const WgPiece &pc = p.pc[pi];
-          const int wpad = (pc.width + 31) & ~31;
-          if (lane * 4 < wpad) {
-            uint8_t *img = pi == 0 ? sA : sB;
-            const int natoms = pi == 0 ? 4 : nb_atoms;
+      for (int pi = 0; pi < NP; ++pi) {
+        const WgPiece &pc = p.pc[pi];
+        const int wpad = (pc.width + 31) & ~31;
+        if (lane * 4 < wpad) {
+          uint8_t *img = pi == 0 ? sA : sB;
+          const int natoms = pi == 0 ? 4 : nb_atoms;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 t = v[pi][j];
-              if (pi == p.colsum_piece) { cs.x += t.x; cs.y += t.y; cs.z += t.z; cs.w += t.w; }
-              if (pc.act) { t.x = wg_act(t.x, pc.act); t.y = wg_act(t.y, pc.act); t.z = wg_act(t.z, pc.act); t.w = wg_act(t.w, pc.act); }
-              t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
-              // stage row r = warp + 8 j: r & 3 == warp & 3, r >> 2 == 2 j + (warp >> 2)
-              const uint32_t off = (uint32_t)(((2 * j + (warp >> 2)) * natoms + pc.atom0 + (lane >> 3)) * 512 +
-                                              (warp & 3) * 128 + (((((lane & 7) >> 1) ^ (warp & 3))) << 5) +
-                                              ((lane & 1) << 4));
-              *reinterpret_cast<float4 *>(img + off) = t;
-            }
+          for (int j = 0; j < 2; ++j) {
+            float4 t = v[pi][j];
+            if (pi == p.colsum_piece) { cs.x += t.x; cs.y += t.y; cs.z += t.z; cs.w += t.w; }
+            if (pc.act) { t.x = wg_act(t.x, pc.act); t.y = wg_act(t.y, pc.act); t.z = wg_act(t.z, pc.act); t.w = wg_act(t.w, pc.act); }
+            t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
+            // stage row r = warp + 16 j: r & 3 == warp & 3, r >> 2 == (warp >> 2) + 4 j
+            const uint32_t off = (uint32_t)((((warp >> 2) + 4 * j) * natoms + pc.atom0 + (lane >> 3)) * 512 +
+                                            (warp & 3) * 128 + (((((lane & 7) >> 1) ^ (warp & 3))) << 5) +
+                                            ((lane & 1) << 4));
+            *reinterpret_cast<float4 *>(img + off) = t;
           }
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[st]);
-      idx_cur = idx_next;
+    };
+    // two stages of loads in flight per warp: the loads of stage it + 1 are issued before stage it is converted
+    float4 v0[NP][2], v1[NP][2];
+    int32_t ix1 = load_idx(1);
+    load_stage(0, load_idx(0), v0);
+    for (int it = 0; it < n_stage_iters; it += 2) {
+      const int32_t ix2 = load_idx(it + 2);
+      load_stage(it + 1, ix1, v1);
+      store_stage(it, v0);
+      const int32_t ix3 = load_idx(it + 3);
+      load_stage(it + 2, ix2, v0);
+      if (it + 1 < n_stage_iters) store_stage(it + 1, v1);
+      ix1 = ix3;
     }
     if (p.colsum != nullptr) {   // column sums: warps reduced in fixed order
       *reinterpret_cast<float4 *>(s_cs + warp * 128 + lane * 4) = cs;
@@ -367,12 +378,17 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
   int stages = (int)((200u * 1024u) / stage_bytes);
   p.stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
   const int smem = p.stages * (int)stage_bytes + WG_PROD_WARPS * 128 * 4 + (2 * WG_MAX_STAGES + 1) * 8 + 64 + 1024;
-  static bool attr = false;
-  if (!attr) {
-    GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
-  wgrad_tc_kernel<<<grid, WG_THREADS, smem, stream>>>(p);
+#define WG_LAUNCH(NP_)                                                                                          \
+  do {                                                                                                         \
+    static bool attr = false;                                                                                  \
+    if (!attr) {                                                                                               \
+      GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr = true;                                                                                             \
+    }                                                                                                          \
+    wgrad_tc_kernel<NP_><<<grid, WG_THREADS, smem, stream>>>(p);                                               \
+  } while (0)
+  if (p.n_pieces == 2) WG_LAUNCH(2); else if (p.n_pieces == 3) WG_LAUNCH(3); else WG_LAUNCH(4);
+#undef WG_LAUNCH
   GNNFD_LAUNCH_CHECK();
   const int m_valid = a->a.width;
   const int total = m_valid * n_valid + cs_valid;

@@ -78,7 +78,10 @@ class FvgnA(Model):
         return x, e, P.mlp_rows(self.decoder.face_mlp, e, prec)
 
     def forward(self, graphs, mode="rollout"):   # Fvgn.py:150-174
-        graphs = self.normalizer.input(graphs)
+        return self.forward_normalised(self.normalizer.input(graphs), mode)
+
+    def forward_normalised(self, graphs, mode="rollout"):
+        """``forward`` after the in-place input normalisation (graphs already normalised and resident)."""
         c_graph, f_graph, v_graph = graphs
         c_graph.edge_attr = f_graph.x
         topo = get_topology(graphs)

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_SILU, ACT_TANH, PRECISIONS, SEG_DIFF2, SEG_DIRECT, SEG_GATHER, SEG_MEAN3,  # noqa: F401
-                   SEG_SUM2, MlpArgs, WgradArgs, check, lib)
+                   SEG_SUM2, MlpArgs, MlpBackwardArgs, WgradArgs, check, lib)
 
 
 LAUNCHES = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -269,6 +269,63 @@ def linear_tc(src: Seg, rows: int, w_t: torch.Tensor, ld_n: int, ld_k: int, w_ro
     check(lib.gnnfd_mlp_forward(C.byref(args), _stream()), "gnnfd_mlp_forward")
     _count(1)
     return out
+
+
+def mlp_backward_workspace(rows: int, device) -> torch.Tensor:
+    """Scratch for ``mlp_backward`` calls of up to ``rows`` rows (three [rows,128] matrices + split-K partials)."""
+    args = MlpArgs()
+    args.rows, args.n_seg, args.has_ln, args.precision, args.n_out = rows, 3, 1, _lib.PREC_BF16X3, 128
+    return torch.empty(lib.gnnfd_mlp_backward_workspace_bytes(C.byref(args)), dtype=torch.uint8, device=device)
+
+
+def mlp_backward(segs: Sequence[Seg], w: MLPWeights, st: "MLPStash", rows: int, g: torch.Tensor, precision: int,
+                 din: Sequence[Optional[dict]], workspace: torch.Tensor):
+    """Whole backward of one fused MLP in one C call (gnnfd_mlp_backward).  ``din[i]`` is None or a dict with
+    optional ``residual`` / ``out``.  Returns ({name: grad} for w1,b1,w2,b2,w3,b3,ln_w,ln_b present, [dIn_i])."""
+    b = MlpBackwardArgs()
+    keep = _fill_args(b.fwd, segs, w, rows, precision)
+    dev = w.w1.device
+    if w.bwd_packs is None or w.bwd_packs.get("prec") != precision:
+        nbytes = lib.gnnfd_pack_mlp_backward_bytes(C.byref(b.fwd))
+        pk = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        check(lib.gnnfd_pack_mlp_backward(C.byref(b.fwd), pk.data_ptr(), _stream()), "gnnfd_pack_mlp_backward")
+        _count(2 + len(segs))
+        w.bwd_packs = {"prec": precision, "pack": pk}
+    b.packed_bwd = w.bwd_packs["pack"].data_ptr()
+    g = _req(g.contiguous(), torch.float32, "g")
+    b.g = g.data_ptr()
+    b.a1, b.a2, b.xhat, b.rstd = st.a1.data_ptr(), st.a2.data_ptr(), _ptr(st.xhat), _ptr(st.rstd)
+    n_out, k_in = w.w3.shape[0], w.w1.shape[1]
+    # every parameter gradient of the MLP in one flat allocation
+    sizes = [("w1", 128 * k_in), ("b1", 128 if w.b1 is not None else 0), ("w2", 128 * 128),
+             ("b2", 128 if w.b2 is not None else 0), ("w3", n_out * 128), ("b3", n_out if w.b3 is not None else 0),
+             ("ln_w", n_out if w.ln_w is not None else 0), ("ln_b", n_out if w.ln_b is not None else 0)]
+    flat = torch.empty(sum(n for _, n in sizes), dtype=torch.float32, device=dev)
+    grads, o = {}, 0
+    shapes = {"w1": (128, k_in), "w2": (128, 128), "w3": (n_out, 128)}
+    for name, n in sizes:
+        if n:
+            grads[name] = flat[o:o + n].view(shapes.get(name, (n,)))
+            setattr(b, "d_" + name, flat.data_ptr() + 4 * o)
+            o += n
+    dins = []
+    for i in range(len(segs)):
+        spec = din[i] if i < len(din) else None
+        if spec is None:
+            dins.append(None)
+            continue
+        out = spec.get("out")
+        if out is None:
+            out = torch.empty(rows, 128, dtype=torch.float32, device=dev)
+        b.din_out[i] = out.data_ptr()
+        res = spec.get("residual")
+        b.din_residual[i] = _req(res, torch.float32, "residual").data_ptr() if res is not None else None
+        dins.append(out)
+    b.workspace, b.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    check(lib.gnnfd_mlp_backward(C.byref(b), _stream()), "gnnfd_mlp_backward")
+    _count((2 if w.has_ln else 0) + 6 + 2 + sum(1 for d in dins if d is not None))
+    del keep
+    return grads, dins
 
 
 def ln_backward(g: torch.Tensor, xhat: torch.Tensor, rstd: torch.Tensor, ln_w: Optional[torch.Tensor]):

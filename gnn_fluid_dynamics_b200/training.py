@@ -48,13 +48,18 @@ class Site:
 
 
 def mlp_backward(w: MLPWeights, st: MLPStash, segs: Sequence[Seg], rows: int, g: torch.Tensor, prec: int,
-                 din: Sequence[Optional[dict]], workspace: Optional[torch.Tensor] = None):
-    """Backward of one fused MLP.  ``g`` = gradient w.r.t. the MLP(+LN) output.  ``din[i]`` is None (segment i
+                 din: Sequence[Optional[dict]], workspace: torch.Tensor):
+    """Backward of one fused MLP through the library's single-call schedule (gnnfd_mlp_backward)."""
+    grads, dins = ops.mlp_backward(segs, w, st, rows, g, prec, din, workspace)
+    return [grads.get(n) for n in PARAM_NAMES], dins
+
+
+def mlp_backward_stepwise(w: MLPWeights, st: MLPStash, segs: Sequence[Seg], rows: int, g: torch.Tensor, prec: int,
+                          din: Sequence[Optional[dict]], workspace: Optional[torch.Tensor] = None):
+    """The same chain issued kernel by kernel from Python (used by the tests to pin the fused call).  ``g`` = gradient w.r.t. the MLP(+LN) output.  ``din[i]`` is None (segment i
     needs no gradient) or a dict with optional ``residual`` (added to the segment's input gradient) and
     ``out`` (destination).  Returns (parameter gradients in PARAM_NAMES order, [dIn_i or None])."""
-    if w.bwd_packs is None:
-        w.bwd_packs = {}
-    packs = w.bwd_packs
+    packs = {}
     code = w.act + 1                      # SiLU -> 1, tanh -> 2 (wgrad act / dgrad mul_mode)
     dev = g.device
     n_out, k_in = w.w3.shape[0], w.w1.shape[1]
@@ -170,7 +175,7 @@ class EncodeProcessDecode(torch.autograd.Function):
         fam = plan.family
         N, E, V = c_x.shape[0], f_x.shape[0], topo.n_vertices
         dev = g_out.device
-        ws = torch.empty(ops.lib.gnnfd_wgrad_workspace_bytes(max(N, E), 384), dtype=torch.uint8, device=dev)
+        ws = ops.mlp_backward_workspace(max(N, E), dev)
         rc_off, rc_perm = topo.build_rowcol_csr()
         vf_off, vf_perm = topo.build_vf_csr()
         site_grads = {}

@@ -119,6 +119,13 @@ typedef struct {
    * dgrad uses a forward weight W[out, in] transposed in place: w1 = W + col0, ld_n = 1, ld_k = in.
    * w1_rows: valid output features (rows >= w1_rows of the 128 are zero); 0 = 128. */
   int32_t w1_ld_n, w1_ld_k, w1_rows;
+  /* bwd_chain = 1 (n_layers 0|3, no LayerNorm, n_out == 128, biases ignored): the dgrad chain of an MLP as one
+   * pass - hidden epilogue l (l = 1, 2) computes v = acc * act'(hid_mul{l}[r, :]) instead of bias + activation,
+   * stores v to save_a{l} (dA2, dA1: the wgrad operands) and feeds it to the next Linear.  All three weights
+   * are addressed with explicit strides (element (n, k) at w[n * ld_n + k * ld_k]), w3_rows = valid outputs. */
+  int32_t bwd_chain;
+  const float *hid_mul1, *hid_mul2;
+  int32_t w2_ld_n, w2_ld_k, w3_ld_n, w3_ld_k, w3_rows;
 } gnnfd_mlp_args;
 
 int gnnfd_abi_version(void);
@@ -195,6 +202,32 @@ typedef struct {
 size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded /* sum of B widths rounded up to 32 */);
 int gnnfd_wgrad(const gnnfd_wgrad_args *args, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The whole backward of one fused MLP in ONE call (the host-side schedule lives in the library so the GPU,
+ * not the foreign-call overhead, bounds the training step):
+ *   LayerNorm backward -> dW3, dA2 = (dy W3) act'(a2) -> dW2, dA1 = (dA2 W2) act'(a1) -> dW1 ->
+ *   input gradient of every segment whose din_out is set: din_out[s] = din_residual[s] + dA1 W1[:, segment s]
+ * `fwd` repeats the forward call's arguments (segments, parameters, rows, act, has_ln, precision); g is the
+ * gradient w.r.t. out_raw; a1/a2/xhat/rstd are the forward's stashes; packed_bwd comes from
+ * gnnfd_pack_mlp_backward (transposed-weight operand packs; rebuild when the parameters change).
+ * Gradient outputs that are NULL are skipped (d_w1..3 are required).  Segment input gradients are
+ * [rows, 128] matrices (columns >= the segment width are zero); gather / mean segments are scattered by
+ * the caller with gnnfd_segment_sum3. */
+typedef struct {
+  gnnfd_mlp_args fwd;
+  const float *g;
+  const float *a1, *a2, *xhat, *rstd;
+  const void *packed_bwd;
+  float *d_w1, *d_b1, *d_w2, *d_b2, *d_w3, *d_b3, *d_ln_w, *d_ln_b;
+  float *din_out[3];
+  const float *din_residual[3];
+  void *workspace;
+  size_t workspace_bytes;
+} gnnfd_mlp_backward_args;
+size_t gnnfd_mlp_backward_workspace_bytes(const gnnfd_mlp_args *fwd);
+size_t gnnfd_pack_mlp_backward_bytes(const gnnfd_mlp_args *fwd);
+int gnnfd_pack_mlp_backward(const gnnfd_mlp_args *fwd, void *packed_out, void *stream);
+int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *args, void *stream);
+
 /* Transpose of a gather = deterministic segment sum with up to three source parts, a scale and a base:
  *   out[r, :] = base[r, :] + scale * sum over p in perm[offsets[r]:offsets[r+1]] (ascending) of
  *               p < n ? a[p, col_a:+width] : p < 2n ? sign_b * b[p-n, col_b:+width] : c[p-2n, col_c:+width]
@@ -212,7 +245,8 @@ int gnnfd_segment_sum3(const float *a, const float *b, const float *c, int32_t l
 int gnnfd_gather_pair_add(float *dst, const float *base, const float *src, int32_t ld_src, const int32_t *i0,
                           const int32_t *i1, float sign, int32_t halves, int64_t rows, void *stream);
 
-/* sizeof(gnnfd_mlp_args) (which = 0), sizeof(gnnfd_wgrad_args) (1), sizeof(gnnfd_segment) (2): lets a
+/* sizeof(gnnfd_mlp_args) (which = 0), sizeof(gnnfd_wgrad_args) (1), sizeof(gnnfd_segment) (2),
+ * sizeof(gnnfd_mlp_backward_args) (3): lets a
  * foreign-function binding verify its struct mirror against the library it loaded. */
 size_t gnnfd_struct_size(int32_t which);
 

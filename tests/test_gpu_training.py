@@ -220,3 +220,26 @@ def test_training_gradients_are_bitwise_reproducible():
         model.loss(out, gn)["total_log_loss"].backward()
         runs.append([p.grad.clone() for p in model.parameters() if p.grad is not None])
     assert all(torch.equal(a, b) for a, b in zip(*runs))
+
+
+def test_fused_backward_call_equals_stepwise_schedule():
+    """gnnfd_mlp_backward (one C call, dgrad chain fused into one 3-layer pass) against the Python-scheduled
+    chain of single-Linear launches: same arithmetic up to accumulation order."""
+    from gnn_fluid_dynamics_b200 import ops, _lib, training
+    from test_gpu_parity import _rand_mlp, _to_weights
+    g = torch.Generator().manual_seed(21)
+    N, E = 500, 900
+    x, e = torch.randn(N, 128, generator=g).to(dev()), torch.randn(E, 128, generator=g).to(dev())
+    row, col = i32(torch.randint(0, N, (E,), generator=g)), i32(torch.randint(0, N, (E,), generator=g))
+    segs = [ops.Seg(e), ops.Seg(x, _lib.SEG_GATHER, (row,)), ops.Seg(x, _lib.SEG_GATHER, (col,))]
+    w = _to_weights(_rand_mlp(384, 128, True, seed=3), _lib.ACT_SILU)
+    _, _, st = ops.mlp_forward(segs, w, E, _lib.PREC_BF16X3, residual=e, want_raw=False, want_sum=True, stash=True)
+    go, res = torch.randn(E, 128, generator=g).to(dev()), torch.randn(E, 128, generator=g).to(dev())
+    ws = ops.mlp_backward_workspace(E, dev())
+    ga, da = training.mlp_backward(w, st, segs, E, go, _lib.PREC_BF16X3, [{"residual": res}, {}, None], ws)
+    gb, db = training.mlp_backward_stepwise(w, st, segs, E, go, _lib.PREC_BF16X3, [{"residual": res}, {}, None])
+    for p, q in zip(ga, gb):
+        assert (p is None) == (q is None)
+        if p is not None:
+            assert rel_l2(p, q) < 2e-5, rel_l2(p, q)
+    assert rel_l2(da[0], db[0]) < 2e-5 and rel_l2(da[1], db[1]) < 2e-5 and da[2] is None and db[2] is None
