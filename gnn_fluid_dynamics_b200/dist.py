@@ -1,0 +1,169 @@
+"""Multi-GPU execution of the hot path.
+
+* Independent meshes (BASELINE.json configs 2, 5): plain data parallelism - every rank runs the whole
+  path on its own meshes, no data-path collective; training adds one gradient all-reduce per step
+  (``allreduce_gradients``).
+* One large mesh (config 4): domain decomposition (``partition.py``) with ONE halo exchange of ghost-cell
+  latents per GN_Block.  The send side packs boundary rows with ``gnnfd_gather_rows``; the transfer is NCCL
+  point-to-point over NVLink (``torch.distributed.batch_isend_irecv``); the receive side lands directly in the
+  ghost rows (contiguous per owner rank, no unpack).  Face latents are never communicated.
+
+``InProcessTransport`` runs all partitions in one process on one GPU (same kernels, same plan, copies
+instead of NCCL): it is how the single-GPU tests pin the partitioned result bit-for-bit to the unpartitioned
+one; ``TorchDistTransport`` is the one-process-per-GPU transport.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .ops import Seg
+from .partition import Partition
+from .processor import H, weights_of
+from ._lib import SEG_GATHER, SEG_MEAN3
+
+
+@dataclass
+class PartState:
+    """Device-side state of one partition: plan, local topology, latents (rows: owned cells, then ghosts)."""
+    part: Partition
+    topo: object                     # MeshTopology of the local sub-mesh
+    x: Optional[torch.Tensor] = None
+    e: Optional[torch.Tensor] = None
+    send_idx: Optional[dict] = None  # peer -> int32 device tensor
+
+    def device_plan(self, device):
+        if self.send_idx is None:
+            self.send_idx = {p: idx.to(torch.int32).to(device) for p, idx in self.part.send.items()}
+        return self
+
+
+def _pack_cuda(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    return ops.gather_rows(t, idx)
+
+
+class InProcessTransport:
+    """All partitions live in this process: the exchange is a row copy between their tensors."""
+
+    def __init__(self, pack: Callable = _pack_cuda):
+        self.pack = pack
+        self.bytes_sent = 0
+
+    def exchange(self, states: Sequence[PartState], get: Callable[[PartState], torch.Tensor]):
+        by_rank = {s.part.rank: s for s in states}
+        for dst in states:
+            t = get(dst)
+            for peer, (start, cnt) in dst.part.recv.items():
+                src = by_rank[peer]
+                src.device_plan(get(src).device)
+                rows = self.pack(get(src), src.send_idx[dst.part.rank])
+                t[start:start + cnt].copy_(rows)
+                self.bytes_sent += rows.numel() * 4
+
+
+class TorchDistTransport:
+    """One partition per process (torch.distributed, NCCL on GPUs / gloo in the CPU tests): grouped
+    point-to-point sends and receives, all posted together so NCCL runs them as one group."""
+
+    def __init__(self, group=None, pack: Callable = _pack_cuda):
+        import torch.distributed as dist
+        self.dist, self.group, self.pack = dist, group, pack
+        self.bytes_sent = 0
+
+    def exchange(self, states: Sequence[PartState], get: Callable[[PartState], torch.Tensor]):
+        dist = self.dist
+        (s,) = states
+        t = get(s)
+        s.device_plan(t.device)
+        ops_, keep = [], []
+        for peer, (start, cnt) in sorted(s.part.recv.items()):
+            ops_.append(dist.P2POp(dist.irecv, t[start:start + cnt], peer, self.group))
+        for peer, idx in sorted(s.send_idx.items()):
+            buf = self.pack(t, idx)
+            keep.append(buf)
+            self.bytes_sent += buf.numel() * 4
+            ops_.append(dist.P2POp(dist.isend, buf, peer, self.group))
+        if ops_:
+            for req in dist.batch_isend_irecv(ops_):
+                req.wait()
+
+
+def _edge_segs(e, xs, topo):
+    return [Seg(e), Seg(xs, SEG_GATHER, (topo.row,)), Seg(xs, SEG_GATHER, (topo.col,))]
+
+
+def run_processor_partitioned(family: str, blocks, states: List[PartState], transport, prec: int):
+    """The GN_Blocks over partitioned latents.  Edge phases run on all local faces, node phases on owned cells
+    only; exactly one halo exchange per block (MGN: block-input x, skipped for block 0 where the ghosts' x is the
+    locally encoded one; FVGN: the raw cell-MLP output x')."""
+    if family not in ("mgn", "fvgn"):
+        raise NotImplementedError(f"domain decomposition covers the 'mgn' and 'fvgn' data-flows, not {family!r}")
+    for i, blk in enumerate(blocks):
+        we, wn = weights_of(blk.face_block.face_mlp), weights_of(blk.cell_block.cell_mlp)
+        if family == "mgn":
+            if i > 0:
+                transport.exchange(states, lambda s: s.x)
+            for s in states:
+                topo, n_own = s.topo, s.part.n_owned
+                e_raw, e_new = ops.mlp_forward(_edge_segs(s.e, s.x, topo), we, s.e.shape[0], prec, residual=s.e,
+                                               want_raw=True, want_sum=True)
+                vsum = ops.segment_sum(e_raw, e_raw, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm,
+                                       topo.n_vertices)
+                x_new = torch.empty_like(s.x)
+                ops.mlp_forward([Seg(s.x), Seg(vsum, SEG_MEAN3, topo.vf)], wn, n_own, prec, residual=s.x,
+                                want_raw=False, want_sum=True, out_sum=x_new)
+                s.x, s.e = x_new, e_new
+        else:
+            for s in states:
+                topo, n_own = s.topo, s.part.n_owned
+                vsum = ops.segment_sum(s.e, s.e, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm,
+                                       topo.n_vertices)
+                s.x_raw, x_new = torch.empty_like(s.x), torch.empty_like(s.x)
+                ops.mlp_forward([Seg(s.x), Seg(vsum, SEG_MEAN3, topo.vf)], wn, n_own, prec, residual=s.x,
+                                want_raw=True, want_sum=True, out_raw=s.x_raw, out_sum=x_new)
+                s.x = x_new
+            transport.exchange(states, lambda s: s.x_raw)
+            for s in states:
+                _, s.e = ops.mlp_forward(_edge_segs(s.e, s.x_raw, s.topo), we, s.e.shape[0], prec, residual=s.e,
+                                         want_raw=False, want_sum=True)
+    return states
+
+
+def encode_process_decode_partitioned(model, states: List[PartState], inputs, transport):
+    """encoder -> partitioned GN_Blocks -> decoder for an Fvgn/Mgn-family model.  ``inputs[k]`` = (c_x, f_x) of
+    partition k (normalised, local rows).  Returns per partition (x[n_owned], e[E_loc], decoder output): the node
+    decoder (MGN) covers the owned cells, the edge decoder (FVGN) all local faces."""
+    from . import processor as P
+    prec = model.prec
+    for s, (c_x, f_x) in zip(states, inputs):
+        s.e = P.mlp_rows(model.encoder.face_mlp, f_x, prec)
+        s.x = P.mlp_rows(model.encoder.cell_mlp, c_x, prec)     # ghosts encoded locally: no exchange before block 0
+    run_processor_partitioned(model.family, model.processer_list, states, transport, prec)
+    outs = []
+    for s in states:
+        n_own = s.part.n_owned
+        if model.family == "mgn":
+            dec = P.mlp_rows(model.decoder.face_mlp, s.x[:n_own], prec)
+        else:
+            dec = P.mlp_rows(model.decoder.face_mlp, s.e, prec)
+        outs.append((s.x[:n_own], s.e, dec))
+    return outs
+
+
+def allreduce_gradients(params, world: int, group=None):
+    """Data-parallel training over independent meshes: ONE flat all-reduce of every gradient per step (the
+    reference's DDP wrapper is bypassed by its own trainer, src/train.py:165; this is the working equivalent)."""
+    import torch.distributed as dist
+    grads = [p.grad for p in params if p.grad is not None]
+    if world <= 1 or not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat /= world
+    o = 0
+    for g in grads:
+        g.copy_(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()

@@ -395,3 +395,16 @@ def gather_pair_add(src: torch.Tensor, i0: torch.Tensor, i1: torch.Tensor, sign:
                                     float(sign), int(halves), rows, _stream()), "gnnfd_gather_pair_add")
     _count(1)
     return out
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = src[idx[r]] (halo pack, gnnfd_gather_rows)."""
+    src = _req(src, torch.float32, "src")
+    idx = _req(idx, torch.int32, "idx")
+    n, width = idx.numel(), src.shape[1]
+    if out is None:
+        out = torch.empty(n, width, dtype=torch.float32, device=src.device)
+    check(lib.gnnfd_gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), n, width, out.data_ptr(), _stream()),
+          "gnnfd_gather_rows")
+    _count(1)
+    return out

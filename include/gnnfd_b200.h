@@ -245,6 +245,12 @@ int gnnfd_segment_sum3(const float *a, const float *b, const float *c, int32_t l
 int gnnfd_gather_pair_add(float *dst, const float *base, const float *src, int32_t ld_src, const int32_t *i0,
                           const int32_t *i1, float sign, int32_t halves, int64_t rows, void *stream);
 
+/* Halo pack of the domain-decomposed processor (one exchange of ghost-cell latents per GN_Block, SURVEY.md 8e;
+ * the reference has no counterpart - it runs one mesh on one GPU): out[r, 0:width] = src[idx[r], 0:width].
+ * The receive side needs no unpack: ghost rows are stored contiguously per owner rank. */
+int gnnfd_gather_rows(const float *src, int32_t ld, const int32_t *idx, int64_t n, int32_t width, float *out,
+                      void *stream);
+
 /* sizeof(gnnfd_mlp_args) (which = 0), sizeof(gnnfd_wgrad_args) (1), sizeof(gnnfd_segment) (2),
  * sizeof(gnnfd_mlp_backward_args) (3): lets a
  * foreign-function binding verify its struct mirror against the library it loaded. */

@@ -1,0 +1,97 @@
+"""GPU: the domain-decomposed processor equals the unpartitioned one BIT FOR BIT on every owned cell and every
+local face (row-independent kernels + order-preserving local CSRs), with all partitions emulated on one GPU
+(InProcessTransport) and - when the box has >= 2 GPUs - with one process per GPU over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from helpers import build_model, golden_graphs
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(name, n_cells, world, device):
+    from gnn_fluid_dynamics_b200.partition import local_graphs, partition_mesh
+    model = build_model(name).eval()
+    _, graphs = golden_graphs(name, n_cells=n_cells, mesh_seed=21, feat_seed=22)
+    graphs = model.normalizer.input([g.clone() for g in graphs])
+    c, f, v = graphs
+    parts = partition_mesh(c.edge_index, v.edge_index, v.face, c.pos[:, 0], world, f_face=f.face)
+    return model.to(device), graphs, parts, [local_graphs(graphs, p) for p in parts]
+
+
+def _states(parts, locals_, device, only=None):
+    from gnn_fluid_dynamics_b200.dist import PartState
+    from gnn_fluid_dynamics_b200.topology import MeshTopology
+    states, inputs = [], []
+    for p, g in zip(parts, locals_):
+        if only is not None and p.rank != only:
+            continue
+        gd = [t.to(device) for t in g]
+        topo = MeshTopology.from_graphs(gd).validate()
+        states.append(PartState(part=p, topo=topo))
+        inputs.append((gd[0].x, gd[1].x))
+    return states, inputs
+
+
+@pytest.mark.parametrize("name", ["MgnA", "FvgnA"])
+@pytest.mark.parametrize("world", [2, 5])
+def test_partitioned_equals_unpartitioned_bitwise(name, world):
+    from gnn_fluid_dynamics_b200.dist import InProcessTransport, encode_process_decode_partitioned
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    dev = torch.device("cuda:0")
+    model, graphs, parts, locals_ = _setup(name, 4000, world, dev)
+    gd = [g.to(dev) for g in graphs]
+    with torch.no_grad():
+        x, e, dec = model.encode_process_decode(gd[0].x, gd[1].x, get_topology(gd).validate())
+        states, inputs = _states(parts, locals_, dev)
+        transport = InProcessTransport()
+        outs = encode_process_decode_partitioned(model, states, inputs, transport)
+    assert transport.bytes_sent > 0
+    for p, (xp, ep, dp) in zip(parts, outs):
+        cells, faces = p.cells[:p.n_owned].to(dev), p.faces.to(dev)
+        assert torch.equal(xp, x[cells])
+        assert torch.equal(ep, e[faces])
+        assert torch.equal(dp, dec[cells] if name == "MgnA" else dec[faces])
+
+
+def _nccl_rank(rank, world, port, name, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from gnn_fluid_dynamics_b200.dist import TorchDistTransport, encode_process_decode_partitioned
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        model, graphs, parts, locals_ = _setup(name, 4000, world, dev)
+        states, inputs = _states(parts, locals_, dev, only=rank)
+        with torch.no_grad():
+            (xp, ep, dp), = encode_process_decode_partitioned(model, states, inputs, TorchDistTransport())
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=xp.cpu().numpy(), e=ep.cpu().numpy(), dec=dp.cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("name", ["MgnA", "FvgnA"])
+def test_nccl_halo_exchange_equals_single_gpu(tmp_path, name):
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    world = min(torch.cuda.device_count(), 4)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_nccl_rank, args=(world, port, name, str(tmp_path)), nprocs=world, join=True)
+    dev = torch.device("cuda:0")
+    model, graphs, parts, _ = _setup(name, 4000, world, dev)
+    gd = [g.to(dev) for g in graphs]
+    with torch.no_grad():
+        x, e, dec = model.encode_process_decode(gd[0].x, gd[1].x, get_topology(gd).validate())
+    for p in parts:
+        d = np.load(tmp_path / f"rank{p.rank}.npz")
+        cells, faces = p.cells[:p.n_owned], p.faces
+        assert np.array_equal(d["x"], x.cpu()[cells].numpy())
+        assert np.array_equal(d["e"], e.cpu()[faces].numpy())
+        assert np.array_equal(d["dec"], (dec.cpu()[cells] if name == "MgnA" else dec.cpu()[faces]).numpy())
