@@ -79,7 +79,7 @@ class ConservativeA(FvgnA):
         u = c_graph.x[:, :2]
         dv = u[c_graph.edge_index[0]] - u[c_graph.edge_index[1]]
         mask = ((f_graph.type == 2) | (f_graph.type == 1)).squeeze(-1)
-        dv[mask] = f_graph.y[:, 0:2][mask]
+        dv = torch.where(mask.unsqueeze(-1), f_graph.y[:, 0:2], dv)   # == dv[mask] = y[mask], without the host sync
         f_graph.x_asym[:, 0:2] = dv
         return [c_graph, f_graph, v_graph]
 

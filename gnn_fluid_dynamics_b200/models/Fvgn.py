@@ -102,7 +102,7 @@ class FvgnA(Model):
         u = c_graph.x[:, :2]
         dv = u[c_graph.edge_index[0]] - u[c_graph.edge_index[1]]
         mask = ((f_graph.type == NODE_INFLOW) | (f_graph.type == NODE_WALL)).squeeze(-1)
-        dv[mask] = f_graph.y[:, 0:2][mask]
+        dv = torch.where(mask.unsqueeze(-1), f_graph.y[:, 0:2], dv)   # == dv[mask] = y[mask], without the host sync
         f_graph.x[:, 0:2] = dv
         return [c_graph, f_graph, v_graph]
 

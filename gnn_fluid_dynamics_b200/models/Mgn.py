@@ -74,7 +74,7 @@ class MgnA(Model):
         c_graph.x = output["cell_velocity"].detach()
         u = c_graph.x[:, :2]
         dv = u[c_graph.edge_index[0]] - u[c_graph.edge_index[1]]
-        dv[f_graph.boundary_mask] = f_graph.y[:, 0:2][f_graph.boundary_mask]
+        dv = torch.where(f_graph.boundary_mask.unsqueeze(-1), f_graph.y[:, 0:2], dv)   # == dv[mask] = y[mask]
         f_graph.x[:, 0:2] = dv
         return [c_graph, f_graph, v_graph]
 

@@ -128,3 +128,21 @@ def fvgn_loss(sd, out, graphs, loss_weights, training=True):
              + w["face_pressure"] * fpl)
     return {"total_log_loss": torch.mean(torch.log(total)), "continuity_loss": cont,
             "cell_velocity_change_loss": cvc, "face_velocity_loss": fvl, "face_pressure_loss": fpl}
+
+
+def rollout_step(model_name, sd, stats, graphs, mp_num):
+    """One autoregressive step on CPU: forward in 'rollout' mode on clones (rollout.py:313), velocity update
+    (rollout.py:340) and update_features (Fvgn.py:133-148 / Mgn.py:139-151), in place on ``graphs``."""
+    c, f, v = graphs
+    out, _ = model_forward(model_name, sd, stats, [g.clone() for g in graphs], mp_num, mode="rollout")
+    vel = c.x[:, :2] + out["cell_velocity_change"]
+    c.x = vel.detach()
+    u = c.x[:, :2]
+    dv = u[c.edge_index[0]] - u[c.edge_index[1]]
+    if model_name == "MgnA":
+        mask = f.boundary_mask
+    else:
+        mask = ((f.type == 2) | (f.type == 1)).squeeze(-1)      # INFLOW | WALL_BOUNDARY (OpenFoam.py:19-24)
+    dv[mask] = f.y[:, 0:2][mask]
+    f.x[:, 0:2] = dv
+    return vel
