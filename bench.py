@@ -31,6 +31,10 @@ WORKLOADS = {
     "fvgn_train_8x20k": ("FvgnA", 8, 20000, "cylinder", True),
     "mgn_fwd_2k": ("MgnA", 1, 2048, "none", False),
     "mgn_fwd_200k": ("MgnA", 1, 200000, "airfoil", False),
+    # autoregressive rollouts (second half of the metric: rollout steps/sec); "rollout" in the training slot
+    "mgn_rollout_2k": ("MgnA", 1, 2048, "cylinder", "rollout"),        # BASELINE.json configs[0] shape
+    "flux_rollout_200k": ("FluxA", 1, 200000, "cylinder", "rollout"),  # configs[2]
+    "mgn_rollout_4m": ("MgnA", 1, 4000000, "airfoil", "rollout"),      # configs[3]: domain-decomposed over --gpus N
 }
 DEFAULT_WORKLOAD = "fvgn_train_8x20k"   # BASELINE.json configs[1]
 
@@ -220,8 +224,11 @@ def main():
     from gnn_fluid_dynamics_b200 import ops
     from gnn_fluid_dynamics_b200.precisions import available
     from gnn_fluid_dynamics_b200.topology import get_topology
+    from gnn_fluid_dynamics_b200.dist import allreduce_gradients
 
     model_name, n_meshes, n_cells, kind, train = WORKLOADS[args.workload]
+    if train == "rollout":
+        return run_rollout(args, world, rank, dev, dist)
     from gnn_fluid_dynamics_b200.models.base import DEFAULT_PRECISION
     prec = args.precision or DEFAULT_PRECISION
     assert prec in available(), prec
@@ -249,13 +256,7 @@ def main():
         loss = model.loss(out, graphs_norm)["total_log_loss"]
         loss.backward()
         if world > 1:   # data-parallel: meshes are independent units, one gradient all-reduce per step
-            flat = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
-            dist.all_reduce(flat)
-            flat /= world
-            o = 0
-            for p in model.parameters():
-                if p.grad is not None:
-                    p.grad.copy_(flat[o:o + p.numel()].view_as(p)); o += p.numel()
+            allreduce_gradients(list(model.parameters()), world)
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         return loss
@@ -389,6 +390,96 @@ def main():
                          "peak_kind": peak_kind,
                          "kernel_ms": k_ms, "algorithmic_bytes": alg},
             "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_rollout(args, world, rank, dev, dist):
+    """Rollout workloads: K autoregressive steps of one mesh.  N = 1: RolloutEngine (CUDA-graph replay);
+    N > 1: the mesh is domain-decomposed, one partition per GPU, halo exchange per GN_Block (strong scaling)."""
+    from helpers import build_model
+    from gnn_fluid_dynamics_b200 import ops
+    from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs
+    model_name, _, n_cells, kind, _ = WORKLOADS[args.workload]
+    prec = args.precision or "bf16x3"
+    model = build_model(model_name, precision=prec).to(dev).eval()
+    mesh = make_mesh(n_cells, kind, seed=0)
+    g = mesh_graphs(mesh, seed=100)
+    if model_name == "MgnA":
+        g[0].y = torch.cat([g[0].y, torch.zeros(g[0].x.shape[0], 1)], 1)
+        g[1].y = g[1].y[:, :2].contiguous()
+    g = _with_batch(g)
+    N, E, V = g[0].x.shape[0], g[0].edge_index.shape[1], g[2].pos.shape[0]
+    halo_bytes = 0
+    if world > 1:
+        from gnn_fluid_dynamics_b200.dist import PartitionedRollout, TorchDistTransport
+        from gnn_fluid_dynamics_b200.partition import local_graphs, partition_mesh
+        parts = partition_mesh(g[0].edge_index, g[2].edge_index, g[2].face, g[0].pos[:, 0], world, f_face=g[1].face)
+        part = parts[rank]
+        transport = TorchDistTransport()
+        eng = PartitionedRollout(model, [part], [[t.to(dev) for t in local_graphs(g, part)]], transport)
+        step = eng.step
+        out_rows = part.n_owned
+    else:
+        from gnn_fluid_dynamics_b200.rollout import RolloutEngine
+        eng = RolloutEngine(model, [t.to(dev) for t in g], cuda_graph=True)
+        step = eng.step
+        out_rows = N
+    host_out = torch.empty(out_rows, 2).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler.start()
+    ops.LAUNCHES = 0
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        step()
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b) / args.steps
+    launches = ops.LAUNCHES
+    clocks = sampler.stop()
+    if world > 1:
+        halo_bytes = transport.bytes_sent // (args.steps + args.warmup)
+    # e2e: every step's velocity field is read back to pinned host memory (what the reference's writer consumes)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v = step()
+        host_out.copy_(v[0] if isinstance(v, list) else v, non_blocking=False)
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        line = {
+            "metric": "processor edge-updates/sec", "value": E * MP_NUM / (ms * 1e-3), "unit": "edge-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)" if prec == "bf16x3" else prec, "data": "synthetic",
+            "config": {"workload": args.workload, "model": model_name, "mp_num": MP_NUM, "hidden": 128, "cells": N,
+                       "faces": E, "vertices": V, "precision": prec, "rollout_steps_per_s": 1e3 / ms,
+                       "timed": "one autoregressive step: normalise + encoder + 15 GN_Blocks + decoder (+ integrator) + state advance",
+                       "execution": ("domain-decomposed, one partition per GPU, 1 halo exchange per GN_Block + 1 per step, "
+                                     f"{halo_bytes} halo bytes sent per step by rank 0") if world > 1 else "CUDA-graph replay",
+                       "l2": "working set > L2" if N > 100000 else "small mesh: L2-resident by nature of the workload"},
+            "e2e": {"value": E * MP_NUM / (ms_e2e * 1e-3), "unit": "edge-updates/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": out_rows * 8, "ms_per_step": ms_e2e,
+                    "api": "RolloutEngine.step / PartitionedRollout.step + velocity read back to pinned host memory"},
+            "gpu_launches": launches if world > 1 else "CUDA graph (kernels of one captured step replayed)",
+            "clocks": clocks, "roofline": None, "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -167,3 +167,60 @@ def allreduce_gradients(params, world: int, group=None):
     for g in grads:
         g.copy_(flat[o:o + g.numel()].view_as(g))
         o += g.numel()
+
+
+class PartitionedRollout:
+    """Autoregressive rollout of ONE large mesh over several partitions (BASELINE.json config 4): per step the
+    encoder / decoder / integrator run locally, the GN_Blocks exchange ghost latents once per block, and the state
+    advance exchanges the ghost cells' new velocity (2 floats per ghost cell) once per step.
+
+    ``local_graphs[k]`` is partition k's [c_graph, f_graph, v_graph] on its device (``partition.local_graphs``);
+    under torch.distributed each process holds exactly one partition."""
+
+    def __init__(self, model, parts: Sequence[Partition], local_graphs: Sequence[list], transport):
+        from .graph import Data
+        from .topology import MeshTopology
+        if model.family not in ("mgn", "fvgn"):
+            raise NotImplementedError("partitioned rollout covers the Mgn / Fvgn families")
+        self.model, self.transport = model.eval(), transport
+        self.graphs = list(local_graphs)
+        self.states = []
+        for p, g in zip(parts, self.graphs):
+            topo = MeshTopology.from_graphs(g).validate()
+            self.states.append(PartState(part=p, topo=topo).device_plan(g[0].x.device))
+        self._Data = Data
+
+    @torch.no_grad()
+    def step(self):
+        """One timestep on every held partition; returns the owned cells' new velocity per partition."""
+        model = self.model
+        norm, inputs = [], []
+        for g in self.graphs:
+            gn = model.normalizer.input([t.clone() for t in g])
+            norm.append(gn)
+            inputs.append((gn[0].x, gn[1].x))
+        outs = encode_process_decode_partitioned(model, self.states, inputs, self.transport)
+        vels = []
+        for s, g, gn, (_, _, dec) in zip(self.states, self.graphs, norm, outs):
+            n_own = s.part.n_owned
+            c, f, _ = gn
+            if model.family == "mgn":
+                output = [dec, None, None]
+            else:
+                c_view = self._Data(normal=c.normal[:n_own], volume=c.volume, edge_index=c.edge_index, dt=c.dt)
+                output = [model.integrator(dec, c_view, f, c.dt), dec, None]
+            output = model.normalizer.output(output, inverse=True)
+            vel = g[0].x[:n_own, :2] + output[0][:, 0:2]
+            g[0].x[:n_own, :2] = vel
+            vels.append(vel)
+        self.transport.exchange(self.states, lambda s: self.graphs[self.states.index(s)][0].x)
+        for g in self.graphs:
+            c, f, _ = g
+            u = c.x[:, :2]
+            dv = u[c.edge_index[0]] - u[c.edge_index[1]]
+            if model.family == "mgn":
+                mask = f.boundary_mask
+            else:
+                mask = ((f.type == 2) | (f.type == 1)).squeeze(-1)
+            f.x[:, 0:2] = torch.where(mask.unsqueeze(-1), f.y[:, 0:2], dv)
+        return vels

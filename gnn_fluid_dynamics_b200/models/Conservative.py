@@ -50,6 +50,9 @@ class ConservativeA(FvgnA):
 
     def encode_process_decode(self, c_x, f_x_symm, f_x_asym, topo, hook=None):
         prec = self.prec
+        if self.wants_grad():
+            raise NotImplementedError("the backward kernels cover the Fvgn/Flux and Mgn/StreamFunc families; "
+                                      f"{type(self).__name__} runs forward / rollout only (wrap the call in torch.no_grad())")
         e = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
         e_asym = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)

@@ -41,6 +41,9 @@ class VertPotA(FluxA):
 
     def encode_process_decode(self, c_x, f_x, topo, hook=None):
         prec = self.prec
+        if self.wants_grad():
+            raise NotImplementedError("the backward kernels cover the Fvgn/Flux and Mgn/StreamFunc families; "
+                                      f"{type(self).__name__} runs forward / rollout only (wrap the call in torch.no_grad())")
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
         x, e, vx = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook)

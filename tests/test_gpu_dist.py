@@ -95,3 +95,23 @@ def test_nccl_halo_exchange_equals_single_gpu(tmp_path, name):
         assert np.array_equal(d["x"], x.cpu()[cells].numpy())
         assert np.array_equal(d["e"], e.cpu()[faces].numpy())
         assert np.array_equal(d["dec"], (dec.cpu()[cells] if name == "MgnA" else dec.cpu()[faces]).numpy())
+
+
+@pytest.mark.parametrize("name", ["MgnA", "FvgnA"])
+def test_partitioned_rollout_equals_single_gpu_rollout(name):
+    """5 autoregressive steps over 3 partitions (in-process transport) == the single-GPU RolloutEngine."""
+    from gnn_fluid_dynamics_b200.dist import InProcessTransport, PartitionedRollout
+    from gnn_fluid_dynamics_b200.partition import local_graphs, partition_mesh
+    from gnn_fluid_dynamics_b200.rollout import RolloutEngine
+    dev = torch.device("cuda:0")
+    model = build_model(name).to(dev).eval()
+    _, graphs = golden_graphs(name, n_cells=3000, mesh_seed=41, feat_seed=42)
+    c, f, v = graphs
+    parts = partition_mesh(c.edge_index, v.edge_index, v.face, c.pos[:, 0], 3, f_face=f.face)
+    pr = PartitionedRollout(model, parts, [[t.to(dev) for t in local_graphs(graphs, p)] for p in parts], InProcessTransport())
+    eng = RolloutEngine(model, [g.clone().to(dev) for g in graphs], cuda_graph=False)
+    for _ in range(5):
+        vels = pr.step()
+        ref = eng.step()
+        for p, vp in zip(parts, vels):
+            assert torch.equal(vp, ref[p.cells[:p.n_owned].to(dev)])
