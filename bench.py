@@ -117,22 +117,22 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the fused edge block, from the committed
-    `ncu --set full` capture of this same command (profiles/*_ncu_summary.json; scripts/summarize_ncu.py)."""
-    if workload != DEFAULT_WORKLOAD:
+def ncu_traffic(which):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of a kernel at the bench shape, from the committed
+    `ncu --set full` capture (profiles/r01_train_kernels_ncu_summary.json <- scripts/prof_train_kernels.py, whose
+    launch order is: forward+stash, wgrad L3, dgrad chain, wgrad L2, wgrad L1, 2 x single Linear) or, for the
+    inference forward, profiles/r01_mlp_tc_ncu_summary.json."""
+    try:
+        if which == "edge_chain":
+            name = "r01_train_kernels_ncu_summary.json"
+            d = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return int(d["launches"][2]["dram_traffic_bytes"]), name
+        name = "r01_mlp_tc_ncu_summary.json"
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
+        edge = max(d["launches"], key=lambda x: x.get("duration_us", 0))      # edge block = the longer launch
+        return int(edge["dram_traffic_bytes"]), name
+    except Exception:  # noqa: BLE001
         return None, None
-    best = None
-    pdir = os.path.join(ROOT, "profiles")
-    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
-        if name.endswith("_ncu_summary.json"):
-            try:
-                d = json.load(open(os.path.join(pdir, name)))
-                edge = max(d["launches"], key=lambda x: x.get("duration_us", 0))   # edge block = the longer launch
-                best = (int(edge["dram_traffic_bytes"]), name)
-            except Exception:  # noqa: BLE001
-                pass
-    return best if best else (None, None)
 
 
 def algorithmic_bytes_edge_kernel(E, N):
@@ -326,29 +326,66 @@ def main():
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
 
-    # ---- dominant kernel (fused edge block) timed alone with CUDA events on its stream -------------
+    # ---- dominant kernels timed alone with CUDA events on their stream (L2 flushed between launches) -------
     model.eval()
     blk = model.processer_list[7]
     from gnn_fluid_dynamics_b200 import processor as P
+    from gnn_fluid_dynamics_b200.ops import Seg
+    from gnn_fluid_dynamics_b200._lib import SEG_GATHER
     x_lat = torch.randn(N, 128, device=dev)
     e_lat = torch.randn(E, 128, device=dev)
-    kev = []
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            if flush is not None:
-                flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            P.edge_mlp_concat(blk.face_block.face_mlp, e_lat, x_lat, topo, model.prec, want_raw=False)
-            b.record()
-            if i >= args.warmup:
-                kev.append((a, b))
-    torch.cuda.synchronize()
-    k_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+    g_lat = torch.randn(E, 128, device=dev)
+    flush_k = flush if flush is not None else torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def time_kernel(fn):
+        ts = []
+        with torch.no_grad():
+            for i in range(args.warmup + args.steps):
+                flush_k.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                if i >= args.warmup:
+                    ts.append((a, b))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ts) / len(ts)
+
     hbm_peak, peak_kind = peaks()
+    w_edge = P.weights_of(blk.face_block.face_mlp)
+    esegs = [Seg(e_lat), Seg(x_lat, SEG_GATHER, (topo.row,)), Seg(x_lat, SEG_GATHER, (topo.col,))]
+    k_ms = time_kernel(lambda: P.edge_mlp_concat(blk.face_block.face_mlp, e_lat, x_lat, topo, model.prec, want_raw=False))
     alg = algorithmic_bytes_edge_kernel(E, N)
-    traffic, traffic_src = ncu_traffic(args.workload)
-    achieved = alg / (k_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic("edge_fwd")
+    fwd_roof = {"kernel": "mlp_tc_kernel<BWD=0>: fused edge block forward (gather + 3-layer MLP + LayerNorm + residual), inference",
+                "bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": alg / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_kind": peak_kind, "kernel_ms": k_ms, "algorithmic_bytes": alg}
+    roofline, other = fwd_roof, []
+    if train:
+        _, _, st = ops.mlp_forward(esegs, w_edge, E, model.prec, residual=e_lat, want_raw=False, want_sum=True, stash=True)
+        packs = {}
+        c_ms = time_kernel(lambda: ops.dgrad_chain(w_edge, st, g_lat, 128, model.prec, residual=g_lat, pack_cache=packs))
+        c_alg = 512 * 7 * E                       # read dy, a2, a1, residual; write dA2, dA1, dIn0
+        c_traffic, c_src = ncu_traffic("edge_chain")
+        roofline = {"kernel": "mlp_tc_kernel<BWD=1>: dgrad chain of the fused edge block (largest single launch of the training step)",
+                    "bound": "hbm", "achieved": c_alg / (c_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": c_alg / (c_ms * 1e-3) / 1e9 / hbm_peak, "traffic": c_traffic, "traffic_source": c_src,
+                    "peak_kind": peak_kind, "kernel_ms": c_ms, "algorithmic_bytes": c_alg}
+        s_ms = time_kernel(lambda: ops.mlp_forward(esegs, w_edge, E, model.prec, residual=e_lat, want_raw=False, want_sum=True, stash=True))
+        s_alg = alg + 512 * 3 * E + 4 * E          # + stash a1, a2, x-hat, rstd
+        wout = torch.empty(128, 128, device=dev)
+        w_ms = time_kernel(lambda: ops.wgrad(Seg(g_lat), [Seg(st.a1)], E, wout, b_act=1))
+        w_alg = 512 * 2 * E
+        wout3 = torch.empty(128, 384, device=dev)
+        w1_ms = time_kernel(lambda: ops.wgrad(Seg(g_lat), esegs, E, wout3))
+        other = [fwd_roof,
+                 {"kernel": "mlp_tc_kernel<BWD=0>: fused edge block forward + training stash", "kernel_ms": s_ms,
+                  "algorithmic_bytes": s_alg, "achieved": s_alg / (s_ms * 1e-3) / 1e9, "frac": s_alg / (s_ms * 1e-3) / 1e9 / hbm_peak},
+                 {"kernel": "wgrad_tc_kernel<2>: dW = dA^T SiLU(a) (tcgen05 tf32, MN-major)", "kernel_ms": w_ms,
+                  "algorithmic_bytes": w_alg, "achieved": w_alg / (w_ms * 1e-3) / 1e9, "frac": w_alg / (w_ms * 1e-3) / 1e9 / hbm_peak},
+                 {"kernel": "wgrad_tc_kernel<4>: dW1 = dA1^T [e | x[row] | x[col]] (gathered operand)", "kernel_ms": w1_ms,
+                  "algorithmic_bytes": alg, "achieved": alg / (w1_ms * 1e-3) / 1e9, "frac": alg / (w1_ms * 1e-3) / 1e9 / hbm_peak}]
 
     # ---- max over ranks, aggregate -------------------------------------------------------------------
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -384,11 +421,7 @@ def main():
                             if train else "model.forward(graphs, mode='train') from pinned host graphs")},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "fused edge block (gather + 3-layer MLP + LayerNorm + residual)",
-                         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_kind": peak_kind,
-                         "kernel_ms": k_ms, "algorithmic_bytes": alg},
+            "roofline": roofline, "roofline_other_kernels": other,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

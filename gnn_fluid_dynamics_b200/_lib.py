@@ -112,7 +112,7 @@ def _load():
     lib.gnnfd_mlp_backward_workspace_bytes.restype = C.c_size_t
     lib.gnnfd_pack_mlp_backward_bytes.argtypes = [C.POINTER(MlpArgs)]
     lib.gnnfd_pack_mlp_backward_bytes.restype = C.c_size_t
-    lib.gnnfd_pack_mlp_backward.argtypes = [C.POINTER(MlpArgs), vp, vp]
+    lib.gnnfd_pack_mlp_backward.argtypes = [C.POINTER(MlpArgs), vp, i32, vp]
     lib.gnnfd_mlp_backward.argtypes = [C.POINTER(MlpBackwardArgs), vp]
     for which, mirror in ((0, MlpArgs), (1, WgradArgs), (2, Segment), (3, MlpBackwardArgs)):
         if lib.gnnfd_struct_size(which) != C.sizeof(mirror):

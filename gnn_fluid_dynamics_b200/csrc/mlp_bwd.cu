@@ -80,7 +80,7 @@ extern "C" size_t gnnfd_pack_mlp_backward_bytes(const gnnfd_mlp_args *fwd) {
   return bwd_layout(fwd).pk_total + 256;
 }
 
-extern "C" int gnnfd_pack_mlp_backward(const gnnfd_mlp_args *f, void *packed_out, void *stream) {
+extern "C" int gnnfd_pack_mlp_backward(const gnnfd_mlp_args *f, void *packed_out, int32_t chain, void *stream) {
   GNNFD_CHECK_ARG(f != nullptr && packed_out != nullptr, "null argument");
   GNNFD_CHECK_ARG(f->precision != GNNFD_PREC_F32, "the backward needs a tensor-core precision");
   const BwdLayout L = bwd_layout(f);
@@ -88,21 +88,26 @@ extern "C" int gnnfd_pack_mlp_backward(const gnnfd_mlp_args *f, void *packed_out
   gnnfd_mlp_args a;
   float dummy_out;
   int rc;
-  chain_args(a, f, f->w3);
-  a.hid_mul1 = a.hid_mul2 = f->w3;
-  a.out_raw = &dummy_out;
-  if ((rc = gnnfd_pack_mlp(&a, pk + L.pk_chain, stream)) != GNNFD_OK) return rc;
-  linear_args(a, f, f->w3, f->n_out, f->n_out, f->w3, 1, 128, 128);       // dH2 = dy . W3
-  a.out_raw = &dummy_out;
-  if ((rc = gnnfd_pack_mlp(&a, pk + L.pk_w3t, stream)) != GNNFD_OK) return rc;
-  linear_args(a, f, f->w2, 128, 128, f->w2, 1, 128, 128);                 // dH1 = dA2 . W2
-  a.out_raw = &dummy_out;
-  if ((rc = gnnfd_pack_mlp(&a, pk + L.pk_w2t, stream)) != GNNFD_OK) return rc;
+  if (chain) {                                                             // one 3-layer pass incl. dIn_0
+    chain_args(a, f, f->w3);
+    a.hid_mul1 = a.hid_mul2 = f->w3;
+    a.out_raw = &dummy_out;
+    if ((rc = gnnfd_pack_mlp(&a, pk + L.pk_chain, stream)) != GNNFD_OK) return rc;
+  } else {
+    linear_args(a, f, f->w3, f->n_out, f->n_out, f->w3, 1, 128, 128);     // dH2 = dy . W3
+    a.out_raw = &dummy_out;
+    if ((rc = gnnfd_pack_mlp(&a, pk + L.pk_w3t, stream)) != GNNFD_OK) return rc;
+    linear_args(a, f, f->w2, 128, 128, f->w2, 1, 128, 128);               // dH1 = dA2 . W2
+    a.out_raw = &dummy_out;
+    if ((rc = gnnfd_pack_mlp(&a, pk + L.pk_w2t, stream)) != GNNFD_OK) return rc;
+  }
   int col0 = 0;
   for (int s = 0; s < f->n_seg; ++s) {                                    // dIn_s = dA1 . W1[:, col0:col0+width]
-    linear_args(a, f, f->w1, 128, 128, f->w1 + col0, 1, f->k_in, f->seg[s].width);
-    a.out_raw = &dummy_out;
-    if ((rc = gnnfd_pack_mlp(&a, pk + L.pk_w1t[s], stream)) != GNNFD_OK) return rc;
+    if (!(chain && s == 0)) {
+      linear_args(a, f, f->w1, 128, 128, f->w1 + col0, 1, f->k_in, f->seg[s].width);
+      a.out_raw = &dummy_out;
+      if ((rc = gnnfd_pack_mlp(&a, pk + L.pk_w1t[s], stream)) != GNNFD_OK) return rc;
+    }
     col0 += f->seg[s].width;
   }
   return GNNFD_OK;

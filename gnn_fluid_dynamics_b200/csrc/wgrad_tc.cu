@@ -75,10 +75,7 @@ __device__ __forceinline__ float to_tf32(float x) {   // round to nearest (the t
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
-__device__ __forceinline__ float wg_act(float v, int act) {
-  if (act == 1) return v * rcp_ftz(1.0f + ex2_ftz(v * -1.4426950408889634f));
-  return tanhf(v);
-}
+__device__ __forceinline__ float wg_silu(float v) { return v * rcp_ftz(1.0f + ex2_ftz(v * -1.4426950408889634f)); }
 
 // one (row, piece) item: the lane's float4 of the assembled operand row (zero outside the matrix / the width)
 __device__ __forceinline__ float4 wg_load_item(const WgPiece &pc, int lane, bool row_ok, int64_t g, int32_t i0,
@@ -159,6 +156,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 16 * j;
       return (q < p.n_slots && it < n_stage_iters && g < r_end) ? __ldg(p.slot[q] + g) : 0;
     };
+    // per-piece constants hoisted out of the stage loop (pi is a compile-time index after unrolling)
+    const float *base[NP];
+    int32_t ldp[NP];
+    uint32_t off0[NP];
+    bool lane_on[NP], fast[NP];
+#pragma unroll
+    for (int pi = 0; pi < NP; ++pi) {
+      const WgPiece &pc = p.pc[pi];
+      const int natoms = pi == 0 ? 4 : nb_atoms;
+      if (NP < 4) { base[pi] = pc.src + pc.col + lane * 4; ldp[pi] = pc.ld; }   // NP == 4: recomputed on use (register budget)
+      lane_on[pi] = lane * 4 < ((pc.width + 31) & ~31);
+      fast[pi] = pc.vec && pc.mode <= GNNFD_SEG_GATHER && (pc.width & 31) == 0;   // whole atoms, 16-byte loads
+      // stage row r = warp + 16 j: r & 3 == warp & 3, r >> 2 == (warp >> 2) + 4 j
+      off0[pi] = (uint32_t)(((warp >> 2) * natoms + pc.atom0 + (lane >> 3)) * 512 + (warp & 3) * 128 +
+                            (((((lane & 7) >> 1) ^ (warp & 3))) << 5) + ((lane & 1) << 4));
+    }
     auto load_stage = [&](int it, int32_t idx, float4(&v)[NP][2]) {
 #pragma unroll
       for (int pi = 0; pi < NP; ++pi) {
@@ -166,13 +179,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 16 * j;
-          int32_t i0 = 0, i1 = 0, i2 = 0;
-          if (pc.mode != GNNFD_SEG_DIRECT) {     // uniform per piece
-            i0 = __shfl_sync(0xffffffffu, idx, (pc.slot0 & 15) * 2 + j);
-            if (pc.mode >= GNNFD_SEG_SUM2) i1 = __shfl_sync(0xffffffffu, idx, ((pc.slot0 + 1) & 15) * 2 + j);
-            if (pc.mode == GNNFD_SEG_MEAN3) i2 = __shfl_sync(0xffffffffu, idx, ((pc.slot0 + 2) & 15) * 2 + j);
+          const bool row_ok = it < n_stage_iters && g < r_end;
+          if (fast[pi]) {
+            int64_t r0 = g;
+            if (pc.mode == GNNFD_SEG_GATHER) r0 = __shfl_sync(0xffffffffu, idx, (pc.slot0 & 15) * 2 + j);
+            const float *bp = NP < 4 ? base[pi] : pc.src + pc.col + lane * 4;
+            const int64_t ldv = NP < 4 ? ldp[pi] : pc.ld;
+            v[pi][j] = (row_ok && lane_on[pi]) ? ldg_f4(bp + r0 * ldv) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+            int32_t i0 = 0, i1 = 0, i2 = 0;
+            if (pc.mode != GNNFD_SEG_DIRECT) {     // uniform per piece
+              i0 = __shfl_sync(0xffffffffu, idx, (pc.slot0 & 15) * 2 + j);
+              if (pc.mode >= GNNFD_SEG_SUM2) i1 = __shfl_sync(0xffffffffu, idx, ((pc.slot0 + 1) & 15) * 2 + j);
+              if (pc.mode == GNNFD_SEG_MEAN3) i2 = __shfl_sync(0xffffffffu, idx, ((pc.slot0 + 2) & 15) * 2 + j);
+            }
+            v[pi][j] = wg_load_item(pc, lane, row_ok, g, i0, i1, i2);
           }
-          v[pi][j] = wg_load_item(pc, lane, it < n_stage_iters && g < r_end, g, i0, i1, i2);
         }
       }
     };
@@ -183,23 +205,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (it >= p.stages) mbar_wait(&empty[st], ((it / p.stages) - 1) & 1);
 #pragma unroll
       for (int pi = 0; pi < NP; ++pi) {
-        const WgPiece &pc = p.pc[pi];
-        const int wpad = (pc.width + 31) & ~31;
-        if (lane * 4 < wpad) {
-          uint8_t *img = pi == 0 ? sA : sB;
-          const int natoms = pi == 0 ? 4 : nb_atoms;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            float4 t = v[pi][j];
-            if (pi == p.colsum_piece) { cs.x += t.x; cs.y += t.y; cs.z += t.z; cs.w += t.w; }
-            if (pc.act) { t.x = wg_act(t.x, pc.act); t.y = wg_act(t.y, pc.act); t.z = wg_act(t.z, pc.act); t.w = wg_act(t.w, pc.act); }
-            t.x = to_tf32(t.x); t.y = to_tf32(t.y); t.z = to_tf32(t.z); t.w = to_tf32(t.w);
-            // stage row r = warp + 16 j: r & 3 == warp & 3, r >> 2 == (warp >> 2) + 4 j
-            const uint32_t off = (uint32_t)((((warp >> 2) + 4 * j) * natoms + pc.atom0 + (lane >> 3)) * 512 +
-                                            (warp & 3) * 128 + (((((lane & 7) >> 1) ^ (warp & 3))) << 5) +
-                                            ((lane & 1) << 4));
-            *reinterpret_cast<float4 *>(img + off) = t;
+        if (lane_on[pi]) {
+          const int act = p.pc[pi].act;
+          uint8_t *img = (pi == 0 ? sA : sB) + off0[pi];
+          float4 t0 = v[pi][0], t1 = v[pi][1];
+          if (pi == p.colsum_piece) {
+            cs.x += t0.x + t1.x; cs.y += t0.y + t1.y; cs.z += t0.z + t1.z; cs.w += t0.w + t1.w;
           }
+          if (act == 1) {        // SiLU of a saved pre-activation (uniform branch, 8 independent MUFU chains)
+            t0.x = wg_silu(t0.x); t0.y = wg_silu(t0.y); t0.z = wg_silu(t0.z); t0.w = wg_silu(t0.w);
+            t1.x = wg_silu(t1.x); t1.y = wg_silu(t1.y); t1.z = wg_silu(t1.z); t1.w = wg_silu(t1.w);
+          } else if (act == 2) {
+            t0.x = tanhf(t0.x); t0.y = tanhf(t0.y); t0.z = tanhf(t0.z); t0.w = tanhf(t0.w);
+            t1.x = tanhf(t1.x); t1.y = tanhf(t1.y); t1.z = tanhf(t1.z); t1.w = tanhf(t1.w);
+          }
+          t0.x = to_tf32(t0.x); t0.y = to_tf32(t0.y); t0.z = to_tf32(t0.z); t0.w = to_tf32(t0.w);
+          t1.x = to_tf32(t1.x); t1.y = to_tf32(t1.y); t1.z = to_tf32(t1.z); t1.w = to_tf32(t1.w);
+          *reinterpret_cast<float4 *>(img) = t0;
+          *reinterpret_cast<float4 *>(img + (pi == 0 ? 4 : nb_atoms) * 2048) = t1;   // row + 16 = 4 K atoms further
         }
       }
       fence_proxy_async();

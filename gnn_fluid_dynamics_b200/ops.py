@@ -285,12 +285,13 @@ def mlp_backward(segs: Sequence[Seg], w: MLPWeights, st: "MLPStash", rows: int, 
     b = MlpBackwardArgs()
     keep = _fill_args(b.fwd, segs, w, rows, precision)
     dev = w.w1.device
-    if w.bwd_packs is None or w.bwd_packs.get("prec") != precision:
+    chain = int(len(din) > 0 and din[0] is not None)
+    if w.bwd_packs is None or w.bwd_packs.get("key") != (precision, chain):
         nbytes = lib.gnnfd_pack_mlp_backward_bytes(C.byref(b.fwd))
         pk = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        check(lib.gnnfd_pack_mlp_backward(C.byref(b.fwd), pk.data_ptr(), _stream()), "gnnfd_pack_mlp_backward")
-        _count(2 + len(segs))
-        w.bwd_packs = {"prec": precision, "pack": pk}
+        check(lib.gnnfd_pack_mlp_backward(C.byref(b.fwd), pk.data_ptr(), chain, _stream()), "gnnfd_pack_mlp_backward")
+        _count(len(segs) if chain else 2 + len(segs))
+        w.bwd_packs = {"key": (precision, chain), "pack": pk}
     b.packed_bwd = w.bwd_packs["pack"].data_ptr()
     g = _req(g.contiguous(), torch.float32, "g")
     b.g = g.data_ptr()
@@ -326,6 +327,44 @@ def mlp_backward(segs: Sequence[Seg], w: MLPWeights, st: "MLPStash", rows: int, 
     _count((2 if w.has_ln else 0) + 6 + 2 + sum(1 for d in dins if d is not None))
     del keep
     return grads, dins
+
+
+def dgrad_chain(w: MLPWeights, st: "MLPStash", dy: torch.Tensor, seg0_width: int, precision: int,
+                residual: Optional[torch.Tensor] = None, pack_cache: Optional[dict] = None):
+    """The dgrad chain of one MLP as ONE tensor-core pass (gnnfd_mlp_forward with bwd_chain = 1):
+    dA2 = (dy W3) * act'(a2), dA1 = (dA2 W2) * act'(a1), dIn0 = dA1 W1[:, 0:seg0_width] (+ residual).
+    Returns (dIn0, dA2, dA1).  gnnfd_mlp_backward issues exactly this launch; exposed for tests and profiling."""
+    dy = _req(dy, torch.float32, "dy")
+    rows, n_out, k_in = dy.shape[0], w.w3.shape[0], w.w1.shape[1]
+    dev = dy.device
+    args = MlpArgs()
+    args.rows, args.n_seg = rows, 1
+    _fill_segment(args.seg[0], Seg(dy), "dy")
+    args.k_in, args.hidden, args.n_out = n_out, 128, 128
+    args.w1, args.w1_ld_n, args.w1_ld_k, args.w1_rows = w.w3.data_ptr(), 1, 128, 128
+    args.w2, args.w2_ld_n, args.w2_ld_k = w.w2.data_ptr(), 1, 128
+    args.w3, args.w3_ld_n, args.w3_ld_k, args.w3_rows = w.w1.data_ptr(), 1, k_in, seg0_width
+    args.act, args.precision, args.n_layers, args.bwd_chain = w.act, precision, 3, 1
+    args.hid_mul1, args.hid_mul2 = st.a2.data_ptr(), st.a1.data_ptr()
+    d_a2 = torch.empty(rows, 128, dtype=torch.float32, device=dev)
+    d_a1 = torch.empty(rows, 128, dtype=torch.float32, device=dev)
+    out = torch.empty(rows, 128, dtype=torch.float32, device=dev)
+    args.save_a1, args.save_a2 = d_a2.data_ptr(), d_a1.data_ptr()
+    if residual is not None:
+        args.residual, args.out_sum = _req(residual, torch.float32, "residual").data_ptr(), out.data_ptr()
+    else:
+        args.out_raw = out.data_ptr()
+    cache = pack_cache if pack_cache is not None else {}
+    pk = cache.get(("chain", precision))
+    if pk is None:
+        pk = torch.empty(lib.gnnfd_pack_mlp_bytes(n_out, 128, 128, precision), dtype=torch.uint8, device=dev)
+        check(lib.gnnfd_pack_mlp(C.byref(args), pk.data_ptr(), _stream()), "gnnfd_pack_mlp")
+        _count(1)
+        cache[("chain", precision)] = pk
+    args.packed = pk.data_ptr()
+    check(lib.gnnfd_mlp_forward(C.byref(args), _stream()), "gnnfd_mlp_forward")
+    _count(1)
+    return out, d_a2, d_a1
 
 
 def ln_backward(g: torch.Tensor, xhat: torch.Tensor, rstd: torch.Tensor, ln_w: Optional[torch.Tensor]):

@@ -225,7 +225,9 @@ typedef struct {
 } gnnfd_mlp_backward_args;
 size_t gnnfd_mlp_backward_workspace_bytes(const gnnfd_mlp_args *fwd);
 size_t gnnfd_pack_mlp_backward_bytes(const gnnfd_mlp_args *fwd);
-int gnnfd_pack_mlp_backward(const gnnfd_mlp_args *fwd, void *packed_out, void *stream);
+int gnnfd_pack_mlp_backward(const gnnfd_mlp_args *fwd, void *packed_out,
+                            int32_t chain /* 1: the call will request din_out[0] (fused chain); 0: it will not */,
+                            void *stream);
 int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *args, void *stream);
 
 /* Transpose of a gather = deterministic segment sum with up to three source parts, a scale and a base:

@@ -243,3 +243,24 @@ def test_fused_backward_call_equals_stepwise_schedule():
         if p is not None:
             assert rel_l2(p, q) < 2e-5, rel_l2(p, q)
     assert rel_l2(da[0], db[0]) < 2e-5 and rel_l2(da[1], db[1]) < 2e-5 and da[2] is None and db[2] is None
+
+
+def test_backward_entry_points_handle_empty_and_tiny_inputs():
+    """rows = 0 (an empty mesh partition) and rows = 1: statuses, zero gradients, no launch faults."""
+    from gnn_fluid_dynamics_b200 import ops, _lib, training
+    from test_gpu_parity import _rand_mlp, _to_weights
+    w = _to_weights(_rand_mlp(128, 128, True, seed=4), _lib.ACT_SILU)
+    for rows in (0, 1):
+        x = torch.randn(rows, 128, device=dev())
+        segs = [ops.Seg(x)]
+        _, _, st = ops.mlp_forward(segs, w, rows, _lib.PREC_BF16X3, stash=True)
+        ws = ops.mlp_backward_workspace(max(rows, 1), dev())
+        grads, dins = training.mlp_backward(w, st, segs, rows, torch.randn(rows, 128, device=dev()), _lib.PREC_BF16X3, [{}], ws)
+        torch.cuda.synchronize()
+        assert all(torch.isfinite(g).all() for g in grads if g is not None)
+        if rows == 0:
+            assert all(float(g.abs().sum()) == 0.0 for g in grads if g is not None)
+        assert dins[0].shape == (rows, 128)
+    out = torch.empty(128, 128, device=dev())
+    ops.wgrad(ops.Seg(torch.empty(0, 128, device=dev())), [ops.Seg(torch.empty(0, 128, device=dev()))], 0, out)
+    assert float(out.abs().sum()) == 0.0
