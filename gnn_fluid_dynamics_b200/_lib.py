@@ -25,7 +25,7 @@ EXPORTS = [
     "gnnfd_ln_backward_workspace_bytes", "gnnfd_ln_backward", "gnnfd_wgrad_workspace_bytes", "gnnfd_wgrad",
     "gnnfd_segment_sum3", "gnnfd_gather_pair_add", "gnnfd_struct_size",
     "gnnfd_mlp_backward_workspace_bytes", "gnnfd_pack_mlp_backward_bytes", "gnnfd_pack_mlp_backward",
-    "gnnfd_mlp_backward", "gnnfd_gather_rows",
+    "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access",
 ]
 ABI_VERSION = 2
 
@@ -50,6 +50,7 @@ class MlpArgs(C.Structure):
         ("bwd_chain", C.c_int32), ("hid_mul1", C.c_void_p), ("hid_mul2", C.c_void_p),
         ("w2_ld_n", C.c_int32), ("w2_ld_k", C.c_int32), ("w3_ld_n", C.c_int32), ("w3_ld_k", C.c_int32),
         ("w3_rows", C.c_int32),
+        ("peer_base", C.c_void_p * 8), ("peer_shift", C.c_int32),
     ]
 
 
@@ -106,6 +107,7 @@ def _load():
                                        vp, i32, vp]
     lib.gnnfd_gather_pair_add.argtypes = [vp, vp, vp, i32, vp, vp, f32, i32, i64, vp]
     lib.gnnfd_gather_rows.argtypes = [vp, i32, vp, i64, i32, vp, vp]
+    lib.gnnfd_enable_peer_access.argtypes = [i32]
     lib.gnnfd_struct_size.argtypes = [i32]
     lib.gnnfd_struct_size.restype = C.c_size_t
     lib.gnnfd_mlp_backward_workspace_bytes.argtypes = [C.POINTER(MlpArgs)]

@@ -36,3 +36,16 @@ extern "C" int gnnfd_gather_rows(const float *src, int32_t ld, const int32_t *id
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }
+
+extern "C" int gnnfd_enable_peer_access(int32_t peer_device) {
+  int dev = 0;
+  GNNFD_CUDA(cudaGetDevice(&dev));
+  if (dev == peer_device) return GNNFD_OK;
+  int can = 0;
+  GNNFD_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  if (!can) { set_error("gnnfd_enable_peer_access: device %d cannot access device %d", dev, peer_device); return GNNFD_E_UNSUPPORTED; }
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return GNNFD_OK; }
+  if (e != cudaSuccess) { set_error("gnnfd_enable_peer_access: %s", cudaGetErrorString(e)); return GNNFD_E_CUDA; }
+  return GNNFD_OK;
+}

@@ -38,6 +38,16 @@ int validate_mlp_args(const gnnfd_mlp_args *a) {
     GNNFD_CHECK_ARG(a->w1 && a->w2 && a->w3, "null weight");
   }
   GNNFD_CHECK_ARG(a->mul_mode >= 0 && a->mul_mode <= 2, "bad mul_mode");
+  GNNFD_CHECK_ARG(a->peer_shift >= 0 && a->peer_shift < 31, "bad peer_shift");
+  if (a->peer_shift > 0) {
+    GNNFD_CHECK_ARG(a->precision != GNNFD_PREC_F32, "peer-memory gathers need a tensor-core precision");
+    for (int s = 0; s < a->n_seg; ++s)
+      if (a->seg[s].mode == GNNFD_SEG_GATHER)
+        GNNFD_CHECK_ARG((a->seg[s].width & 63) == 0 && (a->seg[s].ld & 3) == 0 && (a->seg[s].col & 3) == 0,
+                        "peer-memory gather segments must be 64-column multiples with 16-byte aligned rows");
+      else
+        GNNFD_CHECK_ARG(a->seg[s].mode == GNNFD_SEG_DIRECT, "with peer_shift only DIRECT and GATHER segments are supported");
+  }
   if (a->bwd_chain) {
     GNNFD_CHECK_ARG(a->n_layers != 1 && a->n_out == 128 && !a->has_ln && a->precision != GNNFD_PREC_F32,
                     "bwd_chain needs the 3-layer tensor-core path, n_out == 128 and no LayerNorm");

@@ -146,8 +146,17 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + min(row0 + rbase + 16 * jj, last) * ld);
   } else if (d.mode == GNNFD_SEG_GATHER) {
+    if (p.a.peer_shift > 0) {   // rows of ghost cells come straight from the owning GPU's HBM (P2P over NVLink)
+      const uint32_t mask = (1u << p.a.peer_shift) - 1u;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + (int64_t)ixs[16 * jj] * ld);
+      for (int jj = 0; jj < 8; ++jj) {
+        const uint32_t i = (uint32_t)ixs[16 * jj];
+        v[jj] = ldg_f4(p.a.peer_base[i >> p.a.peer_shift] + d.colk + f4 * 4 + (int64_t)(i & mask) * ld);
+      }
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + (int64_t)ixs[16 * jj] * ld);
+    }
   } else if (d.mode == GNNFD_SEG_MEAN3) {
 #pragma unroll
     for (int h = 0; h < 4; ++h) {

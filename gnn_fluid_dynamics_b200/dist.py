@@ -177,7 +177,9 @@ class PartitionedRollout:
     ``local_graphs[k]`` is partition k's [c_graph, f_graph, v_graph] on its device (``partition.local_graphs``);
     under torch.distributed each process holds exactly one partition."""
 
-    def __init__(self, model, parts: Sequence[Partition], local_graphs: Sequence[list], transport):
+    def __init__(self, model, parts: Sequence[Partition], local_graphs: Sequence[list], transport, peer=None):
+        """``peer`` = (PeerBuffers, row_enc, col_enc) switches the per-block halo from NCCL send/receive to
+        peer-memory gathers inside the fused edge kernel (one partition per process only)."""
         from .graph import Data
         from .topology import MeshTopology
         if model.family not in ("mgn", "fvgn"):
@@ -189,6 +191,9 @@ class PartitionedRollout:
             topo = MeshTopology.from_graphs(g).validate()
             self.states.append(PartState(part=p, topo=topo).device_plan(g[0].x.device))
         self._Data = Data
+        self.peer = peer
+        if peer is not None and len(self.states) != 1:
+            raise RuntimeError("peer-memory halo runs one partition per process")
 
     @torch.no_grad()
     def step(self):
@@ -199,7 +204,18 @@ class PartitionedRollout:
             gn = model.normalizer.input([t.clone() for t in g])
             norm.append(gn)
             inputs.append((gn[0].x, gn[1].x))
-        outs = encode_process_decode_partitioned(model, self.states, inputs, self.transport)
+        if self.peer is None:
+            outs = encode_process_decode_partitioned(model, self.states, inputs, self.transport)
+        else:
+            from . import processor as P
+            bufs, row_enc, col_enc = self.peer
+            (s,), ((c_x, f_x),) = self.states, inputs
+            n_own = s.part.n_owned
+            e0 = P.mlp_rows(model.encoder.face_mlp, f_x, model.prec)
+            x0 = P.mlp_rows(model.encoder.cell_mlp, c_x[:n_own], model.prec)      # ghosts are never materialised
+            x, e = run_processor_peer(model.family, model.processer_list, s, x0, e0, bufs, row_enc, col_enc, model.prec)
+            dec = P.mlp_rows(model.decoder.face_mlp, x if model.family == "mgn" else e, model.prec)
+            outs = [(x, e, dec)]
         vels = []
         for s, g, gn, (_, _, dec) in zip(self.states, self.graphs, norm, outs):
             n_own = s.part.n_owned
@@ -224,3 +240,103 @@ class PartitionedRollout:
                 mask = ((f.type == 2) | (f.type == 1)).squeeze(-1)
             f.x[:, 0:2] = torch.where(mask.unsqueeze(-1), f.y[:, 0:2], dv)
         return vels
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Peer-memory halo: no exchange step at all.  The cell latents of every rank live in buffers that all ranks map
+# (CUDA IPC, NVLink P2P); the fused edge kernel gathers x[row] / x[col] of ghost cells straight from the owning
+# GPU's HBM while it computes (gnnfd_mlp_args.peer_base / peer_shift), tile by tile, so the transfer overlaps
+# the MMA work and ghost rows are never materialised locally.  One cross-rank barrier per GN_Block orders
+# "owner wrote block i's rows" before "peers read them"; the latents are double-buffered so the next block's
+# writes cannot race the previous block's remote reads.
+
+PEER_SHIFT = 28          # gather index = (owner rank << 28) | row in the owner's buffer
+
+
+class PeerBuffers:
+    """``n_buffers`` matrices [n_rows, width] per rank, each mapped into every process of the group."""
+
+    def __init__(self, n_rows: int, width: int, device, world: int, rank: int, n_buffers: int = 2, group=None):
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        from ._lib import check, lib
+        self.world, self.rank = world, rank
+        self.local = [torch.zeros(max(n_rows, 1), width, dtype=torch.float32, device=device) for _ in range(n_buffers)]
+        payload = [reduce_tensor(t) for t in self.local]                  # CUDA IPC handles (picklable)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, payload, group=group)
+        self.views = []                                                    # views[buffer][rank] -> tensor
+        for b in range(n_buffers):
+            row = []
+            for r in range(world):
+                if r == rank:
+                    row.append(self.local[b])
+                else:
+                    fn, fargs = gathered[r][b]
+                    fargs = list(fargs)
+                    owner_device = fargs[6]
+                    # open the handle with THIS rank's device current (cudaIpcOpenMemHandle + lazy peer access maps the
+                    # owner's memory for the opening device); the tensor is then "on" our device but lives in the
+                    # owner's HBM and every access crosses NVLink
+                    fargs[6] = device.index
+                    check(lib.gnnfd_enable_peer_access(owner_device), "gnnfd_enable_peer_access")
+                    row.append(fn(*fargs))
+            self.views.append(row)
+        self._flag = torch.zeros(1, device=device)
+        self._dist, self._group = dist, group
+        dist.barrier(group=group)
+
+    def barrier(self):
+        """Stream-ordered cross-rank barrier: every rank's prior kernels are complete before any rank's later
+        kernels start (a 1-element NCCL all-reduce on the current stream)."""
+        self._dist.all_reduce(self._flag, group=self._group)
+
+
+def peer_indices(part: Partition, parts_send: dict, device) -> tuple:
+    """Peer-encoded copies of the partition's cell indices: local cell c < n_owned -> (rank << S) | c; ghost from
+    peer a at position k of its receive range -> (a << S) | (row of that cell in a's buffer).  ``parts_send[a]`` is
+    partition a's send list towards this rank (== the rows this rank's ghosts occupy in a's buffer)."""
+    enc = torch.empty(part.n_local, dtype=torch.int64)
+    enc[:part.n_owned] = (part.rank << PEER_SHIFT) | torch.arange(part.n_owned)
+    for peer, (start, cnt) in part.recv.items():
+        enc[start:start + cnt] = (peer << PEER_SHIFT) | parts_send[peer]
+    row = enc[part.c_edge_index[0]].to(torch.int32).to(device)
+    col = enc[part.c_edge_index[1]].to(torch.int32).to(device)
+    return row, col
+
+
+def run_processor_peer(family: str, blocks, state: PartState, x0_owned: torch.Tensor, e0: torch.Tensor,
+                       bufs: PeerBuffers, row_enc: torch.Tensor, col_enc: torch.Tensor, prec: int):
+    """GN_Blocks of one partition with peer-memory gathers (one process per GPU).  ``x0_owned`` = encoded owned
+    cells, ``e0`` = encoded local faces.  Returns (x[n_owned], e[E_loc])."""
+    if family not in ("mgn", "fvgn"):
+        raise NotImplementedError(f"peer-memory halo covers the 'mgn' and 'fvgn' data-flows, not {family!r}")
+    topo, n_own = state.topo, state.part.n_owned
+    e = e0
+    if family == "mgn":
+        bufs.local[0][:n_own].copy_(x0_owned)
+        bufs.barrier()
+        for i, blk in enumerate(blocks):
+            we, wn = weights_of(blk.face_block.face_mlp), weights_of(blk.cell_block.cell_mlp)
+            cur, nxt = i % 2, (i + 1) % 2
+            x_cur = bufs.local[cur]
+            segs = [Seg(e), Seg(x_cur, SEG_GATHER, (row_enc,)), Seg(x_cur, SEG_GATHER, (col_enc,))]
+            e_raw, e = ops.mlp_forward(segs, we, e.shape[0], prec, residual=e, want_raw=True, want_sum=True,
+                                       peer=(bufs.views[cur], PEER_SHIFT))
+            vsum = ops.segment_sum(e_raw, e_raw, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices)
+            ops.mlp_forward([Seg(x_cur), Seg(vsum, SEG_MEAN3, topo.vf)], wn, n_own, prec, residual=x_cur,
+                            want_raw=False, want_sum=True, out_sum=bufs.local[nxt])
+            bufs.barrier()
+        return bufs.local[len(blocks) % 2][:n_own], e
+    x = x0_owned
+    for i, blk in enumerate(blocks):
+        we, wn = weights_of(blk.face_block.face_mlp), weights_of(blk.cell_block.cell_mlp)
+        raw = bufs.local[i % 2]
+        vsum = ops.segment_sum(e, e, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices)
+        _, x = ops.mlp_forward([Seg(x), Seg(vsum, SEG_MEAN3, topo.vf)], wn, n_own, prec, residual=x,
+                               want_raw=True, want_sum=True, out_raw=raw)
+        bufs.barrier()
+        segs = [Seg(e), Seg(raw, SEG_GATHER, (row_enc,)), Seg(raw, SEG_GATHER, (col_enc,))]
+        _, e = ops.mlp_forward(segs, we, e.shape[0], prec, residual=e, want_raw=False, want_sum=True,
+                               peer=(bufs.views[i % 2], PEER_SHIFT))
+    return x, e

@@ -178,7 +178,7 @@ def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = 
                 mul: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
                 want_raw: bool = True, want_sum: bool = False,
                 out_raw: Optional[torch.Tensor] = None, out_sum: Optional[torch.Tensor] = None,
-                stash: bool = False):
+                stash: bool = False, peer: Optional[tuple] = None):
     """Run the fused block; returns (out_raw or None, out_sum or None) and, with ``stash=True``
     (training), additionally the ``MLPStash`` the backward consumes."""
     args = MlpArgs()
@@ -200,6 +200,11 @@ def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = 
     args.residual = _ptr(_req(residual, torch.float32, "residual")) if residual is not None else None
     args.out_raw = _ptr(out_raw) if want_raw else None
     args.out_sum = _ptr(out_sum) if want_sum else None
+    if peer is not None:          # (peer matrices, shift): GATHER indices are (peer << shift) | row
+        bases, shift = peer
+        for i, t in enumerate(bases):
+            args.peer_base[i] = t.data_ptr() if t is not None else None
+        args.peer_shift = shift
     st = None
     if stash:
         if precision == _lib.PREC_F32:

@@ -126,6 +126,13 @@ typedef struct {
   int32_t bwd_chain;
   const float *hid_mul1, *hid_mul2;
   int32_t w2_ld_n, w2_ld_k, w3_ld_n, w3_ld_k, w3_rows;
+  /* Peer-memory gather (domain-decomposed mesh, one process per GPU): with peer_shift > 0 every GATHER segment
+   * reads row (i & ((1 << peer_shift) - 1)) of the matrix at peer_base[i >> peer_shift] - the latent rows of
+   * ghost cells are loaded straight from the owning GPU's HBM over NVLink (P2P mapped memory) by the kernel
+   * that consumes them, so there is no halo pack / send / receive step (gnn_fluid_dynamics_b200/dist.py).
+   * All peer matrices share the segment's ld / col.  Tensor-core precisions only. */
+  const float *peer_base[8];
+  int32_t peer_shift;
 } gnnfd_mlp_args;
 
 int gnnfd_abi_version(void);
@@ -252,6 +259,10 @@ int gnnfd_gather_pair_add(float *dst, const float *base, const float *src, int32
  * The receive side needs no unpack: ghost rows are stored contiguously per owner rank. */
 int gnnfd_gather_rows(const float *src, int32_t ld, const int32_t *idx, int64_t n, int32_t width, float *out,
                       void *stream);
+
+/* cudaDeviceEnablePeerAccess(peer_device) for the calling thread's current device (already-enabled is not an
+ * error): kernels of this library may then dereference pointers into that device's memory (peer_base). */
+int gnnfd_enable_peer_access(int32_t peer_device);
 
 /* sizeof(gnnfd_mlp_args) (which = 0), sizeof(gnnfd_wgrad_args) (1), sizeof(gnnfd_segment) (2),
  * sizeof(gnnfd_mlp_backward_args) (3): lets a
