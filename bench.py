@@ -385,9 +385,9 @@ def main():
         other = [fwd_roof,
                  {"kernel": "mlp_tc_kernel<BWD=0>: fused edge block forward + training stash", "kernel_ms": s_ms,
                   "algorithmic_bytes": s_alg, "achieved": s_alg / (s_ms * 1e-3) / 1e9, "frac": s_alg / (s_ms * 1e-3) / 1e9 / hbm_peak},
-                 {"kernel": "wgrad_tc_kernel<2>: dW = dA^T SiLU(a) (tcgen05 tf32, MN-major)", "kernel_ms": w_ms,
+                 {"kernel": "wgrad_tc_kernel<2,0>: dW = dA^T SiLU(a) (tcgen05 split-bf16, MN-major operands)", "kernel_ms": w_ms,
                   "algorithmic_bytes": w_alg, "achieved": w_alg / (w_ms * 1e-3) / 1e9, "frac": w_alg / (w_ms * 1e-3) / 1e9 / hbm_peak},
-                 {"kernel": "wgrad_tc_kernel<4>: dW1 = dA1^T [e | x[row] | x[col]] (gathered operand)", "kernel_ms": w1_ms,
+                 {"kernel": "wgrad_tc_kernel<4,0>: dW1 = dA1^T [e | x[row] | x[col]] (gathered operand)", "kernel_ms": w1_ms,
                   "algorithmic_bytes": alg, "achieved": alg / (w1_ms * 1e-3) / 1e9, "frac": alg / (w1_ms * 1e-3) / 1e9 / hbm_peak}]
 
     # ---- max over ranks, aggregate -------------------------------------------------------------------
@@ -416,7 +416,7 @@ def main():
                        "timed": ("forward (encoder + 15 GN_Blocks + decoder + integrator) + loss + backward + grad clip + Adam step"
                                  if train else "encoder + 15 GN_Blocks + decoder"),
                        "forward_only_ms": fwd_ms,
-                       "backward_precision": "dgrad bf16x3, wgrad tf32 (rna operands), fp32 accumulate" if train else None,
+                       "backward_precision": "dgrad and wgrad split-bf16 (bf16x3), fp32 accumulate" if train else None,
                        "l2": "flushed between iterations" if flush is not None else "working set > L2"},
             "e2e": {"value": E_total * MP_NUM / (ms_e2e * 1e-3), "unit": "edge-updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,

@@ -58,7 +58,7 @@ class WgradArgs(C.Structure):
     _fields_ = [
         ("rows", C.c_int64), ("a", Segment), ("a_act", C.c_int32), ("n_b", C.c_int32), ("b", Segment * 3),
         ("b_act", C.c_int32), ("out", C.c_void_p), ("ld_out", C.c_int32), ("transpose_out", C.c_int32),
-        ("colsum", C.c_void_p), ("colsum_of_b", C.c_int32),
+        ("colsum", C.c_void_p), ("colsum_of_b", C.c_int32), ("precision", C.c_int32),
     ]
 
 

@@ -1,4 +1,9 @@
-// Weight-gradient GEMM of the fused MLP block on tcgen05 (kind::tf32, fp32 accumulation in TMEM), sm_100a.
+// Weight-gradient GEMM of the fused MLP block on tcgen05 (fp32 accumulation in TMEM), sm_100a.
+// Two operand precisions (template MODE):
+//   0  split-bf16 (default): every operand staged as hi = bf16(x), lo = bf16(x - hi); kind::f16 products
+//      hi*hi + lo*hi + hi*lo (~1e-5 on dW, same scheme as the forward) - 4 bytes of shared memory per element,
+//      i.e. exactly the footprint of one TF32 image, and the bf16 pipe runs at twice the TF32 rate;
+//   1  single-pass TF32 (operands rounded to nearest; ~3e-4 on dW, up to ~1e-3 for cancellation-heavy sums).
 //
 //   D[128, n] = sum over rows r of  A[r, 0:128]^T  B[r, 0:n]          (dW = dA^T . H, reduction over E or N rows)
 //
@@ -55,6 +60,22 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_by
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)1 << 61;                  // SWIZZLE_128B_BASE32B
   return d;
+}
+// MN-major SWIZZLE_128B descriptor for 16-bit operands: 64-column (128 B) x 8-row atoms of 1024 B, 16-byte chunk c of
+// row r at c ^ (r & 7); LBO = 1024 B between MN atoms, SBO between K atoms (8 rows each)
+__device__ __forceinline__ uint64_t make_desc_mn16(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+  return d;
+}
+// c = F32, a = b = BF16, both MN-major, M = 128
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
 }
 // c = F32, a = b = TF32, both MN-major, M = 128
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int n) {
@@ -116,13 +137,19 @@ __device__ __forceinline__ float4 wg_load_item(const WgPiece &pc, int lane, bool
   return t;
 }
 
-template <int NP>   // pieces: A + (NP - 1) column blocks of B
+// NP = pieces (A + NP - 1 column blocks of B); MODE 0 split-bf16 (two 16-bit images per operand), 1 TF32.
+// Both modes stage 32 rows x 4 bytes per element: A 16 KB + B n_pad * 128 B per stage.
+template <int NP, int MODE>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int nb_atoms = p.n_pad >> 5;
-  const uint32_t a_bytes = 8 * 4 * 512;                         // [8 k-atoms][4 mn-atoms] = 16 KB
-  const uint32_t b_bytes = 8 * (uint32_t)nb_atoms * 512;        // [8 k-atoms][nb mn-atoms]
+  constexpr bool BF = MODE == 0;
+  // MN atoms: TF32 32 columns x 4 rows (512 B), bf16 64 columns x 8 rows (1024 B)
+  const int nb_atoms = BF ? p.n_pad >> 6 : p.n_pad >> 5;
+  const uint32_t a_img = 32 * 128 * 2;                          // bf16: one [32 rows x 128] image = 8 KB
+  const uint32_t b_img = 32 * (uint32_t)p.n_pad * 2;            // bf16: one [32 rows x n_pad] image
+  const uint32_t a_bytes = 16 * 1024;
+  const uint32_t b_bytes = 32 * (uint32_t)p.n_pad * 4;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t *s_tail = smem + (size_t)p.stages * stage_bytes;
   float *s_cs = (float *)s_tail;                                // [16 warps][128] column-sum scratch
@@ -166,11 +193,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       const WgPiece &pc = p.pc[pi];
       const int natoms = pi == 0 ? 4 : nb_atoms;
       if (NP < 4) { base[pi] = pc.src + pc.col + lane * 4; ldp[pi] = pc.ld; }   // NP == 4: recomputed on use (register budget)
-      lane_on[pi] = lane * 4 < ((pc.width + 31) & ~31);
-      fast[pi] = pc.vec && pc.mode <= GNNFD_SEG_GATHER && (pc.width & 31) == 0;   // whole atoms, 16-byte loads
-      // stage row r = warp + 16 j: r & 3 == warp & 3, r >> 2 == (warp >> 2) + 4 j
-      off0[pi] = (uint32_t)(((warp >> 2) * natoms + pc.atom0 + (lane >> 3)) * 512 + (warp & 3) * 128 +
-                            (((((lane & 7) >> 1) ^ (warp & 3))) << 5) + ((lane & 1) << 4));
+      lane_on[pi] = lane * 4 < (BF ? ((pc.width + 63) & ~63) : ((pc.width + 31) & ~31));
+      fast[pi] = pc.vec && pc.mode <= GNNFD_SEG_GATHER && (pc.width & 31) == 0;   // 16-byte loads, no column tail
+      if (BF) {
+        // bf16 image: stage row r = warp + 16 j -> K atom (warp >> 3) + 2 j, row warp & 7 inside the atom; the lane's 4
+        // columns are 8 bytes: MN atom lane >> 4, 16-byte chunk (lane & 15) >> 1 stored at chunk ^ (r & 7), half lane & 1
+        const int na = pi == 0 ? 2 : nb_atoms, a0 = pc.atom0;
+        off0[pi] = (uint32_t)(((warp >> 3) * na + a0 + (lane >> 4)) * 1024 + (warp & 7) * 128 +
+                              (((((lane & 15) >> 1) ^ (warp & 7))) << 4) + ((lane & 1) << 3));
+      } else {
+        // tf32 image: stage row r = warp + 16 j: r & 3 == warp & 3, r >> 2 == (warp >> 2) + 4 j
+        off0[pi] = (uint32_t)(((warp >> 2) * natoms + pc.atom0 + (lane >> 3)) * 512 + (warp & 3) * 128 +
+                              (((((lane & 7) >> 1) ^ (warp & 3))) << 5) + ((lane & 1) << 4));
+      }
     }
     auto load_stage = [&](int it, int32_t idx, float4(&v)[NP][2]) {
 #pragma unroll
@@ -185,7 +220,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             if (pc.mode == GNNFD_SEG_GATHER) r0 = __shfl_sync(0xffffffffu, idx, (pc.slot0 & 15) * 2 + j);
             const float *bp = NP < 4 ? base[pi] : pc.src + pc.col + lane * 4;
             const int64_t ldv = NP < 4 ? ldp[pi] : pc.ld;
-            v[pi][j] = (row_ok && lane_on[pi]) ? ldg_f4(bp + r0 * ldv) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[pi][j] = (row_ok && lane * 4 < pc.width) ? ldg_f4(bp + r0 * ldv) : make_float4(0.f, 0.f, 0.f, 0.f);
           } else {
             int32_t i0 = 0, i1 = 0, i2 = 0;
             if (pc.mode != GNNFD_SEG_DIRECT) {     // uniform per piece
@@ -219,10 +254,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             t0.x = tanhf(t0.x); t0.y = tanhf(t0.y); t0.z = tanhf(t0.z); t0.w = tanhf(t0.w);
             t1.x = tanhf(t1.x); t1.y = tanhf(t1.y); t1.z = tanhf(t1.z); t1.w = tanhf(t1.w);
           }
-          t0.x = to_tf32(t0.x); t0.y = to_tf32(t0.y); t0.z = to_tf32(t0.z); t0.w = to_tf32(t0.w);
-          t1.x = to_tf32(t1.x); t1.y = to_tf32(t1.y); t1.z = to_tf32(t1.z); t1.w = to_tf32(t1.w);
-          *reinterpret_cast<float4 *>(img) = t0;
-          *reinterpret_cast<float4 *>(img + (pi == 0 ? 4 : nb_atoms) * 2048) = t1;   // row + 16 = 4 K atoms further
+          if (BF) {
+            // hi / lo bf16 pairs of the lane's 4 columns: 8-byte stores into the hi image and the lo image
+            const uint32_t part = pi == 0 ? a_img : b_img;
+            const uint32_t jstep = (uint32_t)(2 * (pi == 0 ? 2 : nb_atoms) * 1024);     // row + 16 = 2 K atoms further
+            uint32_t h0, l0, h1, l1;
+            split2<false>(t0.x, t0.y, h0, l0); split2<false>(t0.z, t0.w, h1, l1);
+            *reinterpret_cast<uint2 *>(img) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2 *>(img + part) = make_uint2(l0, l1);
+            split2<false>(t1.x, t1.y, h0, l0); split2<false>(t1.z, t1.w, h1, l1);
+            *reinterpret_cast<uint2 *>(img + jstep) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2 *>(img + jstep + part) = make_uint2(l0, l1);
+          } else {
+            t0.x = to_tf32(t0.x); t0.y = to_tf32(t0.y); t0.z = to_tf32(t0.z); t0.w = to_tf32(t0.w);
+            t1.x = to_tf32(t1.x); t1.y = to_tf32(t1.y); t1.z = to_tf32(t1.z); t1.w = to_tf32(t1.w);
+            *reinterpret_cast<float4 *>(img) = t0;
+            *reinterpret_cast<float4 *>(img + (pi == 0 ? 4 : nb_atoms) * 2048) = t1;   // row + 16 = 4 K atoms further
+          }
         }
       }
       fence_proxy_async();
@@ -257,7 +305,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       mbar_wait(done, 0);
       tc_fence_after();
       float *dst = p.partial + ((size_t)blockIdx.x * 128 + warp * 32 + lane) * p.n_pad;
-      for (int c = 0; c < nb_atoms; ++c) {
+      for (int c = 0; c < (p.n_pad >> 5); ++c) {
         float acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 32, acc);
 #pragma unroll
@@ -269,20 +317,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   } else {
     // ================================================================================ MMA issuer
     if (lane == 0) {
-      const uint32_t sbo_a = 4 * 512, sbo_b = (uint32_t)nb_atoms * 512;
+      const uint32_t sbo_a = BF ? 2 * 1024 : 4 * 512, sbo_b = (uint32_t)nb_atoms * (BF ? 1024 : 512);
       for (int it = 0; it < n_stage_iters; ++it) {
         const int st = it % p.stages;
         mbar_wait(&full[st], (it / p.stages) & 1);
         tc_fence_after();
         const uint32_t sA = smem_u32(smem + (size_t)st * stage_bytes), sB = sA + a_bytes;
+        if (BF) {
 #pragma unroll 1
-        for (int ka = 0; ka < WG_KR / 8; ++ka) {
-          const uint64_t ad = make_desc_mn(sA + 2 * ka * sbo_a, sbo_a);
-          const uint32_t acc = (it | ka) != 0;
-          for (int n0 = 0; n0 < p.n_pad; n0 += 256) {
-            const int n = min(256, p.n_pad - n0);
-            const uint64_t bd = make_desc_mn(sB + 2 * ka * sbo_b + (n0 >> 5) * 512, sbo_b);
-            umma_tf32_ss(tmem_base + n0, ad, bd, make_idesc_tf32_mn(n), acc);
+          for (int ks = 0; ks < WG_KR / 16; ++ks) {          // K = 16 rows = 2 K atoms per MMA
+            const uint64_t ah = make_desc_mn16(sA + 2 * ks * sbo_a, sbo_a), al = make_desc_mn16(sA + a_img + 2 * ks * sbo_a, sbo_a);
+            for (int n0 = 0; n0 < p.n_pad; n0 += 256) {
+              const int n = min(256, p.n_pad - n0);
+              const uint32_t idesc = make_idesc_bf16_mn(n);
+              const uint32_t boff = 2 * ks * sbo_b + (n0 >> 6) * 1024;
+              const uint64_t bh = make_desc_mn16(sB + boff, sbo_b), bl = make_desc_mn16(sB + b_img + boff, sbo_b);
+              umma_ss(tmem_base + n0, ah, bh, idesc, (it | ks) != 0);
+              umma_ss(tmem_base + n0, al, bh, idesc, 1);
+              umma_ss(tmem_base + n0, ah, bl, idesc, 1);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int ka = 0; ka < WG_KR / 8; ++ka) {
+            const uint64_t ad = make_desc_mn(sA + 2 * ka * sbo_a, sbo_a);
+            const uint32_t acc = (it | ka) != 0;
+            for (int n0 = 0; n0 < p.n_pad; n0 += 256) {
+              const int n = min(256, p.n_pad - n0);
+              const uint64_t bd = make_desc_mn(sB + 2 * ka * sbo_b + (n0 >> 5) * 512, sbo_b);
+              umma_tf32_ss(tmem_base + n0, ad, bd, make_idesc_tf32_mn(n), acc);
+            }
           }
         }
         umma_commit(&empty[st]);
@@ -329,13 +393,14 @@ static int64_t wg_rows_per_cta(int64_t rows, int &grid) {
 
 using namespace gnnfd;
 
-static int wg_n_pad(const gnnfd_wgrad_args *a) {
+static int wg_n_pad(const gnnfd_wgrad_args *a) {   // split-bf16 pads to 64-column atoms, TF32 to 32-column atoms
+  const int g = a->precision == 1 ? 31 : 63;
   int n = 0;
-  for (int s = 0; s < a->n_b; ++s) n += (a->b[s].width + 31) & ~31;
+  for (int s = 0; s < a->n_b; ++s) n += (a->b[s].width + g) & ~g;
   return n;
 }
 
-extern "C" size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded) {
+extern "C" size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded /* to 64 */) {
   if (rows <= 0) return 256;
   int grid;
   wg_rows_per_cta(rows, grid);
@@ -353,7 +418,7 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
   int n_valid = 0;
   for (int s = 0; s < a->n_b; ++s) {
     GNNFD_CHECK_ARG(a->b[s].width > 0 && a->b[s].width <= 128, "B segment width must be 1..128");
-    GNNFD_CHECK_ARG(s == a->n_b - 1 || (a->b[s].width & 31) == 0, "only the last B segment may be narrower than a multiple of 32");
+    GNNFD_CHECK_ARG(s == a->n_b - 1 || (a->b[s].width & 63) == 0, "only the last B segment may be narrower than a multiple of 64");
     n_valid += a->b[s].width;
   }
   const int cs_valid = a->colsum ? (a->colsum_of_b ? a->b[0].width : a->a.width) : 0;
@@ -387,7 +452,7 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
     pc.vec = ((sg.ld & 3) == 0) && ((sg.col & 3) == 0) && ((sg.width & 3) == 0) &&
              ((reinterpret_cast<uintptr_t>(sg.src) & 15) == 0);
     pc.atom0 = pi == 0 ? 0 : atom;
-    if (pi > 0) atom += ((sg.width + 31) & ~31) >> 5;
+    if (pi > 0) atom += a->precision == 1 ? ((sg.width + 31) & ~31) >> 5 : ((sg.width + 63) & ~63) >> 6;
     const int n_idx = sg.mode == GNNFD_SEG_DIRECT ? 0 : sg.mode == GNNFD_SEG_GATHER ? 1 : sg.mode == GNNFD_SEG_MEAN3 ? 3 : 2;
     pc.slot0 = slot;
     for (int q = 0; q < n_idx; ++q) {
@@ -401,16 +466,17 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
   int stages = (int)((200u * 1024u) / stage_bytes);
   p.stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
   const int smem = p.stages * (int)stage_bytes + WG_PROD_WARPS * 128 * 4 + (2 * WG_MAX_STAGES + 1) * 8 + 64 + 1024;
-#define WG_LAUNCH(NP_)                                                                                          \
+#define WG_LAUNCH(NP_, MD_)                                                                                     \
   do {                                                                                                         \
     static bool attr = false;                                                                                  \
     if (!attr) {                                                                                               \
-      GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NP_, MD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr = true;                                                                                             \
     }                                                                                                          \
-    wgrad_tc_kernel<NP_><<<grid, WG_THREADS, smem, stream>>>(p);                                               \
+    wgrad_tc_kernel<NP_, MD_><<<grid, WG_THREADS, smem, stream>>>(p);                                          \
   } while (0)
-  if (p.n_pieces == 2) WG_LAUNCH(2); else if (p.n_pieces == 3) WG_LAUNCH(3); else WG_LAUNCH(4);
+  if (a->precision == 1) { if (p.n_pieces == 2) WG_LAUNCH(2, 1); else if (p.n_pieces == 3) WG_LAUNCH(3, 1); else WG_LAUNCH(4, 1); }
+  else { if (p.n_pieces == 2) WG_LAUNCH(2, 0); else if (p.n_pieces == 3) WG_LAUNCH(3, 0); else WG_LAUNCH(4, 0); }
 #undef WG_LAUNCH
   GNNFD_LAUNCH_CHECK();
   const int m_valid = a->a.width;

@@ -39,11 +39,22 @@ class VertPotA(FluxA):
         kinds, inputs, outputs = super().normalisation_tables()
         return kinds, inputs, outputs + [(0, col(2, 5), "face_flux")]
 
+    def training_plan(self):
+        from ..training import Plan, Site
+        plan = getattr(self, "_gnnfd_plan", None)
+        if plan is None:
+            blocks = [(Site(b.node_block.cell_mlp), Site(b.edge_block.face_mlp)) for b in self.processer_list]
+            plan = Plan("vertpot", Site(self.encoder.face_mlp), Site(self.encoder.cell_mlp), blocks,
+                        Site(self.decoder.edge_mlp), dec_vertex=Site(self.decoder.vertex_mlp))
+            object.__setattr__(self, "_gnnfd_plan", plan)
+        return plan
+
     def encode_process_decode(self, c_x, f_x, topo, hook=None):
         prec = self.prec
-        if self.wants_grad():
-            raise NotImplementedError("the backward kernels cover the Fvgn/Flux and Mgn/StreamFunc families; "
-                                      f"{type(self).__name__} runs forward / rollout only (wrap the call in torch.no_grad())")
+        if self.wants_grad():   # training step: kernel-scheduled backward (training.py), both decoder heads
+            from ..training import encode_process_decode_train
+            edge_out, vertex_out = encode_process_decode_train(self.training_plan(), topo, prec, c_x, f_x)
+            return None, None, None, edge_out, vertex_out
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
         x, e, vx = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook)

@@ -389,18 +389,19 @@ def ln_backward(g: torch.Tensor, xhat: torch.Tensor, rstd: torch.Tensor, ln_w: O
 
 def wgrad(a: Seg, b: Sequence[Seg], rows: int, out: torch.Tensor, a_act: int = 0, b_act: int = 0,
           transpose_out: bool = False, colsum: Optional[torch.Tensor] = None, colsum_of_b: bool = False,
-          workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+          workspace: Optional[torch.Tensor] = None, single_pass: bool = False) -> torch.Tensor:
     """out[m, n] = sum_r A[r, m] B[r, n] on the tensor cores (gnnfd_wgrad); activations: 0 none, 1 SiLU, 2 tanh."""
     args = WgradArgs()
     args.rows = rows
     _fill_segment(args.a, a, "a")
     args.a_act, args.b_act, args.n_b = a_act, b_act, len(b)
-    n_pad = 0
+    n_pad, g = 0, (32 if single_pass else 64)          # column padding of the operand images (TF32 / split-bf16 atoms)
     for i, s in enumerate(b):
-        n_pad += (_fill_segment(args.b[i], s, f"b[{i}]") + 31) // 32 * 32
+        n_pad += (_fill_segment(args.b[i], s, f"b[{i}]") + g - 1) // g * g
     _req(out, torch.float32, "out")
     args.out, args.ld_out, args.transpose_out = out.data_ptr(), out.stride(0), int(transpose_out)
     args.colsum, args.colsum_of_b = _ptr(colsum), int(colsum_of_b)
+    args.precision = 1 if single_pass else 0
     nb = lib.gnnfd_wgrad_workspace_bytes(rows, n_pad)
     if workspace is None or workspace.numel() < nb:
         workspace = torch.empty(nb, dtype=torch.uint8, device=out.device)

@@ -15,7 +15,8 @@ the backward of every sub-block is:
                the CSR of cat[row; col]; the 3-vertex mean becomes a segment sum over cat[vf0; vf1; vf2];
                the edge->vertex scatter_add becomes a gather                     ops.segment_sum3 / gather_pair_add
 
-Families: 'fvgn' (Fvgn/Flux) and 'mgn' (Mgn/StreamFunc).  No atomics anywhere: gradients are bitwise
+Families: 'fvgn' (Fvgn/Flux), 'mgn' (Mgn/StreamFunc) and 'vertpot' (VertPot: FVGN blocks + the Vertex_Block on the
+last block's raw edge output + a second decoder head).  No atomics anywhere: gradients are bitwise
 reproducible run to run.
 """
 from __future__ import annotations
@@ -115,11 +116,15 @@ def mlp_backward_stepwise(w: MLPWeights, st: MLPStash, segs: Sequence[Seg], rows
 class Plan:
     """The MLP sites of one model in execution order + the data-flow family."""
 
-    def __init__(self, family: str, enc_edge: Site, enc_node: Site, blocks: Sequence[tuple], dec: Site):
-        if family not in ("fvgn", "mgn"):
-            raise NotImplementedError(f"training kernels cover the 'fvgn' and 'mgn' families, not {family!r}")
+    def __init__(self, family: str, enc_edge: Site, enc_node: Site, blocks: Sequence[tuple], dec: Site,
+                 dec_vertex: Optional[Site] = None):
+        if family not in ("fvgn", "mgn", "vertpot"):
+            raise NotImplementedError(f"training kernels cover the 'fvgn', 'mgn' and 'vertpot' families, not {family!r}")
         self.family, self.enc_edge, self.enc_node, self.blocks, self.dec = family, enc_edge, enc_node, list(blocks), dec
+        self.dec_vertex = dec_vertex      # VertPot: second head on the vertex sums of the last block's raw edge output
         self.sites = [enc_edge, enc_node] + [s for b in self.blocks for s in b] + [dec]   # block = (node site, edge site)
+        if dec_vertex is not None:
+            self.sites.append(dec_vertex)
 
     def flat_params(self):
         return [p for s in self.sites for p in s.params if p is not None]
@@ -139,20 +144,23 @@ class EncodeProcessDecode(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan: Plan, topo: MeshTopology, prec: int, c_x: torch.Tensor, f_x: torch.Tensor, *params):
-        fam = plan.family
+        fam = "fvgn" if plan.family == "vertpot" else plan.family     # VertPot blocks are FVGN blocks (VertPot.py:195-210)
+        vertpot = plan.family == "vertpot"
         c_x, f_x = c_x.contiguous(), f_x.contiguous()
         N, E = c_x.shape[0], f_x.shape[0]
         e, _, st_ee = ops.mlp_forward([Seg(f_x)], plan.enc_edge.weights(), E, prec, stash=True)
         x, _, st_en = ops.mlp_forward([Seg(c_x)], plan.enc_node.weights(), N, prec, stash=True)
         saved = []
-        for node_site, edge_site in plan.blocks:
+        e_raw_last = None
+        for bi, (node_site, edge_site) in enumerate(plan.blocks):
             wn, we = node_site.weights(), edge_site.weights()
             if fam == "fvgn":
                 vsum = vertex_half_sum(e, topo)
                 x_raw, x_new, st_n = ops.mlp_forward(_node_segs(x, vsum, topo), wn, N, prec, residual=x,
                                                      want_raw=True, want_sum=True, stash=True)
-                _, e_new, st_e = ops.mlp_forward(_edge_segs(e, x_raw, topo), we, E, prec, residual=e,
-                                                 want_raw=False, want_sum=True, stash=True)
+                last_vp = vertpot and bi == len(plan.blocks) - 1
+                e_raw_last, e_new, st_e = ops.mlp_forward(_edge_segs(e, x_raw, topo), we, E, prec, residual=e,
+                                                          want_raw=last_vp, want_sum=True, stash=True)
                 saved.append((x, e, vsum, x_raw, st_n, st_e))
             else:
                 e_raw, e_new, st_e = ops.mlp_forward(_edge_segs(e, x, topo), we, E, prec, residual=e,
@@ -166,13 +174,19 @@ class EncodeProcessDecode(torch.autograd.Function):
         out, _, st_d = ops.mlp_forward([Seg(dec_in)], plan.dec.weights(), dec_in.shape[0], prec, stash=True)
         ctx.plan, ctx.topo, ctx.prec = plan, topo, prec
         ctx.stash = (c_x, f_x, st_ee, st_en, saved, dec_in, st_d)
+        if vertpot:
+            # Vertex_Block (VertPot.py:217-222): full-width sum of the last block's RAW edge output, N output rows
+            vx = ops.segment_sum(e_raw_last, e_raw_last, 0, 0, H, 1.0, topo.vertex_csr_rows(N), topo.vtx_perm, N)
+            out_v, _, st_dv = ops.mlp_forward([Seg(vx)], plan.dec_vertex.weights(), N, prec, stash=True)
+            ctx.vertpot = (vx, st_dv)
+            return out, out_v
         return out
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_out, g_out_v=None):
         plan, topo, prec = ctx.plan, ctx.topo, ctx.prec
         c_x, f_x, st_ee, st_en, saved, dec_in, st_d = ctx.stash
-        fam = plan.family
+        fam = "fvgn" if plan.family == "vertpot" else plan.family
         N, E, V = c_x.shape[0], f_x.shape[0], topo.n_vertices
         dev = g_out.device
         ws = ops.mlp_backward_workspace(max(N, E), dev)
@@ -183,12 +197,20 @@ class EncodeProcessDecode(torch.autograd.Function):
         gd, dins = mlp_backward(plan.dec.weights(), st_d, [Seg(dec_in)], dec_in.shape[0], g_out, prec, [{}], ws)
         site_grads[id(plan.dec)] = gd
         d_e, d_x = (dins[0], None) if fam == "fvgn" else (None, dins[0])
+        g_extra = None          # VertPot: gradient reaching the last block's raw edge output through the vertex head
+        if plan.family == "vertpot":
+            vx, st_dv = ctx.vertpot
+            gv, dins = mlp_backward(plan.dec_vertex.weights(), st_dv, [Seg(vx)], N, g_out_v, prec, [{}], ws)
+            site_grads[id(plan.dec_vertex)] = gv
+            # transpose of the full-width edge->vertex sum: d e_raw[k] = d vx[v0[k]] + d vx[v1[k]], added to d e_new
+            g_extra = ops.gather_pair_add(dins[0], topo.v0, topo.v1, 1.0, False, E, base=d_e)
 
         for (node_site, edge_site), (x_in, e_in, vsum, x_raw, st_n, st_e) in zip(reversed(plan.blocks), reversed(saved)):
             wn, we = node_site.weights(), edge_site.weights()
             if fam == "fvgn":
                 # e_new = e + edge(e, x_raw[row], x_raw[col]);  x_new = x + x_raw;  x_raw = node(x, mean3(S(e)))
-                ge, dins = mlp_backward(we, st_e, _edge_segs(e_in, x_raw, topo), E, d_e, prec,
+                g_edge, g_extra = (g_extra, None) if g_extra is not None else (d_e, None)
+                ge, dins = mlp_backward(we, st_e, _edge_segs(e_in, x_raw, topo), E, g_edge, prec,
                                         [{"residual": d_e}, {}, {}], ws)
                 d_e_acc, t1, t2 = dins
                 d_x_raw = ops.segment_sum3(t1, t2, None, (0, 0, 0), H, 1.0, E, rc_off, rc_perm, N, base=d_x)
@@ -216,7 +238,7 @@ class EncodeProcessDecode(torch.autograd.Function):
             d_x = torch.zeros(N, H, dtype=torch.float32, device=dev)
         site_grads[id(plan.enc_edge)], _ = mlp_backward(plan.enc_edge.weights(), st_ee, [Seg(f_x)], E, d_e, prec, [None], ws)
         site_grads[id(plan.enc_node)], _ = mlp_backward(plan.enc_node.weights(), st_en, [Seg(c_x)], N, d_x, prec, [None], ws)
-        ctx.stash = None
+        ctx.stash = ctx.vertpot = None
         flat = []
         for s in plan.sites:
             gs = site_grads[id(s)]

@@ -187,8 +187,8 @@ size_t gnnfd_ln_backward_workspace_bytes(int64_t rows);
 int gnnfd_ln_backward(const float *g, const float *xhat, const float *rstd, const float *ln_w, int64_t rows,
                       float *dy, float *sums /*[3,128]*/, void *workspace, size_t workspace_bytes, void *stream);
 
-/* Weight gradient of one Linear: out[m, n] = sum_r A[r, m] * B[r, n]  (tcgen05 kind::tf32, MN-major operands,
- * split-K over the grid with an ordered reduction).  A is a DIRECT [rows, <=128] matrix, B is assembled from
+/* Weight gradient of one Linear: out[m, n] = sum_r A[r, m] * B[r, n]  (tcgen05, MN-major operands - split-bf16
+ * kind::f16 by default, single-pass kind::tf32 optionally - split-K over the grid with an ordered reduction).  A is a DIRECT [rows, <=128] matrix, B is assembled from
  * up to three segments exactly like the forward input (so dW1 of a Face_Block reads e, x[row], x[col] in
  * place); a_act / b_act (0 none, 1 SiLU, 2 tanh) turn a saved pre-activation into the hidden activation on
  * load.  colsum (optional) receives the column sums of A (or of B segment 0 when colsum_of_b) - the bias
@@ -205,8 +205,9 @@ typedef struct {
   int32_t transpose_out;
   float *colsum;
   int32_t colsum_of_b;
+  int32_t precision; /* 0 (default): split-bf16 operands, kind::f16 hi*hi + lo*hi + hi*lo (~1e-5);  1: single-pass TF32 (~3e-4) */
 } gnnfd_wgrad_args;
-size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded /* sum of B widths rounded up to 32 */);
+size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded /* sum of B widths, each rounded up to 64 */);
 int gnnfd_wgrad(const gnnfd_wgrad_args *args, void *workspace, size_t workspace_bytes, void *stream);
 
 /* The whole backward of one fused MLP in ONE call (the host-side schedule lives in the library so the GPU,

@@ -14,7 +14,7 @@ from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
 from helpers import LOSS_W, build_model, golden_graphs, load_golden
 
 pytestmark = pytest.mark.gpu
-GRAD_TOL = 1e-3
+GRAD_TOL = 1e-3     # whole-step parameter gradients; measured worst case ~1e-4 (split-bf16 dgrad and wgrad)
 
 
 def dev():
@@ -35,8 +35,10 @@ def test_wgrad_dense_vs_torch(rows):
     out = torch.empty(128, 128, device=dev())
     cs = torch.empty(128, device=dev())
     ops.wgrad(ops.Seg(a.to(dev())), [ops.Seg(b.to(dev()))], rows, out, b_act=1, colsum=cs)
-    assert rel_l2(out, ref.float()) < GRAD_TOL, rel_l2(out, ref.float())
+    assert rel_l2(out, ref.float()) < 5e-5, rel_l2(out, ref.float())          # split-bf16 (default): ~1e-5
     assert rel_l2(cs, a.double().sum(0).float()) < 1e-5
+    ops.wgrad(ops.Seg(a.to(dev())), [ops.Seg(b.to(dev()))], rows, out, b_act=1, single_pass=True)
+    assert rel_l2(out, ref.float()) < GRAD_TOL, rel_l2(out, ref.float())     # single-pass TF32
 
 
 def test_wgrad_gathered_concat_and_narrow_vs_torch():
@@ -56,14 +58,14 @@ def test_wgrad_gathered_concat_and_narrow_vs_torch():
     cs = torch.empty(128, device=dev())
     ops.wgrad(ops.Seg(da_e.to(dev())), [ops.Seg(ed), ops.Seg(xd, _lib.SEG_GATHER, (i32(row),)),
                                         ops.Seg(xd, _lib.SEG_GATHER, (i32(col),))], E, out, colsum=cs)
-    assert rel_l2(out, ref.float()) < GRAD_TOL, rel_l2(out, ref.float())
+    assert rel_l2(out, ref.float()) < 5e-5, rel_l2(out, ref.float())
     assert rel_l2(cs, da_e.double().sum(0).float()) < 1e-5
     # node layer 1
     agg = (vs[vf[0]] + vs[vf[1]] + vs[vf[2]]) / 3.0
     ref = da_n.double().t() @ torch.cat([x, agg], 1).double()
     out = torch.empty(128, 192, device=dev())
     ops.wgrad(ops.Seg(da_n.to(dev())), [ops.Seg(xd), ops.Seg(vsd, _lib.SEG_MEAN3, tuple(i32(t) for t in vf))], N, out)
-    assert rel_l2(out, ref.float()) < GRAD_TOL, rel_l2(out, ref.float())
+    assert rel_l2(out, ref.float()) < 5e-5, rel_l2(out, ref.float())
     # encoder layer 1 (10 input columns) and decoder layer 3 (5 outputs, transposed store, colsum of B)
     f = torch.randn(E, 10, generator=g)
     out = torch.empty(128, 10, device=dev())
@@ -264,3 +266,36 @@ def test_backward_entry_points_handle_empty_and_tiny_inputs():
     out = torch.empty(128, 128, device=dev())
     ops.wgrad(ops.Seg(torch.empty(0, 128, device=dev())), [ops.Seg(torch.empty(0, 128, device=dev()))], 0, out)
     assert float(out.abs().sum()) == 0.0
+
+
+def test_vertpot_processor_gradients_vs_oracle():
+    """VertPot family (FVGN blocks + Vertex_Block + two decoder heads): gradients of a random linear functional of
+    both heads w.r.t. every live parameter against the oracle's autograd."""
+    import oracle
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    name = "VertPotA"
+    model = build_model(name).train()
+    _, graphs = golden_graphs(name, n_cells=400)
+    graphs = model.normalizer.input([g.clone() for g in graphs])
+    c, f, v = graphs
+    params = {k: p.detach().clone().requires_grad_(p.is_floating_point()) for k, p in model.state_dict().items()}
+    topo_cpu = {"c_edge_index": c.edge_index, "v_edge_index": v.edge_index, "v_face": v.face, "n_vertices": v.num_nodes}
+    ref = oracle.processor_fwd("vertpot", params, c.x, f.x, topo_cpu, 15)
+    edge_ref, vert_ref = ref["dec"]
+    gen = torch.Generator().manual_seed(3)
+    r1, r2 = torch.randn(edge_ref.shape, generator=gen), torch.randn(vert_ref.shape, generator=gen)
+    ((edge_ref * r1).sum() + (vert_ref * r2).sum()).backward()
+    model.to(dev())
+    gd = [g.to(dev()) for g in graphs]
+    _, _, _, edge_out, vert_out = model.encode_process_decode(gd[0].x, gd[1].x, get_topology(gd).validate())
+    assert rel_l2(edge_out, edge_ref.detach()) < 2e-3 and rel_l2(vert_out, vert_ref.detach()) < 2e-3
+    ((edge_out * r1.to(dev())).sum() + (vert_out * r2.to(dev())).sum()).backward()
+    worst = ("", 0.0)
+    for k, p in model.named_parameters():
+        g_ref = params[k].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            continue                 # the reference's unused duplicate face_block / cell_block parameters
+        assert p.grad is not None, k
+        err = rel_l2(p.grad, g_ref)
+        worst = max(worst, (k, err), key=lambda t: t[1])
+    assert worst[1] < GRAD_TOL, worst
