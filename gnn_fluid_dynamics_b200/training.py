@@ -9,7 +9,7 @@ the backward of every sub-block is:
   dgrad chain  dA2 = (dy W3) * act'(a2), dA1 = (dA2 W2) * act'(a1), dIn = dA1 W1[:, segment]
                - tcgen05 single-Linear launches, activation derivative and gradient accumulation
                  (out = residual + ...) fused in the epilogue                    ops.linear_tc
-  wgrad        dW = dA^T H on tcgen05 kind::tf32, H = act(a) / the gathered MLP input assembled on the
+  wgrad        dW = dA^T H on tcgen05 (split-bf16, MN-major operands), H = act(a) / the gathered MLP input assembled on the
                fly, bias gradients as column sums of dA                          ops.wgrad
   transposed gathers: the Face_Block's x[row], x[col] gathers become a deterministic segment sum over
                the CSR of cat[row; col]; the 3-vertex mean becomes a segment sum over cat[vf0; vf1; vf2];
