@@ -111,3 +111,43 @@ class ConservativeA(FvgnA):
                 super().__init__()
                 self.cell_mlp = build_mlp(config, hidden_size * 2, hidden_size, hidden_size)
                 self.mp_times = mp_times
+
+
+class ConservativeE(FvgnA):
+    """Reference ``ConservativeE`` (Conservative.py:660-732): FvgnA encoder / decoder / integrator with
+    face-block-first GN_Blocks whose cell block aggregates the raw face output directly onto cells - first half of
+    the latent with equal signs ("symmetric"), second half with opposite signs ("antisymmetric")."""
+    family = "cons_e"
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.processer_list = nn.ModuleList(
+            [self.GN_Block(config, self.hidden_size) for _ in range(config.model.mp_num)])
+
+    class GN_Block(nn.Module):
+        family = "cons_e"
+
+        def __init__(self, config, hidden_size):
+            super().__init__()
+            self.face_block = ConservativeA.GN_Block.Face_Block(config, hidden_size)    # in = 2H (e, x[row] + x[col])
+            self.cell_block = ConservativeA.GN_Block.Cell_Block(config, hidden_size)    # in = 2H (x, sym | asym sums)
+
+
+class ConservativeF(FvgnA):
+    """Reference ``ConservativeF`` (Conservative.py:734-821): FVGN-order blocks whose cell block takes the symmetric
+    half of the face latent through the vertices (two-hop mean) and the antisymmetric half as a signed direct
+    edge->cell sum; concat-form face block."""
+    family = "cons_f"
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.processer_list = nn.ModuleList(
+            [self.GN_Block(config, self.hidden_size) for _ in range(config.model.mp_num)])
+
+    class GN_Block(nn.Module):
+        family = "cons_f"
+
+        def __init__(self, config, hidden_size):
+            super().__init__()
+            self.cell_block = ConservativeA.GN_Block.Cell_Block(config, hidden_size)    # in = 2H (x, two-hop sym, signed asym)
+            self.face_block = FvgnA.GN_Block.Face_Block(config, hidden_size)            # in = 3H

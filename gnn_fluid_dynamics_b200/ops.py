@@ -80,8 +80,8 @@ def segment_sum(a: torch.Tensor, b: torch.Tensor, col_a: int, col_b: int, width:
     _req(perm, torch.int32, "perm")
     if out is None:
         out = torch.empty(n_rows, width, dtype=torch.float32, device=a.device)
-    else:
-        _req(out, torch.float32, "out")
+    elif not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.stride(1) == 1):
+        raise RuntimeError("segment_sum: out must be a CUDA fp32 matrix with unit column stride (column slices are fine)")
     check(lib.gnnfd_segment_sum(a.data_ptr(), b.data_ptr(), a.stride(0), b.stride(0), col_a, col_b,
                                 width, float(sign_b), a.shape[0], offsets.data_ptr(), perm.data_ptr(),
                                 n_rows, out.data_ptr(), out.stride(0), _stream()), "gnnfd_segment_sum")

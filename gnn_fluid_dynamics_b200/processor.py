@@ -6,6 +6,8 @@ their block order follow SURVEY.md section 8a:
   fvgn    : vertex segment-sum(e) -> node MLP(x, mean3) -> edge MLP(e, x'[row], x'[col])   Fvgn.py:274-325
   mgn     : edge MLP(e, x[row], x[col]) -> vertex segment-sum(e') -> node MLP               Mgn.py:216-267
   cons_a  : edge MLP(e, x[row]+x[col]) [* asym] -> signed cell segment-sum(e') -> node MLP  Conservative.py:210-254
+  cons_e  : edge MLP(e, x[row]+x[col]) -> cell sums of e' (half +/+, half +/-) -> node MLP  Conservative.py:677-732
+  cons_f  : vertex sum(sym half) + signed cell sum(asym half) -> node MLP -> edge MLP(e, x'[row], x'[col])  :763-821
   vertpot : fvgn + full-width vertex sum of e'                                              VertPot.py:195-222
 
 The second sub-block consumes the first one's RAW output; both residuals are applied by the
@@ -122,6 +124,28 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
         agg = cell_signed_sum(e_raw, topo)
         _, x_new = ops.mlp_forward([Seg(x), Seg(agg)], weights_of(block.cell_block.cell_mlp),
                                    x.shape[0], prec, residual=x, want_raw=False, want_sum=True)
+        return x_new, e_new, None
+    if family == "cons_e":
+        # ConservativeE (Conservative.py:677-732): sum-form face block, then the RAW face output aggregated onto cells:
+        # first half with equal signs, second half with opposite signs, agg = cat[sym, asym]
+        e_raw, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec)
+        off, perm = topo.build_cell_csr()
+        agg = torch.empty(x.shape[0], H, dtype=torch.float32, device=x.device)
+        ops.segment_sum(e_raw, e_raw, 0, 0, H // 2, 1.0, off, perm, topo.n_cells, out=agg[:, :H // 2])
+        ops.segment_sum(e_raw, e_raw, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells, out=agg[:, H // 2:])
+        _, x_new = ops.mlp_forward([Seg(x), Seg(agg)], weights_of(block.cell_block.cell_mlp), x.shape[0], prec,
+                                   residual=x, want_raw=False, want_sum=True)
+        return x_new, e_new, None
+    if family == "cons_f":
+        # ConservativeF (Conservative.py:763-821): symmetric half two-hop via the vertices (the same half onto both
+        # vertices), antisymmetric half signed edge->cell; then the concat-form face block on the RAW cell output
+        vsum = ops.segment_sum(e, e, 0, 0, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices)
+        off, perm = topo.build_cell_csr()
+        asym = ops.segment_sum(e, e, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells)
+        x_raw, x_new = ops.mlp_forward([Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)],
+                                       weights_of(block.cell_block.cell_mlp), x.shape[0], prec, residual=x,
+                                       want_raw=True, want_sum=True)
+        _, e_new = edge_mlp_concat(block.face_block.face_mlp, e, x_raw, topo, prec, want_raw=False)
         return x_new, e_new, None
     if family == "vertpot":
         vsum = vertex_half_sum(e, topo)

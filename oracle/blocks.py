@@ -18,11 +18,12 @@ import torch
 from .mlp import mlp_from_state
 from .scatter import scatter_add
 
-FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot")
+FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f")
 
 _FAMILY_OF = {
     "FvgnA": "fvgn", "FluxA": "fvgn", "MgnA": "mgn", "StreamFuncA": "mgn",
     "ConservativeA": "cons_a", "ConservativeB": "cons_a", "VertPotA": "vertpot",
+    "ConservativeE": "cons_e", "ConservativeF": "cons_f",
 }
 
 
@@ -75,6 +76,29 @@ def cell_block_signed(sd, prefix, x, e, c_edge_index):
     return mlp_from_state(sd, prefix, torch.cat([x, agg], dim=-1))
 
 
+def cell_block_sym_asym_halves(sd, prefix, x, e, c_edge_index):
+    """ConservativeE Cell_Block (Conservative.py:708-732): the first half of the edge latent is summed onto both
+    cells of the face with the same sign, the second half with opposite signs; agg = cat[sym, asym]."""
+    row, col = c_edge_index[0], c_edge_index[1]
+    idx = torch.cat([col, row], dim=0)
+    es, ea = torch.chunk(e, 2, dim=-1)
+    sym = scatter_add(torch.cat([es, es], dim=0), idx, x.shape[0])
+    asym = scatter_add(torch.cat([ea, -ea], dim=0), idx, x.shape[0])
+    return mlp_from_state(sd, prefix, torch.cat([x, sym, asym], dim=-1))
+
+
+def cell_block_hybrid(sd, prefix, x, e, c_edge_index, v_edge_index, v_face, n_vertices):
+    """ConservativeF Cell_Block (Conservative.py:782-809): symmetric half via the vertices (the SAME half onto both
+    vertices of a face, then the 3-vertex mean), antisymmetric half as a signed direct edge->cell sum."""
+    es, ea = torch.chunk(e, 2, dim=-1)
+    vidx = torch.cat([v_edge_index[0], v_edge_index[1]], dim=0)
+    vsum = scatter_add(torch.cat([es, es], dim=0), vidx, n_vertices)
+    cell_agg = (vsum.index_select(0, v_face[0]) + vsum.index_select(0, v_face[1]) + vsum.index_select(0, v_face[2])) / 3.0
+    row, col = c_edge_index[0], c_edge_index[1]
+    asym = scatter_add(torch.cat([ea, -ea], dim=0), torch.cat([col, row], dim=0), x.shape[0])
+    return mlp_from_state(sd, prefix, torch.cat([x, cell_agg, asym], dim=-1))
+
+
 def vertex_block(e, v_edge_index, n_rows):
     """Vertex_Block (VertPot.py:217-222): full-width edge->vertex sum; the output has
     ``cell_graph.x.size(0)`` rows (N, not V) - rows >= V stay zero."""
@@ -116,6 +140,15 @@ def gn_block_fwd(family, sd, i, x, e, topo, e_asym=None):
     if family == "cons_a":
         er = face_block_sum(sd, f"{p}.face_block.face_mlp", x, e, topo["c_edge_index"], e_asym)
         xr = cell_block_signed(sd, f"{p}.cell_block.cell_mlp", x, er, topo["c_edge_index"])
+        return x + xr, e + er, None
+    if family == "cons_e":      # face block (sum form) -> cell block on the RAW face output (Conservative.py:677-687)
+        er = face_block_sum(sd, f"{p}.face_block.face_mlp", x, e, topo["c_edge_index"])
+        xr = cell_block_sym_asym_halves(sd, f"{p}.cell_block.cell_mlp", x, er, topo["c_edge_index"])
+        return x + xr, e + er, None
+    if family == "cons_f":      # cell block (hybrid) -> face block (concat form) on the RAW cell output (:763-773)
+        xr = cell_block_hybrid(sd, f"{p}.cell_block.cell_mlp", x, e, topo["c_edge_index"], topo["v_edge_index"],
+                               topo["v_face"], topo["n_vertices"])
+        er = face_block_concat(sd, f"{p}.face_block.face_mlp", xr, e, topo["c_edge_index"])
         return x + xr, e + er, None
     if family == "vertpot":
         xr = cell_block_two_hop(sd, f"{p}.node_block.cell_mlp", x, e, topo["v_edge_index"],

@@ -5,7 +5,7 @@ Run here only:  python tests/golden/make_golden.py
 
 What is pinned
   connectivity_{k}.npz : reference utils/geometry.compute_connectivity on three synthetic meshes
-  fwd_{Model}.npz      : reference model forward (MgnA, FvgnA, FluxA, ConservativeA, VertPotA),
+  fwd_{Model}.npz      : reference model forward (MgnA, FvgnA, FluxA, ConservativeA/E/F, VertPotA),
                          hidden 128, 15 blocks, deterministic parameters
                          (gnn_fluid_dynamics_b200.testing.fill_state_dict_deterministic, seed 1),
                          mesh make_mesh(160, kind, seed=3), features mesh_graphs(seed=5):
@@ -44,6 +44,8 @@ MODELS = {
     "FluxA": ("models.Flux", "ellipse", "fvgn"),
     "ConservativeA": ("models.Conservative", "cylinder", "conservative"),
     "VertPotA": ("models.VertPot", "airfoil", "fvgn"),
+    "ConservativeE": ("models.Conservative", "ellipse", "fvgn"),
+    "ConservativeF": ("models.Conservative", "airfoil", "fvgn"),
 }
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1}
@@ -78,7 +80,7 @@ def graphs_for(name, kind, flavour, flip=False):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "VertPotA"):
+    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
@@ -140,6 +142,13 @@ def gen_forward(name):
     print(name, {k: tuple(v.shape) for k, v in out.items()})
 
 
+def gen_keys(name):
+    import json
+    model, _, _ = build_ref(name)
+    keys = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+    json.dump(keys, open(os.path.join(HERE, f"keys_{name}.json"), "w"))
+
+
 def gen_train():
     name = "FvgnA"
     model, kind, flavour = build_ref(name)
@@ -171,7 +180,12 @@ def gen_train():
 
 
 if __name__ == "__main__":
-    gen_connectivity()
+    only = sys.argv[1:]
+    if not only:
+        gen_connectivity()
     for n in MODELS:
-        gen_forward(n)
-    gen_train()
+        if not only or n in only:
+            gen_forward(n)
+            gen_keys(n)
+    if not only:
+        gen_train()
