@@ -284,10 +284,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const int64_t nrow = min((int64_t)TC_BM, a.rows - prow0);
         if (pt == 0 && p.direct_tile_bytes > 0)
           bulk_prefetch_l2(a.seg[0].src + prow0 * a.seg[0].ld, (uint32_t)(nrow * a.seg[0].ld * 4));
-        if (BWD && pt == 32) {   // saved pre-activations read by the hidden epilogues (thread = row)
-          bulk_prefetch_l2(a.hid_mul1 + prow0 * TC_H, (uint32_t)(nrow * TC_H * 4));
-          bulk_prefetch_l2(a.hid_mul2 + prow0 * TC_H, (uint32_t)(nrow * TC_H * 4));
-        }
+        // (the saved pre-activations read by the backward chain's hidden epilogues are NOT prefetched: measured
+        //  7 % slower with the prefetch - 375 vs 349 us on the edge chain - and 240 MB of extra DRAM reads)
       }
       cp_async_commit();
     };
