@@ -160,3 +160,25 @@ def test_peer_memory_gather_equals_single_gpu(tmp_path, name):
         d = np.load(tmp_path / f"rank{p.rank}.npz")
         assert np.array_equal(d["x"], x.cpu()[p.cells[:p.n_owned]].numpy())
         assert np.array_equal(d["e"], e.cpu()[p.faces].numpy())
+
+
+def test_partition_invariance_and_determinism_at_200k_cells():
+    """BASELINE.json config 3 size (200k cells): size-independent properties instead of an oracle run - the result
+    does not depend on how the mesh is cut (4 partitions == unpartitioned, bit for bit) nor on the run."""
+    from gnn_fluid_dynamics_b200.dist import InProcessTransport, encode_process_decode_partitioned
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    dev = torch.device("cuda:0")
+    model, graphs, parts, locals_ = _setup("MgnA", 200000, 4, dev)
+    gd = [g.to(dev) for g in graphs]
+    with torch.no_grad():
+        topo = get_topology(gd).validate()
+        x, e, dec = model.encode_process_decode(gd[0].x, gd[1].x, topo)
+        x2, e2, dec2 = model.encode_process_decode(gd[0].x, gd[1].x, topo)
+        assert torch.equal(x, x2) and torch.equal(e, e2) and torch.equal(dec, dec2)
+        assert torch.isfinite(x).all() and torch.isfinite(e).all()
+        states, inputs = _states(parts, locals_, dev)
+        outs = encode_process_decode_partitioned(model, states, inputs, InProcessTransport())
+    for p, (xp, ep, dp) in zip(parts, outs):
+        assert torch.equal(xp, x[p.cells[:p.n_owned].to(dev)])
+        assert torch.equal(ep, e[p.faces.to(dev)])
+        assert torch.equal(dp, dec[p.cells[:p.n_owned].to(dev)])
