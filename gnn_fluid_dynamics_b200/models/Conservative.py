@@ -151,3 +151,62 @@ class ConservativeF(FvgnA):
             super().__init__()
             self.cell_block = ConservativeA.GN_Block.Cell_Block(config, hidden_size)    # in = 2H (x, two-hop sym, signed asym)
             self.face_block = FvgnA.GN_Block.Face_Block(config, hidden_size)            # in = 3H
+
+
+class ConservativeD(ConservativeA):
+    """Reference ``ConservativeD`` (Conservative.py:417-658): same features / normalisation / encoder containers as
+    ConservativeA, but the antisymmetric face encoding is a second latent stream with its own (bias-free tanh) face
+    block on ``x[row] - x[col]``, the cell block aggregates both streams, and the decoder is
+    ``final_mlp(symm_mlp(e_s) + asym_mlp(e_a))`` with antisymmetric asym / final heads."""
+    family = "cons_d"
+
+    def encode_process_decode(self, c_x, f_x_symm, f_x_asym, topo, hook=None):
+        prec = self.prec
+        if self.wants_grad():
+            raise NotImplementedError("the backward kernels cover the Fvgn/Flux, Mgn/StreamFunc and VertPot families; "
+                                      f"{type(self).__name__} runs forward / rollout only (wrap the call in torch.no_grad())")
+        e_s = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
+        e_a = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
+        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        for i, blk in enumerate(self.processer_list):
+            x, e_s, e_a = P.gn_block_dual(blk, x, e_s, e_a, topo, prec)
+            if hook is not None:
+                hook(i, x, e_s)
+        # decoder: symm head, asym head accumulated onto it through the residual epilogue, final antisymmetric head
+        d_s = P.mlp_rows(self.decoder.symm_mlp, e_s, prec)
+        _, comb = P.ops.mlp_forward([P.Seg(e_a)], P.weights_of(self.decoder.asym_mlp, ACT_TANH), e_a.shape[0], prec,
+                                    residual=d_s, want_raw=False, want_sum=True)
+        self._last_e_asym = e_a
+        return x, e_s, P.mlp_rows(self.decoder.final_mlp, comb, prec, act=ACT_TANH)
+
+    class GN_Block(nn.Module):   # Conservative.py:572-645
+        family = "cons_d"
+
+        def __init__(self, config, hidden_size):
+            super().__init__()
+            self.face_block_symm = self.Face_Block_Symm(config, hidden_size)
+            self.face_block_asym = self.Face_Block_Asym(config, hidden_size)
+            self.cell_block = self.Cell_Block(config, hidden_size)
+
+        class Face_Block_Symm(nn.Module):
+            def __init__(self, config, hidden_size):
+                super().__init__()
+                self.face_mlp = build_mlp(config, hidden_size * 2, hidden_size, hidden_size)
+
+        class Face_Block_Asym(nn.Module):
+            def __init__(self, config, hidden_size):
+                super().__init__()
+                self.face_mlp = build_mlp_antisym(config, hidden_size * 2, hidden_size, hidden_size)
+
+        class Cell_Block(nn.Module):
+            def __init__(self, config, hidden_size, mp_times=2):
+                super().__init__()
+                self.cell_mlp = build_mlp(config, hidden_size * 3, hidden_size, hidden_size)
+                self.mp_times = mp_times
+
+    class Decoder(nn.Module):   # Conservative.py:647-658
+        def __init__(self, config, hidden_size, output_sizes):
+            super().__init__()
+            self.symm_mlp = build_mlp(config, hidden_size, hidden_size, hidden_size, norm_layer=False)
+            self.asym_mlp = build_mlp_antisym(config, hidden_size, hidden_size, hidden_size)
+            self.final_mlp = build_mlp_antisym(config, hidden_size, hidden_size, output_sizes[1])

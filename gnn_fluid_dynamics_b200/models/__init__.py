@@ -3,8 +3,8 @@
 from .Fvgn import FvgnA  # noqa: F401
 from .Mgn import MgnA  # noqa: F401
 from .Flux import FluxA  # noqa: F401
-from .Conservative import ConservativeA, ConservativeE, ConservativeF  # noqa: F401
+from .Conservative import ConservativeA, ConservativeD, ConservativeE, ConservativeF  # noqa: F401
 from .VertPot import VertPotA  # noqa: F401
 
 MODEL_CLASSES = {"FvgnA": FvgnA, "MgnA": MgnA, "FluxA": FluxA, "ConservativeA": ConservativeA,
-                 "VertPotA": VertPotA, "ConservativeE": ConservativeE, "ConservativeF": ConservativeF}
+                 "VertPotA": VertPotA, "ConservativeE": ConservativeE, "ConservativeF": ConservativeF, "ConservativeD": ConservativeD}

@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from ._lib import ACT_SILU, ACT_TANH, PREC_F32, SEG_DIRECT, SEG_GATHER, SEG_MEAN3, SEG_SUM2
+from ._lib import ACT_SILU, ACT_TANH, PREC_F32, SEG_DIFF2, SEG_DIRECT, SEG_GATHER, SEG_MEAN3, SEG_SUM2
 from .ops import MLPWeights, Seg
 from .topology import MeshTopology
 
@@ -154,6 +154,21 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
         vx = vertex_full_sum(e_raw, topo, x.shape[0]) if want_vertex else None
         return x_new, e_new, vx
     raise ValueError(f"unknown family {family!r}")
+
+
+def gn_block_dual(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32):
+    """ConservativeD GN_Block (Conservative.py:572-645): symmetric and antisymmetric edge streams.
+    -> (x_new, e_s_new, e_a_new)."""
+    s_raw, s_new = edge_mlp_sum(block.face_block_symm.face_mlp, e_s, x, topo, prec)
+    segs = [Seg(e_a), Seg(x, SEG_DIFF2, (topo.row, topo.col))]                       # cat[e_a, x[row] - x[col]]
+    a_raw, a_new = ops.mlp_forward(segs, weights_of(block.face_block_asym.face_mlp, ACT_TANH), e_a.shape[0], prec,
+                                   residual=e_a, want_raw=True, want_sum=True)
+    off, perm = topo.build_cell_csr()
+    sym = ops.segment_sum(s_raw, s_raw, 0, 0, H, 1.0, off, perm, topo.n_cells)      # equal signs on both cells
+    asym = ops.segment_sum(a_raw, a_raw, 0, 0, H, -1.0, off, perm, topo.n_cells)    # opposite signs
+    _, x_new = ops.mlp_forward([Seg(x), Seg(sym), Seg(asym)], weights_of(block.cell_block.cell_mlp), x.shape[0], prec,
+                               residual=x, want_raw=False, want_sum=True)
+    return x_new, s_new, a_new
 
 
 def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=None, hook=None):

@@ -18,12 +18,12 @@ import torch
 from .mlp import mlp_from_state
 from .scatter import scatter_add
 
-FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f")
+FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f", "cons_d")
 
 _FAMILY_OF = {
     "FvgnA": "fvgn", "FluxA": "fvgn", "MgnA": "mgn", "StreamFuncA": "mgn",
     "ConservativeA": "cons_a", "ConservativeB": "cons_a", "VertPotA": "vertpot",
-    "ConservativeE": "cons_e", "ConservativeF": "cons_f",
+    "ConservativeE": "cons_e", "ConservativeF": "cons_f", "ConservativeD": "cons_d",
 }
 
 
@@ -97,6 +97,22 @@ def cell_block_hybrid(sd, prefix, x, e, c_edge_index, v_edge_index, v_face, n_ve
     row, col = c_edge_index[0], c_edge_index[1]
     asym = scatter_add(torch.cat([ea, -ea], dim=0), torch.cat([col, row], dim=0), x.shape[0])
     return mlp_from_state(sd, prefix, torch.cat([x, cell_agg, asym], dim=-1))
+
+
+def gn_block_dual(sd, i, x, e_s, e_a, c_edge_index):
+    """ConservativeD GN_Block (Conservative.py:572-645): two edge streams.  Symmetric face block
+    MLP(cat[e_s, x[row] + x[col]]) (SiLU + LayerNorm), antisymmetric face block antisym_MLP(cat[e_a, x[row] - x[col]])
+    (bias-free tanh, no LayerNorm); the cell block sums the raw symmetric output onto both cells with equal signs and
+    the raw antisymmetric output with opposite signs; residuals on x, e_s, e_a after the block."""
+    p = f"processer_list.{i}"
+    row, col = c_edge_index[0], c_edge_index[1]
+    sr = mlp_from_state(sd, f"{p}.face_block_symm.face_mlp", torch.cat([e_s, x[row] + x[col]], dim=1))
+    ar = mlp_from_state(sd, f"{p}.face_block_asym.face_mlp", torch.cat([e_a, x[row] - x[col]], dim=1), act="tanh")
+    idx = torch.cat([col, row], dim=0)
+    sym = scatter_add(torch.cat([sr, sr], dim=0), idx, x.shape[0])
+    asym = scatter_add(torch.cat([ar, -ar], dim=0), idx, x.shape[0])
+    xr = mlp_from_state(sd, f"{p}.cell_block.cell_mlp", torch.cat([x, sym, asym], dim=-1))
+    return x + xr, e_s + sr, e_a + ar
 
 
 def vertex_block(e, v_edge_index, n_rows):
@@ -175,6 +191,19 @@ def processor_fwd(family, sd, c_x, f_x, topo, mp_num, f_x_asym=None, keep_blocks
 
     ConservativeA quirk reproduced: GN_Block returns a fresh Data without ``edge_attr_asym`` so
     the asym multiply fires in block 0 only (Conservative.py:220, 232-233)."""
+    if family == "cons_d":
+        x, e, ea = encoder_fwd("cons_a", sd, c_x, f_x, f_x_asym)      # same encoder containers as ConservativeA
+        out = {"x0": x, "e0": e, "e0_asym": ea}
+        per_block = []
+        for i in range(mp_num):
+            x, e, ea = gn_block_dual(sd, i, x, e, ea, topo["c_edge_index"])
+            if keep_blocks:
+                per_block.append((x, e, ea))
+        out.update({"x": x, "e": e, "ea": ea, "vx": None, "blocks": per_block})
+        # Decoder (Conservative.py:647-658): final_mlp(symm_mlp(e_s) + asym_mlp(e_a))
+        comb = mlp_from_state(sd, "decoder.symm_mlp", e) + mlp_from_state(sd, "decoder.asym_mlp", ea, act="tanh")
+        out["dec"] = mlp_from_state(sd, "decoder.final_mlp", comb, act="tanh")
+        return out
     x, e, ea = encoder_fwd(family, sd, c_x, f_x, f_x_asym)
     out = {"x0": x, "e0": e}
     vx = None

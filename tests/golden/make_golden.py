@@ -46,6 +46,7 @@ MODELS = {
     "VertPotA": ("models.VertPot", "airfoil", "fvgn"),
     "ConservativeE": ("models.Conservative", "ellipse", "fvgn"),
     "ConservativeF": ("models.Conservative", "airfoil", "fvgn"),
+    "ConservativeD": ("models.Conservative", "ellipse", "conservative"),
 }
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1}
@@ -80,7 +81,7 @@ def graphs_for(name, kind, flavour, flip=False):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF"):
+    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
@@ -116,6 +117,8 @@ def gen_forward(name):
         def hook(mod, inp, out):
             cg = out[0] if isinstance(out, tuple) else out
             cap[f"x{tag}"], cap[f"e{tag}"] = cg.x.clone(), cg.edge_attr.clone()
+            if hasattr(cg, "edge_attr_asym"):
+                cap[f"ea{tag}"] = cg.edge_attr_asym.clone()
             if isinstance(out, tuple):
                 cap[f"vx{tag}"] = out[1].x.clone()
         return hook

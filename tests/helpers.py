@@ -11,7 +11,8 @@ LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face
 # (mesh kind, feature flavour) used by tests/golden/make_golden.py per model
 GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "FluxA": ("ellipse", "fvgn"),
                 "ConservativeA": ("cylinder", "conservative"), "VertPotA": ("airfoil", "fvgn"),
-                "ConservativeE": ("ellipse", "fvgn"), "ConservativeF": ("airfoil", "fvgn")}
+                "ConservativeE": ("ellipse", "fvgn"), "ConservativeF": ("airfoil", "fvgn"),
+                "ConservativeD": ("ellipse", "conservative")}
 
 
 def make_config(mp_num=15, precision=None):
@@ -43,7 +44,7 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF"):
+    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD"):
         f.y = f.y[:, :3].contiguous()
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
