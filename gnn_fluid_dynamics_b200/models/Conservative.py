@@ -210,3 +210,47 @@ class ConservativeD(ConservativeA):
             self.symm_mlp = build_mlp(config, hidden_size, hidden_size, hidden_size, norm_layer=False)
             self.asym_mlp = build_mlp_antisym(config, hidden_size, hidden_size, hidden_size)
             self.final_mlp = build_mlp_antisym(config, hidden_size, hidden_size, output_sizes[1])
+
+
+class ConservativeG(FvgnA):
+    """Reference ``ConservativeG`` (Conservative.py:824-896): ConservativeF's hybrid cell block followed by the SUM-form
+    face block ``face_mlp(cat[e, x'[row] + x'[col]])``."""
+    family = "cons_g"
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.processer_list = nn.ModuleList(
+            [self.GN_Block(config, self.hidden_size) for _ in range(config.model.mp_num)])
+
+    class GN_Block(nn.Module):
+        family = "cons_g"
+
+        def __init__(self, config, hidden_size):
+            super().__init__()
+            self.cell_block = ConservativeA.GN_Block.Cell_Block(config, hidden_size)    # in = 2H
+            self.face_block = ConservativeA.GN_Block.Face_Block(config, hidden_size)    # in = 2H (e, x'[row] + x'[col])
+
+
+class ConservativeI(ConservativeG):
+    """Reference ``ConservativeI`` (Conservative.py:1211-1317): ConservativeG whose GN_Blocks re-impose the boundary
+    conditions - the latent of INFLOW / WALL_BOUNDARY faces is reset to its block input after the residual add."""
+    family = "cons_i"
+
+    def forward_normalised(self, graphs, mode="rollout"):
+        f_type = graphs[1].type
+        keep = ~((f_type == 2) | (f_type == 1)).reshape(-1)                 # INFLOW = 2, WALL_BOUNDARY = 1 (OpenFoam.py:19-24)
+        self._e_keep = keep.to(torch.float32).unsqueeze(1).expand(-1, self.hidden_size).contiguous()
+        return super().forward_normalised(graphs, mode)
+
+    def encode_process_decode(self, c_x, f_x, topo, hook=None, e_keep=None):
+        prec = self.prec
+        if self.wants_grad():
+            raise NotImplementedError(f"{type(self).__name__} runs forward / rollout only (wrap the call in torch.no_grad())")
+        e_keep = e_keep if e_keep is not None else self._e_keep
+        e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
+        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook, e_keep=e_keep)
+        return x, e, P.mlp_rows(self.decoder.face_mlp, e, prec)
+
+    class GN_Block(ConservativeG.GN_Block):
+        family = "cons_i"

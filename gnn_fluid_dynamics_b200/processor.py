@@ -80,7 +80,8 @@ def edge_mlp_concat(seq, e, x_src, topo, prec, want_raw, residual=True):
 
 
 def edge_mlp_sum(seq, e, x_src, topo, prec, mul=None):
-    """e' = face_mlp(cat[e, x[row] + x[col]]) [* e_asym]  (Conservative.py:228-234)."""
+    """e' = face_mlp(cat[e, x[row] + x[col]]) [* mul]  (Conservative.py:228-234); ``mul`` is ConservativeA's asym
+    encoding or ConservativeI's keep matrix (0 on INFLOW / WALL faces, so e + 0 * e' leaves their latent untouched)."""
     segs = [Seg(e), Seg(x_src, SEG_SUM2, (topo.row, topo.col))]
     return ops.mlp_forward(segs, weights_of(seq), e.shape[0], prec, mul=mul, residual=e,
                            want_raw=True, want_sum=True)
@@ -107,7 +108,7 @@ def mlp_rows(seq, src: torch.Tensor, prec: int, act: int = ACT_SILU) -> torch.Te
 
 
 def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
-             e_asym: Optional[torch.Tensor] = None, want_vertex: bool = False):
+             e_asym: Optional[torch.Tensor] = None, want_vertex: bool = False, e_keep: Optional[torch.Tensor] = None):
     """One GN_Block -> (x_new, e_new, vertex_x or None)."""
     if family == "fvgn":
         vsum = vertex_half_sum(e, topo)
@@ -147,6 +148,17 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
                                        want_raw=True, want_sum=True)
         _, e_new = edge_mlp_concat(block.face_block.face_mlp, e, x_raw, topo, prec, want_raw=False)
         return x_new, e_new, None
+    if family in ("cons_g", "cons_i"):
+        # ConservativeG / I (Conservative.py:834-896, 1250-1317): F's hybrid cell block, then the SUM-form face block on
+        # the raw cell output; I keeps the previous latent on boundary-condition faces (e_keep = 0 rows)
+        vsum = ops.segment_sum(e, e, 0, 0, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices)
+        off, perm = topo.build_cell_csr()
+        asym = ops.segment_sum(e, e, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells)
+        x_raw, x_new = ops.mlp_forward([Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)],
+                                       weights_of(block.cell_block.cell_mlp), x.shape[0], prec, residual=x,
+                                       want_raw=True, want_sum=True)
+        _, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x_raw, topo, prec, mul=e_keep if family == "cons_i" else None)
+        return x_new, e_new, None
     if family == "vertpot":
         vsum = vertex_half_sum(e, topo)
         x_raw, x_new = node_mlp_two_hop(block.node_block.cell_mlp, x, vsum, topo, prec, want_raw=True)
@@ -171,7 +183,7 @@ def gn_block_dual(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32):
     return x_new, s_new, a_new
 
 
-def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=None, hook=None):
+def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=None, hook=None, e_keep=None):
     """All GN_Blocks.  VertPot's vertex sum is only live after the last block (VertPot.py:208: it is
     overwritten every block and never fed back), so it is computed once."""
     vx = None
@@ -179,7 +191,7 @@ def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=
     for i, blk in enumerate(blocks):
         x, e, vx_i = gn_block(family, blk, x, e, topo, prec,
                               e_asym=e_asym if (family == "cons_a" and i == 0) else None,
-                              want_vertex=(family == "vertpot" and i == n - 1))
+                              want_vertex=(family == "vertpot" and i == n - 1), e_keep=e_keep)
         if vx_i is not None:
             vx = vx_i
         if hook is not None:

@@ -18,12 +18,13 @@ import torch
 from .mlp import mlp_from_state
 from .scatter import scatter_add
 
-FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f", "cons_d")
+FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f", "cons_d", "cons_g", "cons_i")
 
 _FAMILY_OF = {
     "FvgnA": "fvgn", "FluxA": "fvgn", "MgnA": "mgn", "StreamFuncA": "mgn",
     "ConservativeA": "cons_a", "ConservativeB": "cons_a", "VertPotA": "vertpot",
     "ConservativeE": "cons_e", "ConservativeF": "cons_f", "ConservativeD": "cons_d",
+    "ConservativeG": "cons_g", "ConservativeI": "cons_i",
 }
 
 
@@ -137,7 +138,7 @@ def encoder_fwd(family, sd, c_x, f_x, f_x_asym=None):
     return x0, e0, None
 
 
-def gn_block_fwd(family, sd, i, x, e, topo, e_asym=None):
+def gn_block_fwd(family, sd, i, x, e, topo, e_asym=None, bc_mask=None):
     """One GN_Block.  ``topo`` has c_edge_index, v_edge_index, v_face, n_vertices.
     The second sub-block consumes the first one's RAW output, the residuals are added after both
     (Fvgn.py:274-284, Mgn.py:216-226, Conservative.py:210-220, VertPot.py:195-210).
@@ -166,6 +167,17 @@ def gn_block_fwd(family, sd, i, x, e, topo, e_asym=None):
                                topo["v_face"], topo["n_vertices"])
         er = face_block_concat(sd, f"{p}.face_block.face_mlp", xr, e, topo["c_edge_index"])
         return x + xr, e + er, None
+    if family in ("cons_g", "cons_i"):
+        # ConservativeG (Conservative.py:834-896): hybrid cell block (as F) -> SUM-form face block on the raw cell
+        # output.  ConservativeI (:1250-1269) additionally keeps the previous latent on INFLOW / WALL faces.
+        xr = cell_block_hybrid(sd, f"{p}.cell_block.cell_mlp", x, e, topo["c_edge_index"], topo["v_edge_index"],
+                               topo["v_face"], topo["n_vertices"])
+        er = face_block_sum(sd, f"{p}.face_block.face_mlp", xr, e, topo["c_edge_index"])
+        e_new = e + er
+        if family == "cons_i":
+            e_new = e_new.clone()
+            e_new[bc_mask] = e[bc_mask]
+        return x + xr, e_new, None
     if family == "vertpot":
         xr = cell_block_two_hop(sd, f"{p}.node_block.cell_mlp", x, e, topo["v_edge_index"],
                                 topo["v_face"], topo["n_vertices"])
@@ -186,7 +198,7 @@ def decoder_fwd(family, sd, x, e, vx=None):
     return mlp_from_state(sd, "decoder.face_mlp", e)
 
 
-def processor_fwd(family, sd, c_x, f_x, topo, mp_num, f_x_asym=None, keep_blocks=False):
+def processor_fwd(family, sd, c_x, f_x, topo, mp_num, f_x_asym=None, keep_blocks=False, bc_mask=None):
     """encoder -> mp_num x GN_Block -> decoder on already-normalised inputs.
 
     ConservativeA quirk reproduced: GN_Block returns a fresh Data without ``edge_attr_asym`` so
@@ -209,7 +221,7 @@ def processor_fwd(family, sd, c_x, f_x, topo, mp_num, f_x_asym=None, keep_blocks
     vx = None
     per_block = []
     for i in range(mp_num):
-        x, e, vx = gn_block_fwd(family, sd, i, x, e, topo, e_asym=ea if i == 0 else None)
+        x, e, vx = gn_block_fwd(family, sd, i, x, e, topo, e_asym=ea if i == 0 else None, bc_mask=bc_mask)
         if keep_blocks:
             per_block.append((x, e))
     out.update({"x": x, "e": e, "vx": vx, "blocks": per_block})

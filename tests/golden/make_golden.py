@@ -47,6 +47,8 @@ MODELS = {
     "ConservativeE": ("models.Conservative", "ellipse", "fvgn"),
     "ConservativeF": ("models.Conservative", "airfoil", "fvgn"),
     "ConservativeD": ("models.Conservative", "ellipse", "conservative"),
+    "ConservativeG": ("models.Conservative", "cylinder", "fvgn"),
+    "ConservativeI": ("models.Conservative", "airfoil", "fvgn"),
 }
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1}
@@ -81,8 +83,12 @@ def graphs_for(name, kind, flavour, flip=False):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD"):
+    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
+    if name == "ConservativeI":
+        # the reference indexes the [E, 128] latent with the face-type mask (Conservative.py:1264-1267), which only
+        # works for a 1-D type tensor
+        f.type = f.type.reshape(-1)
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
     return mesh, g

@@ -12,7 +12,8 @@ LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face
 GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "FluxA": ("ellipse", "fvgn"),
                 "ConservativeA": ("cylinder", "conservative"), "VertPotA": ("airfoil", "fvgn"),
                 "ConservativeE": ("ellipse", "fvgn"), "ConservativeF": ("airfoil", "fvgn"),
-                "ConservativeD": ("ellipse", "conservative")}
+                "ConservativeD": ("ellipse", "conservative"), "ConservativeG": ("cylinder", "fvgn"),
+                "ConservativeI": ("airfoil", "fvgn")}
 
 
 def make_config(mp_num=15, precision=None):
@@ -44,8 +45,10 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD"):
+    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI"):
         f.y = f.y[:, :3].contiguous()
+    if name == "ConservativeI":
+        f.type = f.type.reshape(-1)      # see tests/golden/make_golden.py: the reference needs a 1-D type tensor here
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
     return mesh, g

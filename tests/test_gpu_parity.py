@@ -159,7 +159,12 @@ def _run_processor(name, model, graphs_dev):
         topo = get_topology(graphs_dev, need_cell_csr=True, two_hop=False).validate()
         x, e, dec = model.encode_process_decode(c.x, f.x_symm, f.x_asym, topo, hook=hook)
         return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
-    topo = get_topology(graphs_dev, need_cell_csr=name in ("ConservativeE", "ConservativeF")).validate()
+    topo = get_topology(graphs_dev, need_cell_csr=name.startswith("Conservative")).validate()
+    if name == "ConservativeI":
+        keep = ~((f.type == 2) | (f.type == 1)).reshape(-1)
+        e_keep = keep.float().unsqueeze(1).expand(-1, 128).contiguous()
+        x, e, dec = model.encode_process_decode(c.x, f.x, topo, hook=hook, e_keep=e_keep)
+        return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
     if name == "VertPotA":
         x, e, vx, dec, dec_v = model.encode_process_decode(c.x, f.x, topo, hook=hook)
         return {"x": x, "e": e, "vx": vx, "dec": dec, "dec_vertex": dec_v, "b1": grab[0]}
@@ -167,7 +172,7 @@ def _run_processor(name, model, graphs_dev):
     return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
 
 
-@pytest.mark.parametrize("name", ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD"])
+@pytest.mark.parametrize("name", ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI"])
 def test_processor_matches_reference_golden(name):
     gold = load_golden(f"fwd_{name}.npz")
     model = build_model(name).eval()
@@ -192,7 +197,7 @@ def test_processor_matches_reference_golden(name):
             assert rel_l2(out["dec_vertex"], torch.from_numpy(gold["dec_vertex"])) < 2 * t
 
 
-@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD"])
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI"])
 @pytest.mark.parametrize("mode", ["train", "rollout"])
 def test_full_forward_matches_reference_golden(name, mode):
     gold = load_golden(f"fwd_{name}.npz")

@@ -13,7 +13,7 @@ from gnn_fluid_dynamics_b200.mesh import connectivity
 from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
 from helpers import GOLDEN, LOSS_W, build_model, golden_graphs, load_golden
 
-MODELS = ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD"]
+MODELS = ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI"]
 TOL = 2e-5   # fp32 CPU restatement vs fp32 CPU reference: summation-order noise only
 
 
@@ -52,7 +52,8 @@ def test_oracle_processor_matches_reference(name):
     c_x, f_x, f_xa, topo = _processor_inputs(name, [g.clone() for g in graphs], model)
     fam = oracle.family_of(name)
     with torch.no_grad():
-        out = oracle.processor_fwd(fam, sd, c_x, f_x, topo, 15, f_x_asym=f_xa, keep_blocks=True)
+        bc = ((graphs[1].type == 2) | (graphs[1].type == 1)).reshape(-1) if name == "ConservativeI" else None
+        out = oracle.processor_fwd(fam, sd, c_x, f_x, topo, 15, f_x_asym=f_xa, keep_blocks=True, bc_mask=bc)
     assert rel_l2(out["x0"], torch.from_numpy(gold["x0"])) < TOL
     assert rel_l2(out["e0"], torch.from_numpy(gold["e0"])) < TOL
     assert rel_l2(out["blocks"][0][0], torch.from_numpy(gold["x1"])) < TOL
