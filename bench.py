@@ -34,6 +34,7 @@ WORKLOADS = {
     # autoregressive rollouts (second half of the metric: rollout steps/sec); "rollout" in the training slot
     "mgn_rollout_2k": ("MgnA", 1, 2048, "cylinder", "rollout"),        # BASELINE.json configs[0] shape
     "flux_rollout_200k": ("FluxA", 1, 200000, "cylinder", "rollout"),  # configs[2]
+    "cons_rollout_200k": ("ConservativeA", 1, 200000, "cylinder", "rollout"),  # configs[2], Conservative variant
     "mgn_rollout_4m": ("MgnA", 1, 4000000, "airfoil", "rollout"),      # configs[3]: domain-decomposed over --gpus N
 }
 DEFAULT_WORKLOAD = "fvgn_train_8x20k"   # BASELINE.json configs[1]
@@ -65,7 +66,7 @@ def build_batch(model_name, n_meshes, n_cells, kind, seed0=0):
 
 def _with_batch(g):
     g[0].batch = torch.zeros(g[0].x.shape[0], dtype=torch.long)
-    g[1].batch = torch.zeros(g[1].x.shape[0], dtype=torch.long)
+    g[1].batch = torch.zeros(g[1].pos.shape[0], dtype=torch.long)
     return g
 
 
@@ -442,10 +443,13 @@ def run_rollout(args, world, rank, dev, dist):
     prec = args.precision or "bf16x3"
     model = build_model(model_name, precision=prec).to(dev).eval()
     mesh = make_mesh(n_cells, kind, seed=0)
-    g = mesh_graphs(mesh, seed=100)
+    cons = model_name.startswith("Conservative")
+    g = mesh_graphs(mesh, seed=100, flavour="conservative" if cons else "fvgn")
     if model_name == "MgnA":
         g[0].y = torch.cat([g[0].y, torch.zeros(g[0].x.shape[0], 1)], 1)
         g[1].y = g[1].y[:, :2].contiguous()
+    elif cons:
+        g[1].y = g[1].y[:, :3].contiguous()
     g = _with_batch(g)
     N, E, V = g[0].x.shape[0], g[0].edge_index.shape[1], g[2].pos.shape[0]
     halo_bytes = 0
@@ -465,7 +469,7 @@ def run_rollout(args, world, rank, dev, dist):
         out_rows = part.n_owned
     else:
         from gnn_fluid_dynamics_b200.rollout import RolloutEngine
-        eng = RolloutEngine(model, [t.to(dev) for t in g], cuda_graph=True)
+        eng = RolloutEngine(model, [t.to(dev) for t in g], cuda_graph=True, need_cell_csr=cons, two_hop=not cons)
         step = eng.step
         out_rows = N
     host_out = torch.empty(out_rows, 2).pin_memory()
