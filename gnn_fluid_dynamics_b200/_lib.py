@@ -25,7 +25,7 @@ EXPORTS = [
     "gnnfd_ln_backward_workspace_bytes", "gnnfd_ln_backward", "gnnfd_wgrad_workspace_bytes", "gnnfd_wgrad",
     "gnnfd_segment_sum3", "gnnfd_gather_pair_add", "gnnfd_struct_size",
     "gnnfd_mlp_backward_workspace_bytes", "gnnfd_pack_mlp_backward_bytes", "gnnfd_pack_mlp_backward",
-    "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access",
+    "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access", "gnnfd_gather_cols_add",
 ]
 ABI_VERSION = 2
 
@@ -108,6 +108,7 @@ def _load():
     lib.gnnfd_gather_pair_add.argtypes = [vp, vp, vp, i32, vp, vp, f32, i32, i64, vp]
     lib.gnnfd_gather_rows.argtypes = [vp, i32, vp, i64, i32, vp, vp]
     lib.gnnfd_enable_peer_access.argtypes = [i32]
+    lib.gnnfd_gather_cols_add.argtypes = [vp, i32, i32, i32, vp, i32, vp, f32, i64, vp]
     lib.gnnfd_struct_size.argtypes = [i32]
     lib.gnnfd_struct_size.restype = C.c_size_t
     lib.gnnfd_mlp_backward_workspace_bytes.argtypes = [C.POINTER(MlpArgs)]

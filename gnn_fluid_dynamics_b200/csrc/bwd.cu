@@ -148,6 +148,23 @@ __global__ void __launch_bounds__(256) gather_pair_add_kernel(float *dst, const 
   *reinterpret_cast<float4 *>(dst + k * 128 + lane * 4) = d;
 }
 
+// dst[k, col:col+width] += scale * src[idx[k], 0:width]  - the transpose of one half of any edge->node segment sum
+// (generic backward of gnnfd_segment_sum for arbitrary column windows); one warp per row, float4 lanes
+__global__ void __launch_bounds__(256) gather_cols_add_kernel(float *__restrict__ dst, int ld_dst, int col, int width,
+                                                              const float *__restrict__ src, int ld_src,
+                                                              const int32_t *__restrict__ idx, float scale, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (k >= rows) return;
+  const int64_t r = __ldg(idx + k);
+  for (int c = lane * 4; c < width; c += 128) {
+    float4 d = *reinterpret_cast<const float4 *>(dst + k * ld_dst + col + c);
+    const float4 v = ldg_f4(src + r * ld_src + c);
+    d.x += scale * v.x; d.y += scale * v.y; d.z += scale * v.z; d.w += scale * v.w;
+    *reinterpret_cast<float4 *>(dst + k * ld_dst + col + c) = d;
+  }
+}
+
 }  // namespace gnnfd
 
 using namespace gnnfd;
@@ -208,6 +225,20 @@ extern "C" int gnnfd_gather_pair_add(float *dst, const float *base, const float 
   const int blocks = (int)((rows * 32 + 255) / 256);
   if (halves) gather_pair_add_kernel<true><<<blocks, 256, 0, stream>>>(dst, base, src, ld_src, i0, i1, sign, rows);
   else gather_pair_add_kernel<false><<<blocks, 256, 0, stream>>>(dst, base, src, ld_src, i0, i1, sign, rows);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}
+
+extern "C" int gnnfd_gather_cols_add(float *dst, int32_t ld_dst, int32_t col, int32_t width, const float *src,
+                                     int32_t ld_src, const int32_t *idx, float scale, int64_t rows, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GNNFD_CHECK_ARG(rows >= 0, "negative rows");
+  if (rows == 0) return GNNFD_OK;
+  GNNFD_CHECK_ARG(dst && src && idx, "null pointer");
+  GNNFD_CHECK_ARG(width > 0 && (width % 4) == 0 && (col % 4) == 0 && (ld_dst % 4) == 0 && (ld_src % 4) == 0,
+                  "widths / columns / strides must be multiples of 4 floats");
+  const int blocks = (int)((rows * 32 + 255) / 256);
+  gather_cols_add_kernel<<<blocks, 256, 0, stream>>>(dst, ld_dst, col, width, src, ld_src, idx, scale, rows);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

@@ -50,9 +50,6 @@ class ConservativeA(FvgnA):
 
     def encode_process_decode(self, c_x, f_x_symm, f_x_asym, topo, hook=None):
         prec = self.prec
-        if self.wants_grad():
-            raise NotImplementedError("the backward kernels cover the Fvgn/Flux and Mgn/StreamFunc families; "
-                                      f"{type(self).__name__} runs forward / rollout only (wrap the call in torch.no_grad())")
         e = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
         e_asym = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
@@ -162,9 +159,6 @@ class ConservativeD(ConservativeA):
 
     def encode_process_decode(self, c_x, f_x_symm, f_x_asym, topo, hook=None):
         prec = self.prec
-        if self.wants_grad():
-            raise NotImplementedError("the backward kernels cover the Fvgn/Flux, Mgn/StreamFunc and VertPot families; "
-                                      f"{type(self).__name__} runs forward / rollout only (wrap the call in torch.no_grad())")
         e_s = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
         e_a = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
@@ -174,8 +168,8 @@ class ConservativeD(ConservativeA):
                 hook(i, x, e_s)
         # decoder: symm head, asym head accumulated onto it through the residual epilogue, final antisymmetric head
         d_s = P.mlp_rows(self.decoder.symm_mlp, e_s, prec)
-        _, comb = P.ops.mlp_forward([P.Seg(e_a)], P.weights_of(self.decoder.asym_mlp, ACT_TANH), e_a.shape[0], prec,
-                                    residual=d_s, want_raw=False, want_sum=True)
+        _, comb = P.A.mlp(self.decoder.asym_mlp, [P.Seg(e_a)], e_a.shape[0], prec, act=ACT_TANH, residual=d_s,
+                          want_raw=False, want_sum=True)
         self._last_e_asym = e_a
         return x, e_s, P.mlp_rows(self.decoder.final_mlp, comb, prec, act=ACT_TANH)
 
@@ -244,8 +238,6 @@ class ConservativeI(ConservativeG):
 
     def encode_process_decode(self, c_x, f_x, topo, hook=None, e_keep=None):
         prec = self.prec
-        if self.wants_grad():
-            raise NotImplementedError(f"{type(self).__name__} runs forward / rollout only (wrap the call in torch.no_grad())")
         e_keep = e_keep if e_keep is not None else self._e_keep
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)

@@ -50,7 +50,8 @@ class MgnA(Model):
 
     def encode_process_decode(self, c_x, f_x, topo, hook=None):
         prec = self.prec
-        if self.wants_grad():   # training step: same kernels + stash, kernel-scheduled backward (training.py)
+        if self.wants_grad() and self.family in ("fvgn", "mgn"):   # hand-scheduled backward (training.py); other
+            # families train through the per-op autograd wrappers the processor is written with (autograd_ops.py)
             from ..training import encode_process_decode_train
             return None, None, encode_process_decode_train(self.training_plan(), topo, prec, c_x, f_x)
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)

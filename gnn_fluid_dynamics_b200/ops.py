@@ -453,3 +453,14 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor
           "gnnfd_gather_rows")
     _count(1)
     return out
+
+
+def gather_cols_add(dst: torch.Tensor, col: int, width: int, src: torch.Tensor, idx: torch.Tensor, scale: float = 1.0):
+    """dst[k, col:col+width] += scale * src[idx[k], :width]  in place (gnnfd_gather_cols_add)."""
+    dst = _req(dst, torch.float32, "dst")
+    src = _req(src, torch.float32, "src")
+    check(lib.gnnfd_gather_cols_add(dst.data_ptr(), dst.stride(0), col, width, src.data_ptr(), src.stride(0),
+                                    _req(idx, torch.int32, "idx").data_ptr(), float(scale), dst.shape[0], _stream()),
+          "gnnfd_gather_cols_add")
+    _count(1)
+    return dst

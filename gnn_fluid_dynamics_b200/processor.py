@@ -19,6 +19,7 @@ from typing import Optional
 
 import torch
 
+from . import autograd_ops as A
 from . import ops
 from ._lib import ACT_SILU, ACT_TANH, PREC_F32, SEG_DIFF2, SEG_DIRECT, SEG_GATHER, SEG_MEAN3, SEG_SUM2
 from .ops import MLPWeights, Seg
@@ -61,21 +62,20 @@ def weights_of(seq: torch.nn.Module, act: int = ACT_SILU) -> MLPWeights:
 def vertex_half_sum(e: torch.Tensor, topo: MeshTopology) -> torch.Tensor:
     """vsum[V, H/2]: half 0 of each face latent onto its first vertex, half 1 onto its second
     (scatter_add of Fvgn.py:312-314) as a deterministic CSR segment sum."""
-    return ops.segment_sum(e, e, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm,
-                           topo.n_vertices)
+    return A.segment_sum(e, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices, topo.v0, topo.v1)
 
 
 def node_mlp_two_hop(seq, x, vsum, topo, prec, want_raw, residual=True):
     """x' = cell_mlp(cat[x, (vsum[vf0]+vsum[vf1]+vsum[vf2])/3])  (Fvgn.py:316-323)."""
     segs = [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf)]
-    return ops.mlp_forward(segs, weights_of(seq), x.shape[0], prec, residual=x if residual else None,
+    return A.mlp(seq, segs, x.shape[0], prec, residual=x if residual else None,
                            want_raw=want_raw, want_sum=residual)
 
 
 def edge_mlp_concat(seq, e, x_src, topo, prec, want_raw, residual=True):
     """e' = face_mlp(cat[e, x[row], x[col]])  (Fvgn.py:292-296, Mgn.py:234-238)."""
     segs = [Seg(e), Seg(x_src, SEG_GATHER, (topo.row,)), Seg(x_src, SEG_GATHER, (topo.col,))]
-    return ops.mlp_forward(segs, weights_of(seq), e.shape[0], prec, residual=e if residual else None,
+    return A.mlp(seq, segs, e.shape[0], prec, residual=e if residual else None,
                            want_raw=want_raw, want_sum=residual)
 
 
@@ -83,19 +83,19 @@ def edge_mlp_sum(seq, e, x_src, topo, prec, mul=None):
     """e' = face_mlp(cat[e, x[row] + x[col]]) [* mul]  (Conservative.py:228-234); ``mul`` is ConservativeA's asym
     encoding or ConservativeI's keep matrix (0 on INFLOW / WALL faces, so e + 0 * e' leaves their latent untouched)."""
     segs = [Seg(e), Seg(x_src, SEG_SUM2, (topo.row, topo.col))]
-    return ops.mlp_forward(segs, weights_of(seq), e.shape[0], prec, mul=mul, residual=e,
+    return A.mlp(seq, segs, e.shape[0], prec, mul=mul, residual=e,
                            want_raw=True, want_sum=True)
 
 
 def cell_signed_sum(e_raw: torch.Tensor, topo: MeshTopology) -> torch.Tensor:
     """agg[c] = sum_{col(k)=c} e_k - sum_{row(k)=c} e_k  (Conservative.py:244-249)."""
     off, perm = topo.build_cell_csr()
-    return ops.segment_sum(e_raw, e_raw, 0, 0, H, -1.0, off, perm, topo.n_cells)
+    return A.segment_sum(e_raw, 0, 0, H, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
 
 
 def vertex_full_sum(e_raw: torch.Tensor, topo: MeshTopology, n_rows: int) -> torch.Tensor:
     """Vertex_Block (VertPot.py:217-222): full-width sum with ``n_rows`` (= N cells) output rows."""
-    return ops.segment_sum(e_raw, e_raw, 0, 0, H, 1.0, topo.vertex_csr_rows(n_rows), topo.vtx_perm, n_rows)
+    return A.segment_sum(e_raw, 0, 0, H, 1.0, topo.vertex_csr_rows(n_rows), topo.vtx_perm, n_rows, topo.v0, topo.v1)
 
 
 # --- encoder / block / decoder ------------------------------------------------------------------
@@ -103,7 +103,7 @@ def vertex_full_sum(e_raw: torch.Tensor, topo: MeshTopology, n_rows: int) -> tor
 def mlp_rows(seq, src: torch.Tensor, prec: int, act: int = ACT_SILU) -> torch.Tensor:
     """Plain per-row MLP (encoder / decoder heads)."""
     src = src.contiguous()
-    out, _ = ops.mlp_forward([Seg(src)], weights_of(seq, act), src.shape[0], prec)
+    out, _ = A.mlp(seq, [Seg(src)], src.shape[0], prec, act=act)
     return out
 
 
@@ -123,40 +123,37 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
     if family == "cons_a":
         e_raw, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec, mul=e_asym)
         agg = cell_signed_sum(e_raw, topo)
-        _, x_new = ops.mlp_forward([Seg(x), Seg(agg)], weights_of(block.cell_block.cell_mlp),
-                                   x.shape[0], prec, residual=x, want_raw=False, want_sum=True)
+        _, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(agg)], x.shape[0], prec, residual=x,
+                         want_raw=False, want_sum=True)
         return x_new, e_new, None
     if family == "cons_e":
         # ConservativeE (Conservative.py:677-732): sum-form face block, then the RAW face output aggregated onto cells:
         # first half with equal signs, second half with opposite signs, agg = cat[sym, asym]
         e_raw, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec)
         off, perm = topo.build_cell_csr()
-        agg = torch.empty(x.shape[0], H, dtype=torch.float32, device=x.device)
-        ops.segment_sum(e_raw, e_raw, 0, 0, H // 2, 1.0, off, perm, topo.n_cells, out=agg[:, :H // 2])
-        ops.segment_sum(e_raw, e_raw, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells, out=agg[:, H // 2:])
-        _, x_new = ops.mlp_forward([Seg(x), Seg(agg)], weights_of(block.cell_block.cell_mlp), x.shape[0], prec,
-                                   residual=x, want_raw=False, want_sum=True)
+        sym = A.segment_sum(e_raw, 0, 0, H // 2, 1.0, off, perm, topo.n_cells, topo.col, topo.row)
+        asym = A.segment_sum(e_raw, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
+        _, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(sym), Seg(asym)], x.shape[0], prec, residual=x,
+                         want_raw=False, want_sum=True)          # cat[x, sym, asym] as three 64-multiple segments
         return x_new, e_new, None
     if family == "cons_f":
         # ConservativeF (Conservative.py:763-821): symmetric half two-hop via the vertices (the same half onto both
         # vertices), antisymmetric half signed edge->cell; then the concat-form face block on the RAW cell output
-        vsum = ops.segment_sum(e, e, 0, 0, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices)
+        vsum = A.segment_sum(e, 0, 0, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices, topo.v0, topo.v1)
         off, perm = topo.build_cell_csr()
-        asym = ops.segment_sum(e, e, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells)
-        x_raw, x_new = ops.mlp_forward([Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)],
-                                       weights_of(block.cell_block.cell_mlp), x.shape[0], prec, residual=x,
-                                       want_raw=True, want_sum=True)
+        asym = A.segment_sum(e, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
+        x_raw, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)],
+                             x.shape[0], prec, residual=x, want_raw=True, want_sum=True)
         _, e_new = edge_mlp_concat(block.face_block.face_mlp, e, x_raw, topo, prec, want_raw=False)
         return x_new, e_new, None
     if family in ("cons_g", "cons_i"):
         # ConservativeG / I (Conservative.py:834-896, 1250-1317): F's hybrid cell block, then the SUM-form face block on
         # the raw cell output; I keeps the previous latent on boundary-condition faces (e_keep = 0 rows)
-        vsum = ops.segment_sum(e, e, 0, 0, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices)
+        vsum = A.segment_sum(e, 0, 0, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices, topo.v0, topo.v1)
         off, perm = topo.build_cell_csr()
-        asym = ops.segment_sum(e, e, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells)
-        x_raw, x_new = ops.mlp_forward([Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)],
-                                       weights_of(block.cell_block.cell_mlp), x.shape[0], prec, residual=x,
-                                       want_raw=True, want_sum=True)
+        asym = A.segment_sum(e, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
+        x_raw, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)],
+                             x.shape[0], prec, residual=x, want_raw=True, want_sum=True)
         _, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x_raw, topo, prec, mul=e_keep if family == "cons_i" else None)
         return x_new, e_new, None
     if family == "vertpot":
@@ -173,13 +170,13 @@ def gn_block_dual(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32):
     -> (x_new, e_s_new, e_a_new)."""
     s_raw, s_new = edge_mlp_sum(block.face_block_symm.face_mlp, e_s, x, topo, prec)
     segs = [Seg(e_a), Seg(x, SEG_DIFF2, (topo.row, topo.col))]                       # cat[e_a, x[row] - x[col]]
-    a_raw, a_new = ops.mlp_forward(segs, weights_of(block.face_block_asym.face_mlp, ACT_TANH), e_a.shape[0], prec,
-                                   residual=e_a, want_raw=True, want_sum=True)
+    a_raw, a_new = A.mlp(block.face_block_asym.face_mlp, segs, e_a.shape[0], prec, act=ACT_TANH, residual=e_a,
+                         want_raw=True, want_sum=True)
     off, perm = topo.build_cell_csr()
-    sym = ops.segment_sum(s_raw, s_raw, 0, 0, H, 1.0, off, perm, topo.n_cells)      # equal signs on both cells
-    asym = ops.segment_sum(a_raw, a_raw, 0, 0, H, -1.0, off, perm, topo.n_cells)    # opposite signs
-    _, x_new = ops.mlp_forward([Seg(x), Seg(sym), Seg(asym)], weights_of(block.cell_block.cell_mlp), x.shape[0], prec,
-                               residual=x, want_raw=False, want_sum=True)
+    sym = A.segment_sum(s_raw, 0, 0, H, 1.0, off, perm, topo.n_cells, topo.col, topo.row)      # equal signs on both cells
+    asym = A.segment_sum(a_raw, 0, 0, H, -1.0, off, perm, topo.n_cells, topo.col, topo.row)    # opposite signs
+    _, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(sym), Seg(asym)], x.shape[0], prec, residual=x,
+                     want_raw=False, want_sum=True)
     return x_new, s_new, a_new
 
 

@@ -210,6 +210,11 @@ typedef struct {
 size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded /* sum of B widths, each rounded up to 64 */);
 int gnnfd_wgrad(const gnnfd_wgrad_args *args, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Generic transpose of one index half of gnnfd_segment_sum (its autograd backward for arbitrary column windows):
+ *   dst[k, col:col+width] += scale * src[idx[k], 0:width]     (dst [rows, >= col+width], in place) */
+int gnnfd_gather_cols_add(float *dst, int32_t ld_dst, int32_t col, int32_t width, const float *src, int32_t ld_src,
+                          const int32_t *idx, float scale, int64_t rows, void *stream);
+
 /* The whole backward of one fused MLP in ONE call (the host-side schedule lives in the library so the GPU,
  * not the foreign-call overhead, bounds the training step):
  *   LayerNorm backward -> dW3, dA2 = (dy W3) act'(a2) -> dW2, dA1 = (dA2 W2) act'(a1) -> dW1 ->

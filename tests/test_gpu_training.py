@@ -299,3 +299,45 @@ def test_vertpot_processor_gradients_vs_oracle():
         err = rel_l2(p.grad, g_ref)
         worst = max(worst, (k, err), key=lambda t: t[1])
     assert worst[1] < GRAD_TOL, worst
+
+
+@pytest.mark.parametrize("name", ["ConservativeA", "ConservativeD", "ConservativeE", "ConservativeF", "ConservativeG",
+                                  "ConservativeI"])
+def test_generic_autograd_path_gradients_vs_oracle(name):
+    """Families without a hand-scheduled backward train through the per-op autograd wrappers (autograd_ops.py):
+    gradients of a random linear functional of the decoder output w.r.t. every live parameter vs the oracle."""
+    import oracle
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    model = build_model(name).train()
+    _, graphs = golden_graphs(name, n_cells=300)
+    graphs = model.normalizer.input([g.clone() for g in graphs])
+    c, f, v = graphs
+    params = {k: p.detach().clone().requires_grad_(p.is_floating_point()) for k, p in model.state_dict().items()}
+    topo_cpu = {"c_edge_index": c.edge_index, "v_edge_index": v.edge_index, "v_face": v.face, "n_vertices": v.num_nodes}
+    dual = name in ("ConservativeA", "ConservativeD")
+    bc = ((f.type == 2) | (f.type == 1)).reshape(-1) if name == "ConservativeI" else None
+    ref = oracle.processor_fwd(oracle.family_of(name), params, c.x, f.x_symm if dual else f.x, topo_cpu, 15,
+                               f_x_asym=f.x_asym if dual else None, bc_mask=bc)
+    r = torch.randn(ref["dec"].shape, generator=torch.Generator().manual_seed(4))
+    (ref["dec"] * r).sum().backward()
+    model.to(dev())
+    gd = [g.to(dev()) for g in graphs]
+    topo = get_topology(gd, need_cell_csr=True, two_hop=not dual).validate()
+    if dual:
+        out = model.encode_process_decode(gd[0].x, gd[1].x_symm, gd[1].x_asym, topo)[2]
+    elif name == "ConservativeI":
+        keep = (~bc).float().unsqueeze(1).expand(-1, 128).contiguous().to(dev())
+        out = model.encode_process_decode(gd[0].x, gd[1].x, topo, e_keep=keep)[2]
+    else:
+        out = model.encode_process_decode(gd[0].x, gd[1].x, topo)[2]
+    assert rel_l2(out, ref["dec"].detach()) < 2e-3
+    (out * r.to(dev())).sum().backward()
+    worst, checked = ("", 0.0), 0
+    for k, p in model.named_parameters():
+        g_ref = params[k].grad
+        if g_ref is None or float(g_ref.abs().max()) == 0.0:
+            continue
+        assert p.grad is not None, k
+        worst = max(worst, (k, rel_l2(p.grad, g_ref)), key=lambda t: t[1])
+        checked += 1
+    assert checked > 100 and worst[1] < GRAD_TOL, (checked, worst)
