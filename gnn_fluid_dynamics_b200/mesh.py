@@ -218,7 +218,7 @@ def mesh_graphs(mesh: Mesh, seed: int = 0, flavour: str = "fvgn", dt: float = 0.
     ``Conservative.py:66-103``): synthetic N(0,1) features on the real connectivity.
 
     flavour 'fvgn': f.x = [du(2), dpos(2), area(1), one_hot(5)];  'conservative': f.x_symm[E,8],
-    f.x_asym[E,4].  ``flip_edges`` applies the training-time random orientation flip
+    f.x_asym[E,4];  'conservative_h': f.x_symm[E,6] (area, one-hot), f.x_asym[E,4].  ``flip_edges`` applies the training-time random orientation flip
     (``utils/transforms.py:3-7``).
     """
     g = torch.Generator().manual_seed(seed)
@@ -257,6 +257,9 @@ def mesh_graphs(mesh: Mesh, seed: int = 0, flavour: str = "fvgn", dt: float = 0.
                               torch.rand(e, 1, generator=g), one_hot], dim=1)
         f.x_asym = torch.cat([torch.randn(e, 2, generator=g),
                               torch.nn.functional.normalize(fnormal, dim=1)], dim=1)
+    elif flavour == "conservative_h":      # ConservativeH features (Conservative.py:916-946)
+        f.x_symm = torch.cat([area_n, one_hot], dim=1)
+        f.x_asym = torch.randn(e, 4, generator=g)         # [du(2), cell edge vector(2)]
     else:
         raise ValueError(flavour)
     v = Data(pos=torch.from_numpy(mesh.vertex_pos).to(f32),

@@ -246,3 +246,98 @@ class ConservativeI(ConservativeG):
 
     class GN_Block(ConservativeG.GN_Block):
         family = "cons_i"
+
+
+class ConservativeH(ConservativeD):
+    """Reference ``ConservativeH`` (Conservative.py:899-1208): symmetric / antisymmetric separation throughout -
+    6 symmetric face features (area, one-hot type), std-scaled antisymmetric features, cell-block-first dual-stream
+    GN_Blocks with the symmetric stream aggregated through the vertices, even / odd decoder heads
+    (``q_n = softplus(even) * tanh(odd)``) and a normal-flux diffusion term in the integrator."""
+    family = "cons_h"
+    _registry_overrides = {}
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.integrator = self.Integrator(config, rho=1)
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 1 + n_class_types(dataset), 0], [0, 5, 0])   # Conservative.py:1012-1013
+
+    @classmethod
+    def normalisation_tables(cls):   # Conservative.py:948-996
+        z, sd = "z_score", "std_scale"
+        kinds = {k: z for k in ["cell_velocity_x", "cell_velocity_y", "cell_velocity_change_x", "cell_velocity_change_y",
+                                "face_area", "face_velocity_x", "face_velocity_y", "face_pressure"]}
+        kinds.update({k: sd for k in ["face_velocity_diff_x", "face_velocity_diff_y", "face_edge_vector_x",
+                                      "face_edge_vector_y"]})
+        inputs = [(0, "x", col(0), "cell_velocity_x"), (0, "x", col(1), "cell_velocity_y"),
+                  (1, "x_asym", col(0), "face_velocity_diff_x"), (1, "x_asym", col(1), "face_velocity_diff_y"),
+                  (1, "x_symm", col(0), "face_area"),
+                  (1, "x_asym", col(2), "face_edge_vector_x"), (1, "x_asym", col(3), "face_edge_vector_y"),
+                  (0, "y", col(0), "cell_velocity_change_x"), (0, "y", col(1), "cell_velocity_change_y"),
+                  (1, "y", col(0), "face_velocity_x"), (1, "y", col(1), "face_velocity_y"),
+                  (1, "y", col(2), "face_pressure")]
+        outputs = [(0, col(0), "cell_velocity_change_x"), (0, col(1), "cell_velocity_change_y"),
+                   (1, col(0), "face_velocity_x"), (1, col(1), "face_velocity_y"), (1, col(2), "face_pressure")]
+        return kinds, inputs, outputs
+
+    def forward(self, graphs, mode="rollout"):   # Conservative.py:1015-1036: two-hop topology + cell CSR
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x_symm
+        c_graph.edge_attr_asym = f_graph.x_asym
+        topo = get_topology(graphs, need_cell_csr=True, two_hop=True)
+        _, _, edge_attr_out = self.encode_process_decode(c_graph.x, f_graph.x_symm, f_graph.x_asym, topo)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
+        output = [acc_pred, edge_attr_out, None]
+        if mode == "rollout":
+            output = self.normalizer.output(output, inverse=True)
+        return {"cell_velocity_change": output[0][:, 0:2], "face_velocity": output[1][:, :2],
+                "face_pressure": output[1][:, 2:3]}
+
+    def encode_process_decode(self, c_x, f_x_symm, f_x_asym, topo, hook=None):
+        prec = self.prec
+        e_s = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
+        e_a = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
+        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        for i, blk in enumerate(self.processer_list):
+            x, e_s, e_a = P.gn_block_dual_two_hop(blk, x, e_s, e_a, topo, prec)
+            if hook is not None:
+                hook(i, x, e_s)
+        self._last_e_asym = e_a
+        # decoder (Conservative.py:1186-1208): even head on cat[h+, h-^2], odd head on cat[h-, h+]
+        n_e = e_s.shape[0]
+        even, _ = P.A.mlp(self.decoder.even_mlp, [P.Seg(e_s), P.Seg(e_a * e_a)], n_e, prec)
+        odd, _ = P.A.mlp(self.decoder.odd_mlp, [P.Seg(e_a), P.Seg(e_s)], n_e, prec, act=ACT_TANH)
+        q_n = torch.nn.functional.softplus(even[:, 3:5]) * torch.tanh(odd)
+        return x, e_s, torch.cat([even[:, 0:3], q_n], dim=-1)
+
+    class Integrator(nn.Module):   # Conservative.py:1038-1083: diffusion term = signed normal flux q . n . area
+        def __init__(self, config, rho):
+            super().__init__()
+            self.rho = rho
+            self.face_area_norm = nn.BatchNorm1d(1)
+            self.face_area = None
+
+        def forward(self, edge_output, c_graph, f_graph, dt):
+            from .Fvgn import flux_dot, normalize_face_area
+            unv, cf = c_graph.normal, f_graph.face
+            area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, dt, self.face_area_norm)
+            self.face_area = area
+            uv, p_face, q_face = edge_output[:, :2], edge_output[:, 2:3], edge_output[:, 3:]
+            uu_vu = torch.cat([uv[:, 0:1] * uv, uv[:, 1:2] * uv], dim=-1)
+            phi_a = sum(flux_dot(uu_vu[cf[j]], unv[:, j, :]) * area[cf[j]] for j in range(3))
+            phi_d = sum(q_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+            phi_p = sum(p_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+            return 1.0 * (-phi_a - phi_p / self.rho) + phi_d
+
+    class GN_Block(ConservativeD.GN_Block):   # same containers, cell block first (Conservative.py:1098-1127)
+        family = "cons_h"
+
+    class Decoder(nn.Module):   # Conservative.py:1186-1208
+        def __init__(self, config, hidden_size, output_sizes):
+            super().__init__()
+            self.even_mlp = build_mlp(config, 2 * hidden_size, hidden_size, 5, norm_layer=False)
+            self.odd_mlp = build_mlp_antisym(config, 2 * hidden_size, hidden_size, 2)

@@ -4,9 +4,9 @@ from .Fvgn import FvgnA  # noqa: F401
 from .Mgn import MgnA  # noqa: F401
 from .Flux import FluxA  # noqa: F401
 from .Conservative import (ConservativeA, ConservativeD, ConservativeE, ConservativeF, ConservativeG,  # noqa: F401
-                           ConservativeI)
+                           ConservativeH, ConservativeI)
 from .VertPot import VertPotA  # noqa: F401
 
 MODEL_CLASSES = {"FvgnA": FvgnA, "MgnA": MgnA, "FluxA": FluxA, "ConservativeA": ConservativeA,
                  "VertPotA": VertPotA, "ConservativeE": ConservativeE, "ConservativeF": ConservativeF, "ConservativeD": ConservativeD,
-                 "ConservativeG": ConservativeG, "ConservativeI": ConservativeI}
+                 "ConservativeG": ConservativeG, "ConservativeI": ConservativeI, "ConservativeH": ConservativeH}

@@ -180,6 +180,20 @@ def gn_block_dual(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32):
     return x_new, s_new, a_new
 
 
+def gn_block_dual_two_hop(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32):
+    """ConservativeH / J GN_Block (Conservative.py:1098-1184), cell block first.  -> (x_new, e_s_new, e_a_new)."""
+    vsum = A.segment_sum(e_s, 0, 0, H, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices, topo.v0, topo.v1)
+    off, perm = topo.build_cell_csr()
+    asym = A.segment_sum(e_a, 0, 0, H, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
+    x_raw, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)], x.shape[0], prec,
+                         residual=x, want_raw=True, want_sum=True)
+    _, s_new = A.mlp(block.face_block_symm.face_mlp, [Seg(e_s), Seg(x_raw, SEG_SUM2, (topo.row, topo.col))],
+                     e_s.shape[0], prec, residual=e_s, want_raw=False, want_sum=True)
+    _, a_new = A.mlp(block.face_block_asym.face_mlp, [Seg(e_a), Seg(x_raw, SEG_DIFF2, (topo.row, topo.col))],
+                     e_a.shape[0], prec, act=ACT_TANH, residual=e_a, want_raw=False, want_sum=True)
+    return x_new, s_new, a_new
+
+
 def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=None, hook=None, e_keep=None):
     """All GN_Blocks.  VertPot's vertex sum is only live after the last block (VertPot.py:208: it is
     overwritten every block and never fed back), so it is computed once."""

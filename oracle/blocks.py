@@ -18,13 +18,13 @@ import torch
 from .mlp import mlp_from_state
 from .scatter import scatter_add
 
-FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f", "cons_d", "cons_g", "cons_i")
+FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f", "cons_d", "cons_g", "cons_i", "cons_h")
 
 _FAMILY_OF = {
     "FvgnA": "fvgn", "FluxA": "fvgn", "MgnA": "mgn", "StreamFuncA": "mgn",
     "ConservativeA": "cons_a", "ConservativeB": "cons_a", "VertPotA": "vertpot",
     "ConservativeE": "cons_e", "ConservativeF": "cons_f", "ConservativeD": "cons_d",
-    "ConservativeG": "cons_g", "ConservativeI": "cons_i",
+    "ConservativeG": "cons_g", "ConservativeI": "cons_i", "ConservativeH": "cons_h", "ConservativeJ": "cons_h",
 }
 
 
@@ -116,6 +116,32 @@ def gn_block_dual(sd, i, x, e_s, e_a, c_edge_index):
     return x + xr, e_s + sr, e_a + ar
 
 
+def gn_block_dual_two_hop(sd, i, x, e_s, e_a, topo):
+    """ConservativeH / J GN_Block (Conservative.py:1098-1184): cell block FIRST - the full symmetric stream summed
+    onto both vertices of each face then the 3-vertex mean, the antisymmetric stream as a signed direct edge->cell
+    sum, cell MLP on cat[x, sym, asym] - then the symmetric (x'[row] + x'[col]) and antisymmetric (x'[row] - x'[col])
+    face blocks on the RAW cell output; residuals on all three streams."""
+    p = f"processer_list.{i}"
+    row, col = topo["c_edge_index"][0], topo["c_edge_index"][1]
+    vidx = torch.cat([topo["v_edge_index"][0], topo["v_edge_index"][1]], dim=0)
+    vsum = scatter_add(torch.cat([e_s, e_s], dim=0), vidx, topo["n_vertices"])
+    vf = topo["v_face"]
+    cell_agg = (vsum.index_select(0, vf[0]) + vsum.index_select(0, vf[1]) + vsum.index_select(0, vf[2])) / 3.0
+    asym = scatter_add(torch.cat([e_a, -e_a], dim=0), torch.cat([col, row], dim=0), x.shape[0])
+    xr = mlp_from_state(sd, f"{p}.cell_block.cell_mlp", torch.cat([x, cell_agg, asym], dim=-1))
+    sr = mlp_from_state(sd, f"{p}.face_block_symm.face_mlp", torch.cat([e_s, xr[row] + xr[col]], dim=1))
+    ar = mlp_from_state(sd, f"{p}.face_block_asym.face_mlp", torch.cat([e_a, xr[row] - xr[col]], dim=1), act="tanh")
+    return x + xr, e_s + sr, e_a + ar
+
+
+def decoder_even_odd(sd, e_s, e_a):
+    """ConservativeH Decoder (Conservative.py:1186-1208): even head on cat[h+, h-^2] -> (u, v, p, |q|(2)); odd
+    (antisymmetric) head on cat[h-, h+] -> sign in (-1, 1);  q_n = softplus(|q|) * tanh(odd)."""
+    even = mlp_from_state(sd, "decoder.even_mlp", torch.cat([e_s, e_a ** 2], dim=-1))
+    odd = torch.tanh(mlp_from_state(sd, "decoder.odd_mlp", torch.cat([e_a, e_s], dim=-1), act="tanh"))
+    return torch.cat([even[:, 0:3], torch.nn.functional.softplus(even[:, 3:5]) * odd], dim=-1)
+
+
 def vertex_block(e, v_edge_index, n_rows):
     """Vertex_Block (VertPot.py:217-222): full-width edge->vertex sum; the output has
     ``cell_graph.x.size(0)`` rows (N, not V) - rows >= V stay zero."""
@@ -203,6 +229,16 @@ def processor_fwd(family, sd, c_x, f_x, topo, mp_num, f_x_asym=None, keep_blocks
 
     ConservativeA quirk reproduced: GN_Block returns a fresh Data without ``edge_attr_asym`` so
     the asym multiply fires in block 0 only (Conservative.py:220, 232-233)."""
+    if family == "cons_h":
+        x, e, ea = encoder_fwd("cons_a", sd, c_x, f_x, f_x_asym)
+        out = {"x0": x, "e0": e, "e0_asym": ea}
+        per_block = []
+        for i in range(mp_num):
+            x, e, ea = gn_block_dual_two_hop(sd, i, x, e, ea, topo)
+            if keep_blocks:
+                per_block.append((x, e, ea))
+        out.update({"x": x, "e": e, "ea": ea, "vx": None, "blocks": per_block, "dec": decoder_even_odd(sd, e, ea)})
+        return out
     if family == "cons_d":
         x, e, ea = encoder_fwd("cons_a", sd, c_x, f_x, f_x_asym)      # same encoder containers as ConservativeA
         out = {"x0": x, "e0": e, "e0_asym": ea}

@@ -27,7 +27,7 @@ import refstub  # noqa: E402
 refstub.install()
 
 from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs  # noqa: E402
-from gnn_fluid_dynamics_b200.testing import default_stats, fill_state_dict_deterministic  # noqa: E402
+from gnn_fluid_dynamics_b200.testing import default_stats, fill_state_dict_deterministic, stats_for  # noqa: E402
 from gnn_fluid_dynamics_b200.graph import Data  # noqa: E402
 
 from utils.config import Config  # noqa: E402  (reference)
@@ -49,6 +49,7 @@ MODELS = {
     "ConservativeD": ("models.Conservative", "ellipse", "conservative"),
     "ConservativeG": ("models.Conservative", "cylinder", "fvgn"),
     "ConservativeI": ("models.Conservative", "airfoil", "fvgn"),
+    "ConservativeH": ("models.Conservative", "cylinder", "conservative_h"),
 }
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1}
@@ -71,7 +72,7 @@ def ref_config():
 def build_ref(name):
     module, kind, flavour = MODELS[name]
     cls = getattr(importlib.import_module(module), name)
-    model = cls(ref_config(), MSE_per_element_torch, _Dataset(), default_stats())
+    model = cls(ref_config(), MSE_per_element_torch, _Dataset(), stats_for(name))
     fill_state_dict_deterministic(model, seed=1)
     return model, kind, flavour
 
@@ -83,7 +84,7 @@ def graphs_for(name, kind, flavour, flip=False):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI"):
+    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
     if name == "ConservativeI":
         # the reference indexes the [E, 128] latent with the face-type mask (Conservative.py:1264-1267), which only

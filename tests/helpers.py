@@ -13,7 +13,7 @@ GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "Fl
                 "ConservativeA": ("cylinder", "conservative"), "VertPotA": ("airfoil", "fvgn"),
                 "ConservativeE": ("ellipse", "fvgn"), "ConservativeF": ("airfoil", "fvgn"),
                 "ConservativeD": ("ellipse", "conservative"), "ConservativeG": ("cylinder", "fvgn"),
-                "ConservativeI": ("airfoil", "fvgn")}
+                "ConservativeI": ("airfoil", "fvgn"), "ConservativeH": ("cylinder", "conservative_h")}
 
 
 def make_config(mp_num=15, precision=None):
@@ -29,8 +29,8 @@ def mse(output, target, mask, batch=None):
 
 def build_model(name, mp_num=15, precision=None, seed=1, device="cpu"):
     from gnn_fluid_dynamics_b200.models import MODEL_CLASSES
-    from gnn_fluid_dynamics_b200.testing import default_stats, fill_state_dict_deterministic
-    model = MODEL_CLASSES[name](make_config(mp_num, precision), mse, None, default_stats())
+    from gnn_fluid_dynamics_b200.testing import fill_state_dict_deterministic, stats_for
+    model = MODEL_CLASSES[name](make_config(mp_num, precision), mse, None, stats_for(name))
     fill_state_dict_deterministic(model, seed=seed)
     return model.to(device)
 
@@ -45,7 +45,7 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI"):
+    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH"):
         f.y = f.y[:, :3].contiguous()
     if name == "ConservativeI":
         f.type = f.type.reshape(-1)      # see tests/golden/make_golden.py: the reference needs a 1-D type tensor here

@@ -302,7 +302,7 @@ def test_vertpot_processor_gradients_vs_oracle():
 
 
 @pytest.mark.parametrize("name", ["ConservativeA", "ConservativeD", "ConservativeE", "ConservativeF", "ConservativeG",
-                                  "ConservativeI"])
+                                  "ConservativeI", "ConservativeH"])
 def test_generic_autograd_path_gradients_vs_oracle(name):
     """Families without a hand-scheduled backward train through the per-op autograd wrappers (autograd_ops.py):
     gradients of a random linear functional of the decoder output w.r.t. every live parameter vs the oracle."""
@@ -314,7 +314,7 @@ def test_generic_autograd_path_gradients_vs_oracle(name):
     c, f, v = graphs
     params = {k: p.detach().clone().requires_grad_(p.is_floating_point()) for k, p in model.state_dict().items()}
     topo_cpu = {"c_edge_index": c.edge_index, "v_edge_index": v.edge_index, "v_face": v.face, "n_vertices": v.num_nodes}
-    dual = name in ("ConservativeA", "ConservativeD")
+    dual = name in ("ConservativeA", "ConservativeD", "ConservativeH")
     bc = ((f.type == 2) | (f.type == 1)).reshape(-1) if name == "ConservativeI" else None
     ref = oracle.processor_fwd(oracle.family_of(name), params, c.x, f.x_symm if dual else f.x, topo_cpu, 15,
                                f_x_asym=f.x_asym if dual else None, bc_mask=bc)
@@ -322,7 +322,7 @@ def test_generic_autograd_path_gradients_vs_oracle(name):
     (ref["dec"] * r).sum().backward()
     model.to(dev())
     gd = [g.to(dev()) for g in graphs]
-    topo = get_topology(gd, need_cell_csr=True, two_hop=not dual).validate()
+    topo = get_topology(gd, need_cell_csr=True, two_hop=(not dual) or name == "ConservativeH").validate()
     if dual:
         out = model.encode_process_decode(gd[0].x, gd[1].x_symm, gd[1].x_asym, topo)[2]
     elif name == "ConservativeI":
