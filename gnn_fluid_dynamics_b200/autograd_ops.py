@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import ops
-from ._lib import ACT_SILU, SEG_DIFF2, SEG_DIRECT, SEG_GATHER, SEG_MEAN3, SEG_SUM2
+from ._lib import ACT_SILU, SEG_DIFF2, SEG_DIRECT, SEG_MEAN3
 from .ops import Seg
 
 _NAMES = ("w1", "b1", "w2", "b2", "w3", "b3", "ln_w", "ln_b")
