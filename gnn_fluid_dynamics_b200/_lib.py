@@ -71,6 +71,7 @@ class MlpBackwardArgs(C.Structure):
         ("d_w3", C.c_void_p), ("d_b3", C.c_void_p), ("d_ln_w", C.c_void_p), ("d_ln_b", C.c_void_p),
         ("din_out", C.c_void_p * 3), ("din_residual", C.c_void_p * 3),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("da1_out", C.c_void_p), ("skip_wgrad_l1", C.c_int32),
     ]
 
 

@@ -124,7 +124,7 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
   if (f->rows == 0) {
     // no rows: parameter gradients are zero
     const int k = f->k_in, n = f->n_out;
-    if (b->d_w1) GNNFD_CUDA(cudaMemsetAsync(b->d_w1, 0, (size_t)128 * k * 4, stream));
+    if (b->d_w1 && !b->skip_wgrad_l1) GNNFD_CUDA(cudaMemsetAsync(b->d_w1, 0, (size_t)128 * k * 4, stream));
     if (b->d_w2) GNNFD_CUDA(cudaMemsetAsync(b->d_w2, 0, (size_t)128 * 128 * 4, stream));
     if (b->d_w3) GNNFD_CUDA(cudaMemsetAsync(b->d_w3, 0, (size_t)n * 128 * 4, stream));
     if (b->d_b1) GNNFD_CUDA(cudaMemsetAsync(b->d_b1, 0, 128 * 4, stream));
@@ -135,12 +135,12 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
     return GNNFD_OK;
   }
   GNNFD_CHECK_ARG(b->g && b->a1 && b->a2 && b->packed_bwd && b->workspace, "null pointer");
-  GNNFD_CHECK_ARG(b->d_w1 && b->d_w2 && b->d_w3, "null weight-gradient output");
+  GNNFD_CHECK_ARG((b->d_w1 || b->skip_wgrad_l1) && b->d_w2 && b->d_w3, "null weight-gradient output");
   const BwdLayout L = bwd_layout(f);
   if (b->workspace_bytes < L.total) { set_error("gnnfd_mlp_backward: workspace too small"); return GNNFD_E_WORKSPACE; }
   uint8_t *ws = (uint8_t *)b->workspace;
   const uint8_t *pk = (const uint8_t *)b->packed_bwd;
-  float *da2 = (float *)(ws + L.da2), *da1 = (float *)(ws + L.da1), *sums = (float *)(ws + L.sums);
+  float *da2 = (float *)(ws + L.da2), *da1 = b->da1_out ? b->da1_out : (float *)(ws + L.da1), *sums = (float *)(ws + L.sums);
   void *wgws = ws + L.wgws;
   const size_t wgws_bytes = L.total - L.wgws;
   const int code = f->act + 1;   // SiLU -> 1, tanh -> 2
@@ -208,12 +208,14 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
   }
   // ---- dW1 = dA1^T In (In assembled from the forward's segments), remaining segment input gradients
   {
-    gnnfd_wgrad_args w{};
-    w.rows = f->rows;
-    w.a = direct(da1, 128, 128); w.n_b = f->n_seg;
-    for (int s = 0; s < f->n_seg; ++s) w.b[s] = f->seg[s];
-    w.out = b->d_w1; w.ld_out = f->k_in; w.colsum = b->d_b1;
-    if ((rc = gnnfd_wgrad(&w, wgws, wgws_bytes, stream)) != GNNFD_OK) return rc;
+    if (!b->skip_wgrad_l1) {
+      gnnfd_wgrad_args w{};
+      w.rows = f->rows;
+      w.a = direct(da1, 128, 128); w.n_b = f->n_seg;
+      for (int s = 0; s < f->n_seg; ++s) w.b[s] = f->seg[s];
+      w.out = b->d_w1; w.ld_out = f->k_in; w.colsum = b->d_b1;
+      if ((rc = gnnfd_wgrad(&w, wgws, wgws_bytes, stream)) != GNNFD_OK) return rc;
+    }
     int col0 = 0;
     for (int s = 0; s < f->n_seg; ++s) {
       if (b->din_out[s] != nullptr && !(chain && s == 0)) {

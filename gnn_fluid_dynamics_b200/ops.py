@@ -284,7 +284,8 @@ def mlp_backward_workspace(rows: int, device) -> torch.Tensor:
 
 
 def mlp_backward(segs: Sequence[Seg], w: MLPWeights, st: "MLPStash", rows: int, g: torch.Tensor, precision: int,
-                 din: Sequence[Optional[dict]], workspace: torch.Tensor):
+                 din: Sequence[Optional[dict]], workspace: torch.Tensor, da1_out: Optional[torch.Tensor] = None,
+                 skip_wgrad_l1: bool = False):
     """Whole backward of one fused MLP in one C call (gnnfd_mlp_backward).  ``din[i]`` is None or a dict with
     optional ``residual`` / ``out``.  Returns ({name: grad} for w1,b1,w2,b2,w3,b3,ln_w,ln_b present, [dIn_i])."""
     b = MlpBackwardArgs()
@@ -328,6 +329,7 @@ def mlp_backward(segs: Sequence[Seg], w: MLPWeights, st: "MLPStash", rows: int, 
         b.din_residual[i] = _req(res, torch.float32, "residual").data_ptr() if res is not None else None
         dins.append(out)
     b.workspace, b.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    b.da1_out, b.skip_wgrad_l1 = _ptr(da1_out), int(skip_wgrad_l1)     # see gnnfd_mlp_backward_args
     check(lib.gnnfd_mlp_backward(C.byref(b), _stream()), "gnnfd_mlp_backward")
     _count((2 if w.has_ln else 0) + 6 + 2 + sum(1 for d in dins if d is not None))
     del keep
@@ -398,7 +400,8 @@ def wgrad(a: Seg, b: Sequence[Seg], rows: int, out: torch.Tensor, a_act: int = 0
     n_pad, g = 0, (32 if single_pass else 64)          # column padding of the operand images (TF32 / split-bf16 atoms)
     for i, s in enumerate(b):
         n_pad += (_fill_segment(args.b[i], s, f"b[{i}]") + g - 1) // g * g
-    _req(out, torch.float32, "out")
+    if not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.stride(1) == 1):
+        raise RuntimeError("wgrad: out must be a CUDA fp32 matrix with unit column stride (column blocks are fine)")
     args.out, args.ld_out, args.transpose_out = out.data_ptr(), out.stride(0), int(transpose_out)
     args.colsum, args.colsum_of_b = _ptr(colsum), int(colsum_of_b)
     args.precision = 1 if single_pass else 0

@@ -66,6 +66,17 @@ class MeshTopology:
             self._rowcol = ops.csr_build(torch.cat([self.row, self.col]), self.n_cells)
         return self._rowcol
 
+    def build_row_csr(self):
+        """CSR of ``row`` alone over cells (edge -> first cell): the node-side reduction of edge gradients."""
+        if getattr(self, "_rowcsr", None) is None:
+            self._rowcsr = ops.csr_build(self.row, self.n_cells)
+        return self._rowcsr
+
+    def build_col_csr(self):
+        if getattr(self, "_colcsr", None) is None:
+            self._colcsr = ops.csr_build(self.col, self.n_cells)
+        return self._colcsr
+
     def build_vf_csr(self):
         """CSR of cat[vf0; vf1; vf2] over vertices: the transpose of the 3-vertex mean (Fvgn.py:317-321)."""
         if getattr(self, "_vfcsr", None) is None:

@@ -55,6 +55,40 @@ def mlp_backward(w: MLPWeights, st: MLPStash, segs: Sequence[Seg], rows: int, g:
     return [grads.get(n) for n in PARAM_NAMES], dins
 
 
+def edge_mlp_backward_node_side(w: MLPWeights, st: MLPStash, e_in, x_src, topo: MeshTopology, g, d_e_res, d_x_base,
+                                prec: int, workspace: torch.Tensor):
+    """Backward of the concat-form face MLP  e' = MLP(cat[e, x[row], x[col]])  with the gathered part done on the NODE
+    side.  By linearity  sum_k dA1[k]^T x[row[k]] = S_row^T x  and  sum_{row[k]=n} dA1[k] W = S_row[n] W  with
+    S_row = segment-sum of dA1 by row (likewise col): dA1 is reduced onto the cells once (two deterministic CSR sums
+    onto [N, 128] matrices) and the weight-gradient GEMMs of the two gathered column blocks and the input-gradient
+    Linear then run over N contiguous node rows instead of E gathered edge rows, with no [E, 128] temporaries.
+    Returns (parameter gradients in PARAM_NAMES order, d_e = d_e_res + dIn_0, d_x = d_x_base + dIn_row + dIn_col)."""
+    E, N = e_in.shape[0], x_src.shape[0]
+    dev = g.device
+    d_a1 = torch.empty(E, H, dtype=torch.float32, device=dev)
+    segs = _edge_segs(e_in, x_src, topo)
+    grads, dins = ops.mlp_backward(segs, w, st, E, g, prec, [{"residual": d_e_res} if d_e_res is not None else {}, None, None],
+                                   workspace, da1_out=d_a1, skip_wgrad_l1=True)
+    # dW1[:, 0:128] = dA1^T e, db1 = column sums of dA1
+    w1g = grads["w1"]
+    ops.wgrad(Seg(d_a1), [Seg(e_in)], E, w1g[:, 0:H], colsum=grads.get("b1"))
+    # S_row, S_col: dA1 reduced onto the cells (deterministic CSR sums)
+    r_off, r_perm = topo.build_row_csr()
+    c_off, c_perm = topo.build_col_csr()
+    s_row = ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, r_off, r_perm, N)
+    s_col = ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, c_off, c_perm, N)
+    # dW1[:, 128:256] = S_row^T x, dW1[:, 256:384] = S_col^T x   (N rows, contiguous operands)
+    ops.wgrad(Seg(s_row), [Seg(x_src)], N, w1g[:, H:2 * H])
+    ops.wgrad(Seg(s_col), [Seg(x_src)], N, w1g[:, 2 * H:3 * H])
+    # d x = base + S_row W1[:, 128:256] + S_col W1[:, 256:384]   (two Linears over N rows, accumulated in place)
+    if w.bwd_packs is None:
+        w.bwd_packs = {}
+    packs = w.bwd_packs.setdefault("node_side", {})
+    d_x = ops.linear_tc(Seg(s_row), N, w.w1[:, H:], 1, 3 * H, H, H, packs, "w1t_row", prec, residual=d_x_base)
+    d_x = ops.linear_tc(Seg(s_col), N, w.w1[:, 2 * H:], 1, 3 * H, H, H, packs, "w1t_col", prec, residual=d_x, out=d_x)
+    return [grads.get(n) for n in PARAM_NAMES], dins[0], d_x
+
+
 def mlp_backward_stepwise(w: MLPWeights, st: MLPStash, segs: Sequence[Seg], rows: int, g: torch.Tensor, prec: int,
                           din: Sequence[Optional[dict]], workspace: Optional[torch.Tensor] = None):
     """The same chain issued kernel by kernel from Python (used by the tests to pin the fused call).  ``g`` = gradient w.r.t. the MLP(+LN) output.  ``din[i]`` is None (segment i
@@ -190,7 +224,6 @@ class EncodeProcessDecode(torch.autograd.Function):
         N, E, V = c_x.shape[0], f_x.shape[0], topo.n_vertices
         dev = g_out.device
         ws = ops.mlp_backward_workspace(max(N, E), dev)
-        rc_off, rc_perm = topo.build_rowcol_csr()
         vf_off, vf_perm = topo.build_vf_csr()
         site_grads = {}
 
@@ -210,10 +243,7 @@ class EncodeProcessDecode(torch.autograd.Function):
             if fam == "fvgn":
                 # e_new = e + edge(e, x_raw[row], x_raw[col]);  x_new = x + x_raw;  x_raw = node(x, mean3(S(e)))
                 g_edge, g_extra = (g_extra, None) if g_extra is not None else (d_e, None)
-                ge, dins = mlp_backward(we, st_e, _edge_segs(e_in, x_raw, topo), E, g_edge, prec,
-                                        [{"residual": d_e}, {}, {}], ws)
-                d_e_acc, t1, t2 = dins
-                d_x_raw = ops.segment_sum3(t1, t2, None, (0, 0, 0), H, 1.0, E, rc_off, rc_perm, N, base=d_x)
+                ge, d_e_acc, d_x_raw = edge_mlp_backward_node_side(we, st_e, e_in, x_raw, topo, g_edge, d_e, d_x, prec, ws)
                 gn, dins = mlp_backward(wn, st_n, _node_segs(x_in, vsum, topo), N, d_x_raw, prec,
                                         [{"residual": d_x} if d_x is not None else {}, {}], ws)
                 d_x, t3 = dins
@@ -226,10 +256,7 @@ class EncodeProcessDecode(torch.autograd.Function):
                 d_x_acc, t3 = dins
                 d_vsum = ops.segment_sum3(t3, None, None, (0, 0, 0), H // 2, 1.0, N, vf_off, vf_perm, V, scale=1.0 / 3.0)
                 d_e_raw = ops.gather_pair_add(d_vsum, topo.v0, topo.v1, 1.0, True, E, base=d_e)
-                ge, dins = mlp_backward(we, st_e, _edge_segs(e_in, x_in, topo), E, d_e_raw, prec,
-                                        [{"residual": d_e} if d_e is not None else {}, {}, {}], ws)
-                d_e, t1, t2 = dins
-                d_x = ops.segment_sum3(t1, t2, None, (0, 0, 0), H, 1.0, E, rc_off, rc_perm, N, base=d_x_acc)
+                ge, d_e, d_x = edge_mlp_backward_node_side(we, st_e, e_in, x_in, topo, d_e_raw, d_e, d_x_acc, prec, ws)
             site_grads[id(node_site)], site_grads[id(edge_site)] = gn, ge
 
         if d_e is None:

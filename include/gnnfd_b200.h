@@ -235,6 +235,13 @@ typedef struct {
   const float *din_residual[3];
   void *workspace;
   size_t workspace_bytes;
+  /* Optional: da1_out [rows, 128] receives dA1 (the gradient at the first hidden pre-activation) and, with
+   * skip_wgrad_l1 = 1, the library leaves dW1 / db1 to the caller.  Used when the MLP input gathers rows of a node
+   * matrix: by linearity sum_e dA1[e]^T x[row[e]] = (segment-sum of dA1 by row)^T x, so the caller reduces dA1 onto
+   * the nodes first and runs the weight-gradient GEMM and the input-gradient Linear over N node rows instead of E
+   * gathered edge rows (gnn_fluid_dynamics_b200/training.py). */
+  float *da1_out;
+  int32_t skip_wgrad_l1;
 } gnnfd_mlp_backward_args;
 size_t gnnfd_mlp_backward_workspace_bytes(const gnnfd_mlp_args *fwd);
 size_t gnnfd_pack_mlp_backward_bytes(const gnnfd_mlp_args *fwd);
