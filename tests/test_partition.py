@@ -140,3 +140,34 @@ def test_world2_gloo_halo_exchange_matches_unpartitioned(tmp_path, name, family)
         assert torch.allclose(torch.from_numpy(d["e"]), ref["e"][faces], rtol=0, atol=2e-6)
         seen[cells] = True
     assert bool(seen.all())
+
+
+def _dp_rank(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from gnn_fluid_dynamics_b200.dist import allreduce_gradients
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2))]
+        g = torch.Generator().manual_seed(100 + rank)
+        params[0].grad = torch.randn(5, 3, generator=g)
+        params[1].grad = torch.randn(7, generator=g)      # params[2] has no gradient (unused parameter)
+        allreduce_gradients(params, world)
+        np.savez(os.path.join(out_dir, f"dp{rank}.npz"), g0=params[0].grad.numpy(), g1=params[1].grad.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_gloo_data_parallel_gradient_allreduce(tmp_path):
+    """Independent meshes per rank (BASELINE.json configs 2 / 5): one flat all-reduce averages every gradient."""
+    world = 2
+    mp.spawn(_dp_rank, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    exp0 = sum(torch.randn(5, 3, generator=torch.Generator().manual_seed(100 + r)) for r in range(world)) / world
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(world)]
+    for g in gens:
+        torch.randn(5, 3, generator=g)
+    exp1 = sum(torch.randn(7, generator=g) for g in gens) / world
+    for r in range(world):
+        d = np.load(tmp_path / f"dp{r}.npz")
+        assert np.allclose(d["g0"], exp0.numpy(), atol=1e-7) and np.allclose(d["g1"], exp1.numpy(), atol=1e-7)
