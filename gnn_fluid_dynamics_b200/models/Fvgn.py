@@ -186,3 +186,83 @@ class FvgnA(Model):
 
         def forward(self, graph, prec=0):
             return P.mlp_rows(self.face_mlp, graph.edge_attr, prec)
+
+
+class FvgnF(FvgnA):
+    """Reference ``FvgnF`` (Fvgn.py:881-1002): ONE GN_Block whose weights are shared by all ``mp_num`` message-passing
+    steps; every MLP input carries an extra constant column ``(step + 1) / mp_num``.  A constant input column is a
+    bias: ``W1 [in | c] + b1 = W1[:, :-1] in + (b1 + c W1[:, -1])``, so the kernels run the ordinary K = 384 / 192
+    blocks with a per-step effective first-layer bias and the shared operand pack (state_dict layout unchanged:
+    ``gn_block.{face,cell}_block.*`` with 385 / 193 input columns, plus FvgnA's unused ``processer_list``)."""
+    family = "fvgn_f"
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.encoder = self.Encoder(config, self.input_sizes, self.hidden_size)
+        self.gn_block = self.GN_Block(config, self.hidden_size)
+        self.decoder = self.Decoder(config, self.hidden_size, self.output_sizes)
+        self.mp_num = config.model.mp_num
+
+    def _step_weights(self, seq):
+        """Per-step MLPWeights of a shared MLP: W1 without its last column, b1 + step * W1[:, -1]; cached until a
+        parameter changes."""
+        inner, ln = P._split_mlp(seq)
+        lin = [m for m in inner if isinstance(m, nn.Linear)]
+        params = [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias, ln.weight, ln.bias]
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        cached = getattr(seq, "_gnnfd_step_w", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        w1 = lin[0].weight.detach()
+        w1_main, w1_step = w1[:, :-1].contiguous(), w1[:, -1]
+        out = []
+        for i in range(self.mp_num):
+            b1 = (lin[0].bias.detach() + ((i + 1) / self.mp_num) * w1_step).contiguous()
+            out.append(P.MLPWeights(w1=w1_main, b1=b1, w2=lin[1].weight.detach(), b2=lin[1].bias.detach(),
+                                    w3=lin[2].weight.detach(), b3=lin[2].bias.detach(), ln_w=ln.weight.detach(),
+                                    ln_b=ln.bias.detach(), has_ln=True, ln_eps=ln.eps))
+        object.__setattr__(seq, "_gnnfd_step_w", (key, out))
+        return out
+
+    def encode_process_decode(self, c_x, f_x, topo, hook=None):
+        prec = self.prec
+        if self.wants_grad():
+            raise NotImplementedError("FvgnF runs forward / rollout only on the B200 path (wrap the call in torch.no_grad())")
+        ops, Seg = P.ops, P.Seg
+        e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
+        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        wn_steps = self._step_weights(self.gn_block.cell_block.cell_mlp)
+        we_steps = self._step_weights(self.gn_block.face_block.face_mlp)
+        for i in range(self.mp_num):
+            wn, we = wn_steps[i], we_steps[i]
+            for w, first in ((wn, wn_steps[0]), (we, we_steps[0])):
+                if w is not first and first.packed is not None and w.packed is None:
+                    w.packed, w.packed_prec = first.packed, first.packed_prec
+            vsum = P.vertex_half_sum(e, topo)
+            x_raw, x_new = ops.mlp_forward([Seg(x), Seg(vsum, P.SEG_MEAN3, topo.vf)], wn, x.shape[0], prec,
+                                           residual=x, want_raw=True, want_sum=True)
+            _, e_new = ops.mlp_forward([Seg(e), Seg(x_raw, P.SEG_GATHER, (topo.row,)), Seg(x_raw, P.SEG_GATHER, (topo.col,))],
+                                       we, e.shape[0], prec, residual=e, want_raw=False, want_sum=True)
+            x, e = x_new, e_new
+            if hook is not None:
+                hook(i, x, e)
+        return x, e, P.mlp_rows(self.decoder.face_mlp, e, prec)
+
+    class GN_Block(nn.Module):   # Fvgn.py:940-996
+        family = "fvgn_f"
+
+        def __init__(self, config, hidden_size):
+            super().__init__()
+            self.face_block = self.Face_Block(config, hidden_size)
+            self.cell_block = self.Cell_Block(config, hidden_size)
+
+        class Face_Block(nn.Module):
+            def __init__(self, config, hidden_size):
+                super().__init__()
+                self.face_mlp = build_mlp(config, hidden_size * 3 + 1, hidden_size, hidden_size)
+
+        class Cell_Block(nn.Module):
+            def __init__(self, config, hidden_size, mp_times=2):
+                super().__init__()
+                self.cell_mlp = build_mlp(config, hidden_size + hidden_size // 2 + 1, hidden_size, hidden_size)
+                self.mp_times = mp_times

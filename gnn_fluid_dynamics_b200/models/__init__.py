@@ -1,12 +1,12 @@
 """B200-native drop-ins for the reference's ``src/models`` modules (same module and class names, so
 ``config.model.module = "gnn_fluid_dynamics_b200.models.Fvgn"``, ``config.model.name = "FvgnA"``)."""
-from .Fvgn import FvgnA  # noqa: F401
+from .Fvgn import FvgnA, FvgnF  # noqa: F401
 from .Mgn import MgnA  # noqa: F401
 from .Flux import FluxA  # noqa: F401
 from .Conservative import (ConservativeA, ConservativeD, ConservativeE, ConservativeF, ConservativeG,  # noqa: F401
                            ConservativeH, ConservativeI)
 from .VertPot import VertPotA  # noqa: F401
 
-MODEL_CLASSES = {"FvgnA": FvgnA, "MgnA": MgnA, "FluxA": FluxA, "ConservativeA": ConservativeA,
+MODEL_CLASSES = {"FvgnA": FvgnA, "FvgnF": FvgnF, "MgnA": MgnA, "FluxA": FluxA, "ConservativeA": ConservativeA,
                  "VertPotA": VertPotA, "ConservativeE": ConservativeE, "ConservativeF": ConservativeF, "ConservativeD": ConservativeD,
                  "ConservativeG": ConservativeG, "ConservativeI": ConservativeI, "ConservativeH": ConservativeH}

@@ -18,13 +18,14 @@ import torch
 from .mlp import mlp_from_state
 from .scatter import scatter_add
 
-FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f", "cons_d", "cons_g", "cons_i", "cons_h")
+FAMILIES = ("fvgn", "mgn", "cons_a", "vertpot", "cons_e", "cons_f", "cons_d", "cons_g", "cons_i", "cons_h", "fvgn_f")
 
 _FAMILY_OF = {
     "FvgnA": "fvgn", "FluxA": "fvgn", "MgnA": "mgn", "StreamFuncA": "mgn",
     "ConservativeA": "cons_a", "ConservativeB": "cons_a", "VertPotA": "vertpot",
     "ConservativeE": "cons_e", "ConservativeF": "cons_f", "ConservativeD": "cons_d",
     "ConservativeG": "cons_g", "ConservativeI": "cons_i", "ConservativeH": "cons_h", "ConservativeJ": "cons_h",
+    "FvgnF": "fvgn_f",
 }
 
 
@@ -229,6 +230,25 @@ def processor_fwd(family, sd, c_x, f_x, topo, mp_num, f_x_asym=None, keep_blocks
 
     ConservativeA quirk reproduced: GN_Block returns a fresh Data without ``edge_attr_asym`` so
     the asym multiply fires in block 0 only (Conservative.py:220, 232-233)."""
+    if family == "fvgn_f":
+        # FvgnF (Fvgn.py:881-1002): ONE shared GN_Block (keys gn_block.*) applied mp_num times, every MLP input gets
+        # the constant column (step + 1) / mp_num appended
+        x, e, _ = encoder_fwd("fvgn", sd, c_x, f_x)
+        out = {"x0": x, "e0": e}
+        per_block = []
+        row, col = topo["c_edge_index"][0], topo["c_edge_index"][1]
+        for i in range(mp_num):
+            step = (i + 1) / mp_num
+            agg, _ = two_hop_aggregate(e, topo["v_edge_index"], topo["v_face"], topo["n_vertices"])
+            xr = mlp_from_state(sd, "gn_block.cell_block.cell_mlp",
+                                torch.cat([x, agg, torch.full((x.shape[0], 1), step, dtype=x.dtype)], dim=-1))
+            er = mlp_from_state(sd, "gn_block.face_block.face_mlp",
+                                torch.cat([e, xr[row], xr[col], torch.full((e.shape[0], 1), step, dtype=e.dtype)], dim=1))
+            x, e = x + xr, e + er
+            if keep_blocks:
+                per_block.append((x, e))
+        out.update({"x": x, "e": e, "vx": None, "blocks": per_block, "dec": mlp_from_state(sd, "decoder.face_mlp", e)})
+        return out
     if family == "cons_h":
         x, e, ea = encoder_fwd("cons_a", sd, c_x, f_x, f_x_asym)
         out = {"x0": x, "e0": e, "e0_asym": ea}

@@ -50,6 +50,7 @@ MODELS = {
     "ConservativeG": ("models.Conservative", "cylinder", "fvgn"),
     "ConservativeI": ("models.Conservative", "airfoil", "fvgn"),
     "ConservativeH": ("models.Conservative", "cylinder", "conservative_h"),
+    "FvgnF": ("models.Fvgn", "airfoil", "fvgn"),
 }
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1}
@@ -84,7 +85,7 @@ def graphs_for(name, kind, flavour, flip=False):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH"):
+    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
     if name == "ConservativeI":
         # the reference indexes the [E, 128] latent with the face-type mask (Conservative.py:1264-1267), which only
@@ -137,8 +138,17 @@ def gen_forward(name):
             cap["dec"] = out.clone()
 
     model.encoder.register_forward_hook(grab_enc)
-    model.processer_list[0].register_forward_hook(grab_block(1))
-    model.processer_list[-1].register_forward_hook(grab_block(15))
+    if hasattr(model, "gn_block"):      # FvgnF: ONE shared block applied mp_num times
+        calls = {"n": 0}
+
+        def grab_shared(mod, inp, out):
+            calls["n"] = calls["n"] % 15 + 1
+            if calls["n"] in (1, 15):
+                grab_block(calls["n"])(mod, inp, out)
+        model.gn_block.register_forward_hook(grab_shared)
+    else:
+        model.processer_list[0].register_forward_hook(grab_block(1))
+        model.processer_list[-1].register_forward_hook(grab_block(15))
     model.decoder.register_forward_hook(grab_dec)
 
     out = {}

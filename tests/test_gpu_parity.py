@@ -172,7 +172,7 @@ def _run_processor(name, model, graphs_dev):
     return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
 
 
-@pytest.mark.parametrize("name", ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH"])
+@pytest.mark.parametrize("name", ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"])
 def test_processor_matches_reference_golden(name):
     gold = load_golden(f"fwd_{name}.npz")
     model = build_model(name).eval()
@@ -197,7 +197,7 @@ def test_processor_matches_reference_golden(name):
             assert rel_l2(out["dec_vertex"], torch.from_numpy(gold["dec_vertex"])) < 2 * t
 
 
-@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH"])
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"])
 @pytest.mark.parametrize("mode", ["train", "rollout"])
 def test_full_forward_matches_reference_golden(name, mode):
     gold = load_golden(f"fwd_{name}.npz")

@@ -13,7 +13,7 @@ from gnn_fluid_dynamics_b200.mesh import connectivity
 from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
 from helpers import GOLDEN, LOSS_W, build_model, golden_graphs, load_golden
 
-MODELS = ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH"]
+MODELS = ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"]
 TOL = 2e-5   # fp32 CPU restatement vs fp32 CPU reference: summation-order noise only
 
 
