@@ -341,3 +341,93 @@ class ConservativeH(ConservativeD):
             super().__init__()
             self.even_mlp = build_mlp(config, 2 * hidden_size, hidden_size, 5, norm_layer=False)
             self.odd_mlp = build_mlp_antisym(config, 2 * hidden_size, hidden_size, 2)
+
+
+def _padded_head(seq, act, n_valid, h=128):
+    """MLPWeights of a 3-Linear MLP whose last Linear has ``n_valid`` < 128 outputs, zero-padded to 128 output rows so
+    the 128-wide kernel path runs it; columns >= n_valid of the result are exactly zero.  Cached per weights version."""
+    w = P.weights_of(seq, act)
+    cached = getattr(w, "_padded", None)
+    if cached is None:
+        w3 = torch.zeros(h, w.w3.shape[1], dtype=torch.float32, device=w.w3.device)
+        w3[:n_valid] = w.w3
+        b3 = None
+        if w.b3 is not None:
+            b3 = torch.zeros(h, dtype=torch.float32, device=w.w3.device)
+            b3[:n_valid] = w.b3
+        cached = P.MLPWeights(w1=w.w1, b1=w.b1, w2=w.w2, b2=w.b2, w3=w3, b3=b3, has_ln=False, act=act)
+        w._padded = cached
+    return cached
+
+
+class ConservativeK(ConservativeH):
+    """Reference ``ConservativeK`` (Conservative.py:1685-1954): ConservativeH with the antisymmetric edge stream at HALF
+    the hidden width.  The 64-wide stream is carried as a [E, 128] matrix whose upper 64 columns are identically zero
+    (its MLPs run the 128-wide kernel path with the last Linear zero-padded to 128 output rows), so every consumer
+    simply reads a 64-column segment of it; forward / rollout only."""
+    family = "cons_h"
+
+    def encode_process_decode(self, c_x, f_x_symm, f_x_asym, topo, hook=None):
+        prec, hh = self.prec, self.hidden_size // 2
+        if self.wants_grad():
+            raise NotImplementedError("ConservativeK runs forward / rollout only on the B200 path (wrap the call in torch.no_grad())")
+        ops, Seg = P.ops, P.Seg
+        e_s = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
+        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        e_a, _ = ops.mlp_forward([Seg(f_x_asym.contiguous())], _padded_head(self.encoder.faceA_mlp, ACT_TANH, hh),
+                                 f_x_asym.shape[0], prec)                               # [E, 128], columns 64.. = 0
+        off, perm = topo.build_cell_csr()
+        for i, blk in enumerate(self.processer_list):
+            vsum = ops.segment_sum(e_s, e_s, 0, 0, P.H, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices)
+            asym = ops.segment_sum(e_a, e_a, 0, 0, hh, -1.0, off, perm, topo.n_cells)   # [N, 64]
+            x_raw, x_new = ops.mlp_forward([Seg(x), Seg(vsum, P.SEG_MEAN3, topo.vf), Seg(asym)],
+                                           P.weights_of(blk.cell_block.cell_mlp), x.shape[0], prec, residual=x,
+                                           want_raw=True, want_sum=True)
+            _, s_new = ops.mlp_forward([Seg(e_s), Seg(x_raw, P.SEG_SUM2, (topo.row, topo.col))],
+                                       P.weights_of(blk.face_block_symm.face_mlp), e_s.shape[0], prec, residual=e_s,
+                                       want_raw=False, want_sum=True)
+            _, a_new = ops.mlp_forward([Seg(e_a, width=hh), Seg(x_raw, P.SEG_DIFF2, (topo.row, topo.col))],
+                                       _padded_head(blk.face_block_asym.face_mlp, ACT_TANH, hh), e_a.shape[0], prec,
+                                       residual=e_a, want_raw=False, want_sum=True)
+            x, e_s, e_a = x_new, s_new, a_new
+            if hook is not None:
+                hook(i, x, e_s)
+        self._last_e_asym = e_a[:, :hh]
+        n_e = e_s.shape[0]
+        ea_sq = (e_a[:, :hh] * e_a[:, :hh]).contiguous()
+        even, _ = ops.mlp_forward([Seg(e_s), Seg(ea_sq)], P.weights_of(self.decoder.even_mlp), n_e, prec)
+        odd, _ = ops.mlp_forward([Seg(e_a, width=hh), Seg(e_s)], P.weights_of(self.decoder.odd_mlp, ACT_TANH), n_e, prec)
+        q_n = torch.nn.functional.softplus(even[:, 3:5]) * torch.tanh(odd)
+        return x, e_s, torch.cat([even[:, 0:3], q_n], dim=-1)
+
+    class Encoder(nn.Module):   # Conservative.py:1848-1860
+        def __init__(self, config, input_sizes, hidden_size):
+            super().__init__()
+            self.faceA_mlp = build_mlp_antisym(config, 4, hidden_size, hidden_size // 2)
+            self.faceS_mlp = build_mlp(config, input_sizes[1], hidden_size, hidden_size)
+            self.cell_mlp = build_mlp(config, input_sizes[0], hidden_size, hidden_size)
+
+    class GN_Block(nn.Module):   # Conservative.py:1862-1934
+        family = "cons_h"
+
+        def __init__(self, config, hidden_size):
+            super().__init__()
+            self.face_block_symm = ConservativeD.GN_Block.Face_Block_Symm(config, hidden_size)
+            self.face_block_asym = self.Face_Block_Asym(config, hidden_size)
+            self.cell_block = self.Cell_Block(config, hidden_size)
+
+        class Face_Block_Asym(nn.Module):
+            def __init__(self, config, hidden_size):
+                super().__init__()
+                self.face_mlp = build_mlp_antisym(config, hidden_size // 2 + hidden_size, hidden_size, hidden_size // 2)
+
+        class Cell_Block(nn.Module):
+            def __init__(self, config, hidden_size):
+                super().__init__()
+                self.cell_mlp = build_mlp(config, 2 * hidden_size + hidden_size // 2, hidden_size, hidden_size)
+
+    class Decoder(nn.Module):   # Conservative.py:1936-1954
+        def __init__(self, config, hidden_size, output_sizes):
+            super().__init__()
+            self.even_mlp = build_mlp(config, hidden_size + hidden_size // 2, hidden_size, 5, norm_layer=False)
+            self.odd_mlp = build_mlp_antisym(config, hidden_size + hidden_size // 2, hidden_size, 2)

@@ -4,9 +4,10 @@ from .Fvgn import FvgnA, FvgnF  # noqa: F401
 from .Mgn import MgnA  # noqa: F401
 from .Flux import FluxA  # noqa: F401
 from .Conservative import (ConservativeA, ConservativeD, ConservativeE, ConservativeF, ConservativeG,  # noqa: F401
-                           ConservativeH, ConservativeI)
+                           ConservativeH, ConservativeI, ConservativeK)
 from .VertPot import VertPotA  # noqa: F401
 
 MODEL_CLASSES = {"FvgnA": FvgnA, "FvgnF": FvgnF, "MgnA": MgnA, "FluxA": FluxA, "ConservativeA": ConservativeA,
                  "VertPotA": VertPotA, "ConservativeE": ConservativeE, "ConservativeF": ConservativeF, "ConservativeD": ConservativeD,
-                 "ConservativeG": ConservativeG, "ConservativeI": ConservativeI, "ConservativeH": ConservativeH}
+                 "ConservativeG": ConservativeG, "ConservativeI": ConservativeI, "ConservativeH": ConservativeH,
+                 "ConservativeK": ConservativeK}

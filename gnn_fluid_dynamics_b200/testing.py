@@ -34,7 +34,7 @@ def stats_for(model_name: str):
     """``default_stats()`` plus the extra registry keys a model family uses (ConservativeH: the std-scaled
     face_velocity_diff_x / _y, Conservative.py:948-962).  Kept separate so the other models' fixtures do not move."""
     out = default_stats()
-    if model_name in ("ConservativeH", "ConservativeJ"):
+    if model_name in ("ConservativeH", "ConservativeJ", "ConservativeK"):
         for i, k in enumerate(("face_velocity_diff_x", "face_velocity_diff_y")):
             out[k] = {"mean": 0.07 + 0.03 * i, "std": 1.2 + 0.1 * i, "min": -1.0, "max": 1.0}
     return out

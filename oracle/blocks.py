@@ -25,7 +25,7 @@ _FAMILY_OF = {
     "ConservativeA": "cons_a", "ConservativeB": "cons_a", "VertPotA": "vertpot",
     "ConservativeE": "cons_e", "ConservativeF": "cons_f", "ConservativeD": "cons_d",
     "ConservativeG": "cons_g", "ConservativeI": "cons_i", "ConservativeH": "cons_h", "ConservativeJ": "cons_h",
-    "FvgnF": "fvgn_f",
+    "FvgnF": "fvgn_f", "ConservativeK": "cons_h",      # K = H with a half-width antisymmetric stream (same data-flow)
 }
 
 

@@ -51,6 +51,7 @@ MODELS = {
     "ConservativeI": ("models.Conservative", "airfoil", "fvgn"),
     "ConservativeH": ("models.Conservative", "cylinder", "conservative_h"),
     "FvgnF": ("models.Fvgn", "airfoil", "fvgn"),
+    "ConservativeK": ("models.Conservative", "ellipse", "conservative_h"),
 }
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1}
@@ -85,7 +86,7 @@ def graphs_for(name, kind, flavour, flip=False):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"):
+    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
     if name == "ConservativeI":
         # the reference indexes the [E, 128] latent with the face-type mask (Conservative.py:1264-1267), which only

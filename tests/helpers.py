@@ -14,7 +14,7 @@ GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "Fl
                 "ConservativeE": ("ellipse", "fvgn"), "ConservativeF": ("airfoil", "fvgn"),
                 "ConservativeD": ("ellipse", "conservative"), "ConservativeG": ("cylinder", "fvgn"),
                 "ConservativeI": ("airfoil", "fvgn"), "ConservativeH": ("cylinder", "conservative_h"),
-                "FvgnF": ("airfoil", "fvgn")}
+                "FvgnF": ("airfoil", "fvgn"), "ConservativeK": ("ellipse", "conservative_h")}
 
 
 def make_config(mp_num=15, precision=None):
@@ -46,7 +46,7 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     if name == "MgnA":
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"):
+    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
         f.y = f.y[:, :3].contiguous()
     if name == "ConservativeI":
         f.type = f.type.reshape(-1)      # see tests/golden/make_golden.py: the reference needs a 1-D type tensor here

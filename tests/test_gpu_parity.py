@@ -155,8 +155,8 @@ def _run_processor(name, model, graphs_dev):
     c, f, v = graphs_dev
     grab = {}
     hook = lambda i, x, e: grab.__setitem__(i, (x, e)) if i in (0, 14) else None
-    if name in ("ConservativeA", "ConservativeD", "ConservativeH"):
-        topo = get_topology(graphs_dev, need_cell_csr=True, two_hop=name == "ConservativeH").validate()
+    if name in ("ConservativeA", "ConservativeD", "ConservativeH", "ConservativeK"):
+        topo = get_topology(graphs_dev, need_cell_csr=True, two_hop=name in ("ConservativeH", "ConservativeK")).validate()
         x, e, dec = model.encode_process_decode(c.x, f.x_symm, f.x_asym, topo, hook=hook)
         return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
     topo = get_topology(graphs_dev, need_cell_csr=name.startswith("Conservative")).validate()
@@ -172,7 +172,7 @@ def _run_processor(name, model, graphs_dev):
     return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
 
 
-@pytest.mark.parametrize("name", ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"])
+@pytest.mark.parametrize("name", ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"])
 def test_processor_matches_reference_golden(name):
     gold = load_golden(f"fwd_{name}.npz")
     model = build_model(name).eval()
@@ -190,14 +190,14 @@ def test_processor_matches_reference_golden(name):
         assert rel_l2(out["x"], torch.from_numpy(gold["x15"])) < t, (prec, rel_l2(out["x"], torch.from_numpy(gold["x15"])))
         assert rel_l2(out["e"], torch.from_numpy(gold["e15"])) < t, (prec, rel_l2(out["e"], torch.from_numpy(gold["e15"])))
         assert rel_l2(out["dec"], torch.from_numpy(gold["dec"])) < 2 * t
-        if name in ("ConservativeD", "ConservativeH"):      # second (antisymmetric) edge stream
+        if name in ("ConservativeD", "ConservativeH", "ConservativeK"):      # second (antisymmetric) edge stream
             assert rel_l2(model._last_e_asym, torch.from_numpy(gold["ea15"])) < t
         if name == "VertPotA":
             assert rel_l2(out["vx"], torch.from_numpy(gold["vx15"])) < t
             assert rel_l2(out["dec_vertex"], torch.from_numpy(gold["dec_vertex"])) < 2 * t
 
 
-@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"])
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"])
 @pytest.mark.parametrize("mode", ["train", "rollout"])
 def test_full_forward_matches_reference_golden(name, mode):
     gold = load_golden(f"fwd_{name}.npz")

@@ -13,7 +13,7 @@ from gnn_fluid_dynamics_b200.mesh import connectivity
 from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
 from helpers import GOLDEN, LOSS_W, build_model, golden_graphs, load_golden
 
-MODELS = ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF"]
+MODELS = ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"]
 TOL = 2e-5   # fp32 CPU restatement vs fp32 CPU reference: summation-order noise only
 
 
@@ -38,7 +38,7 @@ def _processor_inputs(name, graphs, model):
     c, f, v = graphs
     topo = {"c_edge_index": c.edge_index, "v_edge_index": v.edge_index, "v_face": v.face,
             "n_vertices": v.num_nodes}
-    if name in ("ConservativeA", "ConservativeD", "ConservativeH"):
+    if name in ("ConservativeA", "ConservativeD", "ConservativeH", "ConservativeK"):
         return c.x, f.x_symm, f.x_asym, topo
     return c.x, f.x, None, topo
 
