@@ -6,8 +6,7 @@ import pytest
 import torch
 
 import oracle
-from oracle import model as omodel
-from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
+from gnn_fluid_dynamics_b200.testing import rel_l2
 from helpers import build_model, golden_graphs, load_golden
 
 pytestmark = pytest.mark.gpu

@@ -5,7 +5,6 @@ autograd and against the reference-generated golden fixture tests/golden/train_F
 Tolerances: loss 1e-4 relative; gradients rel-L2 <= 1e-3 per parameter tensor (same bar north_star states
 for processor outputs: dgrad runs split-bf16 (~1e-5), wgrad runs single-pass TF32 with round-to-nearest
 operands (~3e-4), fp32 accumulation everywhere)."""
-import numpy as np
 import pytest
 import torch
 
