@@ -53,12 +53,17 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_backward_kernel(
   }
 }
 
-__global__ void sum_partials_kernel(const float *__restrict__ partial, int n_parts, int width, float *__restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// out[i] = sum over parts of partial[c][i]: one warp per output, lanes stride over the parts, fixed shuffle tree
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float *__restrict__ partial, int n_parts, int width,
+                                                           float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= width) return;
   float s = 0.f;
-  for (int c = 0; c < n_parts; ++c) s += partial[(size_t)c * width + i];
-  out[i] = s;
+  for (int c = lane; c < n_parts; c += 32) s += partial[(size_t)c * width + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[i] = s;
 }
 
 static int lnb_grid(int64_t rows) {
@@ -75,7 +80,7 @@ int ln_backward_launch(const float *g, const float *xhat, const float *rstd, con
   if (workspace == nullptr || workspace_bytes < (size_t)grid * 384 * 4) { set_error("ln_backward: workspace too small"); return GNNFD_E_WORKSPACE; }
   ln_backward_kernel<<<grid, LNB_THREADS, 0, stream>>>(g, xhat, rstd, ln_w, rows, dy, (float *)workspace);
   GNNFD_LAUNCH_CHECK();
-  sum_partials_kernel<<<12, 32, 0, stream>>>((const float *)workspace, grid, 384, sums);
+  sum_partials_kernel<<<(384 * 32 + 255) / 256, 256, 0, stream>>>((const float *)workspace, grid, 384, sums);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

@@ -360,23 +360,35 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   if (warp == WG_PROD_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
-// out[m, j] = sum over parts (ascending) of part[c][m][n_pad + j]; optionally transposed store; plus colsum
-__global__ void reduce_partials_kernel(const float *__restrict__ part, int n_parts, int n_pad, int m_valid,
-                                       int n_valid, float *__restrict__ out, int ld_out, int transpose,
-                                       const float *__restrict__ cs_part, float *__restrict__ cs_out, int cs_valid) {
+// out[m, j] = sum over the split-K partials part[c][m][j] (+ column sums), optionally stored transposed.
+// 64 outputs x 4 part-groups per block: group y adds parts y, y + 4, ... (coalesced across the 64 outputs), the four
+// group sums are combined in fixed order - deterministic, and 4x the memory parallelism of one thread per output.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__restrict__ part, int n_parts, int n_pad,
+                                                              int m_valid, int n_valid, float *__restrict__ out,
+                                                              int ld_out, int transpose, const float *__restrict__ cs_part,
+                                                              float *__restrict__ cs_out, int cs_valid) {
+  __shared__ float s_sum[4][64];
   const int total = m_valid * n_valid;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + tx;
+  float s = 0.f;
   if (i < total) {
     const int m = i / n_valid, j = i % n_valid;
     const float *src = part + (size_t)m * n_pad + j;
-    float s = 0.f;
-    for (int c = 0; c < n_parts; ++c) s += src[(size_t)c * 128 * n_pad];
-    if (transpose) out[(size_t)j * ld_out + m] = s; else out[(size_t)m * ld_out + j] = s;
+    for (int c = ty; c < n_parts; c += 4) s += src[(size_t)c * 128 * n_pad];
   } else if (cs_out != nullptr && i - total < cs_valid) {
-    const int k = i - total;
-    float s = 0.f;
-    for (int c = 0; c < n_parts; ++c) s += cs_part[(size_t)c * 128 + k];
-    cs_out[k] = s;
+    for (int c = ty; c < n_parts; c += 4) s += cs_part[(size_t)c * 128 + (i - total)];
+  }
+  s_sum[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    const float r = (s_sum[0][tx] + s_sum[1][tx]) + (s_sum[2][tx] + s_sum[3][tx]);
+    if (i < total) {
+      const int m = i / n_valid, j = i % n_valid;
+      if (transpose) out[(size_t)j * ld_out + m] = r; else out[(size_t)m * ld_out + j] = r;
+    } else if (cs_out != nullptr && i - total < cs_valid) {
+      cs_out[i - total] = r;
+    }
   }
 }
 
@@ -481,7 +493,7 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
   GNNFD_LAUNCH_CHECK();
   const int m_valid = a->a.width;
   const int total = m_valid * n_valid + cs_valid;
-  reduce_partials_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p.partial, grid, n_pad, m_valid, n_valid, a->out,
+  reduce_partials_kernel<<<(total + 63) / 64, 256, 0, stream>>>(p.partial, grid, n_pad, m_valid, n_valid, a->out,
                                                                   a->ld_out, a->transpose_out, cs_part, a->colsum, cs_valid);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
