@@ -23,23 +23,24 @@
 
 namespace gnnfd {
 
-// warp roles: 0-3 epilogue of even local tiles (TMEM slot 0), 4-7 epilogue of odd local tiles (slot 1)
-//             (warp & 3 = TMEM lane quarter, thread = row), 8-15 producers (gather -> split -> swizzled A
-//             stage), 16 = MMA issuer, 17 = weight loader (TMA bulk copies), 18-19 idle.
-// Registers: 5 warps per SM sub-partition cap the launch at 96 per thread; warpgroup 16-19 shrinks to 48
-// (setmaxnreg.dec) and the two producer warpgroups grow to 120 (setmaxnreg.inc; only registers released inside the CTA can be claimed) for their two in-flight
-// k-blocks of gathered rows.
-constexpr int TC_EPI_WARPS = 8, TC_PROD_WARPS = 8;
+// warp roles: 0-7 epilogue of even local tiles (TMEM slot 0), 8-15 epilogue of odd local tiles (slot 1) - the two
+//             groups convert different tiles CONCURRENTLY (warp & 3 = TMEM lane quarter, thread = row, (warp >> 2) & 1 =
+//             column half), 16-23 producers (gather -> split -> swizzled A stage), 24 = MMA issuer, 25 = weight
+//             loader (TMA bulk copies), 26-27 idle.
+// Registers: 896 threads launch at 72 per thread; the epilogue works in 16-column groups to live within that;
+// warpgroup 24-27 shrinks to 40 (setmaxnreg.dec) and the two producer warpgroups grow to 88 (setmaxnreg.inc; only
+// registers released inside the CTA can be claimed).
+constexpr int TC_EPI_WARPS = 16, TC_PROD_WARPS = 8;
+constexpr int TC_EPI_GROUP = 8;       // epilogue warps per tile
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32, TC_PROD_THREADS = TC_PROD_WARPS * 32;
 constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
 constexpr int TC_WLD_WARP = TC_MMA_WARP + 1;
-constexpr int TC_THREADS = (TC_WLD_WARP + 3) * 32;   // 640: warps 18, 19 only complete the register-donor warpgroup
+constexpr int TC_THREADS = (TC_WLD_WARP + 3) * 32;   // 896: the last two warps only complete the register-donor warpgroup
 constexpr int TC_A_STAGES = 3;        // A ring: {A_hi, A_lo} images per stage
 constexpr int TC_W_SLOTS = 4;         // W ring: one 16 KB image (hi or lo part of a k-block) per slot
 constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 96 KB
 constexpr int TC_W_BYTES = TC_W_SLOTS * TC_IMG;        // 64 KB
-constexpr int TC_STG_STRIDE = 36;     // floats per row of a warp's 32x32 output staging block
-constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * TC_STG_STRIDE * 4;   // 36 KB
+constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * 16 * 4;   // 32 KB: one XOR-swizzled 32 x 16 fp32 staging block per epilogue warp
 constexpr int TC_IDX_SLOTS = 4;
 constexpr int TC_IDX_SLOT = 9 * TC_BM;               // ints: [3 seg][3 idx][128 rows]
 constexpr int TC_NBAR = 24;
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   if (tid == 0) {
     for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < TC_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_EPI_GROUP); }
     for (int i = 0; i < 4; ++i) mbar_init(&hid_ready[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 
   if (warp >= TC_EPI_WARPS && warp < TC_MMA_WARP) {
     // =============================================================================== producers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int pt = tid - TC_EPI_THREADS;   // 0..255
     const int f4 = pt & 15;                // float4 column inside the 64-wide k-block
     const int rbase = pt >> 4;             // rows rbase + 16 j
@@ -334,10 +335,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     }
 #endif
   } else if (warp > TC_WLD_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   } else if (warp == TC_WLD_WARP) {
     // ============================================================================ weight loader
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0 && T > 0) {
       const uint8_t *w1p = (const uint8_t *)a.packed;
       const uint8_t *w2p = w1p + (size_t)p.kb1 * p.w_block_bytes;
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     __syncwarp();
   } else if (warp == TC_MMA_WARP) {
     // ================================================================================ MMA issuer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0 && T > 0) {
       constexpr uint32_t IDESC_H = make_idesc(FP16 ? 0 : 1, TC_H);
       const uint32_t idesc3 = make_idesc(FP16 ? 0 : 1, p.n3);
@@ -428,15 +429,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           int slot;
           uint64_t wb = w_acquire(slot);
           for (int k = 0; k < 4; ++k) {
-            const uint32_t ta = a_reg + (kb * 2 + (k >> 1)) * 32 + (k & 1) * 8;
+            const uint32_t ta = a_reg + (kb * 4 + k) * 16;      // 16 fp32 columns -> 8 hi pairs | 8 lo pairs
             umma_ts(d, ta, wb + 2 * k, idesc, (kb | k) != 0);
-            if (NA == 2) umma_ts(d, ta + 16, wb + 2 * k, idesc, 1);
+            if (NA == 2) umma_ts(d, ta + 8, wb + 2 * k, idesc, 1);
           }
           umma_commit(&w_empty[slot]);
           if (NW == 2) {
             wb = w_acquire(slot);
             for (int k = 0; k < 4; ++k) {
-              const uint32_t ta = a_reg + (kb * 2 + (k >> 1)) * 32 + (k & 1) * 8;
+              const uint32_t ta = a_reg + (kb * 4 + k) * 16;
               umma_ts(d, ta, wb + 2 * k, idesc, 1);
             }
             umma_commit(&w_empty[slot]);
@@ -473,15 +474,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     __syncwarp();
   } else {
     // ================================================================================ epilogue
-    // warp = (lane quarter q4, column half eh): thread = row, 64 of the 128 columns, for EVERY tile; half eh
-    // of a hidden layer's output is exactly k-block eh of the next layer's operand.
-    const int q4 = warp & 3, eh = warp >> 2;
+    // warp = (tile group grp, column half eh, lane quarter q4): thread = row, 64 of the 128 columns of every tile of its
+    // group; half eh of a hidden layer's output is exactly k-block eh of the next layer's operand.  All TMEM traffic is
+    // in 16-column groups: 16 fp32 accumulator columns are replaced in place by 8 columns of hi pairs + 8 of lo pairs.
+    const int grp = warp >> 3, q4 = warp & 3, eh = (warp >> 2) & 1;
     const int erow = q4 * 32 + lane;                       // row of the tile owned by this thread
-    const uint32_t stg = smem_u32(s_stg + warp * (32 * TC_STG_STRIDE));   // this warp's 32x32 staging block
+    const uint32_t stg = smem_u32(s_stg + warp * (32 * 16));   // this warp's 32 x 16 staging block (XOR-swizzled)
     const uint32_t vec = smem_u32(s_vec), stat = smem_u32(s_stat);
-    const int rr = lane >> 3, c4 = lane & 7;               // copy-out mapping: 4 rows x 128 B per instruction
+    const int rr = lane >> 2, c4 = lane & 3;               // copy-out mapping: 8 rows x 64 B per instruction
     PROF_DECL;
-    for (int j = 0; j < T; ++j) {
+    for (int j = grp; j < T; j += 2) {
       const int sl = j & 1, n = j >> 1;
       const int64_t row0 = tile_row0(j);
       const uint32_t xr = tmem_base + sl * 256 + ((uint32_t)(q4 * 32) << 16) + eh * 64, yr = xr + 128;
@@ -494,56 +496,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         // backward chain: the saved pre-activation of this layer (rows past the end read row 0; never stored),
         // fetched one 16-column group ahead of its use
         const float *hm = nullptr;
-        float4 m4[2][4];
+        float4 m4[4];
         if (BWD) {
           hm = (layer == 0 ? a.hid_mul1 : a.hid_mul2) + (size_t)((row0 + erow < a.rows) ? row0 + erow : 0) * TC_H + eh * 64;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) m4[0][i] = ldg_f4(hm + i * 4);
+          for (int i = 0; i < 4; ++i) m4[i] = ldg_f4(hm + i * 4);
         }
         PROF_WAIT(0, mbar_wait(&acc_full[sl], (3 * n + layer) & 1));
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          float acc[32];
-          tmem_ld32(reg + c * 32, acc);
-          uint32_t hi[16], lo[16];
+        for (int c = 0; c < 4; ++c) {
+          float v[16];
+          tmem_ld16(reg + c * 16, v);
+          if (BWD) {
+            const bool silu = a.act == GNNFD_ACT_SILU;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float v[16];
-            if (BWD) {
-              if (h == 0 || c == 0) {   // next group: (c, 1) after (c, 0); (1, 0) after (0, 1)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) m4[(h + 1) & 1][i] = ldg_f4(hm + (h == 0 ? c * 32 + 16 : 32) + i * 4);
-              }
-              const bool silu = a.act == GNNFD_ACT_SILU;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float4 m = m4[h & 1][i];
-                v[4 * i] = acc[h * 16 + 4 * i] * (silu ? dsilu(m.x) : dtanh(m.x));
-                v[4 * i + 1] = acc[h * 16 + 4 * i + 1] * (silu ? dsilu(m.y) : dtanh(m.y));
-                v[4 * i + 2] = acc[h * 16 + 4 * i + 2] * (silu ? dsilu(m.z) : dtanh(m.z));
-                v[4 * i + 3] = acc[h * 16 + 4 * i + 3] * (silu ? dsilu(m.w) : dtanh(m.w));
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 b4 = lds_f4(bias + (c * 32 + h * 16 + i) * 4);
-                v[i] = acc[h * 16 + i] + b4.x; v[i + 1] = acc[h * 16 + i + 1] + b4.y;
-                v[i + 2] = acc[h * 16 + i + 2] + b4.z; v[i + 3] = acc[h * 16 + i + 3] + b4.w;
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float4 m = m4[i];
+              v[4 * i] *= silu ? dsilu(m.x) : dtanh(m.x);
+              v[4 * i + 1] *= silu ? dsilu(m.y) : dtanh(m.y);
+              v[4 * i + 2] *= silu ? dsilu(m.z) : dtanh(m.z);
+              v[4 * i + 3] *= silu ? dsilu(m.w) : dtanh(m.w);
             }
-            if (save != nullptr) {   // training: stash the pre-activation / dA (thread = row, 64 B per store group)
+            if (c < 3) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                *reinterpret_cast<float4 *>(save + c * 32 + h * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              for (int i = 0; i < 4; ++i) m4[i] = ldg_f4(hm + (c + 1) * 16 + i * 4);
             }
-            if (BWD) { /* linear chain: no activation */ }
-            else if (a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
+          } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) split2<FP16>(v[2 * i], v[2 * i + 1], hi[h * 8 + i], lo[h * 8 + i]);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = lds_f4(bias + (c * 16 + i) * 4);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
           }
-          tmem_st16(reg + c * 32, hi);
-          if (NA == 2) tmem_st16(reg + c * 32 + 16, lo);
+          if (save != nullptr) {   // training: stash the pre-activation / dA (thread = row, 64 B per store group)
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4 *>(save + c * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+          if (BWD) { /* linear chain: no activation */ }
+          else if (a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split2<FP16>(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+          tmem_st8(reg + c * 16, hi);
+          if (NA == 2) tmem_st8(reg + c * 16 + 8, lo);
         }
         // this half's 64 columns = one k-block of the next layer's operand
         tmem_wait_st();
@@ -560,13 +557,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           // this half: shifted single pass over 64 columns -> (mean_h, M2_h); halves merged with Chan's formula
           float shift = 0.f, s4[4] = {0.f, 0.f, 0.f, 0.f}, q4s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            float acc[32];
-            tmem_ld32(xr + c * 32, acc);
-            const uint32_t b3 = vec + (2 * TC_H + eh * 64 + c * 32) * 4;
+          for (int c = 0; c < 4; ++c) {
+            float acc[16];
+            tmem_ld16(xr + c * 16, acc);
+            const uint32_t b3 = vec + (2 * TC_H + eh * 64 + c * 16) * 4;
             if (c == 0) shift = acc[0] + lds_f4(b3).x;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
+            for (int i = 0; i < 16; i += 4) {
               const float4 b4 = lds_f4(b3 + i * 4);
               const float d0 = acc[i] + b4.x - shift, d1 = acc[i + 1] + b4.y - shift;
               const float d2 = acc[i + 2] + b4.z - shift, d3 = acc[i + 3] + b4.w - shift;
@@ -579,7 +576,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           const float md = sh * (1.0f / 64.0f);
           const float mean_h = shift + md, m2_h = fmaxf(qh - sh * md, 0.f);
           sts_f2(stat + ((sl * 2 + eh) * TC_BM + erow) * 8, make_float2(mean_h, m2_h));
-          named_bar_sync(2 + q4, 64);                   // the two warps that share these 32 rows
+          named_bar_sync(2 + grp * 4 + q4, 64);         // the two warps that share these 32 rows of this tile
           const float2 o = lds_f2(stat + ((sl * 2 + (eh ^ 1)) * TC_BM + erow) * 8);
           const float dm = mean_h - o.x;
           mean = 0.5f * (mean_h + o.x);
@@ -587,45 +584,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           if (a.save_rstd != nullptr && eh == 0 && row0 + erow < a.rows) a.save_rstd[row0 + erow] = rstd;
         }
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          const int col0 = eh * 64 + c * 32;
-          // residual rows of this chunk, coalesced mapping, requested before the TMEM read
-          float4 res[8];
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = eh * 64 + c * 16;
+          // residual rows of this group, coalesced mapping (8 rows x 64 B), requested before the TMEM read
+          float4 res[4];
           if (a.out_sum) {
 #pragma unroll
-            for (int jr = 0; jr < 8; ++jr) {
-              const int64_t g = min(row0 + q4 * 32 + jr * 4 + rr, a.rows - 1);
+            for (int jr = 0; jr < 4; ++jr) {
+              const int64_t g = min(row0 + q4 * 32 + jr * 8 + rr, a.rows - 1);
               res[jr] = ldg_f4(a.residual + (size_t)g * TC_H + col0 + c4 * 4);
             }
           }
-          float acc[32];
-          tmem_ld32(xr + c * 32, acc);
-          if (c == 1) {   // last TMEM read of this tile: the slot may be overwritten by the next L1
+          float acc[16];
+          tmem_ld16(xr + c * 16, acc);
+          if (c == 3) {   // last TMEM read of this tile: the slot may be overwritten by the next L1
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_free[sl]);
           }
-          // staged value = normalised row (x-hat); the LayerNorm affine is applied in the coalesced copy-out,
-          // where the training stash of x-hat is also written
+          // staged value = normalised row (x-hat); the LayerNorm affine is applied in the coalesced copy-out, where the
+          // training stash of x-hat is also written.  Staging block: row r, 16-byte chunk i at chunk i ^ ((r >> 1) & 3).
           const uint32_t b3 = vec + (2 * TC_H + col0) * 4;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = lds_f4(b3 + i * 4);
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = lds_f4(b3 + i * 16);
             float4 o;
-            o.x = (acc[i] + b4.x - mean) * rstd;
-            o.y = (acc[i + 1] + b4.y - mean) * rstd;
-            o.z = (acc[i + 2] + b4.z - mean) * rstd;
-            o.w = (acc[i + 3] + b4.w - mean) * rstd;
-            sts_f4(stg + (lane * TC_STG_STRIDE + i) * 4, o);
+            o.x = (acc[4 * i] + b4.x - mean) * rstd;
+            o.y = (acc[4 * i + 1] + b4.y - mean) * rstd;
+            o.z = (acc[4 * i + 2] + b4.z - mean) * rstd;
+            o.w = (acc[4 * i + 3] + b4.w - mean) * rstd;
+            sts_f4(stg + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4, o);
           }
           __syncwarp();
           const float4 w4 = lds_f4(vec + (3 * TC_H + col0 + c4 * 4) * 4), g4 = lds_f4(vec + (4 * TC_H + col0 + c4 * 4) * 4);
 #pragma unroll
-          for (int jr = 0; jr < 8; ++jr) {
-            const int rl = jr * 4 + rr;
+          for (int jr = 0; jr < 4; ++jr) {
+            const int rl = jr * 8 + rr;
             const int64_t g = row0 + q4 * 32 + rl;
             if (g < a.rows) {
-              float4 o = lds_f4(stg + (rl * TC_STG_STRIDE + c4 * 4) * 4);
+              float4 o = lds_f4(stg + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4);
               const size_t off = (size_t)g * TC_H + col0 + c4 * 4;
               if (a.save_xhat) *reinterpret_cast<float4 *>(a.save_xhat + off) = o;
               o.x = fmaf(o.x, w4.x, g4.x); o.y = fmaf(o.y, w4.y, g4.y);
