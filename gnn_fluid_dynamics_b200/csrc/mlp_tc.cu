@@ -23,30 +23,39 @@
 
 namespace gnnfd {
 
-// warp roles: 0-7 epilogue of even local tiles (TMEM slot 0), 8-15 epilogue of odd local tiles (slot 1) - the two
-//             groups convert different tiles CONCURRENTLY (warp & 3 = TMEM lane quarter, thread = row, (warp >> 2) & 1 =
-//             column half), 16-23 producers (gather -> split -> swizzled A stage), 24 = MMA issuer, 25 = weight
-//             loader (TMA bulk copies), 26-27 idle.
+// warp roles: 0-7 epilogue of even local tiles, 8-15 epilogue of odd local tiles - the two groups convert different
+//             tiles CONCURRENTLY (warp & 3 = TMEM lane quarter, thread = row, (warp >> 2) & 1 = column half),
+//             16-23 producers (gather -> split -> swizzled A stage), 24 = layer-1 MMA issuer, 25 = layer-2/3 MMA
+//             issuer, 26 = layer-1 weight loader, 27 = layer-2/3 weight loader (TMA bulk copies).
+// The two issuers run as a dataflow: nothing orders layer 1 of tile j + 1 against layers 2/3 of tile j except the
+// mbarriers that carry the data, so neither a slow epilogue nor a slow gather stalls the other chain.
+// TMEM: three X regions (layer-1 accumulator / hidden-1 operand / layer-3 accumulator of tiles j % 3) and ONE Y region
+// (layer-2 accumulator / hidden-2 operand), which the in-order tensor pipe hands from tile to tile.
 // Registers: 896 threads launch at 72 per thread; the epilogue works in 16-column groups to live within that;
 // warpgroup 24-27 shrinks to 40 (setmaxnreg.dec) and the two producer warpgroups grow to 88 (setmaxnreg.inc; only
 // registers released inside the CTA can be claimed).
 constexpr int TC_EPI_WARPS = 16, TC_PROD_WARPS = 8;
 constexpr int TC_EPI_GROUP = 8;       // epilogue warps per tile
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32, TC_PROD_THREADS = TC_PROD_WARPS * 32;
-constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
-constexpr int TC_WLD_WARP = TC_MMA_WARP + 1;
-constexpr int TC_THREADS = (TC_WLD_WARP + 3) * 32;   // 896: the last two warps only complete the register-donor warpgroup
-constexpr int TC_A_STAGES = 3;        // A ring: {A_hi, A_lo} images per stage
-constexpr int TC_W_SLOTS = 4;         // W ring: one 16 KB image (hi or lo part of a k-block) per slot
-constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 96 KB
-constexpr int TC_W_BYTES = TC_W_SLOTS * TC_IMG;        // 64 KB
+constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;   // layer-1 issuer (also owns the TMEM allocation)
+constexpr int TC_MMA23_WARP = TC_MMA_WARP + 1;
+constexpr int TC_WLD_WARP = TC_MMA_WARP + 2;
+constexpr int TC_WLD23_WARP = TC_MMA_WARP + 3;
+constexpr int TC_THREADS = (TC_MMA_WARP + 4) * 32;   // 896
+constexpr int TC_A_STAGES = 2;        // A ring: {A_hi, A_lo} images per stage
+constexpr int TC_W1_SLOTS = 3;        // layer-1 W ring: one 16 KB image (hi or lo part of a k-block) per slot
+constexpr int TC_W23_SLOTS = 3;       // layer-2/3 W ring
+constexpr int TC_X_SLOTS = 3;         // X regions in TMEM
+constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 64 KB
+constexpr int TC_W_BYTES = (TC_W1_SLOTS + TC_W23_SLOTS) * TC_IMG;   // 96 KB
 constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * 16 * 4;   // 32 KB: one XOR-swizzled 32 x 16 fp32 staging block per epilogue warp
 constexpr int TC_IDX_SLOTS = 4;
 constexpr int TC_IDX_SLOT = 9 * TC_BM;               // ints: [3 seg][3 idx][128 rows]
-constexpr int TC_NBAR = 24;
+constexpr int TC_NBAR = 32;
 constexpr int TC_SMEM = TC_A_BYTES + TC_W_BYTES + TC_STG_BYTES + TC_IDX_SLOTS * TC_IDX_SLOT * 4 +
                         5 * TC_H * 4 + 4 * TC_BM * 8 + TC_NBAR * 8 + 64 + 1024;
-constexpr int TC_TMEM_COLS = 512;     // two slots x {X, Y} x 128 columns
+constexpr int TC_TMEM_COLS = 512;     // X0 | X1 | X2 | Y, 128 columns each
+constexpr uint32_t TC_Y_COL = TC_X_SLOTS * 128;
 constexpr int TC_MAX_KB = 8;
 
 // how the producers assemble one 64-wide k-block of layer 1's input
@@ -222,17 +231,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   float *s_vec = (float *)(s_idx + TC_IDX_SLOTS * TC_IDX_SLOT);    // b1, b2, b3, ln_w, ln_b
   float2 *s_stat = (float2 *)(s_vec + 5 * TC_H);                   // LayerNorm partials [2 slots][2 halves][128 rows]
   uint64_t *s_bar = (uint64_t *)(s_stat + 4 * TC_BM);
-  uint64_t *a_full = s_bar, *a_empty = s_bar + 3, *w_full = s_bar + 6, *w_empty = s_bar + 10;
-  uint64_t *acc_full = s_bar + 14, *acc_free = s_bar + 16, *hid_ready = s_bar + 18;   // hid_ready[slot*2 + half]
+  uint64_t *a_full = s_bar, *a_empty = s_bar + 2, *w_full = s_bar + 4, *w_empty = s_bar + 7;
+  uint64_t *w23_full = s_bar + 10, *w23_empty = s_bar + 13;
+  uint64_t *acc_full = s_bar + 16, *acc_free = s_bar + 19, *hid_ready = s_bar + 22;   // hid_ready[x_slot*2 + half]
+  uint8_t *s_w23 = s_w + TC_W1_SLOTS * TC_IMG;
   uint32_t *s_tmem = (uint32_t *)(s_bar + TC_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < TC_W_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_EPI_GROUP); }
-    for (int i = 0; i < 4; ++i) mbar_init(&hid_ready[i], 4);
+    for (int i = 0; i < TC_W1_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < TC_W23_SLOTS; ++i) { mbar_init(&w23_full[i], 1); mbar_init(&w23_empty[i], 1); }
+    for (int i = 0; i < TC_X_SLOTS; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_EPI_GROUP); }
+    for (int i = 0; i < 2 * TC_X_SLOTS; ++i) mbar_init(&hid_ready[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
@@ -334,141 +346,139 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       g_tc_prof[14] = prof[1]; g_tc_prof[15] = prof[2]; g_tc_prof[7] = prof[3]; g_tc_prof[11] = prof[4];
     }
 #endif
-  } else if (warp > TC_WLD_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  } else if (warp == TC_WLD_WARP) {
-    // ============================================================================ weight loader
+  } else if (warp == TC_WLD_WARP || warp == TC_WLD23_WARP) {
+    // ============================================================================ weight loaders
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0 && T > 0) {
       const uint8_t *w1p = (const uint8_t *)a.packed;
       const uint8_t *w2p = w1p + (size_t)p.kb1 * p.w_block_bytes;
       const uint8_t *w3p = w2p + (size_t)2 * p.w_block_bytes;
       const uint32_t w3_part = p.w3_block_bytes / NW;
-      uint32_t wl = 0;
+      const bool first = warp == TC_WLD_WARP;
+      const int n_slots = first ? TC_W1_SLOTS : TC_W23_SLOTS;
+      uint64_t *full = first ? w_full : w23_full, *empty = first ? w_empty : w23_empty;
+      uint8_t *ring = first ? s_w : s_w23;
+      int slot = 0;
+      uint32_t round = 0;
       auto load_unit = [&](const uint8_t *src, uint32_t bytes) {
-        const int slot = wl & (TC_W_SLOTS - 1);
-        if (wl >= TC_W_SLOTS) mbar_wait(&w_empty[slot], ((wl / TC_W_SLOTS) - 1) & 1);
-        mbar_expect_tx(&w_full[slot], bytes);
-        bulk_g2s(s_w + slot * TC_IMG, src, bytes, &w_full[slot]);
-        ++wl;
+        if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+        mbar_expect_tx(&full[slot], bytes);
+        bulk_g2s(ring + slot * TC_IMG, src, bytes, &full[slot]);
+        if (++slot == n_slots) { slot = 0; ++round; }
       };
-      // same order as the MMA issuer (see there)
-      auto l1 = [&](int kb0, int kb1) {
-        for (int kb = kb0; kb < kb1; ++kb)
-          for (int part = 0; part < NW; ++part) load_unit(w1p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
-      };
-      auto l2 = [&]() {
-        for (int kb = 0; kb < 2; ++kb)
-          for (int part = 0; part < NW; ++part) load_unit(w2p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
-      };
-      auto l3 = [&]() {
-        for (int kb = 0; kb < 2; ++kb)
-          for (int part = 0; part < NW; ++part) load_unit(w3p + (size_t)kb * p.w3_block_bytes + part * w3_part, w3_part);
-      };
-      const int n1 = (p.kb1 + 2) / 3, n2 = (2 * p.kb1 + 2) / 3;
-      if (p.nl == 1) {
-        for (int j = 0; j < T; ++j) l1(0, p.kb1);
-      } else {
-        l1(0, p.kb1);
-        for (int j = 1; j < T; ++j) { l1(0, n1); l2(); l1(n1, n2); l3(); l1(n2, p.kb1); }
-        l2(); l3();
+      // same order as the issuer that drains this ring (see there)
+      if (first) {
+        for (int j = 0; j < T; ++j)
+          for (int kb = 0; kb < p.kb1; ++kb)
+            for (int part = 0; part < NW; ++part) load_unit(w1p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
+      } else if (p.nl > 1) {
+        for (int j = 0; j < T; ++j) {
+          for (int kb = 0; kb < 2; ++kb)
+            for (int part = 0; part < NW; ++part) load_unit(w2p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
+          for (int kb = 0; kb < 2; ++kb)
+            for (int part = 0; part < NW; ++part) load_unit(w3p + (size_t)kb * p.w3_block_bytes + part * w3_part, w3_part);
+        }
       }
     }
     __syncwarp();
   } else if (warp == TC_MMA_WARP) {
-    // ================================================================================ MMA issuer
+    // ====================================================================== layer-1 MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (lane == 0 && T > 0) {
       constexpr uint32_t IDESC_H = make_idesc(FP16 ? 0 : 1, TC_H);
-      const uint32_t idesc3 = make_idesc(FP16 ? 0 : 1, p.n3);
-      uint32_t wc = 0, ca = 0;
+      constexpr uint32_t idesc1 = IDESC_H;
+      int st = 0, ws = 0;
+      uint32_t a_round = 0, w_round = 0;
       PROF_DECL;
       // consume one weight unit: returns its descriptor; release with umma_commit(&w_empty[slot])
       auto w_acquire = [&](int &slot) {
-        slot = wc & (TC_W_SLOTS - 1);
-        PROF_WAIT(2, mbar_wait(&w_full[slot], (wc / TC_W_SLOTS) & 1));
+        slot = ws;
+        PROF_WAIT(2, mbar_wait(&w_full[slot], w_round & 1));
         tc_fence_after();
-        ++wc;
+        if (++ws == TC_W1_SLOTS) { ws = 0; ++w_round; }
         return make_desc(smem_u32(s_w + slot * TC_IMG));
       };
-      auto layer1 = [&](int j, int kb0, int kb1) {
-        const int sl = j & 1, n = j >> 1;
-        if (kb0 == 0 && n >= 1) { PROF_WAIT(3, mbar_wait(&acc_free[sl], (n - 1) & 1)); tc_fence_after(); }
-        const uint32_t d = tmem_base + sl * 256;
-        for (int kb = kb0; kb < kb1; ++kb, ++ca) {
-          const int st = ca % TC_A_STAGES;
-          PROF_WAIT(4, mbar_wait(&a_full[st], (ca / TC_A_STAGES) & 1));
+      for (int j = 0; j < T; ++j) {
+        const int xs = j % TC_X_SLOTS, n = j / TC_X_SLOTS;
+        if (n >= 1) { PROF_WAIT(3, mbar_wait(&acc_free[xs], (n - 1) & 1)); tc_fence_after(); }
+        const uint32_t d = tmem_base + xs * 128;
+        for (int kb = 0; kb < p.kb1; ++kb) {
+          PROF_WAIT(4, mbar_wait(&a_full[st], a_round & 1));
           tc_fence_after();
           const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
           const uint64_t ah = make_desc(smem_u32(s_a + st * 2 * TC_IMG)), al = ah + (TC_IMG >> 4);
           int slot;
           uint64_t wb = w_acquire(slot);
           for (int k = 0; k < ksteps; ++k) {
-            umma_ss(d, ah + 2 * k, wb + 2 * k, IDESC_H, (kb | k) != 0);
-            if (NA == 2) umma_ss(d, al + 2 * k, wb + 2 * k, IDESC_H, 1);
+            umma_ss(d, ah + 2 * k, wb + 2 * k, idesc1, (kb | k) != 0);
+            if (NA == 2) umma_ss(d, al + 2 * k, wb + 2 * k, idesc1, 1);
           }
           umma_commit(&w_empty[slot]);
           if (NW == 2) {
             wb = w_acquire(slot);
-            for (int k = 0; k < ksteps; ++k) umma_ss(d, ah + 2 * k, wb + 2 * k, IDESC_H, 1);
+            for (int k = 0; k < ksteps; ++k) umma_ss(d, ah + 2 * k, wb + 2 * k, idesc1, 1);
             umma_commit(&w_empty[slot]);
           }
           umma_commit(&a_empty[st]);
+          if (++st == TC_A_STAGES) { st = 0; ++a_round; }
         }
-        if (kb0 < kb1 && kb1 == p.kb1) umma_commit(&acc_full[sl]);   // (empty ranges occur when kb1 < 3)
-      };
-      // layers 2 and 3: A = the in-place converted accumulator region, 32-column chunk per 32 elements
-      auto layer23 = [&](int j, int layer) {
-        const int sl = j & 1;
-        const uint32_t xr = tmem_base + sl * 256, yr = xr + 128;
-        const uint32_t a_reg = layer == 2 ? xr : yr, d = layer == 2 ? yr : xr;
-        const uint32_t idesc = layer == 2 ? IDESC_H : idesc3;
-        for (int kb = 0; kb < 2; ++kb) {
-          PROF_WAIT(5, mbar_wait(&hid_ready[sl * 2 + kb], layer == 2 ? 0 : 1));
-          tc_fence_after();
-          int slot;
-          uint64_t wb = w_acquire(slot);
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t ta = a_reg + (kb * 4 + k) * 16;      // 16 fp32 columns -> 8 hi pairs | 8 lo pairs
-            umma_ts(d, ta, wb + 2 * k, idesc, (kb | k) != 0);
-            if (NA == 2) umma_ts(d, ta + 8, wb + 2 * k, idesc, 1);
-          }
-          umma_commit(&w_empty[slot]);
-          if (NW == 2) {
-            wb = w_acquire(slot);
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t ta = a_reg + (kb * 4 + k) * 16;
-              umma_ts(d, ta, wb + 2 * k, idesc, 1);
-            }
-            umma_commit(&w_empty[slot]);
-          }
-        }
-        umma_commit(&acc_full[sl]);
-      };
-      // Issue order: layer 1 of tile j is interleaved, a third at a time, with layers 2 and 3 of tile
-      // j - 1 (the other TMEM slot).  The A ring drains steadily, so the producers never idle behind a
-      // long L2/L3 phase, and each hidden/final epilogue of tile j - 1 has a third of a tile period.
-      const int n1 = (p.kb1 + 2) / 3, n2 = (2 * p.kb1 + 2) / 3;
-      if (p.nl == 1) {
-        for (int j = 0; j < T; ++j) layer1(j, 0, p.kb1);
-      } else {
-        layer1(0, 0, p.kb1);
-        for (int j = 1; j < T; ++j) {
-          layer1(j, 0, n1);
-          layer23(j - 1, 2);
-          layer1(j, n1, n2);
-          layer23(j - 1, 3);
-          layer1(j, n2, p.kb1);
-        }
-        layer23(T - 1, 2);
-        layer23(T - 1, 3);
+        umma_commit(&acc_full[xs]);
       }
 #ifdef GNNFD_TC_PROF
       if (blockIdx.x == 0) {
         g_tc_prof[0] = clock64() - t_begin;
-        for (int i = 1; i < 6; ++i) g_tc_prof[i] = prof[i];
+        for (int i = 2; i < 5; ++i) g_tc_prof[i] = prof[i];
         g_tc_prof[6] = (unsigned long long)T;
       }
+#endif
+    }
+    __syncwarp();
+  } else if (warp == TC_MMA23_WARP) {
+    // ==================================================================== layer-2/3 MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (lane == 0 && T > 0 && p.nl > 1) {
+      constexpr uint32_t IDESC_H = make_idesc(FP16 ? 0 : 1, TC_H);
+      const uint32_t idesc3 = make_idesc(FP16 ? 0 : 1, p.n3);
+      int ws = 0;
+      uint32_t w_round = 0;
+      PROF_DECL;
+      auto w_acquire = [&](int &slot) {
+        slot = ws;
+        PROF_WAIT(1, mbar_wait(&w23_full[slot], w_round & 1));
+        tc_fence_after();
+        if (++ws == TC_W23_SLOTS) { ws = 0; ++w_round; }
+        return make_desc(smem_u32(s_w23 + slot * TC_IMG));
+      };
+      // A = the in-place converted accumulator region: per 16 fp32 columns, 8 columns of hi pairs | 8 of lo pairs.
+      // Layer 2 of tile j overwrites Y after layer 3 of tile j - 1 has read it: same thread, in-order tensor pipe.
+      for (int j = 0; j < T; ++j) {
+        const int xs = j % TC_X_SLOTS;
+        const uint32_t xr = tmem_base + xs * 128, yr = tmem_base + TC_Y_COL;
+        for (int layer = 2; layer <= 3; ++layer) {
+          const uint32_t a_reg = layer == 2 ? xr : yr, d = layer == 2 ? yr : xr;
+          const uint32_t idesc = layer == 2 ? IDESC_H : idesc3;
+          for (int kb = 0; kb < 2; ++kb) {
+            PROF_WAIT(5, mbar_wait(&hid_ready[xs * 2 + kb], layer == 2 ? 0 : 1));
+            tc_fence_after();
+            int slot;
+            uint64_t wb = w_acquire(slot);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ta = a_reg + (kb * 4 + k) * 16;
+              umma_ts(d, ta, wb + 2 * k, idesc, (kb | k) != 0);
+              if (NA == 2) umma_ts(d, ta + 8, wb + 2 * k, idesc, 1);
+            }
+            umma_commit(&w23_empty[slot]);
+            if (NW == 2) {
+              wb = w_acquire(slot);
+              for (int k = 0; k < 4; ++k) umma_ts(d, a_reg + (kb * 4 + k) * 16, wb + 2 * k, idesc, 1);
+              umma_commit(&w23_empty[slot]);
+            }
+          }
+          umma_commit(&acc_full[xs]);
+        }
+      }
+#ifdef GNNFD_TC_PROF
+      if (blockIdx.x == 0) { g_tc_prof[1] = prof[1]; g_tc_prof[5] = prof[5]; }
 #endif
     }
     __syncwarp();
@@ -484,9 +494,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     const int rr = lane >> 2, c4 = lane & 3;               // copy-out mapping: 8 rows x 64 B per instruction
     PROF_DECL;
     for (int j = grp; j < T; j += 2) {
-      const int sl = j & 1, n = j >> 1;
+      const int xs = j % TC_X_SLOTS, n = j / TC_X_SLOTS;
       const int64_t row0 = tile_row0(j);
-      const uint32_t xr = tmem_base + sl * 256 + ((uint32_t)(q4 * 32) << 16) + eh * 64, yr = xr + 128;
+      const uint32_t lanes = (uint32_t)(q4 * 32) << 16;
+      const uint32_t xr = tmem_base + lanes + xs * 128 + eh * 64, yr = tmem_base + lanes + TC_Y_COL + eh * 64;
       // ---- hidden layers: accumulator -> +bias, act -> hi/lo pairs, written back in place
       for (int layer = 0; layer < p.nl - 1; ++layer) {
         const uint32_t reg = layer == 0 ? xr : yr;
@@ -502,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) m4[i] = ldg_f4(hm + i * 4);
         }
-        PROF_WAIT(0, mbar_wait(&acc_full[sl], (3 * n + layer) & 1));
+        PROF_WAIT(0, mbar_wait(&acc_full[xs], (3 * n + layer) & 1));
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -546,10 +557,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&hid_ready[sl * 2 + eh]);
+        if (lane == 0) mbar_arrive(&hid_ready[xs * 2 + eh]);
       }
       // ---- final epilogue
-      PROF_WAIT(1, mbar_wait(&acc_full[sl], (p.nl * n + p.nl - 1) & 1));
+      PROF_WAIT(1, mbar_wait(&acc_full[xs], (p.nl * n + p.nl - 1) & 1));
       tc_fence_after();
       if (a.n_out == TC_H) {
         float mean = 0.f, rstd = 1.f;
@@ -575,9 +586,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           const float sh = (s4[0] + s4[1]) + (s4[2] + s4[3]), qh = (q4s[0] + q4s[1]) + (q4s[2] + q4s[3]);
           const float md = sh * (1.0f / 64.0f);
           const float mean_h = shift + md, m2_h = fmaxf(qh - sh * md, 0.f);
-          sts_f2(stat + ((sl * 2 + eh) * TC_BM + erow) * 8, make_float2(mean_h, m2_h));
+          sts_f2(stat + ((grp * 2 + eh) * TC_BM + erow) * 8, make_float2(mean_h, m2_h));
           named_bar_sync(2 + grp * 4 + q4, 64);         // the two warps that share these 32 rows of this tile
-          const float2 o = lds_f2(stat + ((sl * 2 + (eh ^ 1)) * TC_BM + erow) * 8);
+          const float2 o = lds_f2(stat + ((grp * 2 + (eh ^ 1)) * TC_BM + erow) * 8);
           const float dm = mean_h - o.x;
           mean = 0.5f * (mean_h + o.x);
           rstd = rsqrtf((m2_h + o.y + dm * dm * 32.0f) * (1.0f / TC_H) + a.ln_eps);
@@ -600,7 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           if (c == 3) {   // last TMEM read of this tile: the slot may be overwritten by the next L1
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_free[sl]);
+            if (lane == 0) mbar_arrive(&acc_free[xs]);
           }
           // staged value = normalised row (x-hat); the LayerNorm affine is applied in the coalesced copy-out, where the
           // training stash of x-hat is also written.  Staging block: row r, 16-byte chunk i at chunk i ^ ((r >> 1) & 3).
@@ -649,7 +660,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           tmem_ld16(xr, acc);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_free[sl]);
+          if (lane == 0) mbar_arrive(&acc_free[xs]);
           const int64_t g = row0 + erow;
           if (g < a.rows) {
 #pragma unroll
@@ -664,7 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             }
           }
         } else {
-          if (lane == 0) mbar_arrive(&acc_free[sl]);
+          if (lane == 0) mbar_arrive(&acc_free[xs]);
         }
       }
     }
