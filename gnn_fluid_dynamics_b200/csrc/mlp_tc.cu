@@ -43,11 +43,12 @@ constexpr int TC_WLD_WARP = TC_MMA_WARP + 2;
 constexpr int TC_WLD23_WARP = TC_MMA_WARP + 3;
 constexpr int TC_THREADS = (TC_MMA_WARP + 4) * 32;   // 896
 constexpr int TC_A_STAGES = 2;        // A ring: {A_hi, A_lo} images per stage
-constexpr int TC_W1_SLOTS = 3;        // layer-1 W ring: one 16 KB image (hi or lo part of a k-block) per slot
-constexpr int TC_W23_SLOTS = 3;       // layer-2/3 W ring
+constexpr int TC_W1_SLOTS = 2;        // layer-1 W ring: one 16 KB image (hi or lo part of a k-block) per slot
+constexpr int TC_W23_SLOTS = 2;       // layer-2/3 W ring (two slots each measured FASTER than three: the 32 KB not
+                                      // carved out of the L1 serve the producers' gathers - 203 -> 194 us on the edge block)
 constexpr int TC_X_SLOTS = 3;         // X regions in TMEM
 constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 64 KB
-constexpr int TC_W_BYTES = (TC_W1_SLOTS + TC_W23_SLOTS) * TC_IMG;   // 96 KB
+constexpr int TC_W_BYTES = (TC_W1_SLOTS + TC_W23_SLOTS) * TC_IMG;   // 64 KB
 constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * 16 * 4;   // 32 KB: one XOR-swizzled 32 x 16 fp32 staging block per epilogue warp
 constexpr int TC_IDX_SLOTS = 4;
 constexpr int TC_IDX_SLOT = 9 * TC_BM;               // ints: [3 seg][3 idx][128 rows]
@@ -266,7 +267,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 
   if (warp >= TC_EPI_WARPS && warp < TC_MMA_WARP) {
     // =============================================================================== producers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    // forward: gathers keep two k-blocks of rows in flight per thread and need the registers; backward chain: the
+    // hidden epilogues (saved pre-activation prefetch) need them more than the contiguous dA loads do
+    if (BWD) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int pt = tid - TC_EPI_THREADS;   // 0..255
     const int f4 = pt & 15;                // float4 column inside the 64-wide k-block
     const int rbase = pt >> 4;             // rows rbase + 16 j
@@ -487,6 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // warp = (tile group grp, column half eh, lane quarter q4): thread = row, 64 of the 128 columns of every tile of its
     // group; half eh of a hidden layer's output is exactly k-block eh of the next layer's operand.  All TMEM traffic is
     // in 16-column groups: 16 fp32 accumulator columns are replaced in place by 8 columns of hi pairs + 8 of lo pairs.
+    if (!BWD) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     const int grp = warp >> 3, q4 = warp & 3, eh = (warp >> 2) & 1;
     const int erow = q4 * 32 + lane;                       // row of the tile owned by this thread
     const uint32_t stg = smem_u32(s_stg + warp * (32 * 16));   // this warp's 32 x 16 staging block (XOR-swizzled)

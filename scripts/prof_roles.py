@@ -35,6 +35,8 @@ for which in ("edge", "node"):
     v = list(buf)
     T = max(v[6], 1)
     print(f"[{which} {prec}] kernel {a.elapsed_time(b)*1e3:.1f} us, tiles/CTA {T}")
-    print(f"  MMA issuer : total {v[0]/T:8.0f} cyc/tile | w_empty {v[1]/T:7.0f} w_full {v[2]/T:7.0f} acc_free {v[3]/T:7.0f} a_full {v[4]/T:7.0f} act_ready {v[5]/T:7.0f}")
+    print(f"  L1 issuer  : total {v[0]/T:8.0f} cyc/tile | w_full {v[2]/T:7.0f} acc_free {v[3]/T:7.0f} a_full {v[4]/T:7.0f}")
+    print(f"  L23 issuer : w23_full {v[1]/T:7.0f} hid_ready {v[5]/T:7.0f}")
+    print(f"  epilogue g0: (its own tiles = every other one; per-tile figures below are over ALL tiles)")
     print(f"  epilogue   : total {v[8]/T:8.0f} cyc/tile | wait hidden {v[9]/T:7.0f} wait final {v[10]/T:7.0f}")
     print(f"  producer   : total {v[12]/T:8.0f} cyc/tile | wait a_empty {v[13]/T:7.0f} convert+store {v[14]/T:7.0f} fence+arrive {v[15]/T:7.0f} issue {v[7]/T:7.0f} boundary {v[11]/T:7.0f}")
