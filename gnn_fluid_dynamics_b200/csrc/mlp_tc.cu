@@ -150,23 +150,27 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
     return;
   }
   const int32_t *ixs = ix + d.seg * 3 * TC_BM + rbase;
+  const uint32_t ixa = smem_u32(ixs);           // the index slot lives in shared memory: ld.shared, not generic loads
   const float *base = d.src + d.colk + f4 * 4;
   const int64_t ld = d.ld;
   if (d.mode == GNNFD_SEG_DIRECT) {
-    const int64_t last = p.a.rows - 1;
+    // one 64-bit tile base, then 32-bit row offsets (a tile spans < 2^31 floats: 128 rows x ld)
+    const float *tb = base + row0 * ld;
+    const int last = (int)min((int64_t)TC_BM, p.a.rows - row0) - 1;
+    const uint32_t ldu = (uint32_t)d.ld;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + min(row0 + rbase + 16 * jj, last) * ld);
+    for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(tb + (uint32_t)min(rbase + 16 * jj, last) * ldu);
   } else if (d.mode == GNNFD_SEG_GATHER) {
     if (p.a.peer_shift > 0) {   // rows of ghost cells come straight from the owning GPU's HBM (P2P over NVLink)
       const uint32_t mask = (1u << p.a.peer_shift) - 1u;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        const uint32_t i = (uint32_t)ixs[16 * jj];
+        const uint32_t i = (uint32_t)lds_s32(ixa + 64 * jj);
         v[jj] = ldg_f4(p.a.peer_base[i >> p.a.peer_shift] + d.colk + f4 * 4 + (int64_t)(i & mask) * ld);
       }
     } else {
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + (int64_t)ixs[16 * jj] * ld);
+      for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + (int64_t)lds_s32(ixa + 64 * jj) * ld);
     }
   } else if (d.mode == GNNFD_SEG_MEAN3) {
 #pragma unroll
@@ -175,9 +179,9 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int jj = h * 2 + u;
-        v[jj] = ldg_f4(base + (int64_t)ixs[16 * jj] * ld);
-        y[u] = ldg_f4(base + (int64_t)ixs[TC_BM + 16 * jj] * ld);
-        z[u] = ldg_f4(base + (int64_t)ixs[2 * TC_BM + 16 * jj] * ld);
+        v[jj] = ldg_f4(base + (int64_t)lds_s32(ixa + 64 * jj) * ld);
+        y[u] = ldg_f4(base + (int64_t)lds_s32(ixa + (TC_BM + 16 * jj) * 4) * ld);
+        z[u] = ldg_f4(base + (int64_t)lds_s32(ixa + (2 * TC_BM + 16 * jj) * 4) * ld);
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -194,8 +198,8 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int jj = h * 4 + u;
-        v[jj] = ldg_f4(base + (int64_t)ixs[16 * jj] * ld);
-        y[u] = ldg_f4(base + (int64_t)ixs[TC_BM + 16 * jj] * ld);
+        v[jj] = ldg_f4(base + (int64_t)lds_s32(ixa + 64 * jj) * ld);
+        y[u] = ldg_f4(base + (int64_t)lds_s32(ixa + (TC_BM + 16 * jj) * 4) * ld);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[h * 4 + u] = diff ? f4_sub(v[h * 4 + u], y[u]) : f4_add(v[h * 4 + u], y[u]);
@@ -204,17 +208,16 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 }
 
 template <bool FP16, int NA>
-__device__ __forceinline__ void tc_store_block(uint8_t *sA, const float4 (&v)[8], int rbase, int f4, bool active) {
+__device__ __forceinline__ void tc_store_block(uint32_t sA, const float4 (&v)[8], uint32_t off0, bool active) {
+  // off0 = sw128(rbase, f4 >> 1) + (f4 & 1) * 8: rows rbase + 16 jj share (r & 7), so row jj is off0 + jj * 2048
   if (active) {
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) {
-      const int r = rbase + 16 * jj;
       uint32_t h0, l0, h1, l1;
       split2<FP16>(v[jj].x, v[jj].y, h0, l0);
       split2<FP16>(v[jj].z, v[jj].w, h1, l1);
-      const uint32_t off = sw128(r, f4 >> 1) + (f4 & 1) * 8;
-      *reinterpret_cast<uint2 *>(sA + off) = make_uint2(h0, h1);
-      if (NA == 2) *reinterpret_cast<uint2 *>(sA + TC_IMG + off) = make_uint2(l0, l1);
+      sts_u2(sA + off0 + jj * 2048, h0, h1);
+      if (NA == 2) sts_u2(sA + TC_IMG + off0 + jj * 2048, l0, l1);
     }
   }
 }
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     const int f4 = pt & 15;                // float4 column inside the 64-wide k-block
     const int rbase = pt >> 4;             // rows rbase + 16 j
     const int NB = T * p.kb1;              // k-blocks this CTA produces, in MMA consumption order
+    const uint32_t sa_u32 = smem_u32(s_a), off0 = sw128(rbase, f4 >> 1) + (f4 & 1) * 8;
 
     auto stage_idx = [&](int j) {          // async copy of tile j's gather indices into slot j & 3
       if (j < T) {
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       }
       PROF_WAIT(0, mbar_wait(&a_empty[st], sphase));
       const int ksteps = (skb == p.kb1 - 1) ? p.ksteps1 : 4;
-      PROF_WAIT(1, (tc_store_block<FP16, NA>(s_a + st * 2 * TC_IMG, v, rbase, f4, f4 * 4 < ksteps * 16)));
+      PROF_WAIT(1, (tc_store_block<FP16, NA>(sa_u32 + st * 2 * TC_IMG, v, off0, f4 * 4 < ksteps * 16)));
       PROF_WAIT(2, fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(&a_full[st]));
       if (++skb == p.kb1) { skb = 0; ++sj; }
       if (++st == TC_A_STAGES) { st = 0; sphase ^= 1; }

@@ -185,6 +185,14 @@ __device__ __forceinline__ float2 lds_f2(uint32_t saddr) {
 __device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ int32_t lds_s32(uint32_t saddr) {
+  int32_t v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t saddr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void sts_f2(uint32_t saddr, float2 v) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(v.x), "f"(v.y) : "memory");
 }

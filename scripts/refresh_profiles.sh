@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round-end refresh of the measurements kept under profiles/ (run on the B200 box through gpurun).
+set -x
+O=gpurun_out/refresh; mkdir -p $O
+timeout 600 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; tail -2 $O/pytest_gpu.log
+timeout 200 python bench.py --steps 10 --warmup 3 > $O/bench_train.json 2> $O/bench_train.err
+timeout 120 python bench.py --workload fvgn_fwd_8x20k --steps 20 --warmup 5 > $O/bench_fwd.json 2> $O/bench_fwd.err
+timeout 120 python bench.py --workload mgn_rollout_2k --steps 50 --warmup 5 > $O/bench_mgn_rollout_2k.json 2> $O/mgn2k.err
+timeout 200 python bench.py --workload flux_rollout_200k --steps 10 --warmup 3 > $O/bench_flux_rollout_200k.json 2> $O/flux.err
+timeout 200 python bench.py --workload cons_rollout_200k --steps 10 --warmup 3 > $O/bench_cons_rollout_200k.json 2> $O/cons.err
+timeout 300 python bench.py --workload mgn_rollout_4m --steps 5 --warmup 3 > $O/bench_4m_1gpu.json 2> $O/4m.err
+timeout 200 python scripts/bench_kernels.py > $O/kernel_microbench.log 2>&1
+# ncu passes (never a bench value): launch list of one training step, then --set full of the training kernels + fwd
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/train_launches.csv python bench.py --steps 1 --warmup 1 > $O/ncu_list.log 2>&1
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"wgrad_tc|mlp_tc_kernel" -s 7 -c 7 -o $O/train_kernels -f python scripts/prof_train_kernels.py > $O/ncu_train.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 2 -c 1 -o $O/fwd_edge -f python scripts/prof_fwd_edge.py > $O/ncu_fwd.log 2>&1
+ls -la $O
