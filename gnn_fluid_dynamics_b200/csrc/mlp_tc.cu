@@ -6,11 +6,11 @@
 //   layers 2, 3: tcgen05.mma TS (A operand read straight from TMEM, W from shared memory)
 //   final epilogue: +bias -> LayerNorm -> *mul -> coalesced (+residual) stores
 //
-// One persistent CTA per SM keeps TWO 128-row tiles in flight (TMEM slots 0/1, 256 columns each): the
-// MMA warp works on one tile's layer while an epilogue warpgroup turns the other tile's accumulator
-// into the next layer's operand.  No intermediate touches HBM or shared memory: a slot is two
-// 128-column regions X, Y;  L1: D=X | E1: X -> X (in place) | L2: A=X, D=Y | E2: Y -> Y | L3: A=Y, D=X.
-// In-place layout: the 32 fp32 columns of chunk c become 16 columns of packed hi pairs + 16 of lo pairs.
+// One persistent CTA per SM keeps THREE 128-row tiles in flight.  TMEM (512 columns) = three X regions (tile j % 3)
+// + one Y region;  L1: D=X | E1: X -> X (in place) | L2: A=X, D=Y | E2: Y -> Y | L3: A=Y, D=X | final: X -> HBM.
+// Y is handed from tile to tile by the in-order tensor pipe (L2 of tile j + 1 is issued after L3 of tile j by the
+// same thread).  No intermediate touches HBM or shared memory.
+// In-place layout: the 16 fp32 columns of group c become 8 columns of packed hi pairs + 8 of lo pairs.
 //
 // Operand precision is a template: split operands (x = hi + lo, products hi*hi + lo*hi + hi*lo) restore
 // ~fp32 accuracy on the bf16/fp16 tensor pipe (single-pass bf16 fails the 1e-3 bar).
