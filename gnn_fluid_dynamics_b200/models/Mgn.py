@@ -101,3 +101,59 @@ class MgnA(Model):
 
         def forward(self, graph, prec=0):
             return P.mlp_rows(self.face_mlp, graph.x, prec)
+
+
+def divergence_from_uc(cell_velocity, weights, neighbours, cell_volume):   # utils/fvm.py:40-52
+    ux, uy = cell_velocity[:, 0], cell_velocity[:, 1]
+    gx = torch.sum(weights[:, :, 0] * (ux[neighbours] - ux[:, None]), dim=1)
+    gy = torch.sum(weights[:, :, 1] * (uy[neighbours] - uy[:, None]), dim=1)
+    return (gx + gy).unsqueeze(-1) * cell_volume
+
+
+class MgnB(MgnA):
+    """Direct prediction of the next velocity, z-score normalisation (Mgn.py:278-391): same encoder / processor /
+    decoder kernels as MgnA, different normalisation tables, output keys and loss."""
+
+    @classmethod
+    def normalisation_tables(cls):   # Mgn.py:318-337
+        kinds, inputs, outputs = MgnA.normalisation_tables()
+        inputs = [r for r in inputs if r[3] not in ("cell_velocity_change_x", "cell_velocity_change_y")]
+        inputs += [(0, "y", col(0), "cell_velocity_x"), (0, "y", col(1), "cell_velocity_y")]
+        outputs = [(0, col(0), "cell_velocity_x"), (0, col(1), "cell_velocity_y"), (0, col(2), "cell_pressure")]
+        return kinds, inputs, outputs
+
+    def forward(self, graphs, mode="train"):   # Mgn.py:340-360
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x
+        topo = get_topology(graphs)
+        _, _, cell_output = self.encode_process_decode(c_graph.x, f_graph.x, topo)
+        output = [cell_output, None, None]
+        if mode == "rollout":
+            output = self.normalizer.output(output, inverse=True)
+        return {"cell_velocity": output[0][:, 0:2], "cell_pressure": output[0][:, 2:3]}
+
+    def loss(self, output, graphs):   # Mgn.py:362-391
+        c_graph, f_graph, v_graph = graphs
+        lf = self.loss_func
+        div = divergence_from_uc(output["cell_velocity"], c_graph.grad_weights, c_graph.grad_neighbours, c_graph.volume)
+        continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
+        cv = lf(output["cell_velocity"], c_graph.y[:, 0:2], None, c_graph.batch)
+        cp = lf(output["cell_pressure"], c_graph.y[:, 2:3], None, f_graph.batch)
+        w = self.config.training.loss_weights
+        total = w["cell_velocity"] * cv + w["cell_pressure"] * cp + w["continuity"] * continuity
+        return {"total_log_loss": torch.mean(torch.log(total)), "cell_velocity_loss": cv,
+                "cell_pressure_loss": cp, "continuity_loss": continuity}
+
+
+class MgnC(MgnB):
+    """MgnB with the velocities scaled by the characteristic velocity (mean_scale) instead of z-scored (Mgn.py:394-424)."""
+
+    @classmethod
+    def normalisation_tables(cls):   # Mgn.py:402-424
+        kinds, inputs, outputs = MgnB.normalisation_tables()
+        kinds["cell_velocity_char"] = "mean_scale"
+        swap = lambda r: r[:-1] + ("cell_velocity_char",) if r[0] == 0 and r[-1] in ("cell_velocity_x", "cell_velocity_y") else r
+        inputs = [swap(r) for r in inputs]          # graphs[0].x / .y velocity columns; the face B.C. rows keep z-score
+        outputs = [(0, col(0), "cell_velocity_char"), (0, col(1), "cell_velocity_char"), (0, col(2), "cell_pressure")]
+        return kinds, inputs, outputs

@@ -1,8 +1,9 @@
 """B200-native drop-ins for the reference's ``src/models`` modules (same module and class names, so
 ``config.model.module = "gnn_fluid_dynamics_b200.models.Fvgn"``, ``config.model.name = "FvgnA"``)."""
 from .Fvgn import FvgnA, FvgnF  # noqa: F401
-from .Mgn import MgnA  # noqa: F401
-from .Flux import FluxA  # noqa: F401
+from .Mgn import MgnA, MgnB, MgnC  # noqa: F401
+from .StreamFunc import StreamFuncA, StreamFuncB, StreamFuncC, StreamFuncD  # noqa: F401
+from .Flux import FluxA, FluxB, FluxC, FluxD  # noqa: F401
 from .Conservative import (ConservativeA, ConservativeD, ConservativeE, ConservativeF, ConservativeG,  # noqa: F401
                            ConservativeH, ConservativeI, ConservativeK)
 from .VertPot import VertPotA  # noqa: F401
@@ -10,4 +11,5 @@ from .VertPot import VertPotA  # noqa: F401
 MODEL_CLASSES = {"FvgnA": FvgnA, "FvgnF": FvgnF, "MgnA": MgnA, "FluxA": FluxA, "ConservativeA": ConservativeA,
                  "VertPotA": VertPotA, "ConservativeE": ConservativeE, "ConservativeF": ConservativeF, "ConservativeD": ConservativeD,
                  "ConservativeG": ConservativeG, "ConservativeI": ConservativeI, "ConservativeH": ConservativeH,
-                 "ConservativeK": ConservativeK}
+                 "ConservativeK": ConservativeK, "MgnB": MgnB, "MgnC": MgnC, "StreamFuncA": StreamFuncA,
+                 "FluxB": FluxB, "FluxC": FluxC, "FluxD": FluxD, "StreamFuncB": StreamFuncB, "StreamFuncC": StreamFuncC, "StreamFuncD": StreamFuncD}

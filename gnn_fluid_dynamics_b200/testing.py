@@ -40,6 +40,17 @@ def stats_for(model_name: str):
     return out
 
 
+def add_mls_fixture(c_graph, k: int = 8, seed: int = 11):
+    """Synthetic moving-least-squares stencil on a cell graph: ``grad_neighbours`` [N, k] (random cells) and
+    ``grad_weights`` [N, k, 2].  The reference computes these offline (utils/maths.py MovingLeastSquaresWeights);
+    the models only consume them (StreamFunc.py:100-105, fvm.py:40-52), so any values exercise the path."""
+    g = torch.Generator().manual_seed(seed)
+    n = c_graph.x.shape[0]
+    c_graph.grad_neighbours = torch.randint(0, n, (n, k), generator=g)
+    c_graph.grad_weights = torch.randn(n, k, 2, generator=g) * 0.3
+    return c_graph
+
+
 def _rs(key: str, seed: int) -> np.random.RandomState:
     return np.random.RandomState((zlib.crc32(key.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
 

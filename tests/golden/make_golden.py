@@ -27,7 +27,7 @@ import refstub  # noqa: E402
 refstub.install()
 
 from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs  # noqa: E402
-from gnn_fluid_dynamics_b200.testing import default_stats, fill_state_dict_deterministic, stats_for  # noqa: E402
+from gnn_fluid_dynamics_b200.testing import add_mls_fixture, default_stats, fill_state_dict_deterministic, stats_for  # noqa: E402
 from gnn_fluid_dynamics_b200.graph import Data  # noqa: E402
 
 from utils.config import Config  # noqa: E402  (reference)
@@ -52,9 +52,21 @@ MODELS = {
     "ConservativeH": ("models.Conservative", "cylinder", "conservative_h"),
     "FvgnF": ("models.Fvgn", "airfoil", "fvgn"),
     "ConservativeK": ("models.Conservative", "ellipse", "conservative_h"),
+    "MgnB": ("models.Mgn", "ellipse", "fvgn"),
+    "MgnC": ("models.Mgn", "airfoil", "fvgn"),
+    "StreamFuncA": ("models.StreamFunc", "cylinder", "fvgn"),
+    "StreamFuncB": ("models.StreamFunc", "ellipse", "fvgn"),
+    "StreamFuncC": ("models.StreamFunc", "airfoil", "fvgn"),
+    "StreamFuncD": ("models.StreamFunc", "cylinder", "fvgn"),
+    "FluxB": ("models.Flux", "cylinder", "fvgn"),
+    "FluxC": ("models.Flux", "airfoil", "fvgn"),
+    "FluxD": ("models.Flux", "ellipse", "fvgn"),
 }
+MGN_LIKE = ("MgnA", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD")
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
-          "face_flux": 1, "face_pressure": 1}
+          "face_flux": 1, "face_pressure": 1, "cell_velocity": 10}
+# models whose fixture also pins model.loss(forward(batch, 'train'), batch) (eval mode, no grad)
+LOSS_MODELS = ("MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
 
 
 class _Dataset:
@@ -83,15 +95,19 @@ def graphs_for(name, kind, flavour, flip=False):
     mesh = make_mesh(160, kind, seed=3)
     g = mesh_graphs(mesh, seed=5, flavour=flavour, flip_edges=flip)
     c, f, v = g
-    if name == "MgnA":
+    if name in MGN_LIKE:
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
     elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
+    if name == "FluxC":
+        f.y = f.y[:, :2].contiguous()
     if name == "ConservativeI":
         # the reference indexes the [E, 128] latent with the face-type mask (Conservative.py:1264-1267), which only
         # works for a 1-D type tensor
         f.type = f.type.reshape(-1)
+    if name.startswith("StreamFunc") or name in ("MgnB", "MgnC"):
+        add_mls_fixture(c)
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
     return mesh, g
@@ -158,6 +174,10 @@ def gen_forward(name):
             res = model([g.clone() for g in graphs], mode=mode)
             for k, v in res.items():
                 out[f"out_{mode}_{k}"] = v.clone()
+        if name in LOSS_MODELS:
+            batch = [g.clone() for g in graphs]
+            for k, v in model.loss(model(batch, mode="train"), batch).items():
+                out[f"loss_{k}"] = v.reshape(1).clone()
     out.update(cap)
     np.savez_compressed(os.path.join(HERE, f"fwd_{name}.npz"), **to_np(out))
     print(name, {k: tuple(v.shape) for k, v in out.items()})

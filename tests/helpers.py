@@ -7,14 +7,20 @@ import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
-          "face_flux": 1, "face_pressure": 1}
+          "face_flux": 1, "face_pressure": 1, "cell_velocity": 10}
+LOSS_MODELS = ("MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
 # (mesh kind, feature flavour) used by tests/golden/make_golden.py per model
 GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "FluxA": ("ellipse", "fvgn"),
                 "ConservativeA": ("cylinder", "conservative"), "VertPotA": ("airfoil", "fvgn"),
                 "ConservativeE": ("ellipse", "fvgn"), "ConservativeF": ("airfoil", "fvgn"),
                 "ConservativeD": ("ellipse", "conservative"), "ConservativeG": ("cylinder", "fvgn"),
                 "ConservativeI": ("airfoil", "fvgn"), "ConservativeH": ("cylinder", "conservative_h"),
-                "FvgnF": ("airfoil", "fvgn"), "ConservativeK": ("ellipse", "conservative_h")}
+                "FvgnF": ("airfoil", "fvgn"), "ConservativeK": ("ellipse", "conservative_h"),
+                "MgnB": ("ellipse", "fvgn"), "MgnC": ("airfoil", "fvgn"), "StreamFuncA": ("cylinder", "fvgn"),
+                "StreamFuncB": ("ellipse", "fvgn"), "StreamFuncC": ("airfoil", "fvgn"), "StreamFuncD": ("cylinder", "fvgn"),
+                "FluxB": ("cylinder", "fvgn"), "FluxC": ("airfoil", "fvgn"), "FluxD": ("ellipse", "fvgn")}
+MGN_LIKE = ("MgnA", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD")
+ALL_MODELS = list(GOLDEN_SETUP)
 
 
 def make_config(mp_num=15, precision=None):
@@ -43,13 +49,18 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     mesh = make_mesh(n_cells, kind, seed=mesh_seed)
     g = mesh_graphs(mesh, seed=feat_seed, flavour=flavour, flip_edges=flip)
     c, f, v = g
-    if name == "MgnA":
+    if name in MGN_LIKE:
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
     elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
         f.y = f.y[:, :3].contiguous()
+    if name == "FluxC":
+        f.y = f.y[:, :2].contiguous()     # (pressure, flux) targets, Flux.py:322
     if name == "ConservativeI":
         f.type = f.type.reshape(-1)      # see tests/golden/make_golden.py: the reference needs a 1-D type tensor here
+    if name.startswith("StreamFunc") or name in ("MgnB", "MgnC"):
+        from gnn_fluid_dynamics_b200.testing import add_mls_fixture
+        add_mls_fixture(c)
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
     return mesh, g

@@ -7,7 +7,7 @@ import torch
 
 import oracle
 from gnn_fluid_dynamics_b200.testing import rel_l2
-from helpers import build_model, golden_graphs, load_golden
+from helpers import ALL_MODELS, LOSS_MODELS, build_model, golden_graphs, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -171,12 +171,14 @@ def _run_processor(name, model, graphs_dev):
     return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
 
 
-@pytest.mark.parametrize("name", ["MgnA", "FvgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"])
+@pytest.mark.parametrize("name", ALL_MODELS)
 def test_processor_matches_reference_golden(name):
     gold = load_golden(f"fwd_{name}.npz")
     model = build_model(name).eval()
     _, graphs = golden_graphs(name)
-    graphs = model.normalizer.input([g.clone() for g in graphs])
+    graphs = [g.clone() for g in graphs]
+    if name != "StreamFuncC":      # StreamFuncC.forward does not normalise (StreamFunc.py:173-176)
+        graphs = model.normalizer.input(graphs)
     model.to(dev())
     gd = [g.to(dev()) for g in graphs]
     for prec in precisions():
@@ -196,7 +198,7 @@ def test_processor_matches_reference_golden(name):
             assert rel_l2(out["dec_vertex"], torch.from_numpy(gold["dec_vertex"])) < 2 * t
 
 
-@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"])
+@pytest.mark.parametrize("name", ALL_MODELS)
 @pytest.mark.parametrize("mode", ["train", "rollout"])
 def test_full_forward_matches_reference_golden(name, mode):
     gold = load_golden(f"fwd_{name}.npz")
@@ -209,6 +211,21 @@ def test_full_forward_matches_reference_golden(name, mode):
         for k, v in out.items():
             err = rel_l2(v, torch.from_numpy(gold[f"out_{mode}_{k}"]))
             assert err < 3 * TOL[prec], (name, k, prec, err)
+
+
+@pytest.mark.parametrize("name", LOSS_MODELS)
+def test_loss_matches_reference_golden(name):
+    """model.loss(model(batch, 'train'), batch) of the glue-only variants against the value the reference computes."""
+    gold = load_golden(f"fwd_{name}.npz")
+    model = build_model(name).to(dev()).eval()
+    _, graphs = golden_graphs(name)
+    batch = [g.clone().to(dev()) for g in graphs]
+    with torch.no_grad():
+        losses = model.loss(model(batch, mode="train"), batch)
+    assert set(f"loss_{k}" for k in losses) == set(k for k in gold if k.startswith("loss_"))
+    for k, v in losses.items():
+        ref = float(gold[f"loss_{k}"][0])
+        assert abs(float(v) - ref) <= 2e-3 * max(abs(ref), 1e-6), (name, k, float(v), ref)
 
 
 @pytest.mark.parametrize("name,n_cells", [("FvgnA", 20000), ("MgnA", 2048)])
