@@ -266,3 +266,248 @@ class FvgnF(FvgnA):
                 super().__init__()
                 self.cell_mlp = build_mlp(config, hidden_size + hidden_size // 2 + 1, hidden_size, hidden_size)
                 self.mp_times = mp_times
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Glue-only variants: FvgnA's encoder / 15 GN_Blocks / decoder (the CUDA hot path) with other normalisation tables,
+# output scalings, integrators and losses.
+# ------------------------------------------------------------------------------------------------------------------
+def calc_gradient_tensor(value, weights, neighbours):   # utils/geometry.py:520-537 (index pairing as written there)
+    vx, vy = value[:, 0], value[:, 1]
+    dx, dy = vx[neighbours] - vx[:, None], vy[neighbours] - vy[:, None]
+    return torch.stack([torch.sum(weights[:, :, 0] * dx, dim=1), torch.sum(weights[:, :, 1] * dy, dim=1),
+                        torch.sum(weights[:, :, 0] * dy, dim=1), torch.sum(weights[:, :, 1] * dx, dim=1)], dim=1)
+
+
+def _advection_pressure(edge_output, c_graph, f_graph):
+    """Phi_A (u u . n A) and Phi_P (p n A) with the PHYSICAL face area (Fvgn.py:431-460 and 1244-1273)."""
+    unv, cf, area = c_graph.normal, f_graph.face, f_graph.area
+    uv, p_face = edge_output[:, 0:2], edge_output[:, 2:3]
+    uu_vu = torch.cat([uv[:, 0:1] * uv, uv[:, 1:2] * uv], dim=-1)
+    phi_a = sum(flux_dot(uu_vu[cf[j]], unv[:, j, :]) * area[cf[j]] for j in range(3))
+    phi_p = sum(p_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+    return phi_a, phi_p
+
+
+def _real_space_loss(model, output, graphs):
+    """Loss of the real-space variants B / J / K (Fvgn.py:388-423 == 1201-1236 == 1343-1378): the continuity term uses
+    the NORMALISED face area column of the face features."""
+    c_graph, f_graph, v_graph = graphs
+    lf = model.loss_func
+    ff, unv, fv, area = f_graph.face, c_graph.normal, output["face_velocity"], f_graph.x[:, 4:5]
+    div = sum(flux_dot(fv[ff[j]], unv[:, j, :]) * area[ff[j]] for j in range(3))
+    continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
+    cvc = lf(output["cell_velocity_change"], c_graph.y, None, c_graph.batch)
+    fvl = lf(output["face_velocity"], f_graph.y[:, :2], ~f_graph.boundary_mask, f_graph.batch)
+    fpl = lf(output["face_pressure"], f_graph.y[:, 2:3], None, f_graph.batch)
+    w = model.config.training.loss_weights
+    total = (w["continuity"] * continuity + w["cell_velocity_change"] * cvc
+             + w["face_velocity"] * fvl + w["face_pressure"] * fpl)
+    return {"total_log_loss": torch.mean(torch.log(total)), "continuity_loss": continuity,
+            "cell_velocity_change_loss": cvc, "face_velocity_loss": fvl, "face_pressure_loss": fpl}
+
+
+class FvgnB(FvgnA):
+    """Real-space integration: the decoder output is de-normalised before the integrator, diffusion comes from a
+    moving-least-squares velocity gradient instead of a predicted flux (Fvgn.py:336-460).  Decoder width 3."""
+    face_grad_weights_use = True
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.integrator = self.Integrator(config, rho=1, nu=1e-3)
+        self.face_mls_weights = None   # MovingLeastSquaresWeights is offline preprocessing (out of scope)
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 5 + n_class_types(dataset), 0], [0, 3, 0])
+
+    def forward(self, graphs, mode="rollout"):   # Fvgn.py:360-386
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x
+        _, _, edge_attr_out = self.encode_process_decode(c_graph.x, f_graph.x, get_topology(graphs))
+        output = self.normalizer.output([None, edge_attr_out.clone(), None], inverse=True)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator(output[1], c_graph, f_graph, self.dt)
+        output = [acc_pred, output[1], None]
+        if mode == "train":
+            output = self.normalizer.output(output)
+        return {"cell_velocity_change": output[0], "face_velocity": output[1][:, :2],
+                "face_pressure": output[1][:, 2:3]}
+
+    def loss(self, output, graphs):
+        return _real_space_loss(self, output, graphs)
+
+    class Integrator(nn.Module):   # Fvgn.py:425-460
+        def __init__(self, config, rho, nu=None):
+            super().__init__()
+            self.rho, self.nu = rho, nu
+
+        def forward(self, edge_output, c_graph, f_graph, dt):
+            unv, cf, area = c_graph.normal, f_graph.face, f_graph.area
+            phi_a, phi_p = _advection_pressure(edge_output, c_graph, f_graph)
+            grad = calc_gradient_tensor(edge_output[:, :2], f_graph.grad_weights, f_graph.grad_neighbours)
+            phi_d = sum(flux_dot(grad[cf[j]], unv[:, j, :]) * area[cf[j]] for j in range(3))
+            return torch.mean(dt) / c_graph.volume * (-phi_a - phi_p / self.rho + self.nu * phi_d)
+
+
+class FvgnD(FvgnA):
+    """Push-forward training: same network and forward as FvgnA; the dataset side changes the target and the
+    statistics (Fvgn.py:789-836)."""
+    pushforward_use = True
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.pushforward_use = True
+
+
+class FvgnE(FvgnA):
+    """Physical normalisation: every quantity scaled by a characteristic velocity / length / pressure
+    (Fvgn.py:839-880)."""
+
+    @classmethod
+    def normalisation_tables(cls):
+        kinds = {"characteristic_velocity": "max_scale", "characteristic_length": "mean_scale",
+                 "characteristic_pressure": "max_scale"}
+        u, l, pr = "characteristic_velocity", "characteristic_length", "characteristic_pressure"
+        inputs = [(0, "x", col(0), u), (0, "x", col(1), u), (0, "y", col(0), u), (0, "y", col(1), u),
+                  (1, "x", col(0), u), (1, "x", col(1), u), (1, "x", col(2), l), (1, "x", col(3), l),
+                  (1, "x", col(4), l), (1, "y", col(0), u), (1, "y", col(1), u), (1, "y", col(2), pr)]
+        outputs = [(0, col(0), u), (0, col(1), u), (1, col(0), u), (1, col(1), u), (1, col(2), pr)]
+        return kinds, inputs, outputs
+
+
+class FvgnH(FvgnA):
+    """Augmented face features: [du(2), face normal(2), area, adjacent distance, angle, one-hot] = 7 + |NodeType|
+    columns (Fvgn.py:1013-1114)."""
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 7 + n_class_types(dataset), 0], [0, 5, 0])
+
+    @classmethod
+    def normalisation_tables(cls):   # Fvgn.py:1064-1114
+        z = "z_score"
+        names = ["cell_velocity_x", "cell_velocity_y", "cell_velocity_change_x", "cell_velocity_change_y",
+                 "face_normal_x", "face_normal_y", "face_area", "face_adjacent_distance", "face_angle",
+                 "face_velocity_x", "face_velocity_y", "face_pressure", "face_velocity_difference_x",
+                 "face_velocity_difference_y"]
+        kinds = {k: z for k in names}
+        inputs = [(0, "x", col(0), "cell_velocity_x"), (0, "x", col(1), "cell_velocity_y"),
+                  (1, "x", col(0), "face_velocity_difference_x"), (1, "x", col(1), "face_velocity_difference_y"),
+                  (1, "x", col(4), "face_area"), (1, "x", col(5), "face_adjacent_distance"),
+                  (1, "x", col(6), "face_angle"), (1, "x", col(2), "face_normal_x"), (1, "x", col(3), "face_normal_y"),
+                  (0, "y", col(0), "cell_velocity_change_x"), (0, "y", col(1), "cell_velocity_change_y"),
+                  (1, "y", col(0), "face_velocity_x"), (1, "y", col(1), "face_velocity_y"),
+                  (1, "y", col(2), "face_pressure")]
+        outputs = [(0, col(0), "cell_velocity_change_x"), (0, col(1), "cell_velocity_change_y"),
+                   (1, col(0), "face_velocity_x"), (1, col(1), "face_velocity_y"), (1, col(2), "face_pressure")]
+        return kinds, inputs, outputs
+
+
+class FvgnI(FvgnA):
+    """FvgnA whose rollout feature update re-imposes INFLOW and WALL faces (Fvgn.py:1117-1137); FvgnA.update_features
+    here already implements exactly that masking, so only the class identity differs."""
+
+
+class FvgnJ(FvgnA):
+    """Learnt real-space output scales / biases and a physical integrator (Fvgn.py:1140-1273)."""
+    face_grad_weights_use = False
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.integrator = self.Integrator(config, rho=1, nu=1e-3)
+        self.face_mls_weights = None
+        self.velocity_scale_x = nn.Parameter(torch.tensor(1.0))
+        self.velocity_scale_y = nn.Parameter(torch.tensor(0.01))
+        self.pressure_scale = nn.Parameter(torch.tensor(1.0))
+        self.diffusion_scale = nn.Parameter(torch.tensor(1.0))
+        self.velocity_bias_x = nn.Parameter(torch.tensor(0.0))
+        self.velocity_bias_y = nn.Parameter(torch.tensor(0.0))
+        self.pressure_bias = nn.Parameter(torch.tensor(0.0))
+        self.diffusion_bias = nn.Parameter(torch.tensor(0.0))
+
+    def forward(self, graphs, mode="rollout"):   # Fvgn.py:1164-1199
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x
+        _, _, raw = self.encode_process_decode(c_graph.x, f_graph.x, get_topology(graphs))
+        edge_attr_out = torch.cat([raw[:, 0:1] * self.velocity_scale_x + self.velocity_bias_x,
+                                   raw[:, 1:2] * self.velocity_scale_y + self.velocity_bias_y,
+                                   raw[:, 2:3] * self.pressure_scale + self.pressure_bias,
+                                   raw[:, 3:5] * self.diffusion_scale + self.diffusion_bias], dim=-1)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
+        output = [acc_pred, edge_attr_out, None]
+        if mode != "rollout":
+            output = self.normalizer.output(output)
+        return {"cell_velocity_change": output[0][:, 0:2], "face_velocity": output[1][:, :2],
+                "face_pressure": output[1][:, 2:3]}
+
+    def loss(self, output, graphs):
+        return _real_space_loss(self, output, graphs)
+
+    class Integrator(nn.Module):   # Fvgn.py:1238-1273
+        def __init__(self, config, rho, nu=None):
+            super().__init__()
+            self.rho, self.nu = rho, nu
+
+        def forward(self, edge_output, c_graph, f_graph, dt):
+            cf, q = f_graph.face, edge_output[:, 3:5]
+            phi_a, phi_p = _advection_pressure(edge_output, c_graph, f_graph)
+            phi_d = q[cf[0], :] + q[cf[1], :] + q[cf[2], :]
+            return torch.mean(dt) / c_graph.volume * (-phi_a - phi_p / self.rho + self.nu * phi_d)
+
+
+class FvgnK(FvgnA):
+    """Dimensionless outputs scaled per mesh by the inflow velocity and the Reynolds length (Fvgn.py:1276-1416)."""
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.integrator = self.Integrator(config, rho=1, nu=1e-3)
+        self.face_mls_weights = None
+        self.anisotropy_ratio = nn.Parameter(torch.tensor(0.0001))
+
+    def forward(self, graphs, mode="rollout"):   # Fvgn.py:1290-1341
+        c0, f0 = graphs[0], graphs[1]
+        inflow = (f0.type == NODE_INFLOW)
+        u_ref = []
+        for b in torch.unique(c0.batch):          # reference values are read BEFORE the in-place normalisation
+            m = (f0.batch == b).reshape(inflow.shape) & inflow
+            if m.any():
+                u_ref.append(f0.y[m.reshape(-1)][0, 0])
+            else:
+                u_ref.append(torch.tensor(1.0, device=c0.y.device))
+        u_ref = torch.stack(u_ref)
+        l_ref = c0.Re * 1e-3 / u_ref
+        u_ref = u_ref[f0.batch].unsqueeze(-1)
+        l_ref = l_ref[f0.batch].unsqueeze(-1)
+        p_ref, d_ref = u_ref ** 2, u_ref * l_ref
+
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x
+        _, _, raw = self.encode_process_decode(c_graph.x, f_graph.x, get_topology(graphs))
+        edge_attr_out = torch.cat([raw[:, 0:1] * u_ref, raw[:, 1:2] * u_ref * self.anisotropy_ratio,
+                                   raw[:, 2:3] * p_ref, raw[:, 3:5] * d_ref], dim=-1)
+        self.dt = c_graph.dt.clone()
+        acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
+        output = [acc_pred, edge_attr_out, None]
+        if mode != "rollout":
+            output = self.normalizer.output(output)
+        return {"cell_velocity_change": output[0][:, 0:2], "face_velocity": output[1][:, :2],
+                "face_pressure": output[1][:, 2:3]}
+
+    def loss(self, output, graphs):
+        return _real_space_loss(self, output, graphs)
+
+    class Integrator(nn.Module):   # Fvgn.py:1380-1416 (one diffusion column, broadcast over both components)
+        def __init__(self, config, rho, nu=None):
+            super().__init__()
+            self.rho, self.nu = rho, nu
+
+        def forward(self, edge_output, c_graph, f_graph, dt):
+            cf, d = f_graph.face, edge_output[:, 3:4]
+            phi_a, phi_p = _advection_pressure(edge_output, c_graph, f_graph)
+            phi_d = d[cf[0], :] + d[cf[1], :] + d[cf[2], :]
+            return torch.mean(dt) / c_graph.volume * (-phi_a - phi_p + phi_d * 1e-3)

@@ -37,6 +37,12 @@ def stats_for(model_name: str):
     if model_name in ("ConservativeH", "ConservativeJ", "ConservativeK"):
         for i, k in enumerate(("face_velocity_diff_x", "face_velocity_diff_y")):
             out[k] = {"mean": 0.07 + 0.03 * i, "std": 1.2 + 0.1 * i, "min": -1.0, "max": 1.0}
+    if model_name == "FvgnE":      # physical normalisation (Fvgn.py:846-851)
+        for i, k in enumerate(("characteristic_velocity", "characteristic_length", "characteristic_pressure")):
+            out[k] = {"mean": 0.6 + 0.2 * i, "std": 1.1, "min": 0.1, "max": 1.5 + 0.5 * i}
+    if model_name == "FvgnH":      # augmented face features (Fvgn.py:1066-1081)
+        for i, k in enumerate(("face_normal_x", "face_normal_y", "face_angle")):
+            out[k] = {"mean": 0.04 * (i + 1), "std": 0.9 + 0.1 * i, "min": -1.0, "max": 1.0}
     return out
 
 
@@ -45,7 +51,7 @@ def add_mls_fixture(c_graph, k: int = 8, seed: int = 11):
     ``grad_weights`` [N, k, 2].  The reference computes these offline (utils/maths.py MovingLeastSquaresWeights);
     the models only consume them (StreamFunc.py:100-105, fvm.py:40-52), so any values exercise the path."""
     g = torch.Generator().manual_seed(seed)
-    n = c_graph.x.shape[0]
+    n = c_graph.pos.shape[0]
     c_graph.grad_neighbours = torch.randint(0, n, (n, k), generator=g)
     c_graph.grad_weights = torch.randn(n, k, 2, generator=g) * 0.3
     return c_graph

@@ -27,6 +27,7 @@ _FAMILY_OF = {
     "ConservativeG": "cons_g", "ConservativeI": "cons_i", "ConservativeH": "cons_h", "ConservativeJ": "cons_h",
     "FvgnF": "fvgn_f", "ConservativeK": "cons_h",      # K = H with a half-width antisymmetric stream (same data-flow)
     # glue-only variants: MgnA's encoder / processor / decoder (Mgn.py:278-424, StreamFunc.py:109-235)
+    "FvgnB": "fvgn", "FvgnD": "fvgn", "FvgnE": "fvgn", "FvgnH": "fvgn", "FvgnI": "fvgn", "FvgnJ": "fvgn", "FvgnK": "fvgn",
     "FluxB": "fvgn", "FluxC": "fvgn", "FluxD": "fvgn",      # FvgnA's network, other integrators (Flux.py:209-595)
     "MgnB": "mgn", "MgnC": "mgn", "StreamFuncA": "mgn", "StreamFuncB": "mgn", "StreamFuncC": "mgn", "StreamFuncD": "mgn",
 }

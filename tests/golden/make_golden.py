@@ -61,12 +61,20 @@ MODELS = {
     "FluxB": ("models.Flux", "cylinder", "fvgn"),
     "FluxC": ("models.Flux", "airfoil", "fvgn"),
     "FluxD": ("models.Flux", "ellipse", "fvgn"),
+    "FvgnB": ("models.Fvgn", "cylinder", "fvgn"),
+    "FvgnD": ("models.Fvgn", "ellipse", "fvgn"),
+    "FvgnE": ("models.Fvgn", "airfoil", "fvgn"),
+    "FvgnH": ("models.Fvgn", "cylinder", "fvgn"),
+    "FvgnI": ("models.Fvgn", "ellipse", "fvgn"),
+    "FvgnJ": ("models.Fvgn", "airfoil", "fvgn"),
+    "FvgnK": ("models.Fvgn", "cylinder", "fvgn"),
 }
+FVGN_LIKE = ("FvgnA", "FvgnB", "FvgnD", "FvgnE", "FvgnH", "FvgnI", "FvgnJ", "FvgnK")
 MGN_LIKE = ("MgnA", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD")
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1, "cell_velocity": 10}
 # models whose fixture also pins model.loss(forward(batch, 'train'), batch) (eval mode, no grad)
-LOSS_MODELS = ("MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
+LOSS_MODELS = ("FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
 
 
 class _Dataset:
@@ -98,10 +106,18 @@ def graphs_for(name, kind, flavour, flip=False):
     if name in MGN_LIKE:
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
+    elif name in FVGN_LIKE + ("ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
     if name == "FluxC":
         f.y = f.y[:, :2].contiguous()
+    if name == "FvgnB":
+        add_mls_fixture(f, seed=12)
+    if name == "FvgnH":
+        extra = torch.randn(f.x.shape[0], 2, generator=torch.Generator().manual_seed(13))
+        f.x = torch.cat([f.x[:, :5], extra, f.x[:, 5:]], dim=1)
+    if name == "FvgnK":
+        c.Re = torch.tensor([150.0])
+        f.type = f.type.reshape(-1)
     if name == "ConservativeI":
         # the reference indexes the [E, 128] latent with the face-type mask (Conservative.py:1264-1267), which only
         # works for a 1-D type tensor

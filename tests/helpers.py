@@ -8,7 +8,7 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1, "cell_velocity": 10}
-LOSS_MODELS = ("MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
+LOSS_MODELS = ("FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
 # (mesh kind, feature flavour) used by tests/golden/make_golden.py per model
 GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "FluxA": ("ellipse", "fvgn"),
                 "ConservativeA": ("cylinder", "conservative"), "VertPotA": ("airfoil", "fvgn"),
@@ -18,7 +18,9 @@ GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "Fl
                 "FvgnF": ("airfoil", "fvgn"), "ConservativeK": ("ellipse", "conservative_h"),
                 "MgnB": ("ellipse", "fvgn"), "MgnC": ("airfoil", "fvgn"), "StreamFuncA": ("cylinder", "fvgn"),
                 "StreamFuncB": ("ellipse", "fvgn"), "StreamFuncC": ("airfoil", "fvgn"), "StreamFuncD": ("cylinder", "fvgn"),
-                "FluxB": ("cylinder", "fvgn"), "FluxC": ("airfoil", "fvgn"), "FluxD": ("ellipse", "fvgn")}
+                "FluxB": ("cylinder", "fvgn"), "FluxC": ("airfoil", "fvgn"), "FluxD": ("ellipse", "fvgn"),
+                "FvgnB": ("cylinder", "fvgn"), "FvgnD": ("ellipse", "fvgn"), "FvgnE": ("airfoil", "fvgn"), "FvgnH": ("cylinder", "fvgn"), "FvgnI": ("ellipse", "fvgn"), "FvgnJ": ("airfoil", "fvgn"), "FvgnK": ("cylinder", "fvgn")}
+FVGN_LIKE = ("FvgnA", "FvgnB", "FvgnD", "FvgnE", "FvgnH", "FvgnI", "FvgnJ", "FvgnK")
 MGN_LIKE = ("MgnA", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD")
 ALL_MODELS = list(GOLDEN_SETUP)
 
@@ -52,10 +54,11 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     if name in MGN_LIKE:
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in ("FvgnA", "ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
+    elif name in FVGN_LIKE + ("ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
         f.y = f.y[:, :3].contiguous()
     if name == "FluxC":
         f.y = f.y[:, :2].contiguous()     # (pressure, flux) targets, Flux.py:322
+    fvgn_variant_fixture(name, c, f)
     if name == "ConservativeI":
         f.type = f.type.reshape(-1)      # see tests/golden/make_golden.py: the reference needs a 1-D type tensor here
     if name.startswith("StreamFunc") or name in ("MgnB", "MgnC"):
@@ -64,6 +67,19 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
     return mesh, g
+
+
+def fvgn_variant_fixture(name, c, f):
+    """Extra inputs of the FvgnA glue variants (same construction in tests/golden/make_golden.py)."""
+    from gnn_fluid_dynamics_b200.testing import add_mls_fixture
+    if name == "FvgnB":       # face moving-least-squares stencil for the diffusion term (Fvgn.py:446)
+        add_mls_fixture(f, seed=12)
+    if name == "FvgnH":       # 7 + 5 face feature columns (Fvgn.py:1057)
+        extra = torch.randn(f.x.shape[0], 2, generator=torch.Generator().manual_seed(13))
+        f.x = torch.cat([f.x[:, :5], extra, f.x[:, 5:]], dim=1)
+    if name == "FvgnK":       # per-mesh Reynolds number; the reference needs a 1-D type tensor here (Fvgn.py:1291-1296)
+        c.Re = torch.tensor([150.0])
+        f.type = f.type.reshape(-1)
 
 
 def load_golden(fname):
