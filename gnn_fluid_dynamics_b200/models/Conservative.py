@@ -12,6 +12,7 @@ from .._lib import ACT_TANH
 from ..topology import get_topology
 from .base import build_mlp, build_mlp_antisym, col, n_class_types
 from .Fvgn import FvgnA
+from .Mgn import MgnA
 
 
 class ConservativeA(FvgnA):
@@ -148,6 +149,69 @@ class ConservativeF(FvgnA):
             super().__init__()
             self.cell_block = ConservativeA.GN_Block.Cell_Block(config, hidden_size)    # in = 2H (x, two-hop sym, signed asym)
             self.face_block = FvgnA.GN_Block.Face_Block(config, hidden_size)            # in = 3H
+
+
+class ConservativeB(MgnA):
+    """ConservativeA's encoder and GN_Blocks under MgnA's node decoder, loss and outputs (Conservative.py:265-414)."""
+    family = "cons_a"
+    _registry_overrides = ConservativeA._registry_overrides
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)      # decoder = self.Decoder (node_mlp), Mgn.py:55
+        self.encoder = ConservativeA.Encoder(config, self.input_sizes, self.hidden_size)
+        self.processer_list = nn.ModuleList(
+            [ConservativeA.GN_Block(config, self.hidden_size) for _ in range(config.model.mp_num)])
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 3 + n_class_types(dataset), 0], [3, 0, 0])
+
+    @classmethod
+    def normalisation_tables(cls):   # Conservative.py:325-366
+        z = "z_score"
+        kinds = {k: z for k in ["cell_velocity_x", "cell_velocity_y", "cell_velocity_change_x", "cell_velocity_change_y",
+                                "cell_pressure", "face_area", "face_adjacent_distance", "face_velocity_x",
+                                "face_velocity_y"]}
+        kinds["face_velocity_diff_char"] = "mean_scale"
+        inputs = [(0, "x", col(0), "cell_velocity_x"), (0, "x", col(1), "cell_velocity_y"),
+                  (1, "x_asym", col(0, 2), "face_velocity_diff_char"),
+                  (1, "x_symm", col(0), "face_area"), (1, "x_symm", col(2), "face_adjacent_distance"),
+                  (0, "y", col(0), "cell_velocity_change_x"), (0, "y", col(1), "cell_velocity_change_y"),
+                  (0, "y", col(2), "cell_pressure"),
+                  (1, "y", col(0), "face_velocity_x"), (1, "y", col(1), "face_velocity_y")]
+        outputs = [(0, col(0), "cell_velocity_change_x"), (0, col(1), "cell_velocity_change_y"),
+                   (0, col(2), "cell_pressure")]
+        return kinds, inputs, outputs
+
+    def training_plan(self):
+        raise NotImplementedError("ConservativeB trains through the per-op autograd wrappers (autograd_ops.py)")
+
+    def encode_process_decode(self, c_x, f_x_symm, f_x_asym, topo, hook=None):
+        prec = self.prec
+        e = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
+        e_asym = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
+        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, e_asym=e_asym, hook=hook)
+        return x, e, P.mlp_rows(self.decoder.node_mlp, x, prec)
+
+    def forward(self, graphs, mode="rollout"):   # Conservative.py:383-404
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x_symm
+        c_graph.edge_attr_asym = f_graph.x_asym
+        topo = get_topology(graphs, need_cell_csr=True, two_hop=False)
+        _, _, cell_output = self.encode_process_decode(c_graph.x, f_graph.x_symm, f_graph.x_asym, topo)
+        output = [cell_output, None, None]
+        if mode == "rollout":
+            output = self.normalizer.output(output, inverse=True)
+        return {"cell_velocity_change": output[0][:, 0:2], "cell_pressure": output[0][:, 2:3]}
+
+    update_features = ConservativeA.update_features   # Conservative.py:367-381 (same body as A's)
+
+    class Decoder(nn.Module):   # Conservative.py:406-414
+        def __init__(self, config, hidden_size, output_sizes):
+            super().__init__()
+            self.node_mlp = build_mlp(config, hidden_size, hidden_size, output_sizes[0], norm_layer=False)
 
 
 class ConservativeD(ConservativeA):
@@ -341,6 +405,73 @@ class ConservativeH(ConservativeD):
             super().__init__()
             self.even_mlp = build_mlp(config, 2 * hidden_size, hidden_size, 5, norm_layer=False)
             self.odd_mlp = build_mlp_antisym(config, 2 * hidden_size, hidden_size, 2)
+
+
+class ConservativeJ(ConservativeH):
+    """Reference ``ConservativeJ`` (Conservative.py:1320-1683): ConservativeH's encoder / dual-stream blocks / even-odd
+    decoder, with learnt real-space output scales and a physical (un-normalised) integrator, as FvgnJ does for FvgnA."""
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.integrator = self.Integrator(config, rho=1.0)
+        self.velocity_scale_x = nn.Parameter(torch.tensor(1.0))
+        self.velocity_scale_y = nn.Parameter(torch.tensor(0.01))
+        self.pressure_scale = nn.Parameter(torch.tensor(1.0))
+        self.diffusion_scale = nn.Parameter(torch.tensor(1.0))
+        self.velocity_bias_x = nn.Parameter(torch.tensor(0.0))
+        self.velocity_bias_y = nn.Parameter(torch.tensor(0.0))
+        self.pressure_bias = nn.Parameter(torch.tensor(0.0))
+
+    def forward(self, graphs, mode="rollout"):   # Conservative.py:1483-1517
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x_symm
+        c_graph.edge_attr_asym = f_graph.x_asym
+        topo = get_topology(graphs, need_cell_csr=True, two_hop=True)
+        _, _, raw = self.encode_process_decode(c_graph.x, f_graph.x_symm, f_graph.x_asym, topo)
+        edge_attr_out = torch.cat([raw[:, 0:1] * self.velocity_scale_x + self.velocity_bias_x,
+                                   raw[:, 1:2] * self.velocity_scale_y + self.velocity_bias_y,
+                                   raw[:, 2:3] * self.pressure_scale + self.pressure_bias,
+                                   raw[:, 3:5] * self.diffusion_scale], dim=-1)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
+        output = [acc_pred, edge_attr_out, None]
+        if mode != "rollout":
+            output = self.normalizer.output(output)      # normalised for the training loss
+        return {"cell_velocity_change": output[0][:, 0:2], "face_velocity": output[1][:, :2],
+                "face_pressure": output[1][:, 2:3]}
+
+    def loss(self, output, graphs):   # Conservative.py:1442-1477: continuity with the normalised face-area feature
+        from .Fvgn import flux_dot
+        c_graph, f_graph, v_graph = graphs
+        lf = self.loss_func
+        ff, unv, fv, area = f_graph.face, c_graph.normal, output["face_velocity"], f_graph.x_symm[:, 0:1]
+        div = sum(flux_dot(fv[ff[j]], unv[:, j, :]) * area[ff[j]] for j in range(3))
+        continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
+        cvc = lf(output["cell_velocity_change"], c_graph.y, None, c_graph.batch)
+        fvl = lf(output["face_velocity"], f_graph.y[:, :2], ~f_graph.boundary_mask, f_graph.batch)
+        fpl = lf(output["face_pressure"], f_graph.y[:, 2:3], None, f_graph.batch)
+        w = self.config.training.loss_weights
+        total = (w["continuity"] * continuity + w["cell_velocity_change"] * cvc
+                 + w["face_velocity"] * fvl + w["face_pressure"] * fpl)
+        return {"total_log_loss": torch.mean(torch.log(total)), "continuity_loss": continuity,
+                "cell_velocity_change_loss": cvc, "face_velocity_loss": fvl, "face_pressure_loss": fpl}
+
+    class Integrator(nn.Module):   # Conservative.py:1520-1557
+        def __init__(self, config, rho):
+            super().__init__()
+            self.rho = rho
+            self.nu = 0.001
+
+        def forward(self, edge_output, c_graph, f_graph, dt):
+            from .Fvgn import flux_dot
+            unv, cf, area = c_graph.normal, f_graph.face, f_graph.area
+            uv, p_face, q_face = edge_output[:, 0:2], edge_output[:, 2:3], edge_output[:, 3:5]
+            uu_vu = torch.cat([uv[:, 0:1] * uv, uv[:, 1:2] * uv], dim=-1)
+            phi_a = sum(flux_dot(uu_vu[cf[j]], unv[:, j, :]) * area[cf[j]] for j in range(3))
+            phi_d = sum(q_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+            phi_p = sum(p_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+            return torch.mean(dt) / c_graph.volume * (-phi_a - phi_p / self.rho + self.nu * phi_d)
 
 
 def _padded_head(seq, act, n_valid, h=128):

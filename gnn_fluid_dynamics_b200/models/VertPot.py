@@ -1,4 +1,5 @@
-"""VertPot family on the B200 kernels - drop-in for reference ``src/models/VertPot.py`` (VertPotA):
+"""VertPot family on the B200 kernels - drop-in for reference ``src/models/VertPot.py`` (VertPotA, B, C, E, G;
+D and F call a function the reference does not define, ``fvm.convert_cell_flux_to_face_flux_alt``, and cannot run there):
 FvgnA blocks (under ``node_block`` / ``edge_block``) plus a Vertex_Block that sums the face block's raw
 output onto vertices; edge + vertex decoder heads (VertPot.py:187-231).
 """
@@ -10,8 +11,8 @@ from torch import nn
 from .. import processor as P
 from ..topology import get_topology
 from .base import build_mlp, col, n_class_types
-from .Flux import FluxA, normalize_vol_dt
-from .Fvgn import FvgnA, normalize_face_area
+from .Flux import FluxA, FluxC, cell_to_face, normalize_vol_dt
+from .Fvgn import FvgnA, calc_gradient_tensor, flux_dot, normalize_face_area
 
 
 def cell_flux_from_vertices(vertex_out, v_face):
@@ -111,3 +112,214 @@ class VertPotA(FluxA):
             super().__init__()
             self.edge_mlp = build_mlp(config, hidden_size, hidden_size, output_sizes[1], norm_layer=False)
             self.vertex_mlp = build_mlp(config, hidden_size, hidden_size, output_sizes[2], norm_layer=False)
+
+
+def cell_flux_to_owner_face_flux(cell_flux, edge_index, face_index):
+    """Face flux = the owner cell's local flux of that face (utils/fvm.py:55-93; the reference additionally raises when
+    a face is not listed exactly once by its owner cell, which a valid mesh never triggers)."""
+    owner = edge_index[0]
+    mask = face_index[:, owner] == torch.arange(edge_index.shape[1], device=cell_flux.device).unsqueeze(0)
+    local = torch.argmax(mask.int(), dim=0)
+    return cell_flux[owner, local].unsqueeze(-1)
+
+
+def cell_flux_to_face_flux_last(cell_flux, face_to_cells, cell_faces):
+    """utils/geometry.py:539-570 as written there, including its pairing of ``cell_faces.flatten()`` ([3, N] row-major)
+    with cell-major (cell, local face) indices; duplicate targets resolve to the LAST writer, which is what the
+    reference's indexed assignment does on the CPU (made explicit here so the GPU result is deterministic)."""
+    n, n_faces = cell_flux.shape[0], face_to_cells.shape[1]
+    gfi = cell_faces.flatten()
+    cells = torch.arange(n, device=cell_flux.device).repeat_interleave(3)
+    local = torch.arange(3, device=cell_flux.device).repeat(n)
+    flux = cell_flux[cells, local]
+    corrected = torch.where(face_to_cells[0, gfi] == cells, flux, -flux)
+    pos = torch.full((n_faces,), -1, dtype=torch.long, device=cell_flux.device)
+    pos = pos.scatter_reduce(0, gfi, torch.arange(3 * n, device=cell_flux.device), reduce="amax")
+    out = torch.where(pos >= 0, corrected[pos.clamp_min(0)], torch.zeros_like(corrected[:1]).expand(n_faces))
+    return out.unsqueeze(-1)
+
+
+class _VertPotNet:
+    """Mixin: VertPotA's processor and two-head decoder under another model's glue (VertPot.py:327-334 etc.)."""
+    family = "vertpot"
+    training_plan = VertPotA.training_plan
+    encode_process_decode = VertPotA.encode_process_decode
+
+    def _install_vertpot_net(self, config):
+        self.processer_list = nn.ModuleList(
+            [VertPotA.GN_Block(config, self.hidden_size) for _ in range(config.model.mp_num)])
+        self.decoder = VertPotA.Decoder(config, self.hidden_size, self.output_sizes)
+
+    def _heads(self, graphs):
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x
+        _, _, _, edge_out, vertex_out = self.encode_process_decode(c_graph.x, f_graph.x, get_topology(graphs))
+        return edge_out, cell_flux_from_vertices(vertex_out, v_graph.face)
+
+
+class VertPotB(VertPotA):
+    """VertPotA with a physical integrator on de-normalised outputs (VertPot.py:234-319)."""
+    face_grad_weights_use = True
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self.integrator = self.Integrator(config, rho=1, nu=1e-3)
+        self.face_mls_weights = None
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 5 + n_class_types(dataset), 0], [0, 3, 1])
+
+    def forward(self, graphs, mode="rollout"):   # VertPot.py:248-281
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x
+        _, _, _, edge_attr_out, vertex_out = self.encode_process_decode(c_graph.x, f_graph.x, get_topology(graphs))
+        cell_flux = cell_flux_from_vertices(vertex_out, v_graph.face)
+        norm_cell_out = torch.cat([torch.zeros_like(c_graph.x[:, 0:2]), cell_flux], dim=1)
+        output = self.normalizer.output([norm_cell_out.clone(), edge_attr_out.clone(), None], inverse=True)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator(output, c_graph, f_graph, self.dt)
+        output[0] = torch.cat([acc_pred, output[0][:, 2:]], dim=1)
+        if mode != "rollout":
+            output = self.normalizer.output([torch.cat([acc_pred, torch.zeros_like(cell_flux)], dim=1), None, None])
+            output[1] = edge_attr_out
+            output[0][:, 2:5] = cell_flux
+        else:
+            output[0][:, 0:2] = acc_pred
+        return {"cell_velocity_change": output[0][:, 0:2], "cell_flux": output[0][:, 2:5],
+                "face_velocity": output[1][:, 0:2], "face_pressure": output[1][:, 2:3]}
+
+    class Integrator(nn.Module):   # VertPot.py:283-319
+        def __init__(self, config, rho, nu=1e-3):
+            super().__init__()
+            self.rho, self.nu = rho, nu
+
+        def forward(self, output, c_graph, f_graph, dt):
+            unv, cf, area = c_graph.normal, f_graph.face, f_graph.area
+            uv, p_face, cell_flux = output[1][:, 0:2], output[1][:, 2:3], output[0][:, 2:5]
+            phi_a = sum(uv[cf[j]] * cell_flux[:, j:j + 1] for j in range(3))
+            grad = calc_gradient_tensor(uv, f_graph.grad_weights, f_graph.grad_neighbours)
+            phi_d = sum(flux_dot(grad[cf[j]], unv[:, j, :]) * area[cf[j]] for j in range(3))
+            phi_p = sum(p_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+            return torch.mean(dt) / c_graph.volume * (-phi_a - phi_p / self.rho + self.nu * phi_d)
+
+
+class VertPotC(_VertPotNet, FluxC):
+    """Pressure and diffusion on faces, the flux from vertex-potential differences, explicit face velocity
+    (VertPot.py:322-444)."""
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self._install_vertpot_net(config)
+        self.integrator = self.Integrator(config, rho=1.0)
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 5 + n_class_types(dataset), 0], [0, 3, 1])
+
+    def forward(self, graphs, mode="rollout"):   # VertPot.py:340-366
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        edge_attr_out, cell_flux = self._heads(graphs)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator([cell_flux, edge_attr_out], c_graph, f_graph, self.dt)
+        output = [torch.cat([acc_pred, cell_flux], dim=1), edge_attr_out, None]
+        if mode == "rollout":
+            output = self.normalizer.output(output, inverse=True)
+        return {"cell_velocity_change": output[0][:, 0:2], "cell_flux": output[0][:, 2:5],
+                "face_pressure": output[1][:, 0:1]}
+
+    def loss(self, output, graphs):   # VertPot.py:410-444
+        c_graph, f_graph, v_graph = graphs
+        lf = self.loss_func
+        div = output["cell_flux"][:, 0] + output["cell_flux"][:, 1] + output["cell_flux"][:, 2]
+        continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
+        cvc = lf(output["cell_velocity_change"], c_graph.y, None, c_graph.batch)
+        fpl = lf(output["face_pressure"], f_graph.y[:, 0:1], None, f_graph.batch)
+        w = self.config.training.loss_weights
+        total = w["continuity"] * continuity + w["cell_velocity_change"] * cvc + w["face_pressure"] * fpl
+        return {"total_log_loss": torch.mean(torch.log(total)), "continuity_loss": continuity,
+                "cell_velocity_change_loss": cvc, "face_pressure_loss": fpl}
+
+    class Integrator(nn.Module):   # VertPot.py:368-408
+        def __init__(self, config, rho):
+            super().__init__()
+            self.rho = rho
+            self.face_area_norm = nn.BatchNorm1d(1)
+            self.face_area = None
+
+        def forward(self, output, c_graph, f_graph, dt):
+            unv, cf = c_graph.normal, f_graph.face
+            cell_flux, edge_output = output
+            uv = cell_to_face(c_graph.x[:, 0:2], c_graph.edge_index, f_graph.pos, c_graph.pos)
+            p_face, flux_d = edge_output[:, 0:1], edge_output[:, 1:3]
+            phi_a = sum(uv[cf[j]] * cell_flux[:, j:j + 1] for j in range(3))
+            phi_d = flux_d[cf[0], :] + flux_d[cf[1], :] + flux_d[cf[2], :]
+            area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, dt, self.face_area_norm)
+            self.face_area = area
+            phi_p = sum(p_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+            return 1.0 * (-phi_a - phi_p / self.rho) + phi_d
+
+
+class VertPotE(_VertPotNet, FluxC):
+    """FluxC's glue and integrator over VertPotA's network; the face flux is read off the owner cell's vertex-potential
+    differences and appended to the edge head (VertPot.py:494-539)."""
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self._install_vertpot_net(config)
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 5 + n_class_types(dataset), 0], [0, 3, 1])
+
+    def forward(self, graphs, mode="rollout"):   # VertPot.py:510-539
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        edge_attr_out, cell_flux = self._heads(graphs)
+        face_flux = cell_flux_to_owner_face_flux(cell_flux, c_graph.edge_index, f_graph.face)
+        edge_attr_out = torch.cat([edge_attr_out, face_flux], dim=1)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
+        output = [acc_pred, edge_attr_out, None]
+        if mode == "rollout":
+            output = self.normalizer.output(output, inverse=True)
+        return {"cell_velocity_change": output[0][:, 0:2], "face_velocity": output[1][:, :2],
+                "face_pressure": output[1][:, 2:3], "face_flux": output[1][:, 3:4]}
+
+
+class VertPotG(VertPotA):
+    """VertPotA plus a face-flux output (and a loss on it) derived from the per-cell vertex-potential differences
+    (VertPot.py:631-818; its GN_Block / Decoder / Integrator restate VertPotA's)."""
+
+    def forward(self, graphs, mode="rollout"):   # VertPot.py:658-687
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x
+        _, _, _, edge_attr_out, vertex_out = self.encode_process_decode(c_graph.x, f_graph.x, get_topology(graphs))
+        cell_flux = cell_flux_from_vertices(vertex_out, v_graph.face)
+        self.dt = c_graph.dt
+        acc_pred = self.integrator([cell_flux, edge_attr_out], c_graph, f_graph, self.dt)
+        output = [torch.cat([acc_pred, cell_flux], dim=1), edge_attr_out, None]
+        if mode == "rollout":
+            output = self.normalizer.output(output, inverse=True)
+        face_flux = cell_flux_to_face_flux_last(output[0][:, 2:5], c_graph.edge_index, f_graph.face)
+        return {"cell_velocity_change": output[0][:, 0:2], "face_flux": face_flux,
+                "face_velocity": output[1][:, 0:2], "face_pressure": output[1][:, 2:3]}
+
+    def loss(self, output, graphs):   # VertPot.py:737-772
+        c_graph, f_graph, v_graph = graphs
+        lf = self.loss_func
+        ff, flux = f_graph.face, output["face_flux"]
+        div = flux[ff[0]] + flux[ff[1]] + flux[ff[2]]
+        continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
+        cvc = lf(output["cell_velocity_change"], c_graph.y, None, c_graph.batch)
+        fvl = lf(output["face_velocity"], f_graph.y[:, 0:2], None, f_graph.batch)
+        fpl = lf(output["face_pressure"], f_graph.y[:, 2:3], None, f_graph.batch)
+        ffl = lf(flux, f_graph.y[:, 3:4], None, f_graph.batch)
+        w = self.config.training.loss_weights
+        total = (w["continuity"] * continuity + w["cell_velocity_change"] * cvc + w["face_velocity"] * fvl
+                 + w["face_pressure"] * fpl + w["face_flux"] * ffl)
+        return {"total_log_loss": torch.mean(torch.log(total)), "continuity_loss": continuity,
+                "cell_velocity_change_loss": cvc, "face_velocity_loss": fvl, "face_pressure_loss": fpl}

@@ -4,13 +4,13 @@ from .Fvgn import FvgnA, FvgnB, FvgnD, FvgnE, FvgnF, FvgnH, FvgnI, FvgnJ, FvgnK 
 from .Mgn import MgnA, MgnB, MgnC  # noqa: F401
 from .StreamFunc import StreamFuncA, StreamFuncB, StreamFuncC, StreamFuncD  # noqa: F401
 from .Flux import FluxA, FluxB, FluxC, FluxD  # noqa: F401
-from .Conservative import (ConservativeA, ConservativeD, ConservativeE, ConservativeF, ConservativeG,  # noqa: F401
-                           ConservativeH, ConservativeI, ConservativeK)
-from .VertPot import VertPotA  # noqa: F401
+from .Conservative import (ConservativeA, ConservativeB, ConservativeD, ConservativeE, ConservativeF, ConservativeG,  # noqa: F401
+                           ConservativeH, ConservativeI, ConservativeJ, ConservativeK)
+from .VertPot import VertPotA, VertPotB, VertPotC, VertPotE, VertPotG  # noqa: F401
 
 MODEL_CLASSES = {"FvgnA": FvgnA, "FvgnF": FvgnF, "MgnA": MgnA, "FluxA": FluxA, "ConservativeA": ConservativeA,
                  "VertPotA": VertPotA, "ConservativeE": ConservativeE, "ConservativeF": ConservativeF, "ConservativeD": ConservativeD,
                  "ConservativeG": ConservativeG, "ConservativeI": ConservativeI, "ConservativeH": ConservativeH,
                  "ConservativeK": ConservativeK, "MgnB": MgnB, "MgnC": MgnC, "StreamFuncA": StreamFuncA,
-                 "FvgnB": FvgnB, "FvgnD": FvgnD, "FvgnE": FvgnE, "FvgnH": FvgnH, "FvgnI": FvgnI, "FvgnJ": FvgnJ,
+                 "ConservativeB": ConservativeB, "ConservativeJ": ConservativeJ, "VertPotB": VertPotB, "VertPotC": VertPotC, "VertPotE": VertPotE, "VertPotG": VertPotG, "FvgnB": FvgnB, "FvgnD": FvgnD, "FvgnE": FvgnE, "FvgnH": FvgnH, "FvgnI": FvgnI, "FvgnJ": FvgnJ,
                  "FvgnK": FvgnK, "FluxB": FluxB, "FluxC": FluxC, "FluxD": FluxD, "StreamFuncB": StreamFuncB, "StreamFuncC": StreamFuncC, "StreamFuncD": StreamFuncD}

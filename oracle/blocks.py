@@ -27,6 +27,8 @@ _FAMILY_OF = {
     "ConservativeG": "cons_g", "ConservativeI": "cons_i", "ConservativeH": "cons_h", "ConservativeJ": "cons_h",
     "FvgnF": "fvgn_f", "ConservativeK": "cons_h",      # K = H with a half-width antisymmetric stream (same data-flow)
     # glue-only variants: MgnA's encoder / processor / decoder (Mgn.py:278-424, StreamFunc.py:109-235)
+    "VertPotB": "vertpot", "VertPotC": "vertpot", "VertPotE": "vertpot", "VertPotG": "vertpot",
+    "ConservativeB": "cons_b", "ConservativeJ": "cons_h",      # J = H's network, other glue (Conservative.py:1320-1683)
     "FvgnB": "fvgn", "FvgnD": "fvgn", "FvgnE": "fvgn", "FvgnH": "fvgn", "FvgnI": "fvgn", "FvgnJ": "fvgn", "FvgnK": "fvgn",
     "FluxB": "fvgn", "FluxC": "fvgn", "FluxD": "fvgn",      # FvgnA's network, other integrators (Flux.py:209-595)
     "MgnB": "mgn", "MgnC": "mgn", "StreamFuncA": "mgn", "StreamFuncB": "mgn", "StreamFuncC": "mgn", "StreamFuncD": "mgn",
@@ -159,7 +161,7 @@ def vertex_block(e, v_edge_index, n_rows):
 def encoder_fwd(family, sd, c_x, f_x, f_x_asym=None):
     """Encoder.forward (Fvgn.py:257-266, Mgn.py:199-208, Conservative.py:191-202).
     Returns (x0, e0, e0_asym-or-None)."""
-    if family == "cons_a":
+    if family in ("cons_a", "cons_b"):
         e0 = mlp_from_state(sd, "encoder.faceS_mlp", f_x)
         ea = mlp_from_state(sd, "encoder.faceA_mlp", f_x_asym, act="tanh")
         x0 = mlp_from_state(sd, "encoder.cell_mlp", c_x)
@@ -185,7 +187,7 @@ def gn_block_fwd(family, sd, i, x, e, topo, e_asym=None, bc_mask=None):
         xr = cell_block_two_hop(sd, f"{p}.cell_block.cell_mlp", x, er, topo["v_edge_index"],
                                 topo["v_face"], topo["n_vertices"])
         return x + xr, e + er, None
-    if family == "cons_a":
+    if family in ("cons_a", "cons_b"):      # ConservativeB = ConservativeA's encoder and blocks (Conservative.py:271-275)
         er = face_block_sum(sd, f"{p}.face_block.face_mlp", x, e, topo["c_edge_index"], e_asym)
         xr = cell_block_signed(sd, f"{p}.cell_block.cell_mlp", x, er, topo["c_edge_index"])
         return x + xr, e + er, None
@@ -224,6 +226,8 @@ def decoder_fwd(family, sd, x, e, vx=None):
     edge+vertex heads (VertPot.py:224-231)."""
     if family == "mgn":
         return mlp_from_state(sd, "decoder.face_mlp", x)
+    if family == "cons_b":      # node head of ConservativeB (Conservative.py:406-414)
+        return mlp_from_state(sd, "decoder.node_mlp", x)
     if family == "vertpot":
         return (mlp_from_state(sd, "decoder.edge_mlp", e), mlp_from_state(sd, "decoder.vertex_mlp", vx))
     return mlp_from_state(sd, "decoder.face_mlp", e)

@@ -58,6 +58,12 @@ MODELS = {
     "StreamFuncB": ("models.StreamFunc", "ellipse", "fvgn"),
     "StreamFuncC": ("models.StreamFunc", "airfoil", "fvgn"),
     "StreamFuncD": ("models.StreamFunc", "cylinder", "fvgn"),
+    "ConservativeB": ("models.Conservative", "airfoil", "conservative"),
+    "ConservativeJ": ("models.Conservative", "ellipse", "conservative_h"),
+    "VertPotB": ("models.VertPot", "cylinder", "fvgn"),
+    "VertPotC": ("models.VertPot", "ellipse", "fvgn"),
+    "VertPotE": ("models.VertPot", "airfoil", "fvgn"),
+    "VertPotG": ("models.VertPot", "cylinder", "fvgn"),
     "FluxB": ("models.Flux", "cylinder", "fvgn"),
     "FluxC": ("models.Flux", "airfoil", "fvgn"),
     "FluxD": ("models.Flux", "ellipse", "fvgn"),
@@ -74,7 +80,7 @@ MGN_LIKE = ("MgnA", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC",
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1, "cell_velocity": 10}
 # models whose fixture also pins model.loss(forward(batch, 'train'), batch) (eval mode, no grad)
-LOSS_MODELS = ("FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
+LOSS_MODELS = ("VertPotC", "VertPotE", "VertPotG", "ConservativeB", "ConservativeJ", "FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
 
 
 class _Dataset:
@@ -103,14 +109,16 @@ def graphs_for(name, kind, flavour, flip=False):
     mesh = make_mesh(160, kind, seed=3)
     g = mesh_graphs(mesh, seed=5, flavour=flavour, flip_edges=flip)
     c, f, v = g
-    if name in MGN_LIKE:
+    if name in MGN_LIKE + ("ConservativeB",):
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in FVGN_LIKE + ("ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
+    elif name in FVGN_LIKE + ("ConservativeA", "VertPotA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK", "ConservativeJ"):
         f.y = f.y[:, :3].contiguous() if name != "VertPotA" else f.y
     if name == "FluxC":
         f.y = f.y[:, :2].contiguous()
-    if name == "FvgnB":
+    if name in ("VertPotC", "VertPotE"):
+        f.y = f.y[:, :2].contiguous()
+    if name in ("FvgnB", "VertPotB"):
         add_mls_fixture(f, seed=12)
     if name == "FvgnH":
         extra = torch.randn(f.x.shape[0], 2, generator=torch.Generator().manual_seed(13))

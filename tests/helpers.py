@@ -8,7 +8,7 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1, "cell_velocity": 10}
-LOSS_MODELS = ("FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
+LOSS_MODELS = ("VertPotC", "VertPotE", "VertPotG", "ConservativeB", "ConservativeJ", "FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
 # (mesh kind, feature flavour) used by tests/golden/make_golden.py per model
 GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "FluxA": ("ellipse", "fvgn"),
                 "ConservativeA": ("cylinder", "conservative"), "VertPotA": ("airfoil", "fvgn"),
@@ -19,6 +19,8 @@ GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "Fl
                 "MgnB": ("ellipse", "fvgn"), "MgnC": ("airfoil", "fvgn"), "StreamFuncA": ("cylinder", "fvgn"),
                 "StreamFuncB": ("ellipse", "fvgn"), "StreamFuncC": ("airfoil", "fvgn"), "StreamFuncD": ("cylinder", "fvgn"),
                 "FluxB": ("cylinder", "fvgn"), "FluxC": ("airfoil", "fvgn"), "FluxD": ("ellipse", "fvgn"),
+                "ConservativeB": ("airfoil", "conservative"), "ConservativeJ": ("ellipse", "conservative_h"),
+                "VertPotB": ("cylinder", "fvgn"), "VertPotC": ("ellipse", "fvgn"), "VertPotE": ("airfoil", "fvgn"), "VertPotG": ("cylinder", "fvgn"),
                 "FvgnB": ("cylinder", "fvgn"), "FvgnD": ("ellipse", "fvgn"), "FvgnE": ("airfoil", "fvgn"), "FvgnH": ("cylinder", "fvgn"), "FvgnI": ("ellipse", "fvgn"), "FvgnJ": ("airfoil", "fvgn"), "FvgnK": ("cylinder", "fvgn")}
 FVGN_LIKE = ("FvgnA", "FvgnB", "FvgnD", "FvgnE", "FvgnH", "FvgnI", "FvgnJ", "FvgnK")
 MGN_LIKE = ("MgnA", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD")
@@ -51,10 +53,10 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     mesh = make_mesh(n_cells, kind, seed=mesh_seed)
     g = mesh_graphs(mesh, seed=feat_seed, flavour=flavour, flip_edges=flip)
     c, f, v = g
-    if name in MGN_LIKE:
+    if name in MGN_LIKE + ("ConservativeB",):
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
         f.y = f.y[:, :2].contiguous()
-    elif name in FVGN_LIKE + ("ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK"):
+    elif name in FVGN_LIKE + ("ConservativeA", "ConservativeE", "ConservativeF", "ConservativeD", "ConservativeG", "ConservativeI", "ConservativeH", "FvgnF", "ConservativeK", "ConservativeJ"):
         f.y = f.y[:, :3].contiguous()
     if name == "FluxC":
         f.y = f.y[:, :2].contiguous()     # (pressure, flux) targets, Flux.py:322
@@ -72,7 +74,9 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
 def fvgn_variant_fixture(name, c, f):
     """Extra inputs of the FvgnA glue variants (same construction in tests/golden/make_golden.py)."""
     from gnn_fluid_dynamics_b200.testing import add_mls_fixture
-    if name == "FvgnB":       # face moving-least-squares stencil for the diffusion term (Fvgn.py:446)
+    if name in ("VertPotC", "VertPotE"):      # FluxC targets: (pressure, flux)
+        f.y = f.y[:, :2].contiguous()
+    if name in ("FvgnB", "VertPotB"):       # face moving-least-squares stencil for the diffusion term (Fvgn.py:446)
         add_mls_fixture(f, seed=12)
     if name == "FvgnH":       # 7 + 5 face feature columns (Fvgn.py:1057)
         extra = torch.randn(f.x.shape[0], 2, generator=torch.Generator().manual_seed(13))

@@ -154,8 +154,8 @@ def _run_processor(name, model, graphs_dev):
     c, f, v = graphs_dev
     grab = {}
     hook = lambda i, x, e: grab.__setitem__(i, (x, e)) if i in (0, 14) else None
-    if name in ("ConservativeA", "ConservativeD", "ConservativeH", "ConservativeK"):
-        topo = get_topology(graphs_dev, need_cell_csr=True, two_hop=name in ("ConservativeH", "ConservativeK")).validate()
+    if name in ("ConservativeA", "ConservativeB", "ConservativeD", "ConservativeH", "ConservativeJ", "ConservativeK"):
+        topo = get_topology(graphs_dev, need_cell_csr=True, two_hop=name in ("ConservativeH", "ConservativeJ", "ConservativeK")).validate()
         x, e, dec = model.encode_process_decode(c.x, f.x_symm, f.x_asym, topo, hook=hook)
         return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
     topo = get_topology(graphs_dev, need_cell_csr=name.startswith("Conservative")).validate()
@@ -164,7 +164,7 @@ def _run_processor(name, model, graphs_dev):
         e_keep = keep.float().unsqueeze(1).expand(-1, 128).contiguous()
         x, e, dec = model.encode_process_decode(c.x, f.x, topo, hook=hook, e_keep=e_keep)
         return {"x": x, "e": e, "dec": dec, "b1": grab[0]}
-    if name == "VertPotA":
+    if name.startswith("VertPot"):
         x, e, vx, dec, dec_v = model.encode_process_decode(c.x, f.x, topo, hook=hook)
         return {"x": x, "e": e, "vx": vx, "dec": dec, "dec_vertex": dec_v, "b1": grab[0]}
     x, e, dec = model.encode_process_decode(c.x, f.x, topo, hook=hook)
@@ -191,9 +191,9 @@ def test_processor_matches_reference_golden(name):
         assert rel_l2(out["x"], torch.from_numpy(gold["x15"])) < t, (prec, rel_l2(out["x"], torch.from_numpy(gold["x15"])))
         assert rel_l2(out["e"], torch.from_numpy(gold["e15"])) < t, (prec, rel_l2(out["e"], torch.from_numpy(gold["e15"])))
         assert rel_l2(out["dec"], torch.from_numpy(gold["dec"])) < 2 * t
-        if name in ("ConservativeD", "ConservativeH", "ConservativeK"):      # second (antisymmetric) edge stream
+        if name in ("ConservativeD", "ConservativeH", "ConservativeJ", "ConservativeK"):      # second (antisymmetric) edge stream
             assert rel_l2(model._last_e_asym, torch.from_numpy(gold["ea15"])) < t
-        if name == "VertPotA":
+        if name.startswith("VertPot"):
             assert rel_l2(out["vx"], torch.from_numpy(gold["vx15"])) < t
             assert rel_l2(out["dec_vertex"], torch.from_numpy(gold["dec_vertex"])) < 2 * t
 
