@@ -351,6 +351,104 @@ class FvgnB(FvgnA):
             return torch.mean(dt) / c_graph.volume * (-phi_a - phi_p / self.rho + self.nu * phi_d)
 
 
+class FvgnC(FvgnA):
+    """Temporal bundling: the decoder predicts ``bundle_size`` future steps at once, [E, k, 5] (Fvgn.py:463-786; its
+    Encoder / GN_Block restate FvgnA's).  The normalisation tables are FvgnA's applied on the last dimension."""
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        window = config.model.bundle_size
+        self.output_sizes = [o * window for o in self.output_sizes]
+        self.decoder = self.Decoder(config, self.hidden_size, self.output_sizes)
+        self.integrator = self.Integrator(config, rho=1)
+
+    def training_plan(self):
+        raise NotImplementedError("FvgnC trains through the per-op autograd wrappers (autograd_ops.py)")
+
+    def encode_process_decode(self, c_x, f_x, topo, hook=None):
+        prec = self.prec
+        e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
+        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook)
+        n_out = self.output_sizes[1]
+        if n_out <= 16:                       # narrow-head path of the fused kernel
+            out = P.mlp_rows(self.decoder.face_mlp, e, prec)
+        else:                                 # wider bundles: last Linear zero-padded to the 128-wide path (no grad)
+            if self.wants_grad():
+                raise NotImplementedError("FvgnC with 5 * bundle_size > 16 runs forward / rollout only on the B200 path")
+            from .Conservative import _padded_head
+            from .._lib import ACT_SILU
+            raw, _ = P.ops.mlp_forward([P.Seg(e)], _padded_head(self.decoder.face_mlp, ACT_SILU, n_out), e.shape[0], prec)
+            out = raw[:, :n_out].contiguous()
+        return x, e, out.view(out.shape[0], n_out // 5, 5)      # Fvgn.py:780-786
+
+    def forward(self, graphs, mode="rollout"):   # Fvgn.py:572-596
+        graphs = self.normalizer.input(graphs)
+        c_graph, f_graph, v_graph = graphs
+        c_graph.edge_attr = f_graph.x
+        _, _, edge_attr_out = self.encode_process_decode(c_graph.x, f_graph.x, get_topology(graphs))
+        self.dt = c_graph.dt
+        acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
+        output = [acc_pred, edge_attr_out, None]
+        if mode == "rollout":
+            output = self.normalizer.output(output, inverse=True)
+        return {"cell_velocity_change": output[0][:, :, 0:2], "face_velocity": output[1][:, :, 0:2],
+                "face_pressure": output[1][:, :, 2:3]}
+
+    def update_features(self, output, input_graphs):   # Fvgn.py:546-560: boundary values of the LAST bundled target
+        c_graph, f_graph, v_graph = input_graphs
+        c_graph.x = output["cell_velocity"].detach()
+        u = c_graph.x[:, :2]
+        dv = u[c_graph.edge_index[0]] - u[c_graph.edge_index[1]]
+        mask = ((f_graph.type == NODE_INFLOW) | (f_graph.type == NODE_WALL)).reshape(-1, 1)
+        f_graph.x[:, 0:2] = torch.where(mask, f_graph.y[:, -1, 0:2], dv)
+        return [c_graph, f_graph, v_graph]
+
+    def loss(self, output, graphs):   # Fvgn.py:598-653: per-step losses averaged over the bundle
+        c_graph, f_graph, v_graph = graphs
+        lf, w = self.loss_func, self.config.training.loss_weights
+        ff, unv = f_graph.face, c_graph.normal
+        parts = {"total": [], "continuity": [], "cvc": [], "fv": [], "fp": []}
+        for t in range(output["face_velocity"].shape[1]):
+            area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, self.dt,
+                                       self.integrator.face_area_norm)
+            fv = output["face_velocity"][:, t, :]
+            div = sum(flux_dot(fv[ff[j]], unv[:, j, :]) * area[ff[j]] for j in range(3))
+            continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
+            cvc = lf(output["cell_velocity_change"][:, t, :], c_graph.y[:, t, :], None, c_graph.batch)
+            fvl = lf(fv, f_graph.y[:, t, :2], ~f_graph.boundary_mask, f_graph.batch)
+            fpl = lf(output["face_pressure"][:, t, :], f_graph.y[:, t, 2:3], None, f_graph.batch)
+            parts["total"].append(w["continuity"] * continuity + w["cell_velocity_change"] * cvc
+                                  + w["face_velocity"] * fvl + w["face_pressure"] * fpl)
+            for k, v in (("continuity", continuity), ("cvc", cvc), ("fv", fvl), ("fp", fpl)):
+                parts[k].append(v)
+        mean = lambda k: torch.mean(torch.stack(parts[k]))
+        return {"total_log_loss": torch.mean(torch.log(mean("total"))), "continuity_loss": mean("continuity"),
+                "cell_velocity_change_loss": mean("cvc"), "face_velocity_loss": mean("fv"),
+                "face_pressure_loss": mean("fp")}
+
+    class Integrator(nn.Module):   # Fvgn.py:655-703: FvgnA's update per bundled step, scaled by (k + 1)
+        def __init__(self, config, rho):
+            super().__init__()
+            self.rho = rho
+            self.face_area_norm = nn.BatchNorm1d(1)
+            self.face_area = None
+
+        def forward(self, edge_output, c_graph, f_graph, dt):
+            unv, cf, k = c_graph.normal, f_graph.face, edge_output.shape[1]
+            area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, dt, self.face_area_norm)
+            self.face_area = area
+            results = []
+            for t in range(k):
+                uv, p_face, flux_d = edge_output[:, t, :2], edge_output[:, t, 2:3], edge_output[:, t, 3:]
+                uu_vu = torch.cat([uv[:, 0:1] * uv, uv[:, 1:2] * uv], dim=-1)
+                phi_a = sum(flux_dot(uu_vu[cf[j]], unv[:, j, :]) * area[cf[j]] for j in range(3))
+                phi_d = flux_d[cf[0], :] + flux_d[cf[1], :] + flux_d[cf[2], :]
+                phi_p = sum(p_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+                results.append((1.0 * (-phi_a - phi_p / self.rho) + phi_d) * (k + 1))
+            return torch.stack(results, dim=1)
+
+
 class FvgnD(FvgnA):
     """Push-forward training: same network and forward as FvgnA; the dataset side changes the target and the
     statistics (Fvgn.py:789-836)."""

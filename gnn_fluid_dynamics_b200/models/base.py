@@ -85,17 +85,17 @@ class Normalizer(nn.Module):
         """In place on the passed graphs, like the reference (normalisation.py:255-264)."""
         for gi, attr, cols, key in self.inputs:
             t = getattr(graphs[gi], attr, None)
-            if t is None or t.dim() < 2 or t.shape[1] < cols.stop:
+            if t is None or t.dim() < 2 or t.shape[-1] < cols.stop:
                 continue
-            t[:, cols] = self._apply_one(t[:, cols], key, inverse)
+            t[..., cols] = self._apply_one(t[..., cols], key, inverse)      # last dim: [R, C] or bundled [R, k, C]
         return graphs
 
     def output(self, outputs, inverse=False):
         for oi, cols, key in self.outputs:
             t = outputs[oi]
-            if t is None or t.shape[1] < cols.stop:
+            if t is None or t.shape[-1] < cols.stop:
                 continue
-            t[:, cols] = self._apply_one(t[:, cols], key, inverse)
+            t[..., cols] = self._apply_one(t[..., cols], key, inverse)
         return outputs
 
 

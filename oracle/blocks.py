@@ -29,7 +29,7 @@ _FAMILY_OF = {
     # glue-only variants: MgnA's encoder / processor / decoder (Mgn.py:278-424, StreamFunc.py:109-235)
     "VertPotB": "vertpot", "VertPotC": "vertpot", "VertPotE": "vertpot", "VertPotG": "vertpot",
     "ConservativeB": "cons_b", "ConservativeJ": "cons_h",      # J = H's network, other glue (Conservative.py:1320-1683)
-    "FvgnB": "fvgn", "FvgnD": "fvgn", "FvgnE": "fvgn", "FvgnH": "fvgn", "FvgnI": "fvgn", "FvgnJ": "fvgn", "FvgnK": "fvgn",
+    "FvgnB": "fvgn", "FvgnC": "fvgn", "FvgnD": "fvgn", "FvgnE": "fvgn", "FvgnH": "fvgn", "FvgnI": "fvgn", "FvgnJ": "fvgn", "FvgnK": "fvgn",
     "FluxB": "fvgn", "FluxC": "fvgn", "FluxD": "fvgn",      # FvgnA's network, other integrators (Flux.py:209-595)
     "MgnB": "mgn", "MgnC": "mgn", "StreamFuncA": "mgn", "StreamFuncB": "mgn", "StreamFuncC": "mgn", "StreamFuncD": "mgn",
 }

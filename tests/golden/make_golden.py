@@ -64,6 +64,7 @@ MODELS = {
     "VertPotC": ("models.VertPot", "ellipse", "fvgn"),
     "VertPotE": ("models.VertPot", "airfoil", "fvgn"),
     "VertPotG": ("models.VertPot", "cylinder", "fvgn"),
+    "FvgnC": ("models.Fvgn", "ellipse", "fvgn"),
     "FluxB": ("models.Flux", "cylinder", "fvgn"),
     "FluxC": ("models.Flux", "airfoil", "fvgn"),
     "FluxD": ("models.Flux", "ellipse", "fvgn"),
@@ -80,7 +81,7 @@ MGN_LIKE = ("MgnA", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC",
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1, "cell_velocity": 10}
 # models whose fixture also pins model.loss(forward(batch, 'train'), batch) (eval mode, no grad)
-LOSS_MODELS = ("VertPotC", "VertPotE", "VertPotG", "ConservativeB", "ConservativeJ", "FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
+LOSS_MODELS = ("FvgnC", "VertPotC", "VertPotE", "VertPotG", "ConservativeB", "ConservativeJ", "FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
 
 
 class _Dataset:
@@ -91,7 +92,7 @@ class _Dataset:
 
 def ref_config():
     return Config.from_dict({
-        "model": {"hidden_width": 128, "mp_num": 15, "cell_grad_weights_order": 1,
+        "model": {"hidden_width": 128, "mp_num": 15, "bundle_size": 3, "cell_grad_weights_order": 1,
                   "face_grad_weights_order": 1},
         "training": {"dropout_rate": 0.0, "loss_weights": LOSS_W},
     })
@@ -123,6 +124,9 @@ def graphs_for(name, kind, flavour, flip=False):
     if name == "FvgnH":
         extra = torch.randn(f.x.shape[0], 2, generator=torch.Generator().manual_seed(13))
         f.x = torch.cat([f.x[:, :5], extra, f.x[:, 5:]], dim=1)
+    if name == "FvgnC":
+        c.y = torch.randn(c.x.shape[0], 3, 2, generator=torch.Generator().manual_seed(21))
+        f.y = torch.randn(f.x.shape[0], 3, 3, generator=torch.Generator().manual_seed(22))
     if name == "FvgnK":
         c.Re = torch.tensor([150.0])
         f.type = f.type.reshape(-1)

@@ -8,7 +8,7 @@ import torch
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 LOSS_W = {"continuity": 0, "cell_velocity_change": 10, "cell_pressure": 1, "face_velocity": 1,
           "face_flux": 1, "face_pressure": 1, "cell_velocity": 10}
-LOSS_MODELS = ("VertPotC", "VertPotE", "VertPotG", "ConservativeB", "ConservativeJ", "FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
+LOSS_MODELS = ("FvgnC", "VertPotC", "VertPotE", "VertPotG", "ConservativeB", "ConservativeJ", "FvgnB", "FvgnE", "FvgnH", "FvgnJ", "FvgnK", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD", "FluxB", "FluxC", "FluxD")
 # (mesh kind, feature flavour) used by tests/golden/make_golden.py per model
 GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "FluxA": ("ellipse", "fvgn"),
                 "ConservativeA": ("cylinder", "conservative"), "VertPotA": ("airfoil", "fvgn"),
@@ -21,14 +21,14 @@ GOLDEN_SETUP = {"MgnA": ("cylinder", "fvgn"), "FvgnA": ("cylinder", "fvgn"), "Fl
                 "FluxB": ("cylinder", "fvgn"), "FluxC": ("airfoil", "fvgn"), "FluxD": ("ellipse", "fvgn"),
                 "ConservativeB": ("airfoil", "conservative"), "ConservativeJ": ("ellipse", "conservative_h"),
                 "VertPotB": ("cylinder", "fvgn"), "VertPotC": ("ellipse", "fvgn"), "VertPotE": ("airfoil", "fvgn"), "VertPotG": ("cylinder", "fvgn"),
-                "FvgnB": ("cylinder", "fvgn"), "FvgnD": ("ellipse", "fvgn"), "FvgnE": ("airfoil", "fvgn"), "FvgnH": ("cylinder", "fvgn"), "FvgnI": ("ellipse", "fvgn"), "FvgnJ": ("airfoil", "fvgn"), "FvgnK": ("cylinder", "fvgn")}
+                "FvgnC": ("ellipse", "fvgn"), "FvgnB": ("cylinder", "fvgn"), "FvgnD": ("ellipse", "fvgn"), "FvgnE": ("airfoil", "fvgn"), "FvgnH": ("cylinder", "fvgn"), "FvgnI": ("ellipse", "fvgn"), "FvgnJ": ("airfoil", "fvgn"), "FvgnK": ("cylinder", "fvgn")}
 FVGN_LIKE = ("FvgnA", "FvgnB", "FvgnD", "FvgnE", "FvgnH", "FvgnI", "FvgnJ", "FvgnK")
 MGN_LIKE = ("MgnA", "MgnB", "MgnC", "StreamFuncA", "StreamFuncB", "StreamFuncC", "StreamFuncD")
 ALL_MODELS = list(GOLDEN_SETUP)
 
 
 def make_config(mp_num=15, precision=None):
-    return NS(model=NS(hidden_width=128, mp_num=mp_num, precision=precision),
+    return NS(model=NS(hidden_width=128, mp_num=mp_num, precision=precision, bundle_size=3),
               training=NS(dropout_rate=0.0, loss_weights=dict(LOSS_W)))
 
 
@@ -81,6 +81,9 @@ def fvgn_variant_fixture(name, c, f):
     if name == "FvgnH":       # 7 + 5 face feature columns (Fvgn.py:1057)
         extra = torch.randn(f.x.shape[0], 2, generator=torch.Generator().manual_seed(13))
         f.x = torch.cat([f.x[:, :5], extra, f.x[:, 5:]], dim=1)
+    if name == "FvgnC":       # temporal bundle of 3 target steps (Fvgn.py:484, 506)
+        c.y = torch.randn(c.x.shape[0], 3, 2, generator=torch.Generator().manual_seed(21))
+        f.y = torch.randn(f.x.shape[0], 3, 3, generator=torch.Generator().manual_seed(22))
     if name == "FvgnK":       # per-mesh Reynolds number; the reference needs a 1-D type tensor here (Fvgn.py:1291-1296)
         c.Re = torch.tensor([150.0])
         f.type = f.type.reshape(-1)

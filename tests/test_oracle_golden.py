@@ -65,8 +65,8 @@ def test_oracle_processor_matches_reference(name):
         assert rel_l2(out["vx"], torch.from_numpy(gold["vx15"])) < TOL
         assert rel_l2(out["dec"][0], torch.from_numpy(gold["dec"])) < TOL
         assert rel_l2(out["dec"][1], torch.from_numpy(gold["dec_vertex"])) < TOL
-    else:
-        assert rel_l2(out["dec"], torch.from_numpy(gold["dec"])) < TOL
+    else:      # (FvgnC's decoder output is viewed [E, k, 5], Fvgn.py:780-786)
+        assert rel_l2(out["dec"].reshape(gold["dec"].shape), torch.from_numpy(gold["dec"])) < TOL
 
 
 @pytest.mark.parametrize("name", ["FvgnA", "MgnA"])
