@@ -5,12 +5,14 @@ Run here only:  python tests/golden/make_golden.py
 
 What is pinned
   connectivity_{k}.npz : reference utils/geometry.compute_connectivity on three synthetic meshes
-  fwd_{Model}.npz      : reference model forward (MgnA, FvgnA, FluxA, ConservativeA/E/F, VertPotA),
+  fwd_{Model}.npz      : reference model forward (every class in MODELS below: 36 of the reference's 38; VertPotD / F
+                         cannot run in the reference),
                          hidden 128, 15 blocks, deterministic parameters
                          (gnn_fluid_dynamics_b200.testing.fill_state_dict_deterministic, seed 1),
                          mesh make_mesh(160, kind, seed=3), features mesh_graphs(seed=5):
                          encoder outputs, processor outputs after block 1 and block 15, decoder
-                         outputs, the forward() dict in 'train' and 'rollout' modes
+                         outputs, the forward() dict in 'train' and 'rollout' modes; for LOSS_MODELS also
+                         model.loss(forward(batch, 'train'), batch)
   train_FvgnA.npz      : reference FvgnA train-mode forward + model.loss + backward: loss values and
                          gradients (norm of every parameter's grad + a few full tensors)
 """
