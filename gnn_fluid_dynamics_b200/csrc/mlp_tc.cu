@@ -43,18 +43,23 @@ constexpr int TC_WLD_WARP = TC_MMA_WARP + 2;
 constexpr int TC_WLD23_WARP = TC_MMA_WARP + 3;
 constexpr int TC_THREADS = (TC_MMA_WARP + 4) * 32;   // 896
 constexpr int TC_A_STAGES = 2;        // A ring: {A_hi, A_lo} images per stage
-constexpr int TC_W1_SLOTS = 2;        // layer-1 W ring: one 16 KB image (hi or lo part of a k-block) per slot
-constexpr int TC_W23_SLOTS = 2;       // layer-2/3 W ring (two slots each measured FASTER than three: the 32 KB not
-                                      // carved out of the L1 serve the producers' gathers - 203 -> 194 us on the edge block)
+// W rings (layer 1 | layers 2/3): one 16 KB image (hi or lo part of a k-block) per slot, TcParams::w_slots slots each.
+// Large launches run TWO slots per ring: measured FASTER than three, because the 32 KB not carved out of the L1 serve
+// the producers' gathers (203 -> 194 us on the edge block).  Launches of a tile or two per CTA are a pure latency
+// chain and get THREE (the 2k-cell rollout step: 1.00 -> 0.9x ms).  The rings sit at the END of shared memory so the
+// dynamic allocation (which sets the L1 carve-out) only covers the slots in use.
+constexpr int TC_W_SLOTS_MAX = 3;
 constexpr int TC_X_SLOTS = 3;         // X regions in TMEM
 constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 64 KB
-constexpr int TC_W_BYTES = (TC_W1_SLOTS + TC_W23_SLOTS) * TC_IMG;   // 64 KB
 constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * 16 * 4;   // 32 KB: one XOR-swizzled 32 x 16 fp32 staging block per epilogue warp
 constexpr int TC_IDX_SLOTS = 4;
 constexpr int TC_IDX_SLOT = 9 * TC_BM;               // ints: [3 seg][3 idx][128 rows]
 constexpr int TC_NBAR = 32;
-constexpr int TC_SMEM = TC_A_BYTES + TC_W_BYTES + TC_STG_BYTES + TC_IDX_SLOTS * TC_IDX_SLOT * 4 +
-                        5 * TC_H * 4 + 4 * TC_BM * 8 + TC_NBAR * 8 + 64 + 1024;
+constexpr int TC_SMEM_FIXED = TC_A_BYTES + TC_STG_BYTES + TC_IDX_SLOTS * TC_IDX_SLOT * 4 +
+                              5 * TC_H * 4 + 4 * TC_BM * 8 + TC_NBAR * 8 + 64;
+constexpr int tc_smem_bytes(int w_slots) {      // + alignment slack before s_a and before the rings
+  return TC_SMEM_FIXED + 2 * w_slots * TC_IMG + 2 * 1024;
+}
 constexpr int TC_TMEM_COLS = 512;     // X0 | X1 | X2 | Y, 128 columns each
 constexpr uint32_t TC_Y_COL = TC_X_SLOTS * 128;
 constexpr int TC_MAX_KB = 8;
@@ -76,6 +81,7 @@ struct TcParams {
   int ksteps1;   // K=16 steps in the LAST k-block of layer 1 (1..4)
   int n3;        // UMMA N of layer 3: 128, or 16 for a narrow head
   int nl;        // layers: 3 (MLP) or 1 (single Linear)
+  int w_slots;   // slots per weight ring: 2 (large launches) or 3 (latency-bound small ones)
   uint32_t w_block_bytes;   // bytes of one packed 128-row k-block (all parts)
   uint32_t w3_block_bytes;  // bytes of one packed layer-3 k-block
   int64_t direct_tile_bytes;   // bytes of one tile's rows of a contiguous DIRECT segment 0 (0: no L2 prefetch)
@@ -229,8 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   const gnnfd_mlp_args &a = p.a;
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *s_a = smem;                                     // A ring
-  uint8_t *s_w = s_a + TC_A_BYTES;                         // W ring
-  float *s_stg = (float *)(s_w + TC_W_BYTES);              // output staging, one 32x36 block per epilogue warp
+  float *s_stg = (float *)(s_a + TC_A_BYTES);              // output staging, one swizzled 32x16 block per epilogue warp
   int32_t *s_idx = (int32_t *)((uint8_t *)s_stg + TC_STG_BYTES);   // [4 tiles][3 seg][3][128]
   float *s_vec = (float *)(s_idx + TC_IDX_SLOTS * TC_IDX_SLOT);    // b1, b2, b3, ln_w, ln_b
   float2 *s_stat = (float2 *)(s_vec + 5 * TC_H);                   // LayerNorm partials [2 slots][2 halves][128 rows]
@@ -238,15 +243,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   uint64_t *a_full = s_bar, *a_empty = s_bar + 2, *w_full = s_bar + 4, *w_empty = s_bar + 7;
   uint64_t *w23_full = s_bar + 10, *w23_empty = s_bar + 13;
   uint64_t *acc_full = s_bar + 16, *acc_free = s_bar + 19, *hid_ready = s_bar + 22;   // hid_ready[x_slot*2 + half]
-  uint8_t *s_w23 = s_w + TC_W1_SLOTS * TC_IMG;
   uint32_t *s_tmem = (uint32_t *)(s_bar + TC_NBAR);
+  const int w_slots = p.w_slots;
+  uint8_t *s_w = (uint8_t *)(((uintptr_t)(s_tmem + 16) + 1023) & ~(uintptr_t)1023);   // layer-1 W ring
+  uint8_t *s_w23 = s_w + w_slots * TC_IMG;                                            // layer-2/3 W ring
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < TC_W1_SLOTS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < TC_W23_SLOTS; ++i) { mbar_init(&w23_full[i], 1); mbar_init(&w23_empty[i], 1); }
+    for (int i = 0; i < TC_W_SLOTS_MAX; ++i) {
+      mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
+      mbar_init(&w23_full[i], 1); mbar_init(&w23_empty[i], 1);
+    }
     for (int i = 0; i < TC_X_SLOTS; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_free[i], TC_EPI_GROUP); }
     for (int i = 0; i < 2 * TC_X_SLOTS; ++i) mbar_init(&hid_ready[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -363,7 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       const uint8_t *w3p = w2p + (size_t)2 * p.w_block_bytes;
       const uint32_t w3_part = p.w3_block_bytes / NW;
       const bool first = warp == TC_WLD_WARP;
-      const int n_slots = first ? TC_W1_SLOTS : TC_W23_SLOTS;
+      const int n_slots = w_slots;
       uint64_t *full = first ? w_full : w23_full, *empty = first ? w_empty : w23_empty;
       uint8_t *ring = first ? s_w : s_w23;
       int slot = 0;
@@ -403,7 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         slot = ws;
         PROF_WAIT(2, mbar_wait(&w_full[slot], w_round & 1));
         tc_fence_after();
-        if (++ws == TC_W1_SLOTS) { ws = 0; ++w_round; }
+        if (++ws == w_slots) { ws = 0; ++w_round; }
         return make_desc(smem_u32(s_w + slot * TC_IMG));
       };
       for (int j = 0; j < T; ++j) {
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         slot = ws;
         PROF_WAIT(1, mbar_wait(&w23_full[slot], w_round & 1));
         tc_fence_after();
-        if (++ws == TC_W23_SLOTS) { ws = 0; ++w_round; }
+        if (++ws == w_slots) { ws = 0; ++w_round; }
         return make_desc(smem_u32(s_w23 + slot * TC_IMG));
       };
       // A = the in-place converted accumulator region: per 16 fp32 columns, 8 columns of hi pairs | 8 of lo pairs.
@@ -854,14 +863,16 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   if (a->rows == 0) return GNNFD_OK;
   const int64_t n_tiles = (a->rows + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  p.w_slots = n_tiles <= 2 * (int64_t)num_sms() ? TC_W_SLOTS_MAX : 2;
 #define LAUNCH1(FP, NA_, NW_, BW)                                                                         \
   do {                                                                                                    \
     static bool attr = false;                                                                             \
     if (!attr) {                                                                                          \
-      GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM)); \
+      GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      tc_smem_bytes(TC_W_SLOTS_MAX)));                                    \
       attr = true;                                                                                        \
     }                                                                                                     \
-    mlp_tc_kernel<FP, NA_, NW_, BW><<<grid, TC_THREADS, TC_SMEM, stream>>>(p);                            \
+    mlp_tc_kernel<FP, NA_, NW_, BW><<<grid, TC_THREADS, tc_smem_bytes(p.w_slots), stream>>>(p);           \
   } while (0)
 #define LAUNCH(FP, NA_, NW_)                                                                              \
   do {                                                                                                    \
