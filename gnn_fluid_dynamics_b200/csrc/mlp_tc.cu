@@ -32,8 +32,8 @@ namespace gnnfd {
 // TMEM: three X regions (layer-1 accumulator / hidden-1 operand / layer-3 accumulator of tiles j % 3) and ONE Y region
 // (layer-2 accumulator / hidden-2 operand), which the in-order tensor pipe hands from tile to tile.
 // Registers: 896 threads launch at 72 per thread; the epilogue works in 16-column groups to live within that;
-// warpgroup 24-27 shrinks to 40 (setmaxnreg.dec) and the two producer warpgroups grow to 88 (setmaxnreg.inc; only
-// registers released inside the CTA can be claimed).
+// warpgroup 24-27 shrinks to 40 (setmaxnreg.dec) and what it releases goes to the producers (forward: 88) or to the
+// epilogue warps (backward chain: 80) (setmaxnreg.inc; only registers released inside the CTA can be claimed).
 constexpr int TC_EPI_WARPS = 16, TC_PROD_WARPS = 8;
 constexpr int TC_EPI_GROUP = 8;       // epilogue warps per tile
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32, TC_PROD_THREADS = TC_PROD_WARPS * 32;
@@ -281,8 +281,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // =============================================================================== producers
     // forward: gathers keep two k-blocks of rows in flight per thread and need the registers; backward chain: the
     // hidden epilogues (saved pre-activation prefetch) need them more than the contiguous dA loads do
-    if (BWD) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // forward: the gather path wants the registers (72 -> 88); backward chain: the hidden epilogues (saved
+    // pre-activation prefetch) want them more than the contiguous dA loads do, so the producers stay at 72 there
+    // (measured: edge forward 163 us with 72/88 vs 185 us with 80/72; dgrad chain 242 us with 80/72 vs 253 us)
+    if (!BWD) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int pt = tid - TC_EPI_THREADS;   // 0..255
     const int f4 = pt & 15;                // float4 column inside the 64-wide k-block
     const int rbase = pt >> 4;             // rows rbase + 16 j
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       }
       cp_async_commit();
     };
-    // blocks are issued two ahead of the one being converted; (ij, ikb) tracks the next block to issue
+    // the loads of block b + 1 are issued right after block b is converted; (ij, ikb) tracks the next block to issue
     int ij = 0, ikb = 0;
     auto issue = [&](float4(&v)[8]) {
       if (ij < T) {
@@ -346,16 +348,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       PROF_WAIT(3, issue(v));
     };
 
-    float4 v0[8], v1[8];
+    // ONE block of loads in flight per thread, one copy of the load / convert / store code: the version that kept two
+    // blocks in flight (two unrolled copies, 64 payload registers) measured 13 % SLOWER on the edge block (194 vs 170 us)
+    // - the roles' hot loops then exceed the 32 KB L1.5 instruction cache and instruction fetch, not gather latency,
+    // paces the producers (profiles/r01_mlp_tc_role_stalls.txt)
+    float4 v0[8];
     stage_idx(0); stage_idx(1); stage_idx(2);
     cp_async_wait_all();
     named_bar_sync(1, TC_PROD_THREADS);
     issue(v0);
-    issue(v1);
-    for (int b = 0; b < NB; b += 2) {
-      step(v0);
-      if (b + 1 < NB) step(v1);
-    }
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) step(v0);
     cp_async_wait_all();
 #ifdef GNNFD_TC_PROF
     if (blockIdx.x == 0 && pt == 0) {
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // warp = (tile group grp, column half eh, lane quarter q4): thread = row, 64 of the 128 columns of every tile of its
     // group; half eh of a hidden layer's output is exactly k-block eh of the next layer's operand.  All TMEM traffic is
     // in 16-column groups: 16 fp32 accumulator columns are replaced in place by 8 columns of hi pairs + 8 of lo pairs.
-    if (!BWD) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (BWD) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     const int grp = warp >> 3, q4 = warp & 3, eh = (warp >> 2) & 1;
     const int erow = q4 * 32 + lane;                       // row of the tile owned by this thread
     const uint32_t stg = smem_u32(s_stg + warp * (32 * 16));   // this warp's 32 x 16 staging block (XOR-swizzled)
