@@ -352,6 +352,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // blocks in flight (two unrolled copies, 64 payload registers) measured 13 % SLOWER on the edge block (194 vs 170 us)
     // - the roles' hot loops then exceed the 32 KB L1.5 instruction cache and instruction fetch, not gather latency,
     // paces the producers (profiles/r01_mlp_tc_role_stalls.txt)
+    // (Also tried: two HALF blocks of 4 rows per thread, the loads of half h of block b + 1 issued right after half h of
+    //  block b is converted, same code size and registers as this - 204 us vs 163 us on the edge block, reverted.)
     float4 v0[8];
     stage_idx(0); stage_idx(1); stage_idx(2);
     cp_async_wait_all();
