@@ -213,6 +213,20 @@ def gen_forward(name):
     print(name, {k: tuple(v.shape) for k, v in out.items()})
 
 
+def gen_update(name):
+    """Reference update_features (the rollout feature update, e.g. Fvgn.py:133-148) on the fixture graphs.  The
+    reference indexes a [E, 2] tensor with the face-type mask, which needs a 1-D type tensor."""
+    model, kind, flavour = build_ref(name)
+    mesh, graphs = graphs_for(name, kind, flavour)
+    g = [x.clone() for x in graphs]
+    g[1].type = g[1].type.reshape(-1)
+    n = g[0].x.shape[0]
+    out = {"cell_velocity": torch.randn(n, 2, generator=torch.Generator().manual_seed(31))}
+    c, f, v = model.update_features(out, g)
+    fx = f.x_asym if hasattr(f, "x_asym") else f.x
+    np.savez_compressed(os.path.join(HERE, f"upd_{name}.npz"), cx=c.x.numpy(), fx2=fx[:, 0:2].numpy())
+
+
 def gen_keys(name):
     import json
     model, _, _ = build_ref(name)
@@ -251,6 +265,10 @@ def gen_train():
 
 
 if __name__ == "__main__":
+    if sys.argv[1:2] == ["--update-only"]:
+        for n in MODELS:
+            gen_update(n)
+        sys.exit(0)
     only = sys.argv[1:]
     if not only:
         gen_connectivity()
@@ -258,5 +276,6 @@ if __name__ == "__main__":
         if not only or n in only:
             gen_forward(n)
             gen_keys(n)
+            gen_update(n)
     if not only:
         gen_train()

@@ -33,6 +33,21 @@ def test_state_dict_keys_match_reference(name):
     assert mine == ref
 
 
+@pytest.mark.parametrize("name", MODELS)
+def test_update_features_matches_reference(name):
+    """The rollout feature update (plain tensor glue, runs on CPU) against the reference's own update_features."""
+    gold = load_golden(f"upd_{name}.npz")
+    model = build_model(name)
+    _, graphs = golden_graphs(name)
+    g = [x.clone() for x in graphs]
+    g[1].type = g[1].type.reshape(-1)
+    out = {"cell_velocity": torch.randn(g[0].x.shape[0], 2, generator=torch.Generator().manual_seed(31))}
+    c, f, v = model.update_features(out, g)
+    fx = f.x_asym if hasattr(f, "x_asym") else f.x
+    assert torch.equal(c.x, torch.from_numpy(gold["cx"]))
+    assert torch.equal(fx[:, 0:2], torch.from_numpy(gold["fx2"]))
+
+
 def _processor_inputs(name, graphs, model):
     if name != "StreamFuncC":      # StreamFuncC.forward does not normalise (StreamFunc.py:173-176)
         graphs = model.normalizer.input(graphs)
