@@ -160,6 +160,13 @@ class Model(nn.Module, ABC):
         ...
 
     @classmethod
+    def transform_features(cls, dataset, graphs, mesh_id=None):
+        """Raw time series -> network inputs / targets, as the reference's dataset calls it on the model class
+        (``src/train.py:350``); see ``models/features.py``."""
+        from .features import transform_for
+        return transform_for(cls, dataset, graphs)
+
+    @classmethod
     def get_normalisation_map(cls):
         """The reference's (registry, inputs, outputs) dict-of-lambdas form of the same tables
         (consumed by its statistics accumulator, ``src/datasets/DataSet.py:318``)."""

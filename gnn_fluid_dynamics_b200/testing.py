@@ -57,6 +57,27 @@ def add_mls_fixture(c_graph, k: int = 8, seed: int = 11):
     return c_graph
 
 
+def raw_graphs(mesh, seed: int = 17, steps: int = 4):
+    """Raw (pre-``transform_features``) graph triplet on a synthetic mesh: velocity / pressure / flux time series on
+    cells and faces plus the static geometry, in the shapes the reference's dataset hands to the model class
+    (``src/datasets/DataSet.py:210-274``: series are [rows, time, channels], face type is [E, 1])."""
+    from .graph import Data
+    g = torch.Generator().manual_seed(seed)
+    n, e = mesh.n_cells, mesh.n_faces
+    f32 = torch.float32
+    c = Data(velocity=torch.randn(n, steps, 2, generator=g), pressure=torch.randn(n, steps, 1, generator=g),
+             pos=torch.from_numpy(mesh.cell_pos).to(f32), volume=torch.from_numpy(mesh.cell_volume).to(f32),
+             normal=torch.from_numpy(mesh.cell_normal).to(f32),
+             edge_index=torch.from_numpy(mesh.cell_edge_index.copy()), dt=torch.tensor(0.01, dtype=f32))
+    f = Data(velocity=torch.randn(e, steps, 2, generator=g), pressure=torch.randn(e, steps, 1, generator=g),
+             flux=torch.randn(e, steps, 1, generator=g), pos=torch.from_numpy(mesh.face_pos).to(f32),
+             face=torch.from_numpy(mesh.face_index.copy()), type=torch.from_numpy(mesh.face_type.copy()),
+             area=torch.from_numpy(mesh.face_area).to(f32), normal=torch.from_numpy(mesh.face_normal).to(f32))
+    v = Data(pos=torch.from_numpy(mesh.vertex_pos).to(f32), edge_index=torch.from_numpy(mesh.vertex_edge_index.copy()),
+             face=torch.from_numpy(mesh.cells.T.copy()))
+    return [c, f, v]
+
+
 def _rs(key: str, seed: int) -> np.random.RandomState:
     return np.random.RandomState((zlib.crc32(key.encode()) ^ (seed * 2654435761)) & 0x7FFFFFFF)
 

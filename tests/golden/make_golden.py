@@ -29,7 +29,7 @@ import refstub  # noqa: E402
 refstub.install()
 
 from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs  # noqa: E402
-from gnn_fluid_dynamics_b200.testing import add_mls_fixture, default_stats, fill_state_dict_deterministic, stats_for  # noqa: E402
+from gnn_fluid_dynamics_b200.testing import add_mls_fixture, default_stats, fill_state_dict_deterministic, raw_graphs, stats_for  # noqa: E402
 from gnn_fluid_dynamics_b200.graph import Data  # noqa: E402
 
 from utils.config import Config  # noqa: E402  (reference)
@@ -227,6 +227,36 @@ def gen_update(name):
     np.savez_compressed(os.path.join(HERE, f"upd_{name}.npz"), cx=c.x.numpy(), fx2=fx[:, 0:2].numpy())
 
 
+TRANSFORM_MODELS = ["FvgnA", "FvgnC", "FvgnD", "FvgnH", "MgnA", "MgnB", "FluxA", "FluxC", "ConservativeA", "ConservativeB",
+                    "ConservativeD", "ConservativeH", "ConservativeJ", "ConservativeK",
+                    "ConservativeE", "StreamFuncC", "VertPotC", "FluxD"]      # the last four inherit (MRO check)
+
+
+class _TrainDataset:
+    class_types = NodeType
+    noise = True
+    mode = "train"
+    config = Config.from_dict({"model": {"hidden_width": 128, "mp_num": 15}, "training": {"noise_std": 0.02}})
+
+
+def gen_transform(name):
+    """Reference ``cls.transform_features(dataset, raw graphs)`` (train mode: noise + random edge flip under
+    torch.manual_seed(77), and valid mode) on a 160-cell mesh."""
+    module, kind, _ = MODELS[name]
+    cls = getattr(importlib.import_module(module), name)
+    out = {}
+    for tag, ds in (("train", _TrainDataset()), ("valid", _Dataset())):
+        graphs = raw_graphs(make_mesh(160, kind, seed=4))
+        torch.manual_seed(77)
+        c, f, v = cls.transform_features(ds, graphs)
+        for gname, g in (("c", c), ("f", f)):
+            for k in ("x", "y", "x_symm", "x_asym", "edge_index", "normal", "boundary_mask", "flux"):
+                if hasattr(g, k) and torch.is_tensor(getattr(g, k)):
+                    out[f"{tag}_{gname}_{k}"] = getattr(g, k).clone()
+        out[f"{tag}_c_has_velocity"] = torch.tensor([int(hasattr(c, "velocity"))])
+    np.savez_compressed(os.path.join(HERE, f"tf_{name}.npz"), **to_np(out))
+
+
 def gen_keys(name):
     import json
     model, _, _ = build_ref(name)
@@ -269,6 +299,10 @@ if __name__ == "__main__":
         for n in MODELS:
             gen_update(n)
         sys.exit(0)
+    if sys.argv[1:2] == ["--transform-only"]:
+        for n in TRANSFORM_MODELS:
+            gen_transform(n)
+        sys.exit(0)
     only = sys.argv[1:]
     if not only:
         gen_connectivity()
@@ -279,3 +313,5 @@ if __name__ == "__main__":
             gen_update(n)
     if not only:
         gen_train()
+        for n in TRANSFORM_MODELS:
+            gen_transform(n)

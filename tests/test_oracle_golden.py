@@ -48,6 +48,45 @@ def test_update_features_matches_reference(name):
     assert torch.equal(fx[:, 0:2], torch.from_numpy(gold["fx2"]))
 
 
+TRANSFORM_MODELS = ["FvgnA", "FvgnC", "FvgnD", "FvgnH", "MgnA", "MgnB", "FluxA", "FluxC", "ConservativeA", "ConservativeB",
+                    "ConservativeD", "ConservativeH", "ConservativeJ", "ConservativeK",
+                    "ConservativeE", "StreamFuncC", "VertPotC", "FluxD"]
+
+
+@pytest.mark.parametrize("name", TRANSFORM_MODELS)
+def test_transform_features_matches_reference(name):
+    """cls.transform_features on raw series (train mode: seeded noise + edge flip; valid mode) vs the reference."""
+    from types import SimpleNamespace as NS
+    from gnn_fluid_dynamics_b200.mesh import make_mesh
+    from gnn_fluid_dynamics_b200.models import MODEL_CLASSES
+    from gnn_fluid_dynamics_b200.testing import raw_graphs
+    from helpers import GOLDEN_SETUP
+    gold = load_golden(f"tf_{name}.npz")
+    types = ["NORMAL", "WALL_BOUNDARY", "INFLOW", "OUTFLOW", "SLIP"]
+    for tag, noise, mode in (("train", True, "train"), ("valid", False, "valid")):
+        ds = NS(class_types=types, noise=noise, mode=mode, config=NS(training=NS(noise_std=0.02)))
+        graphs = raw_graphs(make_mesh(160, GOLDEN_SETUP[name][0], seed=4))
+        torch.manual_seed(77)
+        c, f, v = MODEL_CLASSES[name].transform_features(ds, graphs)
+        seen = 0
+        for gname, g in (("c", c), ("f", f)):
+            for k in ("x", "y", "x_symm", "x_asym", "edge_index", "normal", "boundary_mask", "flux"):
+                key = f"{tag}_{gname}_{k}"
+                has = hasattr(g, k) and torch.is_tensor(getattr(g, k))
+                assert has == (key in gold), key
+                if not has:
+                    continue
+                mine, ref = getattr(g, k), torch.from_numpy(gold[key])
+                assert mine.shape == ref.shape and mine.dtype == ref.dtype, key
+                if mine.is_floating_point():
+                    assert torch.allclose(mine, ref, rtol=1e-6, atol=1e-6), key
+                else:
+                    assert torch.equal(mine, ref), key
+                seen += 1
+        assert seen >= 6
+        assert int(hasattr(c, "velocity")) == int(gold[f"{tag}_c_has_velocity"][0])
+
+
 def _processor_inputs(name, graphs, model):
     if name != "StreamFuncC":      # StreamFuncC.forward does not normalise (StreamFunc.py:173-176)
         graphs = model.normalizer.input(graphs)
