@@ -262,6 +262,16 @@ def gen_keys(name):
     model, _, _ = build_ref(name)
     keys = [[k, list(v.shape)] for k, v in model.state_dict().items()]
     json.dump(keys, open(os.path.join(HERE, f"keys_{name}.json"), "w"))
+    # class-level interface the callers read (train.py:350-355, DataSet.py:318, 344-352)
+    reg, ins, outs = type(model).get_normalisation_map()
+    meta = {"flags": {a: bool(getattr(model, a, False)) for a in
+                      ("pushforward_use", "cell_grad_weights_use", "face_grad_weights_use")},
+            "mls_attrs": [a for a in ("cell_mls_weights", "face_mls_weights") if hasattr(model, a)],
+            "feature_sizes": [list(x) for x in type(model).get_feature_sizes(_Dataset())],
+            "registry_kinds": {k: v[1] for k, v in reg.items()},
+            "input_stat_keys": sorted(v[1] for v in ins.values()),
+            "output_stat_keys": sorted(v[1] for v in outs.values())}
+    json.dump(meta, open(os.path.join(HERE, f"meta_{name}.json"), "w"), sort_keys=True)
 
 
 def gen_train():
@@ -298,6 +308,10 @@ if __name__ == "__main__":
     if sys.argv[1:2] == ["--update-only"]:
         for n in MODELS:
             gen_update(n)
+        sys.exit(0)
+    if sys.argv[1:2] == ["--keys-only"]:
+        for n in MODELS:
+            gen_keys(n)
         sys.exit(0)
     if sys.argv[1:2] == ["--transform-only"]:
         for n in TRANSFORM_MODELS:

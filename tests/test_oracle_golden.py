@@ -48,6 +48,22 @@ def test_update_features_matches_reference(name):
     assert torch.equal(fx[:, 0:2], torch.from_numpy(gold["fx2"]))
 
 
+@pytest.mark.parametrize("name", MODELS)
+def test_class_interface_matches_reference(name):
+    """Flags, feature sizes and normalisation registry the reference's training / dataset code reads off the class."""
+    ref = json.load(open(os.path.join(GOLDEN, f"meta_{name}.json")))
+    model = build_model(name)
+    cls = type(model)
+    for a, v in ref["flags"].items():
+        assert bool(getattr(model, a, False)) == v, a
+    assert [a for a in ("cell_mls_weights", "face_mls_weights") if hasattr(model, a)] == ref["mls_attrs"]
+    assert [list(x) for x in cls.get_feature_sizes(None)] == ref["feature_sizes"]
+    reg, ins, outs = cls.get_normalisation_map()
+    assert {k: v[1] for k, v in reg.items()} == ref["registry_kinds"]
+    assert sorted(v[1] for v in ins.values()) == ref["input_stat_keys"]
+    assert sorted(v[1] for v in outs.values()) == ref["output_stat_keys"]
+
+
 TRANSFORM_MODELS = ["FvgnA", "FvgnC", "FvgnD", "FvgnH", "MgnA", "MgnB", "FluxA", "FluxC", "ConservativeA", "ConservativeB",
                     "ConservativeD", "ConservativeH", "ConservativeJ", "ConservativeK",
                     "ConservativeE", "StreamFuncC", "VertPotC", "FluxD"]
