@@ -227,9 +227,7 @@ def gen_update(name):
     np.savez_compressed(os.path.join(HERE, f"upd_{name}.npz"), cx=c.x.numpy(), fx2=fx[:, 0:2].numpy())
 
 
-TRANSFORM_MODELS = ["FvgnA", "FvgnC", "FvgnD", "FvgnH", "MgnA", "MgnB", "FluxA", "FluxC", "ConservativeA", "ConservativeB",
-                    "ConservativeD", "ConservativeH", "ConservativeJ", "ConservativeK",
-                    "ConservativeE", "StreamFuncC", "VertPotC", "FluxD"]      # the last four inherit (MRO check)
+TRANSFORM_MODELS = list(MODELS)      # 14 classes define it, the others inherit (resolved through the MRO)
 
 
 class _TrainDataset:

@@ -64,9 +64,7 @@ def test_class_interface_matches_reference(name):
     assert sorted(v[1] for v in outs.values()) == ref["output_stat_keys"]
 
 
-TRANSFORM_MODELS = ["FvgnA", "FvgnC", "FvgnD", "FvgnH", "MgnA", "MgnB", "FluxA", "FluxC", "ConservativeA", "ConservativeB",
-                    "ConservativeD", "ConservativeH", "ConservativeJ", "ConservativeK",
-                    "ConservativeE", "StreamFuncC", "VertPotC", "FluxD"]
+TRANSFORM_MODELS = MODELS
 
 
 @pytest.mark.parametrize("name", TRANSFORM_MODELS)
