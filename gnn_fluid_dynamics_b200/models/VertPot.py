@@ -323,3 +323,48 @@ class VertPotG(VertPotA):
                  + w["face_pressure"] * fpl + w["face_flux"] * ffl)
         return {"total_log_loss": torch.mean(torch.log(total)), "continuity_loss": continuity,
                 "cell_velocity_change_loss": cvc, "face_velocity_loss": fvl, "face_pressure_loss": fpl}
+
+
+class _Unrunnable:
+    """VertPotD / VertPotF construct and load checkpoints like the reference's classes, but their ``forward`` cannot be
+    reproduced: in the reference it raises before producing anything (see the class docstrings)."""
+    _why = ""
+
+    def forward(self, graphs, mode="rollout"):
+        raise NotImplementedError(f"{type(self).__name__}.forward: {self._why}")
+
+
+class VertPotD(_Unrunnable, _VertPotNet, FluxA):
+    """Reference ``VertPotD`` (VertPot.py:447-492).  Its forward calls ``fvm.convert_cell_flux_to_face_flux_alt``
+    (VertPot.py:480), a function ``src/utils/fvm.py`` does not define, so the reference raises AttributeError."""
+    _why = ("the reference calls fvm.convert_cell_flux_to_face_flux_alt (VertPot.py:480), which src/utils/fvm.py does "
+            "not define; there is no reference behaviour to match")
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self._install_vertpot_net(config)
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 5 + n_class_types(dataset), 0], [0, 5, 1])
+
+
+class VertPotF(_Unrunnable, _VertPotNet, FluxA):
+    """Reference ``VertPotF`` (VertPot.py:541-628).  Same missing function (VertPot.py:574), and its integrator is built
+    with ``nu=None`` and multiplies by it (VertPot.py:553, 628)."""
+    _why = ("the reference calls fvm.convert_cell_flux_to_face_flux_alt (VertPot.py:574), which src/utils/fvm.py does "
+            "not define, and multiplies by nu=None (VertPot.py:553, 628); there is no reference behaviour to match")
+
+    def __init__(self, config, loss_func, dataset, stats):
+        super().__init__(config, loss_func, dataset, stats)
+        self._install_vertpot_net(config)
+        self.integrator = self.Integrator(config, rho=1.0)
+
+    @classmethod
+    def get_feature_sizes(cls, dataset):
+        return ([2, 5 + n_class_types(dataset), 0], [0, 3, 1])
+
+    class Integrator(nn.Module):   # VertPot.py:593-598 (parameter-free)
+        def __init__(self, config, rho, nu=None):
+            super().__init__()
+            self.rho, self.nu = rho, nu

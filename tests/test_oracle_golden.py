@@ -64,6 +64,20 @@ def test_class_interface_matches_reference(name):
     assert sorted(v[1] for v in outs.values()) == ref["output_stat_keys"]
 
 
+@pytest.mark.parametrize("name", ["VertPotD", "VertPotF"])
+def test_unrunnable_reference_classes_construct_and_explain(name):
+    """The two reference classes whose forward raises in the reference itself (missing fvm function): same constructor
+    and state_dict layout (checkpoints load), forward raises with the reason instead of an AttributeError."""
+    from gnn_fluid_dynamics_b200.models import UNRUNNABLE_CLASSES
+    from gnn_fluid_dynamics_b200.testing import stats_for
+    from helpers import make_config, mse
+    model = UNRUNNABLE_CLASSES[name](make_config(), mse, None, stats_for(name))
+    ref = json.load(open(os.path.join(GOLDEN, f"keys_{name}.json")))
+    assert [[k, list(v.shape)] for k, v in model.state_dict().items()] == ref
+    with pytest.raises(NotImplementedError, match="convert_cell_flux_to_face_flux_alt"):
+        model(None)
+
+
 TRANSFORM_MODELS = MODELS
 
 
