@@ -64,6 +64,23 @@ def build_batch(model_name, n_meshes, n_cells, kind, seed0=0):
     return collate_triplet(samples) if n_meshes > 1 else _with_batch(samples[0])
 
 
+def workload_config(workload, n_cells_total, n_faces, n_vertices):
+    """The `config` object of the JSON line: ONLY what defines the workload, identical in both arms
+    (`--impl ours` and `--impl reference`), so the driver can check that they measured the same thing."""
+    model_name, n_meshes, n_cells, kind, train = WORKLOADS[workload]
+    working_set = 4 * 128 * (2 * n_faces + 3 * n_cells_total) + 4 * 64 * n_vertices
+    if train == "rollout":
+        timed = "one autoregressive step: normalise + encoder + 15 GN_Blocks + decoder (+ integrator) + state advance"
+    elif train:
+        timed = "forward (encoder + 15 GN_Blocks + decoder + integrator) + loss + backward + grad clip + Adam step"
+    else:
+        timed = "encoder + 15 GN_Blocks + decoder"
+    return {"workload": workload, "model": model_name, "mp_num": MP_NUM, "hidden": 128,
+            "meshes_per_gpu": n_meshes, "cells_per_mesh": n_cells, "obstacle": kind, "cells": n_cells_total,
+            "faces": n_faces, "vertices": n_vertices, "timed": timed,
+            "l2": "working set > L2" if working_set >= 256e6 else "flushed between iterations"}
+
+
 def _with_batch(g):
     g[0].batch = torch.zeros(g[0].x.shape[0], dtype=torch.long)
     g[1].batch = torch.zeros(g[1].pos.shape[0], dtype=torch.long)
@@ -142,25 +159,15 @@ def algorithmic_bytes_edge_kernel(E, N):
     return 512 * (2 * E + N) + 8 * E
 
 
-def run_reference(args, world, rank):
-    """Reference arm: the oracle port of the reference's CPU path on the host cores (the Python
-    reference itself cannot travel to the GPU box)."""
-    if rank != 0:
-        return
-    import oracle
+def _oracle_step_fn(model_name, sd, graphs, train):
+    """One step of the CPU arm: the oracle port of the reference's forward (+ loss + backward + Adam step for the
+    training workload) on ONE mesh.  Imports nothing from the product package that loads the CUDA library."""
     from oracle import model as omodel
-    from helpers import LOSS_W, build_model
-    from gnn_fluid_dynamics_b200.testing import default_stats
-    model_name, n_meshes, n_cells, kind, train = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    graphs = build_batch(model_name, 1, n_cells, kind)      # bounded sample: ONE mesh of the batch
-    model = build_model(model_name)
-    sd = {k: v.clone() for k, v in model.state_dict().items()}
-    E = graphs[0].edge_index.shape[1]
+    from fixtures import default_stats
+    from helpers import LOSS_W
     stats = default_stats()
-
-    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    params = {k: v.clone().requires_grad_(bool(train) and v.is_floating_point() and "running" not in k
+                                          and not k.startswith("normalizer.")) for k, v in sd.items()}
     opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-4) if train else None
 
     def step():
@@ -174,7 +181,27 @@ def run_reference(args, world, rank):
         else:
             with torch.no_grad():
                 omodel.model_forward(model_name, sd, stats, g, MP_NUM, mode="train")
+    return step
 
+
+def run_reference(args, world, rank):
+    """Reference arm: the oracle port of the reference's CPU path on the host cores (the Python reference itself
+    cannot travel to the GPU box).  The CUDA library is never loaded here: parameters come from
+    tests/fixtures.py state_dict_from_keys (reference-generated key list + the deterministic fill)."""
+    if rank != 0:
+        return
+    from fixtures import state_dict_from_keys
+    model_name, n_meshes, n_cells, kind, train = WORKLOADS[args.workload]
+    if train == "rollout":
+        train = False        # the CPU arm times the forward of the step (state advance is negligible on the CPU)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = build_batch(model_name, n_meshes, n_cells, kind)      # for the config's totals (same batch as our arm)
+    N, E_total, V = batch[0].x.shape[0], batch[0].edge_index.shape[1], batch[2].pos.shape[0]
+    graphs = build_batch(model_name, 1, n_cells, kind)      # bounded sample: ONE mesh of the batch
+    sd = state_dict_from_keys(model_name)
+    E = graphs[0].edge_index.shape[1]
+    step = _oracle_step_fn(model_name, sd, graphs, train)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -187,11 +214,11 @@ def run_reference(args, world, rank):
         "impl": "reference", "metric": "processor edge-updates/sec", "value": value, "unit": "edge-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": model_name, "mp_num": MP_NUM, "hidden": 128,
-                   "meshes_per_gpu": n_meshes, "cells_per_mesh": n_cells},
+        "config": workload_config(args.workload, N, E_total, V),
         "cpu_baseline": {"value": value, "unit": "edge-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    assert "gnn_fluid_dynamics_b200._lib" not in sys.modules, "the CPU reference arm must not load the CUDA library"
     print(json.dumps(line), flush=True)
 
 
@@ -412,14 +439,9 @@ def main():
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"f32": "f32", "bf16x3": "bf16x3 (split-bf16 operands, fp32 accumulate)"}.get(prec, prec),
             "data": "synthetic",
-            "config": {"workload": args.workload, "model": model_name, "mp_num": MP_NUM, "hidden": 128,
-                       "meshes_per_gpu": n_meshes, "cells_per_mesh": n_cells, "cells": N, "faces": E,
-                       "vertices": V, "precision": prec,
-                       "timed": ("forward (encoder + 15 GN_Blocks + decoder + integrator) + loss + backward + grad clip + Adam step"
-                                 if train else "encoder + 15 GN_Blocks + decoder"),
-                       "forward_only_ms": fwd_ms,
-                       "backward_precision": "dgrad and wgrad split-bf16 (bf16x3), fp32 accumulate" if train else None,
-                       "l2": "flushed between iterations" if flush is not None else "working set > L2"},
+            "config": workload_config(args.workload, N, E, V),
+            "details": {"precision": prec, "forward_only_ms": fwd_ms,
+                        "backward_precision": "dgrad and wgrad split-bf16 (bf16x3), fp32 accumulate" if train else None},
             "e2e": {"value": E_total * MP_NUM / (ms_e2e * 1e-3), "unit": "edge-updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                     "api": ("model.forward + model.loss + backward + Adam step from pinned host graphs, loss read back"
@@ -537,29 +559,16 @@ def run_rollout(args, world, rank, dev, dist):
 
 def time_cpu_baseline(model_name, n_meshes, n_cells, kind, train=False):
     """Oracle port of the reference's CPU path on this box's host cores, bounded sample (1 mesh)."""
-    import oracle  # noqa: F401
-    from oracle import model as omodel
-    from helpers import LOSS_W, build_model
-    from gnn_fluid_dynamics_b200.testing import default_stats
+    from fixtures import state_dict_from_keys
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     graphs = build_batch(model_name, 1, n_cells, kind)
-    sd = {k: v.clone() for k, v in build_model(model_name).state_dict().items()}
     E = graphs[0].edge_index.shape[1]
-    params = {k: v.clone().requires_grad_(train and v.is_floating_point() and "running" not in k) for k, v in sd.items()}
-    opt = torch.optim.Adam([p for p in params.values() if p.requires_grad], lr=1e-4) if train else None
+    step = _oracle_step_fn(model_name, state_dict_from_keys(model_name), graphs, train)
     best = None
     for i in range(4):
         t0 = time.perf_counter()
-        g = [x.clone() for x in graphs]
-        if train:
-            opt.zero_grad(set_to_none=True)
-            out, _ = omodel.model_forward(model_name, params, default_stats(), g, MP_NUM, mode="train", training=True)
-            omodel.fvgn_loss(params, out, g, LOSS_W, training=True)["total_log_loss"].backward()
-            opt.step()
-        else:
-            with torch.no_grad():
-                omodel.model_forward(model_name, sd, default_stats(), g, MP_NUM, mode="train")
+        step()
         dt = time.perf_counter() - t0
         if i > 0:
             best = dt if best is None else min(best, dt)

@@ -2,6 +2,6 @@
 Flux / Conservative / VertPot models of aj-dray/gnn-fluid-dynamics.
 
 Importing the models requires the in-tree CUDA library (``lib/libgnnfd_b200.so``); there is no CPU
-or PyTorch fallback for the hot path.  ``graph`` / ``mesh`` / ``testing`` are importable without it.
+or PyTorch fallback for the hot path.  ``graph`` / ``mesh`` are importable without it.
 """
 __version__ = "0.1.0"

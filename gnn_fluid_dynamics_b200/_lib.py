@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgnnfd_b200.so")
+# GNNFD_LIB: experiment builds of the same library (scripts/abl_edge.py); the default is the in-tree build
+LIB_PATH = os.environ.get("GNNFD_LIB") or os.path.join(_HERE, "lib", "libgnnfd_b200.so")
 
 PREC_F32, PREC_BF16X3, PREC_BF16X1, PREC_FP16X2, PREC_FP16X3 = 0, 1, 2, 3, 4
 PRECISIONS = {"f32": PREC_F32, "bf16x3": PREC_BF16X3, "bf16x1": PREC_BF16X1,

@@ -36,15 +36,23 @@ void set_error(const char *fmt, ...);
     }                                                                                  \
   } while (0)
 
+// Per-device caches (SM count, "dynamic shared memory opt-in done" flags) are keyed by the CURRENT device ordinal:
+// one process may drive several GPUs, and cudaFuncSetAttribute / the SM count are per device.
+constexpr int GNNFD_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < GNNFD_MAX_DEVICES) ? dev : 0;
+}
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[GNNFD_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 // exact-path activations (IEEE expf / tanhf); the tensor-core path uses the fast variants

@@ -281,10 +281,10 @@ int mlp_forward_f32(const gnnfd_mlp_args *args, cudaStream_t stream) {
     set_error("mlp_forward_f32: k_in=%d needs %zu B of shared memory (> 227 KB)", args->k_in, smem);
     return GNNFD_E_UNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[GNNFD_MAX_DEVICES] = {false};
+  if (!attr_set[current_device()]) {
     GNNFD_CUDA(cudaFuncSetAttribute(mlp_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set[current_device()] = true;
   }
   int64_t n_tiles = (args->rows + F32_BM - 1) / F32_BM;
   int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());

@@ -21,6 +21,10 @@
 // k-block, part), so one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) lands a unit.
 #include "tc_common.cuh"
 
+#ifndef GNNFD_ABL
+#define GNNFD_ABL 0   // timing ablations (scripts/abl_edge.py): results are WRONG with any value but 0
+#endif
+
 namespace gnnfd {
 
 // warp roles: 0-7 epilogue of even local tiles, 8-15 epilogue of odd local tiles - the two groups convert different
@@ -324,6 +328,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // the loads of block b + 1 are issued right after block b is converted; (ij, ikb) tracks the next block to issue
     int ij = 0, ikb = 0;
     auto issue = [&](float4(&v)[8]) {
+#if GNNFD_ABL == 2 || GNNFD_ABL == 3   // ablation: no global loads in the producers
+      return;
+#endif
       if (ij < T) {
         tc_load_block(p, s_idx + (ij & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT, tile_row0(ij), ikb, rbase, f4, v);
         if (++ikb == p.kb1) { ikb = 0; ++ij; }
@@ -341,7 +348,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       }
       PROF_WAIT(0, mbar_wait(&a_empty[st], sphase));
       const int ksteps = (skb == p.kb1 - 1) ? p.ksteps1 : 4;
+#if GNNFD_ABL != 3        // ablation 3: no conversion / shared-memory stores either
       PROF_WAIT(1, (tc_store_block<FP16, NA>(sa_u32 + st * 2 * TC_IMG, v, off0, f4 * 4 < ksteps * 16)));
+#endif
       PROF_WAIT(2, fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(&a_full[st]));
       if (++skb == p.kb1) { skb = 0; ++sj; }
       if (++st == TC_A_STAGES) { st = 0; sphase ^= 1; }
@@ -355,6 +364,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // (Also tried: two HALF blocks of 4 rows per thread, the loads of half h of block b + 1 issued right after half h of
     //  block b is converted, same code size and registers as this - 204 us vs 163 us on the edge block, reverted.)
     float4 v0[8];
+#if GNNFD_ABL == 2 || GNNFD_ABL == 3
+    for (int i = 0; i < 8; ++i) v0[i] = make_float4(1.f, 2.f, 3.f, 4.f);
+#endif
     stage_idx(0); stage_idx(1); stage_idx(2);
     cp_async_wait_all();
     named_bar_sync(1, TC_PROD_THREADS);
@@ -384,6 +396,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       uint32_t round = 0;
       auto load_unit = [&](const uint8_t *src, uint32_t bytes) {
         if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+#if GNNFD_ABL == 1   // ablation: weights streamed for the first ring pass only
+        if (round > 0) { mbar_arrive(&full[slot]); if (++slot == n_slots) { slot = 0; ++round; } return; }
+#endif
         mbar_expect_tx(&full[slot], bytes);
         bulk_g2s(ring + slot * TC_IMG, src, bytes, &full[slot]);
         if (++slot == n_slots) { slot = 0; ++round; }
@@ -431,14 +446,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           const uint64_t ah = make_desc(smem_u32(s_a + st * 2 * TC_IMG)), al = ah + (TC_IMG >> 4);
           int slot;
           uint64_t wb = w_acquire(slot);
+#if GNNFD_ABL != 4
           for (int k = 0; k < ksteps; ++k) {
             umma_ss(d, ah + 2 * k, wb + 2 * k, idesc1, (kb | k) != 0);
             if (NA == 2) umma_ss(d, al + 2 * k, wb + 2 * k, idesc1, 1);
           }
+#endif
           umma_commit(&w_empty[slot]);
           if (NW == 2) {
             wb = w_acquire(slot);
+#if GNNFD_ABL != 4
             for (int k = 0; k < ksteps; ++k) umma_ss(d, ah + 2 * k, wb + 2 * k, idesc1, 1);
+#endif
             umma_commit(&w_empty[slot]);
           }
           umma_commit(&a_empty[st]);
@@ -484,15 +503,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             tc_fence_after();
             int slot;
             uint64_t wb = w_acquire(slot);
+#if GNNFD_ABL != 4
             for (int k = 0; k < 4; ++k) {
               const uint32_t ta = a_reg + (kb * 4 + k) * 16;
               umma_ts(d, ta, wb + 2 * k, idesc, (kb | k) != 0);
               if (NA == 2) umma_ts(d, ta + 8, wb + 2 * k, idesc, 1);
             }
+#endif
             umma_commit(&w23_empty[slot]);
             if (NW == 2) {
               wb = w_acquire(slot);
+#if GNNFD_ABL != 4
               for (int k = 0; k < 4; ++k) umma_ts(d, a_reg + (kb * 4 + k) * 16, wb + 2 * k, idesc, 1);
+#endif
               umma_commit(&w23_empty[slot]);
             }
           }
@@ -568,7 +591,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             for (int i = 0; i < 16; i += 4)
               *reinterpret_cast<float4 *>(save + c * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
+#if GNNFD_ABL == 5
+          if (true) {}
+#else
           if (BWD) { /* linear chain: no activation */ }
+#endif
           else if (a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
           uint32_t hi[8], lo[8];
 #pragma unroll
@@ -585,6 +612,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       // ---- final epilogue
       PROF_WAIT(1, mbar_wait(&acc_full[xs], (p.nl * n + p.nl - 1) & 1));
       tc_fence_after();
+#if GNNFD_ABL == 7
+      if (true) { __syncwarp(); if (lane == 0) mbar_arrive(&acc_free[xs]); } else
+#endif
       if (a.n_out == TC_H) {
         float mean = 0.f, rstd = 1.f;
         if (a.has_ln) {
@@ -622,7 +652,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           const int col0 = eh * 64 + c * 16;
           // residual rows of this group, coalesced mapping (8 rows x 64 B), requested before the TMEM read
           float4 res[4];
+#if GNNFD_ABL == 6
+          if (false) {
+#else
           if (a.out_sum) {
+#endif
 #pragma unroll
             for (int jr = 0; jr < 4; ++jr) {
               const int64_t g = min(row0 + q4 * 32 + jr * 8 + rr, a.rows - 1);
@@ -655,7 +689,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           for (int jr = 0; jr < 4; ++jr) {
             const int rl = jr * 8 + rr;
             const int64_t g = row0 + q4 * 32 + rl;
+#if GNNFD_ABL == 6
+            if (g < 0) {
+#else
             if (g < a.rows) {
+#endif
               float4 o = lds_f4(stg + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4);
               const size_t off = (size_t)g * TC_H + col0 + c4 * 4;
               if (a.save_xhat) *reinterpret_cast<float4 *>(a.save_xhat + off) = o;
@@ -871,11 +909,11 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   p.w_slots = n_tiles <= 2 * (int64_t)num_sms() ? TC_W_SLOTS_MAX : 2;
 #define LAUNCH1(FP, NA_, NW_, BW)                                                                         \
   do {                                                                                                    \
-    static bool attr = false;                                                                             \
-    if (!attr) {                                                                                          \
+    static bool attr[GNNFD_MAX_DEVICES] = {false};                                                                             \
+    if (!attr[current_device()]) {                                                                                          \
       GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                       tc_smem_bytes(TC_W_SLOTS_MAX)));                                    \
-      attr = true;                                                                                        \
+      attr[current_device()] = true;                                                                                        \
     }                                                                                                     \
     mlp_tc_kernel<FP, NA_, NW_, BW><<<grid, TC_THREADS, tc_smem_bytes(p.w_slots), stream>>>(p);           \
   } while (0)

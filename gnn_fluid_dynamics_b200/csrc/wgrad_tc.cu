@@ -488,10 +488,10 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
   const int smem = p.stages * (int)stage_bytes + WG_PROD_WARPS * 128 * 4 + (2 * WG_MAX_STAGES + 1) * 8 + 64 + 1024;
 #define WG_LAUNCH(NP_, MD_)                                                                                     \
   do {                                                                                                         \
-    static bool attr = false;                                                                                  \
-    if (!attr) {                                                                                               \
+    static bool attr[GNNFD_MAX_DEVICES] = {false};                                                                                  \
+    if (!attr[current_device()]) {                                                                                               \
       GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NP_, MD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
-      attr = true;                                                                                             \
+      attr[current_device()] = true;                                                                                             \
     }                                                                                                          \
     wgrad_tc_kernel<NP_, MD_><<<grid, WG_THREADS, smem, stream>>>(p);                                          \
   } while (0)

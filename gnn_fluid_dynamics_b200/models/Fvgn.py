@@ -559,6 +559,7 @@ class FvgnJ(FvgnA):
 
 class FvgnK(FvgnA):
     """Dimensionless outputs scaled per mesh by the inflow velocity and the Reynolds length (Fvgn.py:1276-1416)."""
+    host_sync_in_forward = True     # boolean-mask indexing per mesh: RolloutEngine steps it eagerly (no graph capture)
 
     def __init__(self, config, loss_func, dataset, stats):
         super().__init__(config, loss_func, dataset, stats)

@@ -31,6 +31,11 @@ def _stream() -> int:
 def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not (torch.is_tensor(t) and t.is_cuda):
         raise RuntimeError(f"{name}: expected a CUDA tensor (this path has no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # the C launches go to the CURRENT device's stream: a tensor on another GPU would fault or be reached through
+        # peer access silently (use torch.cuda.set_device / `with torch.cuda.device(...)` around the model call)
+        raise RuntimeError(f"{name}: tensor is on cuda:{t.device.index} but the current device is "
+                           f"cuda:{torch.cuda.current_device()}")
     if t.dtype != dtype:
         raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():

@@ -25,20 +25,34 @@ class RolloutEngine:
         self.model = model.eval()
         self.graphs = graphs
         self.topo = attach_topology(graphs, need_cell_csr=need_cell_csr, two_hop=two_hop)
-        self.use_graph = cuda_graph
+        # forwards that synchronise with the host (FvgnK: boolean-mask indexing / torch.unique on the Reynolds
+        # groups, Fvgn.py:1290-1340) cannot be captured: they step eagerly
+        self.use_graph = cuda_graph and not getattr(model, "host_sync_in_forward", False)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._vel: Optional[torch.Tensor] = None
         self.face_attr = "x_asym" if "x_asym" in graphs[1] else "x"
 
     @torch.no_grad()
     def _step_eager(self) -> torch.Tensor:
+        """One pass of the reference loop body (rollout.py:313-369).  A model that returns ``cell_velocity`` is taken
+        at its word (rollout.py:336-337: MgnB / MgnC / StreamFunc); otherwise velocity = x[:, :2] + change
+        (rollout.py:340).  Temporally bundled outputs [N, k, 2] (FvgnC) yield k velocities per forward and the LAST
+        one feeds ``update_features`` (rollout.py:319-332, 369); the returned tensor is then [N, k, 2]."""
         c, f, v = self.graphs
-        cx, fx = c.x, getattr(f, self.face_attr)                      # static state buffers
+        cx = c.x                                                       # static state buffer
         out = self.model([g.clone() for g in self.graphs], mode="rollout")           # rollout.py:313
-        vel = cx[:, :2] + out["cell_velocity_change"]                                   # rollout.py:340
-        self.model.update_features({"cell_velocity": vel}, self.graphs)                 # rollout.py:369
+        if "cell_velocity" in out:
+            vel = out["cell_velocity"]
+        elif "cell_velocity_change" in out:
+            dv = out["cell_velocity_change"]
+            vel = cx[:, None, :2] + dv if dv.dim() == 3 else cx[:, :2] + dv
+        else:
+            raise RuntimeError(f"{type(self.model).__name__}.forward returned neither 'cell_velocity' nor "
+                               f"'cell_velocity_change' (keys: {sorted(out)})")
+        last = vel[:, -1] if vel.dim() == 3 else vel
+        self.model.update_features({"cell_velocity": last}, self.graphs)                # rollout.py:369
         # update_features rebinds c_graph.x to the new tensor; keep the state in the static buffer instead
-        cx[:, :2].copy_(vel)
+        cx[:, :2].copy_(last)
         c.x = cx
         return vel
 

@@ -61,7 +61,7 @@ def raw_graphs(mesh, seed: int = 17, steps: int = 4):
     """Raw (pre-``transform_features``) graph triplet on a synthetic mesh: velocity / pressure / flux time series on
     cells and faces plus the static geometry, in the shapes the reference's dataset hands to the model class
     (``src/datasets/DataSet.py:210-274``: series are [rows, time, channels], face type is [E, 1])."""
-    from .graph import Data
+    from gnn_fluid_dynamics_b200.graph import Data
     g = torch.Generator().manual_seed(seed)
     n, e = mesh.n_cells, mesh.n_faces
     f32 = torch.float32
@@ -85,7 +85,36 @@ def _rs(key: str, seed: int) -> np.random.RandomState:
 @torch.no_grad()
 def fill_state_dict_deterministic(module: torch.nn.Module, seed: int = 1) -> None:
     """Overwrite every Linear / LayerNorm / BatchNorm tensor of ``module`` in place."""
-    sd = module.state_dict()
+    fill_tensor_dict(module.state_dict(), seed)
+
+
+@torch.no_grad()
+def state_dict_from_keys(model_name: str, seed: int = 1):
+    """The deterministic state_dict of ``model_name`` WITHOUT constructing the model: key names and shapes from the
+    reference-generated ``tests/golden/keys_{model}.json``, normaliser buffers from ``stats_for``, everything else from
+    the same key-seeded fill.  Used by the CPU reference arm of bench.py, which must not load the CUDA library."""
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    keys = json.load(open(os.path.join(here, "golden", f"keys_{model_name}.json")))
+    stats = stats_for(model_name)
+    sd = {}
+    for key, shape in keys:
+        if key.startswith("normalizer."):
+            name, stat = key[len("normalizer."):].rsplit("_", 1)
+            sd[key] = torch.tensor(stats[name][stat], dtype=torch.float)
+        elif key.endswith("num_batches_tracked"):
+            sd[key] = torch.zeros(shape, dtype=torch.long)
+        else:
+            sd[key] = torch.zeros(shape, dtype=torch.float32)
+            if key.endswith("anisotropy_ratio"):
+                sd[key].fill_(0.0001)
+    fill_tensor_dict(sd, seed)
+    return sd
+
+
+@torch.no_grad()
+def fill_tensor_dict(sd, seed: int = 1) -> None:
     for key, t in sd.items():
         if "normalizer." in key:
             continue

@@ -8,7 +8,7 @@ What is pinned
   fwd_{Model}.npz      : reference model forward (every class in MODELS below: 36 of the reference's 38; VertPotD / F
                          cannot run in the reference),
                          hidden 128, 15 blocks, deterministic parameters
-                         (gnn_fluid_dynamics_b200.testing.fill_state_dict_deterministic, seed 1),
+                         (tests/fixtures.py fill_state_dict_deterministic, seed 1),
                          mesh make_mesh(160, kind, seed=3), features mesh_graphs(seed=5):
                          encoder outputs, processor outputs after block 1 and block 15, decoder
                          outputs, the forward() dict in 'train' and 'rollout' modes; for LOSS_MODELS also
@@ -24,12 +24,14 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))      # tests/ (fixtures.py)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))   # repo root
 import refstub  # noqa: E402
 
 refstub.install()
 
 from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs  # noqa: E402
-from gnn_fluid_dynamics_b200.testing import add_mls_fixture, default_stats, fill_state_dict_deterministic, raw_graphs, stats_for  # noqa: E402
+from fixtures import add_mls_fixture, default_stats, fill_state_dict_deterministic, raw_graphs, stats_for  # noqa: E402
 from gnn_fluid_dynamics_b200.graph import Data  # noqa: E402
 
 from utils.config import Config  # noqa: E402  (reference)
@@ -108,9 +110,9 @@ def build_ref(name):
     return model, kind, flavour
 
 
-def graphs_for(name, kind, flavour, flip=False):
-    mesh = make_mesh(160, kind, seed=3)
-    g = mesh_graphs(mesh, seed=5, flavour=flavour, flip_edges=flip)
+def graphs_for(name, kind, flavour, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
+    mesh = make_mesh(n_cells, kind, seed=mesh_seed)
+    g = mesh_graphs(mesh, seed=feat_seed, flavour=flavour, flip_edges=flip)
     c, f, v = g
     if name in MGN_LIKE + ("ConservativeB",):
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
@@ -302,7 +304,77 @@ def gen_train():
     print("train", {k: float(v) for k, v in losses.items()}, len(names), "param grads")
 
 
+TRAIN_STEP_MODELS = ("VertPotA", "StreamFuncA", "FluxA", "ConservativeA", "MgnA")
+
+
+def gen_train_step(name):
+    """Reference training step (train.py:251-256: model.train(); forward(batch, 'train'); model.loss; backward) on
+    the 160-cell fixture with flipped edges: loss values, the norm of every parameter gradient and up to six full
+    gradient tensors.  VertPotA / StreamFuncA are BASELINE.json config 5's families."""
+    model, kind, flavour = build_ref(name)
+    model.train()
+    _, graphs = graphs_for(name, kind, flavour, flip=True)
+    batch = [g.clone() for g in graphs]
+    output = model(batch, mode="train")
+    losses = model.loss(output, batch)
+    losses["total_log_loss"].backward()
+    out = {f"loss_{k}": v.detach().reshape(1) for k, v in losses.items()}
+    names, norms = [], []
+    for k, p in model.named_parameters():
+        if p.grad is None or float(p.grad.abs().max()) == 0.0:      # VertPot's unused duplicate blocks get no gradient
+            continue
+        names.append(k)
+        norms.append(float(p.grad.double().norm()))
+    keep = names[:: max(1, len(names) // 6)][:6]
+    grads = dict(model.named_parameters())
+    for k in keep:
+        out["grad_" + k] = grads[k].grad.clone()
+    out["grad_norms"] = torch.tensor(norms, dtype=torch.float64)
+    d = to_np(out)
+    d["grad_names"] = np.array(names)
+    np.savez_compressed(os.path.join(HERE, f"train_{name}.npz"), **d)
+    print("train", name, {k: float(v.detach()) for k, v in losses.items()}, len(names), "param grads", keep)
+
+
+ROLLOUT_MODELS = ("FvgnA", "MgnA", "FluxA", "ConservativeA", "ConservativeD", "MgnB", "StreamFuncA")
+ROLLOUT_KEEP = (1, 10, 50, 100)
+
+
+def gen_rollout(name):
+    """The reference's autoregressive loop (src/rollout.py:313-369) run on CPU for 100 steps on a 400-cell mesh:
+    output = model(clones, mode='rollout'); cell_velocity = output['cell_velocity'] if the model returns it, else
+    x[:, :2] + cell_velocity_change; input_graphs = model.update_features(solutions, input_graphs).
+    Same mesh / features as tests/test_gpu_rollout.py (n_cells=400, mesh_seed=31, feat_seed=32)."""
+    model, kind, flavour = build_ref(name)
+    model.eval()
+    _, graphs = graphs_for(name, kind, flavour, n_cells=400, mesh_seed=31, feat_seed=32)
+    graphs = [g.clone() for g in graphs]
+    type2d = graphs[1].type.reshape(-1, 1).clone()
+    out = {}
+    with torch.no_grad():
+        for step in range(1, 101):
+            graphs[1].type = type2d
+            sol = dict(model([g.clone() for g in graphs], mode="rollout"))
+            if "cell_velocity" not in sol:
+                sol["cell_velocity"] = graphs[0].x[:, 0:2] + sol["cell_velocity_change"]
+            graphs[1].type = type2d.reshape(-1)          # the reference's boolean-mask assignment needs a 1-D type
+            graphs = list(model.update_features(sol, graphs))
+            if step in ROLLOUT_KEEP:
+                out[f"vel_{step}"] = sol["cell_velocity"].clone()
+    assert all(torch.isfinite(v).all() for v in out.values()), name
+    np.savez_compressed(os.path.join(HERE, f"rollout_{name}.npz"), **to_np(out))
+    print("rollout", name, {k: float(v.norm()) for k, v in out.items()})
+
+
 if __name__ == "__main__":
+    if sys.argv[1:2] == ["--train-only"]:
+        for n in TRAIN_STEP_MODELS:
+            gen_train_step(n)
+        sys.exit(0)
+    if sys.argv[1:2] == ["--rollout-only"]:
+        for n in ROLLOUT_MODELS:
+            gen_rollout(n)
+        sys.exit(0)
     if sys.argv[1:2] == ["--update-only"]:
         for n in MODELS:
             gen_update(n)

@@ -40,7 +40,7 @@ def mse(output, target, mask, batch=None):
 
 def build_model(name, mp_num=15, precision=None, seed=1, device="cpu"):
     from gnn_fluid_dynamics_b200.models import MODEL_CLASSES
-    from gnn_fluid_dynamics_b200.testing import fill_state_dict_deterministic, stats_for
+    from fixtures import fill_state_dict_deterministic, stats_for
     model = MODEL_CLASSES[name](make_config(mp_num, precision), mse, None, stats_for(name))
     fill_state_dict_deterministic(model, seed=seed)
     return model.to(device)
@@ -64,7 +64,7 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     if name == "ConservativeI":
         f.type = f.type.reshape(-1)      # see tests/golden/make_golden.py: the reference needs a 1-D type tensor here
     if name.startswith("StreamFunc") or name in ("MgnB", "MgnC"):
-        from gnn_fluid_dynamics_b200.testing import add_mls_fixture
+        from fixtures import add_mls_fixture
         add_mls_fixture(c)
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
@@ -73,7 +73,7 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
 
 def fvgn_variant_fixture(name, c, f):
     """Extra inputs of the FvgnA glue variants (same construction in tests/golden/make_golden.py)."""
-    from gnn_fluid_dynamics_b200.testing import add_mls_fixture
+    from fixtures import add_mls_fixture
     if name in ("VertPotC", "VertPotE"):      # FluxC targets: (pressure, flux)
         f.y = f.y[:, :2].contiguous()
     if name in ("FvgnB", "VertPotB"):       # face moving-least-squares stencil for the diffusion term (Fvgn.py:446)

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import oracle
-from gnn_fluid_dynamics_b200.testing import rel_l2
+from fixtures import rel_l2
 from helpers import ALL_MODELS, LOSS_MODELS, build_model, golden_graphs, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -228,17 +228,21 @@ def test_loss_matches_reference_golden(name):
         assert abs(float(v) - ref) <= 2e-3 * max(abs(ref), 1e-6), (name, k, float(v), ref)
 
 
-@pytest.mark.parametrize("name,n_cells", [("FvgnA", 20000), ("MgnA", 2048)])
+@pytest.mark.parametrize("name,n_cells", [("FvgnA", 20000), ("MgnA", 2048), ("FluxA", 20000), ("ConservativeA", 20000),
+                                          ("ConservativeD", 20000)])
 def test_processor_vs_oracle_at_baseline_sizes(name, n_cells):
-    """BASELINE.json configs[0] (2k-cell MGN) and the per-mesh size of configs[1] (20k-cell FVGN)."""
+    """BASELINE.json configs[0] (2k-cell MGN), the per-mesh size of configs[1] (20k-cell FVGN) and the config-3
+    families (Flux / Conservative face-flux message passing) at 20k cells: every processor output within 1e-3."""
     model = build_model(name).eval()
     _, graphs = golden_graphs(name, n_cells=n_cells, mesh_seed=7, feat_seed=8)
     graphs = model.normalizer.input([g.clone() for g in graphs])
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     c, f, v = graphs
     topo = {"c_edge_index": c.edge_index, "v_edge_index": v.edge_index, "v_face": v.face, "n_vertices": v.num_nodes}
+    dual = name in ("ConservativeA", "ConservativeD")
     with torch.no_grad():
-        ref = oracle.processor_fwd(oracle.family_of(name), sd, c.x, f.x, topo, 15)
+        ref = oracle.processor_fwd(oracle.family_of(name), sd, c.x, f.x_symm if dual else f.x, topo, 15,
+                                   f_x_asym=f.x_asym if dual else None)
     model.to(dev())
     gd = [g.to(dev()) for g in graphs]
     for prec in precisions():
@@ -247,6 +251,9 @@ def test_processor_vs_oracle_at_baseline_sizes(name, n_cells):
             out = _run_processor(name, model, gd)
         assert rel_l2(out["x"], ref["x"]) < TOL[prec], (prec, rel_l2(out["x"], ref["x"]))
         assert rel_l2(out["e"], ref["e"]) < TOL[prec], (prec, rel_l2(out["e"], ref["e"]))
+        assert rel_l2(out["dec"], ref["dec"]) < 2 * TOL[prec], (prec, rel_l2(out["dec"], ref["dec"]))
+        if name == "ConservativeD":
+            assert rel_l2(model._last_e_asym, ref["ea"]) < TOL[prec]
 
 
 def test_batched_meshes_equal_individual_meshes():

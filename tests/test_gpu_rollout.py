@@ -4,8 +4,8 @@ import pytest
 import torch
 
 from oracle import model as omodel
-from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
-from helpers import build_model, golden_graphs
+from fixtures import default_stats, rel_l2
+from helpers import build_model, golden_graphs, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -49,3 +49,43 @@ def test_rollout_engine_other_families_graph_equals_eager(name):
     assert all(torch.equal(p, q) for p, q in zip(va, vb))
     assert torch.isfinite(va[-1]).all()
     assert not torch.equal(va[0], va[-1])
+
+
+ROLLOUT_GOLDEN = ["FvgnA", "MgnA", "FluxA", "ConservativeA", "ConservativeD", "MgnB", "StreamFuncA"]
+
+
+@pytest.mark.parametrize("name", ROLLOUT_GOLDEN)
+def test_rollout_100_steps_vs_reference_golden(name):
+    """BASELINE.json north_star: within 1e-2 after a 100-step rollout.  The golden is the REFERENCE's own loop
+    (src/rollout.py:313-369) run on CPU for 100 steps (tests/golden/make_golden.py --rollout-only): FvgnA / MgnA, the
+    config-3 families (FluxA, ConservativeA, ConservativeD) and the models that return ``cell_velocity`` directly
+    (MgnB, StreamFuncA).  Velocities after 1, 10, 50 and 100 steps."""
+    from gnn_fluid_dynamics_b200.rollout import RolloutEngine
+    gold = load_golden(f"rollout_{name}.npz")
+    dev = torch.device("cuda:0")
+    model = build_model(name).to(dev).eval()
+    _, graphs = golden_graphs(name, n_cells=400, mesh_seed=31, feat_seed=32)
+    cons = name.startswith("Conservative")
+    eng = RolloutEngine(model, [g.clone().to(dev) for g in graphs], cuda_graph=True, need_cell_csr=cons,
+                        two_hop=not cons)
+    vels = eng.run(100, keep=True)
+    for step in (1, 10, 50, 100):
+        err = rel_l2(vels[step - 1], torch.from_numpy(gold[f"vel_{step}"]))
+        assert err < 1e-2, (name, step, err)
+
+
+def test_rollout_bundled_and_host_syncing_models_step():
+    """FvgnC returns [N, k, 2] bundles (the last one advances the state, rollout.py:319-369); FvgnK's forward
+    synchronises with the host, so the engine steps it eagerly instead of capturing it."""
+    from gnn_fluid_dynamics_b200.rollout import RolloutEngine
+    dev = torch.device("cuda:0")
+    for name in ("FvgnC", "FvgnK"):
+        model = build_model(name).to(dev).eval()
+        _, graphs = golden_graphs(name, n_cells=300, mesh_seed=41, feat_seed=42)
+        eng = RolloutEngine(model, [g.clone().to(dev) for g in graphs], cuda_graph=True)
+        if name == "FvgnK":
+            assert not eng.use_graph
+        out = eng.run(3, keep=True)
+        assert out[-1].shape[-1] == 2 and torch.isfinite(out[-1]).all()
+        if name == "FvgnC":
+            assert out[-1].dim() == 3 and out[-1].shape[1] == 3

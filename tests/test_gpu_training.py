@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import model as omodel
-from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
+from fixtures import default_stats, rel_l2
 from helpers import LOSS_W, build_model, golden_graphs, load_golden
 
 pytestmark = pytest.mark.gpu
@@ -168,7 +168,7 @@ def _oracle_step(name, model, graphs):
     return float(loss), {k: p.grad for k, p in params.items() if p.grad is not None}
 
 
-@pytest.mark.parametrize("name,n_cells", [("FvgnA", 160), ("MgnA", 160), ("FvgnA", 3000)])
+@pytest.mark.parametrize("name,n_cells", [("FvgnA", 160), ("MgnA", 160), ("FvgnA", 3000), ("FvgnA", 20000)])
 def test_training_step_gradients_vs_oracle(name, n_cells):
     model = build_model(name).train()
     _, graphs = golden_graphs(name, flip=True, n_cells=n_cells)
@@ -207,6 +207,33 @@ def test_training_step_matches_reference_golden():
             assert abs(float(grads[n].grad.double().norm()) - ref_norm) <= 2e-3 * max(ref_norm, 1e-6) + 1e-9, n
     for k in gold:
         if k.startswith(("grad_processer", "grad_decoder", "grad_encoder")):
+            assert rel_l2(grads[k[5:]].grad, torch.from_numpy(gold[k])) < GRAD_TOL, k
+
+
+@pytest.mark.parametrize("name", ["VertPotA", "StreamFuncA", "FluxA", "ConservativeA", "MgnA"])
+def test_training_step_matches_reference_golden_families(name):
+    """The reference's own training step (forward 'train' + model.loss + backward; tests/golden/make_golden.py
+    --train-only) for BASELINE.json config 5's families (VertPotA, StreamFuncA) and FluxA / ConservativeA / MgnA:
+    loss values, the norm of every live parameter gradient and six full gradient tensors."""
+    gold = load_golden(f"train_{name}.npz")
+    model = build_model(name).to(dev()).train()
+    _, graphs = golden_graphs(name, flip=True)
+    batch = [g.clone().to(dev()) for g in graphs]
+    out = model(batch, mode="train")            # normalises the batch in place, like the reference (train.py:253)
+    losses = model.loss(out, batch)
+    for k, v in losses.items():
+        ref = float(gold[f"loss_{k}"][0])
+        assert abs(float(v) - ref) < 2e-4 * max(1.0, abs(ref)) or abs(ref) < 1e-12, (k, float(v), ref)
+    losses["total_log_loss"].backward()
+    grads = dict(model.named_parameters())
+    checked = 0
+    for n, ref_norm in zip([str(n) for n in gold["grad_names"]], gold["grad_norms"]):
+        assert grads[n].grad is not None, n
+        assert abs(float(grads[n].grad.double().norm()) - ref_norm) <= 2e-3 * max(ref_norm, 1e-6) + 1e-9, n
+        checked += 1
+    assert checked > 200
+    for k in gold:
+        if k.startswith("grad_") and k not in ("grad_names", "grad_norms"):
             assert rel_l2(grads[k[5:]].grad, torch.from_numpy(gold[k])) < GRAD_TOL, k
 
 

@@ -10,7 +10,7 @@ import torch
 import oracle
 from oracle import model as omodel
 from gnn_fluid_dynamics_b200.mesh import connectivity
-from gnn_fluid_dynamics_b200.testing import default_stats, rel_l2
+from fixtures import default_stats, rel_l2
 from helpers import ALL_MODELS, GOLDEN, LOSS_W, build_model, golden_graphs, load_golden
 
 MODELS = ALL_MODELS
@@ -69,7 +69,7 @@ def test_unrunnable_reference_classes_construct_and_explain(name):
     """The two reference classes whose forward raises in the reference itself (missing fvm function): same constructor
     and state_dict layout (checkpoints load), forward raises with the reason instead of an AttributeError."""
     from gnn_fluid_dynamics_b200.models import UNRUNNABLE_CLASSES
-    from gnn_fluid_dynamics_b200.testing import stats_for
+    from fixtures import stats_for
     from helpers import make_config, mse
     model = UNRUNNABLE_CLASSES[name](make_config(), mse, None, stats_for(name))
     ref = json.load(open(os.path.join(GOLDEN, f"keys_{name}.json")))
@@ -87,7 +87,7 @@ def test_transform_features_matches_reference(name):
     from types import SimpleNamespace as NS
     from gnn_fluid_dynamics_b200.mesh import make_mesh
     from gnn_fluid_dynamics_b200.models import MODEL_CLASSES
-    from gnn_fluid_dynamics_b200.testing import raw_graphs
+    from fixtures import raw_graphs
     from helpers import GOLDEN_SETUP
     gold = load_golden(f"tf_{name}.npz")
     types = ["NORMAL", "WALL_BOUNDARY", "INFLOW", "OUTFLOW", "SLIP"]
@@ -196,3 +196,33 @@ def test_scatter_add_matches_loop_and_csr_is_stable_sort():
     ref_perm = torch.sort(torch.from_numpy(idx), stable=True).indices.numpy()
     assert np.array_equal(perm, ref_perm)
     assert np.array_equal(np.diff(off), np.bincount(idx, minlength=40))
+
+
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA"])
+def test_oracle_rollout_matches_reference_rollout(name):
+    """oracle.model.rollout_step against the reference's own 100-step loop (rollout_{name}.npz, generated by
+    tests/golden/make_golden.py --rollout-only from src/rollout.py:313-369 semantics)."""
+    from oracle import model as omodel
+    from fixtures import default_stats
+    gold = load_golden(f"rollout_{name}.npz")
+    model = build_model(name).eval()
+    _, graphs = golden_graphs(name, n_cells=400, mesh_seed=31, feat_seed=32)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    graphs = [g.clone() for g in graphs]
+    with torch.no_grad():
+        for step in range(1, 11):
+            vel = omodel.rollout_step(name, sd, default_stats(), graphs, 15)
+            if step in (1, 10):
+                assert rel_l2(vel, torch.from_numpy(gold[f"vel_{step}"])) < 1e-4, (name, step)
+
+
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "FluxA", "ConservativeA", "VertPotA"])
+def test_state_dict_from_keys_equals_constructed_model(name):
+    """fixtures.state_dict_from_keys (what bench.py's CPU reference arm uses, so that it never loads the CUDA library)
+    reproduces the constructed model's deterministic state_dict bit for bit."""
+    from fixtures import state_dict_from_keys
+    a = state_dict_from_keys(name)
+    b = build_model(name).state_dict()
+    assert list(a) == list(b)
+    for k in a:
+        assert a[k].shape == b[k].shape and torch.equal(a[k].float(), b[k].float()), k
