@@ -28,12 +28,12 @@ EXPORTS = [
     "gnnfd_mlp_backward_workspace_bytes", "gnnfd_pack_mlp_backward_bytes", "gnnfd_pack_mlp_backward",
     "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access", "gnnfd_gather_cols_add",
 ]
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Segment(C.Structure):
     _fields_ = [("src", C.c_void_p), ("idx", C.c_void_p * 3), ("ld", C.c_int32), ("col", C.c_int32),
-                ("width", C.c_int32), ("mode", C.c_int32)]
+                ("width", C.c_int32), ("mode", C.c_int32), ("split", C.c_void_p), ("src_rows", C.c_int64)]
 
 
 class MlpArgs(C.Structure):
@@ -52,6 +52,7 @@ class MlpArgs(C.Structure):
         ("w2_ld_n", C.c_int32), ("w2_ld_k", C.c_int32), ("w3_ld_n", C.c_int32), ("w3_ld_k", C.c_int32),
         ("w3_rows", C.c_int32),
         ("peer_base", C.c_void_p * 8), ("peer_shift", C.c_int32),
+        ("out_split", C.c_void_p), ("split_of_sum", C.c_int32),
     ]
 
 

@@ -112,16 +112,24 @@ class _MLPFn(torch.autograd.Function):
 
 
 def mlp(seq, segs: Sequence[Seg], rows: int, prec: int, act: int = ACT_SILU, mul: Optional[torch.Tensor] = None,
-        residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_sum: bool = False):
+        residual: Optional[torch.Tensor] = None, want_raw: bool = True, want_sum: bool = False,
+        inplace: bool = False, out_split: Optional[torch.Tensor] = None, split_of_sum: bool = False):
     """Fused MLP block of module ``seq`` -> (out_raw or None, out_sum or None); differentiable w.r.t. the module's
-    parameters, the segment sources, ``mul`` and ``residual`` when autograd is recording."""
+    parameters, the segment sources, ``mul`` and ``residual`` when autograd is recording.
+
+    Inference only (``processor.inference_mode``): ``inplace`` writes the sum into ``residual`` itself, ``out_split``
+    receives the 16-bit split shadow of the output for the next block's TMA gathers (see ``ops.mlp_forward``)."""
     from .processor import weights_of
     from .training import Site
     site_params = Site(seq, act).params
     srcs = [s.src for s in segs]
     if not _needs_grad(list(site_params) + srcs + [mul, residual]):
         return ops.mlp_forward(segs, weights_of(seq, act), rows, prec, mul=mul, residual=residual,
-                               want_raw=want_raw, want_sum=want_sum)
+                               want_raw=want_raw, want_sum=want_sum,
+                               out_sum=residual if (inplace and want_sum) else None,
+                               out_split=out_split, split_of_sum=split_of_sum)
+    if inplace or out_split is not None or any(s.split is not None for s in segs):
+        raise RuntimeError("in-place residuals / split shadows are inference-only (autograd is recording)")
     meta = (seq, act, [(s.mode, tuple(s.idx), s.col, s.width) for s in segs], rows, prec, want_raw, want_sum)
     raw, summed = _MLPFn.apply(meta, *site_params, *srcs, mul, residual)
     return raw, summed

@@ -58,7 +58,20 @@ int validate_mlp_args(const gnnfd_mlp_args *a) {
                     "training stashes need a tensor-core precision");
   GNNFD_CHECK_ARG(!a->save_xhat || a->n_out == 128, "save_xhat needs n_out == 128");
   GNNFD_CHECK_ARG(!a->out_sum || a->residual, "out_sum requires residual");
-  GNNFD_CHECK_ARG(a->out_raw || a->out_sum || a->rows == 0, "no output requested");
+  GNNFD_CHECK_ARG(a->out_raw || a->out_sum || a->out_split || a->rows == 0, "no output requested");
+  if (a->out_split)
+    GNNFD_CHECK_ARG((a->precision == GNNFD_PREC_BF16X3 || a->precision == GNNFD_PREC_FP16X3) && a->n_out == 128,
+                    "out_split needs a split precision (BF16X3 / FP16X3) and n_out == 128");
+  for (int s = 0; s < a->n_seg; ++s)
+    if (a->seg[s].split != nullptr) {
+      GNNFD_CHECK_ARG(a->seg[s].src_rows > 0, "segment with a split shadow needs src_rows");
+      // a source that exists ONLY as its shadow (src aliases split) can be consumed by TMA gathers alone
+      if ((const void *)a->seg[s].src == a->seg[s].split)
+        GNNFD_CHECK_ARG((a->precision == GNNFD_PREC_BF16X3 || a->precision == GNNFD_PREC_FP16X3) &&
+                            a->seg[s].mode == GNNFD_SEG_GATHER && (a->seg[s].width & 63) == 0 && (a->seg[s].col & 63) == 0 &&
+                            (a->seg[s].ld & 63) == 0 && a->peer_shift == 0,
+                        "a shadow-only segment must be a 64-column-aligned GATHER at a split precision");
+    }
   return GNNFD_OK;
 }
 }  // namespace gnnfd

@@ -19,6 +19,8 @@
 // (128 B per row), rows in groups of 8 (1024 B atoms), 16-byte chunk c of row r stored at chunk
 // c ^ (r & 7).  Weights are pre-packed by gnnfd_pack_mlp into exactly this image per (layer,
 // k-block, part), so one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) lands a unit.
+#include <cuda.h>   // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
+
 #include "tc_common.cuh"
 
 #ifndef GNNFD_ABL
@@ -46,7 +48,8 @@ constexpr int TC_MMA23_WARP = TC_MMA_WARP + 1;
 constexpr int TC_WLD_WARP = TC_MMA_WARP + 2;
 constexpr int TC_WLD23_WARP = TC_MMA_WARP + 3;
 constexpr int TC_THREADS = (TC_MMA_WARP + 4) * 32;   // 896
-constexpr int TC_A_STAGES = 2;        // A ring: {A_hi, A_lo} images per stage
+constexpr int TC_A_STAGES_MAX = 3;    // A ring: {A_hi, A_lo} images per stage; TcParams::a_stages = 2 (register-staged
+                                      // producers only) or 3 (launches with TMA-gathered k-blocks: no register staging)
 // W rings (layer 1 | layers 2/3): one 16 KB image (hi or lo part of a k-block) per slot, TcParams::w_slots slots each.
 // Large launches run TWO slots per ring: measured FASTER than three, because the 32 KB not carved out of the L1 serve
 // the producers' gathers (203 -> 194 us on the edge block).  Launches of a tile or two per CTA are a pure latency
@@ -54,16 +57,17 @@ constexpr int TC_A_STAGES = 2;        // A ring: {A_hi, A_lo} images per stage
 // dynamic allocation (which sets the L1 carve-out) only covers the slots in use.
 constexpr int TC_W_SLOTS_MAX = 3;
 constexpr int TC_X_SLOTS = 3;         // X regions in TMEM
-constexpr int TC_A_BYTES = TC_A_STAGES * 2 * TC_IMG;   // 64 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_IMG;   // 32 KB per A stage
 constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * 16 * 4;   // 32 KB: one XOR-swizzled 32 x 16 fp32 staging block per epilogue warp
 constexpr int TC_IDX_SLOTS = 4;
 constexpr int TC_IDX_SLOT = 9 * TC_BM;               // ints: [3 seg][3 idx][128 rows]
 constexpr int TC_NBAR = 32;
-constexpr int TC_SMEM_FIXED = TC_A_BYTES + TC_STG_BYTES + TC_IDX_SLOTS * TC_IDX_SLOT * 4 +
+constexpr int TC_SMEM_FIXED = TC_STG_BYTES + TC_IDX_SLOTS * TC_IDX_SLOT * 4 +
                               5 * TC_H * 4 + 4 * TC_BM * 8 + TC_NBAR * 8 + 64;
-constexpr int tc_smem_bytes(int w_slots) {      // + alignment slack before s_a and before the rings
-  return TC_SMEM_FIXED + 2 * w_slots * TC_IMG + 2 * 1024;
+constexpr int tc_smem_bytes(int w_slots, int a_stages) {      // + alignment slack before s_a and before the rings
+  return TC_SMEM_FIXED + a_stages * TC_STAGE_BYTES + 2 * w_slots * TC_IMG + 2 * 1024;
 }
+static_assert(tc_smem_bytes(2, TC_A_STAGES_MAX) <= 227 * 1024 && tc_smem_bytes(TC_W_SLOTS_MAX, 2) <= 227 * 1024, "shared memory");
 constexpr int TC_TMEM_COLS = 512;     // X0 | X1 | X2 | Y, 128 columns each
 constexpr uint32_t TC_Y_COL = TC_X_SLOTS * 128;
 constexpr int TC_MAX_KB = 8;
@@ -77,6 +81,16 @@ struct KbDesc {
   int32_t kvalid;     // valid columns in this k-block (<= 64)
   int32_t seg;        // segment number (index slot)
   int32_t vec;        // 16-byte vector loads are legal
+  int32_t tma;        // 1: GATHER k-block staged by TMA gather4 from the segment's split shadow (tm_seg[seg])
+  int32_t lo_col;     // tma: column offset of the lo parts inside a shadow row (= ld of the fp32 source)
+};
+
+// fast final epilogue (template EPI = 1): what leaves the CTA and how
+enum {
+  EPI_ST_RAW = 1,    // staging = out          -> TMA store to tm_raw
+  EPI_RED_SUM = 2,   // staging = out          -> TMA reduce-add into tm_sum (residual == out_sum, updated in place)
+  EPI_LDRES = 4,     // staging = out + residual (loaded thread-per-row) -> TMA store to tm_sum
+  EPI_SPLIT = 8,     // 16-bit split shadow of out (or of out + residual with EPI_LDRES) -> out_split
 };
 
 struct TcParams {
@@ -90,6 +104,12 @@ struct TcParams {
   uint32_t w3_block_bytes;  // bytes of one packed layer-3 k-block
   int64_t direct_tile_bytes;   // bytes of one tile's rows of a contiguous DIRECT segment 0 (0: no L2 prefetch)
   KbDesc kb[TC_MAX_KB];
+  int a_stages;  // stages of the A ring (2 | 3)
+  int epi;       // EPI_* bits (kernels instantiated with EPI = 1)
+  int n_tma;     // k-blocks staged by TMA
+  alignas(64) CUtensorMap tm_seg[3];   // split shadows of the gathered segments ([src_rows, 2 * ld] 16-bit, box 64 x 1)
+  alignas(64) CUtensorMap tm_raw;      // out_raw / out_sum as [rows, 128] fp32, box 16 x 32, SWIZZLE_64B
+  alignas(64) CUtensorMap tm_sum;
 };
 
 // Diagnostic cycle counters of CTA 0 (role wait times), read back with gnnfd_tc_profile_read; only
@@ -233,20 +253,21 @@ __device__ __forceinline__ void tc_store_block(uint32_t sA, const float4 (&v)[8]
 }
 
 // -------------------------------------------------------------------------------------- kernel
-template <bool FP16, int NA, int NW, bool BWD>
+template <bool FP16, int NA, int NW, bool BWD, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const gnnfd_mlp_args &a = p.a;
+  const int a_stages = p.a_stages;
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *s_a = smem;                                     // A ring
-  float *s_stg = (float *)(s_a + TC_A_BYTES);              // output staging, one swizzled 32x16 block per epilogue warp
+  float *s_stg = (float *)(s_a + a_stages * TC_STAGE_BYTES);   // output staging, one swizzled 32x16 block per epilogue warp
   int32_t *s_idx = (int32_t *)((uint8_t *)s_stg + TC_STG_BYTES);   // [4 tiles][3 seg][3][128]
   float *s_vec = (float *)(s_idx + TC_IDX_SLOTS * TC_IDX_SLOT);    // b1, b2, b3, ln_w, ln_b
   float2 *s_stat = (float2 *)(s_vec + 5 * TC_H);                   // LayerNorm partials [2 slots][2 halves][128 rows]
   uint64_t *s_bar = (uint64_t *)(s_stat + 4 * TC_BM);
-  uint64_t *a_full = s_bar, *a_empty = s_bar + 2, *w_full = s_bar + 4, *w_empty = s_bar + 7;
-  uint64_t *w23_full = s_bar + 10, *w23_empty = s_bar + 13;
-  uint64_t *acc_full = s_bar + 16, *acc_free = s_bar + 19, *hid_ready = s_bar + 22;   // hid_ready[x_slot*2 + half]
+  uint64_t *a_full = s_bar, *a_empty = s_bar + 3, *w_full = s_bar + 6, *w_empty = s_bar + 9;
+  uint64_t *w23_full = s_bar + 12, *w23_empty = s_bar + 15;
+  uint64_t *acc_full = s_bar + 18, *acc_free = s_bar + 21, *hid_ready = s_bar + 24;   // hid_ready[x_slot*2 + half]
   uint32_t *s_tmem = (uint32_t *)(s_bar + TC_NBAR);
   const int w_slots = p.w_slots;
   uint8_t *s_w = (uint8_t *)(((uintptr_t)(s_tmem + 16) + 1023) & ~(uintptr_t)1023);   // layer-1 W ring
@@ -255,7 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < TC_A_STAGES; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < TC_A_STAGES_MAX; ++i) { mbar_init(&a_full[i], TC_PROD_WARPS); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < TC_W_SLOTS_MAX; ++i) {
       mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1);
       mbar_init(&w23_full[i], 1); mbar_init(&w23_empty[i], 1);
@@ -272,6 +293,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     s_vec[i] = (src && c < n) ? __ldg(src + c) : (v == 3 ? 1.f : 0.f);
   }
   if (warp == TC_MMA_WARP) tmem_alloc(s_tmem, TC_TMEM_COLS);
+  if (tid == 32) {
+    for (int i = 0; i < a.n_seg; ++i)
+      if (a.seg[i].split != nullptr) prefetch_tmap(&p.tm_seg[i]);
+    if (EPI == 1) { prefetch_tmap(&p.tm_raw); prefetch_tmap(&p.tm_sum); }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -288,7 +314,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // forward: the gather path wants the registers (72 -> 88); backward chain: the hidden epilogues (saved
     // pre-activation prefetch) want them more than the contiguous dA loads do, so the producers stay at 72 there
     // (measured: edge forward 163 us with 72/88 vs 185 us with 80/72; dgrad chain 242 us with 80/72 vs 253 us)
-    if (!BWD) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    // (launches whose gathers are staged by TMA leave the registers to the epilogue instead: the producers then only
+    //  load the contiguous DIRECT segment)
+    if (!BWD && !(EPI == 1 && p.n_tma > 0)) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int pt = tid - TC_EPI_THREADS;   // 0..255
     const int f4 = pt & 15;                // float4 column inside the 64-wide k-block
     const int rbase = pt >> 4;             // rows rbase + 16 j
@@ -331,6 +359,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #if GNNFD_ABL == 2 || GNNFD_ABL == 3   // ablation: no global loads in the producers
       return;
 #endif
+      while (ij < T && p.kb[ikb].tma) {   // TMA-staged k-blocks have no register stage: skip to the next loaded one
+        if (++ikb == p.kb1) { ikb = 0; ++ij; }
+      }
       if (ij < T) {
         tc_load_block(p, s_idx + (ij & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT, tile_row0(ij), ikb, rbase, f4, v);
         if (++ikb == p.kb1) { ikb = 0; ++ij; }
@@ -347,13 +378,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         stage_idx(sj + 3);
       }
       PROF_WAIT(0, mbar_wait(&a_empty[st], sphase));
+      const KbDesc &dk = p.kb[skb];
+      if (dk.tma) {
+        // TMA gather: 2 parts x 32 groups of 4 rows = 64 gather4 copies per k-block, 8 per producer warp (lanes 0-7):
+        // warp pw stages part pw >> 2, row groups (pw & 3) * 8 + lane, straight into the SWIZZLE_128B A image (the
+        // tensor map carries the same swizzle; the image is 1024 B aligned and a row group is 4 x 128 B).  Each warp
+        // announces its own 8 x 512 B on the stage's barrier, which is also its arrival.
+        const int pw = warp - TC_EPI_WARPS;
+        if (lane == 0) mbar_expect_tx(&a_full[st], 8 * 512);
+        __syncwarp();
+        if (lane < 8) {
+          const int part = pw >> 2, rg = (pw & 3) * 8 + lane;
+          const int32_t *ixs = s_idx + (sj & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT + dk.seg * 3 * TC_BM + rg * 4;
+          const int4 ix = lds_s32x4(smem_u32(ixs));
+          tma_gather4(sa_u32 + st * TC_STAGE_BYTES + part * TC_IMG + rg * 512, &p.tm_seg[dk.seg],
+                      dk.colk + part * dk.lo_col, ix.x, ix.y, ix.z, ix.w, &a_full[st]);
+        }
+        if (++skb == p.kb1) { skb = 0; ++sj; }
+        if (++st == a_stages) { st = 0; sphase ^= 1; }
+        return;
+      }
       const int ksteps = (skb == p.kb1 - 1) ? p.ksteps1 : 4;
 #if GNNFD_ABL != 3        // ablation 3: no conversion / shared-memory stores either
-      PROF_WAIT(1, (tc_store_block<FP16, NA>(sa_u32 + st * 2 * TC_IMG, v, off0, f4 * 4 < ksteps * 16)));
+      PROF_WAIT(1, (tc_store_block<FP16, NA>(sa_u32 + st * TC_STAGE_BYTES, v, off0, f4 * 4 < ksteps * 16)));
 #endif
       PROF_WAIT(2, fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(&a_full[st]));
       if (++skb == p.kb1) { skb = 0; ++sj; }
-      if (++st == TC_A_STAGES) { st = 0; sphase ^= 1; }
+      if (++st == a_stages) { st = 0; sphase ^= 1; }
       PROF_WAIT(3, issue(v));
     };
 
@@ -443,7 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           PROF_WAIT(4, mbar_wait(&a_full[st], a_round & 1));
           tc_fence_after();
           const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
-          const uint64_t ah = make_desc(smem_u32(s_a + st * 2 * TC_IMG)), al = ah + (TC_IMG >> 4);
+          const uint64_t ah = make_desc(smem_u32(s_a + st * TC_STAGE_BYTES)), al = ah + (TC_IMG >> 4);
           int slot;
           uint64_t wb = w_acquire(slot);
 #if GNNFD_ABL != 4
@@ -461,7 +512,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             umma_commit(&w_empty[slot]);
           }
           umma_commit(&a_empty[st]);
-          if (++st == TC_A_STAGES) { st = 0; ++a_round; }
+          if (++st == a_stages) { st = 0; ++a_round; }
         }
         umma_commit(&acc_full[xs]);
       }
@@ -532,7 +583,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // warp = (tile group grp, column half eh, lane quarter q4): thread = row, 64 of the 128 columns of every tile of its
     // group; half eh of a hidden layer's output is exactly k-block eh of the next layer's operand.  All TMEM traffic is
     // in 16-column groups: 16 fp32 accumulator columns are replaced in place by 8 columns of hi pairs + 8 of lo pairs.
-    if (BWD) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    if (BWD || (EPI == 1 && p.n_tma > 0)) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     const int grp = warp >> 3, q4 = warp & 3, eh = (warp >> 2) & 1;
     const int erow = q4 * 32 + lane;                       // row of the tile owned by this thread
     const uint32_t stg = smem_u32(s_stg + warp * (32 * 16));   // this warp's 32 x 16 staging block (XOR-swizzled)
@@ -548,7 +599,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       for (int layer = 0; layer < p.nl - 1; ++layer) {
         const uint32_t reg = layer == 0 ? xr : yr;
         const uint32_t bias = vec + (layer * TC_H + eh * 64) * 4;
-        float *save = layer == 0 ? a.save_a1 : a.save_a2;
+        float *save = EPI == 1 ? nullptr : (layer == 0 ? a.save_a1 : a.save_a2);   // EPI 1: no training stash
         if (save != nullptr) save = (row0 + erow < a.rows) ? save + (size_t)(row0 + erow) * TC_H + eh * 64 : nullptr;
         // backward chain: the saved pre-activation of this layer (rows past the end read row 0; never stored),
         // fetched one 16-column group ahead of its use
@@ -612,6 +663,104 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       // ---- final epilogue
       PROF_WAIT(1, mbar_wait(&acc_full[xs], (p.nl * n + p.nl - 1) & 1));
       tc_fence_after();
+      if constexpr (EPI == 1) {
+        // ---- fast final epilogue (inference: no stash, no mul, n_out = 128).  Thread = row: bias -> LayerNorm -> affine in
+        // registers, the 32 x 16 block of the warp staged in the SWIZZLE_64B layout and written by ONE TMA tensor store
+        // (or reduce-add: the residual add is then done by the memory system and the residual never enters the SM).
+        const int epi = p.epi;
+        float mean = 0.f, rstd = 1.f;
+        if (a.has_ln) {
+          float shift = 0.f, s4[4] = {0.f, 0.f, 0.f, 0.f}, q4s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float acc[16];
+            tmem_ld16(xr + c * 16, acc);
+            const uint32_t b3 = vec + (2 * TC_H + eh * 64 + c * 16) * 4;
+            if (c == 0) shift = acc[0] + lds_f4(b3).x;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = lds_f4(b3 + i * 4);
+              const float d0 = acc[i] + (b4.x - shift), d1 = acc[i + 1] + (b4.y - shift);
+              const float d2 = acc[i + 2] + (b4.z - shift), d3 = acc[i + 3] + (b4.w - shift);
+              s4[0] += d0; s4[1] += d1; s4[2] += d2; s4[3] += d3;
+              q4s[0] = fmaf(d0, d0, q4s[0]); q4s[1] = fmaf(d1, d1, q4s[1]);
+              q4s[2] = fmaf(d2, d2, q4s[2]); q4s[3] = fmaf(d3, d3, q4s[3]);
+            }
+          }
+          const float sh = (s4[0] + s4[1]) + (s4[2] + s4[3]), qh = (q4s[0] + q4s[1]) + (q4s[2] + q4s[3]);
+          const float md = sh * (1.0f / 64.0f);
+          const float mean_h = shift + md, m2_h = fmaxf(qh - sh * md, 0.f);
+          sts_f2(stat + ((grp * 2 + eh) * TC_BM + erow) * 8, make_float2(mean_h, m2_h));
+          named_bar_sync(2 + grp * 4 + q4, 64);         // the two warps that share these 32 rows of this tile
+          const float2 o = lds_f2(stat + ((grp * 2 + (eh ^ 1)) * TC_BM + erow) * 8);
+          const float dm = mean_h - o.x;
+          mean = 0.5f * (mean_h + o.x);
+          rstd = rsqrtf((m2_h + o.y + dm * dm * 32.0f) * (1.0f / TC_H) + a.ln_eps);
+        }
+        const float nmr = -mean * rstd;
+        const int64_t grow = row0 + erow;
+        const int64_t lrow = grow < a.rows ? grow : a.rows - 1;      // clamped (valid) row for loads
+        const int trow = (int)(row0 + q4 * 32);                      // first row of this warp's block
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int col0 = eh * 64 + c * 16;
+          float4 res[4];
+          if (epi & EPI_LDRES) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) res[i] = ldg_f4(a.residual + (size_t)lrow * TC_H + col0 + i * 4);
+          }
+          float acc[16];
+          tmem_ld16(xr + c * 16, acc);
+          if (c == 3) {   // last TMEM read of this tile: the slot may be overwritten by the next L1
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_free[xs]);
+          }
+          const uint32_t b3 = vec + (2 * TC_H + col0) * 4, lw = vec + (3 * TC_H + col0) * 4, lb = vec + (4 * TC_H + col0) * 4;
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = lds_f4(b3 + i * 16), w4 = lds_f4(lw + i * 16), g4 = lds_f4(lb + i * 16);
+            o[4 * i] = fmaf(fmaf(acc[4 * i] + b4.x, rstd, nmr), w4.x, g4.x);
+            o[4 * i + 1] = fmaf(fmaf(acc[4 * i + 1] + b4.y, rstd, nmr), w4.y, g4.y);
+            o[4 * i + 2] = fmaf(fmaf(acc[4 * i + 2] + b4.z, rstd, nmr), w4.z, g4.z);
+            o[4 * i + 3] = fmaf(fmaf(acc[4 * i + 3] + b4.w, rstd, nmr), w4.w, g4.w);
+          }
+          if (epi & EPI_LDRES) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              o[4 * i] += res[i].x; o[4 * i + 1] += res[i].y; o[4 * i + 2] += res[i].z; o[4 * i + 3] += res[i].w;
+            }
+          }
+          if ((epi & EPI_SPLIT) && grow < a.rows) {   // 16-bit hi | lo shadow for the next block's TMA gathers
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split2<FP16>(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+            uint16_t *sp = (uint16_t *)a.out_split + (size_t)grow * (2 * TC_H) + col0;
+            *reinterpret_cast<uint4 *>(sp) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(sp + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4 *>(sp + TC_H) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4 *>(sp + TC_H + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+          if (epi & (EPI_ST_RAW | EPI_RED_SUM | EPI_LDRES)) {
+            // the previous group's TMA copy must have finished READING the staging block before it is overwritten
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              sts_f4(stg + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4,
+                     make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (epi & EPI_ST_RAW) tma_store_2d(&p.tm_raw, stg, col0, trow);
+              if (epi & EPI_RED_SUM) tma_reduce_add_2d(&p.tm_sum, stg, col0, trow);
+              if (epi & EPI_LDRES) tma_store_2d(&p.tm_sum, stg, col0, trow);
+              bulk_commit();
+            }
+          }
+        }
+      } else
 #if GNNFD_ABL == 7
       if (true) { __syncwarp(); if (lane == 0) mbar_arrive(&acc_free[xs]); } else
 #endif
@@ -740,6 +889,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         }
       }
     }
+    if (EPI == 1 && lane == 0) bulk_wait0();      // all TMA stores of this warp have completed
 #ifdef GNNFD_TC_PROF
     if (blockIdx.x == 0 && tid == 0) {
       g_tc_prof[8] = clock64() - t_begin;
@@ -869,6 +1019,38 @@ int pack_mlp_tc(const gnnfd_mlp_args *a, void *packed_out, cudaStream_t stream) 
   return GNNFD_OK;
 }
 
+// ------------------------------------------------------------------------------------ tensor maps
+// cuTensorMapEncodeTiled is a pure host-side encoder in libcuda; it is resolved through the runtime so the library
+// keeps linking against cudart only.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void *ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+// 2-D row-major tensor [outer, inner] of `esize`-byte elements, row stride `stride_bytes`, box [box_outer, box_inner]
+static int make_tmap_2d(CUtensorMap *m, CUtensorMapDataType dt, const void *base, uint64_t inner, uint64_t outer,
+                        uint64_t stride_bytes, uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return GNNFD_E_CUDA; }
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {stride_bytes};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return GNNFD_E_CUDA; }
+  return GNNFD_OK;
+}
+
 int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   TcMode m;
   if (!tc_mode(a->precision, m)) { set_error("mlp_forward_tc: bad precision"); return GNNFD_E_BADARG; }
@@ -896,6 +1078,54 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
     d.kvalid = sg.width - kloc < TC_KB ? sg.width - kloc : TC_KB;
     d.vec = ((sg.ld & 3) == 0) && ((d.colk & 3) == 0) && ((d.kvalid & 3) == 0) &&
             ((reinterpret_cast<uintptr_t>(sg.src) & 15) == 0);
+    // gathered k-block with a split shadow of its source: staged by TMA gather4 (split precisions, full k-blocks)
+    d.tma = (sg.mode == GNNFD_SEG_GATHER && sg.split != nullptr && m.na == 2 && d.kvalid == TC_KB && a->peer_shift == 0 &&
+             (sg.ld % TC_KB) == 0 && sg.src_rows > 0 && (reinterpret_cast<uintptr_t>(sg.split) & 15) == 0) ? 1 : 0;
+    d.lo_col = sg.ld;
+    p.n_tma += d.tma;
+    if (sg.split != nullptr && (const void *)sg.src == sg.split && !d.tma) {
+      set_error("mlp_forward_tc: segment %d exists only as a split shadow but cannot be staged by TMA here", seg);
+      return GNNFD_E_UNSUPPORTED;
+    }
+  }
+  for (int s = 0; s < a->n_seg && p.n_tma > 0; ++s) {
+    const gnnfd_segment &sg = a->seg[s];
+    bool used = false;
+    for (int kb = 0; kb < p.kb1; ++kb) used |= p.kb[kb].tma && p.kb[kb].seg == s;
+    if (!used) continue;
+    const int rc = make_tmap_2d(&p.tm_seg[s], m.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                sg.split, (uint64_t)2 * sg.ld, (uint64_t)sg.src_rows, (uint64_t)4 * sg.ld, TC_KB, 1,
+                                CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != GNNFD_OK) return rc;
+  }
+  p.a_stages = p.n_tma > 0 ? 3 : 2;
+  // fast final epilogue (TMA tensor stores) whenever the call is plain inference on 128 outputs
+  const bool fast = !a->bwd_chain && p.nl == 3 && a->n_out == TC_H && a->mul == nullptr && a->save_a1 == nullptr &&
+                    a->save_a2 == nullptr && a->save_xhat == nullptr && a->save_rstd == nullptr && m.na == 2 && m.nw == 2 &&
+                    (a->out_raw != nullptr || a->out_sum != nullptr || a->out_split != nullptr) &&
+                    !(a->out_raw != nullptr && a->out_sum != nullptr && (a->residual != a->out_sum || a->split_of_sum)) &&
+                    (a->out_sum == nullptr || a->residual != nullptr) &&
+                    ((reinterpret_cast<uintptr_t>(a->out_raw) | reinterpret_cast<uintptr_t>(a->out_sum) |
+                      reinterpret_cast<uintptr_t>(a->out_split) | reinterpret_cast<uintptr_t>(a->residual)) & 15) == 0;
+  if (a->out_split != nullptr && !fast) {
+    set_error("mlp_forward_tc: out_split needs the inference epilogue (n_out = 128, split precision, no stash / mul)");
+    return GNNFD_E_UNSUPPORTED;
+  }
+  if (fast && a->rows > 0) {
+    if (a->out_sum != nullptr) {
+      const bool in_regs = a->residual != a->out_sum || (a->out_split != nullptr && a->split_of_sum);
+      p.epi |= in_regs ? EPI_LDRES : EPI_RED_SUM;
+      const int rc = make_tmap_2d(&p.tm_sum, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a->out_sum, TC_H, (uint64_t)a->rows,
+                                  TC_H * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != GNNFD_OK) return rc;
+    }
+    if (a->out_raw != nullptr) {
+      p.epi |= EPI_ST_RAW;
+      const int rc = make_tmap_2d(&p.tm_raw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a->out_raw, TC_H, (uint64_t)a->rows,
+                                  TC_H * 4, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != GNNFD_OK) return rc;
+    }
+    if (a->out_split != nullptr) p.epi |= EPI_SPLIT;
   }
   {
     const gnnfd_segment &s0 = a->seg[0];
@@ -907,21 +1137,24 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   const int64_t n_tiles = (a->rows + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   p.w_slots = n_tiles <= 2 * (int64_t)num_sms() ? TC_W_SLOTS_MAX : 2;
-#define LAUNCH1(FP, NA_, NW_, BW)                                                                         \
+#define LAUNCH1(FP, NA_, NW_, BW, EP)                                                                     \
   do {                                                                                                    \
-    static bool attr[GNNFD_MAX_DEVICES] = {false};                                                                             \
-    if (!attr[current_device()]) {                                                                                          \
-      GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_, BW>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                      tc_smem_bytes(TC_W_SLOTS_MAX)));                                    \
-      attr[current_device()] = true;                                                                                        \
+    static bool attr[GNNFD_MAX_DEVICES] = {false};                                                        \
+    if (!attr[current_device()]) {                                                                        \
+      GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_, BW, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      227 * 1024));                                                       \
+      attr[current_device()] = true;                                                                      \
     }                                                                                                     \
-    mlp_tc_kernel<FP, NA_, NW_, BW><<<grid, TC_THREADS, tc_smem_bytes(p.w_slots), stream>>>(p);           \
+    mlp_tc_kernel<FP, NA_, NW_, BW, EP><<<grid, TC_THREADS, tc_smem_bytes(p.w_slots, p.a_stages), stream>>>(p);   \
   } while (0)
 #define LAUNCH(FP, NA_, NW_)                                                                              \
   do {                                                                                                    \
-    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true); else LAUNCH1(FP, NA_, NW_, false);                     \
+    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true, 0); else LAUNCH1(FP, NA_, NW_, false, 0);               \
   } while (0)
-  if (!m.fp16 && m.na == 2 && m.nw == 2) LAUNCH(false, 2, 2);
+  if (p.a_stages == 3) p.w_slots = 2;      // 3 A stages + 3-slot weight rings do not fit in 227 KB
+  if (fast && !m.fp16) LAUNCH1(false, 2, 2, false, 1);
+  else if (fast) LAUNCH1(true, 2, 2, false, 1);
+  else if (!m.fp16 && m.na == 2 && m.nw == 2) LAUNCH(false, 2, 2);
   else if (!m.fp16 && m.na == 1) LAUNCH(false, 1, 1);
   else if (m.fp16 && m.nw == 1) LAUNCH(true, 2, 1);
   else LAUNCH(true, 2, 2);

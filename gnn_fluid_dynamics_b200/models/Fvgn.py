@@ -74,8 +74,8 @@ class FvgnA(Model):
             from ..training import encode_process_decode_train
             return None, None, encode_process_decode_train(self.training_plan(), topo, prec, c_x, f_x)
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
-        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
-        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook)
+        x, fast = P.encode_cells(self.encoder.cell_mlp, c_x, prec, self.family, self.processer_list, topo.n_cells)
+        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook, fast=fast)
         return x, e, P.mlp_rows(self.decoder.face_mlp, e, prec)
 
     def forward(self, graphs, mode="rollout"):   # Fvgn.py:150-174
@@ -368,8 +368,8 @@ class FvgnC(FvgnA):
     def encode_process_decode(self, c_x, f_x, topo, hook=None):
         prec = self.prec
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
-        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
-        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook)
+        x, fast = P.encode_cells(self.encoder.cell_mlp, c_x, prec, self.family, self.processer_list, topo.n_cells)
+        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook, fast=fast)
         n_out = self.output_sizes[1]
         if n_out <= 16:                       # narrow-head path of the fused kernel
             out = P.mlp_rows(self.decoder.face_mlp, e, prec)

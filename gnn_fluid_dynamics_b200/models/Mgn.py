@@ -55,8 +55,8 @@ class MgnA(Model):
             from ..training import encode_process_decode_train
             return None, None, encode_process_decode_train(self.training_plan(), topo, prec, c_x, f_x)
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
-        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
-        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook)
+        x, fast = P.encode_cells(self.encoder.cell_mlp, c_x, prec, self.family, self.processer_list, topo.n_cells)
+        x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook, fast=fast)
         return x, e, P.mlp_rows(self.decoder.face_mlp, x, prec)
 
     def forward(self, graphs, mode="train"):   # Mgn.py:153-173

@@ -40,6 +40,21 @@ class VertPotA(FluxA):
         kinds, inputs, outputs = super().normalisation_tables()
         return kinds, inputs, outputs + [(0, col(2, 5), "face_flux")]
 
+    def loss(self, output, graphs):   # VertPot.py:152-186 (continuity on the cell fluxes; no interior mask on faces)
+        c_graph, f_graph, v_graph = graphs
+        lf = self.loss_func
+        cf = output["cell_flux"]
+        div = (cf[:, 0] + cf[:, 1] + cf[:, 2]).unsqueeze(-1)                      # fvm.py:13-19
+        continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
+        cvc = lf(output["cell_velocity_change"], c_graph.y, None, c_graph.batch)
+        fvl = lf(output["face_velocity"], f_graph.y[:, 0:2], None, f_graph.batch)
+        fpl = lf(output["face_pressure"], f_graph.y[:, 2:3], None, f_graph.batch)
+        w = self.config.training.loss_weights
+        total = (w["continuity"] * continuity + w["cell_velocity_change"] * cvc + w["face_velocity"] * fvl
+                 + w["face_pressure"] * fpl)
+        return {"total_log_loss": torch.mean(torch.log(total)), "continuity_loss": continuity,
+                "cell_velocity_change_loss": cvc, "face_velocity_loss": fvl, "face_pressure_loss": fpl}
+
     def training_plan(self):
         from ..training import Plan, Site
         plan = getattr(self, "_gnnfd_plan", None)
@@ -57,8 +72,8 @@ class VertPotA(FluxA):
             edge_out, vertex_out = encode_process_decode_train(self.training_plan(), topo, prec, c_x, f_x)
             return None, None, None, edge_out, vertex_out
         e = P.mlp_rows(self.encoder.face_mlp, f_x, prec)
-        x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
-        x, e, vx = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook)
+        x, fast = P.encode_cells(self.encoder.cell_mlp, c_x, prec, self.family, self.processer_list, topo.n_cells)
+        x, e, vx = P.run_processor(self.family, self.processer_list, x, e, topo, prec, hook=hook, fast=fast)
         edge_out = P.mlp_rows(self.decoder.edge_mlp, e, prec)
         vertex_out = P.mlp_rows(self.decoder.vertex_mlp, vx, prec)
         return x, e, vx, edge_out, vertex_out

@@ -102,6 +102,16 @@ class Seg:
     idx: Sequence[torch.Tensor] = ()
     col: int = 0
     width: Optional[int] = None
+    split: Optional[torch.Tensor] = None   # 16-bit hi|lo shadow of src ([rows, 2 * ld]) written by mlp_forward(out_split=...)
+
+
+def split_dtype(precision: int):
+    """Element type of the split shadow for a tensor-core precision (None: the precision has no split operands)."""
+    if precision == _lib.PREC_BF16X3:
+        return torch.bfloat16
+    if precision == _lib.PREC_FP16X3:
+        return torch.float16
+    return None
 
 
 @dataclass
@@ -149,6 +159,16 @@ def _fill_args(args: MlpArgs, segs: Sequence[Seg], w: MLPWeights, rows: int, pre
             else:
                 sg.idx[j] = None
         sg.ld, sg.col, sg.width, sg.mode = src.stride(0), s.col, width, s.mode
+        sg.src_rows = src.shape[0]
+        sg.split = None
+        if s.split is not None and split_dtype(precision) is not None:
+            sp = s.split
+            if not (sp.is_cuda and sp.dtype == split_dtype(precision) and sp.is_contiguous()
+                    and tuple(sp.shape) == (src.shape[0], 2 * src.stride(0))):
+                raise RuntimeError(f"seg[{i}].split: expected a contiguous {split_dtype(precision)} [{src.shape[0]}, "
+                                   f"{2 * src.stride(0)}] CUDA tensor, got {sp.dtype} {tuple(sp.shape)}")
+            sg.split = sp.data_ptr()
+            keep.append(sp)
         k += width
         keep.append(src)
     args.k_in, args.hidden, args.n_out = k, w.w2.shape[0], w.w3.shape[0]
@@ -183,9 +203,15 @@ def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = 
                 mul: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
                 want_raw: bool = True, want_sum: bool = False,
                 out_raw: Optional[torch.Tensor] = None, out_sum: Optional[torch.Tensor] = None,
-                stash: bool = False, peer: Optional[tuple] = None):
+                stash: bool = False, peer: Optional[tuple] = None,
+                out_split: Optional[torch.Tensor] = None, split_of_sum: bool = False):
     """Run the fused block; returns (out_raw or None, out_sum or None) and, with ``stash=True``
-    (training), additionally the ``MLPStash`` the backward consumes."""
+    (training), additionally the ``MLPStash`` the backward consumes.
+
+    ``out_sum`` may be ``residual`` itself: the residual stream is then updated in place (the fast inference path - the
+    add is done by the TMA store).  ``out_split`` [rows, 256] (``split_dtype(precision)``) receives the 16-bit hi|lo
+    shadow of the raw output (or of the sum with ``split_of_sum``) that the next block's gathers consume through
+    ``Seg.split``."""
     args = MlpArgs()
     keep = _fill_args(args, segs, w, rows, precision)
     n_out = w.w3.shape[0]
@@ -205,6 +231,11 @@ def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = 
     args.residual = _ptr(_req(residual, torch.float32, "residual")) if residual is not None else None
     args.out_raw = _ptr(out_raw) if want_raw else None
     args.out_sum = _ptr(out_sum) if want_sum else None
+    if out_split is not None:
+        if not (out_split.is_cuda and out_split.dtype == split_dtype(precision) and out_split.is_contiguous()
+                and tuple(out_split.shape) == (rows, 2 * n_out)):
+            raise RuntimeError(f"out_split: expected a contiguous {split_dtype(precision)} [{rows}, {2 * n_out}] CUDA tensor")
+        args.out_split, args.split_of_sum = out_split.data_ptr(), int(split_of_sum)
     if peer is not None:          # (peer matrices, shift): GATHER indices are (peer << shift) | row
         bases, shift = peer
         for i, t in enumerate(bases):

@@ -12,6 +12,11 @@ their block order follow SURVEY.md section 8a:
 
 The second sub-block consumes the first one's RAW output; both residuals are applied by the
 kernels' epilogues (out_sum = residual + out), so no clone / add pass exists.
+
+Inference (no gradient recorded, split tensor-core precision) runs the same data-flows in ``Fast`` mode: the residual
+streams x / e are updated IN PLACE (the add is done by the epilogue's TMA reduce-store) and the matrix the edge block
+gathers (x' for the fvgn order, x for the mgn order) is handed over as a 16-bit hi|lo split shadow written by the node
+block's epilogue, which the edge kernel stages with TMA gather4 - the fp32 copy of x' is never written.
 """
 from __future__ import annotations
 
@@ -59,21 +64,53 @@ def weights_of(seq: torch.nn.Module, act: int = ACT_SILU) -> MLPWeights:
 
 # --- sub-blocks -----------------------------------------------------------------------------------
 
+class Fast:
+    """Per-processor-run scratch of the inference fast path: the split shadow of the gathered cell matrix."""
+
+    def __init__(self, n_cells: int, prec: int, device):
+        self.dtype = ops.split_dtype(prec)
+        self.xs = torch.empty(n_cells, 2 * H, dtype=self.dtype, device=device)
+
+    def gather_seg(self, idx) -> Seg:
+        """GATHER segment whose source exists ONLY as the split shadow (src aliases it: the C side then insists on the
+        TMA path instead of ever reading fp32 rows)."""
+        return Seg(self.xs.view(torch.float32), SEG_GATHER, (idx,), split=self.xs)
+
+
+def fast_mode(blocks, tensors, prec: int) -> bool:
+    """In-place residuals + split shadows are legal when nothing records a gradient and the precision has split
+    operands (bf16x3 / fp16x3)."""
+    if ops.split_dtype(prec) is None:
+        return False
+    if not torch.is_grad_enabled():
+        return True
+    return not (any(p.requires_grad for p in blocks.parameters()) or any(t.requires_grad for t in tensors))
+
+
 def vertex_half_sum(e: torch.Tensor, topo: MeshTopology) -> torch.Tensor:
     """vsum[V, H/2]: half 0 of each face latent onto its first vertex, half 1 onto its second
     (scatter_add of Fvgn.py:312-314) as a deterministic CSR segment sum."""
     return A.segment_sum(e, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices, topo.v0, topo.v1)
 
 
-def node_mlp_two_hop(seq, x, vsum, topo, prec, want_raw, residual=True):
-    """x' = cell_mlp(cat[x, (vsum[vf0]+vsum[vf1]+vsum[vf2])/3])  (Fvgn.py:316-323)."""
+def node_mlp_two_hop(seq, x, vsum, topo, prec, want_raw, residual=True, fast: Optional[Fast] = None,
+                     split_of_sum: bool = False):
+    """x' = cell_mlp(cat[x, (vsum[vf0]+vsum[vf1]+vsum[vf2])/3])  (Fvgn.py:316-323).  ``fast``: x is updated in place and
+    the shadow of x' (or of x + x') goes to ``fast.xs``."""
     segs = [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf)]
+    if fast is not None:
+        return A.mlp(seq, segs, x.shape[0], prec, residual=x, want_raw=want_raw, want_sum=True, inplace=True,
+                     out_split=fast.xs, split_of_sum=split_of_sum)
     return A.mlp(seq, segs, x.shape[0], prec, residual=x if residual else None,
                            want_raw=want_raw, want_sum=residual)
 
 
-def edge_mlp_concat(seq, e, x_src, topo, prec, want_raw, residual=True):
-    """e' = face_mlp(cat[e, x[row], x[col]])  (Fvgn.py:292-296, Mgn.py:234-238)."""
+def edge_mlp_concat(seq, e, x_src, topo, prec, want_raw, residual=True, fast: Optional[Fast] = None):
+    """e' = face_mlp(cat[e, x[row], x[col]])  (Fvgn.py:292-296, Mgn.py:234-238).  ``fast``: e is updated in place and
+    x[row] / x[col] are TMA-gathered from the split shadow ``fast.xs`` (``x_src`` is not read)."""
+    if fast is not None:
+        segs = [Seg(e), fast.gather_seg(topo.row), fast.gather_seg(topo.col)]
+        return A.mlp(seq, segs, e.shape[0], prec, residual=e, want_raw=want_raw, want_sum=True, inplace=True)
     segs = [Seg(e), Seg(x_src, SEG_GATHER, (topo.row,)), Seg(x_src, SEG_GATHER, (topo.col,))]
     return A.mlp(seq, segs, e.shape[0], prec, residual=e if residual else None,
                            want_raw=want_raw, want_sum=residual)
@@ -108,8 +145,23 @@ def mlp_rows(seq, src: torch.Tensor, prec: int, act: int = ACT_SILU) -> torch.Te
 
 
 def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
-             e_asym: Optional[torch.Tensor] = None, want_vertex: bool = False, e_keep: Optional[torch.Tensor] = None):
-    """One GN_Block -> (x_new, e_new, vertex_x or None)."""
+             e_asym: Optional[torch.Tensor] = None, want_vertex: bool = False, e_keep: Optional[torch.Tensor] = None,
+             fast: Optional[Fast] = None):
+    """One GN_Block -> (x_new, e_new, vertex_x or None).  With ``fast`` (inference) x / e are updated in place."""
+    if fast is not None and family in ("fvgn", "vertpot"):
+        vsum = vertex_half_sum(e, topo)
+        cell = block.cell_block.cell_mlp if family == "fvgn" else block.node_block.cell_mlp
+        face = block.face_block.face_mlp if family == "fvgn" else block.edge_block.face_mlp
+        node_mlp_two_hop(cell, x, vsum, topo, prec, want_raw=False, fast=fast)          # x += x', shadow of x'
+        e_raw, _ = edge_mlp_concat(face, e, None, topo, prec, want_raw=want_vertex, fast=fast)      # e += e'
+        vx = vertex_full_sum(e_raw, topo, x.shape[0]) if want_vertex else None
+        return x, e, vx
+    if fast is not None and family == "mgn":
+        # fast.xs holds the shadow of the block input x (encoder output, then every node block's x + x')
+        e_raw, _ = edge_mlp_concat(block.face_block.face_mlp, e, None, topo, prec, want_raw=True, fast=fast)
+        vsum = vertex_half_sum(e_raw, topo)
+        node_mlp_two_hop(block.cell_block.cell_mlp, x, vsum, topo, prec, want_raw=False, fast=fast, split_of_sum=True)
+        return x, e, None
     if family == "fvgn":
         vsum = vertex_half_sum(e, topo)
         x_raw, x_new = node_mlp_two_hop(block.cell_block.cell_mlp, x, vsum, topo, prec, want_raw=True)
@@ -194,17 +246,37 @@ def gn_block_dual_two_hop(block, x, e_s, e_a, topo: MeshTopology, prec: int = PR
     return x_new, s_new, a_new
 
 
-def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=None, hook=None, e_keep=None):
+def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=None, hook=None, e_keep=None,
+                  fast: Optional[Fast] = None):
     """All GN_Blocks.  VertPot's vertex sum is only live after the last block (VertPot.py:208: it is
-    overwritten every block and never fed back), so it is computed once."""
+    overwritten every block and never fed back), so it is computed once.
+
+    ``fast`` (see ``Fast`` / ``fast_mode``): x and e - the encoder outputs - are updated in place; for the mgn order
+    ``fast.xs`` must already hold the split shadow of x (``encode_cells``)."""
     vx = None
     n = len(blocks)
     for i, blk in enumerate(blocks):
         x, e, vx_i = gn_block(family, blk, x, e, topo, prec,
                               e_asym=e_asym if (family == "cons_a" and i == 0) else None,
-                              want_vertex=(family == "vertpot" and i == n - 1), e_keep=e_keep)
+                              want_vertex=(family == "vertpot" and i == n - 1), e_keep=e_keep, fast=fast)
         if vx_i is not None:
             vx = vx_i
         if hook is not None:
-            hook(i, x, e)
+            hook(i, x.clone(), e.clone()) if fast is not None else hook(i, x, e)
     return x, e, vx
+
+
+FAST_FAMILIES = ("fvgn", "vertpot", "mgn")
+
+
+def encode_cells(seq, c_x: torch.Tensor, prec: int, family: str, blocks, n_cells: int):
+    """Cell encoder + the fast-path decision for the processor that follows -> (x0, Fast or None).  For the mgn order
+    the encoder's epilogue also writes the split shadow of x0 that the first edge block gathers."""
+    fast = None
+    if family in FAST_FAMILIES and fast_mode(blocks, [c_x], prec) and c_x.shape[0] > 0:
+        fast = Fast(n_cells, prec, c_x.device)
+    src = c_x.contiguous()
+    if fast is not None and family == "mgn":
+        x0, _ = A.mlp(seq, [Seg(src)], src.shape[0], prec, out_split=fast.xs)
+        return x0, fast
+    return mlp_rows(seq, src, prec), fast

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 2
+#define GNNFD_ABI_VERSION 3
 
 enum {
   GNNFD_OK = 0,
@@ -66,6 +66,13 @@ typedef struct {
   int32_t col;           /* first source column */
   int32_t width;         /* number of K columns contributed */
   int32_t mode;          /* GNNFD_SEG_* */
+  /* Optional (GATHER segments, split tensor-core precisions): a 16-bit "split shadow" of src written by the
+   * gnnfd_mlp_forward call that produced src (its out_split): row r = [hi parts of src[r, 0:ld] | lo parts], 2 * ld
+   * 16-bit values (bf16 for BF16X3, fp16 for FP16X3), x = hi + lo.  With it the gathered k-blocks of layer 1 are staged
+   * by TMA (cp.async.bulk.tensor ... tile::gather4) straight into the UMMA shared-memory image: no load / convert /
+   * store work in the SM.  src_rows = number of rows of src (bounds of the TMA tensor map). */
+  const void *split;
+  int64_t src_rows;
 } gnnfd_segment;
 
 /*
@@ -133,6 +140,13 @@ typedef struct {
    * All peer matrices share the segment's ld / col.  Tensor-core precisions only. */
   const float *peer_base[8];
   int32_t peer_shift;
+  /* out_split (optional, n_out == 128, split precisions): [rows, 256] 16-bit split shadow (hi | lo, see
+   * gnnfd_segment.split) of out_raw (split_of_sum = 0) or of out_sum (split_of_sum = 1) - what the NEXT block's
+   * gathers consume.  out_raw itself may then be NULL: the fp32 copy is not needed by anybody in inference.
+   * residual == out_sum (the residual stream updated IN PLACE) is allowed and is the fast path: the add is done by
+   * the TMA store (cp.reduce.async.bulk.tensor .add) in L2 and the residual is never loaded by the SM. */
+  void *out_split;
+  int32_t split_of_sum;
 } gnnfd_mlp_args;
 
 int gnnfd_abi_version(void);

@@ -148,6 +148,68 @@ def test_fused_edge_and_node_blocks_vs_oracle():
         assert rel_l2(raw, ref) < TOL[prec] and rel_l2(summed, x + ref) < TOL[prec]
 
 
+def _split_shadow(t, dtype):
+    """hi | lo shadow of an fp32 matrix exactly as the kernels build it (round-to-nearest-even, lo = x - hi)."""
+    hi = t.to(dtype)
+    lo = (t - hi.float()).to(dtype)
+    return torch.cat([hi, lo], 1).contiguous()
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp16x3"])
+@pytest.mark.parametrize("E,N", [(1, 1), (33, 5), (1000, 700), (70001, 46000)])
+def test_inference_fast_path_tma_gather_and_tma_store(prec, E, N):
+    """The inference fast path of the fused block against the oracle AND against the register-staged path:
+    gathered k-blocks staged by TMA gather4 from the 16-bit split shadow, final epilogue through TMA tensor stores
+    (plain store, reduce-add into the in-place residual, load-add), the split shadow written by the epilogue.
+    Ragged row counts (last tile clipped by the tensor map)."""
+    from gnn_fluid_dynamics_b200 import ops, _lib
+    from gnn_fluid_dynamics_b200.precisions import available
+    if prec not in available():
+        pytest.skip(prec)
+    P_ = _lib.PRECISIONS[prec]
+    sdt = ops.split_dtype(P_)
+    g = torch.Generator().manual_seed(11)
+    x, e = torch.randn(N, 128, generator=g), torch.randn(E, 128, generator=g)
+    row, col = torch.randint(0, N, (E,), generator=g), torch.randint(0, N, (E,), generator=g)
+    i32 = lambda t: t.to(torch.int32).to(dev())
+    xd, ed = x.to(dev()), e.to(dev())
+    p = _rand_mlp(384, 128, True, seed=5)
+    w = _to_weights(p, 0)
+    ref = oracle.mlp3(torch.cat([e, x[row], x[col]], 1), p["w1"], p["b1"], p["w2"], p["b2"], p["w3"], p["b3"], p["ln_w"], p["ln_b"])
+    # register-staged gathers, separate output buffers (the pre-existing path)
+    segs = [ops.Seg(ed), ops.Seg(xd, _lib.SEG_GATHER, (i32(row),)), ops.Seg(xd, _lib.SEG_GATHER, (i32(col),))]
+    raw0, sum0 = ops.mlp_forward(segs, w, E, P_, residual=ed, want_raw=True, want_sum=True)
+    assert rel_l2(raw0, ref) < TOL[prec]
+    # TMA-gathered from the shadow (the fp32 x is not passed at all), in-place residual, raw + sum
+    xs = _split_shadow(xd, sdt)
+    fsegs = lambda e_buf: [ops.Seg(e_buf), ops.Seg(xs.view(torch.float32), _lib.SEG_GATHER, (i32(row),), split=xs),
+                           ops.Seg(xs.view(torch.float32), _lib.SEG_GATHER, (i32(col),), split=xs)]
+    e1 = ed.clone()
+    raw1, sum1 = ops.mlp_forward(fsegs(e1), w, E, P_, residual=e1, want_raw=True, want_sum=True, out_sum=e1)
+    assert sum1.data_ptr() == e1.data_ptr()
+    assert rel_l2(raw1, ref) < TOL[prec] and rel_l2(e1, e + ref) < TOL[prec]
+    assert rel_l2(raw1, raw0) < 2e-6 and rel_l2(e1, sum0) < 2e-6      # same operands; only the epilogue's rounding differs
+    # sum only, in place (reduce-add)
+    e2 = ed.clone()
+    ops.mlp_forward(fsegs(e2), w, E, P_, residual=e2, want_raw=False, want_sum=True, out_sum=e2)
+    assert torch.equal(e2, e1)
+    # sum only, separate buffer (load-add + plain store), with the split shadow of the SUM
+    e3 = ed.clone()
+    sh = torch.empty(E, 256, dtype=sdt, device=dev())
+    _, sum3 = ops.mlp_forward(fsegs(e3), w, E, P_, residual=e3, want_raw=False, want_sum=True, out_split=sh, split_of_sum=True)
+    assert torch.equal(e3, ed) and rel_l2(sum3, sum0) < 2e-6
+    assert torch.equal(sh, _split_shadow(sum3, sdt))
+    # shadow of the RAW output next to the in-place sum (the fvgn node block's hand-over), no fp32 raw written
+    e4 = ed.clone()
+    sh2 = torch.empty(E, 256, dtype=sdt, device=dev())
+    ops.mlp_forward(fsegs(e4), w, E, P_, residual=e4, want_raw=False, want_sum=True, out_sum=e4, out_split=sh2)
+    assert torch.equal(e4, e1) and torch.equal(sh2, _split_shadow(raw1, sdt))
+    # determinism
+    e5 = ed.clone()
+    ops.mlp_forward(fsegs(e5), w, E, P_, residual=e5, want_raw=False, want_sum=True, out_sum=e5)
+    assert torch.equal(e5, e2)
+
+
 # --------------------------------------------------------------------- processors vs golden + oracle
 def _run_processor(name, model, graphs_dev):
     from gnn_fluid_dynamics_b200.topology import get_topology
