@@ -27,6 +27,8 @@ EXPORTS = [
     "gnnfd_segment_sum3", "gnnfd_gather_pair_add", "gnnfd_struct_size",
     "gnnfd_mlp_backward_workspace_bytes", "gnnfd_pack_mlp_backward_bytes", "gnnfd_pack_mlp_backward",
     "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access", "gnnfd_gather_cols_add",
+    "gnnfd_glue_workspace_bytes", "gnnfd_face_area_norm", "gnnfd_face_area_norm_backward", "gnnfd_fvm_integrate",
+    "gnnfd_fvm_integrate_backward", "gnnfd_masked_mse", "gnnfd_masked_mse_backward", "gnnfd_state_advance",
 ]
 ABI_VERSION = 3
 
@@ -120,6 +122,17 @@ def _load():
     lib.gnnfd_pack_mlp_backward_bytes.restype = C.c_size_t
     lib.gnnfd_pack_mlp_backward.argtypes = [C.POINTER(MlpArgs), vp, i32, vp]
     lib.gnnfd_mlp_backward.argtypes = [C.POINTER(MlpBackwardArgs), vp]
+    sz = C.c_size_t
+    lib.gnnfd_glue_workspace_bytes.argtypes = []
+    lib.gnnfd_glue_workspace_bytes.restype = sz
+    lib.gnnfd_face_area_norm.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, i32, f32, f32, i32, vp, vp, vp, sz, vp]
+    lib.gnnfd_face_area_norm_backward.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, f32, vp, vp, vp, vp, sz, vp]
+    lib.gnnfd_fvm_integrate.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, f32, vp, vp, vp]
+    lib.gnnfd_fvm_integrate_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, f32, vp, vp, vp, i32, i32, vp, vp]
+    lib.gnnfd_masked_mse.argtypes = [vp, i32, vp, i32, vp, i64, i32, vp, vp, sz, vp]
+    lib.gnnfd_masked_mse_backward.argtypes = [vp, i32, vp, i32, vp, i64, i32, vp, vp, vp, i32, vp]
+    lib.gnnfd_state_advance.argtypes = [vp, i32, vp, i32, i32, i64, vp, i32, vp, vp, vp, vp, vp, i32, i64, vp, i32, vp, i32,
+                                        vp, vp, vp]
     for which, mirror in ((0, MlpArgs), (1, WgradArgs), (2, Segment), (3, MlpBackwardArgs)):
         if lib.gnnfd_struct_size(which) != C.sizeof(mirror):
             raise ImportError(f"{LIB_PATH}: struct {mirror.__name__} is {lib.gnnfd_struct_size(which)} bytes in the "

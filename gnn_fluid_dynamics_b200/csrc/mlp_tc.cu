@@ -19,6 +19,7 @@
 // (128 B per row), rows in groups of 8 (1024 B atoms), 16-byte chunk c of row r stored at chunk
 // c ^ (r & 7).  Weights are pre-packed by gnnfd_pack_mlp into exactly this image per (layer,
 // k-block, part), so one cp.async.bulk (TMA bulk copy, mbarrier complete_tx) lands a unit.
+#include <stdlib.h>
 #include <cuda.h>   // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
 
 #include "tc_common.cuh"
@@ -107,6 +108,7 @@ struct TcParams {
   int a_stages;  // stages of the A ring (2 | 3)
   int epi;       // EPI_* bits (kernels instantiated with EPI = 1)
   int n_tma;     // k-blocks staged by TMA
+  int l1_depth;  // layer-1 k-blocks whose MMAs may be queued in the tensor pipe at once (0 = unlimited)
   alignas(64) CUtensorMap tm_seg[3];   // split shadows of the gathered segments ([src_rows, 2 * ld] 16-bit, box 64 x 1)
   alignas(64) CUtensorMap tm_raw;      // out_raw / out_sum as [rows, 128] fp32, box 16 x 32, SWIZZLE_64B
   alignas(64) CUtensorMap tm_sum;
@@ -486,11 +488,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         if (++ws == w_slots) { ws = 0; ++w_round; }
         return make_desc(smem_u32(s_w + slot * TC_IMG));
       };
+      // The tensor pipe runs MMAs in issue order and layers 2 / 3 of the tiles ahead sit on the epilogue's critical path
+      // (and hold the single Y region): layer 1 therefore keeps at most l1_depth k-blocks of MMAs queued, so a layer-2 / 3
+      // k-block issued by the other issuer waits behind <= l1_depth x 12 MMAs instead of a whole tile's 72.
+      const int depth = p.l1_depth;
+      int pst = 0;               // stage of the k-block issued `depth` k-blocks ago
+      uint32_t p_round = 0, n_issued = 0;
       for (int j = 0; j < T; ++j) {
         const int xs = j % TC_X_SLOTS, n = j / TC_X_SLOTS;
         if (n >= 1) { PROF_WAIT(3, mbar_wait(&acc_free[xs], (n - 1) & 1)); tc_fence_after(); }
         const uint32_t d = tmem_base + xs * 128;
         for (int kb = 0; kb < p.kb1; ++kb) {
+          if (depth > 0 && n_issued >= (uint32_t)depth) {
+            mbar_wait(&a_empty[pst], p_round & 1);       // its MMAs have completed (commit on a_empty)
+            if (++pst == a_stages) { pst = 0; ++p_round; }
+          }
+          ++n_issued;
           PROF_WAIT(4, mbar_wait(&a_full[st], a_round & 1));
           tc_fence_after();
           const int ksteps = (kb == p.kb1 - 1) ? p.ksteps1 : 4;
@@ -1099,6 +1112,14 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
     if (rc != GNNFD_OK) return rc;
   }
   p.a_stages = p.n_tma > 0 ? 3 : 2;
+  {
+    static int depth = -1;      // experiment knob: GNNFD_L1_DEPTH (0 = unlimited)
+    if (depth < 0) {
+      const char *e = getenv("GNNFD_L1_DEPTH");
+      depth = e ? atoi(e) : 0;
+    }
+    p.l1_depth = depth;
+  }
   // fast final epilogue (TMA tensor stores) whenever the call is plain inference on 128 outputs
   const bool fast = !a->bwd_chain && p.nl == 3 && a->n_out == TC_H && a->mul == nullptr && a->save_a1 == nullptr &&
                     a->save_a2 == nullptr && a->save_xhat == nullptr && a->save_rstd == nullptr && m.na == 2 && m.nw == 2 &&

@@ -34,6 +34,7 @@ class PartState:
     x: Optional[torch.Tensor] = None
     e: Optional[torch.Tensor] = None
     send_idx: Optional[dict] = None  # peer -> int32 device tensor
+    xs: Optional[torch.Tensor] = None    # split precisions: 16-bit hi|lo shadow of the gathered cell matrix (processor.Fast)
 
     def device_plan(self, device):
         if self.send_idx is None:
@@ -101,6 +102,8 @@ def run_processor_partitioned(family: str, blocks, states: List[PartState], tran
     locally encoded one; FVGN: the raw cell-MLP output x')."""
     if family not in ("mgn", "fvgn"):
         raise NotImplementedError(f"domain decomposition covers the 'mgn' and 'fvgn' data-flows, not {family!r}")
+    if ops.split_dtype(prec) is not None and all(s.xs is not None for s in states):
+        return _run_processor_partitioned_fast(family, blocks, states, transport, prec)
     for i, blk in enumerate(blocks):
         we, wn = weights_of(blk.face_block.face_mlp), weights_of(blk.cell_block.cell_mlp)
         if family == "mgn":
@@ -132,15 +135,64 @@ def run_processor_partitioned(family: str, blocks, states: List[PartState], tran
     return states
 
 
+def _shadow_rows(s: PartState) -> torch.Tensor:
+    """The split shadow viewed as fp32 rows (512 B per cell, like a latent row): what the halo exchange moves."""
+    return s.xs.view(torch.float32)
+
+
+def _run_processor_partitioned_fast(family: str, blocks, states: List[PartState], transport, prec: int):
+    """Same data-flow with the single-GPU inference fast path's kernels (``processor.Fast``): x / e updated in place,
+    the gathered cell matrix handed over as its 16-bit split shadow ``s.xs`` (TMA gather4 in the edge kernel) - and it
+    is the SHADOW's ghost rows that travel in the halo exchange (512 B per ghost cell, the size of an fp32 row), so the
+    fp32 ghost rows are never needed.  Bit-identical to ``processor.run_processor`` in fast mode."""
+    for i, blk in enumerate(blocks):
+        we, wn = weights_of(blk.face_block.face_mlp), weights_of(blk.cell_block.cell_mlp)
+
+        def gsegs(s):
+            xf = _shadow_rows(s)
+            return [Seg(s.e), Seg(xf, SEG_GATHER, (s.topo.row,), split=s.xs), Seg(xf, SEG_GATHER, (s.topo.col,), split=s.xs)]
+
+        if family == "mgn":
+            if i > 0:
+                transport.exchange(states, _shadow_rows)
+            for s in states:
+                topo, n_own = s.topo, s.part.n_owned
+                e_raw, _ = ops.mlp_forward(gsegs(s), we, s.e.shape[0], prec, residual=s.e, want_raw=True, want_sum=True,
+                                           out_sum=s.e)
+                vsum = ops.segment_sum(e_raw, e_raw, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm,
+                                       topo.n_vertices)
+                ops.mlp_forward([Seg(s.x), Seg(vsum, SEG_MEAN3, topo.vf)], wn, n_own, prec, residual=s.x,
+                                want_raw=False, want_sum=True, out_sum=s.x, out_split=s.xs[:n_own], split_of_sum=True)
+        else:
+            for s in states:
+                topo, n_own = s.topo, s.part.n_owned
+                vsum = ops.segment_sum(s.e, s.e, 0, H // 2, H // 2, 1.0, topo.vtx_offsets, topo.vtx_perm,
+                                       topo.n_vertices)
+                ops.mlp_forward([Seg(s.x), Seg(vsum, SEG_MEAN3, topo.vf)], wn, n_own, prec, residual=s.x,
+                                want_raw=False, want_sum=True, out_sum=s.x, out_split=s.xs[:n_own])
+            transport.exchange(states, _shadow_rows)
+            for s in states:
+                ops.mlp_forward(gsegs(s), we, s.e.shape[0], prec, residual=s.e, want_raw=False, want_sum=True, out_sum=s.e)
+    return states
+
+
 def encode_process_decode_partitioned(model, states: List[PartState], inputs, transport):
     """encoder -> partitioned GN_Blocks -> decoder for an Fvgn/Mgn-family model.  ``inputs[k]`` = (c_x, f_x) of
     partition k (normalised, local rows).  Returns per partition (x[n_owned], e[E_loc], decoder output): the node
     decoder (MGN) covers the owned cells, the edge decoder (FVGN) all local faces."""
     from . import processor as P
     prec = model.prec
+    sdt = ops.split_dtype(prec)
     for s, (c_x, f_x) in zip(states, inputs):
         s.e = P.mlp_rows(model.encoder.face_mlp, f_x, prec)
-        s.x = P.mlp_rows(model.encoder.cell_mlp, c_x, prec)     # ghosts encoded locally: no exchange before block 0
+        if sdt is not None:      # inference fast path (see _run_processor_partitioned_fast)
+            if s.xs is None or s.xs.shape[0] != c_x.shape[0] or s.xs.dtype != sdt:
+                s.xs = torch.empty(c_x.shape[0], 2 * H, dtype=sdt, device=c_x.device)
+            s.x, _ = ops.mlp_forward([Seg(c_x.contiguous())], weights_of(model.encoder.cell_mlp), c_x.shape[0], prec,
+                                     out_split=s.xs if model.family == "mgn" else None)
+        else:
+            s.xs = None
+            s.x = P.mlp_rows(model.encoder.cell_mlp, c_x, prec)     # ghosts encoded locally: no exchange before block 0
     run_processor_partitioned(model.family, model.processer_list, states, transport, prec)
     outs = []
     for s in states:

@@ -444,7 +444,7 @@ class ConservativeJ(ConservativeH):
     def loss(self, output, graphs):   # Conservative.py:1442-1477: continuity with the normalised face-area feature
         from .Fvgn import flux_dot
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         ff, unv, fv, area = f_graph.face, c_graph.normal, output["face_velocity"], f_graph.x_symm[:, 0:1]
         div = sum(flux_dot(fv[ff[j]], unv[:, j, :]) * area[ff[j]] for j in range(3))
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)

@@ -67,7 +67,7 @@ class FluxA(FvgnA):
 
     def loss(self, output, graphs):   # Flux.py:118-155
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         div = output["cell_flux"][:, 0] + output["cell_flux"][:, 1] + output["cell_flux"][:, 2]   # fvm.py:13-19
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
         cvc = lf(output["cell_velocity_change"], c_graph.y, None, c_graph.batch)
@@ -106,7 +106,7 @@ class FluxA(FvgnA):
 def _face_losses(model, output, graphs, flux_col, pressure_col):
     """The flux-divergence loss shared by FluxB (Flux.py:250-283) and FluxC (Flux.py:423-456)."""
     c_graph, f_graph, v_graph = graphs
-    lf = model.loss_func
+    lf = model.mse_term
     ff, flux = f_graph.face, output["face_flux"]
     div = flux[ff[0]] + flux[ff[1]] + flux[ff[2]]                     # fvm.divergence_from_face_flux
     continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)

@@ -18,11 +18,24 @@ from ..topology import get_topology
 from .base import Model, build_mlp, col, n_class_types
 
 
-def normalize_face_area(face_area, cell_volume, edge_index, dt, batch_norm):
+def normalize_face_area(face_area, cell_volume, edge_index, dt, batch_norm, topo=None):
     """face_area * mean(dt) / mean adjacent cell volume, through BatchNorm1d(1)
-    (reference utils/normalisation.py:325-344)."""
+    (reference utils/normalisation.py:325-344).  With the mesh topology at hand (int32 row / col on the GPU) this is
+    the fused kernel pair of ``fvm_ops.face_area_norm`` (batch statistics, running-stat update and normalisation)."""
+    if topo is not None and face_area.is_cuda and isinstance(batch_norm, nn.BatchNorm1d):
+        from ..fvm_ops import face_area_norm
+        return face_area_norm(face_area, cell_volume, topo.row, topo.col, dt, batch_norm)
     vol = (cell_volume.index_select(0, edge_index[0]) + cell_volume.index_select(0, edge_index[1])) / 2
     return batch_norm((face_area * (torch.mean(dt) / vol)).view(-1, 1))
+
+
+def graph_topology(c_graph):
+    """The MeshTopology ``forward`` attached to the batch (None for a hand-built call without one)."""
+    from ..topology import MeshTopology
+    topo = getattr(c_graph, "topology", None)
+    if isinstance(topo, MeshTopology) and topo.n_faces == c_graph.edge_index.shape[1] and topo.n_cells == c_graph.x.shape[0]:
+        return topo
+    return None
 
 
 def flux_dot(a, n):
@@ -86,6 +99,7 @@ class FvgnA(Model):
         c_graph, f_graph, v_graph = graphs
         c_graph.edge_attr = f_graph.x
         topo = get_topology(graphs)
+        c_graph.topology = topo          # the integrator and the loss of this batch reuse its int32 index tensors
         _, _, edge_attr_out = self.encode_process_decode(c_graph.x, f_graph.x, topo)
         self.dt = c_graph.dt
         acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
@@ -109,11 +123,16 @@ class FvgnA(Model):
 
     def loss(self, output, graphs):   # Fvgn.py:176-212
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
+        topo = graph_topology(c_graph)
         face_area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, self.dt,
-                                        self.integrator.face_area_norm)
+                                        self.integrator.face_area_norm, topo=topo)
         ff, unv, fv = f_graph.face, c_graph.normal, output["face_velocity"]
-        div = sum(flux_dot(fv[ff[j]], unv[:, j, :]) * face_area[ff[j]] for j in range(3))
+        if topo is not None and fv.is_cuda:      # fused fixed-degree divergence (fvm.py:26-37) with its own backward
+            from ..fvm_ops import cell_faces, fvm_divergence
+            div = fvm_divergence(fv, face_area, unv, cell_faces(topo, ff), topo.row, topo.col)
+        else:
+            div = sum(flux_dot(fv[ff[j]], unv[:, j, :]) * face_area[ff[j]] for j in range(3))
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
         cvc = lf(output["cell_velocity_change"], c_graph.y, None, c_graph.batch)
         fvl = lf(output["face_velocity"], f_graph.y[:, :2], ~f_graph.boundary_mask, f_graph.batch)
@@ -134,8 +153,13 @@ class FvgnA(Model):
 
         def forward(self, edge_output, c_graph, f_graph, dt):
             unv, cf = c_graph.normal, f_graph.face
-            area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, dt, self.face_area_norm)
+            topo = graph_topology(c_graph)
+            area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, dt, self.face_area_norm, topo=topo)
             self.face_area = area
+            if topo is not None and edge_output.is_cuda and edge_output.shape[1] == 5:
+                # one kernel forward, one backward (fixed-degree gathers) instead of ~20 tensor kernels
+                from ..fvm_ops import cell_faces, fvm_integrate
+                return fvm_integrate(edge_output, area, unv, cell_faces(topo, cf), topo.row, topo.col, self.rho)
             uv, p_face, flux_d = edge_output[:, :2], edge_output[:, 2:3], edge_output[:, 3:]
             uu_vu = torch.cat([uv[:, 0:1] * uv, uv[:, 1:2] * uv], dim=-1)
             phi_a = sum(flux_dot(uu_vu[cf[j]], unv[:, j, :]) * area[cf[j]] for j in range(3))
@@ -293,7 +317,7 @@ def _real_space_loss(model, output, graphs):
     """Loss of the real-space variants B / J / K (Fvgn.py:388-423 == 1201-1236 == 1343-1378): the continuity term uses
     the NORMALISED face area column of the face features."""
     c_graph, f_graph, v_graph = graphs
-    lf = model.loss_func
+    lf = model.mse_term
     ff, unv, fv, area = f_graph.face, c_graph.normal, output["face_velocity"], f_graph.x[:, 4:5]
     div = sum(flux_dot(fv[ff[j]], unv[:, j, :]) * area[ff[j]] for j in range(3))
     continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
@@ -406,7 +430,7 @@ class FvgnC(FvgnA):
 
     def loss(self, output, graphs):   # Fvgn.py:598-653: per-step losses averaged over the bundle
         c_graph, f_graph, v_graph = graphs
-        lf, w = self.loss_func, self.config.training.loss_weights
+        lf, w = self.mse_term, self.config.training.loss_weights
         ff, unv = f_graph.face, c_graph.normal
         parts = {"total": [], "continuity": [], "cvc": [], "fv": [], "fp": []}
         for t in range(output["face_velocity"].shape[1]):

@@ -81,7 +81,7 @@ class MgnA(Model):
 
     def loss(self, output, graphs):   # Mgn.py:175-197
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         cvc = lf(output["cell_velocity_change"], c_graph.y[:, 0:2], None, c_graph.batch)
         cp = lf(output["cell_pressure"], c_graph.y[:, 2:3], None, f_graph.batch)
         w = self.config.training.loss_weights
@@ -135,7 +135,7 @@ class MgnB(MgnA):
 
     def loss(self, output, graphs):   # Mgn.py:362-391
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         div = divergence_from_uc(output["cell_velocity"], c_graph.grad_weights, c_graph.grad_neighbours, c_graph.volume)
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
         cv = lf(output["cell_velocity"], c_graph.y[:, 0:2], None, c_graph.batch)

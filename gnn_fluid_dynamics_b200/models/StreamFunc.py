@@ -53,7 +53,7 @@ class BaseStreamFunc:   # StreamFunc.py:32-91
 
     def loss(self, output, graphs):   # StreamFunc.py:45-75
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         div = divergence_from_uc(output["cell_velocity"], c_graph.grad_weights, c_graph.grad_neighbours, c_graph.volume)
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
         cv = lf(output["cell_velocity"], c_graph.y[:, 0:2], None, c_graph.batch)
@@ -139,7 +139,7 @@ class StreamFuncD(StreamFuncB):
 
     def loss(self, output, graphs):   # StreamFunc.py:237-275
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         div = divergence_from_uc(output["cell_velocity"], c_graph.grad_weights, c_graph.grad_neighbours, c_graph.volume)
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
         cv = lf(output["cell_velocity"], c_graph.y[:, 0:2], None, c_graph.batch)

@@ -42,7 +42,7 @@ class VertPotA(FluxA):
 
     def loss(self, output, graphs):   # VertPot.py:152-186 (continuity on the cell fluxes; no interior mask on faces)
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         cf = output["cell_flux"]
         div = (cf[:, 0] + cf[:, 1] + cf[:, 2]).unsqueeze(-1)                      # fvm.py:13-19
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
@@ -247,7 +247,7 @@ class VertPotC(_VertPotNet, FluxC):
 
     def loss(self, output, graphs):   # VertPot.py:410-444
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         div = output["cell_flux"][:, 0] + output["cell_flux"][:, 1] + output["cell_flux"][:, 2]
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)
         cvc = lf(output["cell_velocity_change"], c_graph.y, None, c_graph.batch)
@@ -325,7 +325,7 @@ class VertPotG(VertPotA):
 
     def loss(self, output, graphs):   # VertPot.py:737-772
         c_graph, f_graph, v_graph = graphs
-        lf = self.loss_func
+        lf = self.mse_term
         ff, flux = f_graph.face, output["face_flux"]
         div = flux[ff[0]] + flux[ff[1]] + flux[ff[2]]
         continuity = lf(div, torch.zeros_like(div), None, c_graph.batch)

@@ -133,6 +133,15 @@ class Model(nn.Module, ABC):
         self.precision = name
         return self
 
+    def mse_term(self, output, target, mask, batch=None):
+        """One loss term.  The reference's loss callables (``utils/loss.py:16-60``: element-wise masked MSE, which
+        ``train.py:372`` passes) run as ONE fused kernel without boolean-mask indexing (``fvm_ops.masked_mse``); any
+        other callable is applied as given."""
+        from ..fvm_ops import is_plain_mse, masked_mse
+        if output.is_cuda and is_plain_mse(self.loss_func) and output.dtype == torch.float32:
+            return masked_mse(output, target, mask)
+        return self.loss_func(output, target, mask, batch)
+
     def wants_grad(self) -> bool:
         """True when the hot path must record its backward (training step, reference src/train.py:253-256)."""
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.processer_list.parameters())

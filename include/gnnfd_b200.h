@@ -302,6 +302,62 @@ size_t gnnfd_struct_size(int32_t which);
  *              [12..13] producer: total, a_empty wait. */
 int gnnfd_tc_profile_read(uint64_t *out16);
 
+/* ------------------------------------------------------------------------- finite-volume glue
+ * The tensor code between the decoder and the loss / the next rollout step, one kernel per operation, fixed-degree
+ * gathers, deterministic fp64-partial reductions, no host synchronisation (gnn_fluid_dynamics_b200/fvm_ops.py wraps
+ * each pair as a torch.autograd.Function).  `workspace` = gnnfd_glue_workspace_bytes() bytes, zeroed once by the
+ * caller (every kernel leaves it reusable). */
+size_t gnnfd_glue_workspace_bytes(void);
+
+/* out[f] = BatchNorm1d(1)( area[f] * mean(dt) / ((volume[row[f]] + volume[col[f]]) / 2) )
+ * Replaces normalize_face_area, src/utils/normalisation.py:325-344 (called from Integrator.forward
+ * src/models/Fvgn.py:226 and FvgnA.loss src/models/Fvgn.py:182).  training != 0: batch statistics (written to
+ * stats[0] = mean, stats[1] = 1/sqrt(var + eps)) and the running-stat update applied n_updates times (momentum,
+ * unbiased variance, num_batches_tracked += n_updates); training == 0: running statistics, stats unused. */
+int gnnfd_face_area_norm(const float *area, const float *volume, const int32_t *row, const int32_t *col,
+                         const float *dt, int32_t n_dt, int64_t n_faces, const float *bn_weight, const float *bn_bias,
+                         float *running_mean, float *running_var, int64_t *num_batches_tracked, int32_t training,
+                         float momentum, float eps, int32_t n_updates, float *out, float *stats, void *workspace,
+                         size_t workspace_bytes, void *stream);
+/* d_weight = sum_f g[f] * xhat[f], d_bias = sum_f g[f]  (the raw face area carries no gradient) */
+int gnnfd_face_area_norm_backward(const float *area, const float *volume, const int32_t *row, const int32_t *col,
+                                  const float *dt, int32_t n_dt, int64_t n_faces, const float *stats,
+                                  const float *running_mean, const float *running_var, float eps, const float *g,
+                                  float *d_weight, float *d_bias, void *workspace, size_t workspace_bytes, void *stream);
+
+/* FVM integrator, src/models/Fvgn.py:221-255 (chain_flux_dot_product: src/utils/maths.py:12-20), and the cell
+ * divergence of the face velocity, src/utils/fvm.py:26-37.  edge_out rows (stride ld) = (u, v, p, d0, d1);
+ * cf0..2[c] = the three face ids of cell c (f_graph.face); normal = c_graph.normal [N, 3, 2].
+ *   acc[c] = -(sum_j u_f (u_f . n_cj) a_f) - (sum_j p_f n_cj a_f) / rho + sum_j (d0, d1)_f        (acc may be NULL)
+ *   div[c] = sum_j (u_f . n_cj) a_f                                                              (div may be NULL) */
+int gnnfd_fvm_integrate(const float *edge_out, int32_t ld, const float *area, const float *normal, const int32_t *cf0,
+                        const int32_t *cf1, const int32_t *cf2, int64_t n_cells, float rho, float *acc, float *div,
+                        void *stream);
+/* transpose: one thread per face gathers from its (at most two) cells row[f], col[f]; n_cols = 5 with g_acc (all of
+ * u, v, p, d0, d1), 2 with g_div only; d_area[f] = gradient w.r.t. the normalised face area. */
+int gnnfd_fvm_integrate_backward(const float *edge_out, int32_t ld, const float *area, const float *normal,
+                                 const int32_t *cf0, const int32_t *cf1, const int32_t *cf2, const int32_t *row,
+                                 const int32_t *col, int64_t n_faces, float rho, const float *g_acc, const float *g_div,
+                                 float *d_edge_out, int32_t ld_g, int32_t n_cols, float *d_area, void *stream);
+
+/* out2[0] = mean over unmasked rows and all columns of (a - b)^2, out2[1] = number of elements averaged.
+ * Replaces MSE_per_element_torch(output, target, mask), src/utils/loss.py:55-60, without output[mask] indexing. */
+int gnnfd_masked_mse(const float *a, int32_t ld_a, const float *b, int32_t ld_b, const uint8_t *mask, int64_t rows,
+                     int32_t cols, float *out2, void *workspace, size_t workspace_bytes, void *stream);
+int gnnfd_masked_mse_backward(const float *a, int32_t ld_a, const float *b, int32_t ld_b, const uint8_t *mask, int64_t rows,
+                              int32_t cols, const float *fwd_out2, const float *g, float *d_a, int32_t ld_d, void *stream);
+
+/* Rollout state advance: src/rollout.py:336-340 (velocity update), update_features src/models/Fvgn.py:133-148 /
+ * src/models/Mgn.py:139-151 and the next step's input z-scoring src/utils/normalisation.py:255-278, in two kernels.
+ *   vel = has_change ? x_raw[:, 0:2] + delta : delta;  x_raw[:, 0:2] = vel;  x_norm[:, 0:2] = (vel - mean) / scale
+ *   dv = bc_mask[f] ? bc_value[f, 0:2] : vel[row[f]] - vel[col[f]];  f_raw[:, 0:2] = dv;  f_norm[:, 0:2] = z-scored dv
+ * cell_mean_std4 / face_mean_std4: HOST pointers to (mean0, scale0, mean1, scale1); optional outputs may be NULL. */
+int gnnfd_state_advance(float *x_raw, int32_t ld_x, const float *delta, int32_t ld_d, int32_t has_change, int64_t n_cells,
+                        float *x_norm, int32_t ld_xn, const float *cell_mean_std4, const int32_t *row, const int32_t *col,
+                        const uint8_t *bc_mask, const float *bc_value, int32_t ld_bc, int64_t n_faces, float *f_raw,
+                        int32_t ld_f, float *f_norm, int32_t ld_fn, const float *face_mean_std4, float *vel_out,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

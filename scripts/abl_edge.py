@@ -46,3 +46,15 @@ def timeit(fn, n=10):
 te = timeit(lambda: ops.mlp_forward(esegs, we, E, P, residual=e, want_raw=False, want_sum=True))
 tn = timeit(lambda: ops.mlp_forward(nsegs, wn, N, P, residual=x, want_raw=True, want_sum=True))
 print(f"{tag:8s} edge {te[0]:7.1f} us (min {te[1]:7.1f})   node {tn[0]:7.1f} us (min {tn[1]:7.1f})   E={E} N={N} V={V}", flush=True)
+# inference fast path: TMA-gathered split shadow, in-place residual (TMA reduce-add), shadow written by the node block
+xs = torch.empty(N, 256, dtype=torch.bfloat16, device=dev)
+hi = x.to(torch.bfloat16); xs[:, :128] = hi; xs[:, 128:] = (x - hi.float()).to(torch.bfloat16)
+xf = xs.view(torch.float32)
+fsegs = [Seg(e), Seg(xf, _lib.SEG_GATHER, (row,), split=xs), Seg(xf, _lib.SEG_GATHER, (col,), split=xs)]
+tef = timeit(lambda: ops.mlp_forward(fsegs, we, E, P, residual=e, want_raw=False, want_sum=True, out_sum=e))
+# in-place epilogue only (register-staged gathers)
+tei = timeit(lambda: ops.mlp_forward(esegs, we, E, P, residual=e, want_raw=False, want_sum=True, out_sum=e))
+tnf = timeit(lambda: ops.mlp_forward(nsegs, wn, N, P, residual=x, want_raw=False, want_sum=True, out_sum=x, out_split=xs))
+alg_e, alg_n = (512 * (2 * E + N) + 8 * E) / 1e3, (512 * 3 * N + 256 * V + 12 * N) / 1e3
+print(f"{tag:8s} FAST edge {tef[0]:7.1f} us (min {tef[1]:7.1f}, {alg_e / tef[0]:6.0f} GB/s)   edge in-place epilogue only {tei[0]:7.1f} us"
+      f"   node {tnf[0]:7.1f} us (min {tnf[1]:7.1f}, {alg_n / tnf[0]:6.0f} GB/s)", flush=True)

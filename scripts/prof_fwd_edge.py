@@ -20,9 +20,16 @@ g = torch.Generator().manual_seed(0)
 x = torch.randn(N, 128, generator=g).to(dev); e = torch.randn(E, 128, generator=g).to(dev)
 we = _to_weights(_rand_mlp(384, 128, True, seed=1), 0)
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-segs = [Seg(e), Seg(x, _lib.SEG_GATHER, (row,)), Seg(x, _lib.SEG_GATHER, (col,))]
+fast = len(sys.argv) > 1 and sys.argv[1] == "fast"      # inference fast path: TMA-gathered split shadow, in-place residual
+if fast:
+    xs = torch.empty(N, 256, dtype=torch.bfloat16, device=dev)
+    hi = x.to(torch.bfloat16); xs[:, :128] = hi; xs[:, 128:] = (x - hi.float()).to(torch.bfloat16)
+    xf = xs.view(torch.float32)
+    segs = [Seg(e), Seg(xf, _lib.SEG_GATHER, (row,), split=xs), Seg(xf, _lib.SEG_GATHER, (col,), split=xs)]
+else:
+    segs = [Seg(e), Seg(x, _lib.SEG_GATHER, (row,)), Seg(x, _lib.SEG_GATHER, (col,))]
 for it in range(3):
     flush.zero_()
-    ops.mlp_forward(segs, we, E, _lib.PREC_BF16X3, residual=e, want_raw=False, want_sum=True)
+    ops.mlp_forward(segs, we, E, _lib.PREC_BF16X3, residual=e, want_raw=False, want_sum=True, out_sum=e if fast else None)
 torch.cuda.synchronize()
 print("E", E, "N", N)

@@ -19,12 +19,19 @@ N, E = gd[0].x.shape[0], gd[0].edge_index.shape[1]
 x = torch.randn(N, 128, device=dev); e = torch.randn(E, 128, device=dev)
 blk = model.processer_list[3]
 vs = P.vertex_half_sum(e, topo)
-for which in ("edge", "node"):
+fast = P.Fast(N, model.prec, dev)
+hi = x.to(fast.dtype); fast.xs[:, :128] = hi; fast.xs[:, 128:] = (x - hi.float()).to(fast.dtype)
+torch.set_grad_enabled(False)
+for which in ("edge", "node", "edge_fast", "node_fast"):
     def run():
         if which == "edge":
             P.edge_mlp_concat(blk.face_block.face_mlp, e, x, topo, model.prec, want_raw=False)
-        else:
+        elif which == "node":
             P.node_mlp_two_hop(blk.cell_block.cell_mlp, x, vs, topo, model.prec, want_raw=True)
+        elif which == "edge_fast":
+            P.edge_mlp_concat(blk.face_block.face_mlp, e, None, topo, model.prec, want_raw=False, fast=fast)
+        else:
+            P.node_mlp_two_hop(blk.cell_block.cell_mlp, x, vs, topo, model.prec, want_raw=False, fast=fast)
     for _ in range(3):
         run()
     torch.cuda.synchronize()

@@ -1,0 +1,122 @@
+"""Fused finite-volume glue kernels (gnn_fluid_dynamics_b200/fvm_ops.py, csrc/glue.cu) against the oracle's plain tensor
+restatement of the reference formulas (oracle/model.py: fvgn_integrator / fvgn_loss follow Fvgn.py:176-255,
+normalisation.py:325-344, fvm.py:26-37, loss.py:55-60): forward values and autograd gradients, fp32, 1e-5."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from fixtures import rel_l2
+from helpers import golden_graphs
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _setup(n_cells=700, flip=True):
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    _, graphs = golden_graphs("FvgnA", flip=flip, n_cells=n_cells, mesh_seed=5, feat_seed=6)
+    gd = [g.to(dev()) for g in graphs]
+    topo = get_topology(gd).validate()
+    return graphs, gd, topo
+
+
+def _ref_area(bn, f_area, vol, ei, dt, training):
+    raw = (f_area * (torch.mean(dt) / ((vol[ei[0]] + vol[ei[1]]) / 2))).view(-1, 1)
+    return F.batch_norm(raw, bn["running_mean"], bn["running_var"], bn["weight"], bn["bias"], training=training,
+                        momentum=0.1, eps=1e-5)
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_face_area_norm_forward_backward_and_running_stats(training):
+    from gnn_fluid_dynamics_b200 import fvm_ops
+    graphs, gd, topo = _setup()
+    c, f, _ = graphs
+    bn = torch.nn.BatchNorm1d(1)
+    with torch.no_grad():
+        bn.weight.fill_(1.3); bn.bias.fill_(-0.2); bn.running_mean.fill_(0.2); bn.running_var.fill_(1.5)
+    ref = {k: v.detach().clone() for k, v in bn.state_dict().items()}
+    ref["weight"].requires_grad_(True); ref["bias"].requires_grad_(True)
+    dt = torch.tensor([0.01, 0.02, 0.015])
+    out_ref = _ref_area(ref, f.area, c.volume, c.edge_index, dt, training)
+    g = torch.randn(out_ref.shape, generator=torch.Generator().manual_seed(1))
+    (out_ref * g).sum().backward()
+    bn = bn.to(dev()).train(training)
+    out = fvm_ops.face_area_norm(gd[1].area, gd[0].volume, topo.row, topo.col, dt.to(dev()), bn)
+    (out * g.to(dev())).sum().backward()
+    assert rel_l2(out, out_ref) < 1e-5
+    assert rel_l2(bn.weight.grad, ref["weight"].grad) < 1e-5 and rel_l2(bn.bias.grad, ref["bias"].grad) < 1e-5
+    assert rel_l2(bn.running_mean, ref["running_mean"]) < 1e-6 and rel_l2(bn.running_var, ref["running_var"]) < 1e-5
+    assert int(bn.num_batches_tracked) == (1 if training else 0)
+
+
+def test_fvm_integrate_and_divergence_vs_tensor_code():
+    from gnn_fluid_dynamics_b200 import fvm_ops
+    graphs, gd, topo = _setup()
+    c, f, _ = graphs
+    gen = torch.Generator().manual_seed(2)
+    E, N = f.area.shape[0], c.x.shape[0]
+    eo = torch.randn(E, 5, generator=gen).requires_grad_(True)
+    area = (torch.rand(E, 1, generator=gen) + 0.5).requires_grad_(True)
+    unv, cf = c.normal, f.face
+    uv, p, fd = eo[:, :2], eo[:, 2:3], eo[:, 3:]
+    uu = torch.cat([uv[:, 0:1] * uv, uv[:, 1:2] * uv], -1)
+    dot2 = lambda a, n: torch.cat([(a[:, 0:2] * n).sum(-1, keepdim=True), (a[:, 2:4] * n).sum(-1, keepdim=True)], -1)
+    phi_a = sum(dot2(uu[cf[j]], unv[:, j, :]) * area[cf[j]] for j in range(3))
+    phi_d = fd[cf[0]] + fd[cf[1]] + fd[cf[2]]
+    phi_p = sum(p[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+    acc_ref = -phi_a - phi_p / 1.7 + phi_d
+    div_ref = sum((uv[cf[j]] * unv[:, j, :]).sum(-1, keepdim=True) * area[cf[j]] for j in range(3))
+    g1, g2 = torch.randn(N, 2, generator=gen), torch.randn(N, 1, generator=gen)
+    ((acc_ref * g1).sum() + (div_ref * g2).sum()).backward()
+    eo_d = eo.detach().to(dev()).requires_grad_(True)
+    ar_d = area.detach().to(dev()).requires_grad_(True)
+    cfd = fvm_ops.cell_faces(topo, gd[1].face)
+    acc = fvm_ops.fvm_integrate(eo_d, ar_d, gd[0].normal, cfd, topo.row, topo.col, rho=1.7)
+    div = fvm_ops.fvm_divergence(eo_d[:, :2], ar_d, gd[0].normal, cfd, topo.row, topo.col)
+    ((acc * g1.to(dev())).sum() + (div * g2.to(dev())).sum()).backward()
+    assert rel_l2(acc, acc_ref) < 1e-5 and rel_l2(div, div_ref) < 1e-5
+    assert rel_l2(eo_d.grad, eo.grad) < 1e-5 and rel_l2(ar_d.grad, area.grad) < 1e-5
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_masked_mse_vs_torch(masked):
+    from gnn_fluid_dynamics_b200 import fvm_ops
+    gen = torch.Generator().manual_seed(3)
+    a = torch.randn(5001, 5, generator=gen).requires_grad_(True)
+    b = torch.randn(5001, 3, generator=gen)
+    mask = (torch.rand(5001, generator=gen) > 0.3) if masked else None
+    av, bv = a[:, 1:3], b[:, :2]
+    ref = F.mse_loss(av[mask], bv[mask]) if masked else F.mse_loss(av, bv)
+    (ref * 1.7).backward()
+    ad = a.detach().to(dev()).requires_grad_(True)
+    out = fvm_ops.masked_mse(ad[:, 1:3], b.to(dev())[:, :2], None if mask is None else mask.to(dev()))
+    (out * 1.7).backward()
+    assert abs(float(out) - float(ref)) < 1e-6 * max(1.0, abs(float(ref)))
+    assert rel_l2(ad.grad, a.grad) < 1e-6
+    out2 = fvm_ops.masked_mse(ad[:, 1:3].detach(), b.to(dev())[:, :2], None if mask is None else mask.to(dev()))
+    assert torch.equal(out2, out.detach())                      # deterministic reduction
+
+
+def test_state_advance_matches_update_features():
+    """state_advance == rollout.py:340 + FvgnA.update_features + the z-scoring of the next step's inputs."""
+    from gnn_fluid_dynamics_b200 import fvm_ops
+    graphs, gd, topo = _setup(flip=False)
+    c, f, _ = gd
+    gen = torch.Generator().manual_seed(4)
+    delta = torch.randn(c.x.shape[0], 2, generator=gen).to(dev())
+    vel = c.x[:, :2] + delta
+    dv = vel[c.edge_index[0]] - vel[c.edge_index[1]]
+    mask = ((f.type == 2) | (f.type == 1)).reshape(-1)
+    dv = torch.where(mask.unsqueeze(-1), f.y[:, 0:2], dv)
+    x_raw, f_raw = c.x.clone(), f.x.clone()
+    x_norm, f_norm = torch.zeros_like(x_raw), torch.zeros_like(f_raw)
+    cs, fs = (0.1, 1.2, 0.15, 1.1), (0.3, 0.9, 0.25, 1.3)
+    vout = torch.empty_like(vel)
+    fvm_ops.state_advance(x_raw, delta, True, topo.row, topo.col, f_raw, mask, f.y, x_norm=x_norm, cell_stats=cs,
+                          f_norm=f_norm, face_stats=fs, vel_out=vout)
+    assert torch.equal(x_raw[:, :2], vel) and torch.equal(vout, vel) and torch.equal(f_raw[:, :2], dv)
+    assert torch.equal(f_raw[:, 2:], f.x[:, 2:])
+    assert rel_l2(x_norm[:, 0], (vel[:, 0] - cs[0]) / cs[1]) < 1e-6 and rel_l2(f_norm[:, 1], (dv[:, 1] - fs[2]) / fs[3]) < 1e-6

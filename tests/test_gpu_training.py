@@ -210,7 +210,7 @@ def test_training_step_matches_reference_golden():
             assert rel_l2(grads[k[5:]].grad, torch.from_numpy(gold[k])) < GRAD_TOL, k
 
 
-@pytest.mark.parametrize("name", ["VertPotA", "StreamFuncA", "FluxA", "ConservativeA", "MgnA"])
+@pytest.mark.parametrize("name", ["FvgnA", "VertPotA", "StreamFuncA", "FluxA", "ConservativeA", "MgnA"])
 def test_training_step_matches_reference_golden_families(name):
     """The reference's own training step (forward 'train' + model.loss + backward; tests/golden/make_golden.py
     --train-only) for BASELINE.json config 5's families (VertPotA, StreamFuncA) and FluxA / ConservativeA / MgnA:
