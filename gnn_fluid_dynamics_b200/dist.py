@@ -275,13 +275,17 @@ class PartitionedRollout:
             if model.family == "mgn":
                 output = [dec, None, None]
             else:
-                c_view = self._Data(normal=c.normal[:n_own], volume=c.volume, edge_index=c.edge_index, dt=c.dt)
+                # the local topology rides along so the integrator runs the same fused finite-volume kernels as the
+                # single-GPU model (bit-identical velocities on the owned cells)
+                c_view = self._Data(x=c.x, normal=c.normal[:n_own], volume=c.volume, edge_index=c.edge_index, dt=c.dt,
+                                    topology=s.topo)
                 output = [model.integrator(dec, c_view, f, c.dt), dec, None]
             output = model.normalizer.output(output, inverse=True)
             vel = g[0].x[:n_own, :2] + output[0][:, 0:2]
             g[0].x[:n_own, :2] = vel
             vels.append(vel)
-        self.transport.exchange(self.states, lambda s: self.graphs[self.states.index(s)][0].x)
+        by_id = {id(st): g for st, g in zip(self.states, self.graphs)}
+        self.transport.exchange(self.states, lambda s: by_id[id(s)][0].x)
         for g in self.graphs:
             c, f, _ = g
             u = c.x[:, :2]
