@@ -48,9 +48,18 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def _collate(samples):
+    from gnn_fluid_dynamics_b200.graph import collate_triplet
+    return collate_triplet(samples) if len(samples) > 1 else _with_batch([g.clone() for g in samples[0]])
+
+
 def build_batch(model_name, n_meshes, n_cells, kind, seed0=0):
     """Synthetic batch of independent meshes, PyG-style concatenation (training-time edge flips on)."""
-    from gnn_fluid_dynamics_b200.graph import collate_triplet
+    return _collate(build_samples(model_name, n_meshes, n_cells, kind, seed0))
+
+
+def build_samples(model_name, n_meshes, n_cells, kind, seed0=0):
+    """The per-mesh graph triplets of the synthetic batch (what a dataset hands to the collation)."""
     from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs
     samples = []
     for i in range(n_meshes):
@@ -61,7 +70,7 @@ def build_batch(model_name, n_meshes, n_cells, kind, seed0=0):
         else:
             g[1].y = g[1].y[:, :3].contiguous()
         samples.append(g)
-    return collate_triplet(samples) if n_meshes > 1 else _with_batch(samples[0])
+    return samples
 
 
 def workload_config(workload, n_cells_total, n_faces, n_vertices):
@@ -137,20 +146,24 @@ class ClockSampler:
 
 def ncu_traffic(which):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of a kernel at the bench shape, from the committed
-    `ncu --set full` capture (profiles/r01_train_kernels_ncu_summary.json <- scripts/prof_train_kernels.py, whose
-    launch order is: forward+stash, wgrad L3, dgrad chain, wgrad L2, wgrad L1, 2 x single Linear) or, for the
-    inference forward, profiles/r01_mlp_tc_ncu_summary.json."""
+    `ncu --set full` captures: profiles/r02_fwd_edge_fast_ncu_summary.json (inference edge block, scripts/prof_fwd_edge.py
+    fast) and profiles/r01_train_kernels_ncu_summary.json (scripts/prof_train_kernels.py, launch order: forward+stash,
+    wgrad L3, dgrad chain, wgrad L2, wgrad L1, 2 x single Linear - the training kernels' traffic has not changed since)."""
     try:
-        if which == "edge_chain":
+        if which in ("edge_chain", "edge_stash"):
             name = "r01_train_kernels_ncu_summary.json"
             d = json.load(open(os.path.join(ROOT, "profiles", name)))
-            return int(d["launches"][2]["dram_traffic_bytes"]), name
-        name = "r01_mlp_tc_ncu_summary.json"
+            return int(d["launches"][2 if which == "edge_chain" else 0]["dram_traffic_bytes"]), name
+        name = "r02_fwd_edge_fast_ncu_summary.json"
         d = json.load(open(os.path.join(ROOT, "profiles", name)))
-        edge = max(d["launches"], key=lambda x: x.get("duration_us", 0))      # edge block = the longer launch
-        return int(edge["dram_traffic_bytes"]), name
+        return int(d["launches"][0]["dram_traffic_bytes"]), name
     except Exception:  # noqa: BLE001
         return None, None
+
+
+def algorithmic_bytes_forward(E, N, V, family="fvgn"):
+    """Whole processor pass, SURVEY.md section 8d: 512 (3E + 4N + V) + 16E + 12N bytes per GN_Block (FVGN order)."""
+    return MP_NUM * (512 * (3 * E + 4 * N + V) + 16 * E + 12 * N)
 
 
 def algorithmic_bytes_edge_kernel(E, N):
@@ -231,6 +244,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong-4m", default="auto", choices=["auto", "on", "off"],
+                    help="also run BASELINE configs[3] (4M-cell MGN rollout, domain-decomposed over the run's GPUs) and report it "
+                         "under the `strong_4m` key; auto = with the default workload")
     ap.add_argument("--halo", default="nccl", choices=["peer", "nccl"],
                     help="domain-decomposed workloads: ghost latents via NCCL send/receive (default, measured faster) or "
                          "via peer-memory gathers inside the edge kernel")
@@ -266,7 +282,9 @@ def main():
     model = build_model(model_name, precision=prec).to(dev)
     model.train() if train else model.eval()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4) if train else None      # reference src/train.py:83
-    host_graphs = [g.pin_memory() for g in build_batch(model_name, n_meshes, n_cells, kind, seed0=rank * n_meshes)]
+    host_samples = build_samples(model_name, n_meshes, n_cells, kind, seed0=rank * n_meshes)      # per-mesh triplets
+    host_graphs = [g.pin_memory() for g in _collate(host_samples)]
+    host_samples = [[g.pin_memory() for g in smp] for smp in host_samples]
     N, E = host_graphs[0].x.shape[0], host_graphs[0].edge_index.shape[1]
     V = host_graphs[2].pos.shape[0]
 
@@ -338,18 +356,26 @@ def main():
         model.train()
 
     # ---- end-to-end leg (`e2e`): host graphs -> public API -> host result ---------------------------
+    # The public data path: per-mesh host samples (pinned) -> GraphCache.fetch (static geometry / connectivity of each
+    # mesh resident in HBM after its first use, batch collated on the device, only the per-sample attributes - state,
+    # targets, the re-flipped c_graph.edge_index - travel every step) -> model.  SURVEY.md section 8f row 4.
+    from gnn_fluid_dynamics_b200.graph_cache import GraphCache
+    cache = GraphCache(dev)
+    mesh_keys = [("bench", rank, i) for i in range(n_meshes)]
+
     def step_e2e():
-        g = [x.to(dev, non_blocking=True) for x in host_graphs]
+        g = cache.fetch(mesh_keys, host_samples)
         if train:
             return float(train_step(model.normalizer.input(g)).item())      # D2H of the loss
         with torch.no_grad():
             out = model(g, mode="train")
             return out["cell_velocity_change"].to("cpu", non_blocking=False)
 
-    h2d = sum(t.numel() * t.element_size() for g in host_graphs for t in g._store.values() if torch.is_tensor(t))
+    h2d_full = sum(t.numel() * t.element_size() for g in host_graphs for t in g._store.values() if torch.is_tensor(t))
     d2h = 4 if train else N * 2 * 4
     for _ in range(3):
         step_e2e()
+    h2d = cache.h2d_bytes                       # a steady-state step: the per-sample attributes only
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -385,10 +411,17 @@ def main():
     hbm_peak, peak_kind = peaks()
     w_edge = P.weights_of(blk.face_block.face_mlp)
     esegs = [Seg(e_lat), Seg(x_lat, SEG_GATHER, (topo.row,)), Seg(x_lat, SEG_GATHER, (topo.col,))]
-    k_ms = time_kernel(lambda: P.edge_mlp_concat(blk.face_block.face_mlp, e_lat, x_lat, topo, model.prec, want_raw=False))
+    # the inference edge block exactly as the model's forward launches it: x'[row] / x'[col] TMA-gathered from the split
+    # shadow the node block's epilogue wrote, e updated in place by the TMA reduce-store epilogue
+    fast = P.Fast(N, model.prec, dev)
+    hi = x_lat.to(fast.dtype)
+    fast.xs[:, :128] = hi
+    fast.xs[:, 128:] = (x_lat - hi.float()).to(fast.dtype)
+    k_ms = time_kernel(lambda: P.edge_mlp_concat(blk.face_block.face_mlp, e_lat, None, topo, model.prec, want_raw=False, fast=fast))
+    e_lat = torch.randn(E, 128, device=dev)          # (the in-place runs above accumulated into it)
     alg = algorithmic_bytes_edge_kernel(E, N)
     traffic, traffic_src = ncu_traffic("edge_fwd")
-    fwd_roof = {"kernel": "mlp_tc_kernel<BWD=0>: fused edge block forward (gather + 3-layer MLP + LayerNorm + residual), inference",
+    fwd_roof = {"kernel": "mlp_tc_kernel<EPI=1>: fused edge block forward (TMA gather4 + 3-layer MLP + LayerNorm + in-place residual), inference",
                 "bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": alg / (k_ms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_kind": peak_kind, "kernel_ms": k_ms, "algorithmic_bytes": alg}
@@ -399,20 +432,25 @@ def main():
         c_ms = time_kernel(lambda: ops.dgrad_chain(w_edge, st, g_lat, 128, model.prec, residual=g_lat, pack_cache=packs))
         c_alg = 512 * 7 * E                       # read dy, a2, a1, residual; write dA2, dA1, dIn0
         c_traffic, c_src = ncu_traffic("edge_chain")
-        roofline = {"kernel": "mlp_tc_kernel<BWD=1>: dgrad chain of the fused edge block (largest single launch of the training step)",
-                    "bound": "hbm", "achieved": c_alg / (c_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": c_alg / (c_ms * 1e-3) / 1e9 / hbm_peak, "traffic": c_traffic, "traffic_source": c_src,
-                    "peak_kind": peak_kind, "kernel_ms": c_ms, "algorithmic_bytes": c_alg}
+        chain_roof = {"kernel": "mlp_tc_kernel<BWD=1>: dgrad chain of the fused edge block",
+                      "bound": "hbm", "achieved": c_alg / (c_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                      "frac": c_alg / (c_ms * 1e-3) / 1e9 / hbm_peak, "traffic": c_traffic, "traffic_source": c_src,
+                      "peak_kind": peak_kind, "kernel_ms": c_ms, "algorithmic_bytes": c_alg}
         s_ms = time_kernel(lambda: ops.mlp_forward(esegs, w_edge, E, model.prec, residual=e_lat, want_raw=False, want_sum=True, stash=True))
         s_alg = alg + 512 * 3 * E + 4 * E          # + stash a1, a2, x-hat, rstd
+        s_traffic, s_src = ncu_traffic("edge_stash")
+        # the line's `roofline` = the dominant kernel family of the training step by launch-list share
+        # (profiles/r02*_train_launch_shares.md: mlp_tc_kernel<BWD=0> forward + stash launches)
+        roofline = {"kernel": "mlp_tc_kernel<BWD=0>: fused edge block forward + training stash (dominant family of the step)",
+                    "bound": "hbm", "achieved": s_alg / (s_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": s_alg / (s_ms * 1e-3) / 1e9 / hbm_peak, "traffic": s_traffic, "traffic_source": s_src,
+                    "peak_kind": peak_kind, "kernel_ms": s_ms, "algorithmic_bytes": s_alg}
         wout = torch.empty(128, 128, device=dev)
         w_ms = time_kernel(lambda: ops.wgrad(Seg(g_lat), [Seg(st.a1)], E, wout, b_act=1))
         w_alg = 512 * 2 * E
         v_ms = time_kernel(lambda: P.vertex_half_sum(e_lat, topo))
         v_alg = 512 * E + 256 * V + 4 * (2 * E + V + 1)      # read e once, write vsum, CSR offsets + perm
-        other = [fwd_roof,
-                 {"kernel": "mlp_tc_kernel<BWD=0>: fused edge block forward + training stash", "kernel_ms": s_ms,
-                  "algorithmic_bytes": s_alg, "achieved": s_alg / (s_ms * 1e-3) / 1e9, "frac": s_alg / (s_ms * 1e-3) / 1e9 / hbm_peak},
+        other = [fwd_roof, chain_roof,
                  {"kernel": "wgrad_tc_kernel<2,0>: dW = dA^T SiLU(a) (tcgen05 split-bf16, MN-major operands)", "kernel_ms": w_ms,
                   "algorithmic_bytes": w_alg, "achieved": w_alg / (w_ms * 1e-3) / 1e9, "frac": w_alg / (w_ms * 1e-3) / 1e9 / hbm_peak},
                  {"kernel": "segment_sum_kernel<16>: deterministic edge->vertex half-sums over the receiver-sorted CSR (gather / segment-sum phase)",
@@ -432,6 +470,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = time_cpu_baseline(model_name, n_meshes, n_cells, kind, train)
 
+    strong = None
+    if args.strong_4m == "on" or (args.strong_4m == "auto" and args.workload == DEFAULT_WORKLOAD):
+        del model, opt, gd, cache
+        torch.cuda.empty_cache()
+        strong = strong_scaling_4m(world, rank, dev, dist, steps=max(args.steps, 20) if world > 1 else max(5, min(args.steps, 10)),
+                                   halo=args.halo)
+
     if rank == 0:
         line = {
             "metric": "processor edge-updates/sec", "value": E_total * MP_NUM / (ms * 1e-3),
@@ -444,26 +489,46 @@ def main():
                         "backward_precision": "dgrad and wgrad split-bf16 (bf16x3), fp32 accumulate" if train else None},
             "e2e": {"value": E_total * MP_NUM / (ms_e2e * 1e-3), "unit": "edge-updates/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
-                    "api": ("model.forward + model.loss + backward + Adam step from pinned host graphs, loss read back"
-                            if train else "model.forward(graphs, mode='train') from pinned host graphs")},
+                    "h2d_bytes_first_step": h2d_full,
+                    "api": ("GraphCache.fetch(per-mesh pinned host samples: device-side collation, static mesh data resident "
+                            "after the first step) -> " +
+                            ("model.forward + model.loss + backward + Adam step, loss read back"
+                             if train else "model.forward(graphs, mode='train'), result read back"))},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline, "roofline_other_kernels": other,
+            "roofline_forward": whole_pass_roofline(algorithmic_bytes_forward(E, N, V), fwd_ms if train else ms, hbm_peak,
+                                                    "whole forward (encoder + 15 GN_Blocks + decoder): 3 096 B per edge-update, SURVEY.md 8d"),
+            "roofline_step": (whole_pass_roofline(3 * algorithmic_bytes_forward(E, N, V), ms, hbm_peak,
+                                                  "whole training step, counted as 3 x the forward's algorithmic bytes "
+                                                  "(forward + input-gradient pass + weight-gradient pass)") if train else None),
             "cpu_baseline": cpu_baseline,
         }
+        if strong is not None:
+            line["strong_4m"] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_rollout(args, world, rank, dev, dist):
-    """Rollout workloads: K autoregressive steps of one mesh.  N = 1: RolloutEngine (CUDA-graph replay);
-    N > 1: the mesh is domain-decomposed, one partition per GPU, halo exchange per GN_Block (strong scaling)."""
+def whole_pass_roofline(alg_bytes, ms, peak, what):
+    if ms is None:
+        return None
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    return {"what": what, "bound": "hbm", "algorithmic_bytes": alg_bytes, "ms": ms, "achieved": ach, "peak": peak,
+            "unit": "GB/s", "frac": ach / peak}
+
+
+def measure_rollout(workload, world, rank, dev, dist, steps, warmup, halo="nccl", prec="bf16x3", single_gpu_too=False):
+    """K autoregressive steps of one mesh.  world == 1: RolloutEngine (CUDA-graph replay); world > 1: the mesh is
+    domain-decomposed, one partition per GPU, halo exchange per GN_Block (strong scaling).  ``single_gpu_too``: rank 0
+    also times the WHOLE mesh on its own GPU first (the N = 1 point of the strong-scaling curve, same run, same box).
+    Returns a dict of measurements (times are the max over ranks)."""
     from helpers import build_model
     from gnn_fluid_dynamics_b200 import ops
     from gnn_fluid_dynamics_b200.mesh import make_mesh, mesh_graphs
-    model_name, _, n_cells, kind, _ = WORKLOADS[args.workload]
-    prec = args.precision or "bf16x3"
+    from gnn_fluid_dynamics_b200.rollout import RolloutEngine
+    model_name, _, n_cells, kind, _ = WORKLOADS[workload]
     model = build_model(model_name, precision=prec).to(dev).eval()
     mesh = make_mesh(n_cells, kind, seed=0)
     cons = model_name.startswith("Conservative")
@@ -475,6 +540,32 @@ def run_rollout(args, world, rank, dev, dist):
         g[1].y = g[1].y[:, :3].contiguous()
     g = _with_batch(g)
     N, E, V = g[0].x.shape[0], g[0].edge_index.shape[1], g[2].pos.shape[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step, n_steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_steps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n_steps
+
+    n1_ms = None
+    if world > 1 and single_gpu_too:
+        if rank == 0:
+            eng1 = RolloutEngine(model, [t.to(dev) for t in g], cuda_graph=True, need_cell_csr=cons, two_hop=not cons)
+            for _ in range(3):
+                eng1.step()
+            torch.cuda.synchronize()
+            n1_ms = timed(eng1.step, max(3, min(steps, 10)))
+            del eng1
+            torch.cuda.empty_cache()
+        barrier()
     halo_bytes = 0
     if world > 1:
         from gnn_fluid_dynamics_b200.dist import PartitionedRollout, TorchDistTransport
@@ -483,26 +574,18 @@ def run_rollout(args, world, rank, dev, dist):
         part = parts[rank]
         transport = TorchDistTransport()
         peer = None
-        if args.halo == "peer":
+        if halo == "peer":
             from gnn_fluid_dynamics_b200.dist import PeerBuffers, peer_indices
             bufs = PeerBuffers(max(p.n_owned for p in parts), 128, dev, world, rank)
             peer = (bufs,) + peer_indices(part, {a: parts[a].send[rank] for a in part.recv}, dev)
         eng = PartitionedRollout(model, [part], [[t.to(dev) for t in local_graphs(g, part)]], transport, peer=peer)
-        step = eng.step
         out_rows = part.n_owned
     else:
-        from gnn_fluid_dynamics_b200.rollout import RolloutEngine
         eng = RolloutEngine(model, [t.to(dev) for t in g], cuda_graph=True, need_cell_csr=cons, two_hop=not cons)
-        step = eng.step
         out_rows = N
+    step = eng.step
     host_out = torch.empty(out_rows, 2).pin_memory()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
@@ -510,27 +593,54 @@ def run_rollout(args, world, rank, dev, dist):
     ops.LAUNCHES = 0
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     b.record()
     barrier()
-    ms = a.elapsed_time(b) / args.steps
+    ms = a.elapsed_time(b) / steps
     launches = ops.LAUNCHES
     clocks = sampler.stop()
     if world > 1:
-        halo_bytes = transport.bytes_sent // (args.steps + args.warmup)
+        halo_bytes = transport.bytes_sent // (steps + warmup)
     # e2e: every step's velocity field is read back to pinned host memory (what the reference's writer consumes)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         v = step()
         host_out.copy_(v[0] if isinstance(v, list) else v, non_blocking=False)
     barrier()
-    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    del eng
+    torch.cuda.empty_cache()
+    return {"model": model_name, "N": N, "E": E, "V": V, "ms": float(t[0]), "ms_e2e": float(t[1]), "launches": launches,
+            "clocks": clocks, "halo_bytes": halo_bytes, "out_rows": out_rows, "n1_ms": n1_ms, "halo": halo, "prec": prec}
+
+
+def strong_scaling_4m(world, rank, dev, dist, steps, halo):
+    """BASELINE.json configs[3] next to the headline number: the 4M-cell MGN rollout, domain-decomposed over the run's
+    N GPUs (strong scaling), so the driver's 1/2/4/8-GPU runs record it.  On N > 1 rank 0 first times the whole mesh on
+    one GPU, which makes the efficiency self-contained (same box, same clocks)."""
+    m = measure_rollout("mgn_rollout_4m", world, rank, dev, dist, steps=steps, warmup=3, halo=halo, single_gpu_too=True)
+    out = {"workload": "mgn_rollout_4m", "cells": m["N"], "faces": m["E"], "n_gpus": world, "steps": steps,
+           "ms_per_step": m["ms"], "edge_updates_per_s": m["E"] * MP_NUM / (m["ms"] * 1e-3),
+           "rollout_steps_per_s": 1e3 / m["ms"], "scaling": "strong",
+           "halo": ("NCCL send/receive of ghost-cell latents, once per GN_Block + once per step" if world > 1 else None),
+           "halo_bytes_per_step_rank0": m["halo_bytes"], "clocks": m["clocks"], "e2e_ms_per_step": m["ms_e2e"]}
+    if m["n1_ms"] is not None:
+        out["n1_ms_per_step"] = m["n1_ms"]
+        out["efficiency_vs_n1"] = m["n1_ms"] / (world * m["ms"])
+    return out
+
+
+def run_rollout(args, world, rank, dev, dist):
+    """Rollout workloads as the bench line (--workload *_rollout_*)."""
+    prec = args.precision or "bf16x3"
+    m = measure_rollout(args.workload, world, rank, dev, dist, args.steps, args.warmup, args.halo, prec)
+    model_name, N, E, V, ms, ms_e2e = m["model"], m["N"], m["E"], m["V"], m["ms"], m["ms_e2e"]
+    halo_bytes, out_rows, launches, clocks = m["halo_bytes"], m["out_rows"], m["launches"], m["clocks"]
     if rank == 0:
         line = {
             "metric": "processor edge-updates/sec", "value": E * MP_NUM / (ms * 1e-3), "unit": "edge-updates/s",
@@ -551,6 +661,10 @@ def run_rollout(args, world, rank, dev, dist):
                     "api": "RolloutEngine.step / PartitionedRollout.step + velocity read back to pinned host memory"},
             "gpu_launches": launches if world > 1 else "CUDA graph (kernels of one captured step replayed)",
             "clocks": clocks, "roofline": None, "cpu_baseline": None,
+            "roofline_forward": whole_pass_roofline(
+                MP_NUM * ((512 * (3 * E + 4 * N + V) + 16 * E + 12 * N) if not model_name.startswith("Conservative")
+                          else (512 * (3 * E + 4 * N) + 16 * E)), ms, peaks()[0],
+                "one rollout step over the processor's algorithmic bytes (SURVEY.md 8d; encoder / decoder / glue not counted)"),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         if (sj > 0) { PROF_WAIT(4, cp_async_wait_all(); named_bar_sync(1, TC_PROD_THREADS)); }
         stage_idx(sj + 3);
       }
-      PROF_WAIT(0, mbar_wait(&a_empty[st], sphase));
+      // one warp polls the stage's barrier, the others block on a named barrier (see the epilogue's group_wait)
+      PROF_WAIT(0, if (warp == TC_EPI_WARPS) mbar_wait(&a_empty[st], sphase); named_bar_sync(12, TC_PROD_THREADS));
       const KbDesc &dk = p.kb[skb];
       if (dk.tma) {
         // TMA gather: 2 parts x 32 groups of 4 rows = 64 gather4 copies per k-block, 8 per producer warp (lanes 0-7):
@@ -387,15 +388,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         // tensor map carries the same swizzle; the image is 1024 B aligned and a row group is 4 x 128 B).  Each warp
         // announces its own 8 x 512 B on the stage's barrier, which is also its arrival.
         const int pw = warp - TC_EPI_WARPS;
-        if (lane == 0) mbar_expect_tx(&a_full[st], 8 * 512);
-        __syncwarp();
-        if (lane < 8) {
-          const int part = pw >> 2, rg = (pw & 3) * 8 + lane;
-          const int32_t *ixs = s_idx + (sj & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT + dk.seg * 3 * TC_BM + rg * 4;
-          const int4 ix = lds_s32x4(smem_u32(ixs));
-          tma_gather4(sa_u32 + st * TC_STAGE_BYTES + part * TC_IMG + rg * 512, &p.tm_seg[dk.seg],
-                      dk.colk + part * dk.lo_col, ix.x, ix.y, ix.z, ix.w, &a_full[st]);
+        // ONE lane issues the warp's 8 copies in a loop: the tensor-map pointer, column and barrier then live in uniform
+        // registers and only the four row indices are moved per copy (8 divergent lanes made the compiler serialise the
+        // lanes with ~24 instructions per copy: 11.6 % of the kernel's executed instructions, ncu source view)
+#if GNNFD_ABL == 8      // ablation: no TMA gathers (stale operands)
+        if (lane == 0) mbar_arrive(&a_full[st]);
+#else
+        if (lane == 0) {
+          mbar_expect_tx(&a_full[st], 8 * 512);
+          const int part = pw >> 2, rg0 = (pw & 3) * 8;
+          const uint32_t ixa = smem_u32(s_idx + (sj & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT + dk.seg * 3 * TC_BM + rg0 * 4);
+          const uint32_t dst = sa_u32 + st * TC_STAGE_BYTES + part * TC_IMG + rg0 * 512;
+          const int colp = dk.colk + part * dk.lo_col;
+          const CUtensorMap *tm = &p.tm_seg[dk.seg];
+#pragma unroll 1
+          for (int g = 0; g < 8; ++g) {
+            const int4 ix = lds_s32x4(ixa + g * 16);
+            tma_gather4(dst + g * 512, tm, colp, ix.x, ix.y, ix.z, ix.w, &a_full[st]);
+          }
         }
+        __syncwarp();
+#endif
         if (++skb == p.kb1) { skb = 0; ++sj; }
         if (++st == a_stages) { st = 0; sphase ^= 1; }
         return;
@@ -602,6 +615,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     const uint32_t stg = smem_u32(s_stg + warp * (32 * 16));   // this warp's 32 x 16 staging block (XOR-swizzled)
     const uint32_t vec = smem_u32(s_vec), stat = smem_u32(s_stat);
     const int rr = lane >> 2, c4 = lane & 3;               // copy-out mapping: 8 rows x 64 B per instruction
+    // Waiting on an mbarrier polls (try_wait wakes every ~100 cycles: 4 instructions per poll per warp - with 8 warps of
+    // a group, 8 producer warps and the issuers all polling, 29 % of the kernel's executed instructions were polls, ncu
+    // source view).  So ONE warp of the group polls and the other seven block on a named barrier, which costs no issue
+    // slots at all.
+    auto group_wait = [&](uint64_t *bar, uint32_t parity) {
+      if ((warp & 7) == 0) mbar_wait(bar, parity);
+      named_bar_sync(10 + grp, TC_EPI_GROUP * 32);
+    };
     PROF_DECL;
     for (int j = grp; j < T; j += 2) {
       const int xs = j % TC_X_SLOTS, n = j / TC_X_SLOTS;
@@ -623,7 +644,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) m4[i] = ldg_f4(hm + i * 4);
         }
-        PROF_WAIT(0, mbar_wait(&acc_full[xs], (3 * n + layer) & 1));
+        PROF_WAIT(0, group_wait(&acc_full[xs], (3 * n + layer) & 1));
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -674,7 +695,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         if (lane == 0) mbar_arrive(&hid_ready[xs * 2 + eh]);
       }
       // ---- final epilogue
-      PROF_WAIT(1, mbar_wait(&acc_full[xs], (p.nl * n + p.nl - 1) & 1));
+      PROF_WAIT(1, group_wait(&acc_full[xs], (p.nl * n + p.nl - 1) & 1));
       tc_fence_after();
       if constexpr (EPI == 1) {
         // ---- fast final epilogue (inference: no stash, no mul, n_out = 128).  Thread = row: bias -> LayerNorm -> affine in
@@ -755,7 +776,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             *reinterpret_cast<uint4 *>(sp + TC_H) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             *reinterpret_cast<uint4 *>(sp + TC_H + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
           }
+#if GNNFD_ABL == 9      // ablation: nothing leaves the fast epilogue through the staging block
+          if (false) {
+#else
           if (epi & (EPI_ST_RAW | EPI_RED_SUM | EPI_LDRES)) {
+#endif
             // the previous group's TMA copy must have finished READING the staging block before it is overwritten
             if (lane == 0) bulk_wait_read0();
             __syncwarp();

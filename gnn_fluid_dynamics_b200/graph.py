@@ -144,7 +144,8 @@ def collate(graphs: Iterable[Data], offsets: dict | None = None) -> Data:
                 out._store[k] = torch.cat(vals, dim=0)
         else:
             out._store[k] = v0
-    batch = torch.cat([torch.full((n,), i, dtype=torch.long) for i, n in enumerate(n_nodes)])
+    dev = next((v.device for v in graphs[0]._store.values() if torch.is_tensor(v)), None)   # device graphs collate on the device
+    batch = torch.cat([torch.full((n,), i, dtype=torch.long, device=dev) for i, n in enumerate(n_nodes)])
     out._store["batch"] = batch
     return out
 

@@ -13,6 +13,12 @@ import torch
 from . import ops
 
 
+def _tensor_key(t):
+    """Identity of a tensor's contents as far as the host can tell without a sync: storage address + version counter
+    (in-place writes bump it)."""
+    return None if t is None else (t.data_ptr(), t._version, tuple(t.shape))
+
+
 class MeshTopology:
     """``__gnnfd_shared__`` makes ``Data.clone()/to()`` pass the object by reference, so a topology
     attached to ``v_graph.topology`` survives the per-step ``g.clone()`` of the rollout loop
@@ -51,6 +57,31 @@ class MeshTopology:
         if need_cell_csr:
             self.build_cell_csr()
         self._vtx_n_offsets = None
+        self.static = False          # attach_topology: the caller vouches that the mesh does not change
+        self._c_key = _tensor_key(c_edge_index)
+        self._v_key = (_tensor_key(v_edge_index), _tensor_key(v_face))
+
+    def refresh_orientation(self, c_edge_index: torch.Tensor):
+        """New owner / neighbour orientation of the SAME mesh (the reference re-flips ``c_graph.edge_index`` per
+        training sample, ``transforms.py:3-7``): row / col are re-narrowed and the cell CSRs (which depend on the
+        orientation) are dropped and rebuilt on demand; the vertex CSR, ``vf`` and the vf-CSR are static per mesh and
+        kept."""
+        if c_edge_index.shape[1] != self.n_faces:
+            raise RuntimeError("refresh_orientation: a different mesh (face count changed)")
+        cei = ops.index_narrow(c_edge_index, self.n_cells)
+        self._flags = self._flags[1:] + [cei._gnnfd_range_flag] if self._flags else [cei._gnnfd_range_flag]
+        self.row, self.col = cei[0], cei[1]
+        self.cell_offsets = self.cell_perm = None
+        self._rowcol = self._rowcsr = self._colcsr = None
+        self._c_key = _tensor_key(c_edge_index)
+        return self
+
+    def matches(self, c_edge_index, v_edge_index, v_face) -> str:
+        """'same' (built from exactly these tensors, unmodified since), 'orientation' (same vertex-side tensors,
+        another or a modified ``c_graph.edge_index``) or 'other'."""
+        if (_tensor_key(v_edge_index), _tensor_key(v_face)) != self._v_key:
+            return "other"
+        return "same" if _tensor_key(c_edge_index) == self._c_key else "orientation"
 
     def build_cell_csr(self):
         """CSR of cat[col; row] over cells (Conservative.py:244-245)."""
@@ -121,15 +152,26 @@ def get_topology(graphs, need_cell_csr: bool = False, two_hop: bool = True) -> M
         topo = getattr(c, "topology", None)
     if isinstance(topo, MeshTopology) and topo.n_faces == c.edge_index.shape[1] \
             and topo.n_cells == c.x.shape[0] and (not two_hop or topo.vtx_offsets is not None):
-        if need_cell_csr:
-            topo.build_cell_csr()
-        return topo
+        # a topology hung on the graphs by attach_topology is static by contract (rollout: the per-step g.clone() of
+        # rollout.py:313 gives every step fresh tensors of the same mesh).  Any other attached topology is only trusted
+        # for the tensors it was built from: a re-flipped / modified c_graph.edge_index of the same mesh refreshes the
+        # orientation-dependent part, anything else is rebuilt.
+        how = "same" if topo.static else topo.matches(c.edge_index, v.edge_index if two_hop else None,
+                                                      v.face if two_hop else None)
+        if how == "orientation":
+            topo.refresh_orientation(c.edge_index)
+            how = "same"
+        if how == "same":
+            if need_cell_csr:
+                topo.build_cell_csr()
+            return topo
     return MeshTopology.from_graphs(graphs, need_cell_csr, two_hop)
 
 
 def attach_topology(graphs, need_cell_csr: bool = False, two_hop: bool = True) -> MeshTopology:
     """Build the topology once and hang it on the graphs (static meshes: rollout, validation)."""
     topo = MeshTopology.from_graphs(graphs, need_cell_csr, two_hop).validate()
+    topo.static = True
     graphs[0].topology = topo
     if graphs[2] is not None:
         graphs[2].topology = topo
