@@ -30,7 +30,7 @@ EXPORTS = [
     "gnnfd_glue_workspace_bytes", "gnnfd_face_area_norm", "gnnfd_face_area_norm_backward", "gnnfd_fvm_integrate",
     "gnnfd_fvm_integrate_backward", "gnnfd_masked_mse", "gnnfd_masked_mse_backward", "gnnfd_state_advance",
 ]
-ABI_VERSION = 4
+ABI_VERSION = 3
 
 
 class Segment(C.Structure):
@@ -63,7 +63,6 @@ class WgradArgs(C.Structure):
         ("rows", C.c_int64), ("a", Segment), ("a_act", C.c_int32), ("n_b", C.c_int32), ("b", Segment * 3),
         ("b_act", C.c_int32), ("out", C.c_void_p), ("ld_out", C.c_int32), ("transpose_out", C.c_int32),
         ("colsum", C.c_void_p), ("colsum_of_b", C.c_int32), ("precision", C.c_int32),
-        ("ln_xhat", C.c_void_p), ("ln_rstd", C.c_void_p), ("ln_w", C.c_void_p), ("ln_dy", C.c_void_p),
     ]
 
 

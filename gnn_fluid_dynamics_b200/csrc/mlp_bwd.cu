@@ -147,32 +147,26 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
   const int n_out = f->n_out;
   int rc;
 
-  // ---- LayerNorm backward, fused into the load of dW3's A operand (the producer warp that stages a row of g turns
-  //      it into dy, writes dy for the chain below and accumulates d ln_w / d ln_b / d b3): no separate pass
+  // ---- LayerNorm backward
   const float *dy = b->g;
   bool b3_from_ln = false;
-  auto direct = [](const float *src, int ld, int width) {
-    gnnfd_segment s{};
-    s.src = src; s.ld = ld; s.col = 0; s.width = width; s.mode = GNNFD_SEG_DIRECT;
-    return s;
-  };
   if (f->has_ln) {
     GNNFD_CHECK_ARG(n_out == 128 && b->xhat && b->rstd, "LayerNorm backward needs xhat/rstd and n_out == 128");
     float *dyb = (float *)(ws + L.dy);
-    gnnfd_wgrad_args w{};
-    w.rows = f->rows;
-    w.a = direct(b->g, 128, 128); w.n_b = 1; w.b[0] = direct(b->a2, 128, 128); w.b_act = code;
-    w.out = b->d_w3; w.ld_out = 128; w.colsum = sums;
-    w.ln_xhat = b->xhat; w.ln_rstd = b->rstd; w.ln_w = f->ln_w; w.ln_dy = dyb;
-    if ((rc = gnnfd_wgrad(&w, wgws, wgws_bytes, stream)) != GNNFD_OK) return rc;
+    if ((rc = ln_backward_launch(b->g, b->xhat, b->rstd, f->ln_w, f->rows, dyb, sums, ws + L.lnws, L.wgws - L.lnws, stream)) != GNNFD_OK) return rc;
     dy = dyb;
     if (b->d_ln_w) GNNFD_CUDA(cudaMemcpyAsync(b->d_ln_w, sums, 128 * 4, cudaMemcpyDeviceToDevice, stream));
     if (b->d_ln_b) GNNFD_CUDA(cudaMemcpyAsync(b->d_ln_b, sums + 128, 128 * 4, cudaMemcpyDeviceToDevice, stream));
     if (b->d_b3) GNNFD_CUDA(cudaMemcpyAsync(b->d_b3, sums + 256, 128 * 4, cudaMemcpyDeviceToDevice, stream));
     b3_from_ln = true;
   }
-  // ---- dW3 = dy^T act(a2)   (MLPs without LayerNorm: decoder heads, the bias-free tanh blocks)
-  if (!f->has_ln) {
+  auto direct = [](const float *src, int ld, int width) {
+    gnnfd_segment s{};
+    s.src = src; s.ld = ld; s.col = 0; s.width = width; s.mode = GNNFD_SEG_DIRECT;
+    return s;
+  };
+  // ---- dW3 = dy^T act(a2)
+  {
     gnnfd_wgrad_args w{};
     w.rows = f->rows;
     float *cs = (b->d_b3 && !b3_from_ln) ? b->d_b3 : nullptr;

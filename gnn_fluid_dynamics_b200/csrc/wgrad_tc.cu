@@ -48,11 +48,8 @@ struct WgParams {
   int stages;
   int64_t rows_per_cta;    // multiple of WG_KR
   float *partial;          // [grid][128][n_pad]
-  float *colsum;           // [grid][n_cs][128] or nullptr
+  float *colsum;           // [grid][128] or nullptr
   int colsum_piece;
-  // LayerNorm backward fused into the load of piece 0 (template LN): piece 0's source is g
-  const float *ln_xhat, *ln_rstd, *ln_w;
-  float *ln_dy;
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
@@ -142,9 +139,12 @@ __device__ __forceinline__ float4 wg_load_item(const WgPiece &pc, int lane, bool
 
 // NP = pieces (A + NP - 1 column blocks of B); MODE 0 split-bf16 (two 16-bit images per operand), 1 TF32.
 // Both modes stage 32 rows x 4 bytes per element: A 16 KB + B n_pad * 128 B per stage.
-// LN: piece 0 is the gradient at a LayerNorm output; the staging warp (one warp = one row) turns it into dy on the
-// fly, writes dy for the input-gradient chain and accumulates the three parameter-gradient column sums (NP == 2 only).
-template <int NP, int MODE, bool LN = false>
+// LEAN > 0 (NP == 2, MODE == 0 only): the producers run a loop specialised for the case that carries almost all of a
+// training step's weight-gradient bytes - A and B both DIRECT, contiguous [rows, 128] matrices, B optionally a saved
+// pre-activation (LEAN - 1 = its activation: 0 none, 1 SiLU, 2 tanh).  Running row pointers instead of per-load 64-bit
+// index arithmetic, no per-piece mode / width predicates, THREE stages of loads in flight per warp: ~120 instructions
+// per warp and stage against ~340 of the generic assembly loop, which paced the kernel (issue-bound at 2.7 TB/s).
+template <int NP, int MODE, int LEAN = 0>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -157,9 +157,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const uint32_t b_bytes = 32 * (uint32_t)p.n_pad * 4;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t *s_tail = smem + (size_t)p.stages * stage_bytes;
-  constexpr int NCS = LN ? 3 : 1;                               // column-sum vectors per CTA
-  float *s_cs = (float *)s_tail;                                // [NCS][16 warps][128] column-sum scratch
-  uint64_t *s_bar = (uint64_t *)(s_tail + NCS * WG_PROD_WARPS * 128 * 4);
+  float *s_cs = (float *)s_tail;                                // [16 warps][128] column-sum scratch
+  uint64_t *s_bar = (uint64_t *)(s_tail + WG_PROD_WARPS * 128 * 4);
   uint64_t *full = s_bar, *empty = s_bar + WG_MAX_STAGES, *done = s_bar + 2 * WG_MAX_STAGES;
   uint32_t *s_tmem = (uint32_t *)(s_bar + 2 * WG_MAX_STAGES + 1);
 
@@ -183,9 +182,65 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     // =============================================================================== producers
     // warp w owns rows {w, w + 16} of every stage; lane l owns float4 column l of each piece
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 cs_gx = cs, cs_g = cs;                                // LN: column sums of g xhat (d ln_w) and g (d ln_b)
-    float4 lnw4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (LN && p.ln_w != nullptr) lnw4 = ldg_f4(p.ln_w + lane * 4);
+    if constexpr (LEAN > 0) {
+      constexpr int ACT = LEAN - 1;
+      const int n_local = (int)(r_end - r_begin);                       // rows of this CTA (> 0)
+      const float *la = p.pc[0].src + (r_begin + warp) * 128 + lane * 4;   // load pointers of the next stage to fetch
+      const float *lb = p.pc[1].src + (r_begin + warp) * 128 + lane * 4;
+      int lrow = warp;                                                   // its first row, relative to r_begin
+      // image offset of the lane's 4 columns of stage row `warp` (see the generic path below); row + 16 = 2 K atoms on
+      const uint32_t off = (uint32_t)(((warp >> 3) * 2 + (lane >> 4)) * 1024 + (warp & 7) * 128 +
+                                      (((((lane & 15) >> 1) ^ (warp & 7))) << 4) + ((lane & 1) << 3));
+      constexpr uint32_t JSTEP = 4096, PART = 8192;
+      const bool want_cs = p.colsum != nullptr;
+      auto fetch = [&](float4(&a)[2], float4(&b)[2]) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool ok = lrow + 16 * j < n_local;
+          a[j] = ok ? ldg_f4(la + j * 16 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[j] = ok ? ldg_f4(lb + j * 16 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        la += WG_KR * 128; lb += WG_KR * 128; lrow += WG_KR;
+      };
+      const int n_stages = p.stages;
+      int st = 0;
+      uint32_t st_round = 0;
+      auto put = [&](const float4(&a)[2], const float4(&b)[2]) {
+        const uint32_t sA = smem_u32(smem + (size_t)st * stage_bytes) + off, sB = sA + a_bytes;
+        if (st_round > 0) mbar_wait(&empty[st], (st_round - 1) & 1);
+        if (want_cs) {
+          cs.x += a[0].x + a[1].x; cs.y += a[0].y + a[1].y; cs.z += a[0].z + a[1].z; cs.w += a[0].w + a[1].w;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t h0, l0, h1, l1;
+          split2<false>(a[j].x, a[j].y, h0, l0); split2<false>(a[j].z, a[j].w, h1, l1);
+          sts_u2(sA + j * JSTEP, h0, h1);
+          sts_u2(sA + j * JSTEP + PART, l0, l1);
+          float4 t = b[j];
+          if (ACT == 1) { t.x = wg_silu(t.x); t.y = wg_silu(t.y); t.z = wg_silu(t.z); t.w = wg_silu(t.w); }
+          else if (ACT == 2) { t.x = tanhf(t.x); t.y = tanhf(t.y); t.z = tanhf(t.z); t.w = tanhf(t.w); }
+          split2<false>(t.x, t.y, h0, l0); split2<false>(t.z, t.w, h1, l1);
+          sts_u2(sB + j * JSTEP, h0, h1);
+          sts_u2(sB + j * JSTEP + PART, l0, l1);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[st]);
+        if (++st == n_stages) { st = 0; ++st_round; }
+      };
+      float4 a0[2], b0[2], a1[2], b1[2], a2[2], b2[2];
+      fetch(a0, b0);
+      fetch(a1, b1);
+      for (int it = 0; it < n_stage_iters; it += 3) {
+        fetch(a2, b2);
+        put(a0, b0);
+        fetch(a0, b0);
+        if (it + 1 < n_stage_iters) put(a1, b1);
+        fetch(a1, b1);
+        if (it + 2 < n_stage_iters) put(a2, b2);
+      }
+    } else {
     // gather indices of a stage, one per lane: lane = slot * 2 + row slot (fetched one stage before use)
     auto load_idx = [&](int it) -> int32_t {
       const int j = lane & 1, q = lane >> 1;
@@ -216,16 +271,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
                               (((((lane & 7) >> 1) ^ (warp & 3))) << 5) + ((lane & 1) << 4));
       }
     }
-    auto load_stage = [&](int it, int32_t idx, float4(&v)[NP][2], float4(&xh)[2], float(&rs)[2]) {
-      if (LN) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 16 * j;
-          const bool row_ok = it < n_stage_iters && g < r_end;
-          xh[j] = row_ok ? ldg_f4(p.ln_xhat + g * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          rs[j] = row_ok ? __ldg(p.ln_rstd + g) : 0.f;
-        }
-      }
+    auto load_stage = [&](int it, int32_t idx, float4(&v)[NP][2]) {
 #pragma unroll
       for (int pi = 0; pi < NP; ++pi) {
         const WgPiece &pc = p.pc[pi];
@@ -257,34 +303,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int n_stages = p.stages;
     int st = 0;
     uint32_t st_round = 0;
-    auto store_stage = [&](int it, const float4(&v)[NP][2], const float4(&xh)[2], const float(&rs)[2]) {
+    auto store_stage = [&](int it, const float4(&v)[NP][2]) {
       uint8_t *sA = smem + (size_t)st * stage_bytes, *sB = sA + a_bytes;
-      float4 dyv[2];
-      if (LN) {
-        // dy = rstd (g w - mean(g w) - xhat mean(g w xhat)) of the warp's two rows (rows past the end: all zeros)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float4 g4 = v[0][j], x4 = xh[j];
-          const float4 gw = make_float4(g4.x * lnw4.x, g4.y * lnw4.y, g4.z * lnw4.z, g4.w * lnw4.w);
-          float a = (gw.x + gw.y) + (gw.z + gw.w);
-          float b = (gw.x * x4.x + gw.y * x4.y) + (gw.z * x4.z + gw.w * x4.w);
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            b += __shfl_xor_sync(0xffffffffu, b, o);
-          }
-          a *= (1.0f / 128.0f);
-          b *= (1.0f / 128.0f);
-          float4 d;
-          d.x = rs[j] * (gw.x - a - x4.x * b); d.y = rs[j] * (gw.y - a - x4.y * b);
-          d.z = rs[j] * (gw.z - a - x4.z * b); d.w = rs[j] * (gw.w - a - x4.w * b);
-          dyv[j] = d;
-          const int64_t g = r_begin + (int64_t)it * WG_KR + warp + 16 * j;
-          if (g < r_end) *reinterpret_cast<float4 *>(p.ln_dy + g * 128 + lane * 4) = d;
-          cs_gx.x += g4.x * x4.x; cs_gx.y += g4.y * x4.y; cs_gx.z += g4.z * x4.z; cs_gx.w += g4.w * x4.w;
-          cs_g.x += g4.x; cs_g.y += g4.y; cs_g.z += g4.z; cs_g.w += g4.w;
-        }
-      }
       if (st_round > 0) mbar_wait(&empty[st], (st_round - 1) & 1);
 #pragma unroll
       for (int pi = 0; pi < NP; ++pi) {
@@ -292,7 +312,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           const int act = p.pc[pi].act;
           uint8_t *img = (pi == 0 ? sA : sB) + off0[pi];
           float4 t0 = v[pi][0], t1 = v[pi][1];
-          if (LN && pi == 0) { t0 = dyv[0]; t1 = dyv[1]; }
           if (pi == p.colsum_piece) {
             cs.x += t0.x + t1.x; cs.y += t0.y + t1.y; cs.z += t0.z + t1.z; cs.w += t0.w + t1.w;
           }
@@ -328,32 +347,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (++st == n_stages) { st = 0; ++st_round; }
     };
     // two stages of loads in flight per warp: the loads of stage it + 1 are issued before stage it is converted
-    float4 v0[NP][2], v1[NP][2], xh0[2], xh1[2];
-    float rs0[2], rs1[2];
+    float4 v0[NP][2], v1[NP][2];
     int32_t ix1 = load_idx(1);
-    load_stage(0, load_idx(0), v0, xh0, rs0);
+    load_stage(0, load_idx(0), v0);
     for (int it = 0; it < n_stage_iters; it += 2) {
       const int32_t ix2 = load_idx(it + 2);
-      load_stage(it + 1, ix1, v1, xh1, rs1);
-      store_stage(it, v0, xh0, rs0);
+      load_stage(it + 1, ix1, v1);
+      store_stage(it, v0);
       const int32_t ix3 = load_idx(it + 3);
-      load_stage(it + 2, ix2, v0, xh0, rs0);
-      if (it + 1 < n_stage_iters) store_stage(it + 1, v1, xh1, rs1);
+      load_stage(it + 2, ix2, v0);
+      if (it + 1 < n_stage_iters) store_stage(it + 1, v1);
       ix1 = ix3;
     }
+    }   // generic producers
     if (p.colsum != nullptr) {   // column sums: warps reduced in fixed order
-      *reinterpret_cast<float4 *>(s_cs + warp * 128 + lane * 4) = LN ? cs_gx : cs;
-      if (LN) {
-        *reinterpret_cast<float4 *>(s_cs + (WG_PROD_WARPS + warp) * 128 + lane * 4) = cs_g;
-        *reinterpret_cast<float4 *>(s_cs + (2 * WG_PROD_WARPS + warp) * 128 + lane * 4) = cs;     // colsum(dy) = d b3
-      }
+      *reinterpret_cast<float4 *>(s_cs + warp * 128 + lane * 4) = cs;
       named_bar_sync(1, WG_PROD_WARPS * 32);
-      for (int i = tid; i < NCS * 128; i += WG_PROD_WARPS * 32) {
-        const int vsel = i >> 7, c = i & 127;
+      if (tid < 128) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < WG_PROD_WARPS; ++w) s += s_cs[(vsel * WG_PROD_WARPS + w) * 128 + c];
-        p.colsum[(size_t)blockIdx.x * (NCS * 128) + i] = s;
+        for (int w = 0; w < WG_PROD_WARPS; ++w) s += s_cs[w * 128 + tid];
+        p.colsum[(size_t)blockIdx.x * 128 + tid] = s;
       }
     }
     // ================================================================================ epilogue
@@ -420,33 +434,41 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
 }
 
 // out[m, j] = sum over the split-K partials part[c][m][j] (+ column sums), optionally stored transposed.
-// 64 outputs x 4 part-groups per block: group y adds parts y, y + 4, ... (coalesced across the 64 outputs), the four
-// group sums are combined in fixed order - deterministic, and 4x the memory parallelism of one thread per output.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__restrict__ part, int n_parts, int n_pad,
+// 32 outputs x 16 part-groups per block: group y adds parts y, y + 16, ... (coalesced across the 32 outputs: ~10 loads in
+// flight per thread instead of ~37 dependent-latency-bound ones), the sixteen group sums are combined by a fixed tree -
+// deterministic.  (This launch follows every weight-gradient GEMM: ~110 per training step.)
+constexpr int RP_OUT = 32, RP_GROUPS = 16;
+__global__ void __launch_bounds__(RP_OUT * RP_GROUPS) reduce_partials_kernel(const float *__restrict__ part, int n_parts, int n_pad,
                                                               int m_valid, int n_valid, float *__restrict__ out,
                                                               int ld_out, int transpose, const float *__restrict__ cs_part,
-                                                              float *__restrict__ cs_out, int cs_valid, int cs_stride) {
-  __shared__ float s_sum[4][64];
+                                                              float *__restrict__ cs_out, int cs_valid) {
+  __shared__ float s_sum[RP_GROUPS][RP_OUT];
   const int total = m_valid * n_valid;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int i = blockIdx.x * 64 + tx;
+  const int tx = threadIdx.x & (RP_OUT - 1), ty = threadIdx.x / RP_OUT;
+  const int i = blockIdx.x * RP_OUT + tx;
   float s = 0.f;
   if (i < total) {
     const int m = i / n_valid, j = i % n_valid;
     const float *src = part + (size_t)m * n_pad + j;
-    for (int c = ty; c < n_parts; c += 4) s += src[(size_t)c * 128 * n_pad];
+    for (int c = ty; c < n_parts; c += RP_GROUPS) s += src[(size_t)c * 128 * n_pad];
   } else if (cs_out != nullptr && i - total < cs_valid) {
-    for (int c = ty; c < n_parts; c += 4) s += cs_part[(size_t)c * cs_stride + (i - total)];
+    for (int c = ty; c < n_parts; c += RP_GROUPS) s += cs_part[(size_t)c * 128 + (i - total)];
   }
   s_sum[ty][tx] = s;
   __syncthreads();
   if (ty == 0) {
-    const float r = (s_sum[0][tx] + s_sum[1][tx]) + (s_sum[2][tx] + s_sum[3][tx]);
+    float r[RP_GROUPS];
+#pragma unroll
+    for (int g = 0; g < RP_GROUPS; ++g) r[g] = s_sum[g][tx];
+#pragma unroll
+    for (int w = RP_GROUPS / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int g = 0; g < w; ++g) r[g] += r[g + w];
     if (i < total) {
       const int m = i / n_valid, j = i % n_valid;
-      if (transpose) out[(size_t)j * ld_out + m] = r; else out[(size_t)m * ld_out + j] = r;
+      if (transpose) out[(size_t)j * ld_out + m] = r[0]; else out[(size_t)m * ld_out + j] = r[0];
     } else if (cs_out != nullptr && i - total < cs_valid) {
-      cs_out[i - total] = r;
+      cs_out[i - total] = r[0];
     }
   }
 }
@@ -475,7 +497,7 @@ extern "C" size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padde
   if (rows <= 0) return 256;
   int grid;
   wg_rows_per_cta(rows, grid);
-  return (size_t)grid * 128 * (size_t)n_cols_padded * 4 + (size_t)grid * 3 * 128 * 4 + 256;
+  return (size_t)grid * 128 * (size_t)n_cols_padded * 4 + (size_t)grid * 128 * 4 + 256;
 }
 
 extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t workspace_bytes, void *stream_) {
@@ -492,18 +514,7 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
     GNNFD_CHECK_ARG(s == a->n_b - 1 || (a->b[s].width & 63) == 0, "only the last B segment may be narrower than a multiple of 64");
     n_valid += a->b[s].width;
   }
-  const bool ln = a->ln_xhat != nullptr;
-  if (ln) {
-    GNNFD_CHECK_ARG(a->n_b == 1 && a->a.width == 128 && a->a.ld == 128 && a->a.col == 0 && a->precision == 0 &&
-                    a->ln_rstd != nullptr && a->ln_dy != nullptr && a->colsum != nullptr && !a->colsum_of_b &&
-                    a->a_act == 0 && !a->transpose_out,
-                    "fused LayerNorm backward: needs n_b == 1, a 128-wide contiguous g, rstd, dy, a 3 x 128 colsum, split-bf16");
-    GNNFD_CHECK_ARG(((reinterpret_cast<uintptr_t>(a->ln_xhat) | reinterpret_cast<uintptr_t>(a->ln_dy) |
-                      reinterpret_cast<uintptr_t>(a->a.src) | reinterpret_cast<uintptr_t>(a->ln_w)) & 15) == 0,
-                    "fused LayerNorm backward: 16-byte aligned pointers");
-  }
-  const int n_cs = ln ? 3 : 1;
-  const int cs_valid = a->colsum ? (ln ? 384 : (a->colsum_of_b ? a->b[0].width : a->a.width)) : 0;
+  const int cs_valid = a->colsum ? (a->colsum_of_b ? a->b[0].width : a->a.width) : 0;
   if (a->rows == 0) {
     const int m_valid = a->a.width;
     if (a->transpose_out) { for (int j = 0; j < n_valid; ++j) GNNFD_CUDA(cudaMemsetAsync(a->out + (size_t)j * a->ld_out, 0, m_valid * 4, stream)); }
@@ -516,13 +527,12 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
   p.rows_per_cta = wg_rows_per_cta(a->rows, grid);
   p.rows = a->rows;
   p.n_pad = n_pad;
-  const size_t need = (size_t)grid * 128 * (size_t)n_pad * 4 + (size_t)grid * n_cs * 128 * 4;
+  const size_t need = (size_t)grid * 128 * (size_t)n_pad * 4 + (size_t)grid * 128 * 4;
   if (workspace == nullptr || workspace_bytes < need) { set_error("gnnfd_wgrad: workspace too small"); return GNNFD_E_WORKSPACE; }
   p.partial = (float *)workspace;
   float *cs_part = p.partial + (size_t)grid * 128 * n_pad;
   p.colsum = a->colsum ? cs_part : nullptr;
   p.colsum_piece = a->colsum ? (a->colsum_of_b ? 1 : 0) : -1;
-  p.ln_xhat = a->ln_xhat; p.ln_rstd = a->ln_rstd; p.ln_w = a->ln_w; p.ln_dy = a->ln_dy;
   p.n_pieces = 1 + a->n_b;
   int atom = 0, slot = 0;
   for (int pi = 0; pi < p.n_pieces; ++pi) {
@@ -548,8 +558,8 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
   const uint32_t stage_bytes = 16 * 1024 + (uint32_t)n_pad * 128;
   int stages = (int)((200u * 1024u) / stage_bytes);
   p.stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
-  const int smem = p.stages * (int)stage_bytes + n_cs * WG_PROD_WARPS * 128 * 4 + (2 * WG_MAX_STAGES + 1) * 8 + 64 + 1024;
-#define WG_LAUNCH(NP_, MD_, ...)                                                                               \
+  const int smem = p.stages * (int)stage_bytes + WG_PROD_WARPS * 128 * 4 + (2 * WG_MAX_STAGES + 1) * 8 + 64 + 1024;
+#define WG_LAUNCH(NP_, MD_, ...)                                                                                \
   do {                                                                                                         \
     static bool attr[GNNFD_MAX_DEVICES] = {false};                                                                                  \
     if (!attr[current_device()]) {                                                                                               \
@@ -558,16 +568,24 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
     }                                                                                                          \
     wgrad_tc_kernel<NP_, MD_, ##__VA_ARGS__><<<grid, WG_THREADS, smem, stream>>>(p);                            \
   } while (0)
-  if (ln) WG_LAUNCH(2, 0, true);
-  else if (a->precision == 1) { if (p.n_pieces == 2) WG_LAUNCH(2, 1); else if (p.n_pieces == 3) WG_LAUNCH(3, 1); else WG_LAUNCH(4, 1); }
+  // the dominant case of a training step (dW2 / dW3 / the direct column block of dW1): both operands contiguous
+  // [rows, 128] matrices -> the lean producer loop
+  const gnnfd_segment &b0 = a->b[0];
+  const bool lean = a->precision == 0 && a->n_b == 1 && a->a.mode == GNNFD_SEG_DIRECT && b0.mode == GNNFD_SEG_DIRECT &&
+                    a->a.width == 128 && b0.width == 128 && a->a.ld == 128 && b0.ld == 128 && a->a.col == 0 && b0.col == 0 &&
+                    a->a_act == 0 && !a->colsum_of_b && n_pad == 128 &&
+                    ((reinterpret_cast<uintptr_t>(a->a.src) | reinterpret_cast<uintptr_t>(b0.src)) & 15) == 0;
+  if (lean) {
+    if (a->b_act == 0) WG_LAUNCH(2, 0, 1); else if (a->b_act == 1) WG_LAUNCH(2, 0, 2); else WG_LAUNCH(2, 0, 3);
+  } else
+  if (a->precision == 1) { if (p.n_pieces == 2) WG_LAUNCH(2, 1); else if (p.n_pieces == 3) WG_LAUNCH(3, 1); else WG_LAUNCH(4, 1); }
   else { if (p.n_pieces == 2) WG_LAUNCH(2, 0); else if (p.n_pieces == 3) WG_LAUNCH(3, 0); else WG_LAUNCH(4, 0); }
 #undef WG_LAUNCH
   GNNFD_LAUNCH_CHECK();
   const int m_valid = a->a.width;
   const int total = m_valid * n_valid + cs_valid;
-  reduce_partials_kernel<<<(total + 63) / 64, 256, 0, stream>>>(p.partial, grid, n_pad, m_valid, n_valid, a->out,
-                                                                  a->ld_out, a->transpose_out, cs_part, a->colsum, cs_valid,
-                                                                  n_cs * 128);
+  reduce_partials_kernel<<<(total + RP_OUT - 1) / RP_OUT, RP_OUT * RP_GROUPS, 0, stream>>>(p.partial, grid, n_pad, m_valid, n_valid, a->out,
+                                                                  a->ld_out, a->transpose_out, cs_part, a->colsum, cs_valid);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

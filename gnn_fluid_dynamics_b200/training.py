@@ -72,20 +72,28 @@ def edge_mlp_backward_node_side(w: MLPWeights, st: MLPStash, e_in, x_src, topo: 
     # dW1[:, 0:128] = dA1^T e, db1 = column sums of dA1
     w1g = grads["w1"]
     ops.wgrad(Seg(d_a1), [Seg(e_in)], E, w1g[:, 0:H], colsum=grads.get("b1"))
-    # S_row, S_col: dA1 reduced onto the cells (deterministic CSR sums)
+    # S = [S_row | S_col]: dA1 reduced onto the cells (two deterministic CSR sums into the column halves of ONE matrix)
     r_off, r_perm = topo.build_row_csr()
     c_off, c_perm = topo.build_col_csr()
-    s_row = ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, r_off, r_perm, N)
-    s_col = ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, c_off, c_perm, N)
-    # dW1[:, 128:256] = S_row^T x, dW1[:, 256:384] = S_col^T x   (N rows, contiguous operands)
-    ops.wgrad(Seg(s_row), [Seg(x_src)], N, w1g[:, H:2 * H])
-    ops.wgrad(Seg(s_col), [Seg(x_src)], N, w1g[:, 2 * H:3 * H])
-    # d x = base + S_row W1[:, 128:256] + S_col W1[:, 256:384]   (two Linears over N rows, accumulated in place)
+    s_rc = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
+    ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, r_off, r_perm, N, out=s_rc[:, :H])
+    ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, c_off, c_perm, N, out=s_rc[:, H:])
+    # dW1[:, 128:256] = S_row^T x and dW1[:, 256:384] = S_col^T x as ONE weight-gradient GEMM x^T S (x is read once; N
+    # contiguous rows), stored transposed into a [256, 128] scratch whose halves are the two column blocks of dW1
+    t_rc = torch.empty(2 * H, H, dtype=torch.float32, device=dev)
+    ops.wgrad(Seg(x_src), [Seg(s_rc, col=0, width=H), Seg(s_rc, col=H, width=H)], N, t_rc, transpose_out=True,
+              workspace=workspace)
+    w1g[:, H:2 * H].copy_(t_rc[:H])
+    w1g[:, 2 * H:3 * H].copy_(t_rc[H:])
+    # d x = base + S_row W1[:, 128:256] + S_col W1[:, 256:384] = base + S . Wcat with Wcat = [W1[:, 128:256]; W1[:, 256:384]]
+    # stacked along K: ONE K = 256 Linear over N rows
     if w.bwd_packs is None:
         w.bwd_packs = {}
     packs = w.bwd_packs.setdefault("node_side", {})
-    d_x = ops.linear_tc(Seg(s_row), N, w.w1[:, H:], 1, 3 * H, H, H, packs, "w1t_row", prec, residual=d_x_base)
-    d_x = ops.linear_tc(Seg(s_col), N, w.w1[:, 2 * H:], 1, 3 * H, H, H, packs, "w1t_col", prec, residual=d_x, out=d_x)
+    wcat = packs.get("wcat")
+    if wcat is None:
+        wcat = packs["wcat"] = torch.cat([w.w1[:, H:2 * H], w.w1[:, 2 * H:3 * H]], dim=0).contiguous()     # [256 (k), 128 (n)]
+    d_x = ops.linear_tc(Seg(s_rc), N, wcat, 1, H, H, 2 * H, packs, "w1t_rowcol", prec, residual=d_x_base)
     return [grads.get(n) for n in PARAM_NAMES], dins[0], d_x
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 4
+#define GNNFD_ABI_VERSION 3
 
 enum {
   GNNFD_OK = 0,
@@ -220,16 +220,6 @@ typedef struct {
   float *colsum;
   int32_t colsum_of_b;
   int32_t precision; /* 0 (default): split-bf16 operands, kind::f16 hi*hi + lo*hi + hi*lo (~1e-5);  1: single-pass TF32 (~3e-4) */
-  /* LayerNorm backward fused into the load of A (ABI v4; dW3 of a normalised MLP): with ln_xhat set, `a` is the
-   * gradient g at the LayerNorm OUTPUT [rows, 128] and the operand actually multiplied is
-   *   dy = rstd * (g w - mean(g w) - xhat mean(g w xhat))      (reference: autograd of nn.LayerNorm, Model.py:37)
-   * computed per row by the producer warp that stages it (one warp = one row: two shuffle reductions).  dy is also
-   * written to ln_dy [rows, 128] for the input-gradient chain, and colsum must then hold 3 x 128 floats:
-   * d ln_w = colsum(g xhat) | d ln_b = colsum(g) | d b3 = colsum(dy).  Needs n_b == 1, a.width == 128,
-   * precision 0.  Replaces the separate gnnfd_ln_backward pass (one read of g / xhat and one write + one read of dy
-   * less per MLP). */
-  const float *ln_xhat, *ln_rstd, *ln_w;
-  float *ln_dy;
 } gnnfd_wgrad_args;
 size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padded /* sum of B widths, each rounded up to 64 */);
 int gnnfd_wgrad(const gnnfd_wgrad_args *args, void *workspace, size_t workspace_bytes, void *stream);
