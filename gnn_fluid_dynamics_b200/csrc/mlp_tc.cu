@@ -112,6 +112,8 @@ struct TcParams {
   alignas(64) CUtensorMap tm_seg[3];   // split shadows of the gathered segments ([src_rows, 2 * ld] 16-bit, box 64 x 1)
   alignas(64) CUtensorMap tm_raw;      // out_raw / out_sum as [rows, 128] fp32, box 16 x 32, SWIZZLE_64B
   alignas(64) CUtensorMap tm_sum;
+  alignas(64) CUtensorMap tm_save[2];  // save_a1 / save_a2 (training stash; backward chain: dA2 / dA1), same geometry
+  int save_tma;  // the hidden epilogues write their stash through the staging block + TMA tensor stores
 };
 
 // Diagnostic cycle counters of CTA 0 (role wait times), read back with gnnfd_tc_profile_read; only
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     for (int i = 0; i < a.n_seg; ++i)
       if (a.seg[i].split != nullptr) prefetch_tmap(&p.tm_seg[i]);
     if (EPI == 1) { prefetch_tmap(&p.tm_raw); prefetch_tmap(&p.tm_sum); }
+    if (p.save_tma) { prefetch_tmap(&p.tm_save[0]); prefetch_tmap(&p.tm_save[1]); }
   }
   tc_fence_before();
   __syncthreads();
@@ -634,44 +637,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         const uint32_t reg = layer == 0 ? xr : yr;
         const uint32_t bias = vec + (layer * TC_H + eh * 64) * 4;
         float *save = EPI == 1 ? nullptr : (layer == 0 ? a.save_a1 : a.save_a2);   // EPI 1: no training stash
+        const bool save_tma = EPI != 1 && p.save_tma && save != nullptr;              // uniform
         if (save != nullptr) save = (row0 + erow < a.rows) ? save + (size_t)(row0 + erow) * TC_H + eh * 64 : nullptr;
-        // backward chain: the saved pre-activation of this layer (rows past the end read row 0; never stored),
-        // fetched one 16-column group ahead of its use
+        // backward chain: the saved pre-activation of this layer, fetched one 16-column group ahead of its use.  The
+        // loads are COALESCED (8 rows x 64 B per warp instruction, like the final copy-out) and transposed to
+        // thread = row through the warp's staging block: a thread-per-row load touches 32 cache lines per instruction
+        // and the LSU, not HBM, then paces the epilogue.  Rows past the end read a clamped row; never stored.
         const float *hm = nullptr;
         float4 m4[4];
         if (BWD) {
-          hm = (layer == 0 ? a.hid_mul1 : a.hid_mul2) + (size_t)((row0 + erow < a.rows) ? row0 + erow : 0) * TC_H + eh * 64;
+          hm = (layer == 0 ? a.hid_mul1 : a.hid_mul2) + eh * 64 + c4 * 4;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) m4[i] = ldg_f4(hm + i * 4);
+          for (int jr = 0; jr < 4; ++jr)
+            m4[jr] = ldg_f4(hm + (size_t)min(row0 + q4 * 32 + jr * 8 + rr, a.rows - 1) * TC_H);
         }
         PROF_WAIT(0, group_wait(&acc_full[xs], (3 * n + layer) & 1));
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           float v[16];
-          tmem_ld16(reg + c * 16, v);
           if (BWD) {
+            // transpose the prefetched group through the staging block (the previous group's TMA store must have
+            // finished reading it), then prefetch the next group
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+#pragma unroll
+            for (int jr = 0; jr < 4; ++jr) {
+              const int rl = jr * 8 + rr;
+              sts_f4(stg + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4, m4[jr]);
+            }
+            __syncwarp();
+            if (c < 3) {
+#pragma unroll
+              for (int jr = 0; jr < 4; ++jr)
+                m4[jr] = ldg_f4(hm + (c + 1) * 16 + (size_t)min(row0 + q4 * 32 + jr * 8 + rr, a.rows - 1) * TC_H);
+            }
+            tmem_ld16(reg + c * 16, v);
             const bool silu = a.act == GNNFD_ACT_SILU;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 m = m4[i];
+              const float4 m = lds_f4(stg + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4);
               v[4 * i] *= silu ? dsilu(m.x) : dtanh(m.x);
               v[4 * i + 1] *= silu ? dsilu(m.y) : dtanh(m.y);
               v[4 * i + 2] *= silu ? dsilu(m.z) : dtanh(m.z);
               v[4 * i + 3] *= silu ? dsilu(m.w) : dtanh(m.w);
             }
-            if (c < 3) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) m4[i] = ldg_f4(hm + (c + 1) * 16 + i * 4);
-            }
           } else {
+            tmem_ld16(reg + c * 16, v);
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 b4 = lds_f4(bias + (c * 16 + i) * 4);
               v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
           }
-          if (save != nullptr) {   // training: stash the pre-activation / dA (thread = row, 64 B per store group)
+          if (save_tma) {
+            // training stash (pre-activation / dA) of this 32 x 16 block: staged in the warp's SWIZZLE_64B block and
+            // written by ONE TMA tensor store (rows past the end of the matrix are clipped by the tensor map)
+            if (!BWD) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              sts_f4(stg + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4,
+                     make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tm_save[layer], stg, eh * 64 + c * 16, (int)(row0 + q4 * 32));
+              bulk_commit();
+            }
+          } else if (save != nullptr) {   // (fallback: thread = row, 64 B per store group)
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
               *reinterpret_cast<float4 *>(save + c * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -803,6 +839,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       if (true) { __syncwarp(); if (lane == 0) mbar_arrive(&acc_free[xs]); } else
 #endif
       if (a.n_out == TC_H) {
+        if (p.save_tma) {   // the last stash store must have finished reading the staging block the copy-out reuses
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
         float mean = 0.f, rstd = 1.f;
         if (a.has_ln) {
           // this half: shifted single pass over 64 columns -> (mean_h, M2_h); halves merged with Chan's formula
@@ -927,7 +967,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         }
       }
     }
-    if (EPI == 1 && lane == 0) bulk_wait0();      // all TMA stores of this warp have completed
+    if ((EPI == 1 || p.save_tma) && lane == 0) bulk_wait0();      // all TMA stores of this warp have completed
 #ifdef GNNFD_TC_PROF
     if (blockIdx.x == 0 && tid == 0) {
       g_tc_prof[8] = clock64() - t_begin;
@@ -1172,6 +1212,17 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
       if (rc != GNNFD_OK) return rc;
     }
     if (a->out_split != nullptr) p.epi |= EPI_SPLIT;
+  }
+  if (!fast && p.nl == 3 && a->rows > 0 && (a->save_a1 != nullptr || a->save_a2 != nullptr) &&
+      ((reinterpret_cast<uintptr_t>(a->save_a1) | reinterpret_cast<uintptr_t>(a->save_a2)) & 15) == 0) {
+    float *const sv[2] = {a->save_a1, a->save_a2};
+    for (int l = 0; l < 2; ++l) {
+      if (sv[l] == nullptr) continue;
+      const int rc = make_tmap_2d(&p.tm_save[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sv[l], TC_H, (uint64_t)a->rows, TC_H * 4,
+                                  16, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc != GNNFD_OK) return rc;
+    }
+    p.save_tma = 1;
   }
   {
     const gnnfd_segment &s0 = a->seg[0];
