@@ -68,7 +68,8 @@ constexpr int TC_SMEM_FIXED = TC_STG_BYTES + TC_IDX_SLOTS * TC_IDX_SLOT * 4 +
 constexpr int tc_smem_bytes(int w_slots, int a_stages) {      // + alignment slack before s_a and before the rings
   return TC_SMEM_FIXED + a_stages * TC_STAGE_BYTES + 2 * w_slots * TC_IMG + 2 * 1024;
 }
-static_assert(tc_smem_bytes(2, TC_A_STAGES_MAX) <= 227 * 1024 && tc_smem_bytes(TC_W_SLOTS_MAX, 2) <= 227 * 1024, "shared memory");
+static_assert(tc_smem_bytes(2, TC_A_STAGES_MAX) <= 227 * 1024 && tc_smem_bytes(TC_W_SLOTS_MAX, 2) <= 227 * 1024 &&
+              tc_smem_bytes(2, 2) + TC_STG_BYTES <= 227 * 1024, "shared memory");
 constexpr int TC_TMEM_COLS = 512;     // X0 | X1 | X2 | Y, 128 columns each
 constexpr uint32_t TC_Y_COL = TC_X_SLOTS * 128;
 constexpr int TC_MAX_KB = 8;
@@ -113,7 +114,9 @@ struct TcParams {
   alignas(64) CUtensorMap tm_raw;      // out_raw / out_sum as [rows, 128] fp32, box 16 x 32, SWIZZLE_64B
   alignas(64) CUtensorMap tm_sum;
   alignas(64) CUtensorMap tm_save[2];  // save_a1 / save_a2 (training stash; backward chain: dA2 / dA1), same geometry
+  alignas(64) CUtensorMap tm_split;    // out_split as [rows, 256] 16-bit, box 16 x 32, no swizzle
   int save_tma;  // the hidden epilogues write their stash through the staging block + TMA tensor stores
+  int split_tma; // the split shadow leaves through a SECOND staging block (after the weight rings) + TMA tensor stores
 };
 
 // Diagnostic cycle counters of CTA 0 (role wait times), read back with gnnfd_tc_profile_read; only
@@ -302,6 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       if (a.seg[i].split != nullptr) prefetch_tmap(&p.tm_seg[i]);
     if (EPI == 1) { prefetch_tmap(&p.tm_raw); prefetch_tmap(&p.tm_sum); }
     if (p.save_tma) { prefetch_tmap(&p.tm_save[0]); prefetch_tmap(&p.tm_save[1]); }
+    if (p.split_tma) prefetch_tmap(&p.tm_split);
   }
   tc_fence_before();
   __syncthreads();
@@ -616,6 +620,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     const int grp = warp >> 3, q4 = warp & 3, eh = (warp >> 2) & 1;
     const int erow = q4 * 32 + lane;                       // row of the tile owned by this thread
     const uint32_t stg = smem_u32(s_stg + warp * (32 * 16));   // this warp's 32 x 16 staging block (XOR-swizzled)
+    // second block (split shadow: 32 rows x 32 B of hi pairs | 32 x 32 B of lo pairs), behind the weight rings
+    const uint32_t stg2 = smem_u32(s_w23 + w_slots * TC_IMG) + warp * 2048;
     const uint32_t vec = smem_u32(s_vec), stat = smem_u32(s_stat);
     const int rr = lane >> 2, c4 = lane & 3;               // copy-out mapping: 8 rows x 64 B per instruction
     // Waiting on an mbarrier polls (try_wait wakes every ~100 cycles: 4 instructions per poll per warp - with 8 warps of
@@ -802,7 +808,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               o[4 * i] += res[i].x; o[4 * i + 1] += res[i].y; o[4 * i + 2] += res[i].z; o[4 * i + 3] += res[i].w;
             }
           }
-          if ((epi & EPI_SPLIT) && grow < a.rows) {   // 16-bit hi | lo shadow for the next block's TMA gathers
+          const bool both = (epi & EPI_SPLIT) && p.split_tma && (epi & (EPI_ST_RAW | EPI_RED_SUM | EPI_LDRES));
+          if ((epi & EPI_SPLIT) && p.split_tma) {
+            // 16-bit hi | lo shadow for the next block's TMA gathers: staged row-major (32 B of hi pairs per row, then the lo
+            // pairs) and written by two TMA tensor stores - thread-per-row 16-byte stores at a 512 B stride cost 32 cache
+            // lines per instruction and made the LSU pace this epilogue.  Bulk groups alternate between the two staging
+            // blocks, so "at most one group still reading" means the block about to be overwritten is free.
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) split2<FP16>(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+            if (lane == 0) { if (both) bulk_wait_read1(); else bulk_wait_read0(); }
+            __syncwarp();
+            const uint32_t sp = stg2 + lane * 32;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sp), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sp + 16), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sp + 1024), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sp + 1040), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]) : "memory");
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tm_split, stg2, col0, trow);
+              tma_store_2d(&p.tm_split, stg2 + 1024, TC_H + col0, trow);
+              bulk_commit();
+            }
+          } else if ((epi & EPI_SPLIT) && grow < a.rows) {   // (fallback: thread = row stores)
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) split2<FP16>(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
@@ -818,7 +847,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           if (epi & (EPI_ST_RAW | EPI_RED_SUM | EPI_LDRES)) {
 #endif
             // the previous group's TMA copy must have finished READING the staging block before it is overwritten
-            if (lane == 0) bulk_wait_read0();
+            if (lane == 0) { if (both) bulk_wait_read1(); else bulk_wait_read0(); }
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1213,6 +1242,16 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
     }
     if (a->out_split != nullptr) p.epi |= EPI_SPLIT;
   }
+  int extra_smem = 0;
+  if (fast && a->out_split != nullptr && p.a_stages == 2 && (a->rows + TC_BM - 1) / TC_BM > 2 * (int64_t)num_sms()) {
+    // room for the second staging block: two-slot weight rings (186 KB + 32 KB); launches of a tile or two per CTA are
+    // a latency chain and keep the third weight slot instead
+    const int rc = make_tmap_2d(&p.tm_split, m.fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                a->out_split, 2 * TC_H, (uint64_t)a->rows, 4 * TC_H, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != GNNFD_OK) return rc;
+    p.split_tma = 1;
+    extra_smem = TC_STG_BYTES;
+  }
   if (!fast && p.nl == 3 && a->rows > 0 && (a->save_a1 != nullptr || a->save_a2 != nullptr) &&
       ((reinterpret_cast<uintptr_t>(a->save_a1) | reinterpret_cast<uintptr_t>(a->save_a2)) & 15) == 0) {
     float *const sv[2] = {a->save_a1, a->save_a2};
@@ -1233,7 +1272,7 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   if (a->rows == 0) return GNNFD_OK;
   const int64_t n_tiles = (a->rows + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  p.w_slots = n_tiles <= 2 * (int64_t)num_sms() ? TC_W_SLOTS_MAX : 2;
+  p.w_slots = (n_tiles <= 2 * (int64_t)num_sms() && !p.split_tma) ? TC_W_SLOTS_MAX : 2;
 #define LAUNCH1(FP, NA_, NW_, BW, EP)                                                                     \
   do {                                                                                                    \
     static bool attr[GNNFD_MAX_DEVICES] = {false};                                                        \
@@ -1242,7 +1281,7 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
                                       227 * 1024));                                                       \
       attr[current_device()] = true;                                                                      \
     }                                                                                                     \
-    mlp_tc_kernel<FP, NA_, NW_, BW, EP><<<grid, TC_THREADS, tc_smem_bytes(p.w_slots, p.a_stages), stream>>>(p);   \
+    mlp_tc_kernel<FP, NA_, NW_, BW, EP><<<grid, TC_THREADS, tc_smem_bytes(p.w_slots, p.a_stages) + extra_smem, stream>>>(p);   \
   } while (0)
 #define LAUNCH(FP, NA_, NW_)                                                                              \
   do {                                                                                                    \
