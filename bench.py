@@ -292,7 +292,7 @@ def main():
     gd = model.normalizer.input([g.to(dev) for g in host_graphs])
     topo = get_topology(gd).validate()
     if train:
-        topo.build_rowcol_csr(); topo.build_vf_csr()
+        topo.build_row_col_interleaved_csr(); topo.build_vf_csr()
         gd[0].topology = gd[2].topology = topo
     working_set = 4 * 128 * (2 * E + 3 * N) + 4 * 64 * V
     flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev) if working_set < 256e6 else None

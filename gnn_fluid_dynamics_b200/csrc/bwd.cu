@@ -20,26 +20,39 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_backward_kernel(
   const float4 w4 = ln_w ? ldg_f4(ln_w + lane * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
   float4 s_gx = make_float4(0.f, 0.f, 0.f, 0.f), s_g = s_gx, s_dy = s_gx;
   const int64_t n_warps = (int64_t)gridDim.x * LNB_WARPS;
-  for (int64_t r = (int64_t)blockIdx.x * LNB_WARPS + warp; r < rows; r += n_warps) {
-    const float4 g4 = ldg_f4(g + r * 128 + lane * 4), x4 = ldg_f4(xhat + r * 128 + lane * 4);
-    const float rs = __ldg(rstd + r);
-    const float4 gw = make_float4(g4.x * w4.x, g4.y * w4.y, g4.z * w4.z, g4.w * w4.w);
-    float a = (gw.x + gw.y) + (gw.z + gw.w);
-    float b = (gw.x * x4.x + gw.y * x4.y) + (gw.z * x4.z + gw.w * x4.w);
+  // four rows per warp and iteration: eight 512 B loads in flight per warp (one row at a time left the kernel
+  // latency-bound at 3.5 TB/s)
+  constexpr int U = 4;
+  for (int64_t r0 = ((int64_t)blockIdx.x * LNB_WARPS + warp) * U; r0 < rows; r0 += n_warps * U) {
+    float4 g4[U], x4[U];
+    float rs[U];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
+    for (int u = 0; u < U; ++u) {
+      const bool ok = r0 + u < rows;
+      g4[u] = ok ? ldg_f4(g + (r0 + u) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x4[u] = ok ? ldg_f4(xhat + (r0 + u) * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rs[u] = ok ? __ldg(rstd + r0 + u) : 0.f;
     }
-    a *= (1.0f / 128.0f);
-    b *= (1.0f / 128.0f);
-    float4 d;
-    d.x = rs * (gw.x - a - x4.x * b); d.y = rs * (gw.y - a - x4.y * b);
-    d.z = rs * (gw.z - a - x4.z * b); d.w = rs * (gw.w - a - x4.w * b);
-    *reinterpret_cast<float4 *>(dy + r * 128 + lane * 4) = d;
-    s_gx.x += g4.x * x4.x; s_gx.y += g4.y * x4.y; s_gx.z += g4.z * x4.z; s_gx.w += g4.w * x4.w;
-    s_g.x += g4.x; s_g.y += g4.y; s_g.z += g4.z; s_g.w += g4.w;
-    s_dy.x += d.x; s_dy.y += d.y; s_dy.z += d.z; s_dy.w += d.w;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float4 gw = make_float4(g4[u].x * w4.x, g4[u].y * w4.y, g4[u].z * w4.z, g4[u].w * w4.w);
+      float a = (gw.x + gw.y) + (gw.z + gw.w);
+      float b = (gw.x * x4[u].x + gw.y * x4[u].y) + (gw.z * x4[u].z + gw.w * x4[u].w);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      a *= (1.0f / 128.0f);
+      b *= (1.0f / 128.0f);
+      float4 d;
+      d.x = rs[u] * (gw.x - a - x4[u].x * b); d.y = rs[u] * (gw.y - a - x4[u].y * b);
+      d.z = rs[u] * (gw.z - a - x4[u].z * b); d.w = rs[u] * (gw.w - a - x4[u].w * b);
+      if (r0 + u < rows) *reinterpret_cast<float4 *>(dy + (r0 + u) * 128 + lane * 4) = d;
+      s_gx.x += g4[u].x * x4[u].x; s_gx.y += g4[u].y * x4[u].y; s_gx.z += g4[u].z * x4[u].z; s_gx.w += g4[u].w * x4[u].w;
+      s_g.x += g4[u].x; s_g.y += g4[u].y; s_g.z += g4[u].z; s_g.w += g4[u].w;
+      s_dy.x += d.x; s_dy.y += d.y; s_dy.z += d.z; s_dy.w += d.w;
+    }
   }
   *reinterpret_cast<float4 *>(&s_part[warp][0][lane * 4]) = s_gx;
   *reinterpret_cast<float4 *>(&s_part[warp][1][lane * 4]) = s_g;

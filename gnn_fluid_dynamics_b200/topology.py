@@ -72,7 +72,7 @@ class MeshTopology:
         self._flags = self._flags[1:] + [cei._gnnfd_range_flag] if self._flags else [cei._gnnfd_range_flag]
         self.row, self.col = cei[0], cei[1]
         self.cell_offsets = self.cell_perm = None
-        self._rowcol = self._rowcsr = self._colcsr = None
+        self._rowcol = self._rowcsr = self._colcsr = self._rc2csr = None
         self._c_key = _tensor_key(c_edge_index)
         return self
 
@@ -102,6 +102,15 @@ class MeshTopology:
         if getattr(self, "_rowcsr", None) is None:
             self._rowcsr = ops.csr_build(self.row, self.n_cells)
         return self._rowcsr
+
+    def build_row_col_interleaved_csr(self):
+        """CSR over 2 N virtual rows: row 2 n = the faces whose first cell is n, row 2 n + 1 = the faces whose second cell
+        is n (index vector cat[2 row; 2 col + 1]).  One segment sum over it reduces an [E, 128] matrix onto the cells as
+        the [N, 256] matrix [S_row | S_col] (viewed [2 N, 128]) in ONE pass: both reductions of a cell's faces run next
+        to each other, so every source row comes from DRAM once."""
+        if getattr(self, "_rc2csr", None) is None:
+            self._rc2csr = ops.csr_build(torch.cat([self.row * 2, self.col * 2 + 1]), 2 * self.n_cells)
+        return self._rc2csr
 
     def build_col_csr(self):
         if getattr(self, "_colcsr", None) is None:

@@ -72,12 +72,10 @@ def edge_mlp_backward_node_side(w: MLPWeights, st: MLPStash, e_in, x_src, topo: 
     # dW1[:, 0:128] = dA1^T e, db1 = column sums of dA1
     w1g = grads["w1"]
     ops.wgrad(Seg(d_a1), [Seg(e_in)], E, w1g[:, 0:H], colsum=grads.get("b1"))
-    # S = [S_row | S_col]: dA1 reduced onto the cells (two deterministic CSR sums into the column halves of ONE matrix)
-    r_off, r_perm = topo.build_row_csr()
-    c_off, c_perm = topo.build_col_csr()
+    # S = [S_row | S_col]: dA1 reduced onto the cells by ONE deterministic CSR sum (2 N virtual rows, see the topology)
+    rc_off, rc_perm = topo.build_row_col_interleaved_csr()
     s_rc = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)
-    ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, r_off, r_perm, N, out=s_rc[:, :H])
-    ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, c_off, c_perm, N, out=s_rc[:, H:])
+    ops.segment_sum(d_a1, d_a1, 0, 0, H, 1.0, rc_off, rc_perm, 2 * N, out=s_rc.view(2 * N, H))
     # dW1[:, 128:256] = S_row^T x and dW1[:, 256:384] = S_col^T x as ONE weight-gradient GEMM x^T S (x is read once; N
     # contiguous rows), stored transposed into a [256, 128] scratch whose halves are the two column blocks of dW1
     t_rc = torch.empty(2 * H, H, dtype=torch.float32, device=dev)

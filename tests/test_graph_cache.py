@@ -78,7 +78,7 @@ def test_refresh_orientation_equals_fresh_build():
     dev = torch.device("cuda:0")
     g = [t.to(dev) for t in mesh_graphs(make_mesh(2000, "cylinder", seed=3), seed=4, flip_edges=False)]
     topo = MeshTopology.from_graphs(g).validate()
-    topo.build_rowcol_csr(); topo.build_row_csr(); topo.build_cell_csr()
+    topo.build_rowcol_csr(); topo.build_row_csr(); topo.build_cell_csr(); topo.build_row_col_interleaved_csr()
     ei = g[0].edge_index.clone()
     flip = torch.rand(ei.shape[1], device=dev) < 0.5
     ei[:, flip] = ei[:, flip].flip(0)
@@ -86,7 +86,7 @@ def test_refresh_orientation_equals_fresh_build():
     topo.refresh_orientation(ei).validate()
     fresh = MeshTopology.from_graphs(g).validate()
     assert torch.equal(topo.row, fresh.row) and torch.equal(topo.col, fresh.col)
-    for name in ("build_rowcol_csr", "build_row_csr", "build_col_csr", "build_cell_csr"):
+    for name in ("build_rowcol_csr", "build_row_csr", "build_col_csr", "build_cell_csr", "build_row_col_interleaved_csr"):
         a, b = getattr(topo, name)(), getattr(fresh, name)()
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), name
     assert torch.equal(topo.vtx_perm, fresh.vtx_perm)
