@@ -16,8 +16,75 @@ import torch
 from .topology import attach_topology
 
 
+class _FusedStep:
+    """One rollout step of FvgnA / MgnA without the per-step graph clones and per-column (de)normalisation kernels:
+
+      forward on RESIDENT normalised inputs  ->  [integrator]  ->  de-normalise the predicted change (one kernel)  ->
+      ``fvm_ops.state_advance`` (two kernels: rollout.py:340 + update_features, Fvgn.py:133-148 / Mgn.py:139-151, + the
+      z-scoring of the next step's inputs, normalisation.py:255-278)
+
+    The reference's loop body re-clones the three graphs, z-scores every input column and inverts every output column
+    with a handful of tiny tensor kernels each (~100 launches of a few microseconds per step); here the raw state
+    (``c_graph.x``, ``f_graph.x[:, :2]``) and its normalised copy are both kept in HBM and advanced together."""
+
+    KINDS = ("FvgnA", "MgnA")
+
+    @staticmethod
+    def supports(model, graphs) -> bool:
+        c, f, _ = graphs
+        if type(model).__name__ not in _FusedStep.KINDS or c.x.shape[1] != 2 or "x" not in f:
+            return False
+        keys = ("cell_velocity_x", "cell_velocity_y", "face_velocity_difference_x", "face_velocity_difference_y",
+                "cell_velocity_change_x", "cell_velocity_change_y")
+        nz = model.normalizer
+        return all(nz.kinds.get(k) == "z_score" and hasattr(nz, f"{k}_mean") and hasattr(nz, f"{k}_std") for k in keys)
+
+    def __init__(self, model, graphs, topo):
+        from .mesh import NODE_INFLOW, NODE_WALL
+        self.model, self.graphs, self.topo = model, graphs, topo
+        c, f, v = graphs
+        nz = model.normalizer
+        ms = lambda k: (float(getattr(nz, f"{k}_mean")), float(torch.clamp(getattr(nz, f"{k}_std"), min=1e-8) + 1e-8))
+        self.cell_stats = ms("cell_velocity_x") + ms("cell_velocity_y")
+        self.face_stats = ms("face_velocity_difference_x") + ms("face_velocity_difference_y")
+        dev = c.x.device
+        (m0, s0), (m1, s1) = ms("cell_velocity_change_x"), ms("cell_velocity_change_y")
+        self.out_mean = torch.tensor([m0, m1], dtype=torch.float32, device=dev)
+        self.out_scale = torch.tensor([s0, s1], dtype=torch.float32, device=dev)
+        # normalised copies of the inputs: the static columns are z-scored once, the state columns every step
+        gn = nz.input([g.clone() for g in graphs])
+        self.x_norm, self.f_norm = gn[0].x.contiguous(), gn[1].x.contiguous()
+        self.c_norm = gn[0]                       # normals / volumes / dt for the integrator (untouched by the z-scoring)
+        self.c_norm.topology = topo
+        self.f_static = gn[1]
+        if type(model).__name__ == "FvgnA":
+            mask = ((f.type == NODE_INFLOW) | (f.type == NODE_WALL)).reshape(-1)
+        else:
+            mask = f.boundary_mask.reshape(-1)
+        self.mask = mask.to(torch.uint8).contiguous()
+        self.vel = torch.empty(c.x.shape[0], 2, dtype=torch.float32, device=dev)
+        if not (c.x.is_contiguous() and f.x.is_contiguous()):
+            c.x, f.x = c.x.contiguous(), f.x.contiguous()
+
+    @torch.no_grad()
+    def step(self) -> torch.Tensor:
+        from . import fvm_ops
+        model, (c, f, _), topo = self.model, self.graphs, self.topo
+        x, e, dec = model.encode_process_decode(self.x_norm, self.f_norm, topo)
+        if type(model).__name__ == "FvgnA":
+            self.c_norm.x = self.x_norm
+            change = model.integrator(dec, self.c_norm, self.f_static, self.c_norm.dt)      # normalised change [N, 2]
+        else:
+            change = dec[:, 0:2]
+        delta = torch.addcmul(self.out_mean, change, self.out_scale)                       # normalizer.output(inverse)
+        fvm_ops.state_advance(c.x, delta, True, topo.row, topo.col, f.x, self.mask, f.y, x_norm=self.x_norm,
+                              cell_stats=self.cell_stats, f_norm=self.f_norm, face_stats=self.face_stats, vel_out=self.vel)
+        return self.vel
+
+
 class RolloutEngine:
-    def __init__(self, model, graphs, cuda_graph: bool = True, need_cell_csr: bool = False, two_hop: bool = True):
+    def __init__(self, model, graphs, cuda_graph: bool = True, need_cell_csr: bool = False, two_hop: bool = True,
+                 fused_step: bool = True):
         """``graphs`` = [c_graph, f_graph, v_graph] on the GPU; its ``c_graph.x`` / ``f_graph.x`` are the rollout
         state and are advanced in place."""
         if graphs[0].x.device.type != "cuda":
@@ -31,6 +98,9 @@ class RolloutEngine:
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._vel: Optional[torch.Tensor] = None
         self.face_attr = "x_asym" if "x_asym" in graphs[1] else "x"
+        # FvgnA / MgnA: state advance and (de)normalisation as fused kernels on resident buffers (``fused_step=False``
+        # steps through the reference's loop body literally: forward on cloned graphs + update_features)
+        self._fused = _FusedStep(self.model, graphs, self.topo) if fused_step and _FusedStep.supports(self.model, graphs) else None
 
     @torch.no_grad()
     def _step_eager(self) -> torch.Tensor:
@@ -38,6 +108,8 @@ class RolloutEngine:
         at its word (rollout.py:336-337: MgnB / MgnC / StreamFunc); otherwise velocity = x[:, :2] + change
         (rollout.py:340).  Temporally bundled outputs [N, k, 2] (FvgnC) yield k velocities per forward and the LAST
         one feeds ``update_features`` (rollout.py:319-332, 369); the returned tensor is then [N, k, 2]."""
+        if self._fused is not None:
+            return self._fused.step()
         c, f, v = self.graphs
         cx = c.x                                                       # static state buffer
         out = self.model([g.clone() for g in self.graphs], mode="rollout")           # rollout.py:313
@@ -58,17 +130,24 @@ class RolloutEngine:
 
     def _capture(self):
         c, f, _ = self.graphs
-        state = (c.x.clone(), getattr(f, self.face_attr).clone())
+        live = [c.x, getattr(f, self.face_attr)]      # everything a step advances in place
+        if self._fused is not None:
+            live += [self._fused.x_norm, self._fused.f_norm]
+        state = [t.clone() for t in live]
+
+        def restore():
+            for t, s0 in zip(live, state):
+                t.copy_(s0)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):                 # warm-up outside capture (lazy kernel attributes, packs)
             self._step_eager()
         torch.cuda.current_stream().wait_stream(s)
-        c.x.copy_(state[0]); getattr(f, self.face_attr).copy_(state[1])
+        restore()
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._vel = self._step_eager()
-        c.x.copy_(state[0]); getattr(f, self.face_attr).copy_(state[1])
+        restore()
 
     def step(self) -> torch.Tensor:
         """Advance the state by one timestep; returns the new cell velocity [N, 2] (a static buffer when the

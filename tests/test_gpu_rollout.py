@@ -89,3 +89,21 @@ def test_rollout_bundled_and_host_syncing_models_step():
         assert out[-1].shape[-1] == 2 and torch.isfinite(out[-1]).all()
         if name == "FvgnC":
             assert out[-1].dim() == 3 and out[-1].shape[1] == 3
+
+
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA"])
+def test_fused_state_advance_step_equals_literal_loop_body(name):
+    """RolloutEngine's fused step (resident normalised inputs + state-advance kernels) against the
+    reference's literal loop body (forward on cloned graphs, update_features): 20 steps, velocities and face features."""
+    from gnn_fluid_dynamics_b200.rollout import RolloutEngine
+    dev = torch.device("cuda:0")
+    model = build_model(name).to(dev).eval()
+    _, graphs = golden_graphs(name, n_cells=600, mesh_seed=61, feat_seed=62)
+    fused = RolloutEngine(model, [g.clone().to(dev) for g in graphs], cuda_graph=True)
+    lit = RolloutEngine(model, [g.clone().to(dev) for g in graphs], cuda_graph=False, fused_step=False)
+    assert fused._fused is not None and lit._fused is None
+    for _ in range(20):
+        va, vb = fused.step(), lit.step()
+    assert rel_l2(va, vb) < 1e-5, rel_l2(va, vb)
+    assert rel_l2(fused.graphs[1].x, lit.graphs[1].x) < 1e-5
+    assert torch.equal(fused.graphs[0].x[:, :2], va)
