@@ -400,4 +400,7 @@ def run_processor_peer(family: str, blocks, state: PartState, x0_owned: torch.Te
         segs = [Seg(e), Seg(raw, SEG_GATHER, (row_enc,)), Seg(raw, SEG_GATHER, (col_enc,))]
         _, e = ops.mlp_forward(segs, we, e.shape[0], prec, residual=e, want_raw=False, want_sum=True,
                                peer=(bufs.views[i % 2], PEER_SHIFT))
+    # the last block's remote reads of raw[(L - 1) % 2] must finish everywhere before a following call's block 0 (odd L:
+    # the same buffer) overwrites it
+    bufs.barrier()
     return x, e

@@ -77,10 +77,29 @@ class Fast:
         return Seg(self.xs.view(torch.float32), SEG_GATHER, (idx,), split=self.xs)
 
 
+FAST_ENABLED = True      # tests / comparisons can pin the register-staged kernels with ``no_fast()``
+
+
+class no_fast:
+    """Context manager: run inference through the register-staged (training-shaped) kernels instead of the fast path.
+    The two differ in the last bit of the LayerNorm epilogue, so bit-for-bit comparisons against a path that only
+    exists in the register-staged form (the peer-memory halo) use this."""
+
+    def __enter__(self):
+        global FAST_ENABLED
+        self._old, FAST_ENABLED = FAST_ENABLED, False
+        return self
+
+    def __exit__(self, *exc):
+        global FAST_ENABLED
+        FAST_ENABLED = self._old
+        return False
+
+
 def fast_mode(blocks, tensors, prec: int) -> bool:
     """In-place residuals + split shadows are legal when nothing records a gradient and the precision has split
     operands (bf16x3 / fp16x3)."""
-    if ops.split_dtype(prec) is None:
+    if not FAST_ENABLED or ops.split_dtype(prec) is None:
         return False
     if not torch.is_grad_enabled():
         return True
