@@ -55,6 +55,19 @@ inline int num_sms() {
   return n[dev];
 }
 
+// One deferred split-K reduction of a weight-gradient GEMM (wgrad_tc.cu): gnnfd_mlp_backward runs its GEMMs back to
+// back and adds ALL their partials in one launch at the end instead of one small launch after each GEMM.
+struct WgReduceJob {
+  const float *part;      // [n_parts][128][n_pad]
+  const float *cs_part;   // [n_parts][128] column-sum partials (or nullptr)
+  float *out, *cs_out;
+  int n_parts, n_pad, m_valid, n_valid, ld_out, transpose, cs_valid;
+  size_t ws_used;         // bytes of the workspace this GEMM's partials occupy
+};
+constexpr int WG_MAX_REDUCE_JOBS = 6;
+int wgrad_run(const gnnfd_wgrad_args *a, void *workspace, size_t workspace_bytes, cudaStream_t stream, WgReduceJob *defer);
+int wgrad_reduce_jobs(const WgReduceJob *jobs, int n_jobs, cudaStream_t stream);
+
 // exact-path activations (IEEE expf / tanhf); the tensor-core path uses the fast variants
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
 __device__ __forceinline__ float act_f(float v, int act) {

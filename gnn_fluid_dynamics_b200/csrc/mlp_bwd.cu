@@ -27,7 +27,9 @@ static BwdLayout bwd_layout(const gnnfd_mlp_args *f) {
   L.da1 = o; o += mat;
   L.sums = o; o += al256(3 * 128 * 4);
   L.lnws = o; o += al256(ln_backward_ws(f->rows));
-  L.wgws = o; o += al256(gnnfd_wgrad_workspace_bytes(f->rows, 384));
+  // the weight-gradient GEMMs of one MLP keep their split-K partials side by side (dW3, dW2, dW1 lead + rest: <= 128 +
+  // 128 + 128 + 256 columns) and are reduced by ONE launch at the end
+  L.wgws = o; o += 4 * (al256(gnnfd_wgrad_workspace_bytes(f->rows, 160)) + 256);   // 4 GEMMs: 640 columns + 4 column-sum regions
   L.total = o;
   size_t p = 0;
   L.pk_chain = p; p += al256(pack_mlp_bytes_tc(f->n_out, 128, 128, f->precision));
@@ -141,8 +143,19 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
   uint8_t *ws = (uint8_t *)b->workspace;
   const uint8_t *pk = (const uint8_t *)b->packed_bwd;
   float *da2 = (float *)(ws + L.da2), *da1 = b->da1_out ? b->da1_out : (float *)(ws + L.da1), *sums = (float *)(ws + L.sums);
-  void *wgws = ws + L.wgws;
-  const size_t wgws_bytes = L.total - L.wgws;
+  uint8_t *wgws = ws + L.wgws;
+  size_t wgws_bytes = L.total - L.wgws;
+  WgReduceJob jobs[WG_MAX_REDUCE_JOBS];
+  int n_jobs = 0;
+  // run one weight-gradient GEMM with its reduction deferred; its partials take the next slice of the workspace
+  auto wgrad_deferred = [&](const gnnfd_wgrad_args &w) -> int {
+    if (n_jobs >= WG_MAX_REDUCE_JOBS) { set_error("gnnfd_mlp_backward: too many weight-gradient GEMMs"); return GNNFD_E_BADARG; }
+    const int r = wgrad_run(&w, wgws, wgws_bytes, stream, &jobs[n_jobs]);
+    if (r != GNNFD_OK) return r;
+    wgws += jobs[n_jobs].ws_used; wgws_bytes -= jobs[n_jobs].ws_used;
+    ++n_jobs;
+    return GNNFD_OK;
+  };
   const int code = f->act + 1;   // SiLU -> 1, tanh -> 2
   const int n_out = f->n_out;
   int rc;
@@ -177,7 +190,7 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
       w.a = direct(b->a2, 128, 128); w.a_act = code; w.n_b = 1; w.b[0] = direct(dy, n_out, n_out);
       w.out = b->d_w3; w.ld_out = 128; w.transpose_out = 1; w.colsum = cs; w.colsum_of_b = 1;
     }
-    if ((rc = gnnfd_wgrad(&w, wgws, wgws_bytes, stream)) != GNNFD_OK) return rc;
+    if ((rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
   }
   // ---- dgrad chain: dA2 = (dy W3) * act'(a2), dA1 = (dA2 W2) * act'(a1) [, dIn_0 = dA1 W1[:, seg 0] (+ residual)]
   const bool chain = b->din_out[0] != nullptr;
@@ -204,17 +217,31 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
     w.rows = f->rows;
     w.a = direct(da2, 128, 128); w.n_b = 1; w.b[0] = direct(b->a1, 128, 128); w.b_act = code;
     w.out = b->d_w2; w.ld_out = 128; w.colsum = b->d_b2;
-    if ((rc = gnnfd_wgrad(&w, wgws, wgws_bytes, stream)) != GNNFD_OK) return rc;
+    if ((rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
   }
   // ---- dW1 = dA1^T In (In assembled from the forward's segments), remaining segment input gradients
   {
     if (!b->skip_wgrad_l1) {
+      // a contiguous 128-wide leading segment (the residual stream x / e) goes through the lean direct x direct kernel
+      // on its own; the assembled segments (gathers, means) follow in a second GEMM into the remaining columns of dW1
+      const gnnfd_segment &s0 = f->seg[0];
+      const bool lead = f->n_seg > 1 && s0.mode == GNNFD_SEG_DIRECT && s0.width == 128 && s0.ld == 128 && s0.col == 0 &&
+                        (reinterpret_cast<uintptr_t>(s0.src) & 15) == 0;
       gnnfd_wgrad_args w{};
       w.rows = f->rows;
-      w.a = direct(da1, 128, 128); w.n_b = f->n_seg;
-      for (int s = 0; s < f->n_seg; ++s) w.b[s] = f->seg[s];
+      w.a = direct(da1, 128, 128);
       w.out = b->d_w1; w.ld_out = f->k_in; w.colsum = b->d_b1;
-      if ((rc = gnnfd_wgrad(&w, wgws, wgws_bytes, stream)) != GNNFD_OK) return rc;
+      if (lead) {
+        w.n_b = 1; w.b[0] = s0;
+        if ((rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
+        w.n_b = f->n_seg - 1;
+        for (int s = 1; s < f->n_seg; ++s) w.b[s - 1] = f->seg[s];
+        w.out = b->d_w1 + 128; w.colsum = nullptr;
+      } else {
+        w.n_b = f->n_seg;
+        for (int s = 0; s < f->n_seg; ++s) w.b[s] = f->seg[s];
+      }
+      if ((rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
     }
     int col0 = 0;
     for (int s = 0; s < f->n_seg; ++s) {
@@ -229,5 +256,6 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
       col0 += f->seg[s].width;
     }
   }
-  return GNNFD_OK;
+  // ---- all split-K reductions of this MLP in one launch
+  return wgrad_reduce_jobs(jobs, n_jobs, stream);
 }

@@ -473,6 +473,62 @@ __global__ void __launch_bounds__(RP_OUT * RP_GROUPS) reduce_partials_kernel(con
   }
 }
 
+struct WgReduceJobs { WgReduceJob job[WG_MAX_REDUCE_JOBS]; int first_block[WG_MAX_REDUCE_JOBS + 1]; int n; };
+// the same reduction for several GEMMs in one launch: block -> (job, block of the job)
+__global__ void __launch_bounds__(RP_OUT * RP_GROUPS) reduce_partials_multi_kernel(const __grid_constant__ WgReduceJobs jobs) {
+  __shared__ float s_sum[RP_GROUPS][RP_OUT];
+  int q = 0;
+  while (q + 1 < jobs.n && (int)blockIdx.x >= jobs.first_block[q + 1]) ++q;
+  const WgReduceJob &jb = jobs.job[q];
+  const int total = jb.m_valid * jb.n_valid;
+  const int tx = threadIdx.x & (RP_OUT - 1), ty = threadIdx.x / RP_OUT;
+  const int i = ((int)blockIdx.x - jobs.first_block[q]) * RP_OUT + tx;
+  float s = 0.f;
+  if (i < total) {
+    const int m = i / jb.n_valid, j = i % jb.n_valid;
+    const float *src = jb.part + (size_t)m * jb.n_pad + j;
+    for (int c = ty; c < jb.n_parts; c += RP_GROUPS) s += src[(size_t)c * 128 * jb.n_pad];
+  } else if (jb.cs_out != nullptr && i - total < jb.cs_valid) {
+    for (int c = ty; c < jb.n_parts; c += RP_GROUPS) s += jb.cs_part[(size_t)c * 128 + (i - total)];
+  }
+  s_sum[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float r[RP_GROUPS];
+#pragma unroll
+    for (int g = 0; g < RP_GROUPS; ++g) r[g] = s_sum[g][tx];
+#pragma unroll
+    for (int w = RP_GROUPS / 2; w > 0; w >>= 1)
+#pragma unroll
+      for (int g = 0; g < w; ++g) r[g] += r[g + w];
+    if (i < total) {
+      const int m = i / jb.n_valid, j = i % jb.n_valid;
+      if (jb.transpose) jb.out[(size_t)j * jb.ld_out + m] = r[0]; else jb.out[(size_t)m * jb.ld_out + j] = r[0];
+    } else if (jb.cs_out != nullptr && i - total < jb.cs_valid) {
+      jb.cs_out[i - total] = r[0];
+    }
+  }
+}
+
+int wgrad_reduce_jobs(const WgReduceJob *jobs, int n_jobs, cudaStream_t stream) {
+  if (n_jobs <= 0) return GNNFD_OK;
+  if (n_jobs > WG_MAX_REDUCE_JOBS) { set_error("wgrad_reduce_jobs: too many jobs"); return GNNFD_E_BADARG; }
+  WgReduceJobs js{};
+  js.n = n_jobs;
+  int blocks = 0;
+  for (int q = 0; q < n_jobs; ++q) {
+    js.job[q] = jobs[q];
+    js.first_block[q] = blocks;
+    const int total = jobs[q].m_valid * jobs[q].n_valid + (jobs[q].cs_out ? jobs[q].cs_valid : 0);
+    blocks += (total + RP_OUT - 1) / RP_OUT;
+  }
+  js.first_block[n_jobs] = blocks;
+  if (blocks == 0) return GNNFD_OK;
+  reduce_partials_multi_kernel<<<blocks, RP_OUT * RP_GROUPS, 0, stream>>>(js);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}
+
 static int64_t wg_rows_per_cta(int64_t rows, int &grid) {
   const int sms = num_sms();
   int64_t per = (rows + sms - 1) / sms;
@@ -501,7 +557,13 @@ extern "C" size_t gnnfd_wgrad_workspace_bytes(int64_t rows, int32_t n_cols_padde
 }
 
 extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t workspace_bytes, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+  return gnnfd::wgrad_run(a, workspace, workspace_bytes, (cudaStream_t)stream_, nullptr);
+}
+
+// `defer` != nullptr: the split-K partials stay in the workspace (defer->ws_used bytes) and their reduction is described
+// in *defer for a later wgrad_reduce_jobs launch; nullptr: reduced right away.
+int gnnfd::wgrad_run(const gnnfd_wgrad_args *a, void *workspace, size_t workspace_bytes, cudaStream_t stream, WgReduceJob *defer) {
+  if (defer != nullptr) *defer = WgReduceJob{};
   GNNFD_CHECK_ARG(a != nullptr && a->out != nullptr, "null args/out");
   GNNFD_CHECK_ARG(a->rows >= 0, "negative rows");
   GNNFD_CHECK_ARG(a->n_b >= 1 && a->n_b <= 3, "n_b must be 1..3");
@@ -584,6 +646,13 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
   GNNFD_LAUNCH_CHECK();
   const int m_valid = a->a.width;
   const int total = m_valid * n_valid + cs_valid;
+  if (defer != nullptr) {
+    defer->part = p.partial; defer->cs_part = cs_part; defer->out = a->out; defer->cs_out = a->colsum;
+    defer->n_parts = grid; defer->n_pad = n_pad; defer->m_valid = m_valid; defer->n_valid = n_valid;
+    defer->ld_out = a->ld_out; defer->transpose = a->transpose_out; defer->cs_valid = cs_valid;
+    defer->ws_used = (need + 255) & ~(size_t)255;
+    return GNNFD_OK;
+  }
   reduce_partials_kernel<<<(total + RP_OUT - 1) / RP_OUT, RP_OUT * RP_GROUPS, 0, stream>>>(p.partial, grid, n_pad, m_valid, n_valid, a->out,
                                                                   a->ld_out, a->transpose_out, cs_part, a->colsum, cs_valid);
   GNNFD_LAUNCH_CHECK();
