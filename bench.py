@@ -29,6 +29,9 @@ WORKLOADS = {
     # name: (model, meshes per GPU, cells per mesh, obstacle, training step?)
     "fvgn_fwd_8x20k": ("FvgnA", 8, 20000, "cylinder", False),
     "fvgn_train_8x20k": ("FvgnA", 8, 20000, "cylinder", True),
+    # BASELINE.json configs[4]: VertPot / StreamFunc data-parallel training, 8 meshes per GPU (64 over 8 GPUs)
+    "vertpot_train_8x20k": ("VertPotA", 8, 20000, "cylinder", True),
+    "streamfunc_train_8x20k": ("StreamFuncA", 8, 20000, "cylinder", True),
     "mgn_fwd_2k": ("MgnA", 1, 2048, "none", False),
     "mgn_fwd_200k": ("MgnA", 1, 200000, "airfoil", False),
     # autoregressive rollouts (second half of the metric: rollout steps/sec); "rollout" in the training slot
@@ -67,8 +70,13 @@ def build_samples(model_name, n_meshes, n_cells, kind, seed0=0):
         if model_name == "MgnA":
             g[0].y = torch.cat([g[0].y, torch.zeros(g[0].x.shape[0], 1)], 1)
             g[1].y = g[1].y[:, :2].contiguous()
-        else:
+        elif model_name in ("FvgnA", "FluxA", "ConservativeA"):
             g[1].y = g[1].y[:, :3].contiguous()
+        else:                               # the model's own targets / extra inputs, as the parity tests build them
+            from helpers import finish_graphs
+            g = finish_graphs(model_name, g)
+            for t in g[:2]:
+                t._store.pop("batch", None)          # re-created by the collation
         samples.append(g)
     return samples
 
@@ -289,7 +297,9 @@ def main():
     V = host_graphs[2].pos.shape[0]
 
     # ---- device-resident leg (`value`): inputs already normalised and in HBM ------------------------
-    gd = model.normalizer.input([g.to(dev) for g in host_graphs])
+    gd = [g.to(dev) for g in host_graphs]
+    if model_name == "FvgnA":
+        gd = model.normalizer.input(gd)
     topo = get_topology(gd).validate()
     if train:
         topo.build_row_col_interleaved_csr(); topo.build_vf_csr()
@@ -297,11 +307,20 @@ def main():
     working_set = 4 * 128 * (2 * E + 3 * N) + 4 * 64 * V
     flush = torch.empty(160 * 1024 * 1024 // 4, dtype=torch.float32, device=dev) if working_set < 256e6 else None
 
-    def train_step(graphs_norm):
+    has_fn = model_name == "FvgnA"       # (subclasses inherit the method but not its contract)
+
+    def train_step(graphs_in):
         """forward (encoder + 15 GN_Blocks + decoder, integrator) + loss + backward + clip + Adam step
-        (reference Trainer._train_step, src/train.py:245-272)."""
+        (reference Trainer._train_step, src/train.py:245-272).  Models with ``forward_normalised`` take the already
+        normalised resident batch; the others normalise inside ``forward`` (in place, like the reference), so they get
+        a fresh copy of the raw batch every step - what the reference's loader hands its trainer."""
         opt.zero_grad(set_to_none=True)
-        out = model.forward_normalised(graphs_norm, mode="train")
+        if has_fn:
+            graphs_norm = graphs_in
+            out = model.forward_normalised(graphs_norm, mode="train")
+        else:
+            graphs_norm = [g.clone() for g in graphs_in]
+            out = model(graphs_norm, mode="train")
         loss = model.loss(out, graphs_norm)["total_log_loss"]
         loss.backward()
         if world > 1:   # data-parallel: meshes are independent units, one gradient all-reduce per step
@@ -366,7 +385,7 @@ def main():
     def step_e2e():
         g = cache.fetch(mesh_keys, host_samples)
         if train:
-            return float(train_step(model.normalizer.input(g)).item())      # D2H of the loss
+            return float(train_step(model.normalizer.input(g) if has_fn else g).item())      # D2H of the loss
         with torch.no_grad():
             out = model(g, mode="train")
             return out["cell_velocity_change"].to("cpu", non_blocking=False)
@@ -409,7 +428,8 @@ def main():
         return sum(a.elapsed_time(b) for a, b in ts) / len(ts)
 
     hbm_peak, peak_kind = peaks()
-    w_edge = P.weights_of(blk.face_block.face_mlp)
+    face_mlp = (blk.face_block if hasattr(blk, "face_block") else blk.edge_block).face_mlp
+    w_edge = P.weights_of(face_mlp)
     esegs = [Seg(e_lat), Seg(x_lat, SEG_GATHER, (topo.row,)), Seg(x_lat, SEG_GATHER, (topo.col,))]
     # the inference edge block exactly as the model's forward launches it: x'[row] / x'[col] TMA-gathered from the split
     # shadow the node block's epilogue wrote, e updated in place by the TMA reduce-store epilogue
@@ -417,7 +437,7 @@ def main():
     hi = x_lat.to(fast.dtype)
     fast.xs[:, :128] = hi
     fast.xs[:, 128:] = (x_lat - hi.float()).to(fast.dtype)
-    k_ms = time_kernel(lambda: P.edge_mlp_concat(blk.face_block.face_mlp, e_lat, None, topo, model.prec, want_raw=False, fast=fast))
+    k_ms = time_kernel(lambda: P.edge_mlp_concat(face_mlp, e_lat, None, topo, model.prec, want_raw=False, fast=fast))
     e_lat = torch.randn(E, 128, device=dev)          # (the in-place runs above accumulated into it)
     alg = algorithmic_bytes_edge_kernel(E, N)
     traffic, traffic_src = ncu_traffic("edge_fwd")
@@ -467,7 +487,7 @@ def main():
     E_total = float(tot[0])
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and model_name in ("FvgnA", "MgnA"):   # models the oracle trains
         cpu_baseline = time_cpu_baseline(model_name, n_meshes, n_cells, kind, train)
 
     strong = None

@@ -52,6 +52,11 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
     kind, flavour = GOLDEN_SETUP[name]
     mesh = make_mesh(n_cells, kind, seed=mesh_seed)
     g = mesh_graphs(mesh, seed=feat_seed, flavour=flavour, flip_edges=flip)
+    return mesh, finish_graphs(name, g)
+
+
+def finish_graphs(name, g):
+    """Model-specific targets / extra inputs on top of ``mesh_graphs`` (shared with bench.py's synthetic batches)."""
     c, f, v = g
     if name in MGN_LIKE + ("ConservativeB",):
         c.y = torch.cat([c.y, torch.randn(c.x.shape[0], 1, generator=torch.Generator().manual_seed(9))], 1)
@@ -68,7 +73,7 @@ def golden_graphs(name, flip=False, n_cells=160, mesh_seed=3, feat_seed=5):
         add_mls_fixture(c)
     c.batch = torch.zeros(c.x.shape[0], dtype=torch.long)
     f.batch = torch.zeros(f.pos.shape[0], dtype=torch.long)
-    return mesh, g
+    return g
 
 
 def fvgn_variant_fixture(name, c, f):
