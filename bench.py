@@ -384,10 +384,15 @@ def main():
 
     def step_e2e():
         g = cache.fetch(mesh_keys, host_samples)
+        before = torch.cuda.Event()
+        before.record()
         if train:
-            return float(train_step(model.normalizer.input(g) if has_fn else g).item())      # D2H of the loss
+            loss = train_step(model.normalizer.input(g) if has_fn else g)              # enqueued, not waited for
+            cache.prefetch(mesh_keys, host_samples, after=before)      # the next step's inputs travel while this one computes
+            return float(loss.item())                                                  # D2H of the loss
         with torch.no_grad():
             out = model(g, mode="train")
+            cache.prefetch(mesh_keys, host_samples, after=before)
             return out["cell_velocity_change"].to("cpu", non_blocking=False)
 
     h2d_full = sum(t.numel() * t.element_size() for g in host_graphs for t in g._store.values() if torch.is_tensor(t))

@@ -39,8 +39,13 @@ def _nbytes(t: torch.Tensor) -> int:
 
 
 class _Batch:
+    """One batch composition: up to two buffer sets (the static tensors are shared, the per-sample ones are not), so the
+    next step's inputs can be uploaded on a copy stream while the current step still reads the other set."""
+
     def __init__(self, graphs, row_ranges, ei_offset):
-        self.graphs, self.row_ranges, self.ei_offset = graphs, row_ranges, ei_offset
+        self.sets, self.row_ranges, self.ei_offset = [graphs, None], row_ranges, ei_offset
+        self.last_slot = 0           # the set handed out by the latest fetch
+        self.pending = None          # (slot, event) of a prefetch not yet consumed
 
 
 class GraphCache:
@@ -58,6 +63,7 @@ class GraphCache:
         self._meshes: "OrderedDict[Hashable, List[Data]]" = OrderedDict()
         self._batches: "OrderedDict[tuple, _Batch]" = OrderedDict()
         self.mesh_hits = self.mesh_misses = self.batch_hits = self.batch_misses = 0
+        self._copy_stream = None
         self.h2d_bytes = 0                      # bytes uploaded by the last fetch
         self.h2d_static_bytes = 0               # ... of which static attributes of meshes seen for the first time
 
@@ -115,11 +121,7 @@ class GraphCache:
             g._store.pop("_num_nodes", None)                  # the batch's counts follow from its tensors again
         return _Batch(graphs, row_ranges, ei_offset)
 
-    def fetch(self, keys: Sequence[Hashable], host_samples: Sequence[Sequence[Data]]) -> List[Data]:
-        keys = tuple(keys)
-        if len(keys) != len(host_samples):
-            raise ValueError("one mesh key per sample")
-        self.h2d_static_bytes = 0
+    def _batch(self, keys, host_samples) -> _Batch:
         b = self._batches.get(keys)
         if b is None:
             self.batch_misses += 1
@@ -130,10 +132,67 @@ class GraphCache:
         else:
             self.batch_hits += 1
             self._batches.move_to_end(keys)
+        return b
+
+    def fetch(self, keys: Sequence[Hashable], host_samples: Sequence[Sequence[Data]]) -> List[Data]:
+        keys = tuple(keys)
+        if len(keys) != len(host_samples):
+            raise ValueError("one mesh key per sample")
+        self.h2d_static_bytes = 0
+        b = self._batch(keys, host_samples)
+        if b.pending is not None:                  # uploaded ahead of time by prefetch(): just order this stream after it
+            slot, event, moved = b.pending
+            b.pending = None
+            torch.cuda.current_stream(self.device).wait_event(event)
+        else:
+            slot = b.last_slot
+            moved = self._upload(b, slot, host_samples)
+        b.last_slot = slot
+        self.h2d_bytes = moved + self.h2d_static_bytes
+        return b.sets[slot]
+
+    def prefetch(self, keys: Sequence[Hashable], host_samples: Sequence[Sequence[Data]], after=None) -> None:
+        """Start uploading the per-sample attributes of the NEXT batch on the cache's copy stream, into the buffer set the
+        model is not reading; the matching ``fetch`` then only waits for the copy (a loader's double buffering: the
+        host->device traffic of step k + 1 overlaps the compute of step k).  ``after``: a CUDA event recorded on the compute
+        stream BEFORE the current step's kernels were enqueued - the copies then wait only for the work before it (the step
+        that last read the target set), so a caller can enqueue the current step first and the prefetch afterwards, keeping
+        the ~50 small copy calls off the host's critical path."""
+        if self.device.type != "cuda":
+            return
+        keys = tuple(keys)
+        b = self._batch(keys, host_samples)
+        slot = 1 - b.last_slot
+        if b.sets[slot] is None:                   # second buffer set: shares every static tensor with the first
+            twin = []
+            for gi, g in enumerate(b.sets[b.last_slot]):
+                d = Data()
+                for k, v in g._store.items():
+                    if k == "topology":
+                        continue
+                    d._store[k] = torch.empty_like(v) if (torch.is_tensor(v) and k in self.dynamic[gi]) else v
+                twin.append(d)
+            b.sets[slot] = twin
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        free = after
+        if free is None:
+            free = torch.cuda.Event()
+            free.record(torch.cuda.current_stream(self.device))     # everything enqueued so far (the step that last read this set)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(free)
+            moved = self._upload(b, slot, host_samples)
+            done = torch.cuda.Event()
+            done.record(self._copy_stream)
+        b.pending = (slot, done, moved)
+
+    def _upload(self, b: _Batch, slot: int, host_samples) -> int:
+        """Per-sample attributes of every sample -> their row ranges of buffer set ``slot`` (on the current stream)."""
+        graphs = b.sets[slot]
         moved = 0
         for gi in range(3):
             for name in self.dynamic[gi]:
-                dst = b.graphs[gi]._store.get(name)
+                dst = graphs[gi]._store.get(name)
                 if dst is None:
                     continue
                 if name == "edge_index":
@@ -153,8 +212,7 @@ class GraphCache:
                             raise RuntimeError(f"GraphCache: graph {gi}.{name} changed its row count under the same mesh key")
                         dst[r0:r1].copy_(src, non_blocking=True)
                         moved += _nbytes(src)
-        self.h2d_bytes = moved + self.h2d_static_bytes
-        return b.graphs
+        return moved
 
     def clear(self):
         self._meshes.clear()

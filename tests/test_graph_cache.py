@@ -70,6 +70,11 @@ def test_training_step_through_the_cache_equals_the_direct_path():
     for it in range(2):          # second fetch: topology attached by the first step, orientation refreshed in place
         got = grads(cache.fetch([0, 1, 2], samples))
         assert all(torch.equal(a, b) for a, b in zip(ref, got)), it
+    for it in range(3):          # double-buffered: the next batch is uploaded on the copy stream while this one trains
+        g = cache.fetch([0, 1, 2], samples)
+        cache.prefetch([0, 1, 2], samples)
+        got = grads(g)
+        assert all(torch.equal(a, b) for a, b in zip(ref, got)), ("prefetch", it)
 
 
 @pytest.mark.gpu
