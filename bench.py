@@ -476,7 +476,7 @@ def main():
         v_ms = time_kernel(lambda: P.vertex_half_sum(e_lat, topo))
         v_alg = 512 * E + 256 * V + 4 * (2 * E + V + 1)      # read e once, write vsum, CSR offsets + perm
         other = [fwd_roof, chain_roof,
-                 {"kernel": "wgrad_tc_kernel<2,0>: dW = dA^T SiLU(a) (tcgen05 split-bf16, MN-major operands)", "kernel_ms": w_ms,
+                 {"kernel": "wgrad_lean_kernel: dW = dA^T SiLU(a) (tcgen05 split-bf16, MN-major operands; incl. launch + split-K reduction)", "kernel_ms": w_ms,
                   "algorithmic_bytes": w_alg, "achieved": w_alg / (w_ms * 1e-3) / 1e9, "frac": w_alg / (w_ms * 1e-3) / 1e9 / hbm_peak},
                  {"kernel": "segment_sum_kernel<16>: deterministic edge->vertex half-sums over the receiver-sorted CSR (gather / segment-sum phase)",
                   "kernel_ms": v_ms, "algorithmic_bytes": v_alg, "achieved": v_alg / (v_ms * 1e-3) / 1e9,

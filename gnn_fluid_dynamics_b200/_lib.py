@@ -30,7 +30,7 @@ EXPORTS = [
     "gnnfd_glue_workspace_bytes", "gnnfd_face_area_norm", "gnnfd_face_area_norm_backward", "gnnfd_fvm_integrate",
     "gnnfd_fvm_integrate_backward", "gnnfd_masked_mse", "gnnfd_masked_mse_backward", "gnnfd_state_advance",
 ]
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Segment(C.Structure):

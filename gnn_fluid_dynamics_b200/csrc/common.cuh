@@ -67,6 +67,11 @@ struct WgReduceJob {
 constexpr int WG_MAX_REDUCE_JOBS = 6;
 int wgrad_run(const gnnfd_wgrad_args *a, void *workspace, size_t workspace_bytes, cudaStream_t stream, WgReduceJob *defer);
 int wgrad_reduce_jobs(const WgReduceJob *jobs, int n_jobs, cudaStream_t stream);
+// lean direct x direct GEMMs (contiguous [rows, 128] operands, split-bf16): is `a` one, and up to three of them over the
+// same rows in ONE launch with their reductions deferred into jobs_out[0 .. n)
+bool wgrad_is_lean(const gnnfd_wgrad_args *a);
+int wgrad_lean_run(const gnnfd_wgrad_args *const *args, int n, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                   WgReduceJob *jobs_out);
 
 // exact-path activations (IEEE expf / tanhf); the tensor-core path uses the fast variants
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }

@@ -126,7 +126,7 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
   if (f->rows == 0) {
     // no rows: parameter gradients are zero
     const int k = f->k_in, n = f->n_out;
-    if (b->d_w1 && !b->skip_wgrad_l1) GNNFD_CUDA(cudaMemsetAsync(b->d_w1, 0, (size_t)128 * k * 4, stream));
+    if (b->d_w1 && b->skip_wgrad_l1 != 1) GNNFD_CUDA(cudaMemsetAsync(b->d_w1, 0, (size_t)128 * k * 4, stream));
     if (b->d_w2) GNNFD_CUDA(cudaMemsetAsync(b->d_w2, 0, (size_t)128 * 128 * 4, stream));
     if (b->d_w3) GNNFD_CUDA(cudaMemsetAsync(b->d_w3, 0, (size_t)n * 128 * 4, stream));
     if (b->d_b1) GNNFD_CUDA(cudaMemsetAsync(b->d_b1, 0, 128 * 4, stream));
@@ -178,20 +178,6 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
     s.src = src; s.ld = ld; s.col = 0; s.width = width; s.mode = GNNFD_SEG_DIRECT;
     return s;
   };
-  // ---- dW3 = dy^T act(a2)
-  {
-    gnnfd_wgrad_args w{};
-    w.rows = f->rows;
-    float *cs = (b->d_b3 && !b3_from_ln) ? b->d_b3 : nullptr;
-    if (n_out == 128) {
-      w.a = direct(dy, 128, 128); w.n_b = 1; w.b[0] = direct(b->a2, 128, 128); w.b_act = code;
-      w.out = b->d_w3; w.ld_out = 128; w.colsum = cs;
-    } else {   // narrow head: the 128-wide activation on the M side, transposed store
-      w.a = direct(b->a2, 128, 128); w.a_act = code; w.n_b = 1; w.b[0] = direct(dy, n_out, n_out);
-      w.out = b->d_w3; w.ld_out = 128; w.transpose_out = 1; w.colsum = cs; w.colsum_of_b = 1;
-    }
-    if ((rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
-  }
   // ---- dgrad chain: dA2 = (dy W3) * act'(a2), dA1 = (dA2 W2) * act'(a1) [, dIn_0 = dA1 W1[:, seg 0] (+ residual)]
   const bool chain = b->din_out[0] != nullptr;
   if (chain) {
@@ -211,37 +197,63 @@ extern "C" int gnnfd_mlp_backward(const gnnfd_mlp_backward_args *b, void *stream
     a.packed = pk + L.pk_w2t; a.mul = b->a1; a.mul_mode = code; a.out_raw = da1;
     if ((rc = gnnfd_mlp_forward(&a, stream)) != GNNFD_OK) return rc;
   }
-  // ---- dW2 = dA2^T act(a1)
+  // ---- weight gradients.  dW3 = dy^T act(a2), dW2 = dA2^T act(a1) and the leading contiguous block of dW1 = dA1^T In
+  //      are direct x direct GEMMs over the same rows: ONE lean launch with three TMEM accumulators.  (skip_wgrad_l1:
+  //      1 = all of dW1 / db1 is left to the caller, 2 = only the assembled (gathered) segments are.)
+  gnnfd_wgrad_args w3{}, w2{}, w1{};
   {
-    gnnfd_wgrad_args w{};
-    w.rows = f->rows;
-    w.a = direct(da2, 128, 128); w.n_b = 1; w.b[0] = direct(b->a1, 128, 128); w.b_act = code;
-    w.out = b->d_w2; w.ld_out = 128; w.colsum = b->d_b2;
-    if ((rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
+    w3.rows = f->rows;
+    float *cs = (b->d_b3 && !b3_from_ln) ? b->d_b3 : nullptr;
+    if (n_out == 128) {
+      w3.a = direct(dy, 128, 128); w3.n_b = 1; w3.b[0] = direct(b->a2, 128, 128); w3.b_act = code;
+      w3.out = b->d_w3; w3.ld_out = 128; w3.colsum = cs;
+    } else {   // narrow head: the 128-wide activation on the M side, transposed store
+      w3.a = direct(b->a2, 128, 128); w3.a_act = code; w3.n_b = 1; w3.b[0] = direct(dy, n_out, n_out);
+      w3.out = b->d_w3; w3.ld_out = 128; w3.transpose_out = 1; w3.colsum = cs; w3.colsum_of_b = 1;
+    }
+    w2.rows = f->rows;
+    w2.a = direct(da2, 128, 128); w2.n_b = 1; w2.b[0] = direct(b->a1, 128, 128); w2.b_act = code;
+    w2.out = b->d_w2; w2.ld_out = 128; w2.colsum = b->d_b2;
   }
-  // ---- dW1 = dA1^T In (In assembled from the forward's segments), remaining segment input gradients
+  const gnnfd_segment &s0 = f->seg[0];
+  const bool lead = b->skip_wgrad_l1 != 1 && s0.mode == GNNFD_SEG_DIRECT && s0.width == 128 && s0.ld == 128 && s0.col == 0 &&
+                    (f->n_seg > 1 || b->skip_wgrad_l1 == 0) && (reinterpret_cast<uintptr_t>(s0.src) & 15) == 0 && b->d_w1 != nullptr;
+  if (lead) {
+    w1.rows = f->rows;
+    w1.a = direct(da1, 128, 128); w1.n_b = 1; w1.b[0] = s0;
+    w1.out = b->d_w1; w1.ld_out = f->k_in; w1.colsum = b->d_b1;
+  }
   {
-    if (!b->skip_wgrad_l1) {
-      // a contiguous 128-wide leading segment (the residual stream x / e) goes through the lean direct x direct kernel
-      // on its own; the assembled segments (gathers, means) follow in a second GEMM into the remaining columns of dW1
-      const gnnfd_segment &s0 = f->seg[0];
-      const bool lead = f->n_seg > 1 && s0.mode == GNNFD_SEG_DIRECT && s0.width == 128 && s0.ld == 128 && s0.col == 0 &&
-                        (reinterpret_cast<uintptr_t>(s0.src) & 15) == 0;
+    const gnnfd_wgrad_args *lean[3];
+    int n_lean = 0;
+    if (wgrad_is_lean(&w3)) lean[n_lean++] = &w3;
+    if (wgrad_is_lean(&w2)) lean[n_lean++] = &w2;
+    if (lead && wgrad_is_lean(&w1)) lean[n_lean++] = &w1;
+    if (n_lean > 0) {
+      if ((rc = wgrad_lean_run(lean, n_lean, wgws, wgws_bytes, stream, &jobs[n_jobs])) != GNNFD_OK) return rc;
+      for (int j = 0; j < n_lean; ++j) { wgws += jobs[n_jobs].ws_used; wgws_bytes -= jobs[n_jobs].ws_used; ++n_jobs; }
+    }
+    if (!wgrad_is_lean(&w3) && (rc = wgrad_deferred(w3)) != GNNFD_OK) return rc;
+    if (!wgrad_is_lean(&w2) && (rc = wgrad_deferred(w2)) != GNNFD_OK) return rc;
+    if (lead && !wgrad_is_lean(&w1) && (rc = wgrad_deferred(w1)) != GNNFD_OK) return rc;
+  }
+  // ---- the rest of dW1 (assembled segments: gathers, means; or everything when there is no lean leading block),
+  //      remaining segment input gradients
+  {
+    if (b->skip_wgrad_l1 == 0) {
       gnnfd_wgrad_args w{};
       w.rows = f->rows;
       w.a = direct(da1, 128, 128);
-      w.out = b->d_w1; w.ld_out = f->k_in; w.colsum = b->d_b1;
       if (lead) {
-        w.n_b = 1; w.b[0] = s0;
-        if ((rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
         w.n_b = f->n_seg - 1;
         for (int s = 1; s < f->n_seg; ++s) w.b[s - 1] = f->seg[s];
-        w.out = b->d_w1 + 128; w.colsum = nullptr;
+        w.out = b->d_w1 + 128; w.ld_out = f->k_in;
       } else {
         w.n_b = f->n_seg;
         for (int s = 0; s < f->n_seg; ++s) w.b[s] = f->seg[s];
+        w.out = b->d_w1; w.ld_out = f->k_in; w.colsum = b->d_b1;
       }
-      if ((rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
+      if (w.n_b > 0 && (rc = wgrad_deferred(w)) != GNNFD_OK) return rc;
     }
     int col0 = 0;
     for (int s = 0; s < f->n_seg; ++s) {

@@ -139,12 +139,7 @@ __device__ __forceinline__ float4 wg_load_item(const WgPiece &pc, int lane, bool
 
 // NP = pieces (A + NP - 1 column blocks of B); MODE 0 split-bf16 (two 16-bit images per operand), 1 TF32.
 // Both modes stage 32 rows x 4 bytes per element: A 16 KB + B n_pad * 128 B per stage.
-// LEAN > 0 (NP == 2, MODE == 0 only): the producers run a loop specialised for the case that carries almost all of a
-// training step's weight-gradient bytes - A and B both DIRECT, contiguous [rows, 128] matrices, B optionally a saved
-// pre-activation (LEAN - 1 = its activation: 0 none, 1 SiLU, 2 tanh).  Running row pointers instead of per-load 64-bit
-// index arithmetic, no per-piece mode / width predicates, THREE stages of loads in flight per warp: ~120 instructions
-// per warp and stage against ~340 of the generic assembly loop, which paced the kernel (issue-bound at 2.7 TB/s).
-template <int NP, int MODE, int LEAN = 0>
+template <int NP, int MODE>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -182,65 +177,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     // =============================================================================== producers
     // warp w owns rows {w, w + 16} of every stage; lane l owns float4 column l of each piece
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (LEAN > 0) {
-      constexpr int ACT = LEAN - 1;
-      const int n_local = (int)(r_end - r_begin);                       // rows of this CTA (> 0)
-      const float *la = p.pc[0].src + (r_begin + warp) * 128 + lane * 4;   // load pointers of the next stage to fetch
-      const float *lb = p.pc[1].src + (r_begin + warp) * 128 + lane * 4;
-      int lrow = warp;                                                   // its first row, relative to r_begin
-      // image offset of the lane's 4 columns of stage row `warp` (see the generic path below); row + 16 = 2 K atoms on
-      const uint32_t off = (uint32_t)(((warp >> 3) * 2 + (lane >> 4)) * 1024 + (warp & 7) * 128 +
-                                      (((((lane & 15) >> 1) ^ (warp & 7))) << 4) + ((lane & 1) << 3));
-      constexpr uint32_t JSTEP = 4096, PART = 8192;
-      const bool want_cs = p.colsum != nullptr;
-      auto fetch = [&](float4(&a)[2], float4(&b)[2]) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const bool ok = lrow + 16 * j < n_local;
-          a[j] = ok ? ldg_f4(la + j * 16 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-          b[j] = ok ? ldg_f4(lb + j * 16 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        la += WG_KR * 128; lb += WG_KR * 128; lrow += WG_KR;
-      };
-      const int n_stages = p.stages;
-      int st = 0;
-      uint32_t st_round = 0;
-      auto put = [&](const float4(&a)[2], const float4(&b)[2]) {
-        const uint32_t sA = smem_u32(smem + (size_t)st * stage_bytes) + off, sB = sA + a_bytes;
-        if (st_round > 0) mbar_wait(&empty[st], (st_round - 1) & 1);
-        if (want_cs) {
-          cs.x += a[0].x + a[1].x; cs.y += a[0].y + a[1].y; cs.z += a[0].z + a[1].z; cs.w += a[0].w + a[1].w;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint32_t h0, l0, h1, l1;
-          split2<false>(a[j].x, a[j].y, h0, l0); split2<false>(a[j].z, a[j].w, h1, l1);
-          sts_u2(sA + j * JSTEP, h0, h1);
-          sts_u2(sA + j * JSTEP + PART, l0, l1);
-          float4 t = b[j];
-          if (ACT == 1) { t.x = wg_silu(t.x); t.y = wg_silu(t.y); t.z = wg_silu(t.z); t.w = wg_silu(t.w); }
-          else if (ACT == 2) { t.x = tanhf(t.x); t.y = tanhf(t.y); t.z = tanhf(t.z); t.w = tanhf(t.w); }
-          split2<false>(t.x, t.y, h0, l0); split2<false>(t.z, t.w, h1, l1);
-          sts_u2(sB + j * JSTEP, h0, h1);
-          sts_u2(sB + j * JSTEP + PART, l0, l1);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[st]);
-        if (++st == n_stages) { st = 0; ++st_round; }
-      };
-      float4 a0[2], b0[2], a1[2], b1[2], a2[2], b2[2];
-      fetch(a0, b0);
-      fetch(a1, b1);
-      for (int it = 0; it < n_stage_iters; it += 3) {
-        fetch(a2, b2);
-        put(a0, b0);
-        fetch(a0, b0);
-        if (it + 1 < n_stage_iters) put(a1, b1);
-        fetch(a1, b1);
-        if (it + 2 < n_stage_iters) put(a2, b2);
-      }
-    } else {
     // gather indices of a stage, one per lane: lane = slot * 2 + row slot (fetched one stage before use)
     auto load_idx = [&](int it) -> int32_t {
       const int j = lane & 1, q = lane >> 1;
@@ -359,7 +295,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (it + 1 < n_stage_iters) store_stage(it + 1, v1);
       ix1 = ix3;
     }
-    }   // generic producers
     if (p.colsum != nullptr) {   // column sums: warps reduced in fixed order
       *reinterpret_cast<float4 *>(s_cs + warp * 128 + lane * 4) = cs;
       named_bar_sync(1, WG_PROD_WARPS * 32);
@@ -423,6 +358,179 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         }
         umma_commit(&empty[st]);
         if (++st == n_stages) { st = 0; ++st_round; }
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WG_PROD_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ lean kernel
+// The case that carries almost all of a training step's weight-gradient bytes: A and B both DIRECT, contiguous
+// [rows, 128] matrices, B optionally a saved pre-activation (act: 0 none, 1 SiLU, 2 tanh), split-bf16.  The producers run
+// a loop specialised for it - running row pointers instead of per-load 64-bit index arithmetic, no per-piece mode / width
+// predicates, THREE stages of loads in flight per warp: ~120 instructions per warp and stage against ~340 of the generic
+// assembly loop, which paced the kernel (issue-bound at 2.7 TB/s; 4.4 TB/s now).
+// Up to THREE such GEMMs over the same rows run in ONE launch (dW3, dW2 and the leading block of dW1 of an MLP backward):
+// job j accumulates into TMEM columns [128 j, 128 j + 128); the stage ring and its barriers simply continue from job to
+// job, so the launch / prologue / partial-write overhead (~19 us per GEMM against 56 us of streaming) is paid once.
+constexpr int WG_LEAN_MAX_JOBS = 3;
+struct WgLeanJob {
+  const float *a, *b;
+  int32_t act;
+  float *partial;   // [grid][128][128]
+  float *colsum;    // [grid][128] column sums of A, or nullptr
+};
+struct WgLeanParams {
+  WgLeanJob job[WG_LEAN_MAX_JOBS];
+  int n_jobs, stages;
+  int64_t rows, rows_per_cta;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_lean_kernel(const __grid_constant__ WgLeanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr uint32_t a_bytes = 16 * 1024, stage_bytes = 32 * 1024;      // A hi | lo (8 KB each), B hi | lo
+  constexpr uint32_t JSTEP = 4096, PART = 8192;
+  uint8_t *s_tail = smem + (size_t)p.stages * stage_bytes;
+  float *s_cs = (float *)s_tail;                                // [16 warps][128] column-sum scratch
+  uint64_t *s_bar = (uint64_t *)(s_tail + WG_PROD_WARPS * 128 * 4);
+  uint64_t *full = s_bar, *empty = s_bar + WG_MAX_STAGES, *done = s_bar + 2 * WG_MAX_STAGES;
+  uint32_t *s_tmem = (uint32_t *)(s_bar + 2 * WG_MAX_STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], WG_PROD_WARPS); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WG_PROD_WARPS) tmem_alloc(s_tmem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int64_t r_begin = (int64_t)blockIdx.x * p.rows_per_cta;
+  const int64_t r_end = min(p.rows, r_begin + p.rows_per_cta);
+  const int n_local = (int)(r_end - r_begin);                     // rows of this CTA (> 0)
+  const int n_it = (n_local + WG_KR - 1) / WG_KR;
+  const int n_stages = p.stages;
+
+  if (warp < WG_PROD_WARPS) {
+    // =============================================================================== producers
+    // image offset of the lane's 4 columns of stage row `warp`: K atom warp >> 3 (x 2 MN atoms), MN atom lane >> 4, row
+    // warp & 7 inside the atom, 16-byte chunk ((lane & 15) >> 1) ^ (row & 7), half lane & 1; row + 16 = 2 K atoms further
+    const uint32_t off = (uint32_t)(((warp >> 3) * 2 + (lane >> 4)) * 1024 + (warp & 7) * 128 +
+                                    (((((lane & 15) >> 1) ^ (warp & 7))) << 4) + ((lane & 1) << 3));
+    int st = 0;
+    uint32_t st_round = 0;
+    for (int jb = 0; jb < p.n_jobs; ++jb) {
+      const WgLeanJob &job = p.job[jb];
+      const int act = job.act;
+      const bool want_cs = job.colsum != nullptr;
+      float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float *la = job.a + (r_begin + warp) * 128 + lane * 4;      // load pointers of the next stage to fetch
+      const float *lb = job.b + (r_begin + warp) * 128 + lane * 4;
+      int lrow = warp;                                                  // its first row, relative to r_begin
+      auto fetch = [&](float4(&a)[2], float4(&b)[2]) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool ok = lrow + 16 * j < n_local;
+          a[j] = ok ? ldg_f4(la + j * 16 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[j] = ok ? ldg_f4(lb + j * 16 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        la += WG_KR * 128; lb += WG_KR * 128; lrow += WG_KR;
+      };
+      auto put = [&](const float4(&a)[2], const float4(&b)[2]) {
+        const uint32_t sA = smem_u32(smem + (size_t)st * stage_bytes) + off, sB = sA + a_bytes;
+        if (st_round > 0) mbar_wait(&empty[st], (st_round - 1) & 1);
+        if (want_cs) {
+          cs.x += a[0].x + a[1].x; cs.y += a[0].y + a[1].y; cs.z += a[0].z + a[1].z; cs.w += a[0].w + a[1].w;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t h0, l0, h1, l1;
+          split2<false>(a[j].x, a[j].y, h0, l0); split2<false>(a[j].z, a[j].w, h1, l1);
+          sts_u2(sA + j * JSTEP, h0, h1);
+          sts_u2(sA + j * JSTEP + PART, l0, l1);
+          float4 t = b[j];
+          if (act == 1) { t.x = wg_silu(t.x); t.y = wg_silu(t.y); t.z = wg_silu(t.z); t.w = wg_silu(t.w); }
+          else if (act == 2) { t.x = tanhf(t.x); t.y = tanhf(t.y); t.z = tanhf(t.z); t.w = tanhf(t.w); }
+          split2<false>(t.x, t.y, h0, l0); split2<false>(t.z, t.w, h1, l1);
+          sts_u2(sB + j * JSTEP, h0, h1);
+          sts_u2(sB + j * JSTEP + PART, l0, l1);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[st]);
+        if (++st == n_stages) { st = 0; ++st_round; }
+      };
+      float4 a0[2], b0[2], a1[2], b1[2], a2[2], b2[2];
+      fetch(a0, b0);
+      fetch(a1, b1);
+      for (int it = 0; it < n_it; it += 3) {
+        fetch(a2, b2);
+        put(a0, b0);
+        fetch(a0, b0);
+        if (it + 1 < n_it) put(a1, b1);
+        fetch(a1, b1);
+        if (it + 2 < n_it) put(a2, b2);
+      }
+      if (want_cs) {   // column sums of A: warps reduced in fixed order (uniform branch: every producer takes it)
+        *reinterpret_cast<float4 *>(s_cs + warp * 128 + lane * 4) = cs;
+        named_bar_sync(1, WG_PROD_WARPS * 32);
+        if (tid < 128) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int w = 0; w < WG_PROD_WARPS; ++w) sacc += s_cs[w * 128 + tid];
+          job.colsum[(size_t)blockIdx.x * 128 + tid] = sacc;
+        }
+        named_bar_sync(1, WG_PROD_WARPS * 32);      // the scratch is free for the next job
+      }
+    }
+    // ================================================================================ epilogue
+    if (warp < 4) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      for (int jb = 0; jb < p.n_jobs; ++jb) {
+        float *dst = p.job[jb].partial + ((size_t)blockIdx.x * 128 + warp * 32 + lane) * 128;
+        for (int c = 0; c < 4; ++c) {
+          float acc[32];
+          tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + jb * 128 + c * 32, acc);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<float4 *>(dst + c * 32 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+        }
+      }
+      tc_fence_before();
+    }
+  } else {
+    // ================================================================================ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t sbo = 2 * 1024;
+      const uint32_t idesc = make_idesc_bf16_mn(128);
+      int st = 0;
+      uint32_t st_round = 0;
+      for (int jb = 0; jb < p.n_jobs; ++jb) {
+        const uint32_t d = tmem_base + jb * 128;
+        for (int it = 0; it < n_it; ++it) {
+          mbar_wait(&full[st], st_round & 1);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (size_t)st * stage_bytes), sB = sA + a_bytes;
+#pragma unroll
+          for (int ks = 0; ks < WG_KR / 16; ++ks) {          // K = 16 rows = 2 K atoms per MMA
+            const uint64_t ah = make_desc_mn16(sA + 2 * ks * sbo, sbo), al = make_desc_mn16(sA + PART + 2 * ks * sbo, sbo);
+            const uint64_t bh = make_desc_mn16(sB + 2 * ks * sbo, sbo), bl = make_desc_mn16(sB + PART + 2 * ks * sbo, sbo);
+            umma_ss(d, ah, bh, idesc, (it | ks) != 0);
+            umma_ss(d, al, bh, idesc, 1);
+            umma_ss(d, ah, bl, idesc, 1);
+          }
+          umma_commit(&empty[st]);
+          if (++st == n_stages) { st = 0; ++st_round; }
+        }
       }
       umma_commit(done);
     }
@@ -538,6 +646,54 @@ static int64_t wg_rows_per_cta(int64_t rows, int &grid) {
   return per;
 }
 
+bool wgrad_is_lean(const gnnfd_wgrad_args *a) {
+  const gnnfd_segment &b0 = a->b[0];
+  return a->precision == 0 && a->n_b == 1 && a->rows > 0 && a->a.mode == GNNFD_SEG_DIRECT && b0.mode == GNNFD_SEG_DIRECT &&
+         a->a.width == 128 && b0.width == 128 && a->a.ld == 128 && b0.ld == 128 && a->a.col == 0 && b0.col == 0 &&
+         a->a_act == 0 && !a->colsum_of_b && a->a.src != nullptr && b0.src != nullptr && a->out != nullptr &&
+         ((reinterpret_cast<uintptr_t>(a->a.src) | reinterpret_cast<uintptr_t>(b0.src)) & 15) == 0;
+}
+
+int wgrad_lean_run(const gnnfd_wgrad_args *const *args, int n, void *workspace, size_t workspace_bytes, cudaStream_t stream,
+                   WgReduceJob *jobs_out) {
+  if (n < 1 || n > WG_LEAN_MAX_JOBS) { set_error("wgrad_lean_run: 1..3 GEMMs per launch"); return GNNFD_E_BADARG; }
+  for (int j = 0; j < n; ++j)
+    if (!wgrad_is_lean(args[j]) || args[j]->rows != args[0]->rows) {
+      set_error("wgrad_lean_run: GEMM %d is not a lean direct x direct GEMM over the same rows", j);
+      return GNNFD_E_BADARG;
+    }
+  WgLeanParams p{};
+  int grid;
+  p.rows = args[0]->rows;
+  p.rows_per_cta = wg_rows_per_cta(p.rows, grid);
+  p.n_jobs = n;
+  p.stages = WG_MAX_STAGES;
+  const size_t per_job = (((size_t)grid * 128 * 128 * 4 + (size_t)grid * 128 * 4) + 255) & ~(size_t)255;
+  if (workspace == nullptr || workspace_bytes < per_job * n) { set_error("wgrad_lean_run: workspace too small"); return GNNFD_E_WORKSPACE; }
+  for (int j = 0; j < n; ++j) {
+    const gnnfd_wgrad_args *a = args[j];
+    float *part = (float *)((uint8_t *)workspace + per_job * j);
+    float *cs_part = part + (size_t)grid * 128 * 128;
+    p.job[j].a = a->a.src; p.job[j].b = a->b[0].src; p.job[j].act = a->b_act;
+    p.job[j].partial = part; p.job[j].colsum = a->colsum ? cs_part : nullptr;
+    WgReduceJob &r = jobs_out[j];
+    r = WgReduceJob{};
+    r.part = part; r.cs_part = cs_part; r.out = a->out; r.cs_out = a->colsum;
+    r.n_parts = grid; r.n_pad = 128; r.m_valid = 128; r.n_valid = 128;
+    r.ld_out = a->ld_out; r.transpose = a->transpose_out; r.cs_valid = a->colsum ? 128 : 0;
+    r.ws_used = per_job;
+  }
+  const int smem = p.stages * 32 * 1024 + WG_PROD_WARPS * 128 * 4 + (2 * WG_MAX_STAGES + 1) * 8 + 64 + 1024;
+  static bool attr[GNNFD_MAX_DEVICES] = {false};
+  if (!attr[current_device()]) {
+    GNNFD_CUDA(cudaFuncSetAttribute(wgrad_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr[current_device()] = true;
+  }
+  wgrad_lean_kernel<<<grid, WG_THREADS, smem, stream>>>(p);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}
+
 }  // namespace gnnfd
 
 using namespace gnnfd;
@@ -564,6 +720,13 @@ extern "C" int gnnfd_wgrad(const gnnfd_wgrad_args *a, void *workspace, size_t wo
 // in *defer for a later wgrad_reduce_jobs launch; nullptr: reduced right away.
 int gnnfd::wgrad_run(const gnnfd_wgrad_args *a, void *workspace, size_t workspace_bytes, cudaStream_t stream, WgReduceJob *defer) {
   if (defer != nullptr) *defer = WgReduceJob{};
+  if (a != nullptr && wgrad_is_lean(a)) {     // the dominant case: contiguous [rows, 128] x [rows, 128]
+    WgReduceJob job;
+    const int rc = wgrad_lean_run(&a, 1, workspace, workspace_bytes, stream, &job);
+    if (rc != GNNFD_OK) return rc;
+    if (defer != nullptr) { *defer = job; return GNNFD_OK; }
+    return wgrad_reduce_jobs(&job, 1, stream);
+  }
   GNNFD_CHECK_ARG(a != nullptr && a->out != nullptr, "null args/out");
   GNNFD_CHECK_ARG(a->rows >= 0, "negative rows");
   GNNFD_CHECK_ARG(a->n_b >= 1 && a->n_b <= 3, "n_b must be 1..3");
@@ -621,25 +784,15 @@ int gnnfd::wgrad_run(const gnnfd_wgrad_args *a, void *workspace, size_t workspac
   int stages = (int)((200u * 1024u) / stage_bytes);
   p.stages = stages > WG_MAX_STAGES ? WG_MAX_STAGES : stages;
   const int smem = p.stages * (int)stage_bytes + WG_PROD_WARPS * 128 * 4 + (2 * WG_MAX_STAGES + 1) * 8 + 64 + 1024;
-#define WG_LAUNCH(NP_, MD_, ...)                                                                                \
+#define WG_LAUNCH(NP_, MD_)                                                                                     \
   do {                                                                                                         \
     static bool attr[GNNFD_MAX_DEVICES] = {false};                                                                                  \
     if (!attr[current_device()]) {                                                                                               \
-      GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NP_, MD_, ##__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NP_, MD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr[current_device()] = true;                                                                                             \
     }                                                                                                          \
-    wgrad_tc_kernel<NP_, MD_, ##__VA_ARGS__><<<grid, WG_THREADS, smem, stream>>>(p);                            \
+    wgrad_tc_kernel<NP_, MD_><<<grid, WG_THREADS, smem, stream>>>(p);                            \
   } while (0)
-  // the dominant case of a training step (dW2 / dW3 / the direct column block of dW1): both operands contiguous
-  // [rows, 128] matrices -> the lean producer loop
-  const gnnfd_segment &b0 = a->b[0];
-  const bool lean = a->precision == 0 && a->n_b == 1 && a->a.mode == GNNFD_SEG_DIRECT && b0.mode == GNNFD_SEG_DIRECT &&
-                    a->a.width == 128 && b0.width == 128 && a->a.ld == 128 && b0.ld == 128 && a->a.col == 0 && b0.col == 0 &&
-                    a->a_act == 0 && !a->colsum_of_b && n_pad == 128 &&
-                    ((reinterpret_cast<uintptr_t>(a->a.src) | reinterpret_cast<uintptr_t>(b0.src)) & 15) == 0;
-  if (lean) {
-    if (a->b_act == 0) WG_LAUNCH(2, 0, 1); else if (a->b_act == 1) WG_LAUNCH(2, 0, 2); else WG_LAUNCH(2, 0, 3);
-  } else
   if (a->precision == 1) { if (p.n_pieces == 2) WG_LAUNCH(2, 1); else if (p.n_pieces == 3) WG_LAUNCH(3, 1); else WG_LAUNCH(4, 1); }
   else { if (p.n_pieces == 2) WG_LAUNCH(2, 0); else if (p.n_pieces == 3) WG_LAUNCH(3, 0); else WG_LAUNCH(4, 0); }
 #undef WG_LAUNCH

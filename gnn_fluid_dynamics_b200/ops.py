@@ -321,7 +321,7 @@ def mlp_backward_workspace(rows: int, device) -> torch.Tensor:
 
 def mlp_backward(segs: Sequence[Seg], w: MLPWeights, st: "MLPStash", rows: int, g: torch.Tensor, precision: int,
                  din: Sequence[Optional[dict]], workspace: torch.Tensor, da1_out: Optional[torch.Tensor] = None,
-                 skip_wgrad_l1: bool = False):
+                 skip_wgrad_l1: int = 0):
     """Whole backward of one fused MLP in one C call (gnnfd_mlp_backward).  ``din[i]`` is None or a dict with
     optional ``residual`` / ``out``.  Returns ({name: grad} for w1,b1,w2,b2,w3,b3,ln_w,ln_b present, [dIn_i])."""
     b = MlpBackwardArgs()

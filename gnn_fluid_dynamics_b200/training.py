@@ -67,11 +67,11 @@ def edge_mlp_backward_node_side(w: MLPWeights, st: MLPStash, e_in, x_src, topo: 
     dev = g.device
     d_a1 = torch.empty(E, H, dtype=torch.float32, device=dev)
     segs = _edge_segs(e_in, x_src, topo)
+    # (skip_wgrad_l1 = 2: dW1[:, 0:128] = dA1^T e and db1 are computed by the call, in the same launch as dW2 / dW3; the
+    #  columns of the two gathered segments are left to the node-side GEMM below)
     grads, dins = ops.mlp_backward(segs, w, st, E, g, prec, [{"residual": d_e_res} if d_e_res is not None else {}, None, None],
-                                   workspace, da1_out=d_a1, skip_wgrad_l1=True)
-    # dW1[:, 0:128] = dA1^T e, db1 = column sums of dA1
+                                   workspace, da1_out=d_a1, skip_wgrad_l1=2)
     w1g = grads["w1"]
-    ops.wgrad(Seg(d_a1), [Seg(e_in)], E, w1g[:, 0:H], colsum=grads.get("b1"))
     # S = [S_row | S_col]: dA1 reduced onto the cells by ONE deterministic CSR sum (2 N virtual rows, see the topology)
     rc_off, rc_perm = topo.build_row_col_interleaved_csr()
     s_rc = torch.empty(N, 2 * H, dtype=torch.float32, device=dev)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 3
+#define GNNFD_ABI_VERSION 4
 
 enum {
   GNNFD_OK = 0,
@@ -250,7 +250,9 @@ typedef struct {
   void *workspace;
   size_t workspace_bytes;
   /* Optional: da1_out [rows, 128] receives dA1 (the gradient at the first hidden pre-activation) and, with
-   * skip_wgrad_l1 = 1, the library leaves dW1 / db1 to the caller.  Used when the MLP input gathers rows of a node
+   * skip_wgrad_l1 = 1, the library leaves dW1 / db1 to the caller; with skip_wgrad_l1 = 2 (ABI v4) it still computes
+   * db1 and the leading contiguous 128-column block of dW1 (segment 0 DIRECT: the residual stream) - in the same launch
+   * as dW2 / dW3 - and leaves only the assembled (gathered) segments' columns to the caller.  Used when the MLP input gathers rows of a node
    * matrix: by linearity sum_e dA1[e]^T x[row[e]] = (segment-sum of dA1 by row)^T x, so the caller reduces dA1 onto
    * the nodes first and runs the weight-gradient GEMM and the input-gradient Linear over N node rows instead of E
    * gathered edge rows (gnn_fluid_dynamics_b200/training.py). */
