@@ -17,7 +17,8 @@ PREC_F32, PREC_BF16X3, PREC_BF16X1, PREC_FP16X2, PREC_FP16X3 = 0, 1, 2, 3, 4
 PRECISIONS = {"f32": PREC_F32, "bf16x3": PREC_BF16X3, "bf16x1": PREC_BF16X1,
               "fp16x2": PREC_FP16X2, "fp16x3": PREC_FP16X3}
 ACT_SILU, ACT_TANH = 0, 1
-SEG_DIRECT, SEG_GATHER, SEG_SUM2, SEG_DIFF2, SEG_MEAN3 = 0, 1, 2, 3, 4
+SEG_DIRECT, SEG_GATHER, SEG_SUM2, SEG_DIFF2, SEG_MEAN3, SEG_SUM3S = 0, 1, 2, 3, 4, 5
+SUM3S_ZERO = -(2 ** 31)          # GNNFD_SUM3S_ZERO: index entry that contributes nothing
 
 EXPORTS = [
     "gnnfd_abi_version", "gnnfd_last_error", "gnnfd_index_narrow", "gnnfd_csr_workspace_bytes",

@@ -85,6 +85,13 @@ __device__ __forceinline__ float tanh_fast(float v) {
   return r;
 }
 
+// GNNFD_SEG_SUM3S index entry -> (row, sign)
+__device__ __forceinline__ void sum3s_decode(int32_t v, int32_t &row, float &sign) {
+  const bool zero = v == INT32_MIN;
+  row = zero ? 0 : (v >= 0 ? v : ~v);
+  sign = zero ? 0.f : (v >= 0 ? 1.f : -1.f);
+}
+
 __device__ __forceinline__ float4 ldg_f4(const float *p) {
   return __ldg(reinterpret_cast<const float4 *>(p));
 }

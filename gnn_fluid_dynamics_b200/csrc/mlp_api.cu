@@ -19,12 +19,12 @@ int validate_mlp_args(const gnnfd_mlp_args *a) {
   for (int s = 0; s < a->n_seg; ++s) {
     const gnnfd_segment &sg = a->seg[s];
     GNNFD_CHECK_ARG(sg.width > 0 && sg.ld >= sg.col + sg.width && sg.col >= 0, "bad segment geometry");
-    GNNFD_CHECK_ARG(sg.mode >= GNNFD_SEG_DIRECT && sg.mode <= GNNFD_SEG_MEAN3, "bad segment mode");
+    GNNFD_CHECK_ARG(sg.mode >= GNNFD_SEG_DIRECT && sg.mode <= GNNFD_SEG_SUM3S, "bad segment mode");
     if (a->rows > 0) {
       GNNFD_CHECK_ARG(sg.src != nullptr, "null segment source");
       if (sg.mode >= GNNFD_SEG_GATHER) GNNFD_CHECK_ARG(sg.idx[0] != nullptr, "null gather index 0");
       if (sg.mode >= GNNFD_SEG_SUM2) GNNFD_CHECK_ARG(sg.idx[1] != nullptr, "null gather index 1");
-      if (sg.mode == GNNFD_SEG_MEAN3) GNNFD_CHECK_ARG(sg.idx[2] != nullptr, "null gather index 2");
+      if (sg.mode >= GNNFD_SEG_MEAN3) GNNFD_CHECK_ARG(sg.idx[2] != nullptr, "null gather index 2");
     }
     k += sg.width;
   }

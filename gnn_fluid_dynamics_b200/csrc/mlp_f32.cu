@@ -142,8 +142,17 @@ __device__ void assemble_input(const F32Params &p, int64_t row0, float *s_a) {
       for (int s = 0; s < a.n_seg; ++s) {
         const gnnfd_segment &sg = a.seg[s];
         const float *b0, *b1 = nullptr, *b2 = nullptr;
+        float s0 = 1.f, s1 = 1.f, s2 = 1.f;     // SUM3S signs
         if (sg.mode == GNNFD_SEG_DIRECT) {
           b0 = sg.src + g * sg.ld + sg.col;
+        } else if (sg.mode == GNNFD_SEG_SUM3S) {
+          int32_t r0, r1, r2;
+          sum3s_decode(__ldg(sg.idx[0] + g), r0, s0);
+          sum3s_decode(__ldg(sg.idx[1] + g), r1, s1);
+          sum3s_decode(__ldg(sg.idx[2] + g), r2, s2);
+          b0 = sg.src + (int64_t)r0 * sg.ld + sg.col;
+          b1 = sg.src + (int64_t)r1 * sg.ld + sg.col;
+          b2 = sg.src + (int64_t)r2 * sg.ld + sg.col;
         } else {
           b0 = sg.src + (int64_t)__ldg(sg.idx[0] + g) * sg.ld + sg.col;
           if (sg.mode >= GNNFD_SEG_SUM2) b1 = sg.src + (int64_t)__ldg(sg.idx[1] + g) * sg.ld + sg.col;
@@ -164,6 +173,10 @@ __device__ void assemble_input(const F32Params &p, int64_t row0, float *s_a) {
               float4 w = ldg_f4(b1 + c), u = ldg_f4(b2 + c);
               v.x = ((v.x + w.x) + u.x) / 3.0f; v.y = ((v.y + w.y) + u.y) / 3.0f;
               v.z = ((v.z + w.z) + u.z) / 3.0f; v.w = ((v.w + w.w) + u.w) / 3.0f;
+            } else if (sg.mode == GNNFD_SEG_SUM3S) {
+              float4 w = ldg_f4(b1 + c), u = ldg_f4(b2 + c);
+              v.x = (s0 * v.x + s1 * w.x) + s2 * u.x; v.y = (s0 * v.y + s1 * w.y) + s2 * u.y;
+              v.z = (s0 * v.z + s1 * w.z) + s2 * u.z; v.w = (s0 * v.w + s1 * w.w) + s2 * u.w;
             }
             *reinterpret_cast<float4 *>(dst + k + c) = v;
           }
@@ -173,6 +186,7 @@ __device__ void assemble_input(const F32Params &p, int64_t row0, float *s_a) {
             if (sg.mode == GNNFD_SEG_SUM2) v += __ldg(b1 + c);
             else if (sg.mode == GNNFD_SEG_DIFF2) v -= __ldg(b1 + c);
             else if (sg.mode == GNNFD_SEG_MEAN3) v = ((v + __ldg(b1 + c)) + __ldg(b2 + c)) / 3.0f;
+            else if (sg.mode == GNNFD_SEG_SUM3S) v = (s0 * v + s1 * __ldg(b1 + c)) + s2 * __ldg(b2 + c);
             dst[k + c] = v;
           }
         }

@@ -153,6 +153,22 @@ __device__ __noinline__ void tc_load_block_generic(const TcParams &p, const int3
     const int64_t g = row0 + r;
     float t4[4] = {0.f, 0.f, 0.f, 0.f};
     if (active && g < rows) {
+      if (d.mode == GNNFD_SEG_SUM3S) {     // signed sum of three gathered rows
+        int32_t r3[3];
+        float s3[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) sum3s_decode(ixs[u * TC_BM + r], r3[u], s3[u]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (f4 * 4 + q < d.kvalid) {
+            const int64_t c = d.colk + f4 * 4 + q;
+            t4[q] = (s3[0] * __ldg(d.src + (int64_t)r3[0] * d.ld + c) + s3[1] * __ldg(d.src + (int64_t)r3[1] * d.ld + c)) +
+                    s3[2] * __ldg(d.src + (int64_t)r3[2] * d.ld + c);
+          }
+        }
+        v[jj] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+        continue;
+      }
       const int64_t i0 = d.mode == GNNFD_SEG_DIRECT ? g : (int64_t)ixs[r];
       const float *b0 = d.src + i0 * d.ld + d.colk + f4 * 4;
 #pragma unroll
@@ -208,6 +224,31 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
     } else {
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + (int64_t)lds_s32(ixa + 64 * jj) * ld);
+    }
+  } else if (d.mode == GNNFD_SEG_SUM3S) {
+    // (s0 a + s1 b) + s2 c: three gathered rows with the signs decoded from the index entries
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float4 y[2], z[2];
+      float sg[2][3];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int jj = h * 2 + u;
+        int32_t r0, r1, r2;
+        sum3s_decode(lds_s32(ixa + 64 * jj), r0, sg[u][0]);
+        sum3s_decode(lds_s32(ixa + (TC_BM + 16 * jj) * 4), r1, sg[u][1]);
+        sum3s_decode(lds_s32(ixa + (2 * TC_BM + 16 * jj) * 4), r2, sg[u][2]);
+        v[jj] = ldg_f4(base + (int64_t)r0 * ld);
+        y[u] = ldg_f4(base + (int64_t)r1 * ld);
+        z[u] = ldg_f4(base + (int64_t)r2 * ld);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const float4 a = v[h * 2 + u];
+        const float s0 = sg[u][0], s1 = sg[u][1], s2 = sg[u][2];
+        v[h * 2 + u] = make_float4((s0 * a.x + s1 * y[u].x) + s2 * z[u].x, (s0 * a.y + s1 * y[u].y) + s2 * z[u].y,
+                                   (s0 * a.z + s1 * y[u].z) + s2 * z[u].z, (s0 * a.w + s1 * y[u].w) + s2 * z[u].w);
+      }
     }
   } else if (d.mode == GNNFD_SEG_MEAN3) {
 #pragma unroll
@@ -339,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         for (int s = 0; s < a.n_seg; ++s) {
           const gnnfd_segment &sg = a.seg[s];
           const int n_idx = sg.mode == GNNFD_SEG_DIRECT ? 0 : sg.mode == GNNFD_SEG_GATHER ? 1
-                            : sg.mode == GNNFD_SEG_MEAN3 ? 3 : 2;
+                            : sg.mode >= GNNFD_SEG_MEAN3 ? 3 : 2;
           for (int q = pt; q < n_idx * TC_BM; q += TC_PROD_THREADS) {
             const int ji = q / TC_BM, r = q % TC_BM;
             const int64_t g = row0 + r;

@@ -59,12 +59,22 @@ class ConservativeA(FvgnA):
         x, e, _ = P.run_processor(self.family, self.processer_list, x, e, topo, prec, e_asym=e_asym, hook=hook)
         return x, e, P.mlp_rows(self.decoder.face_mlp, e, prec)
 
+    @staticmethod
+    def _attach_signed_ell(topo, f_graph):
+        """Fixed-degree table of the signed edge->cell aggregation (``MeshTopology.build_signed_cell_ell``) for the fused
+        inference path of the 'cons_a' GN_Block; triangle meshes only (``f_graph.face`` [3, N])."""
+        face = getattr(f_graph, "face", None)
+        topo.signed_ell = (topo.build_signed_cell_ell(face)
+                           if torch.is_tensor(face) and face.dim() == 2 and face.shape[0] == 3 and face.shape[1] == topo.n_cells
+                           else None)
+
     def forward(self, graphs, mode="rollout"):   # Conservative.py:164-189
         graphs = self.normalizer.input(graphs)
         c_graph, f_graph, v_graph = graphs
         c_graph.edge_attr = f_graph.x_symm
         c_graph.edge_attr_asym = f_graph.x_asym
         topo = get_topology(graphs, need_cell_csr=True, two_hop=False)
+        self._attach_signed_ell(topo, f_graph)
         _, _, edge_attr_out = self.encode_process_decode(c_graph.x, f_graph.x_symm, f_graph.x_asym, topo)
         self.dt = c_graph.dt
         acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
@@ -200,6 +210,7 @@ class ConservativeB(MgnA):
         c_graph.edge_attr = f_graph.x_symm
         c_graph.edge_attr_asym = f_graph.x_asym
         topo = get_topology(graphs, need_cell_csr=True, two_hop=False)
+        ConservativeA._attach_signed_ell(topo, f_graph)
         _, _, cell_output = self.encode_process_decode(c_graph.x, f_graph.x_symm, f_graph.x_asym, topo)
         output = [cell_output, None, None]
         if mode == "rollout":

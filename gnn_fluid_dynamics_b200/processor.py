@@ -26,7 +26,7 @@ import torch
 
 from . import autograd_ops as A
 from . import ops
-from ._lib import ACT_SILU, ACT_TANH, PREC_F32, SEG_DIFF2, SEG_DIRECT, SEG_GATHER, SEG_MEAN3, SEG_SUM2
+from ._lib import ACT_SILU, ACT_TANH, PREC_F32, SEG_DIFF2, SEG_DIRECT, SEG_GATHER, SEG_MEAN3, SEG_SUM2, SEG_SUM3S
 from .ops import MLPWeights, Seg
 from .topology import MeshTopology
 
@@ -78,6 +78,11 @@ class Fast:
 
 
 FAST_ENABLED = True      # tests / comparisons can pin the register-staged kernels with ``no_fast()``
+# Conservative 'cons_a' blocks: fold the signed edge->cell sum into the node MLP's input assembly (SEG_SUM3S) instead of a
+# separate segment-sum launch.  Correct (tests/test_gpu_parity.py) but MEASURED SLOWER on the 200k-cell rollout (7.88 vs
+# 6.76 ms/step): three register-staged 512 B gathers per cell in the node kernel's producers cost more than the segment-sum
+# kernel plus one contiguous read of agg[N, 128], so it is off by default.
+FUSE_SIGNED_SUM = False
 
 
 class no_fast:
@@ -193,6 +198,14 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
         return x_new, e_new, None
     if family == "cons_a":
         e_raw, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec, mul=e_asym)
+        ell = getattr(topo, "signed_ell", None)
+        if (FUSE_SIGNED_SUM and ell is not None and FAST_ENABLED
+                and not (torch.is_grad_enabled() and (e_raw.requires_grad or x.requires_grad))):
+            # inference: the signed edge->cell sum is the node MLP's own input assembly (three signed gathered rows per
+            # cell, SEG_SUM3S) - agg[N, 128] is never written
+            _, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(e_raw, SEG_SUM3S, ell)], x.shape[0], prec, residual=x,
+                             want_raw=False, want_sum=True)
+            return x_new, e_new, None
         agg = cell_signed_sum(e_raw, topo)
         _, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(agg)], x.shape[0], prec, residual=x,
                          want_raw=False, want_sum=True)

@@ -112,6 +112,34 @@ class MeshTopology:
             self._rc2csr = ops.csr_build(torch.cat([self.row * 2, self.col * 2 + 1]), 2 * self.n_cells)
         return self._rc2csr
 
+    def build_signed_cell_ell(self, f_face: torch.Tensor):
+        """The direct signed edge->cell aggregation of the Conservative models (``agg[c] = sum_{col(k)=c} e_k -
+        sum_{row(k)=c} e_k``, Conservative.py:243-254) as a FIXED-degree table for ``SEG_SUM3S``: a triangle cell has
+        exactly three faces (``f_graph.face`` [3, N]), each contributing +e (the cell is the face's second cell), -e (its
+        first cell) or nothing (boundary face = self-loop: its +e and -e entries cancel).  The three slots of a cell are
+        ordered like the reference's scatter_add visits them (all '+' entries in ascending face id, then the '-' entries),
+        so an interior cell's fused sum is bit-identical to the sequential one.  -> (idx0, idx1, idx2) int32 [N] each,
+        entries encoded as in include/gnnfd_b200.h (k, ~k, GNNFD_SUM3S_ZERO)."""
+        key = (f_face.data_ptr(), f_face._version, self._c_key)
+        cached = getattr(self, "_ell", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        from ._lib import SUM3S_ZERO
+        cf = f_face.to(self.device).long()                        # [3, N] face ids
+        if cf.shape[1] != self.n_cells:
+            raise RuntimeError("build_signed_cell_ell: f_graph.face does not have one column per cell")
+        cell = torch.arange(self.n_cells, device=self.device).unsqueeze(0).expand_as(cf)
+        row, col = self.row.long()[cf], self.col.long()[cf]
+        plus, minus = (col == cell) & (row != cell), (row == cell) & (col != cell)
+        zero = ~(plus | minus)                                     # self-loops (and faces that do not touch the cell)
+        enc = torch.where(plus, cf, torch.where(minus, -cf - 1, torch.full_like(cf, SUM3S_ZERO)))
+        order = torch.where(zero, 2, torch.where(minus, 1, 0)) * (2 * self.n_faces + 2) + cf   # '+' by k, then '-' by k, zeros last
+        perm = torch.argsort(order, dim=0, stable=True)
+        enc = torch.gather(enc, 0, perm).to(torch.int32).contiguous()
+        ell = (enc[0], enc[1], enc[2])
+        self._ell = (key, ell)
+        return ell
+
     def build_col_csr(self):
         if getattr(self, "_colcsr", None) is None:
             self._colcsr = ops.csr_build(self.col, self.n_cells)

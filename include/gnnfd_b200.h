@@ -56,8 +56,15 @@ enum {
   GNNFD_SEG_GATHER = 1, /* src[idx0[r], col:col+width]                 (x[row], x[col])       */
   GNNFD_SEG_SUM2 = 2,   /* src[idx0[r]] + src[idx1[r]]                 (Conservative.py:230)  */
   GNNFD_SEG_DIFF2 = 3,  /* src[idx0[r]] - src[idx1[r]]                 (Conservative.py:621)  */
-  GNNFD_SEG_MEAN3 = 4   /* ((src[idx0[r]] + src[idx1[r]]) + src[idx2[r]]) / 3.0  (Fvgn.py:317-321) */
+  GNNFD_SEG_MEAN3 = 4,  /* ((src[idx0[r]] + src[idx1[r]]) + src[idx2[r]]) / 3.0  (Fvgn.py:317-321) */
+  /* ABI v4: signed sum of three gathered rows, (s0 src[r0] + s1 src[r1]) + s2 src[r2] - the direct signed edge->cell
+   * aggregation of the Conservative models (Conservative.py:243-254) fused into the node MLP's input assembly: a triangle
+   * cell has exactly three faces, so its scatter_add row is a fixed-degree sum.  idx entries encode (row, sign):
+   * v >= 0: +src[v];  v < 0: -src[~v];  GNNFD_SUM3S_ZERO: no contribution (a boundary face is a self-loop whose +e and
+   * -e entries cancel).  Forward only (inference). */
+  GNNFD_SEG_SUM3S = 5
 };
+#define GNNFD_SUM3S_ZERO INT32_MIN
 
 typedef struct {
   const float *src;      /* row-major source matrix */

@@ -346,3 +346,47 @@ def test_determinism_bitwise_repeatable():
         a = model.encode_process_decode(gd[0].x, gd[1].x, topo)
         b = model.encode_process_decode(gd[0].x, gd[1].x, topo)
     assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
+@pytest.mark.parametrize("prec", ["f32", "bf16x3"])
+def test_signed_sum3_segment_equals_cell_signed_sum(prec):
+    """SEG_SUM3S (the Conservative models' signed edge->cell aggregation as the node MLP's own input assembly,
+    Conservative.py:243-254) against the segment-sum kernel + a DIRECT segment: interior cells bit-identical sums, the MLP
+    outputs within the precision's tolerance; and ConservativeA's forward with the fused path against the unfused one."""
+    from gnn_fluid_dynamics_b200 import ops, _lib, processor as P
+    from gnn_fluid_dynamics_b200.ops import Seg
+    from gnn_fluid_dynamics_b200.topology import get_topology
+    dev = torch.device("cuda:0")
+    _, graphs = golden_graphs("ConservativeA", n_cells=3000, mesh_seed=7, feat_seed=8)
+    gd = [g.to(dev) for g in graphs]
+    topo = get_topology(gd, need_cell_csr=True, two_hop=False).validate()
+    ell = topo.build_signed_cell_ell(gd[1].face)
+    N, E = gd[0].x.shape[0], gd[0].edge_index.shape[1]
+    gen = torch.Generator().manual_seed(3)
+    e_raw = torch.randn(E, 128, generator=gen).to(dev)
+    x = torch.randn(N, 128, generator=gen).to(dev)
+    agg = P.cell_signed_sum(e_raw, topo)
+    # the table itself: decode and sum on the host side of the device
+    ref = torch.zeros_like(agg)
+    for i in ell:
+        i = i.long()
+        zero = i == _lib.SUM3S_ZERO
+        rows = torch.where(i >= 0, i, -i - 1).clamp(min=0)
+        sign = torch.where(zero, 0.0, torch.where(i >= 0, 1.0, -1.0)).to(torch.float32)
+        ref = ref + sign[:, None] * e_raw[torch.where(zero, torch.zeros_like(rows), rows)]
+    assert rel_l2(ref, agg) < 1e-6
+    w = _to_weights(_rand_mlp(256, 128, True, seed=4), 0)
+    p = _lib.PRECISIONS[prec]
+    fused, _ = ops.mlp_forward([Seg(x), Seg(e_raw, _lib.SEG_SUM3S, ell)], w, N, p)
+    plain, _ = ops.mlp_forward([Seg(x), Seg(agg)], w, N, p)
+    assert rel_l2(fused, plain) < (1e-6 if prec == "f32" else 2e-5), rel_l2(fused, plain)
+    model = build_model("ConservativeA", precision=prec if prec != "f32" else None).to(dev).eval()
+    with torch.no_grad():
+        out_p = model([g.clone() for g in gd], mode="rollout")
+        P.FUSE_SIGNED_SUM = True
+        try:
+            out_f = model([g.clone() for g in gd], mode="rollout")
+        finally:
+            P.FUSE_SIGNED_SUM = False
+    for k in out_f:
+        assert rel_l2(out_f[k], out_p[k]) < 1e-4, (k, rel_l2(out_f[k], out_p[k]))
