@@ -154,14 +154,16 @@ class ClockSampler:
 
 def ncu_traffic(which):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of a kernel at the bench shape, from the committed
-    `ncu --set full` captures: profiles/r02_fwd_edge_fast_ncu_summary.json (inference edge block, scripts/prof_fwd_edge.py
-    fast) and profiles/r01_train_kernels_ncu_summary.json (scripts/prof_train_kernels.py, launch order: forward+stash,
-    wgrad L3, dgrad chain, wgrad L2, wgrad L1, 2 x single Linear - the training kernels' traffic has not changed since)."""
+    `ncu --set full` captures (scripts/refresh_profiles.sh): profiles/r02_fwd_edge_fast_ncu_summary.json (inference edge
+    block, scripts/prof_fwd_edge.py fast) and profiles/r02_train_kernels_ncu_summary.json (scripts/prof_train_kernels.py:
+    forward + stash, dgrad chain, the lean weight-gradient launch, ...), looked up by kernel instantiation."""
     try:
         if which in ("edge_chain", "edge_stash"):
-            name = "r01_train_kernels_ncu_summary.json"
+            name = "r02_train_kernels_ncu_summary.json"
             d = json.load(open(os.path.join(ROOT, "profiles", name)))
-            return int(d["launches"][2 if which == "edge_chain" else 0]["dram_traffic_bytes"]), name
+            tag = "mlp_tc_kernel<0, 2, 2, 1, 0>" if which == "edge_chain" else "mlp_tc_kernel<0, 2, 2, 0, 0>"
+            hits = [l for l in d["launches"] if tag in l.get("kernel", "")]
+            return int(max(hits, key=lambda l: l.get("duration_us", 0))["dram_traffic_bytes"]), name
         name = "r02_fwd_edge_fast_ncu_summary.json"
         d = json.load(open(os.path.join(ROOT, "profiles", name)))
         return int(d["launches"][0]["dram_traffic_bytes"]), name
@@ -495,12 +497,21 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and model_name in ("FvgnA", "MgnA"):   # models the oracle trains
         cpu_baseline = time_cpu_baseline(model_name, n_meshes, n_cells, kind, train)
 
-    strong = None
+    strong, rollouts = None, None
     if args.strong_4m == "on" or (args.strong_4m == "auto" and args.workload == DEFAULT_WORKLOAD):
         del model, opt, gd, cache
         torch.cuda.empty_cache()
         strong = strong_scaling_4m(world, rank, dev, dist, steps=max(args.steps, 20) if world > 1 else max(5, min(args.steps, 10)),
                                    halo=args.halo)
+        if world == 1:
+            # the second half of BASELINE.json's metric (rollout steps/sec) for configs[0] and configs[2], same run
+            rollouts = {}
+            for wl, n_steps in (("mgn_rollout_2k", 100), ("flux_rollout_200k", 20), ("cons_rollout_200k", 20)):
+                m = measure_rollout(wl, 1, 0, dev, dist, steps=n_steps, warmup=5)
+                rollouts[wl] = {"model": m["model"], "cells": m["N"], "faces": m["E"], "ms_per_step": m["ms"],
+                                "rollout_steps_per_s": 1e3 / m["ms"], "edge_updates_per_s": m["E"] * MP_NUM / (m["ms"] * 1e-3),
+                                "e2e_ms_per_step": m["ms_e2e"], "execution": "CUDA-graph replay, velocity read back per step in e2e",
+                                "clocks": m["clocks"]}
 
     if rank == 0:
         line = {
@@ -531,6 +542,8 @@ def main():
         }
         if strong is not None:
             line["strong_4m"] = strong
+        if rollouts is not None:
+            line["rollouts"] = rollouts
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

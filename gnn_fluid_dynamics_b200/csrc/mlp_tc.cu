@@ -679,6 +679,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       const int64_t row0 = tile_row0(j);
       const uint32_t lanes = (uint32_t)(q4 * 32) << 16;
       const uint32_t xr = tmem_base + lanes + xs * 128 + eh * 64, yr = tmem_base + lanes + TC_Y_COL + eh * 64;
+      // (L2 prefetch of the rows this tile's later phases read - the second hidden layer's saved pre-activations, the
+      //  residual - issued from here measured no gain in an A/B on one box: edge MLP backward 859 vs 834 us)
       // ---- hidden layers: accumulator -> +bias, act -> hi/lo pairs, written back in place
       for (int layer = 0; layer < p.nl - 1; ++layer) {
         const uint32_t reg = layer == 0 ? xr : yr;

@@ -63,7 +63,7 @@ class ConservativeA(FvgnA):
     def _attach_signed_ell(topo, f_graph):
         """Fixed-degree table of the signed edge->cell aggregation (``MeshTopology.build_signed_cell_ell``) for the fused
         inference path of the 'cons_a' GN_Block; triangle meshes only (``f_graph.face`` [3, N])."""
-        face = getattr(f_graph, "face", None)
+        face = getattr(f_graph, "face", None) if P.FUSE_SIGNED_SUM else None      # (off by default: measured slower)
         topo.signed_ell = (topo.build_signed_cell_ell(face)
                            if torch.is_tensor(face) and face.dim() == 2 and face.shape[0] == 3 and face.shape[1] == topo.n_cells
                            else None)
