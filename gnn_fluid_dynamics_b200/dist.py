@@ -35,6 +35,7 @@ class PartState:
     e: Optional[torch.Tensor] = None
     send_idx: Optional[dict] = None  # peer -> int32 device tensor
     xs: Optional[torch.Tensor] = None    # split precisions: 16-bit hi|lo shadow of the gathered cell matrix (processor.Fast)
+    e_asym: Optional[torch.Tensor] = None    # 'cons_a': the antisymmetric face encoding multiplied into block 0's face output
 
     def device_plan(self, device):
         if self.send_idx is None:
@@ -100,8 +101,10 @@ def run_processor_partitioned(family: str, blocks, states: List[PartState], tran
     """The GN_Blocks over partitioned latents.  Edge phases run on all local faces, node phases on owned cells
     only; exactly one halo exchange per block (MGN: block-input x, skipped for block 0 where the ghosts' x is the
     locally encoded one; FVGN: the raw cell-MLP output x')."""
+    if family == "cons_a":
+        return _run_processor_partitioned_cons_a(blocks, states, transport, prec)
     if family not in ("mgn", "fvgn"):
-        raise NotImplementedError(f"domain decomposition covers the 'mgn' and 'fvgn' data-flows, not {family!r}")
+        raise NotImplementedError(f"domain decomposition covers the 'mgn', 'fvgn' and 'cons_a' data-flows, not {family!r}")
     if ops.split_dtype(prec) is not None and all(s.xs is not None for s in states):
         return _run_processor_partitioned_fast(family, blocks, states, transport, prec)
     for i, blk in enumerate(blocks):
@@ -132,6 +135,30 @@ def run_processor_partitioned(family: str, blocks, states: List[PartState], tran
             for s in states:
                 _, s.e = ops.mlp_forward(_edge_segs(s.e, s.x_raw, s.topo), we, s.e.shape[0], prec, residual=s.e,
                                          want_raw=False, want_sum=True)
+    return states
+
+
+def _run_processor_partitioned_cons_a(blocks, states: List[PartState], transport, prec: int):
+    """ConservativeA's GN_Blocks (Conservative.py:210-254) over partitioned latents: face block on all local faces
+    (``x[row] + x[col]`` gathers ghost cells), signed edge->cell sum and cell block on the owned cells, ONE exchange of the
+    block-input ``x`` per block (skipped for block 0: ghosts are encoded locally).  The vertex-star halo of the plan is a
+    superset of the face-neighbour ring this data-flow needs (every face of an owned cell is local), and local faces keep
+    global order, so the owned rows are bit-identical to the single-GPU result."""
+    from ._lib import SEG_SUM2
+    for i, blk in enumerate(blocks):
+        we, wn = weights_of(blk.face_block.face_mlp), weights_of(blk.cell_block.cell_mlp)
+        if i > 0:
+            transport.exchange(states, lambda s: s.x)
+        for s in states:
+            topo, n_own = s.topo, s.part.n_owned
+            segs = [Seg(s.e), Seg(s.x, SEG_SUM2, (topo.row, topo.col))]
+            e_raw, e_new = ops.mlp_forward(segs, we, s.e.shape[0], prec, mul=s.e_asym if i == 0 else None, residual=s.e,
+                                           want_raw=True, want_sum=True)
+            off, perm = topo.build_cell_csr()
+            agg = ops.segment_sum(e_raw, e_raw, 0, 0, H, -1.0, off, perm, n_own)
+            x_new = torch.empty_like(s.x)                     # ghost rows: filled by the next block's exchange
+            ops.mlp_forward([Seg(s.x), Seg(agg)], wn, n_own, prec, residual=s.x, want_raw=False, want_sum=True, out_sum=x_new)
+            s.x, s.e = x_new, e_new
     return states
 
 
@@ -182,6 +209,15 @@ def encode_process_decode_partitioned(model, states: List[PartState], inputs, tr
     decoder (MGN) covers the owned cells, the edge decoder (FVGN) all local faces."""
     from . import processor as P
     prec = model.prec
+    if model.family == "cons_a":       # inputs[k] = (c_x, f_x_symm, f_x_asym); edge decoder (Conservative.py:164-189)
+        from ._lib import ACT_TANH
+        for s, (c_x, f_s, f_a) in zip(states, inputs):
+            s.e = P.mlp_rows(model.encoder.faceS_mlp, f_s, prec)
+            s.e_asym = P.mlp_rows(model.encoder.faceA_mlp, f_a, prec, act=ACT_TANH)
+            s.x = P.mlp_rows(model.encoder.cell_mlp, c_x, prec)
+            s.xs = None
+        run_processor_partitioned("cons_a", model.processer_list, states, transport, prec)
+        return [(s.x[:s.part.n_owned], s.e, P.mlp_rows(model.decoder.face_mlp, s.e, prec)) for s in states]
     sdt = ops.split_dtype(prec)
     for s, (c_x, f_x) in zip(states, inputs):
         s.e = P.mlp_rows(model.encoder.face_mlp, f_x, prec)
