@@ -1,7 +1,7 @@
 // Halo exchange support for the domain-decomposed processor: pack the rows of boundary cells that a peer
 // rank needs into one contiguous send buffer (the receive side lands straight in the ghost rows, which are
 // laid out contiguously per owner rank, so there is no unpack pass).  The transfer itself is NCCL P2P
-// (torch.distributed all_to_all_single) over NVLink - gnn_fluid_dynamics_b200/dist.py.
+// (torch.distributed batch_isend_irecv: grouped ncclSend / ncclRecv) over NVLink - gnn_fluid_dynamics_b200/dist.py.
 #include "common.cuh"
 
 namespace gnnfd {

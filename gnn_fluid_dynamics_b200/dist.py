@@ -371,11 +371,16 @@ class PeerBuffers:
                 else:
                     fn, fargs = gathered[r][b]
                     fargs = list(fargs)
+                    # torch's CUDA-IPC rebuild tuple is not a public contract: refuse to guess if its layout moved
+                    if getattr(fn, "__name__", "") != "rebuild_cuda_tensor" or len(fargs) < 8 or not isinstance(fargs[6], int):
+                        raise RuntimeError("PeerBuffers: torch.multiprocessing.reductions.reduce_tensor returned an unexpected "
+                                           f"rebuild recipe ({getattr(fn, '__name__', fn)}, {len(fargs)} arguments); this torch "
+                                           "version needs a new mapping of the owner-device argument")
                     owner_device = fargs[6]
                     # open the handle with THIS rank's device current (cudaIpcOpenMemHandle + lazy peer access maps the
                     # owner's memory for the opening device); the tensor is then "on" our device but lives in the
                     # owner's HBM and every access crosses NVLink
-                    fargs[6] = device.index
+                    fargs[6] = device.index if device.index is not None else torch.cuda.current_device()
                     check(lib.gnnfd_enable_peer_access(owner_device), "gnnfd_enable_peer_access")
                     row.append(fn(*fargs))
             self.views.append(row)
