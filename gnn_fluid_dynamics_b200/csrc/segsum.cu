@@ -9,6 +9,11 @@
 
 namespace gnnfd {
 
+// A row's sum is a chain of three dependent memory latencies (its CSR offsets -> its perm entries -> the source rows),
+// and one row per warp left the kernel latency-bound (2.5 TB/s on the [E,128] -> [2N,128] reduction of the training
+// step).  So every warp walks its rows in a grid-stride loop as a software pipeline: while the source rows of the current
+// row are in flight it loads the perm entries of its next row and the offsets of the one after.  The summation order of a
+// row is unchanged (ascending source position), so results stay bit-identical to the sequential CPU scatter_add.
 template <int LPR>  // lanes per output row: width = 4 * LPR floats
 __global__ void __launch_bounds__(256) segment_sum_kernel(
     const float *__restrict__ a, const float *__restrict__ b, int ld_a, int ld_b, int col_a, int col_b,
@@ -16,43 +21,72 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(
     int64_t n_rows, float *__restrict__ out, int ld_out) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
-  const int sub = lane % LPR;
-  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  const int64_t row = warp * RPW + lane / LPR;
-  if (row >= n_rows) return;
-  const int beg = offsets[row], end = offsets[row + 1];
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> 5;                     // warps in the grid
+  const int64_t n_groups = (n_rows + RPW - 1) / RPW;                                 // a warp handles RPW rows at a time
   const float *pa = a + col_a + sub * 4;
   const float *pb = b + col_b + sub * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = beg; p < end; p += 4) {
+  auto load_off = [&](int64_t g, int &beg, int &end) {
+    const int64_t row = g * RPW + grp;
+    beg = end = 0;
+    if (g < n_groups && row < n_rows) { beg = __ldg(offsets + row); end = __ldg(offsets + row + 1); }
+  };
+  auto load_perm = [&](int beg, int end, int (&q)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = (beg + j < end) ? __ldg(perm + beg + j) : -1;
+  };
+  int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  int bc, ec, bn, en, qc[4];
+  load_off(g, bc, ec);
+  load_off(g + stride, bn, en);
+  load_perm(bc, ec, qc);
+  for (; g < n_groups; g += stride) {
     float4 v[4];
-    float s[4];
+    float sg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                        // the current row's first four source rows
+      sg[j] = 0.f;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (qc[j] >= 0) {
+        const int64_t q = qc[j];
+        if (q < n_half) { v[j] = ldg_f4(pa + q * ld_a); sg[j] = 1.0f; }
+        else { v[j] = ldg_f4(pb + (q - n_half) * ld_b); sg[j] = sign_b; }
+      }
+    }
+    int qn[4], bnn, enn;
+    load_perm(bn, en, qn);                               // next row's entries, the row after's offsets
+    load_off(g + 2 * stride, bnn, enn);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      s[j] = 0.f;
-      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p + j < end) {
-        int64_t q = perm[p + j];
-        if (q < n_half) {
-          v[j] = ldg_f4(pa + q * ld_a);
-          s[j] = 1.0f;
-        } else {
-          v[j] = ldg_f4(pb + (q - n_half) * ld_b);
-          s[j] = sign_b;
+      if (qc[j] >= 0) {  // sequential order; +-1 scaling is exact
+        acc.x += sg[j] * v[j].x; acc.y += sg[j] * v[j].y; acc.z += sg[j] * v[j].z; acc.w += sg[j] * v[j].w;
+      }
+    }
+    for (int p = bc + 4; p < ec; p += 4) {               // rows with more than four contributions
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sg[j] = 0.f;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p + j < ec) {
+          const int64_t q = __ldg(perm + p + j);
+          if (q < n_half) { v[j] = ldg_f4(pa + q * ld_a); sg[j] = 1.0f; }
+          else { v[j] = ldg_f4(pb + (q - n_half) * ld_b); sg[j] = sign_b; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p + j < ec) {
+          acc.x += sg[j] * v[j].x; acc.y += sg[j] * v[j].y; acc.z += sg[j] * v[j].z; acc.w += sg[j] * v[j].w;
         }
       }
     }
+    const int64_t row = g * RPW + grp;
+    if (row < n_rows) *reinterpret_cast<float4 *>(out + row * (int64_t)ld_out + sub * 4) = acc;
+    bc = bn; ec = en; bn = bnn; en = enn;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (p + j < end) {  // sequential order; +-1 scaling is exact
-        acc.x += s[j] * v[j].x;
-        acc.y += s[j] * v[j].y;
-        acc.z += s[j] * v[j].z;
-        acc.w += s[j] * v[j].w;
-      }
-    }
+    for (int j = 0; j < 4; ++j) qc[j] = qn[j];
   }
-  *reinterpret_cast<float4 *>(out + row * (int64_t)ld_out + sub * 4) = acc;
 }
 
 }  // namespace gnnfd
@@ -76,8 +110,10 @@ extern "C" int gnnfd_segment_sum(const float *a, const float *b, int32_t ld_a, i
   GNNFD_CHECK_ARG(width > 0 && (width % 4) == 0 && lpr <= 32 && (32 % lpr) == 0,
                   "width must be 4*2^k <= 128");
   const int rpw = 32 / lpr;
-  int64_t warps = (n_rows + rpw - 1) / rpw;
-  int blocks = (int)((warps * 32 + 255) / 256);
+  const int64_t warps = (n_rows + rpw - 1) / rpw;
+  int64_t blocks64 = (warps * 32 + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 4;             // grid-stride: the four resident blocks per SM (58 registers) walk all rows
+  const int blocks = (int)(blocks64 < cap ? blocks64 : cap);
 #define LAUNCH(L)                                                                                   \
   segment_sum_kernel<L><<<blocks, 256, 0, stream>>>(a, b, ld_a, ld_b, col_a, col_b, sign_b, n_half, \
                                                     offsets, perm, n_rows, out, ld_out)
