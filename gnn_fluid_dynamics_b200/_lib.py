@@ -30,6 +30,7 @@ EXPORTS = [
     "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access", "gnnfd_gather_cols_add",
     "gnnfd_glue_workspace_bytes", "gnnfd_face_area_norm", "gnnfd_face_area_norm_backward", "gnnfd_fvm_integrate",
     "gnnfd_fvm_integrate_backward", "gnnfd_masked_mse", "gnnfd_masked_mse_backward", "gnnfd_state_advance",
+    "gnnfd_affine_columns",
 ]
 ABI_VERSION = 4
 
@@ -134,6 +135,7 @@ def _load():
     lib.gnnfd_masked_mse_backward.argtypes = [vp, i32, vp, i32, vp, i64, i32, vp, vp, vp, i32, vp]
     lib.gnnfd_state_advance.argtypes = [vp, i32, vp, i32, i32, i64, vp, i32, vp, vp, vp, vp, vp, i32, i64, vp, i32, vp, i32,
                                         vp, vp, vp]
+    lib.gnnfd_affine_columns.argtypes = [vp, i64, i32, i32, vp, vp, vp, i32, vp]
     for which, mirror in ((0, MlpArgs), (1, WgradArgs), (2, Segment), (3, MlpBackwardArgs)):
         if lib.gnnfd_struct_size(which) != C.sizeof(mirror):
             raise ImportError(f"{LIB_PATH}: struct {mirror.__name__} is {lib.gnnfd_struct_size(which)} bytes in the "

@@ -391,6 +391,33 @@ extern "C" int gnnfd_masked_mse_backward(const float *a, int32_t ld_a, const flo
   return GNNFD_OK;
 }
 
+// t[r, cols[k]] = (t[r, cols[k]] - shift[k]) / scale[k]   (inverse: t * scale + shift; two roundings each, like the
+// tensor expressions they replace)
+__global__ void __launch_bounds__(GL_THREADS) affine_columns_kernel(float *__restrict__ t, int64_t rows, int ld, int n_spec,
+                                                                  const int32_t *__restrict__ cols,
+                                                                  const float *__restrict__ shift,
+                                                                  const float *__restrict__ scale, int inverse) {
+  const int64_t total = rows * n_spec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n_spec;
+    const int k = (int)(i - r * n_spec);
+    float *p = t + r * ld + __ldg(cols + k);
+    const float a = __ldg(shift + k), b = __ldg(scale + k), x = *p;
+    *p = inverse ? __fadd_rn(__fmul_rn(x, b), a) : __fdiv_rn(__fsub_rn(x, a), b);
+  }
+}
+
+extern "C" int gnnfd_affine_columns(float *t, int64_t rows, int32_t ld, int32_t n_spec, const int32_t *cols,
+                                    const float *shift, const float *scale, int32_t inverse, void *stream) {
+  GNNFD_CHECK_ARG(rows >= 0 && n_spec >= 0 && ld >= 1, "bad sizes");
+  if (rows == 0 || n_spec == 0) return GNNFD_OK;
+  GNNFD_CHECK_ARG(t && cols && shift && scale, "null pointer");
+  affine_columns_kernel<<<gl_blocks(rows * n_spec), GL_THREADS, 0, (cudaStream_t)stream>>>(t, rows, ld, n_spec, cols, shift,
+                                                                                          scale, inverse);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}
+
 extern "C" int gnnfd_state_advance(float *x_raw, int32_t ld_x, const float *delta, int32_t ld_d, int32_t has_change,
                                    int64_t n_cells, float *x_norm, int32_t ld_xn, const float *cell_mean_std4,
                                    const int32_t *row, const int32_t *col, const uint8_t *bc_mask, const float *bc_value,

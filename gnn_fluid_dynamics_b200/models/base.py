@@ -81,21 +81,95 @@ class Normalizer(nn.Module):
             return data * rng + g("min") if inverse else (data - g("min")) / rng
         raise ValueError(kind)
 
+    # --- fused path: one kernel per tensor instead of ~4 tensor kernels per normalised column --------------------
+    def _shift_scale(self, key):
+        """(shift, scale) 0-dim tensors of a stats key: forward = (x - shift) / scale, inverse = x * scale + shift."""
+        kind = self.kinds[key]
+        g = lambda s: getattr(self, f"{key}_{s}")
+        if kind == "z_score":
+            return g("mean"), torch.clamp(g("std"), min=1e-8) + 1e-8
+        if kind in ("mean_scale", "std_scale", "max_scale"):
+            scale = g({"mean_scale": "mean", "std_scale": "std", "max_scale": "max"}[kind]) + 1e-8
+            return torch.zeros_like(scale), scale
+        if kind == "min_max":
+            return g("min"), g("max") - g("min") + 1e-8
+        raise ValueError(kind)
+
+    def _spec(self, rows, width):
+        """Device arrays (columns, shift, scale) of the table rows that apply to a tensor of ``width`` columns, cached until
+        a statistics buffer is replaced or modified.  None: overlapping columns (the sequential tensor path handles them)."""
+        bufs = tuple(self.buffers())
+        key = (tuple(rows), width, tuple((b.data_ptr(), b._version) for b in bufs))
+        cache = self.__dict__.setdefault("_spec_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            cols, shift, scale = [], [], []
+            for c, k in rows:
+                if width < c.stop:
+                    continue
+                a, b = self._shift_scale(k)
+                for j in range(c.start, c.stop):
+                    cols.append(j); shift.append(a); scale.append(b)
+            if len(set(cols)) != len(cols):
+                hit = (None,)
+            elif not cols:
+                hit = ((None, None, None, 0),)
+            else:
+                dev = shift[0].device
+                hit = ((torch.tensor(cols, dtype=torch.int32, device=dev), torch.stack(shift).float().contiguous(),
+                        torch.stack(scale).float().contiguous(), len(cols)),)
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = hit
+        return hit[0]
+
+    def _apply_fused(self, t, rows, inverse) -> bool:
+        """True if the tensor was (de)normalised by ``gnnfd_affine_columns`` (CUDA fp32 [R, C] with contiguous columns)."""
+        if not (torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] >= 1
+                and (t.stride(1) == 1 or t.shape[1] == 1) and not (torch.is_grad_enabled() and t.requires_grad)):
+            return False
+        spec = self._spec(rows, t.shape[1])
+        if spec is None or spec[0] is not None and spec[0].device != t.device:
+            return False
+        cols, shift, scale, n = spec
+        if n and t.shape[0]:
+            from .. import ops
+            from .._lib import check, lib
+            check(lib.gnnfd_affine_columns(t.data_ptr(), t.shape[0], t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]),
+                                           n, cols.data_ptr(), shift.data_ptr(), scale.data_ptr(), int(inverse), ops._stream()),
+                  "gnnfd_affine_columns")
+            ops._count(1)
+        return True
+
     def input(self, graphs, inverse=False):
         """In place on the passed graphs, like the reference (normalisation.py:255-264)."""
+        groups = {}
         for gi, attr, cols, key in self.inputs:
+            groups.setdefault((gi, attr), []).append((cols, key))
+        for (gi, attr), rows in groups.items():
             t = getattr(graphs[gi], attr, None)
-            if t is None or t.dim() < 2 or t.shape[-1] < cols.stop:
+            if t is None or t.dim() < 2:
                 continue
-            t[..., cols] = self._apply_one(t[..., cols], key, inverse)      # last dim: [R, C] or bundled [R, k, C]
+            if self._apply_fused(t, rows, inverse):
+                continue
+            for cols, key in rows:
+                if t.shape[-1] >= cols.stop:
+                    t[..., cols] = self._apply_one(t[..., cols], key, inverse)      # last dim: [R, C] or bundled [R, k, C]
         return graphs
 
     def output(self, outputs, inverse=False):
+        groups = {}
         for oi, cols, key in self.outputs:
+            groups.setdefault(oi, []).append((cols, key))
+        for oi, rows in groups.items():
             t = outputs[oi]
-            if t is None or t.shape[-1] < cols.stop:
+            if t is None:
                 continue
-            t[..., cols] = self._apply_one(t[..., cols], key, inverse)
+            if self._apply_fused(t, rows, inverse):
+                continue
+            for cols, key in rows:
+                if t.shape[-1] >= cols.stop:
+                    t[..., cols] = self._apply_one(t[..., cols], key, inverse)
         return outputs
 
 

@@ -356,6 +356,15 @@ int gnnfd_masked_mse(const float *a, int32_t ld_a, const float *b, int32_t ld_b,
 int gnnfd_masked_mse_backward(const float *a, int32_t ld_a, const float *b, int32_t ld_b, const uint8_t *mask, int64_t rows,
                               int32_t cols, const float *fwd_out2, const float *g, float *d_a, int32_t ld_d, void *stream);
 
+/* In-place per-column affine (de)normalisation of a [rows, ld] matrix (ABI v4):
+ *   forward:  t[r, cols[k]] = (t[r, cols[k]] - shift[k]) / scale[k]        inverse:  t * scale[k] + shift[k]
+ * for k < n_spec; cols / shift / scale are DEVICE arrays (no host read of the statistics).  Replaces the per-column
+ * tensor expressions of Normalizer.input / output (src/utils/normalisation.py:255-322: z_score, mean / std / max scale,
+ * min_max all have this form) - ~4 tiny kernels per normalised column - with one launch per tensor, bit-identical
+ * (separately rounded subtract / divide, multiply / add). */
+int gnnfd_affine_columns(float *t, int64_t rows, int32_t ld, int32_t n_spec, const int32_t *cols, const float *shift,
+                         const float *scale, int32_t inverse, void *stream);
+
 /* Rollout state advance: src/rollout.py:336-340 (velocity update), update_features src/models/Fvgn.py:133-148 /
  * src/models/Mgn.py:139-151 and the next step's input z-scoring src/utils/normalisation.py:255-278, in two kernels.
  *   vel = has_change ? x_raw[:, 0:2] + delta : delta;  x_raw[:, 0:2] = vel;  x_norm[:, 0:2] = (vel - mean) / scale

@@ -120,3 +120,26 @@ def test_state_advance_matches_update_features():
     assert torch.equal(x_raw[:, :2], vel) and torch.equal(vout, vel) and torch.equal(f_raw[:, :2], dv)
     assert torch.equal(f_raw[:, 2:], f.x[:, 2:])
     assert rel_l2(x_norm[:, 0], (vel[:, 0] - cs[0]) / cs[1]) < 1e-6 and rel_l2(f_norm[:, 1], (dv[:, 1] - fs[2]) / fs[3]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["FvgnA", "ConservativeA", "MgnC"])
+def test_fused_normaliser_is_bit_identical_to_the_tensor_expressions(name):
+    """Normalizer.input / output through gnnfd_affine_columns (one launch per tensor) == the per-column tensor expressions
+    of normalisation.py:255-322, bit for bit, forward and inverse (z_score, mean_scale kinds; CPU path = the expressions)."""
+    from helpers import build_model, golden_graphs
+    model = build_model(name)
+    _, graphs = golden_graphs(name, n_cells=500)
+    ref = model.normalizer.input([g.clone() for g in graphs])                    # CPU: tensor expressions
+    model.to(dev())
+    got = model.normalizer.input([g.clone().to(dev()) for g in graphs])          # CUDA: fused kernel
+    for a, b in zip(ref, got):
+        for k in a.keys():
+            if torch.is_tensor(a[k]) and a[k].is_floating_point():
+                assert torch.equal(a[k], b[k].cpu()), k
+    outs = [torch.randn(500, 5), torch.randn(700, 5), None]
+    ref_o = model.cpu().normalizer.output([None if t is None else t.clone() for t in outs], inverse=True)
+    model.to(dev())
+    got_o = model.normalizer.output([None if t is None else t.clone().to(dev()) for t in outs], inverse=True)
+    for a, b in zip(ref_o, got_o):
+        if a is not None:
+            assert torch.equal(a, b.cpu())
