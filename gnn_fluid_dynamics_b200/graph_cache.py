@@ -140,8 +140,13 @@ class GraphCache:
             raise ValueError("one mesh key per sample")
         self.h2d_static_bytes = 0
         b = self._batch(keys, host_samples)
+        token = tuple(id(g) for s in host_samples for g in s)
+        if b.pending is not None and b.pending[3] != token:
+            # a prefetch of OTHER samples is in flight for this batch composition: let it land, then upload these
+            torch.cuda.current_stream(self.device).wait_event(b.pending[1])
+            b.pending = None
         if b.pending is not None:                  # uploaded ahead of time by prefetch(): just order this stream after it
-            slot, event, moved = b.pending
+            slot, event, moved, _ = b.pending
             b.pending = None
             torch.cuda.current_stream(self.device).wait_event(event)
         else:
@@ -184,7 +189,7 @@ class GraphCache:
             moved = self._upload(b, slot, host_samples)
             done = torch.cuda.Event()
             done.record(self._copy_stream)
-        b.pending = (slot, done, moved)
+        b.pending = (slot, done, moved, tuple(id(g) for s in host_samples for g in s))
 
     def _upload(self, b: _Batch, slot: int, host_samples) -> int:
         """Per-sample attributes of every sample -> their row ranges of buffer set ``slot`` (on the current stream)."""
