@@ -726,17 +726,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 m = lds_f4(stg + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4);
-              v[4 * i] *= silu ? dsilu(m.x) : dtanh(m.x);
-              v[4 * i + 1] *= silu ? dsilu(m.y) : dtanh(m.y);
-              v[4 * i + 2] *= silu ? dsilu(m.z) : dtanh(m.z);
-              v[4 * i + 3] *= silu ? dsilu(m.w) : dtanh(m.w);
+              float d0, d1, d2, d3;
+              if (silu) { dsilu2(m.x, m.y, d0, d1); dsilu2(m.z, m.w, d2, d3); }
+              else { d0 = dtanh(m.x); d1 = dtanh(m.y); d2 = dtanh(m.z); d3 = dtanh(m.w); }
+              mul2(v[4 * i], v[4 * i + 1], d0, d1);
+              mul2(v[4 * i + 2], v[4 * i + 3], d2, d3);
             }
           } else {
             tmem_ld16(reg + c * 16, v);
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 b4 = lds_f4(bias + (c * 16 + i) * 4);
-              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              add2(v[i], v[i + 1], b4.x, b4.y);
+              add2(v[i + 2], v[i + 3], b4.z, b4.w);
             }
           }
           if (save_tma) {
@@ -798,12 +800,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             if (c == 0) shift = acc[0] + lds_f4(b3).x;
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-              const float4 b4 = lds_f4(b3 + i * 4);
-              const float d0 = acc[i] + (b4.x - shift), d1 = acc[i + 1] + (b4.y - shift);
-              const float d2 = acc[i + 2] + (b4.z - shift), d3 = acc[i + 3] + (b4.w - shift);
-              s4[0] += d0; s4[1] += d1; s4[2] += d2; s4[3] += d3;
-              q4s[0] = fmaf(d0, d0, q4s[0]); q4s[1] = fmaf(d1, d1, q4s[1]);
-              q4s[2] = fmaf(d2, d2, q4s[2]); q4s[3] = fmaf(d3, d3, q4s[3]);
+              float4 b4 = lds_f4(b3 + i * 4);
+              sub2(b4.x, b4.y, shift, shift); sub2(b4.z, b4.w, shift, shift);
+              float d0 = acc[i], d1 = acc[i + 1], d2 = acc[i + 2], d3 = acc[i + 3];
+              add2(d0, d1, b4.x, b4.y); add2(d2, d3, b4.z, b4.w);
+              add2(s4[0], s4[1], d0, d1); add2(s4[2], s4[3], d2, d3);
+              float t0 = d0, t1 = d1, t2 = d2, t3 = d3;
+              fma2(t0, t1, d0, d1, q4s[0], q4s[1]); fma2(t2, t3, d2, d3, q4s[2], q4s[3]);
+              q4s[0] = t0; q4s[1] = t1; q4s[2] = t2; q4s[3] = t3;
             }
           }
           const float sh = (s4[0] + s4[1]) + (s4[2] + s4[3]), qh = (q4s[0] + q4s[1]) + (q4s[2] + q4s[3]);
@@ -840,15 +844,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 b4 = lds_f4(b3 + i * 16), w4 = lds_f4(lw + i * 16), g4 = lds_f4(lb + i * 16);
-            o[4 * i] = fmaf(fmaf(acc[4 * i] + b4.x, rstd, nmr), w4.x, g4.x);
-            o[4 * i + 1] = fmaf(fmaf(acc[4 * i + 1] + b4.y, rstd, nmr), w4.y, g4.y);
-            o[4 * i + 2] = fmaf(fmaf(acc[4 * i + 2] + b4.z, rstd, nmr), w4.z, g4.z);
-            o[4 * i + 3] = fmaf(fmaf(acc[4 * i + 3] + b4.w, rstd, nmr), w4.w, g4.w);
+            float x0 = acc[4 * i], x1 = acc[4 * i + 1], x2 = acc[4 * i + 2], x3 = acc[4 * i + 3];
+            add2(x0, x1, b4.x, b4.y); add2(x2, x3, b4.z, b4.w);
+            fma2(x0, x1, rstd, rstd, nmr, nmr); fma2(x2, x3, rstd, rstd, nmr, nmr);
+            fma2(x0, x1, w4.x, w4.y, g4.x, g4.y); fma2(x2, x3, w4.z, w4.w, g4.z, g4.w);
+            o[4 * i] = x0; o[4 * i + 1] = x1; o[4 * i + 2] = x2; o[4 * i + 3] = x3;
           }
           if (epi & EPI_LDRES) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              o[4 * i] += res[i].x; o[4 * i + 1] += res[i].y; o[4 * i + 2] += res[i].z; o[4 * i + 3] += res[i].w;
+              add2(o[4 * i], o[4 * i + 1], res[i].x, res[i].y);
+              add2(o[4 * i + 2], o[4 * i + 3], res[i].z, res[i].w);
             }
           }
           const bool both = (epi & EPI_SPLIT) && p.split_tma && (epi & (EPI_ST_RAW | EPI_RED_SUM | EPI_LDRES));
@@ -928,11 +934,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 b4 = lds_f4(b3 + i * 4);
-              const float d0 = acc[i] + b4.x - shift, d1 = acc[i + 1] + b4.y - shift;
-              const float d2 = acc[i + 2] + b4.z - shift, d3 = acc[i + 3] + b4.w - shift;
-              s4[0] += d0; s4[1] += d1; s4[2] += d2; s4[3] += d3;
-              q4s[0] = fmaf(d0, d0, q4s[0]); q4s[1] = fmaf(d1, d1, q4s[1]);
-              q4s[2] = fmaf(d2, d2, q4s[2]); q4s[3] = fmaf(d3, d3, q4s[3]);
+              float d0 = acc[i], d1 = acc[i + 1], d2 = acc[i + 2], d3 = acc[i + 3];
+              add2(d0, d1, b4.x, b4.y); add2(d2, d3, b4.z, b4.w);
+              sub2(d0, d1, shift, shift); sub2(d2, d3, shift, shift);
+              add2(s4[0], s4[1], d0, d1); add2(s4[2], s4[3], d2, d3);
+              float t0 = d0, t1 = d1, t2 = d2, t3 = d3;
+              fma2(t0, t1, d0, d1, q4s[0], q4s[1]); fma2(t2, t3, d2, d3, q4s[2], q4s[3]);
+              q4s[0] = t0; q4s[1] = t1; q4s[2] = t2; q4s[3] = t3;
             }
           }
           const float sh = (s4[0] + s4[1]) + (s4[2] + s4[3]), qh = (q4s[0] + q4s[1]) + (q4s[2] + q4s[3]);
@@ -975,11 +983,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 b4 = lds_f4(b3 + i * 16);
-            float4 o;
-            o.x = (acc[4 * i] + b4.x - mean) * rstd;
-            o.y = (acc[4 * i + 1] + b4.y - mean) * rstd;
-            o.z = (acc[4 * i + 2] + b4.z - mean) * rstd;
-            o.w = (acc[4 * i + 3] + b4.w - mean) * rstd;
+            float4 o = make_float4(acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);
+            add2(o.x, o.y, b4.x, b4.y); add2(o.z, o.w, b4.z, b4.w);
+            sub2(o.x, o.y, mean, mean); sub2(o.z, o.w, mean, mean);
+            mul2(o.x, o.y, rstd, rstd); mul2(o.z, o.w, rstd, rstd);
             sts_f4(stg + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4, o);
           }
           __syncwarp();
@@ -996,8 +1003,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               float4 o = lds_f4(stg + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4);
               const size_t off = (size_t)g * TC_H + col0 + c4 * 4;
               if (a.save_xhat) *reinterpret_cast<float4 *>(a.save_xhat + off) = o;
-              o.x = fmaf(o.x, w4.x, g4.x); o.y = fmaf(o.y, w4.y, g4.y);
-              o.z = fmaf(o.z, w4.z, g4.z); o.w = fmaf(o.w, w4.w, g4.w);
+              fma2(o.x, o.y, w4.x, w4.y, g4.x, g4.y);
+              fma2(o.z, o.w, w4.z, w4.w, g4.z, g4.w);
               if (a.mul) {
                 float4 m = ldg_f4(a.mul + off);
                 if (a.mul_mode == 1) { m.x = dsilu(m.x); m.y = dsilu(m.y); m.z = dsilu(m.z); m.w = dsilu(m.w); }
@@ -1007,7 +1014,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + off) = o;
               if (a.out_sum) {
                 float4 r4 = res[jr];
-                r4.x += o.x; r4.y += o.y; r4.z += o.z; r4.w += o.w;
+                add2(r4.x, r4.y, o.x, o.y); add2(r4.z, r4.w, o.z, o.w);
                 *reinterpret_cast<float4 *>(a.out_sum + off) = r4;
               }
             }

@@ -184,19 +184,44 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 f16, 1 bf16*/, int
          ((uint32_t)(TC_BM >> 4) << 24);
 }
 
+// ------------------------------------------------------------------------------ packed fp32 pairs
+// sm_100 has two-wide fp32 arithmetic on register pairs (SASS FADD2 / FMUL2 / FFMA2).  Measured on B200
+// (profiles/r02_ffma2_issue_rate.log): the same FP32 lanes per clock as the scalar forms but HALF the issue slots - and
+// the epilogue warps of the MLP kernel are bound by their dependent instruction stream, not by the FP32 pipe.  Each
+// operation is separately rounded (rn), so results are bit-identical to the scalar expressions.
+__device__ __forceinline__ void add2(float &a, float &b, float c, float d) {      // (a, b) += (c, d)
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tadd.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a), "+f"(b) : "f"(c), "f"(d));
+}
+__device__ __forceinline__ void sub2(float &a, float &b, float c, float d) {      // (a, b) -= (c, d)
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tsub.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a), "+f"(b) : "f"(c), "f"(d));
+}
+__device__ __forceinline__ void mul2(float &a, float &b, float c, float d) {      // (a, b) *= (c, d)
+  asm("{\n\t.reg .b64 x, y;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tmul.rn.f32x2 x, x, y;\n\tmov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a), "+f"(b) : "f"(c), "f"(d));
+}
+__device__ __forceinline__ void fma2(float &a, float &b, float c, float d, float e, float f) {   // (a, b) = (a, b) * (c, d) + (e, f)
+  asm("{\n\t.reg .b64 x, y, z;\n\tmov.b64 x, {%0, %1};\n\tmov.b64 y, {%2, %3};\n\tmov.b64 z, {%4, %5};\n\t"
+      "fma.rn.f32x2 x, x, y, z;\n\tmov.b64 {%0, %1}, x;\n\t}"
+      : "+f"(a), "+f"(b) : "f"(c), "f"(d), "f"(e), "f"(f));
+}
+
 // -------------------------------------------------------------------------- operand conversion
 template <bool FP16>
 __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
   if constexpr (FP16) {
     __half2 h = __floats2half2_rn(a, b);
     float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    sub2(a, b, hf.x, hf.y);
+    __half2 l = __floats2half2_rn(a, b);
     hi = *reinterpret_cast<uint32_t *>(&h);
     lo = *reinterpret_cast<uint32_t *>(&l);
   } else {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     float2 hf = __bfloat1622float2(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    sub2(a, b, hf.x, hf.y);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a, b);
     hi = *reinterpret_cast<uint32_t *>(&h);
     lo = *reinterpret_cast<uint32_t *>(&l);
   }
@@ -246,6 +271,19 @@ __device__ __forceinline__ float dsilu(float x) {
   const float sg = rcp_ftz(1.0f + ex2_ftz(x * -1.4426950408889634f));   // same fast sigmoid as the forward's SiLU
   return sg * fmaf(x, 1.0f - sg, 1.0f);
 }
+// two derivatives at once (same operations, pairwise)
+__device__ __forceinline__ void dsilu2(float x0, float x1, float &d0, float &d1) {
+  float e0 = x0, e1 = x1;
+  mul2(e0, e1, -1.4426950408889634f, -1.4426950408889634f);
+  e0 = ex2_ftz(e0); e1 = ex2_ftz(e1);
+  add2(e0, e1, 1.0f, 1.0f);
+  const float s0 = rcp_ftz(e0), s1 = rcp_ftz(e1);       // sigmoid
+  float t0 = 1.0f, t1 = 1.0f;
+  sub2(t0, t1, s0, s1);                                   // 1 - sg
+  fma2(t0, t1, x0, x1, 1.0f, 1.0f);                       // x (1 - sg) + 1
+  mul2(t0, t1, s0, s1);
+  d0 = t0; d1 = t1;
+}
 __device__ __forceinline__ float dtanh(float x) {
   const float t = tanhf(x);
   return 1.0f - t * t;
@@ -256,11 +294,18 @@ __device__ __forceinline__ void act16(float (&v)[16]) {
   if constexpr (ACT == GNNFD_ACT_SILU) {
     float e[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) e[i] = ex2_ftz(v[i] * -1.4426950408889634f);
+    for (int i = 0; i < 16; i += 2) {
+      e[i] = v[i]; e[i + 1] = v[i + 1];
+      mul2(e[i], e[i + 1], -1.4426950408889634f, -1.4426950408889634f);
+      e[i] = ex2_ftz(e[i]); e[i + 1] = ex2_ftz(e[i + 1]);
+    }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) e[i] = rcp_ftz(1.0f + e[i]);
+    for (int i = 0; i < 16; i += 2) {
+      add2(e[i], e[i + 1], 1.0f, 1.0f);
+      e[i] = rcp_ftz(e[i]); e[i + 1] = rcp_ftz(e[i + 1]);
+    }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] *= e[i];
+    for (int i = 0; i < 16; i += 2) mul2(v[i], v[i + 1], e[i], e[i + 1]);
   } else {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = tanhf(v[i]);

@@ -97,6 +97,14 @@ __device__ __forceinline__ float to_tf32(float x) {   // round to nearest (the t
   return __uint_as_float(u);
 }
 __device__ __forceinline__ float wg_silu(float v) { return v * rcp_ftz(1.0f + ex2_ftz(v * -1.4426950408889634f)); }
+// the same on a pair, with the packed two-wide fp32 operations (half the issue slots; tc_common.cuh)
+__device__ __forceinline__ void wg_silu2(float &a, float &b) {
+  float e0 = a, e1 = b;
+  mul2(e0, e1, -1.4426950408889634f, -1.4426950408889634f);
+  e0 = ex2_ftz(e0); e1 = ex2_ftz(e1);
+  add2(e0, e1, 1.0f, 1.0f);
+  mul2(a, b, rcp_ftz(e0), rcp_ftz(e1));
+}
 
 // one (row, piece) item: the lane's float4 of the assembled operand row (zero outside the matrix / the width)
 __device__ __forceinline__ float4 wg_load_item(const WgPiece &pc, int lane, bool row_ok, int64_t g, int32_t i0,
@@ -457,7 +465,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_lean_kernel(const __grid_
           sts_u2(sA + j * JSTEP, h0, h1);
           sts_u2(sA + j * JSTEP + PART, l0, l1);
           float4 t = b[j];
-          if (act == 1) { t.x = wg_silu(t.x); t.y = wg_silu(t.y); t.z = wg_silu(t.z); t.w = wg_silu(t.w); }
+          if (act == 1) { wg_silu2(t.x, t.y); wg_silu2(t.z, t.w); }
           else if (act == 2) { t.x = tanhf(t.x); t.y = tanhf(t.y); t.z = tanhf(t.z); t.w = tanhf(t.w); }
           split2<false>(t.x, t.y, h0, l0); split2<false>(t.z, t.w, h1, l1);
           sts_u2(sB + j * JSTEP, h0, h1);
