@@ -693,12 +693,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         // thread = row through the warp's staging block: a thread-per-row load touches 32 cache lines per instruction
         // and the LSU, not HBM, then paces the epilogue.  Rows past the end read a clamped row; never stored.
         const float *hm = nullptr;
-        float4 m4[4];
+        // 16-column group cg of this layer's saved pre-activations -> the warp's second staging block, as asynchronous
+        // 16-byte copies (no registers in flight: with register prefetch the compiler spilled the loaded values, and a
+        // spill store waits for its load - the whole DRAM latency sat right behind the prefetch)
+        auto hm_copy = [&](int cg) {
+#pragma unroll
+          for (int jr = 0; jr < 4; ++jr) {
+            const int rl = jr * 8 + rr;
+            cp_async16(stg2 + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4,
+                       hm + cg * 16 + (size_t)min(row0 + q4 * 32 + rl, a.rows - 1) * TC_H);
+          }
+          cp_async_commit();
+        };
         if (BWD) {
           hm = (layer == 0 ? a.hid_mul1 : a.hid_mul2) + eh * 64 + c4 * 4;
-#pragma unroll
-          for (int jr = 0; jr < 4; ++jr)
-            m4[jr] = ldg_f4(hm + (size_t)min(row0 + q4 * 32 + jr * 8 + rr, a.rows - 1) * TC_H);
+          hm_copy(0);
         }
         PROF_WAIT(0, group_wait(&acc_full[xs], (3 * n + layer) & 1));
         tc_fence_after();
@@ -706,26 +715,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         for (int c = 0; c < 4; ++c) {
           float v[16];
           if (BWD) {
-            // transpose the prefetched group through the staging block (the previous group's TMA store must have
-            // finished reading it), then prefetch the next group
-            if (lane == 0) bulk_wait_read0();
+            // this group's copies have landed (every lane waits for its own, then the warp meets): read the thread's own
+            // row, and start the next group's copies into the same block once every lane has read
+            cp_async_wait_all();
             __syncwarp();
+            float4 mm[4];
 #pragma unroll
-            for (int jr = 0; jr < 4; ++jr) {
-              const int rl = jr * 8 + rr;
-              sts_f4(stg + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4, m4[jr]);
-            }
+            for (int i = 0; i < 4; ++i) mm[i] = lds_f4(stg2 + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4);
             __syncwarp();
-            if (c < 3) {
-#pragma unroll
-              for (int jr = 0; jr < 4; ++jr)
-                m4[jr] = ldg_f4(hm + (c + 1) * 16 + (size_t)min(row0 + q4 * 32 + jr * 8 + rr, a.rows - 1) * TC_H);
-            }
+            if (c < 3) hm_copy(c + 1);
             tmem_ld16(reg + c * 16, v);
             const bool silu = a.act == GNNFD_ACT_SILU;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float4 m = lds_f4(stg + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4);
+              const float4 m = mm[i];
               float d0, d1, d2, d3;
               if (silu) { dsilu2(m.x, m.y, d0, d1); dsilu2(m.z, m.w, d2, d3); }
               else { d0 = dtanh(m.x); d1 = dtanh(m.y); d2 = dtanh(m.z); d3 = dtanh(m.w); }
@@ -744,10 +747,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           if (save_tma) {
             // training stash (pre-activation / dA) of this 32 x 16 block: staged in the warp's SWIZZLE_64B block and
             // written by ONE TMA tensor store (rows past the end of the matrix are clipped by the tensor map)
-            if (!BWD) {
-              if (lane == 0) bulk_wait_read0();
-              __syncwarp();
-            }
+            if (lane == 0) bulk_wait_read0();      // the previous group's TMA store has finished reading the block
+            __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               sts_f4(stg + (lane * 16 + ((i ^ ((lane >> 1) & 3)) << 2)) * 4,
@@ -1322,7 +1323,8 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   if (a->rows == 0) return GNNFD_OK;
   const int64_t n_tiles = (a->rows + TC_BM - 1) / TC_BM;
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  p.w_slots = (n_tiles <= 2 * (int64_t)num_sms() && !p.split_tma) ? TC_W_SLOTS_MAX : 2;
+  if (a->bwd_chain) extra_smem = TC_STG_BYTES;      // second staging block: asynchronous copies of the saved pre-activations
+  p.w_slots = (n_tiles <= 2 * (int64_t)num_sms() && extra_smem == 0) ? TC_W_SLOTS_MAX : 2;
 #define LAUNCH1(FP, NA_, NW_, BW, EP)                                                                     \
   do {                                                                                                    \
     static bool attr[GNNFD_MAX_DEVICES] = {false};                                                        \

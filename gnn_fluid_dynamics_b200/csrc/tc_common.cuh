@@ -55,6 +55,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
