@@ -1013,10 +1013,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
               }
               if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + off) = o;
+              float4 r4 = o;
               if (a.out_sum) {
-                float4 r4 = res[jr];
+                r4 = res[jr];
                 add2(r4.x, r4.y, o.x, o.y); add2(r4.z, r4.w, o.z, o.w);
                 *reinterpret_cast<float4 *>(a.out_sum + off) = r4;
+              }
+              if (a.out_split != nullptr) {
+                // training: the 16-bit hi | lo shadow of the raw output (or of the sum) for the next block's TMA gathers
+                // (8 rows x 32 B per warp instruction and part)
+                const float4 t = a.split_of_sum ? r4 : o;
+                float t0 = t.x, t1 = t.y, t2 = t.z, t3 = t.w;
+                uint32_t h0, l0, h1, l1;
+                split2<FP16>(t0, t1, h0, l0);
+                split2<FP16>(t2, t3, h1, l1);
+                uint16_t *sp = (uint16_t *)a.out_split + (size_t)g * (2 * TC_H) + col0 + c4 * 4;
+                *reinterpret_cast<uint2 *>(sp) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2 *>(sp + TC_H) = make_uint2(l0, l1);
               }
             }
           }
@@ -1273,8 +1286,10 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
                     (a->out_sum == nullptr || a->residual != nullptr) &&
                     ((reinterpret_cast<uintptr_t>(a->out_raw) | reinterpret_cast<uintptr_t>(a->out_sum) |
                       reinterpret_cast<uintptr_t>(a->out_split) | reinterpret_cast<uintptr_t>(a->residual)) & 15) == 0;
-  if (a->out_split != nullptr && !fast) {
-    set_error("mlp_forward_tc: out_split needs the inference epilogue (n_out = 128, split precision, no stash / mul)");
+  if (a->out_split != nullptr && !fast &&
+      !(p.nl == 3 && a->n_out == TC_H && m.na == 2 && !a->bwd_chain && (reinterpret_cast<uintptr_t>(a->out_split) & 15) == 0 &&
+        (!a->split_of_sum || a->out_sum != nullptr))) {
+    set_error("mlp_forward_tc: out_split needs n_out = 128 and a split precision");
     return GNNFD_E_UNSUPPORTED;
   }
   if (fast && a->rows > 0) {
