@@ -30,7 +30,7 @@ EXPORTS = [
     "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access", "gnnfd_gather_cols_add",
     "gnnfd_glue_workspace_bytes", "gnnfd_face_area_norm", "gnnfd_face_area_norm_backward", "gnnfd_fvm_integrate",
     "gnnfd_fvm_integrate_backward", "gnnfd_masked_mse", "gnnfd_masked_mse_backward", "gnnfd_state_advance",
-    "gnnfd_affine_columns",
+    "gnnfd_affine_columns", "gnnfd_set_launch_overlap",
 ]
 ABI_VERSION = 4
 
@@ -93,6 +93,7 @@ def _load():
         raise ImportError(f"{LIB_PATH} does not export {missing}")
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     lib.gnnfd_abi_version.restype = C.c_int
+    lib.gnnfd_set_launch_overlap.argtypes = [C.c_int32]
     lib.gnnfd_last_error.restype = C.c_char_p
     lib.gnnfd_index_narrow.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.gnnfd_csr_workspace_bytes.argtypes = [i64, i64]
@@ -146,6 +147,26 @@ def _load():
 
 
 lib = _load()
+
+
+_launch_overlap = None
+# inference on meshes up to this many faces is launch-latency bound: overlap the launches (see include/gnnfd_b200.h)
+LAUNCH_OVERLAP_MAX_FACES = 32768
+
+
+def set_launch_overlap(on: bool) -> None:
+    """Launch policy of the library's kernels (gnnfd_set_launch_overlap); cached, so calling it per forward is free."""
+    global _launch_overlap
+    on = bool(on)
+    if on != _launch_overlap:
+        lib.gnnfd_set_launch_overlap(int(on))
+        _launch_overlap = on
+
+
+def choose_launch_overlap(n_faces: int, training: bool) -> None:
+    """Training steps (hundreds of short dependent launches per step) and launch-bound small meshes overlap their
+    launches; large-mesh inference steps measured 1-2 % slower with it and keep plain stream order."""
+    set_launch_overlap(training or n_faces <= LAUNCH_OVERLAP_MAX_FACES)
 
 
 def check(rc: int, what: str) -> None:

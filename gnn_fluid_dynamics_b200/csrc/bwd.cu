@@ -15,6 +15,7 @@ constexpr int LNB_THREADS = 256, LNB_WARPS = LNB_THREADS / 32;
 __global__ void __launch_bounds__(LNB_THREADS) ln_backward_kernel(
     const float *__restrict__ g, const float *__restrict__ xhat, const float *__restrict__ rstd,
     const float *__restrict__ ln_w, int64_t rows, float *__restrict__ dy, float *__restrict__ partial) {
+  pdl_entry();
   __shared__ float s_part[LNB_WARPS][3][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 w4 = ln_w ? ldg_f4(ln_w + lane * 4) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(LNB_THREADS) ln_backward_kernel(
 // out[i] = sum over parts of partial[c][i]: one warp per output, lanes stride over the parts, fixed shuffle tree
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float *__restrict__ partial, int n_parts, int width,
                                                            float *__restrict__ out) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= width) return;
@@ -91,9 +93,9 @@ int ln_backward_launch(const float *g, const float *xhat, const float *rstd, con
                        float *dy, float *sums, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int grid = lnb_grid(rows);
   if (workspace == nullptr || workspace_bytes < (size_t)grid * 384 * 4) { set_error("ln_backward: workspace too small"); return GNNFD_E_WORKSPACE; }
-  ln_backward_kernel<<<grid, LNB_THREADS, 0, stream>>>(g, xhat, rstd, ln_w, rows, dy, (float *)workspace);
+  launch_pdl(ln_backward_kernel, dim3(grid), dim3(LNB_THREADS), 0, stream, g, xhat, rstd, ln_w, rows, dy, (float *)workspace);
   GNNFD_LAUNCH_CHECK();
-  sum_partials_kernel<<<(384 * 32 + 255) / 256, 256, 0, stream>>>((const float *)workspace, grid, 384, sums);
+  launch_pdl(sum_partials_kernel, dim3((384 * 32 + 255) / 256), dim3(256), 0, stream, (const float *)workspace, grid, 384, sums);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(256) segment_sum3_kernel(
     int col_b, int col_c, float sign_b, int64_t n_part, const int32_t *__restrict__ offsets,
     const int32_t *__restrict__ perm, int64_t n_rows, float scale, const float *__restrict__ base, int ld_base,
     float *__restrict__ out, int ld_out) {
+  pdl_entry();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
@@ -148,6 +151,7 @@ template <bool HALVES>
 __global__ void __launch_bounds__(256) gather_pair_add_kernel(float *dst, const float *base, const float *__restrict__ src,
                                                               int ld_src, const int32_t *__restrict__ i0,
                                                               const int32_t *__restrict__ i1, float sign, int64_t rows) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (k >= rows) return;
@@ -171,6 +175,7 @@ __global__ void __launch_bounds__(256) gather_pair_add_kernel(float *dst, const 
 __global__ void __launch_bounds__(256) gather_cols_add_kernel(float *__restrict__ dst, int ld_dst, int col, int width,
                                                               const float *__restrict__ src, int ld_src,
                                                               const int32_t *__restrict__ idx, float scale, int64_t rows) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (k >= rows) return;
@@ -218,7 +223,7 @@ extern "C" int gnnfd_segment_sum3(const float *a, const float *b, const float *c
   const int64_t warps = (n_rows + rpw - 1) / rpw;
   const int blocks = (int)((warps * 32 + 255) / 256);
 #define LAUNCH(L)                                                                                            \
-  segment_sum3_kernel<L><<<blocks, 256, 0, stream>>>(a, b, c, ld, col_a, col_b, col_c, sign_b, n_part, offsets, \
+  launch_pdl(segment_sum3_kernel<L>, dim3(blocks), dim3(256), 0, stream, a, b, c, ld, col_a, col_b, col_c, sign_b, n_part, offsets, \
                                                      perm, n_rows, scale, base, ld_base, out, ld_out)
   switch (lpr) {
     case 32: LAUNCH(32); break;
@@ -241,8 +246,8 @@ extern "C" int gnnfd_gather_pair_add(float *dst, const float *base, const float 
   GNNFD_CHECK_ARG(dst && src && i0 && i1, "null pointer");
   GNNFD_CHECK_ARG((ld_src % 4) == 0, "ld_src must be a multiple of 4 floats");
   const int blocks = (int)((rows * 32 + 255) / 256);
-  if (halves) gather_pair_add_kernel<true><<<blocks, 256, 0, stream>>>(dst, base, src, ld_src, i0, i1, sign, rows);
-  else gather_pair_add_kernel<false><<<blocks, 256, 0, stream>>>(dst, base, src, ld_src, i0, i1, sign, rows);
+  if (halves) launch_pdl(gather_pair_add_kernel<true>, dim3(blocks), dim3(256), 0, stream, dst, base, src, ld_src, i0, i1, sign, rows);
+  else launch_pdl(gather_pair_add_kernel<false>, dim3(blocks), dim3(256), 0, stream, dst, base, src, ld_src, i0, i1, sign, rows);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }
@@ -256,7 +261,7 @@ extern "C" int gnnfd_gather_cols_add(float *dst, int32_t ld_dst, int32_t col, in
   GNNFD_CHECK_ARG(width > 0 && (width % 4) == 0 && (col % 4) == 0 && (ld_dst % 4) == 0 && (ld_src % 4) == 0,
                   "widths / columns / strides must be multiples of 4 floats");
   const int blocks = (int)((rows * 32 + 255) / 256);
-  gather_cols_add_kernel<<<blocks, 256, 0, stream>>>(dst, ld_dst, col, width, src, ld_src, idx, scale, rows);
+  launch_pdl(gather_cols_add_kernel, dim3(blocks), dim3(256), 0, stream, dst, ld_dst, col, width, src, ld_src, idx, scale, rows);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

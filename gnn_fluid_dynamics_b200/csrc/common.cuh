@@ -55,6 +55,38 @@ inline int num_sms() {
   return n[dev];
 }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// A step of the hot path is a chain of several hundred DEPENDENT launches on one stream.  Every kernel of the chain
+// is launched with programmaticStreamSerializationAllowed, raises `griddepcontrol.launch_dependents` as its first
+// instruction and executes `griddepcontrol.wait` before its first access to global memory: the next kernel's CTAs
+// become resident on an SM as soon as the previous kernel's CTA there has retired, run their on-chip prologue (barrier
+// initialisation, TMEM allocation, tensor-map prefetch) under the previous kernel's tail, and then block in hardware
+// until the previous grid has completed and its writes are visible.  Nothing before the wait touches global memory, so
+// the result is the stream-ordered one.  A kernel launched WITHOUT the attribute sees both instructions as no-ops.
+// GNNFD_PDL=0 in the environment switches the attribute off (plain stream serialisation).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// the two together: kernels without an on-chip prologue
+__device__ __forceinline__ void pdl_entry() { pdl_launch_dependents(); pdl_wait(); }
+
+bool pdl_enabled();
+
+// launches `kernel` (which MUST execute pdl_wait() before touching global memory) with the PDL attribute
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // One deferred split-K reduction of a weight-gradient GEMM (wgrad_tc.cu): gnnfd_mlp_backward runs its GEMMs back to
 // back and adds ALL their partials in one launch at the end instead of one small launch after each GEMM.
 struct WgReduceJob {

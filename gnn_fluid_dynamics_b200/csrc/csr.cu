@@ -6,6 +6,9 @@
 //   positions.  The per-row sort makes the result independent of the atomics' arrival order, so the
 //   output is deterministic and bit-exact.
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <atomic>
 
 #include "common.cuh"
 
@@ -17,6 +20,22 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// launch overlap (programmatic dependent launch, common.cuh): -1 = not chosen yet (the environment decides, default
+// off); GNNFD_PDL = 0 / 1 in the environment pins it for the whole process
+static std::atomic<int> g_pdl{-1};
+static int pdl_env() {
+  static const int v = [] {
+    const char *e = getenv("GNNFD_PDL");
+    return e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
+  }();
+  return v;
+}
+bool pdl_enabled() {
+  const int env = pdl_env();
+  if (env >= 0) return env != 0;
+  return g_pdl.load(std::memory_order_relaxed) > 0;
 }
 
 __global__ void narrow_kernel(const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t n,
@@ -168,6 +187,10 @@ using namespace gnnfd;
 
 extern "C" int gnnfd_abi_version(void) { return GNNFD_ABI_VERSION; }
 extern "C" const char *gnnfd_last_error(void) { return g_err; }
+extern "C" int gnnfd_set_launch_overlap(int32_t on) {
+  const int prev = g_pdl.exchange(on != 0 ? 1 : 0, std::memory_order_relaxed);
+  return prev > 0 ? 1 : 0;
+}
 
 extern "C" int gnnfd_index_narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t limit,
                                   int32_t *err_flag, void *stream) {

@@ -80,6 +80,7 @@ __global__ void face_area_stats_kernel(const float *area, const float *vol, cons
                                        const float *dt, int n_dt, int64_t E, float eps, float momentum, int n_updates,
                                        float *running_mean, float *running_var, long long *nbt, float *stats,
                                        double *partials, unsigned int *ticket) {
+  pdl_entry();
   const float dt_mean = mean_of(dt, n_dt);
   double v[2] = {0.0, 0.0};
   for (int64_t f = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; f < E; f += (int64_t)gridDim.x * GL_THREADS) {
@@ -108,6 +109,7 @@ __global__ void face_area_stats_kernel(const float *area, const float *vol, cons
 __global__ void face_area_apply_kernel(const float *area, const float *vol, const int32_t *row, const int32_t *col,
                                        const float *dt, int n_dt, int64_t E, const float *stats, const float *running_mean,
                                        const float *running_var, float eps, const float *w, const float *b, float *out) {
+  pdl_entry();
   const float dt_mean = mean_of(dt, n_dt);
   const float mean = stats != nullptr ? stats[0] : *running_mean;
   const float rstd = stats != nullptr ? stats[1] : rsqrtf(*running_var + eps);
@@ -122,6 +124,7 @@ __global__ void face_area_bwd_kernel(const float *area, const float *vol, const 
                                      const float *dt, int n_dt, int64_t E, const float *stats, const float *running_mean,
                                      const float *running_var, float eps, const float *g, float *dw, float *db,
                                      double *partials, unsigned int *ticket) {
+  pdl_entry();
   const float dt_mean = mean_of(dt, n_dt);
   const float mean = stats != nullptr ? stats[0] : *running_mean;
   const float rstd = stats != nullptr ? stats[1] : rsqrtf(*running_var + eps);
@@ -144,6 +147,7 @@ __global__ void face_area_bwd_kernel(const float *area, const float *vol, const 
 __global__ void fvm_integrate_fwd_kernel(const float *eo, int ld, const float *area, const float *normal,
                                          const int32_t *cf0, const int32_t *cf1, const int32_t *cf2, int64_t N,
                                          float inv_rho, float *acc, float *div) {
+  pdl_entry();
   for (int64_t c = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; c < N; c += (int64_t)gridDim.x * GL_THREADS) {
     float ax = 0.f, ay = 0.f, px = 0.f, py = 0.f, dx = 0.f, dy = 0.f, dv = 0.f;
     const float *nc = normal + c * 6;
@@ -179,6 +183,7 @@ __global__ void fvm_integrate_bwd_kernel(const float *eo, int ld, const float *a
                                          const int32_t *cf0, const int32_t *cf1, const int32_t *cf2, const int32_t *row,
                                          const int32_t *col, int64_t E, float inv_rho, const float *g_acc,
                                          const float *g_div, float *d_eo, int ld_g, int n_cols, float *d_area) {
+  pdl_entry();
   for (int64_t f = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; f < E; f += (int64_t)gridDim.x * GL_THREADS) {
     const float *r = eo + f * ld;
     const float u = __ldg(r), v = __ldg(r + 1), a = __ldg(area + f);
@@ -223,6 +228,7 @@ __global__ void fvm_integrate_bwd_kernel(const float *eo, int ld, const float *a
 // out[0] = sum over unmasked rows, all C columns, of (a - b)^2 / (count * C);  out[1] = count * C
 __global__ void masked_mse_fwd_kernel(const float *a, int ld_a, const float *b, int ld_b, const uint8_t *mask, int64_t R, int C,
                                       float *out, double *partials, unsigned int *ticket) {
+  pdl_entry();
   double v[2] = {0.0, 0.0};
   for (int64_t r = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; r < R; r += (int64_t)gridDim.x * GL_THREADS) {
     if (mask != nullptr && !mask[r]) continue;
@@ -240,6 +246,7 @@ __global__ void masked_mse_fwd_kernel(const float *a, int ld_a, const float *b, 
 // d_a[r, c] = g * 2 (a - b) / count  on unmasked rows, 0 elsewhere  (written to [R, C] with stride ld_d)
 __global__ void masked_mse_bwd_kernel(const float *a, int ld_a, const float *b, int ld_b, const uint8_t *mask, int64_t R, int C,
                                       const float *fwd_out, const float *g, float *d_a, int ld_d) {
+  pdl_entry();
   const float s = 2.0f * (*g) / fwd_out[1];
   for (int64_t r = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; r < R; r += (int64_t)gridDim.x * GL_THREADS) {
     const bool on = mask == nullptr || mask[r];
@@ -254,6 +261,7 @@ __global__ void masked_mse_bwd_kernel(const float *a, int ld_a, const float *b, 
 //   x_raw[:, 0:2] = vel ; x_norm[:, 0:2] = (vel - mean) / std    (update_features + normalizer.input, next step's input)
 __global__ void advance_cells_kernel(float *x_raw, int ld_x, const float *delta, int ld_d, int has_change, int64_t N,
                                      float *x_norm, int ld_n, float m0, float s0, float m1, float s1, float *vel_out) {
+  pdl_entry();
   for (int64_t c = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; c < N; c += (int64_t)gridDim.x * GL_THREADS) {
     float u = __ldg(delta + c * ld_d), v = __ldg(delta + c * ld_d + 1);
     if (has_change) { u += x_raw[c * ld_x]; v += x_raw[c * ld_x + 1]; }
@@ -267,6 +275,7 @@ __global__ void advance_cells_kernel(float *x_raw, int ld_x, const float *delta,
 __global__ void advance_faces_kernel(const float *x_raw, int ld_x, const int32_t *row, const int32_t *col,
                                      const uint8_t *bc_mask, const float *bc_value, int ld_bc, int64_t E, float *f_raw,
                                      int ld_f, float *f_norm, int ld_n, float m0, float s0, float m1, float s1) {
+  pdl_entry();
   for (int64_t f = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; f < E; f += (int64_t)gridDim.x * GL_THREADS) {
     float du, dv;
     if (bc_mask != nullptr && bc_mask[f]) {
@@ -312,12 +321,12 @@ extern "C" int gnnfd_face_area_norm(const float *area, const float *volume, cons
     unsigned int *ticket;
     GNNFD_CHECK_ARG(stats != nullptr, "training mode needs the stats output");
     if (!split_ws(workspace, workspace_bytes, partials, ticket)) { set_error("gnnfd_face_area_norm: workspace too small"); return GNNFD_E_WORKSPACE; }
-    face_area_stats_kernel<<<grid, GL_THREADS, 0, st>>>(area, volume, row, col, dt, n_dt, n_faces, eps, momentum, n_updates,
+    launch_pdl(face_area_stats_kernel, dim3(grid), dim3(GL_THREADS), 0, st, area, volume, row, col, dt, n_dt, n_faces, eps, momentum, n_updates,
                                                        running_mean, running_var, (long long *)num_batches_tracked, stats,
                                                        partials, ticket);
     GNNFD_LAUNCH_CHECK();
   }
-  face_area_apply_kernel<<<grid, GL_THREADS, 0, st>>>(area, volume, row, col, dt, n_dt, n_faces, training ? stats : nullptr,
+  launch_pdl(face_area_apply_kernel, dim3(grid), dim3(GL_THREADS), 0, st, area, volume, row, col, dt, n_dt, n_faces, training ? stats : nullptr,
                                                      running_mean, running_var, eps, bn_weight, bn_bias, out);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
@@ -333,7 +342,7 @@ extern "C" int gnnfd_face_area_norm_backward(const float *area, const float *vol
   double *partials;
   unsigned int *ticket;
   if (!split_ws(workspace, workspace_bytes, partials, ticket)) { set_error("gnnfd_face_area_norm_backward: workspace too small"); return GNNFD_E_WORKSPACE; }
-  face_area_bwd_kernel<<<gl_blocks(n_faces), GL_THREADS, 0, (cudaStream_t)stream>>>(
+  launch_pdl(face_area_bwd_kernel, dim3(gl_blocks(n_faces)), dim3(GL_THREADS), 0, (cudaStream_t)stream, 
       area, volume, row, col, dt, n_dt, n_faces, stats, running_mean, running_var, eps, g, d_weight, d_bias, partials, ticket);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
@@ -346,7 +355,7 @@ extern "C" int gnnfd_fvm_integrate(const float *edge_out, int32_t ld, const floa
   if (n_cells == 0) return GNNFD_OK;
   GNNFD_CHECK_ARG(edge_out && area && normal && cf0 && cf1 && cf2 && (acc || div), "null pointer");
   GNNFD_CHECK_ARG(acc == nullptr || ld >= 5, "the integrator reads 5 columns (u, v, p, d0, d1)");
-  fvm_integrate_fwd_kernel<<<gl_blocks(n_cells), GL_THREADS, 0, (cudaStream_t)stream>>>(edge_out, ld, area, normal, cf0, cf1,
+  launch_pdl(fvm_integrate_fwd_kernel, dim3(gl_blocks(n_cells)), dim3(GL_THREADS), 0, (cudaStream_t)stream, edge_out, ld, area, normal, cf0, cf1,
                                                                                        cf2, n_cells, 1.0f / rho, acc, div);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
@@ -361,7 +370,7 @@ extern "C" int gnnfd_fvm_integrate_backward(const float *edge_out, int32_t ld, c
   if (n_faces == 0) return GNNFD_OK;
   GNNFD_CHECK_ARG(edge_out && area && normal && cf0 && cf1 && cf2 && row && col && d_edge_out && (g_acc || g_div), "null pointer");
   GNNFD_CHECK_ARG(g_acc == nullptr || (ld >= 5 && n_cols == 5), "the integrator's backward writes 5 columns");
-  fvm_integrate_bwd_kernel<<<gl_blocks(n_faces), GL_THREADS, 0, (cudaStream_t)stream>>>(
+  launch_pdl(fvm_integrate_bwd_kernel, dim3(gl_blocks(n_faces)), dim3(GL_THREADS), 0, (cudaStream_t)stream, 
       edge_out, ld, area, normal, cf0, cf1, cf2, row, col, n_faces, 1.0f / rho, g_acc, g_div, d_edge_out, ld_g, n_cols, d_area);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
@@ -373,7 +382,7 @@ extern "C" int gnnfd_masked_mse(const float *a, int32_t ld_a, const float *b, in
   double *partials;
   unsigned int *ticket;
   if (!split_ws(workspace, workspace_bytes, partials, ticket)) { set_error("gnnfd_masked_mse: workspace too small"); return GNNFD_E_WORKSPACE; }
-  masked_mse_fwd_kernel<<<gl_blocks(rows), GL_THREADS, 0, (cudaStream_t)stream>>>(a, ld_a, b, ld_b, mask, rows, cols, out2,
+  launch_pdl(masked_mse_fwd_kernel, dim3(gl_blocks(rows)), dim3(GL_THREADS), 0, (cudaStream_t)stream, a, ld_a, b, ld_b, mask, rows, cols, out2,
                                                                                  partials, ticket);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
@@ -385,7 +394,7 @@ extern "C" int gnnfd_masked_mse_backward(const float *a, int32_t ld_a, const flo
   GNNFD_CHECK_ARG(rows >= 0 && cols >= 1 && ld_a >= cols && ld_b >= cols && ld_d >= cols && a && b && fwd_out2 && g && d_a,
                   "bad arguments");
   if (rows == 0) return GNNFD_OK;
-  masked_mse_bwd_kernel<<<gl_blocks(rows), GL_THREADS, 0, (cudaStream_t)stream>>>(a, ld_a, b, ld_b, mask, rows, cols, fwd_out2,
+  launch_pdl(masked_mse_bwd_kernel, dim3(gl_blocks(rows)), dim3(GL_THREADS), 0, (cudaStream_t)stream, a, ld_a, b, ld_b, mask, rows, cols, fwd_out2,
                                                                                  g, d_a, ld_d);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
@@ -397,6 +406,7 @@ __global__ void __launch_bounds__(GL_THREADS) affine_columns_kernel(float *__res
                                                                   const int32_t *__restrict__ cols,
                                                                   const float *__restrict__ shift,
                                                                   const float *__restrict__ scale, int inverse) {
+  pdl_entry();
   const int64_t total = rows * n_spec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / n_spec;
@@ -412,7 +422,7 @@ extern "C" int gnnfd_affine_columns(float *t, int64_t rows, int32_t ld, int32_t 
   GNNFD_CHECK_ARG(rows >= 0 && n_spec >= 0 && ld >= 1, "bad sizes");
   if (rows == 0 || n_spec == 0) return GNNFD_OK;
   GNNFD_CHECK_ARG(t && cols && shift && scale, "null pointer");
-  affine_columns_kernel<<<gl_blocks(rows * n_spec), GL_THREADS, 0, (cudaStream_t)stream>>>(t, rows, ld, n_spec, cols, shift,
+  launch_pdl(affine_columns_kernel, dim3(gl_blocks(rows * n_spec)), dim3(GL_THREADS), 0, (cudaStream_t)stream, t, rows, ld, n_spec, cols, shift,
                                                                                           scale, inverse);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
@@ -429,7 +439,7 @@ extern "C" int gnnfd_state_advance(float *x_raw, int32_t ld_x, const float *delt
   cudaStream_t st = (cudaStream_t)stream;
   const float *cm = cell_mean_std4, *fm = face_mean_std4;
   if (n_cells > 0) {
-    advance_cells_kernel<<<gl_blocks(n_cells), GL_THREADS, 0, st>>>(x_raw, ld_x, delta, ld_d, has_change, n_cells, x_norm, ld_xn,
+    launch_pdl(advance_cells_kernel, dim3(gl_blocks(n_cells)), dim3(GL_THREADS), 0, st, x_raw, ld_x, delta, ld_d, has_change, n_cells, x_norm, ld_xn,
                                                                    cm ? cm[0] : 0.f, cm ? cm[1] : 1.f, cm ? cm[2] : 0.f,
                                                                    cm ? cm[3] : 1.f, vel_out);
     GNNFD_LAUNCH_CHECK();
@@ -437,7 +447,7 @@ extern "C" int gnnfd_state_advance(float *x_raw, int32_t ld_x, const float *delt
   if (n_faces > 0 && f_raw != nullptr) {
     GNNFD_CHECK_ARG(row && col && ld_f >= 2, "face update needs row / col");
     GNNFD_CHECK_ARG(bc_mask == nullptr || (bc_value != nullptr && ld_bc >= 2), "bc_mask needs bc_value");
-    advance_faces_kernel<<<gl_blocks(n_faces), GL_THREADS, 0, st>>>(x_raw, ld_x, row, col, bc_mask, bc_value, ld_bc, n_faces,
+    launch_pdl(advance_faces_kernel, dim3(gl_blocks(n_faces)), dim3(GL_THREADS), 0, st, x_raw, ld_x, row, col, bc_mask, bc_value, ld_bc, n_faces,
                                                                    f_raw, ld_f, f_norm, ld_fn, fm ? fm[0] : 0.f,
                                                                    fm ? fm[1] : 1.f, fm ? fm[2] : 0.f, fm ? fm[3] : 1.f);
     GNNFD_LAUNCH_CHECK();

@@ -9,6 +9,7 @@ namespace gnnfd {
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ src, int ld,
                                                           const int32_t *__restrict__ idx, int64_t n, int width,
                                                           float *__restrict__ out) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= n) return;
@@ -32,7 +33,7 @@ extern "C" int gnnfd_gather_rows(const float *src, int32_t ld, const int32_t *id
   GNNFD_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                   "buffers must be 16-byte aligned");
   const int blocks = (int)((n * 32 + 255) / 256);
-  gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, ld, idx, n, width, out);
+  launch_pdl(gather_rows_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, src, ld, idx, n, width, out);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

@@ -198,6 +198,7 @@ __device__ void assemble_input(const F32Params &p, int64_t row0, float *s_a) {
 }
 
 __global__ void __launch_bounds__(F32_THREADS, 1) mlp_f32_kernel(const F32Params p) {
+  pdl_entry();
   extern __shared__ __align__(16) float smem[];
   const gnnfd_mlp_args &a = p.a;
   float *s_a = smem;                                // [64][stride_a]
@@ -302,7 +303,7 @@ int mlp_forward_f32(const gnnfd_mlp_args *args, cudaStream_t stream) {
   }
   int64_t n_tiles = (args->rows + F32_BM - 1) / F32_BM;
   int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  mlp_f32_kernel<<<grid, F32_THREADS, smem, stream>>>(p);
+  launch_pdl(mlp_f32_kernel, dim3(grid), dim3(F32_THREADS), smem, stream, p);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

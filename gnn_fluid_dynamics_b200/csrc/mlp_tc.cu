@@ -303,6 +303,7 @@ __device__ __forceinline__ void tc_store_block(uint32_t sA, const float4 (&v)[8]
 // -------------------------------------------------------------------------------------- kernel
 template <bool FP16, int NA, int NW, bool BWD, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const gnnfd_mlp_args &a = p.a;
   const int a_stages = p.a_stages;
@@ -333,13 +334,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     for (int i = 0; i < 2 * TC_X_SLOTS; ++i) mbar_init(&hid_ready[i], 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
-    const int v = i / TC_H, c = i % TC_H;
-    const float *src = v == 0 ? a.b1 : v == 1 ? a.b2 : v == 2 ? (p.nl == 1 ? a.b1 : a.b3) : v == 3 ? a.ln_w : a.ln_b;
-    if (BWD && v < 3) src = nullptr;
-    const int n = (v == 2 || v >= 3) ? a.n_out : TC_H;
-    s_vec[i] = (src && c < n) ? __ldg(src + c) : (v == 3 ? 1.f : 0.f);
-  }
   if (warp == TC_MMA_WARP) tmem_alloc(s_tmem, TC_TMEM_COLS);
   if (tid == 32) {
     for (int i = 0; i < a.n_seg; ++i)
@@ -347,6 +341,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     if (EPI == 1) { prefetch_tmap(&p.tm_raw); prefetch_tmap(&p.tm_sum); }
     if (p.save_tma) { prefetch_tmap(&p.tm_save[0]); prefetch_tmap(&p.tm_save[1]); }
     if (p.split_tma) prefetch_tmap(&p.tm_split);
+  }
+  // programmatic dependent launch (common.cuh): everything above is on-chip set-up that may run under the previous
+  // kernel's tail; from here on global memory is read
+  pdl_wait();
+  for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
+    const int v = i / TC_H, c = i % TC_H;
+    const float *src = v == 0 ? a.b1 : v == 1 ? a.b2 : v == 2 ? (p.nl == 1 ? a.b1 : a.b3) : v == 3 ? a.ln_w : a.ln_b;
+    if (BWD && v < 3) src = nullptr;
+    const int n = (v == 2 || v >= 3) ? a.n_out : TC_H;
+    s_vec[i] = (src && c < n) ? __ldg(src + c) : (v == 3 ? 1.f : 0.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -1013,23 +1017,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
               }
               if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + off) = o;
-              float4 r4 = o;
               if (a.out_sum) {
-                r4 = res[jr];
+                float4 r4 = res[jr];
                 add2(r4.x, r4.y, o.x, o.y); add2(r4.z, r4.w, o.z, o.w);
                 *reinterpret_cast<float4 *>(a.out_sum + off) = r4;
-              }
-              if (a.out_split != nullptr) {
-                // training: the 16-bit hi | lo shadow of the raw output (or of the sum) for the next block's TMA gathers
-                // (8 rows x 32 B per warp instruction and part)
-                const float4 t = a.split_of_sum ? r4 : o;
-                float t0 = t.x, t1 = t.y, t2 = t.z, t3 = t.w;
-                uint32_t h0, l0, h1, l1;
-                split2<FP16>(t0, t1, h0, l0);
-                split2<FP16>(t2, t3, h1, l1);
-                uint16_t *sp = (uint16_t *)a.out_split + (size_t)g * (2 * TC_H) + col0 + c4 * 4;
-                *reinterpret_cast<uint2 *>(sp) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2 *>(sp + TC_H) = make_uint2(l0, l1);
               }
             }
           }
@@ -1089,6 +1080,7 @@ struct PackJobs { PackJob job[3]; int n_jobs; int nw; };
 // One launch packs every matrix of an MLP: one thread per (matrix, k-block, image row, 16-byte chunk).
 template <bool FP16>
 __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
+  pdl_entry();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   for (int q = 0; q < jobs.n_jobs; ++q) {
     const PackJob &jb = jobs.job[q];
@@ -1184,8 +1176,8 @@ int pack_mlp_tc(const gnnfd_mlp_args *a, void *packed_out, cudaStream_t stream) 
   }
   int total = 0;
   for (int q = 0; q < jobs.n_jobs; ++q) total += jobs.job[q].n_kblocks * jobs.job[q].n_img_rows * 8;
-  if (m.fp16) pack_weights_kernel<true><<<(total + 255) / 256, 256, 0, stream>>>(jobs);
-  else pack_weights_kernel<false><<<(total + 255) / 256, 256, 0, stream>>>(jobs);
+  if (m.fp16) launch_pdl(pack_weights_kernel<true>, dim3((total + 255) / 256), dim3(256), 0, stream, jobs);
+  else launch_pdl(pack_weights_kernel<false>, dim3((total + 255) / 256), dim3(256), 0, stream, jobs);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }
@@ -1286,10 +1278,8 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
                     (a->out_sum == nullptr || a->residual != nullptr) &&
                     ((reinterpret_cast<uintptr_t>(a->out_raw) | reinterpret_cast<uintptr_t>(a->out_sum) |
                       reinterpret_cast<uintptr_t>(a->out_split) | reinterpret_cast<uintptr_t>(a->residual)) & 15) == 0;
-  if (a->out_split != nullptr && !fast &&
-      !(p.nl == 3 && a->n_out == TC_H && m.na == 2 && !a->bwd_chain && (reinterpret_cast<uintptr_t>(a->out_split) & 15) == 0 &&
-        (!a->split_of_sum || a->out_sum != nullptr))) {
-    set_error("mlp_forward_tc: out_split needs n_out = 128 and a split precision");
+  if (a->out_split != nullptr && !fast) {
+    set_error("mlp_forward_tc: out_split needs the inference epilogue (n_out = 128, split precision, no stash / mul)");
     return GNNFD_E_UNSUPPORTED;
   }
   if (fast && a->rows > 0) {
@@ -1348,7 +1338,7 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
                                       227 * 1024));                                                       \
       attr[current_device()] = true;                                                                      \
     }                                                                                                     \
-    mlp_tc_kernel<FP, NA_, NW_, BW, EP><<<grid, TC_THREADS, tc_smem_bytes(p.w_slots, p.a_stages) + extra_smem, stream>>>(p);   \
+    launch_pdl(mlp_tc_kernel<FP, NA_, NW_, BW, EP>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(p.w_slots, p.a_stages) + extra_smem, stream, p);   \
   } while (0)
 #define LAUNCH(FP, NA_, NW_)                                                                              \
   do {                                                                                                    \

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(
     const float *__restrict__ a, const float *__restrict__ b, int ld_a, int ld_b, int col_a, int col_b,
     float sign_b, int64_t n_half, const int32_t *__restrict__ offsets, const int32_t *__restrict__ perm,
     int64_t n_rows, float *__restrict__ out, int ld_out) {
+  pdl_entry();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR, grp = lane / LPR;
@@ -115,7 +116,7 @@ extern "C" int gnnfd_segment_sum(const float *a, const float *b, int32_t ld_a, i
   const int64_t cap = (int64_t)num_sms() * 4;             // grid-stride: the four resident blocks per SM (58 registers) walk all rows
   const int blocks = (int)(blocks64 < cap ? blocks64 : cap);
 #define LAUNCH(L)                                                                                   \
-  segment_sum_kernel<L><<<blocks, 256, 0, stream>>>(a, b, ld_a, ld_b, col_a, col_b, sign_b, n_half, \
+  launch_pdl(segment_sum_kernel<L>, dim3(blocks), dim3(256), 0, stream, a, b, ld_a, ld_b, col_a, col_b, sign_b, n_half, \
                                                     offsets, perm, n_rows, out, ld_out)
   switch (lpr) {
     case 32: LAUNCH(32); break;

@@ -149,6 +149,7 @@ __device__ __forceinline__ float4 wg_load_item(const WgPiece &pc, int lane, bool
 // Both modes stage 32 rows x 4 bytes per element: A 16 KB + B n_pad * 128 B per stage.
 template <int NP, int MODE>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr bool BF = MODE == 0;
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WG_PROD_WARPS) tmem_alloc(s_tmem, 512);
+  pdl_wait();   // everything above is on-chip set-up that may run under the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -399,6 +401,7 @@ struct WgLeanParams {
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_lean_kernel(const __grid_constant__ WgLeanParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr uint32_t a_bytes = 16 * 1024, stage_bytes = 32 * 1024;      // A hi | lo (8 KB each), B hi | lo
@@ -416,6 +419,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_lean_kernel(const __grid_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WG_PROD_WARPS) tmem_alloc(s_tmem, 512);
+  pdl_wait();   // everything above is on-chip set-up that may run under the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -558,6 +562,7 @@ __global__ void __launch_bounds__(RP_OUT * RP_GROUPS) reduce_partials_kernel(con
                                                               int m_valid, int n_valid, float *__restrict__ out,
                                                               int ld_out, int transpose, const float *__restrict__ cs_part,
                                                               float *__restrict__ cs_out, int cs_valid) {
+  pdl_entry();
   __shared__ float s_sum[RP_GROUPS][RP_OUT];
   const int total = m_valid * n_valid;
   const int tx = threadIdx.x & (RP_OUT - 1), ty = threadIdx.x / RP_OUT;
@@ -592,6 +597,7 @@ __global__ void __launch_bounds__(RP_OUT * RP_GROUPS) reduce_partials_kernel(con
 struct WgReduceJobs { WgReduceJob job[WG_MAX_REDUCE_JOBS]; int first_block[WG_MAX_REDUCE_JOBS + 1]; int n; };
 // the same reduction for several GEMMs in one launch: block -> (job, block of the job)
 __global__ void __launch_bounds__(RP_OUT * RP_GROUPS) reduce_partials_multi_kernel(const __grid_constant__ WgReduceJobs jobs) {
+  pdl_entry();
   __shared__ float s_sum[RP_GROUPS][RP_OUT];
   int q = 0;
   while (q + 1 < jobs.n && (int)blockIdx.x >= jobs.first_block[q + 1]) ++q;
@@ -640,7 +646,7 @@ int wgrad_reduce_jobs(const WgReduceJob *jobs, int n_jobs, cudaStream_t stream) 
   }
   js.first_block[n_jobs] = blocks;
   if (blocks == 0) return GNNFD_OK;
-  reduce_partials_multi_kernel<<<blocks, RP_OUT * RP_GROUPS, 0, stream>>>(js);
+  launch_pdl(reduce_partials_multi_kernel, dim3(blocks), dim3(RP_OUT * RP_GROUPS), 0, stream, js);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }
@@ -697,7 +703,7 @@ int wgrad_lean_run(const gnnfd_wgrad_args *const *args, int n, void *workspace, 
     GNNFD_CUDA(cudaFuncSetAttribute(wgrad_lean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr[current_device()] = true;
   }
-  wgrad_lean_kernel<<<grid, WG_THREADS, smem, stream>>>(p);
+  launch_pdl(wgrad_lean_kernel, dim3(grid), dim3(WG_THREADS), smem, stream, p);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }
@@ -799,7 +805,7 @@ int gnnfd::wgrad_run(const gnnfd_wgrad_args *a, void *workspace, size_t workspac
       GNNFD_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<NP_, MD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
       attr[current_device()] = true;                                                                                             \
     }                                                                                                          \
-    wgrad_tc_kernel<NP_, MD_><<<grid, WG_THREADS, smem, stream>>>(p);                            \
+    launch_pdl(wgrad_tc_kernel<NP_, MD_>, dim3(grid), dim3(WG_THREADS), smem, stream, p);                            \
   } while (0)
   if (a->precision == 1) { if (p.n_pieces == 2) WG_LAUNCH(2, 1); else if (p.n_pieces == 3) WG_LAUNCH(3, 1); else WG_LAUNCH(4, 1); }
   else { if (p.n_pieces == 2) WG_LAUNCH(2, 0); else if (p.n_pieces == 3) WG_LAUNCH(3, 0); else WG_LAUNCH(4, 0); }
@@ -814,7 +820,7 @@ int gnnfd::wgrad_run(const gnnfd_wgrad_args *a, void *workspace, size_t workspac
     defer->ws_used = (need + 255) & ~(size_t)255;
     return GNNFD_OK;
   }
-  reduce_partials_kernel<<<(total + RP_OUT - 1) / RP_OUT, RP_OUT * RP_GROUPS, 0, stream>>>(p.partial, grid, n_pad, m_valid, n_valid, a->out,
+  launch_pdl(reduce_partials_kernel, dim3((total + RP_OUT - 1) / RP_OUT), dim3(RP_OUT * RP_GROUPS), 0, stream, p.partial, grid, n_pad, m_valid, n_valid, a->out,
                                                                   a->ld_out, a->transpose_out, cs_part, a->colsum, cs_valid);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;

@@ -13,6 +13,7 @@ from typing import List, Optional
 
 import torch
 
+from ._lib import choose_launch_overlap
 from .topology import attach_topology
 
 
@@ -152,6 +153,7 @@ class RolloutEngine:
     def step(self) -> torch.Tensor:
         """Advance the state by one timestep; returns the new cell velocity [N, 2] (a static buffer when the
         step is graph-replayed: clone it to keep it)."""
+        choose_launch_overlap(self.topo.n_faces, False)     # (a captured graph keeps the policy it was captured with)
         if not self.use_graph:
             return self._step_eager()
         if self._graph is None:

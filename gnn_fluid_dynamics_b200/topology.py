@@ -11,6 +11,7 @@ from typing import Optional
 import torch
 
 from . import ops
+from ._lib import choose_launch_overlap
 
 
 def _tensor_key(t):
@@ -182,7 +183,14 @@ class MeshTopology:
 
 
 def get_topology(graphs, need_cell_csr: bool = False, two_hop: bool = True) -> MeshTopology:
-    """Topology attached by ``attach_topology`` if it matches the graphs, else a fresh build."""
+    """Topology attached by ``attach_topology`` if it matches the graphs, else a fresh build.  Every model forward starts
+    here, so this is also where the launch policy of the pass is chosen (``_lib.choose_launch_overlap``)."""
+    topo = _get_topology(graphs, need_cell_csr, two_hop)
+    choose_launch_overlap(topo.n_faces, torch.is_grad_enabled())
+    return topo
+
+
+def _get_topology(graphs, need_cell_csr: bool, two_hop: bool) -> MeshTopology:
     c, _, v = graphs
     topo = getattr(v, "topology", None) if v is not None else None
     if topo is None:

@@ -21,7 +21,6 @@ reproducible run to run.
 """
 from __future__ import annotations
 
-import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -31,10 +30,6 @@ from ._lib import ACT_SILU, SEG_GATHER, SEG_MEAN3
 from .ops import MLPStash, MLPWeights, Seg
 from .processor import H, _split_mlp, vertex_half_sum, weights_of
 from .topology import MeshTopology
-
-# training forward: gathered k-blocks of the edge block staged by TMA gather4 from a split shadow (GNNFD_TRAIN_TMA_GATHER=1; measured neutral on the
-# training step - 28.6 vs 28.6 ms, A/B on one box - so the register-staged producers stay the default)
-TRAIN_TMA_GATHER = os.environ.get("GNNFD_TRAIN_TMA_GATHER", "0") == "1"
 
 PARAM_NAMES = ("w1", "b1", "w2", "b2", "w3", "b3", "ln_w", "ln_b")
 
@@ -179,10 +174,8 @@ def _node_segs(x, vsum, topo):
     return [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf)]
 
 
-def _edge_segs(e, xs, topo, split=None):
-    """``split``: the 16-bit hi | lo shadow of ``xs`` (written by the kernel that produced ``xs``): the gathered k-blocks
-    are then staged by TMA gather4 instead of through the producers' registers."""
-    return [Seg(e), Seg(xs, SEG_GATHER, (topo.row,), split=split), Seg(xs, SEG_GATHER, (topo.col,), split=split)]
+def _edge_segs(e, xs, topo):
+    return [Seg(e), Seg(xs, SEG_GATHER, (topo.row,)), Seg(xs, SEG_GATHER, (topo.col,))]
 
 
 class EncodeProcessDecode(torch.autograd.Function):
@@ -195,15 +188,8 @@ class EncodeProcessDecode(torch.autograd.Function):
         vertpot = plan.family == "vertpot"
         c_x, f_x = c_x.contiguous(), f_x.contiguous()
         N, E = c_x.shape[0], f_x.shape[0]
-        # the matrix the edge block gathers also exists as a 16-bit hi | lo shadow written by the kernel that produced it
-        # (one buffer for the whole forward: every block's edge kernel reads it before the next node kernel rewrites it):
-        # its gathered k-blocks are staged by TMA gather4 - the producers' one-block-in-flight register staging of four
-        # gathered k-blocks per tile was the training forward's critical path (ncu: the epilogue waited on layer 1)
-        sdt = ops.split_dtype(prec)
-        xs = torch.empty(N, 2 * H, dtype=sdt, device=c_x.device) if (TRAIN_TMA_GATHER and sdt is not None and N > 0) else None
         e, _, st_ee = ops.mlp_forward([Seg(f_x)], plan.enc_edge.weights(), E, prec, stash=True)
-        x, _, st_en = ops.mlp_forward([Seg(c_x)], plan.enc_node.weights(), N, prec, stash=True,
-                                      out_split=xs if fam == "mgn" else None)
+        x, _, st_en = ops.mlp_forward([Seg(c_x)], plan.enc_node.weights(), N, prec, stash=True)
         saved = []
         e_raw_last = None
         for bi, (node_site, edge_site) in enumerate(plan.blocks):
@@ -211,17 +197,17 @@ class EncodeProcessDecode(torch.autograd.Function):
             if fam == "fvgn":
                 vsum = vertex_half_sum(e, topo)
                 x_raw, x_new, st_n = ops.mlp_forward(_node_segs(x, vsum, topo), wn, N, prec, residual=x,
-                                                     want_raw=True, want_sum=True, stash=True, out_split=xs)
+                                                     want_raw=True, want_sum=True, stash=True)
                 last_vp = vertpot and bi == len(plan.blocks) - 1
-                e_raw_last, e_new, st_e = ops.mlp_forward(_edge_segs(e, x_raw, topo, xs), we, E, prec, residual=e,
+                e_raw_last, e_new, st_e = ops.mlp_forward(_edge_segs(e, x_raw, topo), we, E, prec, residual=e,
                                                           want_raw=last_vp, want_sum=True, stash=True)
                 saved.append((x, e, vsum, x_raw, st_n, st_e))
             else:
-                e_raw, e_new, st_e = ops.mlp_forward(_edge_segs(e, x, topo, xs), we, E, prec, residual=e,
+                e_raw, e_new, st_e = ops.mlp_forward(_edge_segs(e, x, topo), we, E, prec, residual=e,
                                                      want_raw=True, want_sum=True, stash=True)
                 vsum = vertex_half_sum(e_raw, topo)
                 _, x_new, st_n = ops.mlp_forward(_node_segs(x, vsum, topo), wn, N, prec, residual=x,
-                                                 want_raw=False, want_sum=True, stash=True, out_split=xs, split_of_sum=True)
+                                                 want_raw=False, want_sum=True, stash=True)
                 saved.append((x, e, vsum, None, st_n, st_e))
             x, e = x_new, e_new
         dec_in = e if fam == "fvgn" else x

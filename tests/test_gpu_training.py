@@ -250,24 +250,6 @@ def test_training_gradients_are_bitwise_reproducible():
     assert all(torch.equal(a, b) for a, b in zip(*runs))
 
 
-@pytest.mark.parametrize("name", ["FvgnA", "MgnA"])
-def test_training_forward_tma_gather_variant_is_bit_identical(name, monkeypatch):
-    """GNNFD_TRAIN_TMA_GATHER=1 (edge block's gathered k-blocks from the 16-bit split shadow the node kernel's training
-    epilogue writes) against the default register-staged producers: same operand split, same gradients bit for bit."""
-    from gnn_fluid_dynamics_b200 import training
-    model = build_model(name).to(dev()).train()
-    _, graphs = golden_graphs(name, flip=True, n_cells=2000)
-    runs = []
-    for flag in (False, True):
-        monkeypatch.setattr(training, "TRAIN_TMA_GATHER", flag)
-        model.zero_grad(set_to_none=True)
-        out = model([g.clone().to(dev()) for g in graphs], mode="train")
-        gn = model.normalizer.input([g.clone().to(dev()) for g in graphs])
-        model.loss(out, gn)["total_log_loss"].backward()
-        runs.append([p.grad.clone() for p in model.parameters() if p.grad is not None])
-    assert all(torch.equal(a, b) for a, b in zip(*runs))
-
-
 def test_fused_backward_call_equals_stepwise_schedule():
     """gnnfd_mlp_backward (one C call, dgrad chain fused into one 3-layer pass) against the Python-scheduled
     chain of single-Linear launches: same arithmetic up to accumulation order."""
