@@ -24,14 +24,19 @@ DEFAULT_PRECISION = "bf16x3"
 def build_mlp(config, in_size, hidden_size, out_size, norm_layer=True):
     """Parameter container with the reference's layout (Model.py:12-40): ``Sequential(Linear, SiLU,
     Linear, SiLU, Linear)`` (indices 0,2,4), wrapped as ``Sequential(mlp, LayerNorm)`` when normalised.
-    Dropout (only inserted by the reference when ``dropout_rate > 0``; 0.0 in every shipped config)
-    is not supported on the fused path."""
+    With ``config.training.dropout_rate > 0`` the reference inserts a Dropout after each SiLU (Linear
+    indices 0,3,6); the same layout is built here so that its checkpoints load.  Dropout is the identity
+    in eval mode, which is all the fused kernels implement: a TRAINING forward of such a model raises
+    (``processor.weights_of``); 0.0 in every shipped config."""
     rate = getattr(getattr(config, "training", None), "dropout_rate", 0.0) or 0.0
+    layers = [nn.Linear(in_size, hidden_size), nn.SiLU()]
     if rate > 0:
-        raise NotImplementedError("dropout_rate > 0 is not supported by the fused B200 path")
-    mlp = nn.Sequential(nn.Linear(in_size, hidden_size), nn.SiLU(),
-                        nn.Linear(hidden_size, hidden_size), nn.SiLU(),
-                        nn.Linear(hidden_size, out_size))
+        layers.append(nn.Dropout(p=rate))
+    layers += [nn.Linear(hidden_size, hidden_size), nn.SiLU()]
+    if rate > 0:
+        layers.append(nn.Dropout(p=rate))
+    layers.append(nn.Linear(hidden_size, out_size))
+    mlp = nn.Sequential(*layers)
     if norm_layer:
         return nn.Sequential(mlp, nn.LayerNorm(normalized_shape=out_size))
     return mlp

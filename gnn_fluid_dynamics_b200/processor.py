@@ -44,6 +44,9 @@ def weights_of(seq: torch.nn.Module, act: int = ACT_SILU) -> MLPWeights:
     """MLPWeights view of a reference-layout MLP module, cached on the module and refreshed when a
     parameter is replaced or modified in place (``_version``), e.g. by an optimizer step."""
     inner, ln = _split_mlp(seq)
+    if seq.training and any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in inner):
+        raise NotImplementedError("training-mode dropout (config.training.dropout_rate > 0, Model.py:29-33) is not implemented "
+                                  "by the fused MLP kernels; eval() / rollout of such a model is supported")
     lin = [m for m in inner if isinstance(m, torch.nn.Linear)]
     params = [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias]
     if ln is not None:

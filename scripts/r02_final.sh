@@ -1,0 +1,15 @@
+#!/bin/bash
+# Final round-2 measurement pass on one B200 (through gpurun): tests, driver-style bench lines, kernel timings, ncu passes.
+O=gpurun_out/r02_final; mkdir -p $O
+timeout 1500 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; tail -2 $O/pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
+( time timeout 900 python bench.py > $O/bench_default.json 2> $O/bench_default.err ) 2> $O/bench_default.time; tail -3 $O/bench_default.time; python scripts/print_bench.py $O/bench_default.json
+( time timeout 900 python bench.py --impl reference > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err ) 2> $O/bench_reference.time; tail -3 $O/bench_reference.time; cat $O/bench_reference_arm.json | cut -c1-400
+timeout 200 python bench.py --workload fvgn_fwd_8x20k --steps 20 --warmup 5 --no-cpu-baseline > $O/bench_fwd.json 2> $O/bench_fwd.err; python scripts/print_bench.py $O/bench_fwd.json | head -1
+for w in vertpot_train_8x20k streamfunc_train_8x20k; do timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_$w.json 2> $O/bench_$w.err; echo "$w $(python scripts/print_bench.py $O/bench_$w.json | head -1)"; done
+timeout 300 python scripts/bench_kernels.py > $O/kernel_microbench.log 2>&1; cat $O/kernel_microbench.log
+timeout 300 python scripts/abl_edge.py fast > $O/fast_path_timing.log 2>&1; cat $O/fast_path_timing.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $O/train_launches_all.csv python bench.py --steps 2 --warmup 3 --strong-4m off --no-cpu-baseline > $O/ncu_list.log 2>&1; tail -1 $O/ncu_list.log | cut -c1-200
+timeout 200 python scripts/prof_train_kernels.py > $O/plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:"wgrad|mlp_tc_kernel" -s 7 -c 7 -o $O/train_kernels -f python scripts/prof_train_kernels.py > $O/ncu_train.log 2>&1; tail -1 $O/ncu_train.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 2 -c 1 -o $O/fwd_edge_fast -f python scripts/prof_fwd_edge.py fast > $O/ncu_fwd.log 2>&1; tail -1 $O/ncu_fwd.log
+ls -la $O

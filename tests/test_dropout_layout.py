@@ -1,0 +1,64 @@
+"""config.training.dropout_rate > 0 (reference Model.py:29-33): a Dropout follows each SiLU, so the Linear layers sit at
+Sequential indices 0, 3, 6 instead of 0, 2, 4.  The same layout is built here (checkpoints load); eval-mode forwards are
+the dropout-free computation; a training-mode forward raises instead of silently dropping nothing."""
+import re
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+from helpers import LOSS_W, build_model, golden_graphs, mse
+
+
+def _dropout_model(name, rate=0.1):
+    from gnn_fluid_dynamics_b200.models import MODEL_CLASSES
+    from fixtures import stats_for
+    cfg = NS(model=NS(hidden_width=128, mp_num=15, precision=None, bundle_size=3),
+             training=NS(dropout_rate=rate, loss_weights=dict(LOSS_W)))
+    return MODEL_CLASSES[name](cfg, mse, None, stats_for(name))
+
+
+def test_build_mlp_layout_with_dropout():
+    """Module order of Model.py:26-35: Linear, SiLU, Dropout, Linear, SiLU, Dropout, Linear (+ LayerNorm wrapper)."""
+    from gnn_fluid_dynamics_b200.models.base import build_mlp
+    cfg = NS(training=NS(dropout_rate=0.25))
+    m = build_mlp(cfg, 10, 128, 128)
+    assert [type(x).__name__ for x in m[0]] == ["Linear", "SiLU", "Dropout", "Linear", "SiLU", "Dropout", "Linear"]
+    assert all(x.p == 0.25 for x in m[0] if isinstance(x, torch.nn.Dropout))
+    assert list(m.state_dict()) == ["0.0.weight", "0.0.bias", "0.3.weight", "0.3.bias", "0.6.weight", "0.6.bias",
+                                    "1.weight", "1.bias"]
+    assert list(build_mlp(cfg, 10, 128, 3, norm_layer=False).state_dict()) == [
+        "0.weight", "0.bias", "3.weight", "3.bias", "6.weight", "6.bias"]
+    assert list(build_mlp(NS(training=NS(dropout_rate=0.0)), 10, 128, 128).state_dict()) == [
+        "0.0.weight", "0.0.bias", "0.2.weight", "0.2.bias", "0.4.weight", "0.4.bias", "1.weight", "1.bias"]
+
+
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA", "ConservativeA"])
+def test_state_dict_layout_with_dropout(name):
+    plain, drop = build_model(name).state_dict(), _dropout_model(name).state_dict()
+    assert len(plain) == len(drop)
+    assert sorted(tuple(v.shape) for v in plain.values()) == sorted(tuple(v.shape) for v in drop.values())
+    assert any(re.search(r"\.[36]\.(weight|bias)$", k) for k in drop), "no Linear at index 3 / 6"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["FvgnA", "MgnA"])
+def test_eval_forward_ignores_dropout_and_training_raises(name):
+    dev = torch.device("cuda:0")
+    plain = build_model(name).to(dev).eval()
+    drop = _dropout_model(name).to(dev).eval()
+    sd, tgt = plain.state_dict(), drop.state_dict()
+    src_keys = {re.sub(r"\.3\.(weight|bias)$", r".2.\1", re.sub(r"\.6\.(weight|bias)$", r".4.\1", k)): k for k in tgt}
+    drop.load_state_dict({src_keys[k]: v for k, v in sd.items() if k in src_keys} |
+                         {k: v for k, v in sd.items() if k in tgt and k not in src_keys.values()}, strict=False)
+    for k, dk in src_keys.items():
+        assert torch.equal(drop.state_dict()[dk], sd[k]), (k, dk)
+    _, graphs = golden_graphs(name, n_cells=300)
+    with torch.no_grad():
+        a = plain([g.clone().to(dev) for g in graphs], mode="rollout")
+        b = drop([g.clone().to(dev) for g in graphs], mode="rollout")
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    drop.train()
+    with pytest.raises(NotImplementedError, match="dropout"):
+        drop([g.clone().to(dev) for g in graphs], mode="train")
