@@ -10,6 +10,6 @@ for w in vertpot_train_8x20k streamfunc_train_8x20k; do timeout 300 python bench
 timeout 300 python scripts/bench_kernels.py > $O/kernel_microbench.log 2>&1; cat $O/kernel_microbench.log
 timeout 300 python scripts/abl_edge.py fast > $O/fast_path_timing.log 2>&1; cat $O/fast_path_timing.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file $O/train_launches_all.csv python bench.py --steps 2 --warmup 3 --strong-4m off --no-cpu-baseline > $O/ncu_list.log 2>&1; tail -1 $O/ncu_list.log | cut -c1-200
-timeout 200 python scripts/prof_train_kernels.py > $O/plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:"wgrad|mlp_tc_kernel" -s 7 -c 7 -o $O/train_kernels -f python scripts/prof_train_kernels.py > $O/ncu_train.log 2>&1; tail -1 $O/ncu_train.log
+timeout 200 python scripts/prof_train_kernels.py > $O/plain.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:"wgrad|mlp_tc_kernel" -s 6 -c 6 -o $O/train_kernels -f python scripts/prof_train_kernels.py > $O/ncu_train.log 2>&1; tail -1 $O/ncu_train.log
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -s 2 -c 1 -o $O/fwd_edge_fast -f python scripts/prof_fwd_edge.py fast > $O/ncu_fwd.log 2>&1; tail -1 $O/ncu_fwd.log
 ls -la $O
