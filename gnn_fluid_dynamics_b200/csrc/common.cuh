@@ -128,4 +128,45 @@ __device__ __forceinline__ float4 ldg_f4(const float *p) {
   return __ldg(reinterpret_cast<const float4 *>(p));
 }
 
+// ---- L2 eviction-priority hints ----------------------------------------------------------------------------------
+// A step streams several hundred MB through a 126 MB L2 per launch; most of it is written once and read much later (the
+// training stash, the residual streams) while the gathered cell / vertex latents (<= 82 MB) are re-read ~6 times by
+// faces that are far apart in face order.  Write-once streams are stored with an evict-first policy and the gathered
+// rows loaded with evict-last, so the streams stop displacing the rows that are re-read.  The policy is an OPERAND (a
+// 64-bit descriptor, the encodings createpolicy.fractional.L2::evict_* produces at fraction 1.0): the same instruction
+// with L2_EVICT_NORMAL is the unhinted access, so the hints cost no code and can be A/B-ed at run time
+// (GNNFD_L2_HINTS, l2_hint_mask()).
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull, L2_EVICT_FIRST = 0x12F0000000000000ull,
+                   L2_EVICT_LAST = 0x14F0000000000000ull;
+enum {
+  L2H_ST_STASH = 1,    // training stash (pre-activations, x-hat, dA): evict-first stores
+  L2H_ST_OUT = 2,      // residual-stream outputs (out_sum, split shadow): evict-first stores
+  L2H_LD_STREAM = 4,   // contiguous (DIRECT) operand rows, saved pre-activations, residual rows: evict-first loads
+  L2H_LD_KEEP = 8,     // gathered rows: evict-last loads
+  L2H_ST_RAW = 16,     // raw outputs (consumed by the next launch): evict-first stores
+};
+constexpr int L2_HINT_DEFAULT = 0;
+int l2_hint_mask();    // GNNFD_L2_HINTS / gnnfd_set_l2_hints (csr.cu)
+struct L2Policies { uint64_t st_stash, st_out, st_raw, ld_stream, ld_keep; };
+inline L2Policies l2_policies() {
+  const int m = l2_hint_mask();
+  L2Policies p;
+  p.st_stash = (m & L2H_ST_STASH) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+  p.st_out = (m & L2H_ST_OUT) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+  p.st_raw = (m & L2H_ST_RAW) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+  p.ld_stream = (m & L2H_LD_STREAM) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+  p.ld_keep = (m & L2H_LD_KEEP) ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+  return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float *p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_f4_hint(float *p, float4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w), "l"(pol) : "memory");
+}
+
 }  // namespace gnnfd

@@ -38,6 +38,19 @@ bool pdl_enabled() {
   return g_pdl.load(std::memory_order_relaxed) > 0;
 }
 
+// L2 eviction-priority hints (common.cuh): GNNFD_L2_HINTS=<mask> in the environment pins the mask for the process,
+// else gnnfd_set_l2_hints chooses it; default L2_HINT_DEFAULT
+static std::atomic<int> g_l2_hints{-1};
+int l2_hint_mask() {
+  static const int env = [] {
+    const char *e = getenv("GNNFD_L2_HINTS");
+    return e == nullptr ? -1 : atoi(e);
+  }();
+  if (env >= 0) return env;
+  const int v = g_l2_hints.load(std::memory_order_relaxed);
+  return v >= 0 ? v : L2_HINT_DEFAULT;
+}
+
 __global__ void narrow_kernel(const int64_t *__restrict__ src, int32_t *__restrict__ dst, int64_t n,
                               int64_t limit, int32_t *err) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -190,6 +203,12 @@ extern "C" const char *gnnfd_last_error(void) { return g_err; }
 extern "C" int gnnfd_set_launch_overlap(int32_t on) {
   const int prev = g_pdl.exchange(on != 0 ? 1 : 0, std::memory_order_relaxed);
   return prev > 0 ? 1 : 0;
+}
+
+extern "C" int gnnfd_set_l2_hints(int32_t mask) {
+  const int prev = l2_hint_mask();
+  g_l2_hints.store(mask < 0 ? -1 : mask, std::memory_order_relaxed);
+  return prev;
 }
 
 extern "C" int gnnfd_index_narrow(const int64_t *src, int32_t *dst, int64_t n, int64_t limit,

@@ -117,6 +117,7 @@ struct TcParams {
   alignas(64) CUtensorMap tm_split;    // out_split as [rows, 256] 16-bit, box 16 x 32, no swizzle
   int save_tma;  // the hidden epilogues write their stash through the staging block + TMA tensor stores
   int split_tma; // the split shadow leaves through a SECOND staging block (after the weight rings) + TMA tensor stores
+  L2Policies pol;   // L2 eviction-priority operands of the global accesses (common.cuh)
 };
 
 // Diagnostic cycle counters of CTA 0 (role wait times), read back with gnnfd_tc_profile_read; only
@@ -212,7 +213,7 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
     const int last = (int)min((int64_t)TC_BM, p.a.rows - row0) - 1;
     const uint32_t ldu = (uint32_t)d.ld;
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(tb + (uint32_t)min(rbase + 16 * jj, last) * ldu);
+    for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4_hint(tb + (uint32_t)min(rbase + 16 * jj, last) * ldu, p.pol.ld_stream);
   } else if (d.mode == GNNFD_SEG_GATHER) {
     if (p.a.peer_shift > 0) {   // rows of ghost cells come straight from the owning GPU's HBM (P2P over NVLink)
       const uint32_t mask = (1u << p.a.peer_shift) - 1u;
@@ -223,7 +224,7 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
       }
     } else {
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4(base + (int64_t)lds_s32(ixa + 64 * jj) * ld);
+      for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4_hint(base + (int64_t)lds_s32(ixa + 64 * jj) * ld, p.pol.ld_keep);
     }
   } else if (d.mode == GNNFD_SEG_SUM3S) {
     // (s0 a + s1 b) + s2 c: three gathered rows with the signs decoded from the index entries
@@ -238,9 +239,9 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
         sum3s_decode(lds_s32(ixa + 64 * jj), r0, sg[u][0]);
         sum3s_decode(lds_s32(ixa + (TC_BM + 16 * jj) * 4), r1, sg[u][1]);
         sum3s_decode(lds_s32(ixa + (2 * TC_BM + 16 * jj) * 4), r2, sg[u][2]);
-        v[jj] = ldg_f4(base + (int64_t)r0 * ld);
-        y[u] = ldg_f4(base + (int64_t)r1 * ld);
-        z[u] = ldg_f4(base + (int64_t)r2 * ld);
+        v[jj] = ldg_f4_hint(base + (int64_t)r0 * ld, p.pol.ld_keep);
+        y[u] = ldg_f4_hint(base + (int64_t)r1 * ld, p.pol.ld_keep);
+        z[u] = ldg_f4_hint(base + (int64_t)r2 * ld, p.pol.ld_keep);
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -257,9 +258,9 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int jj = h * 2 + u;
-        v[jj] = ldg_f4(base + (int64_t)lds_s32(ixa + 64 * jj) * ld);
-        y[u] = ldg_f4(base + (int64_t)lds_s32(ixa + (TC_BM + 16 * jj) * 4) * ld);
-        z[u] = ldg_f4(base + (int64_t)lds_s32(ixa + (2 * TC_BM + 16 * jj) * 4) * ld);
+        v[jj] = ldg_f4_hint(base + (int64_t)lds_s32(ixa + 64 * jj) * ld, p.pol.ld_keep);
+        y[u] = ldg_f4_hint(base + (int64_t)lds_s32(ixa + (TC_BM + 16 * jj) * 4) * ld, p.pol.ld_keep);
+        z[u] = ldg_f4_hint(base + (int64_t)lds_s32(ixa + (2 * TC_BM + 16 * jj) * 4) * ld, p.pol.ld_keep);
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -276,8 +277,8 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int jj = h * 4 + u;
-        v[jj] = ldg_f4(base + (int64_t)lds_s32(ixa + 64 * jj) * ld);
-        y[u] = ldg_f4(base + (int64_t)lds_s32(ixa + (TC_BM + 16 * jj) * 4) * ld);
+        v[jj] = ldg_f4_hint(base + (int64_t)lds_s32(ixa + 64 * jj) * ld, p.pol.ld_keep);
+        y[u] = ldg_f4_hint(base + (int64_t)lds_s32(ixa + (TC_BM + 16 * jj) * 4) * ld, p.pol.ld_keep);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[h * 4 + u] = diff ? f4_sub(v[h * 4 + u], y[u]) : f4_add(v[h * 4 + u], y[u]);
@@ -456,7 +457,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll 1
           for (int g = 0; g < 8; ++g) {
             const int4 ix = lds_s32x4(ixa + g * 16);
-            tma_gather4(dst + g * 512, tm, colp, ix.x, ix.y, ix.z, ix.w, &a_full[st]);
+            tma_gather4_hint(dst + g * 512, tm, colp, ix.x, ix.y, ix.z, ix.w, &a_full[st], p.pol.ld_keep);
           }
         }
         __syncwarp();
@@ -704,8 +705,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
           for (int jr = 0; jr < 4; ++jr) {
             const int rl = jr * 8 + rr;
-            cp_async16(stg2 + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4,
-                       hm + cg * 16 + (size_t)min(row0 + q4 * 32 + rl, a.rows - 1) * TC_H);
+            cp_async16_hint(stg2 + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4,
+                            hm + cg * 16 + (size_t)min(row0 + q4 * 32 + rl, a.rows - 1) * TC_H, p.pol.ld_stream);
           }
           cp_async_commit();
         };
@@ -760,7 +761,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&p.tm_save[layer], stg, eh * 64 + c * 16, (int)(row0 + q4 * 32));
+              tma_store_2d_hint(&p.tm_save[layer], stg, eh * 64 + c * 16, (int)(row0 + q4 * 32), p.pol.st_stash);
               bulk_commit();
             }
           } else if (save != nullptr) {   // (fallback: thread = row, 64 B per store group)
@@ -835,7 +836,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           float4 res[4];
           if (epi & EPI_LDRES) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) res[i] = ldg_f4(a.residual + (size_t)lrow * TC_H + col0 + i * 4);
+            for (int i = 0; i < 4; ++i) res[i] = ldg_f4_hint(a.residual + (size_t)lrow * TC_H + col0 + i * 4, p.pol.ld_stream);
           }
           float acc[16];
           tmem_ld16(xr + c * 16, acc);
@@ -910,9 +911,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              if (epi & EPI_ST_RAW) tma_store_2d(&p.tm_raw, stg, col0, trow);
-              if (epi & EPI_RED_SUM) tma_reduce_add_2d(&p.tm_sum, stg, col0, trow);
-              if (epi & EPI_LDRES) tma_store_2d(&p.tm_sum, stg, col0, trow);
+              if (epi & EPI_ST_RAW) tma_store_2d_hint(&p.tm_raw, stg, col0, trow, p.pol.st_raw);
+              if (epi & EPI_RED_SUM) tma_reduce_add_2d_hint(&p.tm_sum, stg, col0, trow, p.pol.st_out);
+              if (epi & EPI_LDRES) tma_store_2d_hint(&p.tm_sum, stg, col0, trow, p.pol.st_out);
               bulk_commit();
             }
           }
@@ -972,7 +973,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #pragma unroll
             for (int jr = 0; jr < 4; ++jr) {
               const int64_t g = min(row0 + q4 * 32 + jr * 8 + rr, a.rows - 1);
-              res[jr] = ldg_f4(a.residual + (size_t)g * TC_H + col0 + c4 * 4);
+              res[jr] = ldg_f4_hint(a.residual + (size_t)g * TC_H + col0 + c4 * 4, p.pol.ld_stream);
             }
           }
           float acc[16];
@@ -1007,7 +1008,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #endif
               float4 o = lds_f4(stg + (rl * 16 + ((c4 ^ ((rl >> 1) & 3)) << 2)) * 4);
               const size_t off = (size_t)g * TC_H + col0 + c4 * 4;
-              if (a.save_xhat) *reinterpret_cast<float4 *>(a.save_xhat + off) = o;
+              if (a.save_xhat) stg_f4_hint(a.save_xhat + off, o, p.pol.st_stash);
               fma2(o.x, o.y, w4.x, w4.y, g4.x, g4.y);
               fma2(o.z, o.w, w4.z, w4.w, g4.z, g4.w);
               if (a.mul) {
@@ -1016,11 +1017,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
                 else if (a.mul_mode == 2) { m.x = dtanh(m.x); m.y = dtanh(m.y); m.z = dtanh(m.z); m.w = dtanh(m.w); }
                 o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
               }
-              if (a.out_raw) *reinterpret_cast<float4 *>(a.out_raw + off) = o;
+              if (a.out_raw) stg_f4_hint(a.out_raw + off, o, p.pol.st_raw);
               if (a.out_sum) {
                 float4 r4 = res[jr];
                 add2(r4.x, r4.y, o.x, o.y); add2(r4.z, r4.w, o.z, o.w);
-                *reinterpret_cast<float4 *>(a.out_sum + off) = r4;
+                stg_f4_hint(a.out_sum + off, r4, p.pol.st_out);
               }
             }
           }
@@ -1219,6 +1220,7 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   if (!tc_mode(a->precision, m)) { set_error("mlp_forward_tc: bad precision"); return GNNFD_E_BADARG; }
   TcParams p{};
   p.a = *a;
+  p.pol = l2_policies();
   if (tc_geometry(a, m, p) != GNNFD_OK) {
     set_error("mlp_forward_tc: unsupported shape (hidden=%d n_out=%d)", a->hidden, a->n_out);
     return GNNFD_E_UNSUPPORTED;

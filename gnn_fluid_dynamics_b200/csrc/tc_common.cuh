@@ -58,6 +58,9 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16_hint(uint32_t smem_addr, const void *gmem, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gmem), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -150,6 +153,14 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const void *tmap, int 
       "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_gather4_hint(uint32_t dst, const void *tmap, int col, int r0, int r1, int r2, int r3,
+                                                 uint64_t *bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;" ::"r"(dst),
+      "l"(tmap), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
 // shared -> global tile store / reduce-add (fp32 add performed by the memory system), bulk-group completion
 __device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src),
@@ -159,6 +170,18 @@ __device__ __forceinline__ void tma_store_2d(const void *tmap, uint32_t src, int
 __device__ __forceinline__ void tma_reduce_add_2d(const void *tmap, uint32_t src, int c0, int c1) {
   asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
                "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+// the same with an L2 eviction-priority operand (common.cuh: L2_EVICT_*)
+__device__ __forceinline__ void tma_store_2d_hint(const void *tmap, uint32_t src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(tmap),
+               "r"(src), "r"(c0), "r"(c1), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d_hint(const void *tmap, uint32_t src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
+                   tmap),
+               "r"(src), "r"(c0), "r"(c1), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -168,6 +168,13 @@ const char *gnnfd_last_error(void);
  * (its kernels are library launches, src/train.py:253-256). */
 int gnnfd_set_launch_overlap(int32_t on);
 
+/* L2 eviction-priority hints of the streaming kernels (bit mask: 1 = training stash stored evict-first, 2 = residual-stream
+ * outputs stored evict-first, 4 = contiguous operand rows loaded evict-first, 8 = gathered rows loaded evict-last,
+ * 16 = raw outputs stored evict-first; negative = the library's default).  The hint is an operand of the same
+ * instructions, so results are bit-identical under every mask.  Returns the mask in force before the call.
+ * GNNFD_L2_HINTS=<mask> in the environment overrides it for the whole process.  Replaces nothing in the reference. */
+int gnnfd_set_l2_hints(int32_t mask);
+
 /* int64 -> int32 index conversion with range check [0, limit); *err_flag (device int32, caller
  * zeroes it) is set to 1 if any index is out of range.  Replaces nothing in the reference: it is
  * the one-off narrowing of edge_index / face tensors (src/datasets/DataSet.py:212-213 uses long). */
