@@ -32,7 +32,7 @@ EXPORTS = [
     "gnnfd_fvm_integrate_backward", "gnnfd_masked_mse", "gnnfd_masked_mse_backward", "gnnfd_state_advance",
     "gnnfd_affine_columns", "gnnfd_set_launch_overlap", "gnnfd_set_l2_hints",
 ]
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Segment(C.Structure):
@@ -57,6 +57,7 @@ class MlpArgs(C.Structure):
         ("w3_rows", C.c_int32),
         ("peer_base", C.c_void_p * 8), ("peer_shift", C.c_int32),
         ("out_split", C.c_void_p), ("split_of_sum", C.c_int32),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
     ]
 
 

@@ -117,6 +117,18 @@ __device__ __forceinline__ float tanh_fast(float v) {
   return r;
 }
 
+// ---- dropout mask (gnnfd_mlp_args.dropout_p): a counter-based hash of (seed, hidden layer, row, column) --------------
+// lowbias32 integer finaliser; the unit is dropped when dropout_hash(...) < p * 2^32
+__host__ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_layer_key(uint64_t seed, int layer) {
+  return hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) + 0x9E3779B9u * (uint32_t)(layer + 1)));
+}
+__host__ __device__ __forceinline__ uint32_t dropout_row_hash(uint32_t key, uint32_t row) { return hash32(row * 0x9E3779B1u ^ key); }
+__host__ __device__ __forceinline__ uint32_t dropout_hash(uint32_t row_hash, uint32_t col) { return hash32(row_hash + col); }
+
 // GNNFD_SEG_SUM3S index entry -> (row, sign)
 __device__ __forceinline__ void sum3s_decode(int32_t v, int32_t &row, float &sign) {
   const bool zero = v == INT32_MIN;

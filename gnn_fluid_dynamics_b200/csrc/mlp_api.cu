@@ -56,6 +56,10 @@ int validate_mlp_args(const gnnfd_mlp_args *a) {
   if (a->precision == GNNFD_PREC_F32)
     GNNFD_CHECK_ARG(!a->save_a1 && !a->save_a2 && !a->save_rstd && !a->save_xhat && a->mul_mode == 0,
                     "training stashes need a tensor-core precision");
+  GNNFD_CHECK_ARG(a->dropout_p >= 0.f && a->dropout_p < 1.f, "dropout_p must be in [0, 1)");
+  if (a->dropout_p > 0.f)
+    GNNFD_CHECK_ARG(a->precision != GNNFD_PREC_F32 && a->n_layers != 1 && !a->bwd_chain && a->act == GNNFD_ACT_SILU,
+                    "dropout needs the 3-layer SiLU MLP at a tensor-core precision");
   GNNFD_CHECK_ARG(!a->save_xhat || a->n_out == 128, "save_xhat needs n_out == 128");
   GNNFD_CHECK_ARG(!a->out_sum || a->residual, "out_sum requires residual");
   GNNFD_CHECK_ARG(a->out_raw || a->out_sum || a->out_split || a->rows == 0, "no output requested");

@@ -88,6 +88,8 @@ struct KbDesc {
 };
 
 // fast final epilogue (template EPI = 1): what leaves the CTA and how
+// (template EPI = 2: the generic epilogue with training-mode dropout of the hidden activations - its own instantiation so
+//  that the hidden epilogue of every other launch carries no mask code)
 enum {
   EPI_ST_RAW = 1,    // staging = out          -> TMA store to tm_raw
   EPI_RED_SUM = 2,   // staging = out          -> TMA reduce-add into tm_sum (residual == out_sum, updated in place)
@@ -118,6 +120,8 @@ struct TcParams {
   int save_tma;  // the hidden epilogues write their stash through the staging block + TMA tensor stores
   int split_tma; // the split shadow leaves through a SECOND staging block (after the weight rings) + TMA tensor stores
   L2Policies pol;   // L2 eviction-priority operands of the global accesses (common.cuh)
+  uint32_t drop_thresh;    // dropout (template EPI = 2): a hidden unit is dropped when its hash < drop_thresh
+  uint32_t drop_key[2];    // per hidden layer (common.cuh: dropout_layer_key)
 };
 
 // Diagnostic cycle counters of CTA 0 (role wait times), read back with gnnfd_tc_profile_read; only
@@ -748,6 +752,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               add2(v[i], v[i + 1], b4.x, b4.y);
               add2(v[i + 2], v[i + 3], b4.z, b4.w);
             }
+            if constexpr (EPI == 2) {
+              // training-mode dropout: a dropped unit's PRE-activation becomes GNNFD_DROPPED, whose SiLU and SiLU' are
+              // both -0 - the stash written below then carries the mask into the backward kernels
+              const uint32_t rh = dropout_row_hash(p.drop_key[layer], (uint32_t)(row0 + erow));
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (dropout_hash(rh, (uint32_t)(eh * 64 + c * 16 + i)) < p.drop_thresh) v[i] = GNNFD_DROPPED;
+            }
           }
           if (save_tma) {
             // training stash (pre-activation / dA) of this 32 x 16 block: staged in the warp's SWIZZLE_64B block and
@@ -1221,6 +1233,12 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   TcParams p{};
   p.a = *a;
   p.pol = l2_policies();
+  if (a->dropout_p > 0.f) {
+    const double t = (double)a->dropout_p * 4294967296.0;
+    p.drop_thresh = t >= 4294967295.0 ? 4294967295u : (t < 1.0 ? 1u : (uint32_t)t);
+    p.drop_key[0] = dropout_layer_key(a->dropout_seed, 0);
+    p.drop_key[1] = dropout_layer_key(a->dropout_seed, 1);
+  }
   if (tc_geometry(a, m, p) != GNNFD_OK) {
     set_error("mlp_forward_tc: unsupported shape (hidden=%d n_out=%d)", a->hidden, a->n_out);
     return GNNFD_E_UNSUPPORTED;
@@ -1275,6 +1293,7 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   // fast final epilogue (TMA tensor stores) whenever the call is plain inference on 128 outputs
   const bool fast = !a->bwd_chain && p.nl == 3 && a->n_out == TC_H && a->mul == nullptr && a->save_a1 == nullptr &&
                     a->save_a2 == nullptr && a->save_xhat == nullptr && a->save_rstd == nullptr && m.na == 2 && m.nw == 2 &&
+                    a->dropout_p == 0.f &&
                     (a->out_raw != nullptr || a->out_sum != nullptr || a->out_split != nullptr) &&
                     !(a->out_raw != nullptr && a->out_sum != nullptr && (a->residual != a->out_sum || a->split_of_sum)) &&
                     (a->out_sum == nullptr || a->residual != nullptr) &&
@@ -1344,7 +1363,9 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   } while (0)
 #define LAUNCH(FP, NA_, NW_)                                                                              \
   do {                                                                                                    \
-    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true, 0); else LAUNCH1(FP, NA_, NW_, false, 0);               \
+    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true, 0);                                                     \
+    else if (p.drop_thresh != 0u) LAUNCH1(FP, NA_, NW_, false, 2);                                        \
+    else LAUNCH1(FP, NA_, NW_, false, 0);                                                                 \
   } while (0)
   if (p.a_stages == 3) p.w_slots = 2;      // 3 A stages + 3-slot weight rings do not fit in 227 KB
   if (fast && !m.fp16) LAUNCH1(false, 2, 2, false, 1);

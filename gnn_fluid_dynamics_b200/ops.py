@@ -131,6 +131,9 @@ class MLPWeights:
     packed: Optional[torch.Tensor] = None
     packed_prec: int = -1
     bwd_packs: Optional[dict] = None   # dgrad operand packs keyed by (which, col0, precision)
+    # training-mode dropout of the two hidden activations (gnnfd_mlp_args.dropout_p): w2 / w3 above are then the module's
+    # weights ALREADY divided by (1 - drop_p) and mlp_backward scales their gradients by the same factor
+    drop_p: float = 0.0
 
 
 @dataclass
@@ -141,6 +144,12 @@ class MLPStash:
     a2: torch.Tensor
     xhat: Optional[torch.Tensor]
     rstd: Optional[torch.Tensor]
+
+
+def dropout_seed() -> int:
+    """A fresh 63-bit seed from torch's default CPU generator (so ``torch.manual_seed`` makes training runs repeatable);
+    no device synchronisation."""
+    return int(torch.empty((), dtype=torch.int64).random_().item()) & (2 ** 63 - 1)
 
 
 def _fill_args(args: MlpArgs, segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int):
@@ -252,6 +261,8 @@ def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = 
                       rstd=torch.empty(rows, dtype=torch.float32, device=dev) if w.has_ln else None)
         args.save_a1, args.save_a2 = st.a1.data_ptr(), st.a2.data_ptr()
         args.save_xhat, args.save_rstd = _ptr(st.xhat), _ptr(st.rstd)
+    if w.drop_p > 0.0:
+        args.dropout_p, args.dropout_seed = w.drop_p, dropout_seed()
     check(lib.gnnfd_mlp_forward(C.byref(args), _stream()), "gnnfd_mlp_forward")
     _count(1)
     del keep
@@ -369,6 +380,9 @@ def mlp_backward(segs: Sequence[Seg], w: MLPWeights, st: "MLPStash", rows: int, 
     check(lib.gnnfd_mlp_backward(C.byref(b), _stream()), "gnnfd_mlp_backward")
     _count((2 if w.has_ln else 0) + 6 + 2 + sum(1 for d in dins if d is not None))
     del keep
+    if w.drop_p > 0.0:      # w2 / w3 were the module's weights / (1 - p): chain rule of that substitution
+        grads["w2"].mul_(1.0 / (1.0 - w.drop_p))
+        grads["w3"].mul_(1.0 / (1.0 - w.drop_p))
     return grads, dins
 
 

@@ -42,25 +42,34 @@ def _split_mlp(seq: torch.nn.Module):
 
 def weights_of(seq: torch.nn.Module, act: int = ACT_SILU) -> MLPWeights:
     """MLPWeights view of a reference-layout MLP module, cached on the module and refreshed when a
-    parameter is replaced or modified in place (``_version``), e.g. by an optimizer step."""
+    parameter is replaced or modified in place (``_version``), e.g. by an optimizer step.
+
+    ``config.training.dropout_rate > 0`` (Model.py:29-33: a Dropout after each SiLU): in training mode the view carries
+    ``drop_p`` and the second / third Linear's weights divided by (1 - p) - the kernel drops hidden units by replacing
+    their pre-activation (include/gnnfd_b200.h: dropout_p), the rescale of the kept ones is folded into the weights of
+    the layer that consumes them and undone on their gradients by ``ops.mlp_backward``.  In eval mode Dropout is the
+    identity and the view is the plain one."""
     inner, ln = _split_mlp(seq)
-    if seq.training and any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in inner):
-        raise NotImplementedError("training-mode dropout (config.training.dropout_rate > 0, Model.py:29-33) is not implemented "
-                                  "by the fused MLP kernels; eval() / rollout of such a model is supported")
+    drops = [m.p for m in inner if isinstance(m, torch.nn.Dropout)]
+    drop_p = float(drops[0]) if (seq.training and drops and drops[0] > 0) else 0.0
+    if drop_p > 0.0 and (act != ACT_SILU or len(drops) != 2 or drops[1] != drops[0] or drop_p >= 1.0):
+        raise NotImplementedError("training-mode dropout is implemented for the reference's layout only: one Dropout of the "
+                                  "same rate p < 1 after each of the two SiLUs (Model.py:26-35)")
     lin = [m for m in inner if isinstance(m, torch.nn.Linear)]
     params = [lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias]
     if ln is not None:
         params += [ln.weight, ln.bias]
-    key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params)
+    key = tuple((p.data_ptr(), p._version) if p is not None else None for p in params) + (drop_p,)
     cached = getattr(seq, "_gnnfd_w", None)
     if cached is not None and cached[0] == key:
         return cached[1]
     d = lambda p: None if p is None else p.detach()
-    w = MLPWeights(w1=d(lin[0].weight), b1=d(lin[0].bias), w2=d(lin[1].weight), b2=d(lin[1].bias),
-                   w3=d(lin[2].weight), b3=d(lin[2].bias),
+    keep = lambda p: d(p) if drop_p == 0.0 else d(p) / (1.0 - drop_p)
+    w = MLPWeights(w1=d(lin[0].weight), b1=d(lin[0].bias), w2=keep(lin[1].weight), b2=d(lin[1].bias),
+                   w3=keep(lin[2].weight), b3=d(lin[2].bias),
                    ln_w=d(ln.weight) if ln is not None else None,
                    ln_b=d(ln.bias) if ln is not None else None,
-                   has_ln=ln is not None, ln_eps=ln.eps if ln is not None else 1e-5, act=act)
+                   has_ln=ln is not None, ln_eps=ln.eps if ln is not None else 1e-5, act=act, drop_p=drop_p)
     object.__setattr__(seq, "_gnnfd_w", (key, w))
     return w
 
@@ -109,6 +118,8 @@ def fast_mode(blocks, tensors, prec: int) -> bool:
     operands (bf16x3 / fp16x3)."""
     if not FAST_ENABLED or ops.split_dtype(prec) is None:
         return False
+    if blocks.training and any(isinstance(m, torch.nn.Dropout) and m.p > 0 for m in blocks.modules()):
+        return False          # train()-mode forward of a dropout model (even under no_grad): the masking epilogue
     if not torch.is_grad_enabled():
         return True
     return not (any(p.requires_grad for p in blocks.parameters()) or any(t.requires_grad for t in tensors))

@@ -150,6 +150,9 @@ def mlp_backward_stepwise(w: MLPWeights, st: MLPStash, segs: Sequence[Seg], rows
             dins.append(ops.linear_tc(Seg(d_a1), rows, w.w1[:, col0:], 1, k_in, width, H, packs, ("w1t", col0), prec,
                                       residual=spec.get("residual"), out=spec.get("out")))
         col0 += width
+    if w.drop_p > 0.0:      # see ops.mlp_backward
+        grads["w2"].mul_(1.0 / (1.0 - w.drop_p))
+        grads["w3"].mul_(1.0 / (1.0 - w.drop_p))
     return [grads.get(n) for n in PARAM_NAMES], dins
 
 

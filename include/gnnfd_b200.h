@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 4
+#define GNNFD_ABI_VERSION 5
 
 enum {
   GNNFD_OK = 0,
@@ -154,7 +154,19 @@ typedef struct {
    * the TMA store (cp.reduce.async.bulk.tensor .add) in L2 and the residual is never loaded by the SM. */
   void *out_split;
   int32_t split_of_sum;
+  /* ABI v5: training-mode dropout of the two hidden activations (config.training.dropout_rate > 0 puts a Dropout after
+   * each SiLU, src/models/Model.py:29-33).  With 0 < dropout_p < 1 hidden unit (row r, column n) of hidden layer l (0, 1)
+   * is dropped when gnnfd_dropout_hash(dropout_seed, l, r, n) < dropout_p * 2^32 (a counter-based hash, restated in
+   * tests/test_gpu_dropout.py; no generator state on the device).  The kernel replaces a dropped unit's PRE-activation
+   * by GNNFD_DROPPED before the stash and the activation: SiLU(-1e30) = -0 and SiLU'(-1e30) = -0 in the kernels' own
+   * formulas, so save_a1 / save_a2 carry the mask and gnnfd_mlp_backward needs no mask input.  The 1 / (1 - p) rescale
+   * of the kept units is the CALLER's: pass w2 and w3 already divided by (1 - p) - in the forward, the pack and the
+   * backward - and scale d_w2 / d_w3 by 1 / (1 - p) (the chain rule of that substitution).  SiLU MLPs at tensor-core
+   * precisions only; 0 = no dropout (inference, and every shipped config). */
+  float dropout_p;
+  uint64_t dropout_seed;
 } gnnfd_mlp_args;
+#define GNNFD_DROPPED (-1e30f)
 
 int gnnfd_abi_version(void);
 const char *gnnfd_last_error(void);

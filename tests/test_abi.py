@@ -24,7 +24,7 @@ def test_header_symbols_exported():
 
 def test_abi_version_and_struct_layout():
     from gnn_fluid_dynamics_b200 import _lib
-    assert _lib.lib.gnnfd_abi_version() == _lib.ABI_VERSION == 4
+    assert _lib.lib.gnnfd_abi_version() == _lib.ABI_VERSION == 5
     for which, mirror in ((0, _lib.MlpArgs), (1, _lib.WgradArgs), (2, _lib.Segment)):
         assert _lib.lib.gnnfd_struct_size(which) == ctypes.sizeof(mirror)
     # gnnfd_segment: ptr + 3 ptr + 4 int32 + split ptr + int64 src_rows = 64 bytes; args struct must be 8-byte aligned

@@ -1,6 +1,6 @@
 """config.training.dropout_rate > 0 (reference Model.py:29-33): a Dropout follows each SiLU, so the Linear layers sit at
 Sequential indices 0, 3, 6 instead of 0, 2, 4.  The same layout is built here (checkpoints load); eval-mode forwards are
-the dropout-free computation; a training-mode forward raises instead of silently dropping nothing."""
+the dropout-free computation; a training-mode forward drops hidden units (tests/test_gpu_dropout.py)."""
 import re
 from types import SimpleNamespace as NS
 
@@ -43,7 +43,7 @@ def test_state_dict_layout_with_dropout(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["FvgnA", "MgnA"])
-def test_eval_forward_ignores_dropout_and_training_raises(name):
+def test_eval_forward_ignores_dropout_and_training_applies_it(name):
     dev = torch.device("cuda:0")
     plain = build_model(name).to(dev).eval()
     drop = _dropout_model(name).to(dev).eval()
@@ -60,5 +60,6 @@ def test_eval_forward_ignores_dropout_and_training_raises(name):
     for k in a:
         assert torch.equal(a[k], b[k]), k
     drop.train()
-    with pytest.raises(NotImplementedError, match="dropout"):
-        drop([g.clone().to(dev) for g in graphs], mode="train")
+    with torch.no_grad():
+        c = drop([g.clone().to(dev) for g in graphs], mode="rollout")
+    assert any(not torch.equal(a[k], c[k]) for k in a) and all(torch.isfinite(c[k]).all() for k in c)
