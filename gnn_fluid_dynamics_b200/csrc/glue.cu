@@ -176,6 +176,50 @@ __global__ void fvm_integrate_fwd_kernel(const float *eo, int ld, const float *a
   }
 }
 
+// ---------------------------------------------------------------------------------- Flux integrator
+// FluxA's integrator (Flux.py:166-206) on the signed per-cell face flux (face_flux_to_cell_flux, utils/fvm.py:96-156):
+//   s_cj = +1 if c owns face f = cf[j][c], -1 if c is the neighbour of an interior face, else 0;  phi_cj = phi_f s_cj
+//   acc[c] = 1 * (-(sum_j u_f phi_cj k_f) - (sum_j p_f n_cj a_f) / rho) + sum_j d_f
+// eo rows: (u, v, p, phi, d0, d1); k = normalised mean(dt) / face volume (normalize_vol_dt), a = normalised face area.
+// Forward only (evaluation / rollout); every product and sum is separately rounded in the reference's order, so the
+// result equals the tensor expression bit for bit.  cell_flux[c, j] = (phi_f * flux_scale + flux_shift) s_cj (optional).
+__global__ void flux_integrate_fwd_kernel(const float *eo, int ld, int flux_col, const float *coeff, const float *area,
+                                          const float *normal, const int32_t *cf0, const int32_t *cf1, const int32_t *cf2,
+                                          const int32_t *row, const int32_t *col, int64_t N, float inv_rho, float *acc,
+                                          float *cell_flux, float flux_scale, float flux_shift) {
+  pdl_entry();
+  for (int64_t c = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; c < N; c += (int64_t)gridDim.x * GL_THREADS) {
+    float ax = 0.f, ay = 0.f, px = 0.f, py = 0.f, dx = 0.f, dy = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int64_t f = __ldg((j == 0 ? cf0 : j == 1 ? cf1 : cf2) + c);
+      const float *r = eo + f * ld;
+      const int32_t owner = __ldg(row + f), neigh = __ldg(col + f);
+      const bool interior = !(owner == neigh || neigh < 0);
+      const float sg = (int64_t)owner == c ? 1.f : ((interior && (int64_t)neigh == c) ? -1.f : 0.f);
+      const float phi = __ldg(r + flux_col);
+      if (cell_flux != nullptr) cell_flux[3 * c + j] = __fmul_rn(__fadd_rn(__fmul_rn(phi, flux_scale), flux_shift), sg);
+      if (acc != nullptr) {
+        const float cfl = __fmul_rn(phi, sg), k = __ldg(coeff + f), a = __ldg(area + f);
+        const float nx = __ldg(normal + c * 6 + 2 * j), ny = __ldg(normal + c * 6 + 2 * j + 1);
+        const float tx = __fmul_rn(__fmul_rn(__ldg(r), cfl), k), ty = __fmul_rn(__fmul_rn(__ldg(r + 1), cfl), k);
+        const float p = __ldg(r + 2);
+        const float qx = __fmul_rn(__fmul_rn(p, nx), a), qy = __fmul_rn(__fmul_rn(p, ny), a);
+        ax = __fadd_rn(ax, tx); ay = __fadd_rn(ay, ty);
+        px = __fadd_rn(px, qx); py = __fadd_rn(py, qy);
+        const float d0 = __ldg(r + 4), d1 = __ldg(r + 5);
+        dx = j == 0 ? d0 : __fadd_rn(dx, d0);
+        dy = j == 0 ? d1 : __fadd_rn(dy, d1);
+      }
+    }
+    if (acc != nullptr) {
+      // (a tensor divided by a Python scalar is multiplied by the scalar's fp32 reciprocal)
+      acc[2 * c] = __fadd_rn(__fmul_rn(1.0f, __fsub_rn(-ax, __fmul_rn(px, inv_rho))), dx);
+      acc[2 * c + 1] = __fadd_rn(__fmul_rn(1.0f, __fsub_rn(-ay, __fmul_rn(py, inv_rho))), dy);
+    }
+  }
+}
+
 // transpose: one thread per face; its (at most two) cells are c_edge_index[:, f], the slot of f inside a cell is found
 // by comparing the cell's three face ids - a fixed-degree gather, no atomics, fixed order (row cell, then col cell).
 // g_acc [N,2] (may be NULL), g_div [N] (may be NULL) -> d_eo [E, ld_g] (columns 0..4, accumulated or written), d_area [E]
@@ -344,6 +388,21 @@ extern "C" int gnnfd_face_area_norm_backward(const float *area, const float *vol
   if (!split_ws(workspace, workspace_bytes, partials, ticket)) { set_error("gnnfd_face_area_norm_backward: workspace too small"); return GNNFD_E_WORKSPACE; }
   launch_pdl(face_area_bwd_kernel, dim3(gl_blocks(n_faces)), dim3(GL_THREADS), 0, (cudaStream_t)stream, 
       area, volume, row, col, dt, n_dt, n_faces, stats, running_mean, running_var, eps, g, d_weight, d_bias, partials, ticket);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}
+
+extern "C" int gnnfd_flux_integrate(const float *edge_out, int32_t ld, int32_t flux_col, const float *coeff, const float *area,
+                                    const float *normal, const int32_t *cf0, const int32_t *cf1, const int32_t *cf2,
+                                    const int32_t *row, const int32_t *col, int64_t n_cells, float rho, float *acc,
+                                    float *cell_flux, float flux_scale, float flux_shift, void *stream) {
+  GNNFD_CHECK_ARG(n_cells >= 0 && ld >= 1 && flux_col >= 0 && flux_col < ld && rho != 0.f, "bad sizes");
+  if (n_cells == 0) return GNNFD_OK;
+  GNNFD_CHECK_ARG(edge_out && cf0 && cf1 && cf2 && row && col && (acc || cell_flux), "null pointer");
+  GNNFD_CHECK_ARG(acc == nullptr || (ld >= 6 && flux_col == 3 && coeff && area && normal),
+                  "the integrator reads 6 columns (u, v, p, phi, d0, d1) and needs coeff / area / normal");
+  launch_pdl(flux_integrate_fwd_kernel, dim3(gl_blocks(n_cells)), dim3(GL_THREADS), 0, (cudaStream_t)stream, edge_out, ld,
+             flux_col, coeff, area, normal, cf0, cf1, cf2, row, col, n_cells, 1.0f / rho, acc, cell_flux, flux_scale, flux_shift);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

@@ -171,6 +171,40 @@ def fvm_integrate(edge_out: torch.Tensor, area: torch.Tensor, normal: torch.Tens
     return _FvmIntegrate.apply(edge_out, area, normal, cf[0], cf[1], cf[2], row, col, rho, True, False)
 
 
+def flux_integrate(edge_out: torch.Tensor, coeff: Optional[torch.Tensor], area: Optional[torch.Tensor],
+                   normal: Optional[torch.Tensor], cf: Sequence[torch.Tensor], row: torch.Tensor, col: torch.Tensor,
+                   rho: float = 1.0, want_acc: bool = True, want_cell_flux: bool = False, flux_col: int = 3,
+                   flux_scale: float = 1.0, flux_shift: float = 0.0):
+    """FluxA's integrator on the signed per-cell face flux (Flux.py:166-206, fvm.py:96-156) as ONE kernel, forward only:
+    ``edge_out`` rows are (u, v, p, phi, d0, d1); returns acc [N, 2] and / or cell_flux [N, 3] =
+    (edge_out[:, flux_col] * flux_scale + flux_shift)[cf] * sign (see gnnfd_flux_integrate).  Bit-identical to the tensor
+    expression; no autograd (the training path keeps the tensor code)."""
+    if torch.is_grad_enabled() and edge_out.requires_grad:
+        raise RuntimeError("flux_integrate is forward-only (evaluation / rollout)")
+    eo, ld = _rows2d(edge_out, "edge_out")
+    cf = [_i32(t, "cell_face") for t in cf]
+    row, col = _i32(row, "row"), _i32(col, "col")
+    N, dev = cf[0].shape[0], eo.device
+    ptr = lambda t: None if t is None else t.data_ptr()
+    if want_acc:
+        coeff = _f32(coeff, "coeff").reshape(-1).contiguous()
+        area = _f32(area, "face_area").reshape(-1).contiguous()
+        normal = _f32(normal, "cell_normal").contiguous()
+        if normal.dim() != 3 or normal.shape[1:] != (3, 2):
+            raise RuntimeError(f"cell_normal: expected [N, 3, 2], got {tuple(normal.shape)}")
+    acc = torch.empty(N, 2, dtype=torch.float32, device=dev) if want_acc else None
+    cfl = torch.empty(N, 3, dtype=torch.float32, device=dev) if want_cell_flux else None
+    check(lib.gnnfd_flux_integrate(eo.data_ptr(), ld, flux_col, ptr(coeff) if want_acc else None,
+                                   ptr(area) if want_acc else None, ptr(normal) if want_acc else None, cf[0].data_ptr(),
+                                   cf[1].data_ptr(), cf[2].data_ptr(), row.data_ptr(), col.data_ptr(), N, float(rho),
+                                   ptr(acc), ptr(cfl), float(flux_scale), float(flux_shift), ops._stream()),
+          "gnnfd_flux_integrate")
+    ops._count(1)
+    if want_acc and want_cell_flux:
+        return acc, cfl
+    return acc if want_acc else cfl
+
+
 def fvm_divergence(face_velocity: torch.Tensor, area: torch.Tensor, normal: torch.Tensor, cf: Sequence[torch.Tensor],
                    row: torch.Tensor, col: torch.Tensor) -> torch.Tensor:
     """div[c] = sum_j (u_f . n_cj) a_f  -> [N, 1]   (fvm.py:26-37)."""

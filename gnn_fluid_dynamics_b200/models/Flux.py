@@ -10,7 +10,7 @@ from torch import nn
 
 from ..topology import get_topology
 from .base import col, n_class_types
-from .Fvgn import FvgnA, normalize_face_area
+from .Fvgn import FvgnA, graph_topology, normalize_face_area
 
 
 def normalize_vol_dt(cell_volume, edge_index, dt, batch_norm):   # utils/normalisation.py:346-365
@@ -54,16 +54,22 @@ class FluxA(FvgnA):
         c_graph, f_graph, v_graph = graphs
         c_graph.edge_attr = f_graph.x
         topo = get_topology(graphs)
+        c_graph.topology = topo          # the integrator reuses its int32 index tensors
         _, _, edge_attr_out = self.encode_process_decode(c_graph.x, f_graph.x, topo)
         self.dt = c_graph.dt
         acc_pred = self.integrator(edge_attr_out, c_graph, f_graph, self.dt)
         output = [acc_pred, edge_attr_out, None]
         if mode == "rollout":
             output = self.normalizer.output(output, inverse=True)
-        cell_flux = face_flux_to_cell_flux(output[1][:, 3:4], f_graph.face, c_graph.edge_index)
+        if output[1].is_cuda and not (torch.is_grad_enabled() and output[1].requires_grad):
+            from ..fvm_ops import cell_faces, flux_integrate      # one kernel instead of ~15 index / where kernels
+            cell_flux = flux_integrate(output[1], None, None, None, cell_faces(topo, f_graph.face), topo.row, topo.col,
+                                       want_acc=False, want_cell_flux=True, flux_col=3)
+        else:
+            cell_flux = face_flux_to_cell_flux(output[1][:, 3:4], f_graph.face, c_graph.edge_index).squeeze(-1)
         return {"cell_velocity_change": output[0][:, 0:2], "face_velocity": output[1][:, 0:2],
                 "face_pressure": output[1][:, 2:3], "face_flux": output[1][:, 3:4],
-                "cell_flux": cell_flux.squeeze(-1)}
+                "cell_flux": cell_flux}
 
     def loss(self, output, graphs):   # Flux.py:118-155
         c_graph, f_graph, v_graph = graphs
@@ -91,6 +97,16 @@ class FluxA(FvgnA):
 
         def forward(self, edge_output, c_graph, f_graph, dt):
             unv, cf = c_graph.normal, f_graph.face
+            topo = graph_topology(c_graph)
+            if (topo is not None and edge_output.is_cuda and edge_output.shape[1] == 6
+                    and not (torch.is_grad_enabled() and edge_output.requires_grad)):
+                # evaluation / rollout: signs, gathers, products and sums of the expression below as one kernel
+                # (bit-identical: every operation separately rounded in the same order)
+                from ..fvm_ops import cell_faces, flux_integrate
+                coeff = normalize_vol_dt(c_graph.volume, c_graph.edge_index, dt, self.vol_dt_norm)
+                area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, dt, self.face_area_norm, topo=topo)
+                self.face_area = area
+                return flux_integrate(edge_output, coeff, area, unv, cell_faces(topo, cf), topo.row, topo.col, self.rho)
             uv, p_face = edge_output[:, :2], edge_output[:, 2:3]
             flux_face, flux_d = edge_output[:, 3:4], edge_output[:, 4:6]
             cell_flux = face_flux_to_cell_flux(flux_face, cf, c_graph.edge_index)

@@ -18,7 +18,7 @@ from .topology import attach_topology
 
 
 class _FusedStep:
-    """One rollout step of FvgnA / MgnA without the per-step graph clones and per-column (de)normalisation kernels:
+    """One rollout step of FvgnA / MgnA / FluxA without the per-step graph clones and per-column (de)normalisation kernels:
 
       forward on RESIDENT normalised inputs  ->  [integrator]  ->  de-normalise the predicted change (one kernel)  ->
       ``fvm_ops.state_advance`` (two kernels: rollout.py:340 + update_features, Fvgn.py:133-148 / Mgn.py:139-151, + the
@@ -28,7 +28,7 @@ class _FusedStep:
     with a handful of tiny tensor kernels each (~100 launches of a few microseconds per step); here the raw state
     (``c_graph.x``, ``f_graph.x[:, :2]``) and its normalised copy are both kept in HBM and advanced together."""
 
-    KINDS = ("FvgnA", "MgnA")
+    KINDS = ("FvgnA", "MgnA", "FluxA")
 
     @staticmethod
     def supports(model, graphs) -> bool:
@@ -58,7 +58,7 @@ class _FusedStep:
         self.c_norm = gn[0]                       # normals / volumes / dt for the integrator (untouched by the z-scoring)
         self.c_norm.topology = topo
         self.f_static = gn[1]
-        if type(model).__name__ == "FvgnA":
+        if type(model).__name__ in ("FvgnA", "FluxA"):      # FluxA inherits FvgnA.update_features
             mask = ((f.type == NODE_INFLOW) | (f.type == NODE_WALL)).reshape(-1)
         else:
             mask = f.boundary_mask.reshape(-1)
@@ -66,6 +66,19 @@ class _FusedStep:
         self.vel = torch.empty(c.x.shape[0], 2, dtype=torch.float32, device=dev)
         if not (c.x.is_contiguous() and f.x.is_contiguous()):
             c.x, f.x = c.x.contiguous(), f.x.contiguous()
+        if type(model).__name__ == "FluxA":
+            # FluxA's integrator (Flux.py:166-206): the mesh, dt and the evaluation-mode BatchNorm statistics are fixed
+            # over a rollout, so the normalised mean(dt) / face-volume coefficient and the normalised face area are
+            # computed ONCE here; per step the integrator is then one kernel (fvm_ops.flux_integrate)
+            from .fvm_ops import cell_faces
+            from .models.Flux import normalize_vol_dt
+            from .models.Fvgn import normalize_face_area
+            ig = model.integrator
+            with torch.no_grad():
+                self.flux_coeff = normalize_vol_dt(gn[0].volume, gn[0].edge_index, gn[0].dt, ig.vol_dt_norm).reshape(-1).contiguous()
+                self.flux_area = normalize_face_area(gn[1].area, gn[0].volume, gn[0].edge_index, gn[0].dt, ig.face_area_norm,
+                                                     topo=topo).reshape(-1).contiguous()
+            self.flux_cf = cell_faces(topo, gn[1].face)
 
     @torch.no_grad()
     def step(self) -> torch.Tensor:
@@ -75,6 +88,9 @@ class _FusedStep:
         if type(model).__name__ == "FvgnA":
             self.c_norm.x = self.x_norm
             change = model.integrator(dec, self.c_norm, self.f_static, self.c_norm.dt)      # normalised change [N, 2]
+        elif type(model).__name__ == "FluxA":
+            change = fvm_ops.flux_integrate(dec, self.flux_coeff, self.flux_area, self.c_norm.normal, self.flux_cf,
+                                            topo.row, topo.col, model.integrator.rho)
         else:
             change = dec[:, 0:2]
         delta = torch.addcmul(self.out_mean, change, self.out_scale)                       # normalizer.output(inverse)

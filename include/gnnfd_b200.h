@@ -370,6 +370,18 @@ int gnnfd_face_area_norm_backward(const float *area, const float *volume, const 
 int gnnfd_fvm_integrate(const float *edge_out, int32_t ld, const float *area, const float *normal, const int32_t *cf0,
                         const int32_t *cf1, const int32_t *cf2, int64_t n_cells, float rho, float *acc, float *div,
                         void *stream);
+/* FluxA's integrator, src/models/Flux.py:166-206, on the signed per-cell face flux of face_flux_to_cell_flux,
+ * src/utils/fvm.py:96-156 (forward only: evaluation / rollout).  edge_out rows (stride ld) = (u, v, p, phi, d0, d1);
+ * row / col = c_graph.edge_index (owner, neighbour; a boundary face is a self-loop or has neighbour -1);
+ * coeff = normalize_vol_dt(...) [E], area = normalize_face_area(...) [E] (both static over a rollout).
+ *   s_cj = +1 if c == row[f], -1 if f is interior and c == col[f], else 0      (f = cf_j[c])
+ *   acc[c] = 1 * (-(sum_j (u, v)_f (phi_f s_cj) coeff_f) - (sum_j p_f n_cj area_f) / rho) + sum_j (d0, d1)_f   (may be NULL)
+ *   cell_flux[c, j] = (edge_out[f, flux_col] * flux_scale + flux_shift) s_cj                                    (may be NULL)
+ * Rounded operation by operation in the reference's order: bit-identical to the tensor expression. */
+int gnnfd_flux_integrate(const float *edge_out, int32_t ld, int32_t flux_col, const float *coeff, const float *area,
+                         const float *normal, const int32_t *cf0, const int32_t *cf1, const int32_t *cf2,
+                         const int32_t *row, const int32_t *col, int64_t n_cells, float rho, float *acc, float *cell_flux,
+                         float flux_scale, float flux_shift, void *stream);
 /* transpose: one thread per face gathers from its (at most two) cells row[f], col[f]; n_cols = 5 with g_acc (all of
  * u, v, p, d0, d1), 2 with g_div only; d_area[f] = gradient w.r.t. the normalised face area. */
 int gnnfd_fvm_integrate_backward(const float *edge_out, int32_t ld, const float *area, const float *normal,

@@ -12,7 +12,10 @@ from gnn_fluid_dynamics_b200.topology import get_topology
 dev = torch.device("cuda:0")
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 model = build_model("FvgnA", precision=prec).to(dev).eval()
-g = collate_triplet([mesh_graphs(make_mesh(20000, "cylinder", seed=i), seed=i) for i in range(8)])
+# optional: cells per mesh, number of meshes (default = the bench shape; "2000 1" = the launch-bound 2k-cell rollout shape)
+n_cells = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
+n_meshes = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+g = collate_triplet([mesh_graphs(make_mesh(n_cells, "cylinder", seed=i), seed=i) for i in range(n_meshes)])
 gd = [x.to(dev) for x in g]
 topo = get_topology(gd).validate()
 N, E = gd[0].x.shape[0], gd[0].edge_index.shape[1]

@@ -143,3 +143,65 @@ def test_fused_normaliser_is_bit_identical_to_the_tensor_expressions(name):
     for a, b in zip(ref_o, got_o):
         if a is not None:
             assert torch.equal(a, b.cpu())
+
+
+def test_flux_integrate_is_bit_identical_to_the_tensor_expression():
+    """FluxA's integrator (Flux.py:166-206) and face_flux_to_cell_flux (fvm.py:96-156) as one kernel
+    (gnnfd_flux_integrate) against the tensor expressions of models/Flux.py evaluated on the SAME device, bit for bit:
+    the kernel rounds every product and sum separately, in the expression's order."""
+    from gnn_fluid_dynamics_b200 import fvm_ops
+    from gnn_fluid_dynamics_b200.models.Flux import face_flux_to_cell_flux
+    graphs, gd, topo = _setup(n_cells=900, flip=True)
+    c, f, _ = gd
+    gen = torch.Generator().manual_seed(9)
+    E, N = f.area.shape[0], c.x.shape[0]
+    eo = torch.randn(E, 6, generator=gen).to(dev())
+    coeff = torch.randn(E, 1, generator=gen).to(dev())
+    area = torch.randn(E, 1, generator=gen).to(dev())
+    unv, cf = c.normal, f.face
+    rho = 1.3
+    cell_flux = face_flux_to_cell_flux(eo[:, 3:4], cf, c.edge_index)
+    uv, p_face, flux_d = eo[:, :2], eo[:, 2:3], eo[:, 4:6]
+    phi_a = sum(uv[cf[j]] * cell_flux[:, j] * coeff[cf[j]] for j in range(3))
+    phi_d = flux_d[cf[0], :] + flux_d[cf[1], :] + flux_d[cf[2], :]
+    phi_p = sum(p_face[cf[j]] * unv[:, j, :] * area[cf[j]] for j in range(3))
+    ref = 1.0 * (-phi_a - phi_p / rho) + phi_d
+    cfs = fvm_ops.cell_faces(topo, cf)
+    acc, cfl = fvm_ops.flux_integrate(eo, coeff, area, unv, cfs, topo.row, topo.col, rho, want_cell_flux=True)
+    assert torch.equal(acc, ref)
+    assert torch.equal(cfl, cell_flux.squeeze(-1))
+    # boundary faces are self-loops: the owner keeps +1, nobody gets -1
+    boundary = (c.edge_index[0] == c.edge_index[1])
+    assert bool(boundary.any())
+    # de-normalised flux column of a wider matrix, cell flux only
+    wide = torch.randn(E, 9, generator=gen).to(dev())
+    got = fvm_ops.flux_integrate(wide, None, None, None, cfs, topo.row, topo.col, want_acc=False, want_cell_flux=True,
+                                 flux_col=7, flux_scale=2.5, flux_shift=-0.75)
+    assert torch.equal(got, face_flux_to_cell_flux(wide[:, 7:8] * 2.5 + (-0.75), cf, c.edge_index).squeeze(-1))
+
+
+def test_flux_model_forward_with_the_kernel_equals_the_tensor_path():
+    """FluxA.forward in evaluation mode (kernel integrator + kernel cell flux) == the same forward with the topology hidden
+    from the integrator (tensor expressions): the face outputs and the cell flux bit for bit, the integrated change to
+    1e-6 (with the topology hidden the face-area BatchNorm is ATen's, not fvm_ops.face_area_norm: last-bit differences)."""
+    from helpers import build_model
+    from gnn_fluid_dynamics_b200.models import Flux
+    model = build_model("FluxA").to(dev()).eval()
+    _, graphs = golden_graphs("FluxA", n_cells=800, mesh_seed=15, feat_seed=16)
+    with torch.no_grad():
+        a = model([g.clone().to(dev()) for g in graphs], mode="rollout")
+        orig_topo, orig_ops = Flux.graph_topology, None
+        Flux.graph_topology = lambda c_graph: None            # integrator -> tensor expressions
+        try:
+            b = model([g.clone().to(dev()) for g in graphs], mode="rollout")
+        finally:
+            Flux.graph_topology = orig_topo
+    assert set(a) == set(b)
+    for k in a:
+        if k == "cell_flux":
+            ref = Flux.face_flux_to_cell_flux(b["face_flux"], graphs[1].face.to(dev()), graphs[0].edge_index.to(dev()))
+            assert torch.equal(a[k], ref.squeeze(-1))
+        if k == "cell_velocity_change":
+            assert rel_l2(a[k], b[k]) < 1e-6, rel_l2(a[k], b[k])
+        else:
+            assert torch.equal(a[k], b[k]), k
