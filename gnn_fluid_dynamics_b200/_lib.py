@@ -57,7 +57,7 @@ class MlpArgs(C.Structure):
         ("w3_rows", C.c_int32),
         ("peer_base", C.c_void_p * 8), ("peer_shift", C.c_int32),
         ("out_split", C.c_void_p), ("split_of_sum", C.c_int32),
-        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_uint64), ("static_operands", C.c_int32),
     ]
 
 

@@ -349,7 +349,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   }
   // programmatic dependent launch (common.cuh): everything above is on-chip set-up that may run under the previous
   // kernel's tail; from here on global memory is read
-  pdl_wait();
+  // (static_operands: the weights, the bias / LayerNorm vectors and the gather indices were produced long before this
+  //  launch, so they too are fetched under the previous kernel's tail and only the roles that touch activations wait)
+  const bool early = !BWD && a.static_operands != 0;
+  if (!early) pdl_wait();
   for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
     const int v = i / TC_H, c = i % TC_H;
     const float *src = v == 0 ? a.b1 : v == 1 ? a.b2 : v == 2 ? (p.nl == 1 ? a.b1 : a.b3) : v == 3 ? a.ln_w : a.ln_b;
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       // are still resident when read (three tiles ahead, the whole grid streams more than the L2 holds in
       // between and every prefetched line was fetched from DRAM twice - ncu dram__bytes_read)
       const int jp = j - 2;
-      if (jp >= 0 && jp < T) {
+      if (jp >= 0 && jp < T && !(early && j < 3)) {      // (the first three calls run before griddepcontrol.wait)
         const int64_t prow0 = tile_row0(jp);
         const int64_t nrow = min((int64_t)TC_BM, a.rows - prow0);
         if (pt == 0 && p.direct_tile_bytes > 0)
@@ -491,6 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     for (int i = 0; i < 8; ++i) v0[i] = make_float4(1.f, 2.f, 3.f, 4.f);
 #endif
     stage_idx(0); stage_idx(1); stage_idx(2);
+    if (early) pdl_wait();      // from here on the segment sources are read
     cp_async_wait_all();
     named_bar_sync(1, TC_PROD_THREADS);
     issue(v0);
@@ -667,6 +671,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
     // group; half eh of a hidden layer's output is exactly k-block eh of the next layer's operand.  All TMEM traffic is
     // in 16-column groups: 16 fp32 accumulator columns are replaced in place by 8 columns of hi pairs + 8 of lo pairs.
     if (BWD || (EPI == 1 && p.n_tma > 0)) asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
+    if (early) pdl_wait();      // residual / mul loads and every store of this role follow
     const int grp = warp >> 3, q4 = warp & 3, eh = (warp >> 2) & 1;
     const int erow = q4 * 32 + lane;                       // row of the tile owned by this thread
     const uint32_t stg = smem_u32(s_stg + warp * (32 * 16));   // this warp's 32 x 16 staging block (XOR-swizzled)

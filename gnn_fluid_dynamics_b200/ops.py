@@ -5,6 +5,8 @@ PyTorch is plumbing here (device memory, the current stream); all arithmetic hap
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple
@@ -146,6 +148,9 @@ class MLPStash:
     rstd: Optional[torch.Tensor]
 
 
+STATIC_OPERANDS = os.environ.get("GNNFD_STATIC_OPERANDS", "1") != "0"      # A/B knob of the early operand fetch
+
+
 def dropout_seed() -> int:
     """A fresh 63-bit seed from torch's default CPU generator (so ``torch.manual_seed`` makes training runs repeatable);
     no device synchronisation."""
@@ -226,9 +231,15 @@ def mlp_forward(segs: Sequence[Seg], w: MLPWeights, rows: int, precision: int = 
     n_out = w.w3.shape[0]
     dev = w.w1.device
     if precision != _lib.PREC_F32:
-        if w.packed is None or w.packed_prec != precision:
+        packed_now = w.packed is None or w.packed_prec != precision
+        if packed_now:
             pack_mlp(w, precision)
         args.packed = w.packed.data_ptr()
+        # Inside a CUDA-graph capture, operands produced BEFORE the capture (the pack of an earlier call, the parameters,
+        # the topology's index arrays) cannot be written by anything in flight when the replayed launch starts: the kernel
+        # may fetch them ahead of griddepcontrol.wait (gnnfd_mlp_args.static_operands; inference launches only)
+        args.static_operands = int(STATIC_OPERANDS and not packed_now and not stash and not torch.is_grad_enabled()
+                                   and torch.cuda.is_current_stream_capturing())
     if want_raw and out_raw is None:
         out_raw = torch.empty(rows, n_out, dtype=torch.float32, device=dev)
     if want_sum:

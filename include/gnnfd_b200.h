@@ -165,6 +165,13 @@ typedef struct {
    * precisions only; 0 = no dropout (inference, and every shipped config). */
   float dropout_p;
   uint64_t dropout_seed;
+  /* ABI v5: static_operands = 1 promises that the operand pack (`packed`), the bias / LayerNorm vectors and the gather
+   * index arrays are NOT written by any kernel that can still be in flight when this one starts (e.g. they were produced
+   * before the CUDA graph this launch is captured in).  With programmatic dependent launch (gnnfd_set_launch_overlap) the
+   * kernel then streams its weights, loads those vectors and stages the first tiles' indices BEFORE griddepcontrol.wait,
+   * i.e. under the previous kernel's tail; everything the previous kernels produce (segment sources, residual, mul) is
+   * still read after the wait.  Results are identical; forward / inference launches only (ignored with bwd_chain). */
+  int32_t static_operands;
 } gnnfd_mlp_args;
 #define GNNFD_DROPPED (-1e30f)
 
