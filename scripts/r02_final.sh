@@ -1,6 +1,6 @@
 #!/bin/bash
 # Final round-2 measurement pass on one B200 (through gpurun): tests, driver-style bench lines, kernel timings, ncu passes.
-O=gpurun_out/r02_final; mkdir -p $O
+O=gpurun_out/${OUT:-r02_final}; mkdir -p $O
 timeout 1500 python -m pytest tests -q -m gpu > $O/pytest_gpu.log 2>&1; tail -2 $O/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/smoke.log 2>&1; tail -1 $O/smoke.log
 ( time timeout 900 python bench.py > $O/bench_default.json 2> $O/bench_default.err ) 2> $O/bench_default.time; tail -3 $O/bench_default.time; python scripts/print_bench.py $O/bench_default.json
