@@ -359,6 +359,13 @@ def main():
     launches = ops.LAUNCHES
     ms = sum(s.elapsed_time(e) for s, e in ev) / args.steps
     clocks = sampler.stop()
+    if os.environ.get("GNNFD_BENCH_PROFILE_STEP") and rank == 0:
+        # diagnostic (never part of a reported number): one more step under torch.profiler, top operators by device time
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step_resident()
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70), file=sys.stderr)
 
     # forward-only time of the same batch (reported next to the training number)
     fwd_ms = None

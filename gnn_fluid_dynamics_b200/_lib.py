@@ -30,7 +30,7 @@ EXPORTS = [
     "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access", "gnnfd_gather_cols_add",
     "gnnfd_glue_workspace_bytes", "gnnfd_face_area_norm", "gnnfd_face_area_norm_backward", "gnnfd_fvm_integrate",
     "gnnfd_fvm_integrate_backward", "gnnfd_masked_mse", "gnnfd_masked_mse_backward", "gnnfd_state_advance",
-    "gnnfd_affine_columns", "gnnfd_set_launch_overlap", "gnnfd_set_l2_hints", "gnnfd_flux_integrate",
+    "gnnfd_affine_columns", "gnnfd_set_launch_overlap", "gnnfd_set_l2_hints", "gnnfd_flux_integrate", "gnnfd_gather3", "gnnfd_gather3_backward",
 ]
 ABI_VERSION = 5
 
@@ -132,6 +132,8 @@ def _load():
     lib.gnnfd_glue_workspace_bytes.restype = sz
     lib.gnnfd_face_area_norm.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, i32, f32, f32, i32, vp, vp, vp, sz, vp]
     lib.gnnfd_face_area_norm_backward.argtypes = [vp, vp, vp, vp, vp, i32, i64, vp, vp, vp, f32, vp, vp, vp, vp, sz, vp]
+    lib.gnnfd_gather3.argtypes = [vp, i32, i32, vp, vp, vp, i64, vp, vp]
+    lib.gnnfd_gather3_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, i64, vp, i32, vp]
     lib.gnnfd_flux_integrate.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, f32, vp, vp, f32, f32, vp]
     lib.gnnfd_fvm_integrate.argtypes = [vp, i32, vp, vp, vp, vp, vp, i64, f32, vp, vp, vp]
     lib.gnnfd_fvm_integrate_backward.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, f32, vp, vp, vp, i32, i32, vp, vp]

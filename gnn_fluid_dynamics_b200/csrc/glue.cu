@@ -176,6 +176,49 @@ __global__ void fvm_integrate_fwd_kernel(const float *eo, int ld, const float *a
   }
 }
 
+// ------------------------------------------------------------------------------------- face gather
+// out[j][c][:] = t[cf_j[c]][0:w]: the three `t[f_graph.face[j]]` gathers every integrator / divergence of the model
+// zoo starts with (Fvgn.py:232-246, Flux.py:186-203, VertPot.py:128-146, Conservative.py:..., fvm.py:26-37) as one launch.
+__global__ void gather3_fwd_kernel(const float *t, int ld, int w, const int32_t *cf0, const int32_t *cf1,
+                                   const int32_t *cf2, int64_t N, float *out) {
+  pdl_entry();
+  const int64_t total = 3 * N;
+  for (int64_t i = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * GL_THREADS) {
+    const int j = (int)(i / N);
+    const int64_t c = i - (int64_t)j * N;
+    const int64_t f = __ldg((j == 0 ? cf0 : j == 1 ? cf1 : cf2) + c);
+    const float *r = t + f * ld;
+    float *o = out + i * w;
+    for (int k = 0; k < w; ++k) o[k] = __ldg(r + k);
+  }
+}
+// transpose (autograd of the gather): one thread per face adds the gradients of the slots that gathered it - its (at most
+// two) cells row[f], col[f], slot found by comparing the cell's three face ids; fixed order (row cell first, slots
+// ascending), no atomics, no sort: d_t[f][0:w] = sum_{(c, j): cf_j[c] = f} g[j][c][0:w]
+__global__ void gather3_bwd_kernel(const float *g, int w, const int32_t *cf0, const int32_t *cf1, const int32_t *cf2,
+                                   const int32_t *row, const int32_t *col, int64_t N, int64_t E, float *d_t, int ld_d) {
+  pdl_entry();
+  for (int64_t f = (int64_t)blockIdx.x * GL_THREADS + threadIdx.x; f < E; f += (int64_t)gridDim.x * GL_THREADS) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int32_t c0 = __ldg(row + f), c1 = __ldg(col + f);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int32_t c = s == 0 ? c0 : c1;
+      if (s == 1 && c1 == c0) break;                     // boundary face: self-loop, one cell
+      if (c < 0) continue;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        if (__ldg((j == 0 ? cf0 : j == 1 ? cf1 : cf2) + c) == (int32_t)f) {
+          const float *r = g + ((int64_t)j * N + c) * w;
+          for (int k = 0; k < w; ++k) acc[k] += __ldg(r + k);
+        }
+      }
+    }
+    float *o = d_t + f * ld_d;
+    for (int k = 0; k < w; ++k) o[k] = acc[k];
+  }
+}
+
 // ---------------------------------------------------------------------------------- Flux integrator
 // FluxA's integrator (Flux.py:166-206) on the signed per-cell face flux (face_flux_to_cell_flux, utils/fvm.py:96-156):
 //   s_cj = +1 if c owns face f = cf[j][c], -1 if c is the neighbour of an interior face, else 0;  phi_cj = phi_f s_cj
@@ -388,6 +431,29 @@ extern "C" int gnnfd_face_area_norm_backward(const float *area, const float *vol
   if (!split_ws(workspace, workspace_bytes, partials, ticket)) { set_error("gnnfd_face_area_norm_backward: workspace too small"); return GNNFD_E_WORKSPACE; }
   launch_pdl(face_area_bwd_kernel, dim3(gl_blocks(n_faces)), dim3(GL_THREADS), 0, (cudaStream_t)stream, 
       area, volume, row, col, dt, n_dt, n_faces, stats, running_mean, running_var, eps, g, d_weight, d_bias, partials, ticket);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}
+
+extern "C" int gnnfd_gather3(const float *t, int32_t ld, int32_t width, const int32_t *cf0, const int32_t *cf1,
+                             const int32_t *cf2, int64_t n_cells, float *out, void *stream) {
+  GNNFD_CHECK_ARG(n_cells >= 0 && width >= 1 && width <= 8 && ld >= width, "bad sizes (width 1..8)");
+  if (n_cells == 0) return GNNFD_OK;
+  GNNFD_CHECK_ARG(t && cf0 && cf1 && cf2 && out, "null pointer");
+  launch_pdl(gather3_fwd_kernel, dim3(gl_blocks(3 * n_cells)), dim3(GL_THREADS), 0, (cudaStream_t)stream, t, ld, width, cf0,
+             cf1, cf2, n_cells, out);
+  GNNFD_LAUNCH_CHECK();
+  return GNNFD_OK;
+}
+
+extern "C" int gnnfd_gather3_backward(const float *g, int32_t width, const int32_t *cf0, const int32_t *cf1,
+                                      const int32_t *cf2, const int32_t *row, const int32_t *col, int64_t n_cells,
+                                      int64_t n_faces, float *d_t, int32_t ld_d, void *stream) {
+  GNNFD_CHECK_ARG(n_cells >= 0 && n_faces >= 0 && width >= 1 && width <= 8 && ld_d >= width, "bad sizes (width 1..8)");
+  if (n_faces == 0) return GNNFD_OK;
+  GNNFD_CHECK_ARG(g && cf0 && cf1 && cf2 && row && col && d_t, "null pointer");
+  launch_pdl(gather3_bwd_kernel, dim3(gl_blocks(n_faces)), dim3(GL_THREADS), 0, (cudaStream_t)stream, g, width, cf0, cf1,
+             cf2, row, col, n_cells, n_faces, d_t, ld_d);
   GNNFD_LAUNCH_CHECK();
   return GNNFD_OK;
 }

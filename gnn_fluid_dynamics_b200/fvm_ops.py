@@ -171,6 +171,42 @@ def fvm_integrate(edge_out: torch.Tensor, area: torch.Tensor, normal: torch.Tens
     return _FvmIntegrate.apply(edge_out, area, normal, cf[0], cf[1], cf[2], row, col, rho, True, False)
 
 
+class _Gather3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t, cf0, cf1, cf2, row, col):
+        t2, ld = _rows2d(t, "t")
+        N, w = cf0.shape[0], t2.shape[1]
+        out = torch.empty(3, N, w, dtype=torch.float32, device=t2.device)
+        check(lib.gnnfd_gather3(t2.data_ptr(), ld, w, cf0.data_ptr(), cf1.data_ptr(), cf2.data_ptr(), N, out.data_ptr(),
+                                ops._stream()), "gnnfd_gather3")
+        ops._count(1)
+        ctx.save_for_backward(cf0, cf1, cf2, row, col)
+        ctx.shape = tuple(t.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        cf0, cf1, cf2, row, col = ctx.saved_tensors
+        g = g.contiguous()
+        N, w = g.shape[1], g.shape[2]
+        E = ctx.shape[0]
+        d = torch.empty(E, w, dtype=torch.float32, device=g.device)
+        check(lib.gnnfd_gather3_backward(g.data_ptr(), w, cf0.data_ptr(), cf1.data_ptr(), cf2.data_ptr(), row.data_ptr(),
+                                         col.data_ptr(), N, E, d.data_ptr(), w, ops._stream()), "gnnfd_gather3_backward")
+        ops._count(1)
+        return d.view(ctx.shape), None, None, None, None, None
+
+
+def gather3(t: torch.Tensor, cf: Sequence[torch.Tensor], row: torch.Tensor, col: torch.Tensor) -> torch.Tensor:
+    """``stack([t[cf[0]], t[cf[1]], t[cf[2]]])`` -> [3, N, w] for a per-face matrix ``t`` [E, w] (w <= 8): the three
+    ``x[f_graph.face[j]]`` gathers of the integrators / divergences as ONE kernel whose autograd is a fixed-degree,
+    sort-free transpose (each face collects from its <= 2 cells ``row[f]``, ``col[f]``); see gnnfd_gather3."""
+    if t.dim() != 2 or t.shape[1] > 8:
+        raise RuntimeError(f"gather3: expected [E, w <= 8], got {tuple(t.shape)}")
+    cf = [_i32(x, "cell_face") for x in cf]
+    return _Gather3.apply(_f32(t, "t"), cf[0], cf[1], cf[2], _i32(row, "row"), _i32(col, "col"))
+
+
 def flux_integrate(edge_out: torch.Tensor, coeff: Optional[torch.Tensor], area: Optional[torch.Tensor],
                    normal: Optional[torch.Tensor], cf: Sequence[torch.Tensor], row: torch.Tensor, col: torch.Tensor,
                    rho: float = 1.0, want_acc: bool = True, want_cell_flux: bool = False, flux_col: int = 3,

@@ -12,7 +12,10 @@ from .. import processor as P
 from ..topology import get_topology
 from .base import build_mlp, col, n_class_types
 from .Flux import FluxA, FluxC, cell_to_face, normalize_vol_dt
-from .Fvgn import FvgnA, calc_gradient_tensor, flux_dot, normalize_face_area
+from .Fvgn import FvgnA, calc_gradient_tensor, flux_dot, graph_topology, normalize_face_area
+
+import os
+USE_GATHER3 = os.environ.get("GNNFD_GATHER3", "1") != "0"      # A/B knob
 
 
 def cell_flux_from_vertices(vertex_out, v_face):
@@ -83,6 +86,7 @@ class VertPotA(FluxA):
         c_graph, f_graph, v_graph = graphs
         c_graph.edge_attr = f_graph.x
         topo = get_topology(graphs)
+        c_graph.topology = topo          # the integrator reuses its int32 index tensors
         _, _, _, edge_attr_out, vertex_out = self.encode_process_decode(c_graph.x, f_graph.x, topo)
         cell_flux = cell_flux_from_vertices(vertex_out, v_graph.face)
         self.dt = c_graph.dt
@@ -104,6 +108,22 @@ class VertPotA(FluxA):
         def forward(self, output, c_graph, f_graph, dt):
             unv, cf = c_graph.normal, f_graph.face
             cell_flux, edge_output = output
+            topo = graph_topology(c_graph)
+            if topo is not None and edge_output.is_cuda and edge_output.shape[1] == 5 and USE_GATHER3:
+                # the fifteen x[cf[j]] gathers of the expression below as two gather3 launches (rows of edge_output; the
+                # coefficient / area pair), whose autograd is a fixed-degree sort-free transpose instead of index_put; the
+                # arithmetic is the same tensor expression in the same order
+                from ..fvm_ops import cell_faces, gather3
+                cfs = cell_faces(topo, cf)
+                coeff = normalize_vol_dt(c_graph.volume, c_graph.edge_index, dt, self.vol_dt_norm, topo=topo)
+                area = normalize_face_area(f_graph.area, c_graph.volume, c_graph.edge_index, dt, self.face_area_norm, topo=topo)
+                self.face_area = area
+                eo = gather3(edge_output, cfs, topo.row, topo.col)                              # [3, N, (u, v, p, d0, d1)]
+                ka = gather3(torch.cat([coeff, area], dim=1), cfs, topo.row, topo.col)          # [3, N, (coeff, area)]
+                phi_a = sum(eo[j][:, 0:2] * cell_flux[:, j:j + 1] * ka[j][:, 0:1] for j in range(3))
+                phi_d = eo[0][:, 3:5] + eo[1][:, 3:5] + eo[2][:, 3:5]
+                phi_p = sum(eo[j][:, 2:3] * unv[:, j, :] * ka[j][:, 1:2] for j in range(3))
+                return 1.0 * (-phi_a - phi_p / self.rho) + phi_d
             uv, p_face, flux_d = edge_output[:, 0:2], edge_output[:, 2:3], edge_output[:, 3:5]
             coeff = normalize_vol_dt(c_graph.volume, c_graph.edge_index, dt, self.vol_dt_norm)
             phi_a = sum(uv[cf[j]] * cell_flux[:, j:j + 1] * coeff[cf[j]] for j in range(3))

@@ -75,7 +75,7 @@ class _FusedStep:
             from .models.Fvgn import normalize_face_area
             ig = model.integrator
             with torch.no_grad():
-                self.flux_coeff = normalize_vol_dt(gn[0].volume, gn[0].edge_index, gn[0].dt, ig.vol_dt_norm).reshape(-1).contiguous()
+                self.flux_coeff = normalize_vol_dt(gn[0].volume, gn[0].edge_index, gn[0].dt, ig.vol_dt_norm, topo=topo).reshape(-1).contiguous()
                 self.flux_area = normalize_face_area(gn[1].area, gn[0].volume, gn[0].edge_index, gn[0].dt, ig.face_area_norm,
                                                      topo=topo).reshape(-1).contiguous()
             self.flux_cf = cell_faces(topo, gn[1].face)

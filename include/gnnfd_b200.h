@@ -377,6 +377,18 @@ int gnnfd_face_area_norm_backward(const float *area, const float *volume, const 
 int gnnfd_fvm_integrate(const float *edge_out, int32_t ld, const float *area, const float *normal, const int32_t *cf0,
                         const int32_t *cf1, const int32_t *cf2, int64_t n_cells, float rho, float *acc, float *div,
                         void *stream);
+/* out[j][c][0:width] = t[cf_j[c]][0:width], j = 0..2: the three `x[f_graph.face[j]]` gathers that every integrator /
+ * divergence of the model zoo starts with (src/models/Fvgn.py:232-246, Flux.py:186-203, VertPot.py:128-146,
+ * src/utils/fvm.py:26-37) as one launch; out is [3, n_cells, width] contiguous, width <= 8.  The backward replaces
+ * autograd's sort-based index_put: one thread per face adds the gradients of the (cell, slot) pairs that gathered it - its
+ * at most two cells row[f], col[f] (c_graph.edge_index) - in a fixed order, no atomics:
+ *   d_t[f][0:width] = sum_{(c, j): cf_j[c] = f} g[j][c][0:width]     (every face row is written; ld_d = row stride of d_t) */
+int gnnfd_gather3(const float *t, int32_t ld, int32_t width, const int32_t *cf0, const int32_t *cf1, const int32_t *cf2,
+                  int64_t n_cells, float *out, void *stream);
+int gnnfd_gather3_backward(const float *g, int32_t width, const int32_t *cf0, const int32_t *cf1, const int32_t *cf2,
+                           const int32_t *row, const int32_t *col, int64_t n_cells, int64_t n_faces, float *d_t,
+                           int32_t ld_d, void *stream);
+
 /* FluxA's integrator, src/models/Flux.py:166-206, on the signed per-cell face flux of face_flux_to_cell_flux,
  * src/utils/fvm.py:96-156 (forward only: evaluation / rollout).  edge_out rows (stride ld) = (u, v, p, phi, d0, d1);
  * row / col = c_graph.edge_index (owner, neighbour; a boundary face is a self-loop or has neighbour -1);

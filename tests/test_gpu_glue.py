@@ -205,3 +205,27 @@ def test_flux_model_forward_with_the_kernel_equals_the_tensor_path():
             assert rel_l2(a[k], b[k]) < 1e-6, rel_l2(a[k], b[k])
         else:
             assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("width", [1, 2, 5, 8])
+def test_gather3_forward_bitwise_and_backward_vs_index_put(width):
+    """gnnfd_gather3: the three x[f_graph.face[j]] gathers as one launch (bit-identical to indexing) and its sort-free
+    transpose against autograd's index_put backward (same sums, possibly another order: 1e-6)."""
+    from gnn_fluid_dynamics_b200 import fvm_ops
+    graphs, gd, topo = _setup(n_cells=1100, flip=True)
+    c, f, _ = gd
+    gen = torch.Generator().manual_seed(13)
+    E, N = f.area.shape[0], c.x.shape[0]
+    wide = torch.randn(E, width + 3, generator=gen).to(dev())
+    t = wide[:, 1:1 + width].detach().requires_grad_(True)          # a column slice of a wider matrix
+    t_ref = t.detach().clone().requires_grad_(True)
+    cf = f.face
+    out = fvm_ops.gather3(t, fvm_ops.cell_faces(topo, cf), topo.row, topo.col)
+    ref = torch.stack([t_ref[cf[0]], t_ref[cf[1]], t_ref[cf[2]]])
+    assert out.shape == (3, N, width) and torch.equal(out, ref)
+    g = torch.randn(3, N, width, generator=gen).to(dev())
+    (out * g).sum().backward()
+    (ref * g).sum().backward()
+    assert rel_l2(t.grad, t_ref.grad) < 1e-6
+    # every face of a valid mesh is listed by its cells: the transpose touches every row
+    assert bool((t.grad.abs().sum(1) > 0).all())
