@@ -33,7 +33,7 @@ def _workspace(device) -> torch.Tensor:
 def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if not (t.is_cuda and t.dtype == torch.float32):
         raise RuntimeError(f"{name}: expected a CUDA fp32 tensor (this path has no CPU fallback)")
-    if t.device.index != torch.cuda.current_device():
+    if t.device.index != ops._current_device():
         raise RuntimeError(f"{name}: tensor is on cuda:{t.device.index}, current device is cuda:{torch.cuda.current_device()}")
     return t
 

@@ -26,14 +26,27 @@ def _count(n: int) -> None:
     LAUNCHES += n
 
 
+# A training step issues ~250 library calls and ~1 800 argument checks; torch.cuda.current_stream() builds a Stream object
+# and torch.cuda.current_device() walks the lazy-init guard on every call (2 + 2 ms of the ~15 ms a step takes to enqueue,
+# scripts/prof_host.py).  The raw getters below are what those wrappers end in.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
+def _current_device() -> int:
+    return _raw_device() if _raw_device is not None else torch.cuda.current_device()
+
+
 def _stream() -> int:
+    if _raw_stream is not None:
+        return _raw_stream(_current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
 def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     if not (torch.is_tensor(t) and t.is_cuda):
         raise RuntimeError(f"{name}: expected a CUDA tensor (this path has no CPU fallback)")
-    if t.device.index != torch.cuda.current_device():
+    if t.device.index != _current_device():
         # the C launches go to the CURRENT device's stream: a tensor on another GPU would fault or be reached through
         # peer access silently (use torch.cuda.set_device / `with torch.cuda.device(...)` around the model call)
         raise RuntimeError(f"{name}: tensor is on cuda:{t.device.index} but the current device is "
