@@ -30,7 +30,7 @@ EXPORTS = [
     "gnnfd_mlp_backward", "gnnfd_gather_rows", "gnnfd_enable_peer_access", "gnnfd_gather_cols_add",
     "gnnfd_glue_workspace_bytes", "gnnfd_face_area_norm", "gnnfd_face_area_norm_backward", "gnnfd_fvm_integrate",
     "gnnfd_fvm_integrate_backward", "gnnfd_masked_mse", "gnnfd_masked_mse_backward", "gnnfd_state_advance",
-    "gnnfd_affine_columns", "gnnfd_set_launch_overlap", "gnnfd_set_l2_hints", "gnnfd_flux_integrate", "gnnfd_gather3", "gnnfd_gather3_backward",
+    "gnnfd_affine_columns", "gnnfd_set_launch_overlap", "gnnfd_set_l2_hints", "gnnfd_flux_integrate", "gnnfd_gather3", "gnnfd_gather3_backward", "gnnfd_dropout_hash",
 ]
 ABI_VERSION = 5
 
@@ -96,6 +96,8 @@ def _load():
     lib.gnnfd_abi_version.restype = C.c_int
     lib.gnnfd_set_launch_overlap.argtypes = [C.c_int32]
     lib.gnnfd_set_l2_hints.argtypes = [C.c_int32]
+    lib.gnnfd_dropout_hash.argtypes = [C.c_uint64, C.c_int32, C.c_uint32, C.c_uint32]
+    lib.gnnfd_dropout_hash.restype = C.c_uint32
     lib.gnnfd_last_error.restype = C.c_char_p
     lib.gnnfd_index_narrow.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.gnnfd_csr_workspace_bytes.argtypes = [i64, i64]

@@ -118,6 +118,10 @@ extern "C" int gnnfd_tc_profile_read(uint64_t *out16) {
   return tc_profile_read((unsigned long long *)out16);
 }
 
+extern "C" uint32_t gnnfd_dropout_hash(uint64_t seed, int32_t layer, uint32_t row, uint32_t col) {
+  return dropout_hash(dropout_row_hash(dropout_layer_key(seed, layer), row), col);      // host evaluation of common.cuh
+}
+
 extern "C" size_t gnnfd_struct_size(int32_t which) {
   switch (which) {
     case 0: return sizeof(gnnfd_mlp_args);

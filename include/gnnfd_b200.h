@@ -178,6 +178,11 @@ typedef struct {
 int gnnfd_abi_version(void);
 const char *gnnfd_last_error(void);
 
+/* The dropout mask function of gnnfd_mlp_args.dropout_p, evaluated on the HOST (no GPU needed): hidden unit
+ * (row, col) of hidden layer `layer` (0 | 1) is dropped iff gnnfd_dropout_hash(seed, layer, row, col) < p * 2^32.
+ * Lets a binding (and tests/test_abi.py) pin its own restatement of the mask. */
+uint32_t gnnfd_dropout_hash(uint64_t seed, int32_t layer, uint32_t row, uint32_t col);
+
 /* Launch policy of every kernel of this library: on != 0 launches them with programmatic stream serialisation
  * (programmatic dependent launch): the next kernel's CTAs become resident as SMs drain and run their on-chip prologue
  * under the previous kernel's tail; every kernel executes griddepcontrol.wait before its first global access, so the

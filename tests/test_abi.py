@@ -49,3 +49,30 @@ def test_product_never_imports_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_dropout_hash_known_answers_and_numpy_restatement():
+    """The dropout mask function (gnnfd_mlp_args.dropout_p) evaluated by the library on the HOST against (a) the numpy
+    restatement the GPU tests compare the kernel's mask with (tests/test_gpu_dropout.py) and (b) its statistics: a fair
+    coin per unit, independent across rows, columns, layers and seeds."""
+    import importlib.util
+    import numpy as np
+    from gnn_fluid_dynamics_b200 import _lib
+    spec = importlib.util.spec_from_file_location("t_dropout", os.path.join(ROOT, "tests", "test_gpu_dropout.py"))
+    src = open(spec.origin).read()
+    ns = {"np": np}
+    exec(src[src.index("def _hash32"):src.index("def _torch_reference")], ns)      # the restatement only (no CUDA imports)
+    seed = 0x0123_4567_89AB_CDEF
+    for layer in (0, 1):
+        ref = ns["expected_dropped"](seed, layer, 40, 0.25)
+        thresh = int(float(np.float32(0.25)) * 4294967296.0)
+        got = np.array([[_lib.lib.gnnfd_dropout_hash(seed, layer, r, c) < thresh for c in range(128)] for r in range(40)])
+        assert np.array_equal(got, ref), layer
+    # statistics of the library's own function: keep rate and independence between layers / neighbouring seeds
+    h = lambda s, l: np.array([[_lib.lib.gnnfd_dropout_hash(s, l, r, c) for c in range(128)] for r in range(64)], dtype=np.float64)
+    a, b, c = h(seed, 0), h(seed, 1), h(seed + 1, 0)
+    for x in (a, b, c):
+        assert abs(x.mean() / 2 ** 32 - 0.5) < 0.01
+    assert abs(np.corrcoef(a.ravel(), b.ravel())[0, 1]) < 0.05 and abs(np.corrcoef(a.ravel(), c.ravel())[0, 1]) < 0.05
+    assert abs(np.corrcoef(a[:, :-1].ravel(), a[:, 1:].ravel())[0, 1]) < 0.05      # neighbouring columns
+    assert abs(np.corrcoef(a[:-1].ravel(), a[1:].ravel())[0, 1]) < 0.05            # neighbouring rows
