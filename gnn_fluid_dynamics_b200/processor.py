@@ -154,12 +154,14 @@ def edge_mlp_concat(seq, e, x_src, topo, prec, want_raw, residual=True, fast: Op
                            want_raw=want_raw, want_sum=residual)
 
 
-def edge_mlp_sum(seq, e, x_src, topo, prec, mul=None):
+def edge_mlp_sum(seq, e, x_src, topo, prec, mul=None, inplace=False):
     """e' = face_mlp(cat[e, x[row] + x[col]]) [* mul]  (Conservative.py:228-234); ``mul`` is ConservativeA's asym
-    encoding or ConservativeI's keep matrix (0 on INFLOW / WALL faces, so e + 0 * e' leaves their latent untouched)."""
+    encoding or ConservativeI's keep matrix (0 on INFLOW / WALL faces, so e + 0 * e' leaves their latent untouched).
+    ``inplace`` (inference): e is updated in place - without ``mul`` that is the TMA-store epilogue (raw stored, the residual
+    add done by the reduce-store, the residual rows never loaded by the SM)."""
     segs = [Seg(e), Seg(x_src, SEG_SUM2, (topo.row, topo.col))]
     return A.mlp(seq, segs, e.shape[0], prec, mul=mul, residual=e,
-                           want_raw=True, want_sum=True)
+                           want_raw=True, want_sum=True, inplace=inplace)
 
 
 def cell_signed_sum(e_raw: torch.Tensor, topo: MeshTopology) -> torch.Tensor:
@@ -184,7 +186,7 @@ def mlp_rows(seq, src: torch.Tensor, prec: int, act: int = ACT_SILU) -> torch.Te
 
 def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
              e_asym: Optional[torch.Tensor] = None, want_vertex: bool = False, e_keep: Optional[torch.Tensor] = None,
-             fast: Optional[Fast] = None):
+             fast: Optional[Fast] = None, inplace: bool = False):
     """One GN_Block -> (x_new, e_new, vertex_x or None).  With ``fast`` (inference) x / e are updated in place."""
     if fast is not None and family in ("fvgn", "vertpot"):
         vsum = vertex_half_sum(e, topo)
@@ -210,6 +212,13 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
         vsum = vertex_half_sum(e_raw, topo)
         _, x_new = node_mlp_two_hop(block.cell_block.cell_mlp, x, vsum, topo, prec, want_raw=False)
         return x_new, e_new, None
+    if family == "cons_a" and inplace:
+        # inference: both residual streams updated in place through the TMA-store epilogue (see edge_mlp_sum)
+        e_raw, _ = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec, mul=e_asym, inplace=True)
+        agg = cell_signed_sum(e_raw, topo)
+        A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(agg)], x.shape[0], prec, residual=x, want_raw=False, want_sum=True,
+              inplace=True)
+        return x, e, None
     if family == "cons_a":
         e_raw, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec, mul=e_asym)
         ell = getattr(topo, "signed_ell", None)
@@ -301,14 +310,18 @@ def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=
     ``fast.xs`` must already hold the split shadow of x (``encode_cells``)."""
     vx = None
     n = len(blocks)
+    # 'cons_a' inference: x, e are the encoder's fresh outputs and are advanced in place (no shadow: the sum-form face block
+    # gathers fp32 rows)
+    inplace = (family == "cons_a" and fast is None and not FUSE_SIGNED_SUM and x.shape[0] > 0
+               and fast_mode(blocks, [x, e] + ([e_asym] if e_asym is not None else []), prec))
     for i, blk in enumerate(blocks):
         x, e, vx_i = gn_block(family, blk, x, e, topo, prec,
                               e_asym=e_asym if (family == "cons_a" and i == 0) else None,
-                              want_vertex=(family == "vertpot" and i == n - 1), e_keep=e_keep, fast=fast)
+                              want_vertex=(family == "vertpot" and i == n - 1), e_keep=e_keep, fast=fast, inplace=inplace)
         if vx_i is not None:
             vx = vx_i
         if hook is not None:
-            hook(i, x.clone(), e.clone()) if fast is not None else hook(i, x, e)
+            hook(i, x.clone(), e.clone()) if (fast is not None or inplace) else hook(i, x, e)
     return x, e, vx
 
 
