@@ -237,10 +237,12 @@ class ConservativeD(ConservativeA):
         e_s = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
         e_a = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        # inference: the encoder's fresh outputs are advanced in place (TMA-store epilogue, processor.fast_mode)
+        inplace = x.shape[0] > 0 and P.fast_mode(self.processer_list, [x, e_s, e_a], prec)
         for i, blk in enumerate(self.processer_list):
-            x, e_s, e_a = P.gn_block_dual(blk, x, e_s, e_a, topo, prec)
+            x, e_s, e_a = P.gn_block_dual(blk, x, e_s, e_a, topo, prec, inplace=inplace)
             if hook is not None:
-                hook(i, x, e_s)
+                hook(i, x.clone(), e_s.clone()) if inplace else hook(i, x, e_s)
         # decoder: symm head, asym head accumulated onto it through the residual epilogue, final antisymmetric head
         d_s = P.mlp_rows(self.decoder.symm_mlp, e_s, prec)
         _, comb = P.A.mlp(self.decoder.asym_mlp, [P.Seg(e_a)], e_a.shape[0], prec, act=ACT_TANH, residual=d_s,
@@ -377,10 +379,11 @@ class ConservativeH(ConservativeD):
         e_s = P.mlp_rows(self.encoder.faceS_mlp, f_x_symm, prec)
         e_a = P.mlp_rows(self.encoder.faceA_mlp, f_x_asym, prec, act=ACT_TANH)
         x = P.mlp_rows(self.encoder.cell_mlp, c_x, prec)
+        inplace = x.shape[0] > 0 and P.fast_mode(self.processer_list, [x, e_s, e_a], prec)      # see ConservativeD
         for i, blk in enumerate(self.processer_list):
-            x, e_s, e_a = P.gn_block_dual_two_hop(blk, x, e_s, e_a, topo, prec)
+            x, e_s, e_a = P.gn_block_dual_two_hop(blk, x, e_s, e_a, topo, prec, inplace=inplace)
             if hook is not None:
-                hook(i, x, e_s)
+                hook(i, x.clone(), e_s.clone()) if inplace else hook(i, x, e_s)
         self._last_e_asym = e_a
         # decoder (Conservative.py:1186-1208): even head on cat[h+, h-^2], odd head on cat[h-, h+]
         n_e = e_s.shape[0]

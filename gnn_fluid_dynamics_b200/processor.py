@@ -272,32 +272,34 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
     raise ValueError(f"unknown family {family!r}")
 
 
-def gn_block_dual(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32):
+def gn_block_dual(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32, inplace: bool = False):
     """ConservativeD GN_Block (Conservative.py:572-645): symmetric and antisymmetric edge streams.
-    -> (x_new, e_s_new, e_a_new)."""
-    s_raw, s_new = edge_mlp_sum(block.face_block_symm.face_mlp, e_s, x, topo, prec)
+    -> (x_new, e_s_new, e_a_new).  ``inplace`` (inference, ``fast_mode``): the three residual streams are advanced in place
+    through the TMA-store epilogue (both face blocks read x before the cell block updates it)."""
+    s_raw, s_new = edge_mlp_sum(block.face_block_symm.face_mlp, e_s, x, topo, prec, inplace=inplace)
     segs = [Seg(e_a), Seg(x, SEG_DIFF2, (topo.row, topo.col))]                       # cat[e_a, x[row] - x[col]]
     a_raw, a_new = A.mlp(block.face_block_asym.face_mlp, segs, e_a.shape[0], prec, act=ACT_TANH, residual=e_a,
-                         want_raw=True, want_sum=True)
+                         want_raw=True, want_sum=True, inplace=inplace)
     off, perm = topo.build_cell_csr()
     sym = A.segment_sum(s_raw, 0, 0, H, 1.0, off, perm, topo.n_cells, topo.col, topo.row)      # equal signs on both cells
     asym = A.segment_sum(a_raw, 0, 0, H, -1.0, off, perm, topo.n_cells, topo.col, topo.row)    # opposite signs
     _, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(sym), Seg(asym)], x.shape[0], prec, residual=x,
-                     want_raw=False, want_sum=True)
+                     want_raw=False, want_sum=True, inplace=inplace)
     return x_new, s_new, a_new
 
 
-def gn_block_dual_two_hop(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32):
-    """ConservativeH / J GN_Block (Conservative.py:1098-1184), cell block first.  -> (x_new, e_s_new, e_a_new)."""
+def gn_block_dual_two_hop(block, x, e_s, e_a, topo: MeshTopology, prec: int = PREC_F32, inplace: bool = False):
+    """ConservativeH / J GN_Block (Conservative.py:1098-1184), cell block first.  -> (x_new, e_s_new, e_a_new).
+    ``inplace``: see ``gn_block_dual`` (the face blocks gather the cell block's RAW output, a separate matrix)."""
     vsum = A.segment_sum(e_s, 0, 0, H, 1.0, topo.vtx_offsets, topo.vtx_perm, topo.n_vertices, topo.v0, topo.v1)
     off, perm = topo.build_cell_csr()
     asym = A.segment_sum(e_a, 0, 0, H, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
     x_raw, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)], x.shape[0], prec,
-                         residual=x, want_raw=True, want_sum=True)
+                         residual=x, want_raw=True, want_sum=True, inplace=inplace)
     _, s_new = A.mlp(block.face_block_symm.face_mlp, [Seg(e_s), Seg(x_raw, SEG_SUM2, (topo.row, topo.col))],
-                     e_s.shape[0], prec, residual=e_s, want_raw=False, want_sum=True)
+                     e_s.shape[0], prec, residual=e_s, want_raw=False, want_sum=True, inplace=inplace)
     _, a_new = A.mlp(block.face_block_asym.face_mlp, [Seg(e_a), Seg(x_raw, SEG_DIFF2, (topo.row, topo.col))],
-                     e_a.shape[0], prec, act=ACT_TANH, residual=e_a, want_raw=False, want_sum=True)
+                     e_a.shape[0], prec, act=ACT_TANH, residual=e_a, want_raw=False, want_sum=True, inplace=inplace)
     return x_new, s_new, a_new
 
 
