@@ -236,12 +236,12 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
     if family == "cons_e":
         # ConservativeE (Conservative.py:677-732): sum-form face block, then the RAW face output aggregated onto cells:
         # first half with equal signs, second half with opposite signs, agg = cat[sym, asym]
-        e_raw, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec)
+        e_raw, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x, topo, prec, inplace=inplace)
         off, perm = topo.build_cell_csr()
         sym = A.segment_sum(e_raw, 0, 0, H // 2, 1.0, off, perm, topo.n_cells, topo.col, topo.row)
         asym = A.segment_sum(e_raw, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
         _, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(sym), Seg(asym)], x.shape[0], prec, residual=x,
-                         want_raw=False, want_sum=True)          # cat[x, sym, asym] as three 64-multiple segments
+                         want_raw=False, want_sum=True, inplace=inplace)   # cat[x, sym, asym] as three 64-multiple segments
         return x_new, e_new, None
     if family == "cons_f":
         # ConservativeF (Conservative.py:763-821): symmetric half two-hop via the vertices (the same half onto both
@@ -250,8 +250,13 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
         off, perm = topo.build_cell_csr()
         asym = A.segment_sum(e, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
         x_raw, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)],
-                             x.shape[0], prec, residual=x, want_raw=True, want_sum=True)
-        _, e_new = edge_mlp_concat(block.face_block.face_mlp, e, x_raw, topo, prec, want_raw=False)
+                             x.shape[0], prec, residual=x, want_raw=True, want_sum=True, inplace=inplace)
+        if inplace:
+            segs = [Seg(e), Seg(x_raw, SEG_GATHER, (topo.row,)), Seg(x_raw, SEG_GATHER, (topo.col,))]
+            _, e_new = A.mlp(block.face_block.face_mlp, segs, e.shape[0], prec, residual=e, want_raw=False, want_sum=True,
+                             inplace=True)
+        else:
+            _, e_new = edge_mlp_concat(block.face_block.face_mlp, e, x_raw, topo, prec, want_raw=False)
         return x_new, e_new, None
     if family in ("cons_g", "cons_i"):
         # ConservativeG / I (Conservative.py:834-896, 1250-1317): F's hybrid cell block, then the SUM-form face block on
@@ -260,8 +265,9 @@ def gn_block(family: str, block, x, e, topo: MeshTopology, prec: int = PREC_F32,
         off, perm = topo.build_cell_csr()
         asym = A.segment_sum(e, H // 2, H // 2, H // 2, -1.0, off, perm, topo.n_cells, topo.col, topo.row)
         x_raw, x_new = A.mlp(block.cell_block.cell_mlp, [Seg(x), Seg(vsum, SEG_MEAN3, topo.vf), Seg(asym)],
-                             x.shape[0], prec, residual=x, want_raw=True, want_sum=True)
-        _, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x_raw, topo, prec, mul=e_keep if family == "cons_i" else None)
+                             x.shape[0], prec, residual=x, want_raw=True, want_sum=True, inplace=inplace)
+        _, e_new = edge_mlp_sum(block.face_block.face_mlp, e, x_raw, topo, prec, mul=e_keep if family == "cons_i" else None,
+                                inplace=inplace)
         return x_new, e_new, None
     if family == "vertpot":
         vsum = vertex_half_sum(e, topo)
@@ -312,10 +318,11 @@ def run_processor(family: str, blocks, x, e, topo, prec: int = PREC_F32, e_asym=
     ``fast.xs`` must already hold the split shadow of x (``encode_cells``)."""
     vx = None
     n = len(blocks)
-    # 'cons_a' inference: x, e are the encoder's fresh outputs and are advanced in place (no shadow: the sum-form face block
-    # gathers fp32 rows)
-    inplace = (family == "cons_a" and fast is None and not FUSE_SIGNED_SUM and x.shape[0] > 0
-               and fast_mode(blocks, [x, e] + ([e_asym] if e_asym is not None else []), prec))
+    # Conservative families in inference: x, e are the encoder's fresh outputs and are advanced in place (no shadow: the
+    # sum-form face block gathers fp32 rows)
+    inplace = (family in ("cons_a", "cons_e", "cons_f", "cons_g", "cons_i") and fast is None and x.shape[0] > 0
+               and not (family == "cons_a" and FUSE_SIGNED_SUM)
+               and fast_mode(blocks, [x, e] + [t for t in (e_asym, e_keep) if t is not None], prec))
     for i, blk in enumerate(blocks):
         x, e, vx_i = gn_block(family, blk, x, e, topo, prec,
                               e_asym=e_asym if (family == "cons_a" and i == 0) else None,
