@@ -145,6 +145,10 @@ def _run_processor_partitioned_cons_a(blocks, states: List[PartState], transport
     superset of the face-neighbour ring this data-flow needs (every face of an owned cell is local), and local faces keep
     global order, so the owned rows are bit-identical to the single-GPU result."""
     from ._lib import SEG_SUM2
+    from .processor import fast_mode
+    # inference: the residual streams advance in place through the TMA-store epilogue, exactly as processor.run_processor
+    # does for this family (the same kernels on the same rows: bit-identical owned rows either way)
+    inplace = fast_mode(blocks, [t for s in states for t in (s.x, s.e)], prec)
     for i, blk in enumerate(blocks):
         we, wn = weights_of(blk.face_block.face_mlp), weights_of(blk.cell_block.cell_mlp)
         if i > 0:
@@ -153,10 +157,10 @@ def _run_processor_partitioned_cons_a(blocks, states: List[PartState], transport
             topo, n_own = s.topo, s.part.n_owned
             segs = [Seg(s.e), Seg(s.x, SEG_SUM2, (topo.row, topo.col))]
             e_raw, e_new = ops.mlp_forward(segs, we, s.e.shape[0], prec, mul=s.e_asym if i == 0 else None, residual=s.e,
-                                           want_raw=True, want_sum=True)
+                                           want_raw=True, want_sum=True, out_sum=s.e if inplace else None)
             off, perm = topo.build_cell_csr()
             agg = ops.segment_sum(e_raw, e_raw, 0, 0, H, -1.0, off, perm, n_own)
-            x_new = torch.empty_like(s.x)                     # ghost rows: filled by the next block's exchange
+            x_new = s.x if inplace else torch.empty_like(s.x)     # ghost rows: filled by the next block's exchange
             ops.mlp_forward([Seg(s.x), Seg(agg)], wn, n_own, prec, residual=s.x, want_raw=False, want_sum=True, out_sum=x_new)
             s.x, s.e = x_new, e_new
     return states

@@ -41,18 +41,16 @@ def _states(parts, locals_, device, only=None):
 @pytest.mark.parametrize("world", [2, 5])
 def test_partitioned_conservative_equals_unpartitioned_bitwise(world):
     """ConservativeA (face-flux message passing: SUM2 face block, signed edge->cell sum, block-0 asym multiply) over a
-    partitioned mesh == the single-GPU result, bit for bit, on owned cells / local faces.  (The partitioned data-flow
-    runs the coalesced-store epilogue: the single-GPU side is pinned to it with ``no_fast``, see there.)"""
+    partitioned mesh == the single-GPU result, bit for bit, on owned cells / local faces (both advance the residual
+    streams in place through the TMA-store epilogue)."""
     from gnn_fluid_dynamics_b200.dist import InProcessTransport, PartState, encode_process_decode_partitioned
-    from gnn_fluid_dynamics_b200.processor import no_fast
     from gnn_fluid_dynamics_b200.topology import MeshTopology, get_topology
     dev = torch.device("cuda:0")
     model, graphs, parts, locals_ = _setup("ConservativeA", 4000, world, dev)
     gd = [g.to(dev) for g in graphs]
     with torch.no_grad():
         topo = get_topology(gd, need_cell_csr=True, two_hop=False).validate()
-        with no_fast():
-            x, e, dec = model.encode_process_decode(gd[0].x, gd[1].x_symm, gd[1].x_asym, topo)
+        x, e, dec = model.encode_process_decode(gd[0].x, gd[1].x_symm, gd[1].x_asym, topo)
         states, inputs = [], []
         for p, g in zip(parts, locals_):
             gl = [t.to(dev) for t in g]
