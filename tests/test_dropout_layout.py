@@ -63,3 +63,44 @@ def test_eval_forward_ignores_dropout_and_training_applies_it(name):
     with torch.no_grad():
         c = drop([g.clone().to(dev) for g in graphs], mode="rollout")
     assert any(not torch.equal(a[k], c[k]) for k in a) and all(torch.isfinite(c[k]).all() for k in c)
+
+
+def test_weights_view_folds_the_keep_scale_in_training_only():
+    """processor.weights_of (host logic, no GPU): in train() mode a dropout MLP's view carries drop_p and W2, W3 divided by
+    (1 - p) - the kernel only masks, the rescale of the kept units lives in the consuming layer's weights - while W1, the
+    biases and the LayerNorm affine are untouched; eval() gives the plain view; the cached view follows mode switches and
+    optimizer-style in-place updates."""
+    from gnn_fluid_dynamics_b200.models.base import build_mlp
+    from gnn_fluid_dynamics_b200.processor import weights_of
+    torch.manual_seed(0)
+    m = build_mlp(NS(training=NS(dropout_rate=0.2)), 12, 128, 128)
+    lin = [x for x in m[0] if isinstance(x, torch.nn.Linear)]
+    m.train()
+    w = weights_of(m)
+    assert w.drop_p == pytest.approx(0.2)
+    assert torch.equal(w.w1, lin[0].weight) and torch.equal(w.b2, lin[1].bias) and torch.equal(w.ln_w, m[1].weight)
+    assert torch.allclose(w.w2 * 0.8, lin[1].weight, rtol=1e-6, atol=0) and torch.allclose(w.w3 * 0.8, lin[2].weight, rtol=1e-6, atol=0)
+    assert weights_of(m) is w                                   # cached
+    m.eval()
+    we = weights_of(m)
+    assert we.drop_p == 0.0 and torch.equal(we.w2, lin[1].weight) and torch.equal(we.w3, lin[2].weight)
+    m.train()
+    with torch.no_grad():
+        lin[1].weight.mul_(2.0)                                 # what an optimizer step does
+    w2 = weights_of(m)
+    assert w2 is not w and torch.allclose(w2.w2 * 0.8, lin[1].weight, rtol=1e-6, atol=0)
+    # no dropout configured: train() and eval() share the plain view
+    p = build_mlp(NS(training=NS(dropout_rate=0.0)), 12, 128, 128).train()
+    assert weights_of(p).drop_p == 0.0 and torch.equal(weights_of(p).w2, [x for x in p[0] if isinstance(x, torch.nn.Linear)][1].weight)
+
+
+def test_unsupported_dropout_layouts_are_rejected():
+    from gnn_fluid_dynamics_b200.models.base import build_mlp
+    from gnn_fluid_dynamics_b200.processor import weights_of
+    m = build_mlp(NS(training=NS(dropout_rate=0.2)), 12, 128, 128).train()
+    drops = [x for x in m[0] if isinstance(x, torch.nn.Dropout)]
+    drops[1].p = 0.3                                            # two different rates: not the reference's layout
+    with pytest.raises(NotImplementedError, match="dropout"):
+        weights_of(m)
+    drops[1].p = 0.2
+    assert weights_of(m).drop_p == pytest.approx(0.2)
