@@ -197,15 +197,20 @@ __device__ __noinline__ void tc_load_block_generic(const TcParams &p, const int3
 
 // Issue the global loads of k-block kb of the tile starting at row0 into v.  Rows past the end of the
 // matrix read a clamped (valid) row: their results are never stored.
+// LEAN (template): the launch has only full, 16-byte aligned k-blocks of DIRECT / GATHER / MEAN3 segments and no peer
+// matrices (host-checked in mlp_forward_tc) - the other assembly modes are not compiled into the producers' loop.
+template <bool LEAN>
 __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *ix, int64_t row0, int kb,
                                               int rbase, int f4, float4 (&v)[8]) {
   const KbDesc &d = p.kb[kb];
-  if (!d.vec || d.kvalid != TC_KB) {
-    float4 t[8];   // only this temporary gets a stack home; v stays in registers
-    tc_load_block_generic(p, ix, row0, kb, rbase, f4, t);
+  if constexpr (!LEAN) {
+    if (!d.vec || d.kvalid != TC_KB) {
+      float4 t[8];   // only this temporary gets a stack home; v stays in registers
+      tc_load_block_generic(p, ix, row0, kb, rbase, f4, t);
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) v[jj] = t[jj];
-    return;
+      for (int jj = 0; jj < 8; ++jj) v[jj] = t[jj];
+      return;
+    }
   }
   const int32_t *ixs = ix + d.seg * 3 * TC_BM + rbase;
   const uint32_t ixa = smem_u32(ixs);           // the index slot lives in shared memory: ld.shared, not generic loads
@@ -219,7 +224,7 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4_hint(tb + (uint32_t)min(rbase + 16 * jj, last) * ldu, p.pol.ld_stream);
   } else if (d.mode == GNNFD_SEG_GATHER) {
-    if (p.a.peer_shift > 0) {   // rows of ghost cells come straight from the owning GPU's HBM (P2P over NVLink)
+    if (!LEAN && p.a.peer_shift > 0) {   // rows of ghost cells come straight from the owning GPU's HBM (P2P over NVLink)
       const uint32_t mask = (1u << p.a.peer_shift) - 1u;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
@@ -230,7 +235,7 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) v[jj] = ldg_f4_hint(base + (int64_t)lds_s32(ixa + 64 * jj) * ld, p.pol.ld_keep);
     }
-  } else if (d.mode == GNNFD_SEG_SUM3S) {
+  } else if (!LEAN && d.mode == GNNFD_SEG_SUM3S) {
     // (s0 a + s1 b) + s2 c: three gathered rows with the signs decoded from the index entries
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
@@ -255,7 +260,7 @@ __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *
                                    (s0 * a.z + s1 * y[u].z) + s2 * z[u].z, (s0 * a.w + s1 * y[u].w) + s2 * z[u].w);
       }
     }
-  } else if (d.mode == GNNFD_SEG_MEAN3) {
+  } else if (LEAN || d.mode == GNNFD_SEG_MEAN3) {
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       float4 y[2], z[2];
@@ -306,12 +311,16 @@ __device__ __forceinline__ void tc_store_block(uint32_t sA, const float4 (&v)[8]
 }
 
 // -------------------------------------------------------------------------------------- kernel
-template <bool FP16, int NA, int NW, bool BWD, int EPI>
+template <bool FP16, int NA, int NW, bool BWD, int EPI, bool LEAN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const gnnfd_mlp_args &a = p.a;
   const int a_stages = p.a_stages;
+  // LEAN instantiation (host-checked): 3-layer SiLU MLP, 128 outputs, no `mul`, no peer matrices, full aligned k-blocks of
+  // DIRECT / GATHER / MEAN3 segments, stash (if any) through TMA - the rarely used variants are not compiled into the
+  // roles' hot loops, which together overflow the instruction cache otherwise (no_inst stalls, ncu)
+  const int nl = LEAN ? 3 : p.nl;
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *s_a = smem;                                     // A ring
   float *s_stg = (float *)(s_a + a_stages * TC_STAGE_BYTES);   // output staging, one swizzled 32x16 block per epilogue warp
@@ -355,7 +364,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   if (!early) pdl_wait();
   for (int i = tid; i < 5 * TC_H; i += TC_THREADS) {
     const int v = i / TC_H, c = i % TC_H;
-    const float *src = v == 0 ? a.b1 : v == 1 ? a.b2 : v == 2 ? (p.nl == 1 ? a.b1 : a.b3) : v == 3 ? a.ln_w : a.ln_b;
+    const float *src = v == 0 ? a.b1 : v == 1 ? a.b2 : v == 2 ? (nl == 1 ? a.b1 : a.b3) : v == 3 ? a.ln_w : a.ln_b;
     if (BWD && v < 3) src = nullptr;
     const int n = (v == 2 || v >= 3) ? a.n_out : TC_H;
     s_vec[i] = (src && c < n) ? __ldg(src + c) : (v == 3 ? 1.f : 0.f);
@@ -425,7 +434,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         if (++ikb == p.kb1) { ikb = 0; ++ij; }
       }
       if (ij < T) {
-        tc_load_block(p, s_idx + (ij & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT, tile_row0(ij), ikb, rbase, f4, v);
+        tc_load_block<LEAN>(p, s_idx + (ij & (TC_IDX_SLOTS - 1)) * TC_IDX_SLOT, tile_row0(ij), ikb, rbase, f4, v);
         if (++ikb == p.kb1) { ikb = 0; ++ij; }
       }
     };
@@ -535,7 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         for (int j = 0; j < T; ++j)
           for (int kb = 0; kb < p.kb1; ++kb)
             for (int part = 0; part < NW; ++part) load_unit(w1p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
-      } else if (p.nl > 1) {
+      } else if (nl > 1) {
         for (int j = 0; j < T; ++j) {
           for (int kb = 0; kb < 2; ++kb)
             for (int part = 0; part < NW; ++part) load_unit(w2p + (size_t)kb * p.w_block_bytes + part * TC_IMG, TC_IMG);
@@ -615,9 +624,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   } else if (warp == TC_MMA23_WARP) {
     // ==================================================================== layer-2/3 MMA issuer
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (lane == 0 && T > 0 && p.nl > 1) {
+    if (lane == 0 && T > 0 && nl > 1) {
       constexpr uint32_t IDESC_H = make_idesc(FP16 ? 0 : 1, TC_H);
-      const uint32_t idesc3 = make_idesc(FP16 ? 0 : 1, p.n3);
+      const uint32_t idesc3 = make_idesc(FP16 ? 0 : 1, LEAN ? TC_H : p.n3);
       int ws = 0;
       uint32_t w_round = 0;
       PROF_DECL;
@@ -696,7 +705,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       // (L2 prefetch of the rows this tile's later phases read - the second hidden layer's saved pre-activations, the
       //  residual - issued from here measured no gain in an A/B on one box: edge MLP backward 859 vs 834 us)
       // ---- hidden layers: accumulator -> +bias, act -> hi/lo pairs, written back in place
-      for (int layer = 0; layer < p.nl - 1; ++layer) {
+      for (int layer = 0; layer < nl - 1; ++layer) {
         const uint32_t reg = layer == 0 ? xr : yr;
         const uint32_t bias = vec + (layer * TC_H + eh * 64) * 4;
         float *save = EPI == 1 ? nullptr : (layer == 0 ? a.save_a1 : a.save_a2);   // EPI 1: no training stash
@@ -739,7 +748,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             __syncwarp();
             if (c < 3) hm_copy(c + 1);
             tmem_ld16(reg + c * 16, v);
-            const bool silu = a.act == GNNFD_ACT_SILU;
+            const bool silu = LEAN || a.act == GNNFD_ACT_SILU;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 m = mm[i];
@@ -781,7 +790,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               tma_store_2d_hint(&p.tm_save[layer], stg, eh * 64 + c * 16, (int)(row0 + q4 * 32), p.pol.st_stash);
               bulk_commit();
             }
-          } else if (save != nullptr) {   // (fallback: thread = row, 64 B per store group)
+          } else if (!LEAN && save != nullptr) {   // (fallback: thread = row, 64 B per store group)
 #pragma unroll
             for (int i = 0; i < 16; i += 4)
               *reinterpret_cast<float4 *>(save + c * 16 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -791,7 +800,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #else
           if (BWD) { /* linear chain: no activation */ }
 #endif
-          else if (a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
+          else if (LEAN || a.act == GNNFD_ACT_SILU) act16<GNNFD_ACT_SILU>(v); else act16<GNNFD_ACT_TANH>(v);
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) split2<FP16>(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
@@ -805,7 +814,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
         if (lane == 0) mbar_arrive(&hid_ready[xs * 2 + eh]);
       }
       // ---- final epilogue
-      PROF_WAIT(1, group_wait(&acc_full[xs], (p.nl * n + p.nl - 1) & 1));
+      PROF_WAIT(1, group_wait(&acc_full[xs], (nl * n + nl - 1) & 1));
       tc_fence_after();
       if constexpr (EPI == 1) {
         // ---- fast final epilogue (inference: no stash, no mul, n_out = 128).  Thread = row: bias -> LayerNorm -> affine in
@@ -939,7 +948,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
 #if GNNFD_ABL == 7
       if (true) { __syncwarp(); if (lane == 0) mbar_arrive(&acc_free[xs]); } else
 #endif
-      if (a.n_out == TC_H) {
+      if (LEAN || a.n_out == TC_H) {
         if (p.save_tma) {   // the last stash store must have finished reading the staging block the copy-out reuses
           if (lane == 0) bulk_wait_read0();
           __syncwarp();
@@ -1028,7 +1037,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               if (a.save_xhat) stg_f4_hint(a.save_xhat + off, o, p.pol.st_stash);
               fma2(o.x, o.y, w4.x, w4.y, g4.x, g4.y);
               fma2(o.z, o.w, w4.z, w4.w, g4.z, g4.w);
-              if (a.mul) {
+              if (!LEAN && a.mul) {
                 float4 m = ldg_f4(a.mul + off);
                 if (a.mul_mode == 1) { m.x = dsilu(m.x); m.y = dsilu(m.y); m.z = dsilu(m.z); m.w = dsilu(m.w); }
                 else if (a.mul_mode == 2) { m.x = dtanh(m.x); m.y = dtanh(m.y); m.z = dtanh(m.z); m.w = dtanh(m.w); }
@@ -1356,25 +1365,45 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   if (a->bwd_chain) extra_smem = TC_STG_BYTES;      // second staging block: asynchronous copies of the saved pre-activations
   p.w_slots = (n_tiles <= 2 * (int64_t)num_sms() && extra_smem == 0) ? TC_W_SLOTS_MAX : 2;
-#define LAUNCH1(FP, NA_, NW_, BW, EP)                                                                     \
+  // LEAN instantiations (BF16X3 only; see the kernel): the common launches of the hot path - full aligned k-blocks of
+  // DIRECT / GATHER / MEAN3 (or TMA-staged) segments, SiLU, 128 outputs, no `mul`, no peer matrices, stash through TMA
+  bool lean = p.nl == 3 && a->n_out == TC_H && a->act == GNNFD_ACT_SILU && a->mul == nullptr && a->peer_shift == 0 &&
+              ((a->save_a1 == nullptr && a->save_a2 == nullptr) || p.save_tma) && !m.fp16 && m.na == 2 && m.nw == 2;
+  for (int kb = 0; kb < p.kb1 && lean; ++kb) {
+    const KbDesc &d = p.kb[kb];
+    lean = d.tma || (d.vec && d.kvalid == TC_KB &&
+                     (d.mode == GNNFD_SEG_DIRECT || d.mode == GNNFD_SEG_GATHER || d.mode == GNNFD_SEG_MEAN3));
+  }
+  {
+    static int lean_on = -1;      // A/B knob: GNNFD_LEAN=0 runs the all-purpose instantiations everywhere
+    if (lean_on < 0) {
+      const char *e = getenv("GNNFD_LEAN");
+      lean_on = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    lean = lean && lean_on;
+  }
+#define LAUNCH1(FP, NA_, NW_, BW, EP, LN)                                                                 \
   do {                                                                                                    \
     static bool attr[GNNFD_MAX_DEVICES] = {false};                                                        \
     if (!attr[current_device()]) {                                                                        \
-      GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_, BW, EP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      GNNFD_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<FP, NA_, NW_, BW, EP, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       227 * 1024));                                                       \
       attr[current_device()] = true;                                                                      \
     }                                                                                                     \
-    launch_pdl(mlp_tc_kernel<FP, NA_, NW_, BW, EP>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(p.w_slots, p.a_stages) + extra_smem, stream, p);   \
+    launch_pdl(mlp_tc_kernel<FP, NA_, NW_, BW, EP, LN>, dim3(grid), dim3(TC_THREADS), tc_smem_bytes(p.w_slots, p.a_stages) + extra_smem, stream, p);   \
   } while (0)
 #define LAUNCH(FP, NA_, NW_)                                                                              \
   do {                                                                                                    \
-    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true, 0);                                                     \
-    else if (p.drop_thresh != 0u) LAUNCH1(FP, NA_, NW_, false, 2);                                        \
-    else LAUNCH1(FP, NA_, NW_, false, 0);                                                                 \
+    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true, 0, false);                                              \
+    else if (p.drop_thresh != 0u) LAUNCH1(FP, NA_, NW_, false, 2, false);                                 \
+    else LAUNCH1(FP, NA_, NW_, false, 0, false);                                                          \
   } while (0)
   if (p.a_stages == 3) p.w_slots = 2;      // 3 A stages + 3-slot weight rings do not fit in 227 KB
-  if (fast && !m.fp16) LAUNCH1(false, 2, 2, false, 1);
-  else if (fast) LAUNCH1(true, 2, 2, false, 1);
+  if (lean && fast) LAUNCH1(false, 2, 2, false, 1, true);
+  else if (lean && a->bwd_chain) LAUNCH1(false, 2, 2, true, 0, true);
+  else if (lean && p.drop_thresh == 0u) LAUNCH1(false, 2, 2, false, 0, true);
+  else if (fast && !m.fp16) LAUNCH1(false, 2, 2, false, 1, false);
+  else if (fast) LAUNCH1(true, 2, 2, false, 1, false);
   else if (!m.fp16 && m.na == 2 && m.nw == 2) LAUNCH(false, 2, 2);
   else if (!m.fp16 && m.na == 1) LAUNCH(false, 1, 1);
   else if (m.fp16 && m.nw == 1) LAUNCH(true, 2, 1);
