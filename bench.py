@@ -161,7 +161,8 @@ def ncu_traffic(which):
         if which in ("edge_chain", "edge_stash"):
             name = "r02_train_kernels_ncu_summary.json"
             d = json.load(open(os.path.join(ROOT, "profiles", name)))
-            tag = "mlp_tc_kernel<0, 2, 2, 1, 0>" if which == "edge_chain" else "mlp_tc_kernel<0, 2, 2, 0, 0>"
+            # (instantiation prefix: <FP16, NA, NW, BWD, EPI[, LEAN]>)
+            tag = "mlp_tc_kernel<0, 2, 2, 1, 0" if which == "edge_chain" else "mlp_tc_kernel<0, 2, 2, 0, 0"
             hits = [l for l in d["launches"] if tag in l.get("kernel", "")]
             return int(max(hits, key=lambda l: l.get("duration_us", 0))["dram_traffic_bytes"]), name
         name = "r02_fwd_edge_fast_ncu_summary.json"

@@ -199,7 +199,7 @@ __device__ __noinline__ void tc_load_block_generic(const TcParams &p, const int3
 // matrix read a clamped (valid) row: their results are never stored.
 // LEAN (template): the launch has only full, 16-byte aligned k-blocks of DIRECT / GATHER / MEAN3 segments and no peer
 // matrices (host-checked in mlp_forward_tc) - the other assembly modes are not compiled into the producers' loop.
-template <bool LEAN>
+template <int LEAN>
 __device__ __forceinline__ void tc_load_block(const TcParams &p, const int32_t *ix, int64_t row0, int kb,
                                               int rbase, int f4, float4 (&v)[8]) {
   const KbDesc &d = p.kb[kb];
@@ -311,7 +311,7 @@ __device__ __forceinline__ void tc_store_block(uint32_t sA, const float4 (&v)[8]
 }
 
 // -------------------------------------------------------------------------------------- kernel
-template <bool FP16, int NA, int NW, bool BWD, int EPI, bool LEAN = false>
+template <bool FP16, int NA, int NW, bool BWD, int EPI, int LEAN = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_constant__ TcParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
@@ -320,7 +320,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   // LEAN instantiation (host-checked): 3-layer SiLU MLP, 128 outputs, no `mul`, no peer matrices, full aligned k-blocks of
   // DIRECT / GATHER / MEAN3 segments, stash (if any) through TMA - the rarely used variants are not compiled into the
   // roles' hot loops, which together overflow the instruction cache otherwise (no_inst stalls, ncu)
-  const int nl = LEAN ? 3 : p.nl;
+  // (LEAN = 2: the same for a single Linear - n_layers = 1, contiguous operand rows, optional act'(mul) / residual: the
+  //  dgrad launches of the backward)
+  const int nl = LEAN == 1 ? 3 : LEAN == 2 ? 1 : p.nl;
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *s_a = smem;                                     // A ring
   float *s_stg = (float *)(s_a + a_stages * TC_STAGE_BYTES);   // output staging, one swizzled 32x16 block per epilogue warp
@@ -1037,7 +1039,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
               if (a.save_xhat) stg_f4_hint(a.save_xhat + off, o, p.pol.st_stash);
               fma2(o.x, o.y, w4.x, w4.y, g4.x, g4.y);
               fma2(o.z, o.w, w4.z, w4.w, g4.z, g4.w);
-              if (!LEAN && a.mul) {
+              if (LEAN != 1 && a.mul) {
                 float4 m = ldg_f4(a.mul + off);
                 if (a.mul_mode == 1) { m.x = dsilu(m.x); m.y = dsilu(m.y); m.z = dsilu(m.z); m.w = dsilu(m.w); }
                 else if (a.mul_mode == 2) { m.x = dtanh(m.x); m.y = dtanh(m.y); m.z = dtanh(m.z); m.w = dtanh(m.w); }
@@ -1367,8 +1369,10 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   p.w_slots = (n_tiles <= 2 * (int64_t)num_sms() && extra_smem == 0) ? TC_W_SLOTS_MAX : 2;
   // LEAN instantiations (BF16X3 only; see the kernel): the common launches of the hot path - full aligned k-blocks of
   // DIRECT / GATHER / MEAN3 (or TMA-staged) segments, SiLU, 128 outputs, no `mul`, no peer matrices, stash through TMA
-  bool lean = p.nl == 3 && a->n_out == TC_H && a->act == GNNFD_ACT_SILU && a->mul == nullptr && a->peer_shift == 0 &&
-              ((a->save_a1 == nullptr && a->save_a2 == nullptr) || p.save_tma) && !m.fp16 && m.na == 2 && m.nw == 2;
+  bool lean = a->n_out == TC_H && a->peer_shift == 0 && !m.fp16 && m.na == 2 && m.nw == 2 &&
+              (p.nl == 1 ? (a->save_a1 == nullptr && a->save_a2 == nullptr && !a->has_ln && !a->bwd_chain)
+                         : (a->act == GNNFD_ACT_SILU && a->mul == nullptr &&
+                            ((a->save_a1 == nullptr && a->save_a2 == nullptr) || p.save_tma)));
   for (int kb = 0; kb < p.kb1 && lean; ++kb) {
     const KbDesc &d = p.kb[kb];
     lean = d.tma || (d.vec && d.kvalid == TC_KB &&
@@ -1394,16 +1398,17 @@ int mlp_forward_tc(const gnnfd_mlp_args *a, cudaStream_t stream) {
   } while (0)
 #define LAUNCH(FP, NA_, NW_)                                                                              \
   do {                                                                                                    \
-    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true, 0, false);                                              \
-    else if (p.drop_thresh != 0u) LAUNCH1(FP, NA_, NW_, false, 2, false);                                 \
-    else LAUNCH1(FP, NA_, NW_, false, 0, false);                                                          \
+    if (a->bwd_chain) LAUNCH1(FP, NA_, NW_, true, 0, 0);                                                  \
+    else if (p.drop_thresh != 0u) LAUNCH1(FP, NA_, NW_, false, 2, 0);                                     \
+    else LAUNCH1(FP, NA_, NW_, false, 0, 0);                                                              \
   } while (0)
   if (p.a_stages == 3) p.w_slots = 2;      // 3 A stages + 3-slot weight rings do not fit in 227 KB
-  if (lean && fast) LAUNCH1(false, 2, 2, false, 1, true);
-  else if (lean && a->bwd_chain) LAUNCH1(false, 2, 2, true, 0, true);
-  else if (lean && p.drop_thresh == 0u) LAUNCH1(false, 2, 2, false, 0, true);
-  else if (fast && !m.fp16) LAUNCH1(false, 2, 2, false, 1, false);
-  else if (fast) LAUNCH1(true, 2, 2, false, 1, false);
+  if (lean && p.nl == 1) LAUNCH1(false, 2, 2, false, 0, 2);
+  else if (lean && fast) LAUNCH1(false, 2, 2, false, 1, 1);
+  else if (lean && a->bwd_chain) LAUNCH1(false, 2, 2, true, 0, 1);
+  else if (lean && p.drop_thresh == 0u) LAUNCH1(false, 2, 2, false, 0, 1);
+  else if (fast && !m.fp16) LAUNCH1(false, 2, 2, false, 1, 0);
+  else if (fast) LAUNCH1(true, 2, 2, false, 1, 0);
   else if (!m.fp16 && m.na == 2 && m.nw == 2) LAUNCH(false, 2, 2);
   else if (!m.fp16 && m.na == 1) LAUNCH(false, 1, 1);
   else if (m.fp16 && m.nw == 1) LAUNCH(true, 2, 1);
