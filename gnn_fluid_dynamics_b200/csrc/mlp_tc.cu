@@ -596,6 +596,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           int slot;
           uint64_t wb = w_acquire(slot);
 #if GNNFD_ABL != 4
+#pragma unroll 1
           for (int k = 0; k < ksteps; ++k) {
             umma_ss(d, ah + 2 * k, wb + 2 * k, idesc1, (kb | k) != 0);
             if (NA == 2) umma_ss(d, al + 2 * k, wb + 2 * k, idesc1, 1);
@@ -605,6 +606,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           if (NW == 2) {
             wb = w_acquire(slot);
 #if GNNFD_ABL != 4
+#pragma unroll 1
             for (int k = 0; k < ksteps; ++k) umma_ss(d, ah + 2 * k, wb + 2 * k, idesc1, 1);
 #endif
             umma_commit(&w_empty[slot]);
@@ -641,18 +643,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       };
       // A = the in-place converted accumulator region: per 16 fp32 columns, 8 columns of hi pairs | 8 of lo pairs.
       // Layer 2 of tile j overwrites Y after layer 3 of tile j - 1 has read it: same thread, in-order tensor pipe.
+      // (the issuer loops stay ROLLED: one thread issues an MMA every ~64+ cycles, so loop overhead is free, while the
+      //  unrolled form was 12 KB of code next to the other roles' hot loops in the shared instruction cache)
+#pragma unroll 1
       for (int j = 0; j < T; ++j) {
         const int xs = j % TC_X_SLOTS;
         const uint32_t xr = tmem_base + xs * 128, yr = tmem_base + TC_Y_COL;
+#pragma unroll 1
         for (int layer = 2; layer <= 3; ++layer) {
           const uint32_t a_reg = layer == 2 ? xr : yr, d = layer == 2 ? yr : xr;
           const uint32_t idesc = layer == 2 ? IDESC_H : idesc3;
+#pragma unroll 1
           for (int kb = 0; kb < 2; ++kb) {
             PROF_WAIT(5, mbar_wait(&hid_ready[xs * 2 + kb], layer == 2 ? 0 : 1));
             tc_fence_after();
             int slot;
             uint64_t wb = w_acquire(slot);
 #if GNNFD_ABL != 4
+#pragma unroll 1
             for (int k = 0; k < 4; ++k) {
               const uint32_t ta = a_reg + (kb * 4 + k) * 16;
               umma_ts(d, ta, wb + 2 * k, idesc, (kb | k) != 0);
@@ -663,6 +671,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             if (NW == 2) {
               wb = w_acquire(slot);
 #if GNNFD_ABL != 4
+#pragma unroll 1
               for (int k = 0; k < 4; ++k) umma_ts(d, a_reg + (kb * 4 + k) * 16, wb + 2 * k, idesc, 1);
 #endif
               umma_commit(&w23_empty[slot]);
