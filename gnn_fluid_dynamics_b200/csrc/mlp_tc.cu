@@ -323,6 +323,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
   // (LEAN = 2: the same for a single Linear - n_layers = 1, contiguous operand rows, optional act'(mul) / residual: the
   //  dgrad launches of the backward)
   const int nl = LEAN == 1 ? 3 : LEAN == 2 ? 1 : p.nl;
+  // MMA issuer loops: ROLLED in the training / all-purpose instantiations (one thread issues an MMA every 64+ cycles, so
+  // loop overhead is free there, while the unrolled form was 20 KB of code in the instruction cache the roles share:
+  // forward + stash 194 -> 188 us), UNROLLED in the inference instantiation, whose single-tile launches are a latency chain
+  // (2k-cell rollout 0.671 ms/step unrolled vs 0.683 rolled) and which is not instruction-fetch bound
+  constexpr int U4 = EPI == 1 ? 4 : 1, U2 = EPI == 1 ? 2 : 1;
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *s_a = smem;                                     // A ring
   float *s_stg = (float *)(s_a + a_stages * TC_STAGE_BYTES);   // output staging, one swizzled 32x16 block per epilogue warp
@@ -596,7 +601,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           int slot;
           uint64_t wb = w_acquire(slot);
 #if GNNFD_ABL != 4
-#pragma unroll 1
+#pragma unroll U4
           for (int k = 0; k < ksteps; ++k) {
             umma_ss(d, ah + 2 * k, wb + 2 * k, idesc1, (kb | k) != 0);
             if (NA == 2) umma_ss(d, al + 2 * k, wb + 2 * k, idesc1, 1);
@@ -606,7 +611,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
           if (NW == 2) {
             wb = w_acquire(slot);
 #if GNNFD_ABL != 4
-#pragma unroll 1
+#pragma unroll U4
             for (int k = 0; k < ksteps; ++k) umma_ss(d, ah + 2 * k, wb + 2 * k, idesc1, 1);
 #endif
             umma_commit(&w_empty[slot]);
@@ -643,24 +648,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
       };
       // A = the in-place converted accumulator region: per 16 fp32 columns, 8 columns of hi pairs | 8 of lo pairs.
       // Layer 2 of tile j overwrites Y after layer 3 of tile j - 1 has read it: same thread, in-order tensor pipe.
-      // (the issuer loops stay ROLLED: one thread issues an MMA every ~64+ cycles, so loop overhead is free, while the
-      //  unrolled form was 12 KB of code next to the other roles' hot loops in the shared instruction cache)
+      // (loop unrolling: see U4 / U2 above)
 #pragma unroll 1
       for (int j = 0; j < T; ++j) {
         const int xs = j % TC_X_SLOTS;
         const uint32_t xr = tmem_base + xs * 128, yr = tmem_base + TC_Y_COL;
-#pragma unroll 1
+#pragma unroll U2
         for (int layer = 2; layer <= 3; ++layer) {
           const uint32_t a_reg = layer == 2 ? xr : yr, d = layer == 2 ? yr : xr;
           const uint32_t idesc = layer == 2 ? IDESC_H : idesc3;
-#pragma unroll 1
+#pragma unroll U2
           for (int kb = 0; kb < 2; ++kb) {
             PROF_WAIT(5, mbar_wait(&hid_ready[xs * 2 + kb], layer == 2 ? 0 : 1));
             tc_fence_after();
             int slot;
             uint64_t wb = w_acquire(slot);
 #if GNNFD_ABL != 4
-#pragma unroll 1
+#pragma unroll U4
             for (int k = 0; k < 4; ++k) {
               const uint32_t ta = a_reg + (kb * 4 + k) * 16;
               umma_ts(d, ta, wb + 2 * k, idesc, (kb | k) != 0);
@@ -671,7 +675,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) mlp_tc_kernel(const __grid_cons
             if (NW == 2) {
               wb = w_acquire(slot);
 #if GNNFD_ABL != 4
-#pragma unroll 1
+#pragma unroll U4
               for (int k = 0; k < 4; ++k) umma_ts(d, a_reg + (kb * 4 + k) * 16, wb + 2 * k, idesc, 1);
 #endif
               umma_commit(&w23_empty[slot]);
