@@ -23,6 +23,21 @@ def mlp3(x, w1, b1, w2, b2, w3, b3, ln_w=None, ln_b=None, act="silu", ln=None, e
     return y
 
 
+def mlp3_dropout(x, w1, b1, w2, b2, w3, b3, keep1, keep2, p, ln_w=None, ln_b=None, eps=1e-5):
+    """Training-mode forward of ``build_mlp`` with ``config.training.dropout_rate = p > 0`` (Model.py:26-35:
+    Linear, SiLU, Dropout, Linear, SiLU, Dropout, Linear [, LayerNorm]) for GIVEN keep masks: ``nn.Dropout`` zeroes the
+    dropped units and scales the kept ones by 1 / (1 - p).  The masks the reference would draw come from torch's generator
+    and cannot be reproduced by another implementation, so the oracle takes them as an input (the CUDA path reports the
+    mask it applied through its stash; tests/test_gpu_dropout.py)."""
+    s = 1.0 / (1.0 - p)
+    h = F.silu(F.linear(x, w1, b1)) * keep1 * s
+    h = F.silu(F.linear(h, w2, b2)) * keep2 * s
+    y = F.linear(h, w3, b3)
+    if ln_w is not None:
+        y = F.layer_norm(y, (y.shape[-1],), ln_w, ln_b, eps)
+    return y
+
+
 def mlp_from_state(sd, prefix: str, x, act="silu"):
     """Run the MLP stored under ``prefix`` of a reference-layout state_dict.
 

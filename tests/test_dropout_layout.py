@@ -104,3 +104,31 @@ def test_unsupported_dropout_layouts_are_rejected():
         weights_of(m)
     drops[1].p = 0.2
     assert weights_of(m).drop_p == pytest.approx(0.2)
+
+
+def test_oracle_dropout_forward_is_pinned_to_nn_dropout():
+    """oracle.mlp3_dropout (masks as an input) against the reference-layout module itself in train() mode: the masks torch
+    drew are read off the Dropout layers with forward hooks (output != 0 wherever the input was non-zero) and plugged into
+    the oracle - same output, same parameter gradients (CPU, fp32)."""
+    from gnn_fluid_dynamics_b200.models.base import build_mlp
+    from oracle.mlp import mlp3_dropout
+    torch.manual_seed(3)
+    p = 0.3
+    m = build_mlp(NS(training=NS(dropout_rate=p)), 16, 128, 128).train()
+    x = torch.randn(200, 16)
+    masks = []
+    hooks = [d.register_forward_hook(lambda mod, inp, out: masks.append((out != 0) | (inp[0] == 0)))
+             for d in m[0] if isinstance(d, torch.nn.Dropout)]
+    y_ref = m(x)
+    for h in hooks:
+        h.remove()
+    assert len(masks) == 2 and 0.6 < masks[0].float().mean() < 0.8
+    lin = [l for l in m[0] if isinstance(l, torch.nn.Linear)]
+    y = mlp3_dropout(x, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight, lin[2].bias,
+                     masks[0].float(), masks[1].float(), p, m[1].weight, m[1].bias)
+    assert torch.allclose(y, y_ref, rtol=1e-5, atol=1e-6)
+    g = torch.randn_like(y)
+    ref_grads = torch.autograd.grad((y_ref * g).sum(), list(m.parameters()))
+    grads = torch.autograd.grad((y * g).sum(), list(m.parameters()))
+    for a, b in zip(grads, ref_grads):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)

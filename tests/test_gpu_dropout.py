@@ -4,7 +4,7 @@ reproduce, so parity is checked the way a mask-based op allows:
 
   * the mask the kernel applied is read back from the stash (a dropped unit's saved pre-activation is GNNFD_DROPPED) and
     must equal the documented counter-based hash (include/gnnfd_b200.h: dropout_p), restated here in numpy;
-  * with THAT mask plugged into a plain fp64 torch restatement of Linear-SiLU-Dropout-Linear-SiLU-Dropout-Linear-LayerNorm
+  * with THAT mask plugged into the oracle (oracle.mlp.mlp3_dropout, pinned to nn.Dropout on the CPU), evaluated in fp64,
     the kernel's output, every parameter gradient and every input gradient agree within the fp32-parity tolerance;
   * keep rate, run-to-run behaviour under torch.manual_seed and eval-mode identity at the model level.
 """
@@ -47,15 +47,13 @@ def expected_dropped(seed, layer, rows, p):
 
 
 def _torch_reference(p, x, m1, m2, drop_p, ln):
-    """fp64 Linear-SiLU-Dropout(mask m1)-Linear-SiLU-Dropout(mask m2)-Linear(-LayerNorm); returns (out, leaf tensors)."""
+    """The oracle's Linear-SiLU-Dropout(mask m1)-Linear-SiLU-Dropout(mask m2)-Linear(-LayerNorm) (oracle.mlp.mlp3_dropout,
+    pinned to nn.Dropout on the CPU in tests/test_dropout_layout.py), evaluated in fp64; returns (out, leaf tensors, input)."""
+    from oracle.mlp import mlp3_dropout
     leaf = {k: v.double().to(dev()).requires_grad_(True) for k, v in p.items() if v is not None}
     xin = x.double().requires_grad_(True)
-    s = 1.0 / (1.0 - drop_p)
-    h1 = torch.nn.functional.silu(xin @ leaf["w1"].T + leaf["b1"]) * m1 * s
-    h2 = torch.nn.functional.silu(h1 @ leaf["w2"].T + leaf["b2"]) * m2 * s
-    out = h2 @ leaf["w3"].T + leaf["b3"]
-    if ln:
-        out = torch.nn.functional.layer_norm(out, (out.shape[1],), leaf["ln_w"], leaf["ln_b"], 1e-5)
+    out = mlp3_dropout(xin, leaf["w1"], leaf["b1"], leaf["w2"], leaf["b2"], leaf["w3"], leaf["b3"], m1, m2, drop_p,
+                       leaf.get("ln_w") if ln else None, leaf.get("ln_b") if ln else None)
     return out, leaf, xin
 
 
